@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: long-running CPU test")
+
+
+@pytest.fixture(scope="session")
+def reference():
+    """The unmodified reference package, or skip when /root/reference is absent."""
+    from oracle.refload import load_reference
+
+    ref = load_reference()
+    if ref is None:
+        pytest.skip("reference not available here (GPU box); goldens cover this")
+    return ref
