@@ -1,0 +1,269 @@
+#!/usr/bin/env python
+"""bench.py -- operator-apply throughput (Gdof/s) and HBM-roofline fraction on B200.
+
+Workload at N=1 = BASELINE.json configs[1]: TensorMesh 512^3 DC-resistivity nodal operator
+y = G^T Me(sigma) G phi, applied matrix-free by ONE fused kernel (K8).  A "step" is one
+apply over one synthetic field (phi ~ N(0,1), sigma log-normal).  "dof" = one output row.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 512]
+
+Under torchrun (N>1) every rank owns a z-slab of the same global mesh (strong scaling),
+halos exchanged over NCCL; timing = barrier + cuda sync, CUDA events, max over ranks.
+`--impl reference` times the reference's own CPU path (scipy csr_matvec on the assembled
+G^T Me G) on a bounded sample of the same workload on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "operator_apply_gdof_per_s"
+UNIT = "Gdof/s"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference's scipy path on a bounded sample
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_arm(n_sample, steps, warmup):
+    """scipy csr_matvec on the assembled A = G^T Me(sigma) G (what the reference/SimPEG applies)."""
+    from oracle import tensor_ops as T  # the checker; allowed here (cpu_baseline leg only)
+
+    g = T.Grid([n_sample] * 3)
+    sigma = np.exp(np.random.default_rng(6).standard_normal(g.nC))
+    phi = np.random.default_rng(5).standard_normal(g.nN)
+    G = T.nodal_gradient(g)
+    Me = T.inner_product(g, "E", sigma)
+    A = (G.T @ Me @ G).tocsr()
+    for _ in range(warmup):
+        A @ phi
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        A @ phi
+    dt = (time.perf_counter() - t0) / steps
+    return g.nN / dt / 1e9, dt, g.nN
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = args.cpu_n
+    val, dt, ndof = cpu_reference_arm(n_sample, max(args.steps, 1), max(args.warmup, 1))
+    sample = (f"TensorMesh {n_sample}^3 (of the 512^3 workload), assembled A=G^T Me(sigma) G as scipy CSR, "
+              f"A @ phi via scipy csr_matvec, 1 thread (scipy SpMV is single-threaded) of {os.cpu_count()} cores")
+    line = {
+        "metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"TensorMesh 512^3 DC nodal G^T Me(sigma) G apply (CPU sample at {n_sample}^3)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import discretize_b200 as dz
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback on the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.n
+    if world == 1:
+        mesh = dz.TensorMesh([n, n, n])
+        gen = torch.Generator(device=dev); gen.manual_seed(5)
+        phi = torch.randn(mesh.nN, dtype=torch.float64, device=dev, generator=gen)
+        gen.manual_seed(6)
+        sigma = torch.exp(torch.randn(mesh.nC, dtype=torch.float64, device=dev, generator=gen))
+        G = mesh.nodal_gradient
+        A = G.T @ mesh.get_edge_inner_product(sigma) @ G  # fuses into the single K8 kernel
+        assert type(A).__name__ == "DCNodalOperator"
+        out = torch.empty(mesh.nN, dtype=torch.float64, device=dev)
+        step = lambda: A.apply_device(phi, out=out)
+        ndof_total = mesh.nN
+        alg_bytes = 8.0 * (2 * mesh.nN + mesh.nC)
+        launches_per_step = 1
+        parallelism = "1 GPU"
+    else:
+        from discretize_b200.slab import SlabDCNodal
+
+        op = SlabDCNodal(n, n, n, rank, world, seed_phi=5, seed_sigma=6)
+        step = op.step
+        ndof_total = (n + 1) ** 3
+        alg_bytes = 8.0 * (2 * (n + 1) ** 3 + n ** 3) / world
+        launches_per_step = op.launches_per_step
+        parallelism = f"z-slabs x{world}, NCCL halo send/recv"
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    sync()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = ndof_total / (ms_step * 1e-3) / 1e9
+
+    # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region
+    e2e = None
+    if world == 1:
+        host_in = torch.empty(mesh.nN, dtype=torch.float64).pin_memory()
+        host_in.copy_(phi)
+        e2e_steps = max(2, min(args.steps, 5))
+        y = A @ host_in  # warm-up (public API: CPU tensor in -> CPU tensor out)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            y = A @ host_in
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        assert y.device.type == "cpu" and y.shape[0] == mesh.nN
+        e2e = {"value": ndof_total / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(8 * mesh.nN),
+               "d2h_bytes_per_step": int(8 * mesh.nN), "ms_per_step": dt * 1e3,
+               "api": "A = G.T @ mesh.get_edge_inner_product(sigma) @ G; y = A @ x_host (pinned)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (ms_step * 1e-3) / 1e9  # per-GPU GB/s of the dominant kernel's algorithmic bytes
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"TensorMesh {n}^3 DC-resistivity nodal operator G^T Me(sigma) G matrix-free apply",
+                   "dofs_per_step": int(ndof_total), "parallelism": parallelism,
+                   "l2": "inputs (phi 1.08 GB + sigma 1.07 GB) exceed the 126 MB L2; no flush needed"},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "k_dc_nodal<RY>",
+                     "algorithmic_bytes_per_launch": alg_bytes},
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu:
+        val, dt, _ = cpu_reference_arm(args.cpu_n, 3, 1)
+        line["cpu_baseline"] = {
+            "value": val, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{args.cpu_n}^3 sample of the workload: scipy csr_matvec on the assembled G^T Me G "
+                      f"(oracle port of the reference build), 1 of {os.cpu_count()} host cores",
+        }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=512, help="cells per axis (512 = BASELINE configs[1])")
+    ap.add_argument("--cpu-n", type=int, default=128, help="cells per axis of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

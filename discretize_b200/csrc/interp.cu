@@ -1,0 +1,256 @@
+// K10/K11: TensorMesh.get_interpolation_matrix on the GPU.
+//
+// reference: base/base_tensor_mesh.py:684-790 -> utils/interpolation_utils.py:44-172 ->
+// _extensions/interputils_cython.pyx:42-182 (_bisect_right, _get_inds_ws, _interpmat3D).
+//
+// Point location is three bisections over the *same float64 1-D arrays the host built*
+// (node / cell-centre coordinates), with the reference's exact comparison `x < a[mid]`,
+// so indices are bit-exact; weights use the reference's expression order.
+#include "tm_common.cuh"
+
+namespace dzb {
+
+constexpr int IT = 128;  // threads (= points) per tile
+
+struct AxisHit {
+  i64 i1, i2;
+  double w1, w2;
+};
+
+// _bisect_right + _get_inds_ws (interputils_cython.pyx:42-67)
+__device__ __forceinline__ AxisHit locate_axis(const double *__restrict__ a, i64 n, double xp) {
+  i64 lo = 0, hi = n;
+  while (lo < hi) {
+    const i64 mid = (lo + hi) / 2;
+    if (xp < a[mid]) hi = mid;
+    else lo = mid + 1;
+  }
+  AxisHit h;
+  h.i2 = max(min(lo, n - 1), (i64)0);
+  h.i1 = max(min(lo - 1, n - 1), (i64)0);
+  if (h.i1 == h.i2) h.w1 = 0.5;
+  else h.w1 = (a[h.i2] - xp) / (a[h.i2] - a[h.i1]);
+  h.w2 = 1 - h.w1;
+  return h;
+}
+
+struct Axes {
+  const double *tx, *ty, *tz;
+  i64 ntx, nty, ntz;
+};
+
+// copies the three 1-D arrays into shared memory when they fit, else uses them in place
+__device__ __forceinline__ Axes stage_axes(const Axes &g, double *smem, i64 smem_doubles) {
+  Axes a = g;
+  if (g.ntx + g.nty + g.ntz <= smem_doubles) {
+    for (i64 t = threadIdx.x; t < g.ntx; t += blockDim.x) smem[t] = g.tx[t];
+    for (i64 t = threadIdx.x; t < g.nty; t += blockDim.x) smem[g.ntx + t] = g.ty[t];
+    for (i64 t = threadIdx.x; t < g.ntz; t += blockDim.x) smem[g.ntx + g.nty + t] = g.tz[t];
+    a.tx = smem;
+    a.ty = smem + g.ntx;
+    a.tz = smem + g.ntx + g.nty;
+    __syncthreads();
+  }
+  return a;
+}
+
+// entry order of _interpmat3D (interputils_cython.pyx:145-180): e = 0..7 ->
+// x: 1,1,2,2,1,1,2,2   y: 1,2,1,2,1,2,1,2   z: 1,1,1,1,2,2,2,2
+__device__ __forceinline__ void entries(const AxisHit &hx, const AxisHit &hy, const AxisHit &hz, i64 nx, i64 ny,
+                                        i64 col_offset, i64 (&col)[8], double (&w)[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const bool x2 = (e >> 1) & 1, y2 = e & 1, z2 = (e >> 2) & 1;
+    const i64 ix = x2 ? hx.i2 : hx.i1, iy = y2 ? hy.i2 : hy.i1, iz = z2 ? hz.i2 : hz.i1;
+    col[e] = col_offset + ix + nx * (iy + ny * iz);
+    w[e] = ((x2 ? hx.w2 : hx.w1) * (y2 ? hy.w2 : hy.w1)) * (z2 ? hz.w2 : hz.w1);
+  }
+}
+
+// K10: locate + weights.  Persistent tiles of IT points; outputs are transposed through
+// shared memory so that the (npts x 8) tables are written with fully coalesced stores.
+__global__ void __launch_bounds__(IT) k_interp_locate(Axes g, const double *__restrict__ pts, i64 npts, i64 col_offset,
+                                                      i64 *__restrict__ cols, double *__restrict__ w) {
+  extern __shared__ double smem[];
+  double *sw = smem;                          // IT*9 weights (padded rows)
+  i64 *sc = (i64 *)(smem + IT * 9);           // IT*9 columns
+  double *sax = smem + 2 * IT * 9;
+  const Axes a = stage_axes(g, sax, 4096);
+  const i64 ntiles = (npts + IT - 1) / IT;
+  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const i64 p = tile * IT + threadIdx.x;
+    if (p < npts) {
+      const AxisHit hx = locate_axis(a.tx, a.ntx, __ldg(pts + 3 * p));
+      const AxisHit hy = locate_axis(a.ty, a.nty, __ldg(pts + 3 * p + 1));
+      const AxisHit hz = locate_axis(a.tz, a.ntz, __ldg(pts + 3 * p + 2));
+      i64 c8[8];
+      double w8[8];
+      entries(hx, hy, hz, a.ntx, a.nty, col_offset, c8, w8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {  // row pitch 9: at most 2-way bank conflicts
+        sw[threadIdx.x * 9 + e] = w8[e];
+        sc[threadIdx.x * 9 + e] = c8[e];
+      }
+    }
+    __syncthreads();
+    const i64 base = tile * IT * 8;
+    const i64 lim = min((i64)IT * 8, npts * 8 - base);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const i64 t = threadIdx.x + r * IT;
+      if (t < lim) {
+        const i64 q = (t >> 3) * 9 + (t & 7);
+        w[base + t] = sw[q];
+        cols[base + t] = sc[q];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// K11: y[p] = scale[p] * sum_e w[p,e] v[cols[p,e]].  Eight lanes per point: the tables are
+// read fully coalesced, the gathers run 32-wide, partial sums combine with shuffles.
+__global__ void __launch_bounds__(256) k_interp_apply(const i64 *__restrict__ cols, const double *__restrict__ w,
+                                                      const double *__restrict__ scale, i64 npts,
+                                                      const double *__restrict__ v, double *__restrict__ y) {
+  const i64 nent = npts * 8;
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  const i64 nent_pad = (nent + 31) / 32 * 32;
+  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < nent_pad; t += stride) {
+    double part = 0.0;
+    if (t < nent) part = __ldg(w + t) * __ldg(v + __ldg(cols + t));
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    part += __shfl_xor_sync(0xffffffffu, part, 4);
+    if ((t & 7) == 0 && t < nent) {
+      const i64 p = t >> 3;
+      y[p] = scale ? part * __ldg(scale + p) : part;
+    }
+  }
+}
+
+// y[cols[p,e]] += scale[p] w[p,e] x[p]
+__global__ void __launch_bounds__(256) k_interp_apply_t(const i64 *__restrict__ cols, const double *__restrict__ w,
+                                                        const double *__restrict__ scale, i64 npts,
+                                                        const double *__restrict__ x, double *__restrict__ y) {
+  const i64 nent = npts * 8;
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < nent; t += stride) {
+    const i64 p = t >> 3;
+    double xv = __ldg(x + p);
+    if (scale) xv *= __ldg(scale + p);
+    atomicAdd(y + __ldg(cols + t), __ldg(w + t) * xv);
+  }
+}
+
+// fused locate + apply: nothing but the points is read and y written (plus the gathers)
+__global__ void __launch_bounds__(256) k_interp_fused(Axes g, const double *__restrict__ pts, i64 npts, i64 col_offset,
+                                                      const double *__restrict__ scale, const double *__restrict__ v,
+                                                      double *__restrict__ y) {
+  extern __shared__ double smem[];
+  const Axes a = stage_axes(g, smem, 4096);
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += stride) {
+    const AxisHit hx = locate_axis(a.tx, a.ntx, __ldg(pts + 3 * p));
+    const AxisHit hy = locate_axis(a.ty, a.nty, __ldg(pts + 3 * p + 1));
+    const AxisHit hz = locate_axis(a.tz, a.ntz, __ldg(pts + 3 * p + 2));
+    i64 c8[8];
+    double w8[8];
+    entries(hx, hy, hz, a.ntx, a.nty, col_offset, c8, w8);
+    double acc = 0.0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc += w8[e] * __ldg(v + c8[e]);
+    y[p] = scale ? acc * __ldg(scale + p) : acc;
+  }
+}
+
+struct Box {
+  double lo[3], hi[3], tol[3];
+};
+
+// is_inside (base_tensor_mesh.py:638-682)
+__global__ void k_points_inside(const double *__restrict__ pts, i64 npts, Box b, uint8_t *__restrict__ inside) {
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += stride) {
+    bool in = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double x = __ldg(pts + 3 * p + a);
+      in = in && (x >= b.lo[a] - b.tol[a]) && (x <= b.hi[a] + b.tol[a]);
+    }
+    inside[p] = in ? 1 : 0;
+  }
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static unsigned blocks_for(i64 work_items, int per_block, int waves) {
+  const i64 need = (work_items + per_block - 1) / per_block;
+  const i64 cap = (i64)sm_count() * waves;
+  return (unsigned)max((i64)1, min(need, cap));
+}
+
+}  // namespace dzb
+
+using namespace dzb;
+
+extern "C" int dzb_interp_locate(const double *tx, int64_t ntx, const double *ty, int64_t nty, const double *tz,
+                                 int64_t ntz, const double *pts, int64_t npts, int64_t col_offset, int64_t *cols,
+                                 double *w, void *stream) {
+  if (npts == 0) return 0;
+  Axes g{tx, ty, tz, ntx, nty, ntz};
+  const size_t smem = (2 * IT * 9 + 4096) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_interp_locate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  k_interp_locate<<<blocks_for(npts, IT, 8), IT, smem, (cudaStream_t)stream>>>(g, pts, npts, col_offset, (i64 *)cols, w);
+  return check_launch("dzb_interp_locate");
+}
+
+extern "C" int dzb_interp_apply(const int64_t *cols, const double *w, const double *row_scale, int64_t npts,
+                                const double *v, double *y, void *stream) {
+  if (npts == 0) return 0;
+  k_interp_apply<<<blocks_for(npts * 8, 256, 16), 256, 0, (cudaStream_t)stream>>>((const i64 *)cols, w, row_scale, npts, v, y);
+  return check_launch("dzb_interp_apply");
+}
+
+extern "C" int dzb_interp_apply_t(const int64_t *cols, const double *w, const double *row_scale, int64_t npts,
+                                  const double *x, double *y, void *stream) {
+  if (npts == 0) return 0;
+  k_interp_apply_t<<<blocks_for(npts * 8, 256, 16), 256, 0, (cudaStream_t)stream>>>((const i64 *)cols, w, row_scale, npts, x, y);
+  return check_launch("dzb_interp_apply_t");
+}
+
+extern "C" int dzb_interp_fused(const double *tx, int64_t ntx, const double *ty, int64_t nty, const double *tz,
+                                int64_t ntz, const double *pts, int64_t npts, int64_t col_offset,
+                                const double *row_scale, const double *v, double *y, void *stream) {
+  if (npts == 0) return 0;
+  Axes g{tx, ty, tz, ntx, nty, ntz};
+  const size_t smem = 4096 * sizeof(double);
+  k_interp_fused<<<blocks_for(npts, 256, 8), 256, smem, (cudaStream_t)stream>>>(g, pts, npts, col_offset, row_scale, v, y);
+  return check_launch("dzb_interp_fused");
+}
+
+extern "C" int dzb_points_inside(const double *pts, int64_t npts, const double *lo_host, const double *hi_host,
+                                 const double *tol_host, uint8_t *inside, void *stream) {
+  if (npts == 0) return 0;
+  Box b;
+  for (int a = 0; a < 3; ++a) {
+    b.lo[a] = lo_host[a];
+    b.hi[a] = hi_host[a];
+    b.tol[a] = tol_host[a];
+  }
+  k_points_inside<<<blocks_for(npts, 256, 16), 256, 0, (cudaStream_t)stream>>>(pts, npts, b, inside);
+  return check_launch("dzb_points_inside");
+}

@@ -1,0 +1,73 @@
+// Elementary TensorMesh operators: y = A x, y = A^T x and CSR materialisation,
+// all driven by the row generators in tm_rows.cuh (one thread per output row,
+// 3-D thread blocks so that the y/z neighbours of a row are served from L1).
+#include "tm_rows.cuh"
+#include "tm_rowkernels.cuh"
+
+namespace dzb {
+
+template <class R> static void shape_of(const TM &m, i64 *nr, i64 *nc) {
+  *nr = R::nrows(m);
+  *nc = R::ncols(m);
+}
+
+#define DZB_FOR_OP(OPID, BODY)                                                     \
+  case OPID:                                                                       \
+    if (transpose) { typedef Rows<OPID, true> R; BODY; }                           \
+    else { typedef Rows<OPID, false> R; BODY; }                                    \
+    break;
+
+#define DZB_DISPATCH(BODY)                                                         \
+  switch (op) {                                                                    \
+    DZB_FOR_OP(DZB_OP_DIV, BODY) DZB_FOR_OP(DZB_OP_CURL, BODY) DZB_FOR_OP(DZB_OP_GRAD, BODY)            \
+    DZB_FOR_OP(DZB_OP_AVE_F2CC, BODY) DZB_FOR_OP(DZB_OP_AVE_F2CCV, BODY) DZB_FOR_OP(DZB_OP_AVE_FX2CC, BODY) \
+    DZB_FOR_OP(DZB_OP_AVE_FY2CC, BODY) DZB_FOR_OP(DZB_OP_AVE_FZ2CC, BODY) DZB_FOR_OP(DZB_OP_AVE_E2CC, BODY) \
+    DZB_FOR_OP(DZB_OP_AVE_E2CCV, BODY) DZB_FOR_OP(DZB_OP_AVE_EX2CC, BODY) DZB_FOR_OP(DZB_OP_AVE_EY2CC, BODY) \
+    DZB_FOR_OP(DZB_OP_AVE_EZ2CC, BODY) DZB_FOR_OP(DZB_OP_AVE_N2CC, BODY)                                 \
+    default:                                                                       \
+      set_error("unknown operator id");                                            \
+      return -1;                                                                   \
+  }
+
+}  // namespace dzb
+
+using namespace dzb;
+
+extern "C" int dzb_tm_shape(const DzbTensorMesh *mm, int op, int64_t *nrows, int64_t *ncols) {
+  if (!valid_mesh(mm)) return -1;
+  TM m(*mm);
+  const int transpose = 0;
+  i64 nr = 0, nc = 0;
+  DZB_DISPATCH(shape_of<R>(m, &nr, &nc));
+  *nrows = nr;
+  *ncols = nc;
+  return 0;
+}
+
+extern "C" int dzb_tm_apply(const DzbTensorMesh *mm, int op, int transpose, const double *x, double *y, void *stream) {
+  if (!valid_mesh(mm)) return -1;
+  TM m(*mm);
+  Args a{x, y, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t s = (cudaStream_t)stream;
+  DZB_DISPATCH(launch_all(R(), MODE_APPLY, m, a, s));
+  return check_launch("dzb_tm_apply");
+}
+
+extern "C" int dzb_tm_csr_count(const DzbTensorMesh *mm, int op, int transpose, int64_t *row_nnz, void *stream) {
+  if (!valid_mesh(mm)) return -1;
+  TM m(*mm);
+  Args a{nullptr, nullptr, (i64 *)row_nnz, nullptr, nullptr, nullptr};
+  cudaStream_t s = (cudaStream_t)stream;
+  DZB_DISPATCH(launch_all(R(), MODE_COUNT, m, a, s));
+  return check_launch("dzb_tm_csr_count");
+}
+
+extern "C" int dzb_tm_csr_fill(const DzbTensorMesh *mm, int op, int transpose, const int64_t *indptr, int64_t *indices,
+                               double *data, void *stream) {
+  if (!valid_mesh(mm)) return -1;
+  TM m(*mm);
+  Args a{nullptr, nullptr, nullptr, (const i64 *)indptr, (i64 *)indices, data};
+  cudaStream_t s = (cudaStream_t)stream;
+  DZB_DISPATCH(launch_all(R(), MODE_FILL, m, a, s));
+  return check_launch("dzb_tm_csr_fill");
+}

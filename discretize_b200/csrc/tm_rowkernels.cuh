@@ -1,0 +1,98 @@
+// Generic kernels over a row generator `gen` (see tm_rows.cuh): one thread per output
+// row, 3-D thread blocks (32 x 4 x 4) so that y/z neighbours of a row hit L1.
+//   k_apply : y[row] = sum_j val_j * x[col_j]
+//   k_count : row_nnz[row] = number of stored entries
+//   k_fill  : sorted column indices and values at indptr[row]
+#pragma once
+#include "tm_common.cuh"
+
+namespace dzb {
+
+constexpr int BX = 32, BY = 4, BZ = 4;
+
+template <int LOC> static dim3 grid_for(const TM &m) {
+  return dim3((unsigned)((m.sx<LOC>() + BX - 1) / BX), (unsigned)((m.sy<LOC>() + BY - 1) / BY),
+              (unsigned)((m.sz<LOC>() + BZ - 1) / BZ));
+}
+
+template <class R, int COMP>
+__global__ void __launch_bounds__(BX *BY *BZ) k_apply(R gen, TM m, const double *__restrict__ x, double *__restrict__ y) {
+  constexpr int LOC = R::template loc<COMP>();
+  const i64 i = (i64)blockIdx.x * BX + threadIdx.x;
+  const i64 j = (i64)blockIdx.y * BY + threadIdx.y;
+  const i64 k = (i64)blockIdx.z * BZ + threadIdx.z;
+  if (i >= m.sx<LOC>() || j >= m.sy<LOC>() || k >= m.sz<LOC>()) return;
+  double acc = 0.0;
+  gen.template row<COMP>(m, i, j, k, [&](i64 c, double v) { acc += v * __ldg(x + c); });
+  y[R::template row_off<COMP>(m) + m.lidx<LOC>(i, j, k)] = acc;
+}
+
+template <class R, int COMP>
+__global__ void __launch_bounds__(BX *BY *BZ) k_count(R gen, TM m, i64 *__restrict__ row_nnz) {
+  constexpr int LOC = R::template loc<COMP>();
+  const i64 i = (i64)blockIdx.x * BX + threadIdx.x;
+  const i64 j = (i64)blockIdx.y * BY + threadIdx.y;
+  const i64 k = (i64)blockIdx.z * BZ + threadIdx.z;
+  if (i >= m.sx<LOC>() || j >= m.sy<LOC>() || k >= m.sz<LOC>()) return;
+  int n = 0;
+  gen.template row<COMP>(m, i, j, k, [&](i64, double) { ++n; });
+  row_nnz[R::template row_off<COMP>(m) + m.lidx<LOC>(i, j, k)] = n;
+}
+
+template <class R, int COMP>
+__global__ void __launch_bounds__(BX *BY *BZ)
+    k_fill(R gen, TM m, const i64 *__restrict__ indptr, i64 *__restrict__ indices, double *__restrict__ data) {
+  constexpr int LOC = R::template loc<COMP>();
+  const i64 i = (i64)blockIdx.x * BX + threadIdx.x;
+  const i64 j = (i64)blockIdx.y * BY + threadIdx.y;
+  const i64 k = (i64)blockIdx.z * BZ + threadIdx.z;
+  if (i >= m.sx<LOC>() || j >= m.sy<LOC>() || k >= m.sz<LOC>()) return;
+  i64 cols[R::MAXNNZ];
+  double vals[R::MAXNNZ];
+  int n = 0;
+  gen.template row<COMP>(m, i, j, k, [&](i64 c, double v) {
+    // insertion into the sorted prefix (rows have <= 12 entries)
+    int p = n++;
+    while (p > 0 && cols[p - 1] > c) {
+      cols[p] = cols[p - 1];
+      vals[p] = vals[p - 1];
+      --p;
+    }
+    cols[p] = c;
+    vals[p] = v;
+  });
+  const i64 base = indptr[R::template row_off<COMP>(m) + m.lidx<LOC>(i, j, k)];
+  for (int q = 0; q < n; ++q) {
+    indices[base + q] = cols[q];
+    data[base + q] = vals[q];
+  }
+}
+
+enum Mode { MODE_APPLY, MODE_COUNT, MODE_FILL };
+
+struct Args {
+  const double *x;
+  double *y;
+  i64 *row_nnz;
+  const i64 *indptr;
+  i64 *indices;
+  double *data;
+};
+
+template <class R, int COMP> static void launch_comp(const R &gen, int mode, const TM &m, const Args &a, cudaStream_t s) {
+  constexpr int LOC = R::template loc<COMP>();
+  if (m.count<LOC>() == 0) return;
+  dim3 g = grid_for<LOC>(m), b(BX, BY, BZ);
+  if (mode == MODE_APPLY) k_apply<R, COMP><<<g, b, 0, s>>>(gen, m, a.x, a.y);
+  else if (mode == MODE_COUNT) k_count<R, COMP><<<g, b, 0, s>>>(gen, m, a.row_nnz);
+  else k_fill<R, COMP><<<g, b, 0, s>>>(gen, m, a.indptr, a.indices, a.data);
+}
+
+template <class R> static void launch_all(const R &gen, int mode, const TM &m, const Args &a, cudaStream_t s) {
+  launch_comp<R, 0>(gen, mode, m, a, s);
+  if (R::NCOMP > 1) launch_comp<R, (R::NCOMP > 1 ? 1 : 0)>(gen, mode, m, a, s);
+  if (R::NCOMP > 2) launch_comp<R, (R::NCOMP > 2 ? 2 : 0)>(gen, mode, m, a, s);
+}
+
+
+}  // namespace dzb

@@ -1,0 +1,142 @@
+"""get_interpolation_matrix as a CUDA operator (K10 locate+weights, K11 apply).
+
+reference: base/base_tensor_mesh.py:684-790 -> utils/interpolation_utils.py:44-172 ->
+_extensions/interputils_cython.pyx:42-182.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from ._lib import check, load
+from .operators import Operator, cuda_device, ptr, stream_ptr, to_device
+
+
+def _location_layout(mesh, location_type):
+    """(tensor key, column offset, number of columns) of a location type (:729-769)."""
+    lt = mesh._parse_location_type(location_type)
+    nC = mesh.n_cells
+    if lt in ("cell_centers", "nodes"):
+        return lt, 0, (nC if lt == "cell_centers" else mesh.n_nodes)
+    if lt in ("faces_x", "faces_y", "faces_z"):
+        ind = "xyz".index(lt[-1])
+        return lt, int(sum(mesh.n_faces_per_direction[:ind])), mesh.n_faces
+    if lt in ("edges_x", "edges_y", "edges_z"):
+        ind = "xyz".index(lt[-1])
+        return lt, int(sum(mesh.n_edges_per_direction[:ind])), mesh.n_edges
+    if lt in ("cell_centers_x", "cell_centers_y", "cell_centers_z"):
+        return "cell_centers", "xyz".index(lt[-1]) * nC, 3 * nC
+    raise NotImplementedError(
+        "get_interpolation_matrix: location_type==" + lt + " and mesh.dim==" + str(mesh.dim)
+    )
+
+
+class InterpolationOperator(Operator):
+    """Q (npts x ncols), <= 8 entries per row, stored as (npts, 8) column/weight tables on the GPU."""
+
+    def __init__(self, mesh, pts_dev, location_type, zeros_outside, row_scale, store=True):
+        key, off, ncols = _location_layout(mesh, location_type)
+        npts = pts_dev.shape[0]
+        super().__init__((npts, ncols))
+        self.mesh, self.col_offset, self.row_scale = mesh, off, row_scale
+        self.pts = pts_dev
+        self.axes = [to_device(t) for t in mesh.get_tensor(key)]
+        self.cols = self.w = None
+        if store:
+            self._locate()
+
+    def _axes_args(self):
+        a = self.axes
+        return (ptr(a[0]), a[0].numel(), ptr(a[1]), a[1].numel(), ptr(a[2]), a[2].numel())
+
+    def _locate(self):
+        npts = self.shape[0]
+        dev = cuda_device()
+        self.cols = torch.empty((npts, 8), dtype=torch.int64, device=dev)
+        self.w = torch.empty((npts, 8), dtype=torch.float64, device=dev)
+        check(load().dzb_interp_locate(*self._axes_args(), ptr(self.pts), npts, self.col_offset, ptr(self.cols),
+                                       ptr(self.w), stream_ptr()), "dzb_interp_locate")
+
+    def _dev_apply(self, x, out):
+        npts = self.shape[0]
+        if self.cols is None:  # fused locate + apply, nothing stored
+            check(load().dzb_interp_fused(*self._axes_args(), ptr(self.pts), npts, self.col_offset,
+                                          ptr(self.row_scale), ptr(x), ptr(out), stream_ptr()), "dzb_interp_fused")
+        else:
+            check(load().dzb_interp_apply(ptr(self.cols), ptr(self.w), ptr(self.row_scale), npts, ptr(x), ptr(out),
+                                          stream_ptr()), "dzb_interp_apply")
+
+    def _dev_apply_t(self, x, out):
+        if self.cols is None:
+            self._locate()
+        out.zero_()
+        check(load().dzb_interp_apply_t(ptr(self.cols), ptr(self.w), ptr(self.row_scale), self.shape[0], ptr(x),
+                                        ptr(out), stream_ptr()), "dzb_interp_apply_t")
+
+    def _tocsr(self):
+        """COO -> CSR exactly like the reference: duplicate columns summed, sorted, explicit zeros kept;
+        zeros_outside rows become full rows of explicit zeros (base_tensor_mesh.py:771-772)."""
+        if self.cols is None:
+            self._locate()
+        npts, ncols = self.shape
+        cols = self.cols.cpu().numpy().reshape(-1)
+        w = self.w.cpu().numpy().reshape(-1)
+        rows = np.repeat(np.arange(npts), 8)
+        Q = sp.csr_matrix((w, (rows, cols)), shape=(npts, ncols))
+        Q.sum_duplicates()
+        Q.sort_indices()
+        if self.row_scale is not None:
+            outside = self.row_scale.cpu().numpy() == 0.0
+            if outside.any():
+                if outside.sum() * ncols > 5e8:
+                    raise MemoryError("zeros_outside rows are dense in the reference's matrix; too large to materialise")
+                counts = np.diff(Q.indptr).astype(np.int64)
+                counts[outside] = ncols
+                indptr = np.r_[0, np.cumsum(counts)]
+                indices = np.empty(indptr[-1], dtype=np.int64)
+                data = np.zeros(indptr[-1])
+                for r in range(npts):
+                    lo, hi = indptr[r], indptr[r + 1]
+                    if outside[r]:
+                        indices[lo:hi] = np.arange(ncols)
+                    else:
+                        indices[lo:hi] = Q.indices[Q.indptr[r]:Q.indptr[r + 1]]
+                        data[lo:hi] = Q.data[Q.indptr[r]:Q.indptr[r + 1]]
+                Q = sp.csr_matrix((data, indices, indptr), shape=(npts, ncols))
+        return Q
+
+
+def make_interpolation_operator(mesh, loc, location_type="cell_centers", zeros_outside=False, store=True):
+    from .tensor_mesh import as_array_n_by_dim
+
+    if isinstance(loc, torch.Tensor):
+        pts = to_device(loc)
+        if pts.ndim == 1:
+            pts = pts.reshape(1, -1)
+        if pts.shape[1] != mesh.dim:
+            raise ValueError("pts must be a column vector of shape (nPts, {0:d})".format(mesh.dim))
+    else:
+        pts = to_device(as_array_n_by_dim(loc, mesh.dim).astype(np.float64))
+    npts = pts.shape[0]
+    # is_inside is always evaluated against the nodes tensor (base_tensor_mesh.py:638, 720-723)
+    nodes = mesh.get_tensor("nodes")
+    lo = (C.c_double * 3)(*[float(t.min()) for t in nodes])
+    hi = (C.c_double * 3)(*[float(t.max()) for t in nodes])
+    tol = (C.c_double * 3)(*[float(np.diff(t).min() * 1.0e-10) for t in nodes])
+    inside = torch.empty(npts, dtype=torch.uint8, device=pts.device)
+    check(load().dzb_points_inside(ptr(pts), npts, lo, hi, tol, ptr(inside), stream_ptr()), "dzb_points_inside")
+    all_inside = bool(inside.all().item()) if npts else True
+    row_scale = None
+    if not zeros_outside:
+        if not all_inside:
+            raise ValueError("Points outside of mesh")
+    elif not all_inside:
+        # outside points are moved to the mesh centre and their rows zeroed (:723-725, 771-772)
+        center = torch.tensor([float(v.mean()) for v in mesh.get_tensor("CC")], dtype=torch.float64, device=pts.device)
+        mask = inside.to(torch.bool)
+        pts = torch.where(mask[:, None], pts, center[None, :]).contiguous()
+        row_scale = mask.to(torch.float64)
+    return InterpolationOperator(mesh, pts, location_type, zeros_outside, row_scale, store=store)

@@ -1,0 +1,425 @@
+"""LinearOperator-compatible operators backed by CUDA kernels.
+
+The reference returns ``scipy.sparse`` matrices from its mesh properties and applies
+them with ``A @ x`` (scipy ``csr_matvec``).  Here every such property returns an
+:class:`Operator`: ``isinstance(op, scipy.sparse.linalg.LinearOperator)`` holds,
+``op @ x`` / ``op.T @ y`` / ``op.dot`` / ``op * x`` / ``matvec`` / ``rmatvec`` /
+``matmat`` work on numpy arrays (one H2D + one D2H copy) or on torch CUDA float64
+tensors (zero copy, the result stays on the device), ``A @ B``, ``A + B``,
+``alpha * A`` and ``A.T`` compose lazily -- recognising ``G.T @ Me @ G`` and
+``C.T @ Mf @ C + Me`` and replacing them with single fused kernels -- and
+``op.tocsr()`` materialises the same sparsity and values as the reference.
+
+No CPU fallback exists: applying an operator without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+from scipy.sparse.linalg import LinearOperator
+
+from . import _lib
+from ._lib import DzbError
+
+try:  # torch is plumbing: device memory, streams, torch.distributed
+    import torch
+except Exception as exc:  # pragma: no cover
+    raise ImportError("discretize_b200 needs PyTorch for device memory and streams") from exc
+
+
+# ----------------------------------------------------------------------------------------
+# device plumbing
+# ----------------------------------------------------------------------------------------
+def cuda_device():
+    if not torch.cuda.is_available():
+        raise DzbError(
+            "no CUDA device available: discretize_b200 operators only run on the GPU "
+            "(there is deliberately no CPU fallback)"
+        )
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+def to_device(x, dtype=None):
+    """numpy / torch -> contiguous CUDA tensor (float64 unless dtype is given)."""
+    dtype = torch.float64 if dtype is None else dtype
+    dev = cuda_device()
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=dtype).contiguous()
+    a = np.ascontiguousarray(x, dtype={torch.float64: np.float64, torch.int64: np.int64,
+                                       torch.int32: np.int32, torch.uint8: np.uint8}[dtype])
+    return torch.from_numpy(a).to(dev)
+
+
+def _is_scalar(x):
+    return np.isscalar(x) or (isinstance(x, (np.ndarray, torch.Tensor)) and x.ndim == 0)
+
+
+# ----------------------------------------------------------------------------------------
+# base class
+# ----------------------------------------------------------------------------------------
+class Operator(LinearOperator):
+    """A float64 linear operator applied by CUDA kernels.
+
+    Subclasses implement ``_dev_apply(x, out)`` and ``_dev_apply_t(x, out)`` on
+    contiguous 1-D CUDA float64 tensors and (where the reference has a matrix)
+    ``_tocsr()``.
+    """
+
+    def __init__(self, shape):
+        LinearOperator.__init__(self, np.dtype(np.float64), tuple(int(s) for s in shape))
+
+    # -- kernels -------------------------------------------------------------------------
+    def _dev_apply(self, x, out):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def _dev_apply_t(self, x, out):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def _tocsr(self):
+        raise NotImplementedError(f"{type(self).__name__} has no matrix form")
+
+    # scipy's abstract hooks (solvers call matvec/rmatvec, which we override below)
+    def _matvec(self, x):
+        return self._apply_any(x, False)
+
+    def _rmatvec(self, x):
+        return self._apply_any(x, True)
+
+    def _matmat(self, X):
+        return self._apply_any(X, False)
+
+    def _rmatmat(self, X):
+        return self._apply_any(X, True)
+
+    # -- dispatch on the input type ---------------------------------------------------------
+    def apply_device(self, x, transpose=False, out=None):
+        """y = A x (or A^T x) for a 1-D CUDA float64 tensor; result stays on the device."""
+        n_out, n_in = (self.shape[1], self.shape[0]) if transpose else self.shape
+        if x.numel() != n_in:
+            raise ValueError(f"dimension mismatch: operator {self.shape}, transpose={transpose}, vector {tuple(x.shape)}")
+        if out is None:
+            out = torch.empty(n_out, dtype=torch.float64, device=x.device)
+        (self._dev_apply_t if transpose else self._dev_apply)(x, out)
+        return out
+
+    def _apply_any(self, x, transpose):
+        n_in = self.shape[0] if transpose else self.shape[1]
+        is_torch = isinstance(x, torch.Tensor)
+        if not is_torch:
+            x = np.asarray(x)
+            if np.iscomplexobj(x):
+                return self._apply_any(x.real, transpose) + 1j * self._apply_any(x.imag, transpose)
+        if x.ndim == 1 or (x.ndim == 2 and x.shape[1] == 1 and x.shape[0] == n_in):
+            if x.shape[0] != n_in:
+                raise ValueError(f"dimension mismatch: operator {self.shape}, input {tuple(x.shape)}")
+            if is_torch and x.device.type == "cpu":
+                # host tensor in -> host tensor out (pinned in -> pinned out, async copies)
+                xd = x.to(device=cuda_device(), dtype=torch.float64, non_blocking=True).reshape(-1)
+                yd = self.apply_device(xd, transpose)
+                y = torch.empty(yd.shape, dtype=torch.float64, pin_memory=x.is_pinned())
+                y.copy_(yd, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return y.reshape(-1, 1) if x.ndim == 2 else y
+            xd = to_device(x).reshape(-1)
+            yd = self.apply_device(xd, transpose)
+            y = yd if is_torch else yd.cpu().numpy()
+            return y.reshape(-1, 1) if x.ndim == 2 else y
+        if x.ndim == 2 and x.shape[0] == n_in:
+            xd = to_device(x)
+            cols = [self.apply_device(xd[:, c].contiguous(), transpose) for c in range(xd.shape[1])]
+            yd = torch.stack(cols, dim=1) if cols else torch.empty(
+                (self.shape[1] if transpose else self.shape[0], 0), dtype=torch.float64, device=xd.device)
+            return yd if is_torch else yd.cpu().numpy()
+        raise ValueError(f"dimension mismatch: operator {self.shape}, input {tuple(x.shape)}")
+
+    # -- public LinearOperator surface ----------------------------------------------------------
+    def matvec(self, x):
+        return self._apply_any(x, False)
+
+    def rmatvec(self, x):
+        return self._apply_any(x, True)
+
+    def matmat(self, X):
+        return self._apply_any(X, False)
+
+    def rmatmat(self, X):
+        return self._apply_any(X, True)
+
+    def dot(self, x):
+        if isinstance(x, Operator):
+            return ProductOperator.make([self, x])
+        if sp.issparse(x):
+            return ProductOperator.make([self, as_operator(x)])
+        if _is_scalar(x):
+            return ScaledOperator(self, float(x))
+        return self._apply_any(x, False)
+
+    __mul__ = dot
+
+    def __matmul__(self, x):
+        if _is_scalar(x):
+            raise ValueError("Scalar operands are not allowed, use '*' instead")
+        return self.dot(x)
+
+    def __call__(self, x):
+        return self.dot(x)
+
+    def __rmul__(self, x):
+        if _is_scalar(x):
+            return ScaledOperator(self, float(x))
+        return self.__rmatmul__(x)
+
+    def __rmatmul__(self, x):
+        if _is_scalar(x):
+            raise ValueError("Scalar operands are not allowed, use '*' instead")
+        if sp.issparse(x):
+            return ProductOperator.make([as_operator(x), self])
+        # x @ A == (A^T x^T)^T
+        if isinstance(x, torch.Tensor):
+            return self._apply_any(x if x.ndim == 1 else x.T, True) if x.ndim == 1 else self._apply_any(x.T, True).T
+        x = np.asarray(x)
+        return self._apply_any(x, True) if x.ndim == 1 else self._apply_any(x.T, True).T
+
+    def __add__(self, other):
+        if sp.issparse(other):
+            other = as_operator(other)
+        if isinstance(other, Operator):
+            return SumOperator.make([self, other])
+        return NotImplemented
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        if sp.issparse(other):
+            other = as_operator(other)
+        if isinstance(other, Operator):
+            return SumOperator.make([self, ScaledOperator(other, -1.0)])
+        return NotImplemented
+
+    def __neg__(self):
+        return ScaledOperator(self, -1.0)
+
+    def __truediv__(self, other):
+        if not _is_scalar(other):
+            raise ValueError("Can only divide a linear operator by a scalar.")
+        return ScaledOperator(self, 1.0 / float(other))
+
+    def _transpose(self):
+        return TransposedOperator(self)
+
+    _adjoint = _transpose
+
+    def transpose(self):
+        return self._transpose()
+
+    def adjoint(self):
+        return self._transpose()
+
+    @property
+    def T(self):
+        return self._transpose()
+
+    @property
+    def H(self):
+        return self._transpose()
+
+    # -- matrix forms -----------------------------------------------------------------------------
+    def tocsr(self):
+        """The reference's matrix: same sparsity (canonical CSR: sorted, duplicates summed) and values."""
+        return self._tocsr()
+
+    def tocsc(self):
+        return self.tocsr().tocsc()
+
+    def tocoo(self):
+        return self.tocsr().tocoo()
+
+    def toarray(self):
+        return self.tocsr().toarray()
+
+    todense = toarray
+
+    def diagonal(self):
+        return self.tocsr().diagonal()
+
+    @property
+    def nnz(self):
+        return self.tocsr().nnz
+
+    def __repr__(self):
+        return f"<{self.shape[0]}x{self.shape[1]} {type(self).__name__} (CUDA, float64)>"
+
+
+def csr_from_device(indptr, indices, data, shape):
+    """Device CSR arrays -> scipy.sparse.csr_matrix (int32 indices when they fit, like scipy)."""
+    indptr = indptr.cpu().numpy()
+    indices = indices.cpu().numpy()
+    data = data.cpu().numpy()
+    if max(shape[1], int(indptr[-1]) if indptr.size else 0) < 2**31 - 1:
+        indptr = indptr.astype(np.int32)
+        indices = indices.astype(np.int32)
+    m = sp.csr_matrix((data, indices, indptr), shape=shape)
+    m.has_sorted_indices = True
+    return m
+
+
+# ----------------------------------------------------------------------------------------
+# algebra
+# ----------------------------------------------------------------------------------------
+class TransposedOperator(Operator):
+    def __init__(self, base):
+        super().__init__((base.shape[1], base.shape[0]))
+        self.base = base
+
+    def _dev_apply(self, x, out):
+        self.base._dev_apply_t(x, out)
+
+    def _dev_apply_t(self, x, out):
+        self.base._dev_apply(x, out)
+
+    def _transpose(self):
+        return self.base
+
+    _adjoint = _transpose
+
+    def _tocsr(self):
+        return self.base.tocsr().T.tocsr()
+
+
+class ScaledOperator(Operator):
+    def __init__(self, base, alpha):
+        if isinstance(base, ScaledOperator):
+            base, alpha = base.base, alpha * base.alpha
+        super().__init__(base.shape)
+        self.base, self.alpha = base, float(alpha)
+
+    def _dev_apply(self, x, out):
+        self.base._dev_apply(x, out)
+        out.mul_(self.alpha)
+
+    def _dev_apply_t(self, x, out):
+        self.base._dev_apply_t(x, out)
+        out.mul_(self.alpha)
+
+    def _transpose(self):
+        return ScaledOperator(self.base.T, self.alpha)
+
+    _adjoint = _transpose
+
+    def _tocsr(self):
+        return (self.base.tocsr() * self.alpha).tocsr()
+
+
+class SumOperator(Operator):
+    def __init__(self, terms):
+        shape = terms[0].shape
+        for t in terms:
+            if t.shape != shape:
+                raise ValueError(f"cannot add operators of shapes {shape} and {t.shape}")
+        super().__init__(shape)
+        self.terms = list(terms)
+
+    @staticmethod
+    def make(terms):
+        flat = []
+        for t in terms:
+            flat.extend(t.terms if isinstance(t, SumOperator) else [t])
+        from .fusion import fuse_sum
+
+        fused = fuse_sum(flat)
+        return fused if fused is not None else SumOperator(flat)
+
+    def _dev_apply(self, x, out):
+        self.terms[0]._dev_apply(x, out)
+        tmp = torch.empty_like(out)
+        for t in self.terms[1:]:
+            t._dev_apply(x, tmp)
+            out.add_(tmp)
+
+    def _dev_apply_t(self, x, out):
+        self.terms[0]._dev_apply_t(x, out)
+        tmp = torch.empty_like(out)
+        for t in self.terms[1:]:
+            t._dev_apply_t(x, tmp)
+            out.add_(tmp)
+
+    def _transpose(self):
+        return SumOperator.make([t.T for t in self.terms])
+
+    _adjoint = _transpose
+
+    def _tocsr(self):
+        acc = self.terms[0].tocsr()
+        for t in self.terms[1:]:
+            acc = acc + t.tocsr()
+        return acc.tocsr()
+
+
+class ProductOperator(Operator):
+    """A1 @ A2 @ ... @ An, applied right to left with one temporary per factor."""
+
+    def __init__(self, factors):
+        for a, b in zip(factors[:-1], factors[1:]):
+            if a.shape[1] != b.shape[0]:
+                raise ValueError(f"cannot multiply operators of shapes {a.shape} and {b.shape}")
+        super().__init__((factors[0].shape[0], factors[-1].shape[1]))
+        self.factors = list(factors)
+
+    @staticmethod
+    def make(factors):
+        flat = []
+        for f in factors:
+            flat.extend(f.factors if isinstance(f, ProductOperator) else [f])
+        for a, b in zip(flat[:-1], flat[1:]):
+            if a.shape[1] != b.shape[0]:
+                raise ValueError(f"cannot multiply operators of shapes {a.shape} and {b.shape}")
+        from .fusion import fuse_product
+
+        fused = fuse_product(flat)
+        if fused is not None:
+            return fused
+        return flat[0] if len(flat) == 1 else ProductOperator(flat)
+
+    def _dev_apply(self, x, out):
+        cur = x
+        for f in reversed(self.factors[1:]):
+            cur = f.apply_device(cur, False)
+        self.factors[0]._dev_apply(cur, out)
+
+    def _dev_apply_t(self, x, out):
+        cur = x
+        for f in self.factors[:-1]:
+            cur = f.apply_device(cur, True)
+        self.factors[-1]._dev_apply_t(cur, out)
+
+    def _transpose(self):
+        return ProductOperator.make([f.T for f in reversed(self.factors)])
+
+    _adjoint = _transpose
+
+    def _tocsr(self):
+        acc = self.factors[0].tocsr()
+        for f in self.factors[1:]:
+            acc = acc @ f.tocsr()
+        return acc.tocsr()
+
+
+def as_operator(a):
+    """Wrap a scipy.sparse matrix as a device CSR operator (generic SpMV kernel)."""
+    if isinstance(a, Operator):
+        return a
+    if sp.issparse(a):
+        from .csr import CsrOperator
+
+        return CsrOperator.from_scipy(a)
+    raise TypeError(f"cannot convert {type(a)} to an Operator")

@@ -1,0 +1,336 @@
+"""TensorMesh operators: thin host objects over the libdzb kernels."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import _lib
+from ._lib import check, load
+from .operators import Operator, csr_from_device, cuda_device, ptr, stream_ptr, to_device
+
+
+def _csr_two_pass(nrows, ncols, count, fill):
+    """count(row_nnz) ; indptr = exclusive scan ; fill(indptr, indices, data) -> scipy CSR."""
+    dev = cuda_device()
+    row_nnz = torch.zeros(nrows, dtype=torch.int64, device=dev)
+    count(row_nnz)
+    indptr = torch.zeros(nrows + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(row_nnz, 0, out=indptr[1:])
+    nnz = int(indptr[-1].item())
+    indices = torch.empty(nnz, dtype=torch.int64, device=dev)
+    data = torch.empty(nnz, dtype=torch.float64, device=dev)
+    fill(indptr, indices, data)
+    return csr_from_device(indptr, indices, data, (nrows, ncols))
+
+
+class StencilOperator(Operator):
+    """DIV / CURL / GRAD / averaging, matrix-free (K1-K4).
+
+    reference: operators/differential_operators.py:225-235 (face_divergence), :2169-2181
+    (edge_curl), :658-664 (nodal_gradient), :2478-3253 (average_*).
+    """
+
+    def __init__(self, mesh, op_id, transpose=False, name=None):
+        nr, nc = C.c_int64(), C.c_int64()
+        check(load().dzb_tm_shape(C.byref(mesh._host_mesh_counts()), op_id, C.byref(nr), C.byref(nc)), "dzb_tm_shape")
+        shape = (nc.value, nr.value) if transpose else (nr.value, nc.value)
+        super().__init__(shape)
+        self.mesh, self.op_id, self.transposed, self.name = mesh, op_id, bool(transpose), name
+
+    def _launch(self, x, out, transpose):
+        check(load().dzb_tm_apply(C.byref(self.mesh.device_mesh()), self.op_id, int(transpose), ptr(x), ptr(out),
+                                  stream_ptr()), "dzb_tm_apply")
+
+    def _dev_apply(self, x, out):
+        self._launch(x, out, self.transposed)
+
+    def _dev_apply_t(self, x, out):
+        self._launch(x, out, not self.transposed)
+
+    def _transpose(self):
+        return StencilOperator(self.mesh, self.op_id, not self.transposed, self.name)
+
+    _adjoint = _transpose
+
+    def _tocsr(self):
+        lib, dm, tr = load(), self.mesh.device_mesh(), int(self.transposed)
+        return _csr_two_pass(
+            self.shape[0], self.shape[1],
+            lambda rn: check(lib.dzb_tm_csr_count(C.byref(dm), self.op_id, tr, ptr(rn), stream_ptr()), "csr_count"),
+            lambda ip, ix, da: check(lib.dzb_tm_csr_fill(C.byref(dm), self.op_id, tr, ptr(ip), ptr(ix), ptr(da),
+                                                         stream_ptr()), "csr_fill"),
+        )
+
+    def __repr__(self):
+        t = ".T" if self.transposed else ""
+        return f"<{self.shape[0]}x{self.shape[1]} StencilOperator {self.name}{t} (CUDA, matrix-free)>"
+
+
+# ----------------------------------------------------------------------------------------
+# models
+# ----------------------------------------------------------------------------------------
+class _Model:
+    """Classified physical property (utils/matrix_utils.py:1048-1068 TensorType)."""
+
+    def __init__(self, mesh, model):
+        from .tensor_mesh import is_scalar
+
+        nC = mesh.n_cells
+        self.scalar = 0.0
+        self.dev = None
+        if model is None:
+            self.tt, self.kind, self.scalar = -1, _lib.MODEL_SCALAR, 1.0
+        elif is_scalar(model) and not isinstance(model, torch.Tensor):
+            self.tt, self.kind, self.scalar = 0, _lib.MODEL_SCALAR, float(np.asarray(model).reshape(-1)[0])
+        else:
+            size = model.numel() if isinstance(model, torch.Tensor) else np.asarray(model).size
+            if size == nC:
+                self.tt, self.kind, ncol = 1, _lib.MODEL_ISO, 1
+            elif size == nC * 3:
+                self.tt, self.kind, ncol = 2, _lib.MODEL_ANISO, 3
+            elif size == nC * 6:
+                self.tt, self.kind, ncol = 3, _lib.MODEL_TENSOR, 6
+            else:
+                shp = tuple(model.shape)
+                raise Exception("Unexpected shape of tensor: {}".format(shp))
+            # Fortran-ordered columns, like mkvc / reshape(order="F") in the reference
+            if isinstance(model, torch.Tensor):
+                t = model.to(torch.float64)
+                if t.ndim == 2:
+                    t = t.T
+                self.dev = to_device(t).reshape(-1)
+            else:
+                a = np.asarray(model, dtype=np.float64)
+                self.dev = to_device(a.reshape(-1, order="F"))
+        self.n_params = {-1: 1, 0: 1, 1: nC, 2: 3 * nC, 3: 6 * nC}[self.tt]
+
+
+# ----------------------------------------------------------------------------------------
+# mass matrices
+# ----------------------------------------------------------------------------------------
+class MassOperator(Operator):
+    """get_face_inner_product / get_edge_inner_product as an operator (K5 / K6).
+
+    Symmetric; the matrix is never stored: entries are generated from the model,
+    cell widths and (for full tensors) the corner tables inside the kernel.
+    """
+
+    def __init__(self, mesh, proj, model, invert_model, invert_matrix):
+        n = mesh.n_faces if proj == "F" else mesh.n_edges
+        super().__init__((n, n))
+        self.mesh, self.proj, self.model = mesh, proj, model
+        self.invert_model, self.invert_matrix = bool(invert_model), bool(invert_matrix)
+        self.flags = ((_lib.FLAG_EDGES if proj == "E" else 0)
+                      | (_lib.FLAG_INVERT_MODEL if invert_model else 0)
+                      | (_lib.FLAG_INVERT_MATRIX if invert_matrix else 0))
+
+    @property
+    def is_diagonal(self):
+        return self.model.kind != _lib.MODEL_TENSOR
+
+    def _dev_apply(self, x, out):
+        check(load().dzb_tm_mass_apply(C.byref(self.mesh.device_mesh()), self.flags, self.model.kind,
+                                       ptr(self.model.dev), self.model.scalar, ptr(x), ptr(out), stream_ptr()),
+              "dzb_tm_mass_apply")
+
+    _dev_apply_t = _dev_apply
+
+    def _transpose(self):
+        return self
+
+    _adjoint = _transpose
+
+    def diagonal_device(self):
+        """Diagonal of a diagonal mass matrix as a CUDA tensor."""
+        if not self.is_diagonal:
+            raise ValueError("full-tensor mass matrices are not diagonal")
+        out = torch.empty(self.shape[0], dtype=torch.float64, device=cuda_device())
+        check(load().dzb_tm_mass_diag(C.byref(self.mesh.device_mesh()), self.flags, self.model.kind,
+                                      ptr(self.model.dev), self.model.scalar, ptr(out), stream_ptr()),
+              "dzb_tm_mass_diag")
+        return out
+
+    def diagonal(self):
+        if self.is_diagonal:
+            return self.diagonal_device().cpu().numpy()
+        return self.tocsr().diagonal()
+
+    def _tocsr(self):
+        if self.is_diagonal:
+            return sp.diags(self.diagonal(), format="csr")
+        lib, dm = load(), self.mesh.device_mesh()
+        m = _csr_two_pass(
+            self.shape[0], self.shape[1],
+            lambda rn: check(lib.dzb_tm_mass_tensor_csr_count(C.byref(dm), self.flags, ptr(rn), stream_ptr()),
+                             "mass_tensor_csr_count"),
+            lambda ip, ix, da: check(lib.dzb_tm_mass_tensor_csr_fill(C.byref(dm), self.flags, ptr(self.model.dev),
+                                                                     ptr(ip), ptr(ix), ptr(da), stream_ptr()),
+                                     "mass_tensor_csr_fill"),
+        )
+        m.eliminate_zeros()  # scipy's sparse products / sums in the reference never store exact zeros
+        return m
+
+
+def make_mass_operator(mesh, proj, model, invert_model, invert_matrix, do_fast):
+    """reference: operators/inner_products.py:147-219."""
+    if proj not in ("F", "E"):
+        raise TypeError("projection_type must be 'F' for faces or 'E' for edges")
+    md = _Model(mesh, model)
+    if md.kind == _lib.MODEL_TENSOR and invert_matrix:
+        raise Exception("Solver needed to invert A.")
+    # do_fast=False takes the corner-sum route in the reference; for scalar / isotropic /
+    # anisotropic models it yields the same diagonal matrix, so both routes share K5.
+    return MassOperator(mesh, proj, md, invert_model, invert_matrix)
+
+
+# ----------------------------------------------------------------------------------------
+# derivatives of the mass matrices with respect to the model
+# ----------------------------------------------------------------------------------------
+class MassDerivOperator(Operator):
+    """F(v) = d(M(model) v)/d(model): n x n_params (K7).
+
+    reference: base/base_tensor_mesh.py:865-988 (fast path), inner_products.py:459-565 (tensor).
+    ``F(v) @ dm`` and ``F(v).T @ w`` are matrix-free kernels.
+    """
+
+    def __init__(self, mesh, proj, model, v, invert_model, invert_matrix, ncols, scalar_mode=None):
+        n = mesh.n_faces if proj == "F" else mesh.n_edges
+        super().__init__((n, ncols))
+        self.mesh, self.proj, self.model = mesh, proj, model
+        self.v = to_device(v).reshape(-1)
+        if self.v.numel() != n:
+            raise ValueError(f"v must have {n} entries")
+        self.scalar_mode = scalar_mode  # None | "broadcast": n x 1 built from the isotropic kernel
+        self.flags = ((_lib.FLAG_EDGES if proj == "E" else 0)
+                      | (_lib.FLAG_INVERT_MODEL if invert_model else 0)
+                      | (_lib.FLAG_INVERT_MATRIX if invert_matrix else 0))
+        self._iso_model = None
+        if model.kind == _lib.MODEL_SCALAR:
+            self._iso_model = torch.full((mesh.n_cells,), model.scalar, dtype=torch.float64, device=cuda_device())
+
+    def _call(self, transpose, x, out):
+        kind, mp = self.model.kind, self.model.dev
+        if kind == _lib.MODEL_SCALAR:
+            kind, mp = _lib.MODEL_ISO, self._iso_model
+        check(load().dzb_tm_mass_deriv_apply(C.byref(self.mesh.device_mesh()), self.flags, kind, ptr(mp), 0.0,
+                                             ptr(self.v), int(transpose), ptr(x), ptr(out), stream_ptr()),
+              "dzb_tm_mass_deriv_apply")
+
+    def _dev_apply(self, x, out):
+        if self.scalar_mode == "broadcast":
+            x = x.expand(self.mesh.n_cells).contiguous()
+        self._call(False, x, out)
+
+    def _dev_apply_t(self, x, out):
+        if self.scalar_mode == "broadcast":
+            tmp = torch.empty(self.mesh.n_cells, dtype=torch.float64, device=x.device)
+            self._call(True, x, tmp)
+            out.copy_(tmp.sum().reshape(1))
+        else:
+            self._call(True, x, out)
+
+    def _tocsr(self):
+        # columns generated by applying F(v) to unit vectors is O(n_params) launches; instead use
+        # the structure: every column block is  diag-scaled incidence, recovered from F(v)^T e_f.
+        # Small meshes only (parity / debugging): probe with the identity in blocks.
+        n, k = self.shape
+        if n * 1.0 * k > 4e8:
+            raise MemoryError("MassDerivOperator.tocsr() is meant for small meshes")
+        eye = torch.eye(k, dtype=torch.float64, device=cuda_device())
+        cols = [self.apply_device(eye[:, c].contiguous(), False) for c in range(k)]
+        dense = torch.stack(cols, dim=1).cpu().numpy() if cols else np.zeros((n, 0))
+        return sp.csr_matrix(dense)
+
+
+def make_mass_deriv(mesh, proj, model, do_fast, invert_model, invert_matrix):
+    """Returns the callable ``v -> operator`` (inner_products.py:405-457)."""
+    md = _Model(mesh, model)
+    nC = mesh.n_cells
+    if md.tt == -1:
+        return None
+    generic = (md.kind == _lib.MODEL_TENSOR) or not do_fast
+    if generic and (invert_model or invert_matrix):
+        raise NotImplementedError(
+            "inverting the property or the matrix is not yet implemented for this mesh/tensorType. You should write it!"
+        )
+    if md.tt == 0:
+        if invert_model and not invert_matrix and not generic:
+            # the reference raises here (sdiag of a bare float / shape mismatch); keep it an error
+            raise TypeError("Vector must be a numpy array")
+        if invert_matrix and not invert_model and not generic:
+            ncols, mode = nC, None  # reference quirk: n x nC (base_tensor_mesh.py:927-928)
+        else:
+            ncols, mode = 1, "broadcast"
+    else:
+        ncols, mode = md.n_params, None
+
+    def inner_product_deriv(v=None):
+        if v is None:
+            raise Exception("v must be supplied for this implementation.")
+        return MassDerivOperator(mesh, proj, md, v, invert_model, invert_matrix, ncols, mode)
+
+    return inner_product_deriv
+
+
+# ----------------------------------------------------------------------------------------
+# fused composites
+# ----------------------------------------------------------------------------------------
+class DCNodalOperator(Operator):
+    """G^T Me(sigma) G in one kernel (K8); symmetric positive semi-definite.
+
+    reference composition: tutorials/pde/3_nodal_dirichlet_poisson.py:146-160.
+    """
+
+    def __init__(self, mesh, sigma_dev):
+        n = mesh.n_nodes
+        super().__init__((n, n))
+        self.mesh, self.sigma = mesh, sigma_dev
+
+    def _dev_apply(self, x, out):
+        check(load().dzb_tm_dc_nodal(C.byref(self.mesh.device_mesh()), ptr(self.sigma), ptr(x), ptr(out), stream_ptr()),
+              "dzb_tm_dc_nodal")
+
+    _dev_apply_t = _dev_apply
+
+    def _transpose(self):
+        return self
+
+    _adjoint = _transpose
+
+    def _tocsr(self):
+        G = self.mesh.nodal_gradient.tocsr()
+        md = _Model(self.mesh, self.sigma)
+        Me = MassOperator(self.mesh, "E", md, False, False).tocsr()
+        return (G.T @ Me @ G).tocsr()
+
+
+class MaxwellOperator(Operator):
+    """C^T Mf(mui) C + Me(sigma) in one kernel (K9); symmetric.
+
+    reference composition: tests/boundaries/test_boundary_maxwell.py:95-99.
+    """
+
+    def __init__(self, mesh, mui_dev, sigma_dev, scale_sigma=1.0):
+        n = mesh.n_edges
+        super().__init__((n, n))
+        self.mesh, self.mui, self.sigma = mesh, mui_dev, sigma_dev
+
+    def _dev_apply(self, x, out):
+        check(load().dzb_tm_maxwell(C.byref(self.mesh.device_mesh()), ptr(self.mui), ptr(self.sigma), ptr(x), ptr(out),
+                                    stream_ptr()), "dzb_tm_maxwell")
+
+    _dev_apply_t = _dev_apply
+
+    def _transpose(self):
+        return self
+
+    _adjoint = _transpose
+
+    def _tocsr(self):
+        Cm = self.mesh.edge_curl.tocsr()
+        Mf = MassOperator(self.mesh, "F", _Model(self.mesh, self.mui), False, False).tocsr()
+        Me = MassOperator(self.mesh, "E", _Model(self.mesh, self.sigma), False, False).tocsr()
+        return (Cm.T @ Mf @ Cm + Me).tocsr()

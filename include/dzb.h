@@ -1,0 +1,154 @@
+/*
+ * dzb.h -- C ABI of libdzb.so, the B200 (sm_100a) operator-application library.
+ *
+ * Drop-in boundary for the operator-application hot path of simpeg/discretize.
+ * The reference has no FFI on this path: its operators are scipy.sparse matrices
+ * built by python properties and applied by scipy's csr_matvec.  Each entry point
+ * below replaces "build that matrix, then A @ x" for one reference property; the
+ * reference interface it replaces is cited as file:line (relative to the
+ * reference tree).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Rules of the ABI
+ *   - plain C: pointers, sizes, ints.  No torch / C++ types cross it.
+ *   - every pointer is a DEVICE pointer unless the name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - nothing allocates: the caller owns inputs, outputs and workspaces.
+ *   - nothing synchronises: kernels are enqueued on `stream` and the call returns.
+ *   - return 0 on success, <0 on error; dzb_last_error() gives the message.
+ *   - all reals are float64; vector layouts are the reference's (x fastest,
+ *     faces = [Fx;Fy;Fz], edges = [Ex;Ey;Ez]; base/base_regular_mesh.py:601-762).
+ */
+#ifndef DZB_H
+#define DZB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DZB_ABI_VERSION 1
+
+/* 3-D tensor mesh: cell counts and DEVICE pointers to the 1-D cell widths and
+ * their reciprocals (reference: base/base_tensor_mesh.py:86-114 `h`). */
+typedef struct {
+  int64_t nx, ny, nz;
+  const double *hx, *hy, *hz;    /* lengths nx, ny, nz */
+  const double *rhx, *rhy, *rhz; /* 1/h, same lengths  */
+} DzbTensorMesh;
+
+/* Elementary operators (all 3-D TensorMesh). */
+enum DzbOp {
+  DZB_OP_DIV = 0,        /* face_divergence            operators/differential_operators.py:225-235 */
+  DZB_OP_CURL = 1,       /* edge_curl                  :2169-2181 */
+  DZB_OP_GRAD = 2,       /* nodal_gradient             :658-664   */
+  DZB_OP_AVE_F2CC = 3,   /* average_face_to_cell       :2478-2492 */
+  DZB_OP_AVE_F2CCV = 4,  /* average_face_to_cell_vector:2494-2508 */
+  DZB_OP_AVE_FX2CC = 5,  /* average_face_x_to_cell     :2510-2787 */
+  DZB_OP_AVE_FY2CC = 6,
+  DZB_OP_AVE_FZ2CC = 7,
+  DZB_OP_AVE_E2CC = 8,   /* average_edge_to_cell       :2894-2908 */
+  DZB_OP_AVE_E2CCV = 9,  /* average_edge_to_cell_vector:2910-2924 */
+  DZB_OP_AVE_EX2CC = 10, /* average_edge_x_to_cell     :2926-3203 */
+  DZB_OP_AVE_EY2CC = 11,
+  DZB_OP_AVE_EZ2CC = 12,
+  DZB_OP_AVE_N2CC = 13,  /* average_node_to_cell       :3236-3253 */
+  DZB_OP_COUNT = 14
+};
+
+/* Physical-property layouts (utils/matrix_utils.py:1048-1068 TensorType). */
+enum DzbModelKind {
+  DZB_MODEL_SCALAR = 0, /* one value, passed in `model_scalar`              */
+  DZB_MODEL_ISO = 1,    /* nC values                                        */
+  DZB_MODEL_ANISO = 2,  /* 3*nC values, columns xx,yy,zz (Fortran order)    */
+  DZB_MODEL_TENSOR = 3  /* 6*nC values, columns xx,yy,zz,xy,xz,yz           */
+};
+
+enum DzbFlags {
+  DZB_INVERT_MODEL = 1,  /* use 1/model (3x3 inverse for TENSOR)             */
+  DZB_INVERT_MATRIX = 2, /* use the reciprocal of the (diagonal) mass matrix */
+  DZB_EDGES = 4          /* edge inner product; default is faces             */
+};
+
+int dzb_version(void);
+const char *dzb_last_error(void);
+
+/* ---- elementary operators --------------------------------------------------- */
+/* y = A x (transpose == 0) or y = A^T x (transpose != 0), A = mesh.<op>. */
+int dzb_tm_apply(const DzbTensorMesh *m, int op, int transpose, const double *x, double *y, void *stream);
+/* Shape of mesh.<op> (host call). */
+int dzb_tm_shape(const DzbTensorMesh *m_host_counts_only, int op, int64_t *nrows, int64_t *ncols);
+/* CSR materialisation of mesh.<op> (or its transpose): pass 1 writes the number of
+ * stored entries of each row into row_nnz[nrows]; the caller turns that into indptr
+ * (exclusive scan); pass 2 writes sorted column indices and values. */
+int dzb_tm_csr_count(const DzbTensorMesh *m, int op, int transpose, int64_t *row_nnz, void *stream);
+int dzb_tm_csr_fill(const DzbTensorMesh *m, int op, int transpose, const int64_t *indptr, int64_t *indices,
+                    double *data, void *stream);
+
+/* ---- mass matrices: get_face_inner_product / get_edge_inner_product ---------- */
+/* operators/inner_products.py:35-99 -> base/base_tensor_mesh.py:792-863 (diagonal)
+ * and inner_products.py:147-272 (full tensor).  flags: DzbFlags. */
+/* diag[n] = diagonal of M(model)  (SCALAR / ISO / ANISO only). */
+int dzb_tm_mass_diag(const DzbTensorMesh *m, int flags, int model_kind, const double *model, double model_scalar,
+                     double *diag, void *stream);
+/* y = M(model) x for any model kind, generated on the fly (no stored matrix). */
+int dzb_tm_mass_apply(const DzbTensorMesh *m, int flags, int model_kind, const double *model, double model_scalar,
+                      const double *x, double *y, void *stream);
+/* CSR of the full-tensor mass matrix (<= 9 entries per row). */
+int dzb_tm_mass_tensor_csr_count(const DzbTensorMesh *m, int flags, int64_t *row_nnz, void *stream);
+int dzb_tm_mass_tensor_csr_fill(const DzbTensorMesh *m, int flags, const double *model, const int64_t *indptr,
+                                int64_t *indices, double *data, void *stream);
+
+/* ---- model derivatives: get_{face,edge}_inner_product_deriv ------------------- */
+/* inner_products.py:274-326, 405-565; base_tensor_mesh.py:865-988.
+ * F(v) = d(M(model) v)/d(model) is n x (nC*k), k = 1 (SCALAR: n x 1; ISO), 3, 6.
+ * transpose == 0: y[n]      = F(v) dm      (dm has nC*k entries, 1 for SCALAR)
+ * transpose != 0: y[nC*k]   = F(v)^T w     (w has n entries). */
+int dzb_tm_mass_deriv_apply(const DzbTensorMesh *m, int flags, int model_kind, const double *model,
+                            double model_scalar, const double *v, int transpose, const double *x, double *y,
+                            void *stream);
+
+/* ---- fused composites -------------------------------------------------------- */
+/* y = G^T Me(sigma) G phi  (DC resistivity, nodal; tutorials/pde/3_nodal_dirichlet_poisson.py:146-160):
+ * nodal_gradient (:658-664) + get_edge_inner_product (isotropic sigma, nC) in ONE kernel.
+ * Slab form for z-decomposition: the local mesh `m` holds cell layers [k0,k1) of a
+ * global mesh; lower/upper != 0 say that the slab has a neighbour below/above, in
+ * which case phi carries one extra node plane and sigma one extra cell layer on that
+ * side (halo), and y is written for the owned planes only.  lower = upper = 0 is the
+ * plain single-GPU operator. */
+int dzb_tm_dc_nodal(const DzbTensorMesh *m, const double *sigma, const double *phi, double *y, void *stream);
+
+/* y = C^T Mf(mui) C e + Me(sigma) e  (Maxwell, E-formulation;
+ * tests/boundaries/test_boundary_maxwell.py:95-99): edge_curl (:2169-2181) +
+ * get_face_inner_product(mui) + get_edge_inner_product(sigma), isotropic models. */
+int dzb_tm_maxwell(const DzbTensorMesh *m, const double *mui, const double *sigma, const double *e, double *y,
+                   void *stream);
+
+/* ---- interpolation: get_interpolation_matrix --------------------------------- */
+/* base/base_tensor_mesh.py:684-790 -> utils/interpolation_utils.py:44-172 ->
+ * _extensions/interputils_cython.pyx:42-182.
+ * tx,ty,tz: the three 1-D sample arrays of the location grid (device, lengths
+ * ntx,nty,ntz), exactly the float64 arrays the host built (bit-exact bisection).
+ * pts: (npts,3) row-major.  cols[npts*8] (int64, F-order flat index + col_offset) and
+ * w[npts*8] in the reference's entry order. */
+int dzb_interp_locate(const double *tx, int64_t ntx, const double *ty, int64_t nty, const double *tz, int64_t ntz,
+                      const double *pts, int64_t npts, int64_t col_offset, int64_t *cols, double *w, void *stream);
+/* y[npts] = Q v from stored cols/w;  row_scale (may be NULL) multiplies each row (0 for zeros_outside rows). */
+int dzb_interp_apply(const int64_t *cols, const double *w, const double *row_scale, int64_t npts, const double *v,
+                     double *y, void *stream);
+/* y[ncols] += Q^T x (y must be zeroed by the caller). */
+int dzb_interp_apply_t(const int64_t *cols, const double *w, const double *row_scale, int64_t npts, const double *x,
+                       double *y, void *stream);
+/* Fused locate + apply: y = Q v without storing Q. */
+int dzb_interp_fused(const double *tx, int64_t ntx, const double *ty, int64_t nty, const double *tz, int64_t ntz,
+                     const double *pts, int64_t npts, int64_t col_offset, const double *row_scale, const double *v,
+                     double *y, void *stream);
+/* inside[npts] = 1 if the point is inside the mesh (is_inside, base_tensor_mesh.py:638-682);
+ * lo/hi/tol: 3 doubles each on the HOST. */
+int dzb_points_inside(const double *pts, int64_t npts, const double *lo_host, const double *hi_host,
+                      const double *tol_host, uint8_t *inside, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DZB_H */

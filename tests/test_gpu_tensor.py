@@ -1,0 +1,420 @@
+"""GPU parity tests: the CUDA path (through the python mirror of the reference API, which
+calls the C ABI) against the numpy oracle and the committed reference fixtures.
+
+Tolerances (north_star): sparsity patterns / interpolation indices bit-exact; operator
+values and matvec results <= 1e-12 relative (float64).
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as sla
+
+from oracle import tensor_ops as T
+from tests.helpers import (MESHES, ORACLE_OPS, RTOL, adversarial_points, assert_close_vec, assert_same_matrix,
+                           golden_matrix, load_golden, make_pair)
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.fail("gpu tests need a CUDA device (no CPU fallback exists)")
+
+
+# ------------------------------------------------------------------------------------------
+# elementary operators
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mesh_name", list(MESHES))
+@pytest.mark.parametrize("name", list(ORACLE_OPS))
+def test_elementary_matrix_and_apply(mesh_name, name):
+    mesh, grid = make_pair(mesh_name)
+    ref = ORACLE_OPS[name](grid)
+    op = getattr(mesh, name)
+    assert op.shape == ref.shape
+    assert_same_matrix(op.tocsr(), ref)
+    assert_same_matrix(op.T.tocsr(), ref.T.tocsr())
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(ref.shape[1])
+    y = rng.standard_normal(ref.shape[0])
+    assert_close_vec(op @ x, ref @ x)
+    assert_close_vec(op.T @ y, ref.T @ y)
+
+
+@pytest.mark.parametrize("name", list(ORACLE_OPS))
+def test_elementary_vs_reference_fixture(name):
+    g = load_golden()
+    import discretize_b200 as dz
+
+    mesh = dz.TensorMesh([g["hx"], g["hy"], g["hz"]], origin=g["origin"])
+    assert_same_matrix(getattr(mesh, name).tocsr(), golden_matrix(g, name))
+
+
+def test_config1_64cubed():
+    """BASELINE config 1: TensorMesh 64^3, D @ u_f, C @ e, Mf(sigma) @ u_f -- full element-wise parity."""
+    import discretize_b200 as dz
+
+    mesh, grid = dz.TensorMesh([64, 64, 64]), T.Grid([64, 64, 64])
+    u = np.random.default_rng(1).standard_normal(mesh.nF)
+    e = np.random.default_rng(2).standard_normal(mesh.nE)
+    sigma = np.random.default_rng(3).random(mesh.nC) + 0.5
+    D, C = T.face_divergence(grid), T.edge_curl(grid)
+    Mf = T.inner_product(grid, "F", sigma)
+    assert_same_matrix(mesh.face_divergence.tocsr(), D)
+    assert_same_matrix(mesh.edge_curl.tocsr(), C)
+    assert_same_matrix(mesh.get_face_inner_product(sigma).tocsr(), Mf)
+    assert_close_vec(mesh.face_divergence @ u, D @ u)
+    assert_close_vec(mesh.edge_curl @ e, C @ e)
+    assert_close_vec(mesh.get_face_inner_product(sigma) @ u, Mf @ u)
+    # non-uniform variant
+    rng = np.random.default_rng(4)
+    h = [rng.random(64) + 0.5 for _ in range(3)]
+    mesh, grid = dz.TensorMesh(h), T.Grid(h)
+    assert_close_vec(mesh.face_divergence @ u, T.face_divergence(grid) @ u)
+    assert_close_vec(mesh.edge_curl @ e, T.edge_curl(grid) @ e)
+    assert_close_vec(mesh.get_face_inner_product(sigma) @ u, T.inner_product(grid, "F", sigma) @ u)
+
+
+def test_mimetic_identities_device():
+    mesh, _ = make_pair("nonuniform")
+    rng = np.random.default_rng(0)
+    e = rng.standard_normal(mesh.nE)
+    phi = rng.standard_normal(mesh.nN)
+    dc = mesh.face_divergence @ (mesh.edge_curl @ e)
+    cg = mesh.edge_curl @ (mesh.nodal_gradient @ phi)
+    assert np.abs(dc).max() < 1e-12 * np.abs(e).max() * 100
+    assert np.abs(cg).max() < 1e-12 * np.abs(phi).max() * 100
+
+
+# ------------------------------------------------------------------------------------------
+# mass matrices
+# ------------------------------------------------------------------------------------------
+def _models(grid, rng):
+    return {
+        "none": None,
+        "scalar": 2.5,
+        "iso": rng.random(grid.nC) + 0.5,
+        "aniso": rng.random((grid.nC, 3)) + 0.5,
+        "tensor": np.c_[rng.random((grid.nC, 3)) + 2.0, rng.random((grid.nC, 3)) * 0.5 - 0.25],
+    }
+
+
+@pytest.mark.parametrize("mesh_name", ["uniform", "nonuniform", "thin"])
+@pytest.mark.parametrize("proj", ["F", "E"])
+@pytest.mark.parametrize("im", [False, True])
+@pytest.mark.parametrize("ix", [False, True])
+def test_mass(mesh_name, proj, im, ix):
+    mesh, grid = make_pair(mesh_name)
+    rng = np.random.default_rng(3)
+    get = mesh.get_face_inner_product if proj == "F" else mesh.get_edge_inner_product
+    n = grid.nF if proj == "F" else grid.nE
+    x = rng.standard_normal(n)
+    for mk, m in _models(grid, rng).items():
+        if mk == "tensor" and ix:
+            with pytest.raises(Exception, match="Solver needed"):
+                get(m, invert_model=im, invert_matrix=ix)
+            continue
+        ref = T.inner_product(grid, proj, m, invert_model=im, invert_matrix=ix)
+        op = get(m, invert_model=im, invert_matrix=ix)
+        assert_same_matrix(op.tocsr(), ref)
+        assert_close_vec(op @ x, ref @ x)
+        assert_close_vec(op.T @ x, ref @ x)
+
+
+@pytest.mark.parametrize("proj", ["F", "E"])
+@pytest.mark.parametrize("mk", ["iso", "aniso", "tensor"])
+def test_mass_vs_reference_fixture(proj, mk):
+    g = load_golden()
+    import discretize_b200 as dz
+
+    mesh = dz.TensorMesh([g["hx"], g["hy"], g["hz"]], origin=g["origin"])
+    get = mesh.get_face_inner_product if proj == "F" else mesh.get_edge_inner_product
+    for im in (False, True):
+        for ix in (False, True):
+            if mk == "tensor" and ix:
+                continue
+            assert_same_matrix(get(g["model_" + mk], invert_model=im, invert_matrix=ix).tocsr(),
+                               golden_matrix(g, f"mass_{proj}_{mk}_{int(im)}{int(ix)}"))
+
+
+def test_mass_errors():
+    mesh, grid = make_pair("uniform")
+    with pytest.raises(TypeError, match="invProp"):
+        mesh.get_face_inner_product(invProp=True)
+    with pytest.raises(TypeError, match="doFast"):
+        mesh.get_edge_inner_product(doFast=True)
+    with pytest.raises(Exception, match="Unexpected shape of tensor"):
+        mesh.get_face_inner_product(np.ones(grid.nC + 1))
+
+
+@pytest.mark.parametrize("mesh_name", ["uniform", "nonuniform"])
+@pytest.mark.parametrize("proj", ["F", "E"])
+@pytest.mark.parametrize("im", [False, True])
+@pytest.mark.parametrize("ix", [False, True])
+def test_mass_deriv(mesh_name, proj, im, ix):
+    mesh, grid = make_pair(mesh_name)
+    rng = np.random.default_rng(5)
+    n = grid.nF if proj == "F" else grid.nE
+    v = rng.standard_normal(n)
+    w = rng.standard_normal(n)
+    get = mesh.get_face_inner_product_deriv if proj == "F" else mesh.get_edge_inner_product_deriv
+    for mk, m in _models(grid, rng).items():
+        if mk == "none":
+            continue
+        if mk == "tensor" and (im or ix):
+            with pytest.raises(NotImplementedError):
+                get(m, invert_model=im, invert_matrix=ix)
+            continue
+        if mk == "scalar" and im and not ix:
+            continue  # undefined in the reference (raises there)
+        ref = T.inner_product_deriv(grid, proj, m, v, invert_model=im, invert_matrix=ix)
+        op = get(m, invert_model=im, invert_matrix=ix)(v)
+        assert op.shape == ref.shape, (mk, op.shape, ref.shape)
+        dm = rng.standard_normal(ref.shape[1])
+        assert_close_vec(op @ dm, ref @ dm)
+        assert_close_vec(op.T @ w, ref.T @ w)
+        assert_same_matrix(op.tocsr(), ref)
+
+
+@pytest.mark.parametrize("proj", ["F", "E"])
+def test_mass_deriv_generic_path(proj):
+    mesh, grid = make_pair("nonuniform")
+    rng = np.random.default_rng(6)
+    n = grid.nF if proj == "F" else grid.nE
+    v, w = rng.standard_normal(n), rng.standard_normal(n)
+    get = mesh.get_face_inner_product_deriv if proj == "F" else mesh.get_edge_inner_product_deriv
+    for mk, m in _models(grid, rng).items():
+        if mk == "none":
+            continue
+        ref = T.inner_product_deriv(grid, proj, m, v, do_fast=False)
+        op = get(m, do_fast=False)(v)
+        dm = rng.standard_normal(ref.shape[1])
+        assert_close_vec(op @ dm, ref @ dm)
+        assert_close_vec(op.T @ w, ref.T @ w)
+
+
+# ------------------------------------------------------------------------------------------
+# fused composites
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mesh_name", list(MESHES))
+def test_dc_nodal_fused(mesh_name):
+    from discretize_b200.tensor_ops import DCNodalOperator
+
+    mesh, grid = make_pair(mesh_name)
+    rng = np.random.default_rng(6)
+    sigma = np.exp(rng.standard_normal(grid.nC))
+    phi = rng.standard_normal(grid.nN)
+    G = T.nodal_gradient(grid)
+    Me = T.inner_product(grid, "E", sigma)
+    ref = (G.T @ Me @ G).tocsr()
+    Gd = mesh.nodal_gradient
+    A = Gd.T @ mesh.get_edge_inner_product(sigma) @ Gd
+    assert isinstance(A, DCNodalOperator)  # the algebra fused it
+    assert_close_vec(A @ phi, ref @ phi)
+    assert_close_vec(A.T @ phi, ref @ phi)
+    # unfused chain of elementary kernels gives the same thing
+    chain = Gd.T @ (mesh.get_edge_inner_product(sigma) @ (Gd @ phi))
+    assert_close_vec(A @ phi, chain)
+    assert_same_matrix(A.tocsr(), ref)
+
+
+def test_dc_nodal_fixture_and_tuning():
+    import ctypes
+
+    import discretize_b200 as dz
+    from discretize_b200._lib import load
+
+    g = load_golden()
+    mesh = dz.TensorMesh([g["hx"], g["hy"], g["hz"]], origin=g["origin"])
+    ref = golden_matrix(g, "dc_nodal")
+    phi = np.random.default_rng(7).standard_normal(mesh.nN)
+    Gd = mesh.nodal_gradient
+    A = Gd.T @ mesh.get_edge_inner_product(g["model_iso"]) @ Gd
+    lib = load()
+    lib.dzb_tune_dc.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.dzb_tune_dc.restype = None
+    try:
+        for ry in (2, 4, 8):
+            for kchunk in (1, 3, 32):
+                lib.dzb_tune_dc(ry, kchunk)
+                assert_close_vec(A @ phi, ref @ phi)
+    finally:
+        lib.dzb_tune_dc(4, 32)
+
+
+def test_dc_nodal_128_against_chain_and_cg():
+    """Size-independent checks at a larger size: fused == unfused chain; SPD => CG converges."""
+    import discretize_b200 as dz
+
+    rng = np.random.default_rng(8)
+    h = [rng.random(128) + 0.5, rng.random(96) + 0.5, rng.random(100) + 0.5]
+    mesh = dz.TensorMesh(h)
+    sigma = np.exp(rng.standard_normal(mesh.nC))
+    phi = rng.standard_normal(mesh.nN)
+    Gd = mesh.nodal_gradient
+    Me = mesh.get_edge_inner_product(sigma)
+    A = Gd.T @ Me @ Gd
+    fused = A @ phi
+    chain = Gd.T @ (Me @ (Gd @ phi))
+    assert_close_vec(fused, chain)
+    # symmetry <x, A y> == <A x, y>
+    psi = rng.standard_normal(mesh.nN)
+    assert abs(psi @ fused - (A @ psi) @ phi) <= 1e-10 * abs(psi @ fused)
+    # constants are in the null space
+    assert np.abs(A @ np.ones(mesh.nN)).max() < 1e-9 * np.abs(fused).max()
+
+
+@pytest.mark.parametrize("mesh_name", list(MESHES))
+def test_maxwell_fused(mesh_name):
+    from discretize_b200.tensor_ops import MaxwellOperator
+
+    mesh, grid = make_pair(mesh_name)
+    rng = np.random.default_rng(9)
+    sigma = np.exp(rng.standard_normal(grid.nC))
+    mui = np.exp(rng.standard_normal(grid.nC))
+    e = rng.standard_normal(grid.nE)
+    C = T.edge_curl(grid)
+    ref = (C.T @ T.inner_product(grid, "F", mui) @ C + T.inner_product(grid, "E", sigma)).tocsr()
+    Cd = mesh.edge_curl
+    A = Cd.T @ mesh.get_face_inner_product(mui) @ Cd + mesh.get_edge_inner_product(sigma)
+    assert isinstance(A, MaxwellOperator)
+    assert_close_vec(A @ e, ref @ e)
+    chain = Cd.T @ (mesh.get_face_inner_product(mui) @ (Cd @ e)) + mesh.get_edge_inner_product(sigma) @ e
+    assert_close_vec(A @ e, chain)
+    assert_same_matrix(A.tocsr(), ref)
+
+
+# ------------------------------------------------------------------------------------------
+# interpolation
+# ------------------------------------------------------------------------------------------
+LOCS = ["CC", "N", "Fx", "Fy", "Fz", "Ex", "Ey", "Ez", "CCVx", "CCVy", "CCVz"]
+
+
+@pytest.mark.parametrize("mesh_name", ["uniform", "nonuniform", "thin"])
+@pytest.mark.parametrize("loc", LOCS)
+def test_interpolation(mesh_name, loc):
+    from discretize_b200.interp import make_interpolation_operator
+
+    mesh, grid = make_pair(mesh_name)
+    rng = np.random.default_rng(10)
+    pts = adversarial_points(grid, rng)
+    ref = T.interpolation_matrix(grid, pts, loc)
+    Q = mesh.get_interpolation_matrix(pts, loc)
+    assert Q.shape == ref.shape
+    assert_same_matrix(Q.tocsr(), ref, 0.0)  # indices AND weights bit-exact
+    v = rng.standard_normal(ref.shape[1])
+    y = rng.standard_normal(ref.shape[0])
+    assert_close_vec(Q @ v, ref @ v)
+    assert_close_vec(Q.T @ y, ref.T @ y)
+    Qf = make_interpolation_operator(mesh, pts, loc, store=False)  # fused locate+apply
+    assert_close_vec(Qf @ v, ref @ v)
+
+
+@pytest.mark.parametrize("loc", LOCS)
+def test_interpolation_vs_reference_fixture(loc):
+    import discretize_b200 as dz
+
+    g = load_golden()
+    mesh = dz.TensorMesh([g["hx"], g["hy"], g["hz"]], origin=g["origin"])
+    assert_same_matrix(mesh.get_interpolation_matrix(g["interp_pts"], loc).tocsr(), golden_matrix(g, "interp_" + loc), 0.0)
+
+
+@pytest.mark.parametrize("loc", ["CC", "N", "Ex"])
+def test_interpolation_outside(loc):
+    mesh, grid = make_pair("nonuniform")
+    rng = np.random.default_rng(11)
+    pts = adversarial_points(grid, rng, 60)
+    pts[5] += 100.0
+    pts[17, 1] -= 50.0
+    with pytest.raises(ValueError, match="Points outside of mesh"):
+        mesh.get_interpolation_matrix(pts, loc)
+    with pytest.raises(TypeError, match="locType"):
+        mesh.get_interpolation_matrix(pts, locType=loc)
+    ref = T.interpolation_matrix(grid, pts, loc, zeros_outside=True)
+    Q = mesh.get_interpolation_matrix(pts, loc, zeros_outside=True)
+    v = rng.standard_normal(ref.shape[1])
+    out = Q @ v
+    assert out[5] == 0.0 and out[17] == 0.0
+    assert_close_vec(out, ref @ v)
+    assert_same_matrix(Q.tocsr(), ref, 0.0)
+
+
+def test_interpolation_large_roundtrip():
+    """Size-independent property at 2e6 points on 64^3: a trilinear field is reproduced exactly
+    (to rounding) at interior points, for nodes and for edge/face grids inside their hulls."""
+    import discretize_b200 as dz
+
+    mesh = dz.TensorMesh([64, 64, 64])
+    rng = np.random.default_rng(12)
+    pts = rng.random((2_000_000, 3)) * 0.9 + 0.05
+    f = lambda X: 1.0 + 2.0 * X[:, 0] - 0.5 * X[:, 1] + 3.0 * X[:, 2]
+    for loc, grid_pts in (("N", mesh.nodes), ("Ex", mesh.edges_x), ("Fz", mesh.faces_z), ("CC", mesh.cell_centers)):
+        Q = mesh.get_interpolation_matrix(pts, loc)
+        ncols = Q.shape[1]
+        v = np.zeros(ncols)
+        off = {"N": 0, "CC": 0, "Ex": 0, "Fz": mesh.nFx + mesh.nFy}[loc]
+        v[off:off + grid_pts.shape[0]] = f(grid_pts)
+        assert np.abs(Q @ v - f(pts)).max() < 1e-12
+
+
+# ------------------------------------------------------------------------------------------
+# LinearOperator protocol / algebra
+# ------------------------------------------------------------------------------------------
+def test_linear_operator_protocol():
+    mesh, grid = make_pair("nonuniform")
+    D = mesh.face_divergence
+    Dref = T.face_divergence(grid)
+    assert isinstance(D, sla.LinearOperator)
+    assert D.dtype == np.float64 and D.shape == Dref.shape
+    rng = np.random.default_rng(13)
+    x = rng.standard_normal(D.shape[1])
+    X = rng.standard_normal((D.shape[1], 3))
+    y = rng.standard_normal(D.shape[0])
+    for got in (D @ x, D * x, D.dot(x), D.matvec(x), D(x)):
+        assert isinstance(got, np.ndarray)
+        assert_close_vec(got, Dref @ x)
+    assert_close_vec(D.matmat(X), Dref @ X)
+    assert_close_vec(D @ X, Dref @ X)
+    assert_close_vec(D.rmatvec(y), Dref.T @ y)
+    assert_close_vec(D.T @ y, Dref.T @ y)
+    assert_close_vec(D.H @ y, Dref.T @ y)
+    assert_close_vec(y @ D, Dref.T @ y)
+    assert (D @ x.reshape(-1, 1)).shape == (D.shape[0], 1)
+    # torch in -> torch out, stays on the device
+    xd = torch.from_numpy(x).cuda()
+    yd = D @ xd
+    assert isinstance(yd, torch.Tensor) and yd.is_cuda
+    assert_close_vec(yd.cpu().numpy(), Dref @ x)
+    # complex vectors (frequency-domain fields)
+    z = x + 1j * rng.standard_normal(D.shape[1])
+    assert_close_vec(D @ z, Dref @ z)
+    # algebra
+    A = 2.0 * D - D / 4.0
+    assert_close_vec(A @ x, 1.75 * (Dref @ x))
+    assert_close_vec((-D).T @ y, -(Dref.T @ y))
+    S = D.T @ D
+    assert_close_vec(S @ x, Dref.T @ (Dref @ x))
+    assert_same_matrix((D.T @ D).tocsr(), (Dref.T @ Dref).tocsr())
+    with pytest.raises(ValueError):
+        D @ np.ones(3)
+    with pytest.raises(ValueError):
+        D @ mesh.edge_curl.T
+    # scipy solvers accept it
+    M = mesh.get_edge_inner_product(rng.random(grid.nC) + 0.5)
+    b = rng.standard_normal(M.shape[0])
+    sol, info = sla.cg(M, b, rtol=1e-12, maxiter=50)
+    assert info == 0
+    assert_close_vec(M @ sol, b, 1e-9)
+
+
+def test_aliases_and_counts():
+    mesh, grid = make_pair("nonuniform")
+    assert (mesh.nC, mesh.nN, mesh.nF, mesh.nE) == (grid.nC, grid.nN, grid.nF, grid.nE)
+    assert tuple(mesh.vnF) == grid.vnF and tuple(mesh.vnE) == grid.vnE
+    assert mesh.aveF2CC is mesh.average_face_to_cell
+    assert mesh.aveE2CCV.shape == (3 * grid.nC, grid.nE)
+    np.testing.assert_array_equal(mesh.cell_volumes, grid.cell_volumes())
+    np.testing.assert_array_equal(mesh.face_areas, grid.face_areas())
+    np.testing.assert_array_equal(mesh.edge_lengths, grid.edge_lengths())
