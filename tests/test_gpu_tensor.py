@@ -404,7 +404,7 @@ def test_linear_operator_protocol():
     # scipy solvers accept it
     M = mesh.get_edge_inner_product(rng.random(grid.nC) + 0.5)
     b = rng.standard_normal(M.shape[0])
-    sol, info = sla.cg(M, b, rtol=1e-12, maxiter=50)
+    sol, info = sla.cg(M, b, rtol=1e-12, maxiter=5000)
     assert info == 0
     assert_close_vec(M @ sol, b, 1e-9)
 
