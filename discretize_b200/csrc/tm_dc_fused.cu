@@ -18,10 +18,13 @@
 //     halo lane on each side; x-neighbours are exchanged with warp shuffles),
 //   * each lane keeps RY consecutive y-rows (+ halo rows) in registers,
 //   * the warp marches along z keeping the previous plane / cell layer in
-//     registers, so every phi and sigma value is loaded from HBM/L2 once per strip
-//     and every output written once: algorithmic bytes = 8 (2 nN + nC).
-//   * loads are 256-byte coalesced row segments; there is no shared memory and no
-//     block-level synchronisation at all.
+//     registers and prefetching the next one, so every phi and sigma value is loaded
+//     once per strip and every output written once: algorithmic bytes = 8 (2 nN + nC),
+//   * loads are 256-byte coalesced row segments; out-of-range rows / columns / planes
+//     are handled by CLAMPING the address (always a valid, finite entry) and zeroing
+//     the cell measure (hx, hy or hz = 0), so that the inner loop carries no masks:
+//     a cell outside the mesh has V sigma = 0 and an edge without cells has weight 0.
+#include "bulk_pipe.cuh"
 #include "tm_common.cuh"
 
 namespace dzb {
@@ -29,132 +32,379 @@ namespace dzb {
 constexpr int DC_WARPS = 4;      // warps per block, consecutive x strips
 constexpr int DC_XOUT = 30;      // outputs per warp strip (lanes 1..30)
 
-template <int RY>
-__global__ void __launch_bounds__(DC_WARPS * 32)
+template <int RY, int MINB>
+__global__ void __launch_bounds__(DC_WARPS * 32, MINB)
     k_dc_nodal(TM m, const double *__restrict__ sigma, const double *__restrict__ phi, double *__restrict__ y,
                int kchunk) {
+  // per-block row constants (all warps of a block share j0): cell rows j0-1 .. j0+RY-1
+  __shared__ double s_hy[RY + 1], s_qy[RY + 1];
+  const int j0 = blockIdx.y * RY;  // first output row
+  if (threadIdx.x < RY + 1) {
+    const int jc = j0 - 1 + (int)threadIdx.x;
+    const bool ok = (jc >= 0) && (jc < m.ny);
+    const double r = ok ? m.rhy[jc] : 0.0;
+    s_hy[threadIdx.x] = ok ? m.hy[jc] : 0.0;
+    s_qy[threadIdx.x] = 0.25 * r * r;
+  }
+  __syncthreads();
+
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const i64 nNx = m.nx + 1, nNy = m.ny + 1, nNz = m.nz + 1;
-  const i64 X0 = ((i64)blockIdx.x * DC_WARPS + warp) * DC_XOUT;
+  const int nx = (int)m.nx, ny = (int)m.ny, nz = (int)m.nz;
+  const int nNx = nx + 1, nNy = ny + 1, nNz = nz + 1;
+  const int X0 = (blockIdx.x * DC_WARPS + warp) * DC_XOUT;
   if (X0 >= nNx) return;
-  const i64 i = X0 + lane - 1;          // node column of this lane (lane 0 / 31 are halo)
-  const i64 j0 = (i64)blockIdx.y * RY;  // first output row
-  const i64 kb = (i64)blockIdx.z * kchunk;
-  const i64 ke = min(kb + (i64)kchunk, nNz);
+  const int i = X0 + lane - 1;          // node column of this lane (lane 0 / 31 are halo)
+  const int kb = blockIdx.z * kchunk;
+  const int ke = min(kb + kchunk, nNz);
 
   const bool node_ok = (i >= 0) && (i < nNx);
-  const bool cell_ok = (i >= 0) && (i < m.nx) && (lane < 31);  // lane 31's cells are never needed
-  const double hx = cell_ok ? __ldg(m.hx + i) : 0.0;
-  const double qx = cell_ok ? 0.25 * __ldg(m.rhx + i) : 0.0;
+  const bool cell_ok = (i >= 0) && (i < nx) && (lane < 31);  // lane 31's cells are never needed
+  const int ic = min(max(i, 0), nNx - 1), icc = min(max(i, 0), nx - 1);
+  const double hx = cell_ok ? __ldg(m.hx + icc) : 0.0;
+  const double rx = cell_ok ? __ldg(m.rhx + icc) : 0.0;
+  const double qx = 0.25 * rx * rx;
 
-  // row constants.  phi rows: j0-1 .. j0+RY  (RY+2);  cell rows: j0-1 .. j0+RY-1 (RY+1)
-  double hy[RY + 1], qy[RY + 1];
-  bool prow[RY + 2], crow[RY + 1];
+  // clamped in-plane offsets (elements) of the rows this lane reads
+  int offp[RY + 2], offc[RY + 1];
 #pragma unroll
-  for (int r = 0; r < RY + 2; ++r) prow[r] = node_ok && (j0 - 1 + r >= 0) && (j0 - 1 + r < nNy);
+  for (int r = 0; r < RY + 2; ++r) offp[r] = ic + nNx * min(max(j0 - 1 + r, 0), nNy - 1);
 #pragma unroll
-  for (int r = 0; r < RY + 1; ++r) {
-    const i64 jc = j0 - 1 + r;
-    const bool ok = (jc >= 0) && (jc < m.ny);
-    crow[r] = cell_ok && ok;
-    hy[r] = ok ? __ldg(m.hy + jc) : 0.0;
-    qy[r] = ok ? 0.25 * __ldg(m.rhy + jc) : 0.0;
-  }
+  for (int r = 0; r < RY + 1; ++r) offc[r] = icc + nx * min(max(j0 - 1 + r, 0), ny - 1);
 
-  const i64 pstride = nNx * nNy;     // node plane
-  const i64 cstride = m.nx * m.ny;   // cell layer
-  // pointers to row j0-1 of the current plane / layer (may be formally out of range; guarded)
-  const double *pphi = phi + i + nNx * (j0 - 1);
-  const double *psig = sigma + i + m.nx * (j0 - 1);
+  const i64 pstride = (i64)nNx * nNy;     // node plane
+  const i64 cstride = (i64)nx * ny;       // cell layer
 
-  double ph0[RY + 2], ph1[RY + 2];   // phi on planes k and k+1
-  double Ap[RY], Bp[RY + 1];         // layer k-1: hz * (y-pair of sigma hy), hz * (x-pair of sigma hx)
-  double fzp[RY];                    // z-flux between planes k-1 and k
+  double ph0[RY + 2], ph1[RY + 2], ph2[RY + 2];  // phi planes, roles rotate: k, k+1, (prefetched) k+2
+  double sgA[RY + 1], sgB[RY + 1], sgC[RY + 1];  // sigma layers, roles rotate: k, (prefetched) k+1
+  double Ap[RY], Bp[RY + 1];                      // layer k-1: y-pair / x-pair sums of V sigma
+  double fzp[RY];                                 // z-flux between planes k-1 and k
 
-  // ---- preamble: plane kb-1 / layer kb-1 ------------------------------------------------
+#define DC_LOAD_PLANE(dst, base)                                    \
+  _Pragma("unroll") for (int r = 0; r < RY + 2; ++r) dst[r] = __ldg((base) + offp[r]);
+#define DC_LOAD_LAYER(dst, base)                                    \
+  _Pragma("unroll") for (int r = 0; r < RY + 1; ++r) dst[r] = __ldg((base) + offc[r]);
+
+  // ---- preamble: plane kb-1 / layer kb-1 (clamped to 0 with zero thickness at the bottom) --------
   {
     const bool have = kb >= 1;
-    double phm[RY + 2], sg[RY + 1];
-#pragma unroll
-    for (int r = 0; r < RY + 2; ++r) {
-      phm[r] = (have && prow[r]) ? __ldg(pphi + (kb - 1) * pstride + r * nNx) : 0.0;
-      ph0[r] = prow[r] ? __ldg(pphi + kb * pstride + r * nNx) : 0.0;
-    }
-#pragma unroll
-    for (int r = 0; r < RY + 1; ++r) sg[r] = (have && crow[r]) ? __ldg(psig + (kb - 1) * cstride + r * m.nx) : 0.0;
-    const double hz = have ? __ldg(m.hz + kb - 1) : 0.0;
-    const double qz = have ? 0.25 * __ldg(m.rhz + kb - 1) : 0.0;
-    double p[RY + 1];
+    const int km = have ? kb - 1 : 0;
+    DC_LOAD_PLANE(ph1, phi + km * pstride);  // ph1 temporarily holds plane kb-1
+    DC_LOAD_PLANE(ph0, phi + kb * pstride);
+    DC_LOAD_LAYER(sgA, sigma + km * cstride);
+    const double hz = have ? __ldg(m.hz + km) : 0.0;
+    const double rz = have ? __ldg(m.rhz + km) : 0.0;
+    const double qz = 0.25 * rz * rz;
+    const double hxz = hx * hz;
+    double s[RY + 1], sl[RY + 1];
 #pragma unroll
     for (int r = 0; r < RY + 1; ++r) {
-      p[r] = sg[r] * hy[r];
-      const double t = sg[r] * hx;
-      const double tl = __shfl_up_sync(0xffffffffu, t, 1);
-      Bp[r] = hz * (tl + t);
+      s[r] = (sgA[r] * s_hy[r]) * hxz;
+      sl[r] = __shfl_up_sync(0xffffffffu, s[r], 1);
+      Bp[r] = sl[r] + s[r];
     }
 #pragma unroll
     for (int r = 0; r < RY; ++r) {
-      const double a = p[r] + p[r + 1];
-      Ap[r] = hz * a;
-      const double ha = hx * a;
-      const double hal = __shfl_up_sync(0xffffffffu, ha, 1);
-      const double wz = qz * (hal + ha);
-      fzp[r] = wz * (ph0[r + 1] - phm[r + 1]);
+      const double a = s[r] + s[r + 1];
+      const double al = sl[r] + sl[r + 1];
+      Ap[r] = a;
+      fzp[r] = (qz * (a + al)) * (ph0[r + 1] - ph1[r + 1]);
     }
   }
+  // plane kb+1 and layer kb (clamped), then running pointers for the prefetches
+  const double *pnext = phi + (i64)min(kb + 1, nNz - 1) * pstride;
+  const double *cnext = sigma + (i64)min(kb, nz - 1) * cstride;
+  DC_LOAD_PLANE(ph1, pnext);
+  DC_LOAD_LAYER(sgA, cnext);
+  double *py = y + ((i64)kb * pstride + ic + (i64)nNx * j0);
+  const bool writer = (lane >= 1) && (lane <= DC_XOUT) && node_ok;
 
   // ---- march ------------------------------------------------------------------------------
-  for (i64 k = kb; k < ke; ++k) {
-    const bool havep = (k + 1) < nNz;   // plane k+1 exists
-    const bool havec = k < m.nz;        // layer k exists
-    double sg[RY + 1];
-#pragma unroll
-    for (int r = 0; r < RY + 2; ++r) ph1[r] = (havep && prow[r]) ? __ldg(pphi + (k + 1) * pstride + r * nNx) : 0.0;
-#pragma unroll
-    for (int r = 0; r < RY + 1; ++r) sg[r] = (havec && crow[r]) ? __ldg(psig + k * cstride + r * m.nx) : 0.0;
-    const double hz = havec ? __ldg(m.hz + k) : 0.0;
-    const double qz = havec ? 0.25 * __ldg(m.rhz + k) : 0.0;
+  // One z-step.  P0/P1 = phi on planes k, k+1; P2 receives the prefetch of plane k+2;
+  // S0 = sigma on layer k; S1 receives the prefetch of layer k+1.  The caller rotates the
+  // roles (period 3) so that no register-to-register copies are needed.
+  auto step = [&](const double(&P0)[RY + 2], const double(&P1)[RY + 2], double(&P2)[RY + 2],
+                  const double(&S0)[RY + 1], double(&S1)[RY + 1], int k) __attribute__((always_inline)) {
+    if (k + 2 < nNz) pnext += pstride;   // clamped at the top plane / layer
+    if (k + 1 < nz) cnext += cstride;
+    DC_LOAD_PLANE(P2, pnext);
+    DC_LOAD_LAYER(S1, cnext);
 
-    double p[RY + 1], B[RY + 1], fy[RY + 1];
+    const bool havec = k < nz;        // layer k exists
+    const int kc = havec ? k : nz - 1;
+    const double hz = havec ? __ldg(m.hz + kc) : 0.0;
+    const double rz = havec ? __ldg(m.rhz + kc) : 0.0;
+    const double qz = 0.25 * rz * rz;
+    const double hxz = hx * hz;
+
+    double s[RY + 1], sl[RY + 1], fy[RY + 1];
 #pragma unroll
     for (int r = 0; r < RY + 1; ++r) {
-      p[r] = sg[r] * hy[r];
-      const double t = sg[r] * hx;
-      const double tl = __shfl_up_sync(0xffffffffu, t, 1);
-      B[r] = hz * (tl + t);
+      s[r] = (S0[r] * s_hy[r]) * hxz;                 // V sigma of cell (i, j0-1+r, k); 0 outside the mesh
+      sl[r] = __shfl_up_sync(0xffffffffu, s[r], 1);   // same for cell column i-1
+      const double b = sl[r] + s[r];
       // y-edge between node rows (j0-1+r) and (j0+r), bordered by cell row j0-1+r
-      const double wy = qy[r] * (Bp[r] + B[r]);
-      fy[r] = wy * (ph0[r + 1] - ph0[r]);
-      Bp[r] = B[r];
+      fy[r] = (s_qy[r] * (Bp[r] + b)) * (P0[r + 1] - P0[r]);
+      Bp[r] = b;
     }
 #pragma unroll
     for (int r = 0; r < RY; ++r) {
-      const double a = p[r] + p[r + 1];
-      const double A = hz * a;
+      const double a = s[r] + s[r + 1];
+      const double al = sl[r] + sl[r + 1];
       // x-edge from this lane's node to the next one, node row j0+r
-      const double wx = qx * (Ap[r] + A);
-      const double phr = __shfl_down_sync(0xffffffffu, ph0[r + 1], 1);
-      const double fx = wx * (phr - ph0[r + 1]);
+      const double phr = __shfl_down_sync(0xffffffffu, P0[r + 1], 1);
+      const double fx = (qx * (Ap[r] + a)) * (phr - P0[r + 1]);
       const double fxl = __shfl_up_sync(0xffffffffu, fx, 1);
-      Ap[r] = A;
+      Ap[r] = a;
       // z-edge from plane k to k+1
-      const double ha = hx * a;
-      const double hal = __shfl_up_sync(0xffffffffu, ha, 1);
-      const double wz = qz * (hal + ha);
-      const double fz = wz * (ph1[r + 1] - ph0[r + 1]);
+      const double fz = (qz * (a + al)) * (P1[r + 1] - P0[r + 1]);
       const double out = (fxl - fx) + (fy[r] - fy[r + 1]) + (fzp[r] - fz);
       fzp[r] = fz;
-      const i64 j = j0 + r;
-      if (lane >= 1 && lane <= DC_XOUT && node_ok && j < nNy) y[i + nNx * (j + nNy * k)] = out;
+      if (writer && (j0 + r) < nNy) py[r * nNx] = out;
     }
+    py += pstride;
+  };
+
+  int k = kb;
+  while (true) {
+    step(ph0, ph1, ph2, sgA, sgB, k);
+    if (++k >= ke) break;
+    step(ph1, ph2, ph0, sgB, sgC, k);
+    if (++k >= ke) break;
+    step(ph2, ph0, ph1, sgC, sgA, k);
+    if (++k >= ke) break;
+  }
+#undef DC_LOAD_PLANE
+#undef DC_LOAD_LAYER
+}
+
+// ---------------------------------------------------------------------------------------------
+// Variant "ring" (default): same math, but the phi planes / sigma layers are staged in shared
+// memory by the TMA engine (cp.async.bulk -> SASS UBLKCP; one instruction per row segment,
+// issued by a dedicated producer warp) in a DC_SLOTS-deep mbarrier ring, warp-specialised:
+//
+//   producer warp : for stage j = kb-2 .. ke-1: wait for the slot to be released, then issue one
+//                   bulk copy per in-range row of node plane j+1 (RY+2 rows) and cell layer j
+//                   (RY+1 rows); completion is counted in bytes on full[slot].
+//   consumer warps: z-step j waits on full[slot(j)], reads P1 = plane j+1 and sigma layer j from
+//                   stage j and P0 = plane j from stage j-1 with LDS, computes the fluxes (x
+//                   neighbours by warp shuffle), writes plane j, and releases stage j-1.
+//
+// A block spans up to DC_MAXW strips of 30 node columns (the whole row for nx <= 538), so the
+// consumers carry no global address arithmetic and no register prefetch buffers, and two stages
+// (~90 KB) of loads are in flight per SM independent of occupancy.
+//
+// Bulk copies need 16-byte aligned source, destination and size, but rows of the reference's
+// layout start at arbitrary 8-byte offsets ((n+1)*8-byte pitch).  Each row copy therefore starts
+// at the aligned-down address; with a shared-memory row pitch of the same parity as the global
+// pitch, every row of a stage lands at  base + lead + r*pitch + c  with ONE lead bit per stage.
+// Rows / planes outside the mesh are not copied at all: the tiles are zero-initialised, hold only
+// finite values, and everything outside the mesh is multiplied by a zero cell measure.
+// Requirement (dzb.h): the 8 bytes following the last element of phi / sigma are readable.
+// ---------------------------------------------------------------------------------------------
+constexpr int DC_SLOTS = 4;       // ring depth: stage j-1 and j in use, j+1 and j+2 in flight
+constexpr int DC_MAXCHUNK = 128;  // max z-planes per block (size of the hz table)
+
+// compile-time geometry of a block with NWC consumer warps; PARX = nx & 1
+template <int RY, int NWC, int PARX> struct DcRing {
+  static constexpr int RP = RY + 2, RC = RY + 1;
+  static constexpr int NCP = NWC * DC_XOUT + 2, NCC = NWC * DC_XOUT + 1;  // staged node / cell columns
+  // shared-memory row pitches (doubles), parity-matched to nNx = nx+1 and nx
+  static constexpr int PP = (NCP + 3) + ((((NCP + 3) & 1) != ((PARX + 1) & 1)) ? 1 : 0);
+  static constexpr int CP = (NCC + 3) + ((((NCC + 3) & 1) != PARX) ? 1 : 0);
+  static constexpr int REGP = (RP * PP + 4 + 1) & ~1, REGC = (RC * CP + 4 + 1) & ~1;
+  static constexpr int STAGE = REGP + REGC;
+  static constexpr size_t SMEM = (size_t)DC_SLOTS * STAGE * 8 + 2 * DC_SLOTS * 8 + 2 * RC * 8 + 2 * (DC_MAXCHUNK + 2) * 8;
+};
+
+template <int RY, int NWC, int PARX>
+__global__ void __launch_bounds__((NWC + 1) * 32, 1)
+    k_dc_nodal_ring(TM m, const double *__restrict__ sigma, const double *__restrict__ phi, double *__restrict__ y,
+                    int kchunk, int nwc) {
+  typedef DcRing<RY, NWC, PARX> G;
+  constexpr int RP = G::RP, RC = G::RC, S = DC_SLOTS, PP = G::PP, CP = G::CP;
+  static_assert(S == 4, "the consumer loop is unrolled over a ring of four slots");
+  extern __shared__ __align__(128) unsigned char dc_smem_raw[];
+  const int nx = (int)m.nx, ny = (int)m.ny, nz = (int)m.nz;
+  const int nNx = nx + 1, nNy = ny + 1, nNz = nz + 1;
+  double *tiles = reinterpret_cast<double *>(dc_smem_raw);               // [S][STAGE]
+  uint64_t *full = reinterpret_cast<uint64_t *>(tiles + S * G::STAGE);
+  uint64_t *empty = full + S;
+  double *s_hy = reinterpret_cast<double *>(empty + S);
+  double *s_qy = s_hy + RC;
+  double *s_hz = s_qy + RC;                 // [kchunk+1]: layers kb-1 .. ke-1 (0 outside the mesh)
+  double *s_qz = s_hz + (DC_MAXCHUNK + 2);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthreads = (nwc + 1) * 32;
+  const int j0 = blockIdx.y * RY;
+  const int Xb = blockIdx.x * (nwc * DC_XOUT);
+  const int kb = blockIdx.z * kchunk;
+  const int ke = min(kb + kchunk, nNz);
+  const int jfirst = kb - 2;  // first stage of this block
+
+  for (int t = tid; t < S * G::STAGE; t += nthreads) tiles[t] = 0.0;  // tiles only ever hold finite values
+  if (tid < RC) {
+    const int jc = j0 - 1 + tid;
+    const bool ok = (jc >= 0) && (jc < ny);
+    const double r = ok ? m.rhy[jc] : 0.0;
+    s_hy[tid] = ok ? m.hy[jc] : 0.0;
+    s_qy[tid] = 0.25 * r * r;
+  }
+  for (int t = tid; t <= ke - kb; t += nthreads) {
+    const int k = kb - 1 + t;
+    const bool ok = (k >= 0) && (k < nz);
+    const double r = ok ? m.rhz[k] : 0.0;
+    s_hz[t] = ok ? m.hz[k] : 0.0;
+    s_qz[t] = 0.25 * r * r;
+  }
+  if (tid == 0) {
+    for (int q = 0; q < S; ++q) {
+      mbar_init(&full[q], 1);
+      mbar_init(&empty[q], nwc);
+    }
+    fence_barrier_init();
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  const long long pstride = (long long)nNx * nNy, cstride = (long long)nx * ny;
+  const int cs = max(Xb - 1, 0);  // first staged column (nodes and cells)
+  // absolute element address (address / 8) of (column cs, virtual row j0-1, plane 0)
+  const long long pa0 = (long long)((unsigned long long)phi >> 3) + cs + (long long)nNx * (j0 - 1);
+  const long long ca0 = (long long)((unsigned long long)sigma >> 3) + cs + (long long)nx * (j0 - 1);
+  const int nq = ke - jfirst;  // stages / steps are numbered q = j - jfirst
+
+  if (warp == nwc) {
+    // ================= producer warp =================
+    if (lane == 0) {
+      const long long pend = (((long long)((unsigned long long)phi >> 3) + pstride * nNz) + 1) & ~1ll;
+      const long long cend = (((long long)((unsigned long long)sigma >> 3) + cstride * nz) + 1) & ~1ll;
+      const int ncp = nwc * DC_XOUT + 2, ncc = nwc * DC_XOUT + 1;
+      for (int q = 0; q < nq; ++q) {
+        const int jst = jfirst + q, slot = q % S, n = q / S;
+        if (n >= 1) mbar_wait(&empty[slot], (n - 1) & 1);
+        double *tp = tiles + slot * G::STAGE, *tc = tp + G::REGP;
+        const int pj = jst + 1, lj = jst;
+        const bool havep = (pj >= 0) && (pj < nNz), havel = (lj >= 0) && (lj < nz);
+        const long long pa = pa0 + pstride * pj, ca = ca0 + cstride * lj;
+        const int lead0p = (int)(pa & 1), lead0c = (int)(ca & 1);
+        long long src[RP + RC];
+        unsigned bytes[RP + RC];
+        unsigned total = 0;
 #pragma unroll
-    for (int r = 0; r < RY + 2; ++r) ph0[r] = ph1[r];
+        for (int r = 0; r < RP + RC; ++r) {
+          const bool isp = r < RP;
+          const int rr = isp ? r : r - RP;
+          const int jr = j0 - 1 + rr;
+          const bool on = isp ? (havep && jr >= 0 && jr < nNy) : (havel && jr >= 0 && jr < ny);
+          const long long A = isp ? pa + (long long)rr * nNx : ca + (long long)rr * nx;
+          const long long Aal = A & ~1ll;
+          long long nel = ((A - Aal) + (isp ? ncp : ncc) + 1) & ~1ll;
+          nel = min(nel, (isp ? pend : cend) - Aal);
+          src[r] = Aal;
+          bytes[r] = on ? (unsigned)(nel * 8) : 0u;
+          total += bytes[r];
+        }
+        mbar_arrive_expect_tx(&full[slot], total);
+#pragma unroll
+        for (int r = 0; r < RP + RC; ++r) {
+          if (bytes[r] == 0) continue;
+          const bool isp = r < RP;
+          const int rr = isp ? r : r - RP;
+          // row rr lands at  base + 2 + lead0 + rr*pitch  (minus its own lead: 16-byte aligned)
+          double *dst = isp ? tp + 2 + lead0p + rr * PP - (int)((pa + (long long)rr * nNx) & 1)
+                            : tc + 2 + lead0c + rr * CP - (int)((ca + (long long)rr * nx) & 1);
+          bulk_g2s(dst, reinterpret_cast<const void *>(src[r] << 3), bytes[r], &full[slot]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ================= consumer warps =================
+  const int i = Xb + warp * DC_XOUT + lane - 1;  // node column of this lane (lane 0 / 31 are halo)
+  const bool node_ok = (i >= 0) && (i < nNx);
+  const bool cell_ok = (i >= 0) && (i < nx) && (lane < 31);
+  const int icc = min(max(i, 0), nx - 1);
+  const double hx = cell_ok ? __ldg(m.hx + icc) : 0.0;
+  const double rx = cell_ok ? __ldg(m.rhx + icc) : 0.0;
+  const double qx = 0.25 * rx * rx;
+  const int c2 = i - cs + 2;  // shared-memory column of this lane for lead 0 (>= 1)
+  const bool writer = (lane >= 1) && (lane <= DC_XOUT) && node_ok;
+  const int pbP = (int)(pstride & 1), pbC = (int)(cstride & 1);
+  const int l0p = (int)(pa0 & 1), l0c = (int)(ca0 & 1);
+  unsigned wmask = 0;  // output rows that exist
+#pragma unroll
+  for (int r = 0; r < RY; ++r)
+    if (writer && (j0 + r) < nNy) wmask |= 1u << r;
+
+  double Ap[RY], Bp[RY + 1], fzp[RY];
+#pragma unroll
+  for (int r = 0; r < RY; ++r) Ap[r] = fzp[r] = 0.0;
+#pragma unroll
+  for (int r = 0; r < RY + 1; ++r) Bp[r] = 0.0;
+
+  double *py = y + ((long long)(kb - 1) * pstride + min(max(i, 0), nNx - 1) + (long long)nNx * j0);
+
+  // steps q = 1 .. nq-1 (z-plane j = jfirst + q); slots are static inside the 4x unrolled body
+  for (int qb = 0; qb < nq; qb += S) {
+    const unsigned par = (unsigned)(qb / S) & 1u;
+#pragma unroll
+    for (int u = 0; u < S; ++u) {
+      const int q = qb + u;
+      if (q == 0) continue;
+      if (q >= nq) break;
+      const int j = jfirst + q;
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int slot = u, slot_prev = (u + S - 1) % S;
+      mbar_wait(&full[slot], par);
+      // lead bits of the planes j (stage j-1), j+1 (stage j) and of layer j (stage j)
+      const int lp0 = (l0p + pbP * j) & 1, lp1 = (l0p + pbP * (j + 1)) & 1, lc = (l0c + pbC * j) & 1;
+      const double *tP0 = tiles + slot_prev * G::STAGE + (c2 + lp0);
+      const double *tP1 = tiles + slot * G::STAGE + (c2 + lp1);
+      const double *tS = tiles + slot * G::STAGE + G::REGP + (c2 + lc);
+      const double hz = s_hz[j - (kb - 1)], qz = s_qz[j - (kb - 1)];
+      const double hxz = hx * hz;
+
+      double P0[RP], s[RC], sl[RC], fy[RC];
+#pragma unroll
+      for (int r = 0; r < RP; ++r) P0[r] = tP0[r * PP];
+#pragma unroll
+      for (int r = 0; r < RC; ++r) {
+        s[r] = (tS[r * CP] * s_hy[r]) * hxz;            // V sigma of cell (i, j0-1+r, j); 0 outside the mesh
+        sl[r] = __shfl_up_sync(0xffffffffu, s[r], 1);   // same for cell column i-1
+        const double b = sl[r] + s[r];
+        fy[r] = (s_qy[r] * (Bp[r] + b)) * (P0[r + 1] - P0[r]);
+        Bp[r] = b;
+      }
+      const unsigned wm = (j >= kb) ? wmask : 0u;
+#pragma unroll
+      for (int r = 0; r < RY; ++r) {
+        const double a = s[r] + s[r + 1];
+        const double al = sl[r] + sl[r + 1];
+        const double phr = tP0[(r + 1) * PP + 1];
+        const double ph1 = tP1[(r + 1) * PP];
+        const double fx = (qx * (Ap[r] + a)) * (phr - P0[r + 1]);
+        const double fxl = __shfl_up_sync(0xffffffffu, fx, 1);
+        Ap[r] = a;
+        const double fz = (qz * (a + al)) * (ph1 - P0[r + 1]);
+        const double out = (fxl - fx) + (fy[r] - fy[r + 1]) + (fzp[r] - fz);
+        fzp[r] = fz;
+        if ((wm >> r) & 1u) py[r * nNx] = out;
+      }
+      py += pstride;
+      // the plane of stage j-1 is dead now: hand its slot back to the producer
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[slot_prev]);
+    }
   }
 }
 
 static int g_dc_ry = 4;
-static int g_dc_kchunk = 32;
+static int g_dc_kchunk = 64;
+static int g_dc_variant = 1;  // 0 = register marching, 1 = bulk-copy staged ring
 
 }  // namespace dzb
 
@@ -165,6 +415,41 @@ extern "C" void dzb_tune_dc(int ry, int kchunk) {
   if (ry == 2 || ry == 4 || ry == 8) g_dc_ry = ry;
   if (kchunk > 0) g_dc_kchunk = kchunk;
 }
+extern "C" void dzb_tune_dc_variant(int variant) { g_dc_variant = variant; }
+
+template <int RY, int NWC, int PARX>
+static int launch_dc_ring_t(const TM &m, const double *sigma, const double *phi, double *y, int kchunk, int xblocks,
+                            int nwc, cudaStream_t s) {
+  typedef DcRing<RY, NWC, PARX> G;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(k_dc_nodal_ring<RY, NWC, PARX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)G::SMEM) != cudaSuccess)
+      return -1;
+    attr_done = true;
+  }
+  const int nNy = (int)m.ny + 1, nNz = (int)m.nz + 1;
+  dim3 grid((unsigned)xblocks, (unsigned)((nNy + RY - 1) / RY), (unsigned)((nNz + kchunk - 1) / kchunk));
+  k_dc_nodal_ring<RY, NWC, PARX><<<grid, dim3((nwc + 1) * 32), G::SMEM, s>>>(m, sigma, phi, y, kchunk, nwc);
+  return 0;
+}
+
+constexpr int DC_NWC_BIG = 18, DC_NWC_SMALL = 6;
+
+static int launch_dc_ring(const TM &m, const double *sigma, const double *phi, double *y, int kchunk, cudaStream_t s) {
+  const int nNx = (int)m.nx + 1;
+  const int strips = (nNx + DC_XOUT - 1) / DC_XOUT;
+  const bool small = strips <= DC_NWC_SMALL;
+  const int maxw = small ? DC_NWC_SMALL : DC_NWC_BIG;
+  const int xblocks = (strips + maxw - 1) / maxw;
+  const int nwc = (strips + xblocks - 1) / xblocks;  // balanced consumer warps per block
+  kchunk = kchunk > DC_MAXCHUNK ? DC_MAXCHUNK : kchunk;
+  const int parx = (int)(m.nx & 1);
+  if (small) return parx ? launch_dc_ring_t<4, DC_NWC_SMALL, 1>(m, sigma, phi, y, kchunk, xblocks, nwc, s)
+                         : launch_dc_ring_t<4, DC_NWC_SMALL, 0>(m, sigma, phi, y, kchunk, xblocks, nwc, s);
+  return parx ? launch_dc_ring_t<4, DC_NWC_BIG, 1>(m, sigma, phi, y, kchunk, xblocks, nwc, s)
+              : launch_dc_ring_t<4, DC_NWC_BIG, 0>(m, sigma, phi, y, kchunk, xblocks, nwc, s);
+}
 
 extern "C" int dzb_tm_dc_nodal(const DzbTensorMesh *mm, const double *sigma, const double *phi, double *y,
                                void *stream) {
@@ -174,6 +459,10 @@ extern "C" int dzb_tm_dc_nodal(const DzbTensorMesh *mm, const double *sigma, con
   }
   TM m(*mm);
   const i64 nNx = m.nx + 1, nNy = m.ny + 1, nNz = m.nz + 1;
+  if (nNx * nNy >= (i64)1 << 31 || nNz >= (i64)1 << 30) {
+    set_error("dzb_tm_dc_nodal: a node plane must have fewer than 2^31 entries");
+    return -1;
+  }
   const i64 strips = (nNx + DC_XOUT - 1) / DC_XOUT;
   const int ry = g_dc_ry;
   int kchunk = g_dc_kchunk;
@@ -181,8 +470,12 @@ extern "C" int dzb_tm_dc_nodal(const DzbTensorMesh *mm, const double *sigma, con
             (unsigned)((nNz + kchunk - 1) / kchunk));
   dim3 block(DC_WARPS * 32);
   cudaStream_t s = (cudaStream_t)stream;
-  if (ry == 2) k_dc_nodal<2><<<grid, block, 0, s>>>(m, sigma, phi, y, kchunk);
-  else if (ry == 4) k_dc_nodal<4><<<grid, block, 0, s>>>(m, sigma, phi, y, kchunk);
-  else k_dc_nodal<8><<<grid, block, 0, s>>>(m, sigma, phi, y, kchunk);
+  if (g_dc_variant == 1 && m.ny >= 2 && m.nN() < ((i64)1 << 31)) {
+    if (launch_dc_ring(m, sigma, phi, y, kchunk, s) == 0) return check_launch("dzb_tm_dc_nodal");
+    cudaGetLastError();  // fall through to the register variant
+  }
+  if (ry == 2) k_dc_nodal<2, 6><<<grid, block, 0, s>>>(m, sigma, phi, y, kchunk);
+  else if (ry == 4) k_dc_nodal<4, 4><<<grid, block, 0, s>>>(m, sigma, phi, y, kchunk);
+  else k_dc_nodal<8, 2><<<grid, block, 0, s>>>(m, sigma, phi, y, kchunk);
   return check_launch("dzb_tm_dc_nodal");
 }

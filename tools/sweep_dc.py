@@ -31,8 +31,13 @@ for _ in range(10):
     b.copy_(phi)
 e1.record(); torch.cuda.synchronize()
 print("copy GB/s", 16.0 * mesh.nN / (e0.elapsed_time(e1) / 10 * 1e-3) / 1e9)
-for ry in (2, 4, 8):
-    for kc in (8, 16, 32, 64, 128, 513):
+lib.dzb_tune_dc_variant.argtypes = [ctypes.c_int]
+lib.dzb_tune_dc_variant.restype = None
+variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1]
+ref = None
+for variant, ry, kc in [(v, r, k) for v in variants for r in (2, 4, 8) for k in (16, 32, 64, 128)]:
+    if True:
+        lib.dzb_tune_dc_variant(variant)
         lib.dzb_tune_dc(ry, kc)
         for _ in range(3):
             A.apply_device(phi, out=out)
@@ -41,4 +46,7 @@ for ry in (2, 4, 8):
             A.apply_device(phi, out=out)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        print(f"ry={ry} kchunk={kc:4d}  {ms:.3f} ms  {mesh.nN/ms/1e6:.1f} Gdof/s  {alg/ms/1e6:.0f} GB/s  frac {alg/ms/1e6/6541.1:.3f}", flush=True)
+        if ref is None:
+            ref = out.clone()
+        err = float((out - ref).abs().max() / ref.abs().max())
+        print(f"v={variant} err={err:.1e} ry={ry} kchunk={kc:4d}  {ms:.3f} ms  {mesh.nN/ms/1e6:.1f} Gdof/s  {alg/ms/1e6:.0f} GB/s  frac {alg/ms/1e6/6541.1:.3f}", flush=True)
