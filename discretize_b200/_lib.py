@@ -51,6 +51,7 @@ SIGNATURES = {
     "dzb_tm_mass_tensor_csr_fill": [_MP, _I, _P, _P, _P, _P, _P],
     "dzb_tm_mass_deriv_apply": [_MP, _I, _I, _P, _D, _P, _I, _P, _P, _P],
     "dzb_tm_dc_nodal": [_MP, _P, _P, _P, _P],
+    "dzb_tm_dc_nodal_range": [_MP, _P, _P, _P, _L, _L, _P],
     "dzb_tm_maxwell": [_MP, _P, _P, _P, _P, _P],
     "dzb_interp_locate": [_P, _L, _P, _L, _P, _L, _P, _L, _L, _P, _P, _P],
     "dzb_interp_apply": [_P, _P, _P, _L, _P, _P, _P],

@@ -35,7 +35,7 @@ constexpr int DC_XOUT = 30;      // outputs per warp strip (lanes 1..30)
 template <int RY, int MINB>
 __global__ void __launch_bounds__(DC_WARPS * 32, MINB)
     k_dc_nodal(TM m, const double *__restrict__ sigma, const double *__restrict__ phi, double *__restrict__ y,
-               int kchunk) {
+               int kchunk, int k_begin, int k_end) {
   // per-block row constants (all warps of a block share j0): cell rows j0-1 .. j0+RY-1
   __shared__ double s_hy[RY + 1], s_qy[RY + 1];
   const int j0 = blockIdx.y * RY;  // first output row
@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(DC_WARPS * 32, MINB)
   const int X0 = (blockIdx.x * DC_WARPS + warp) * DC_XOUT;
   if (X0 >= nNx) return;
   const int i = X0 + lane - 1;          // node column of this lane (lane 0 / 31 are halo)
-  const int kb = blockIdx.z * kchunk;
-  const int ke = min(kb + kchunk, nNz);
+  const int kb = k_begin + blockIdx.z * kchunk;
+  const int ke = min(kb + kchunk, k_end);
 
   const bool node_ok = (i >= 0) && (i < nNx);
   const bool cell_ok = (i >= 0) && (i < nx) && (lane < 31);  // lane 31's cells are never needed
@@ -220,7 +220,7 @@ template <int RY, int NWC, int PARX> struct DcRing {
 template <int RY, int NWC, int PARX>
 __global__ void __launch_bounds__((NWC + 1) * 32, 1)
     k_dc_nodal_ring(TM m, const double *__restrict__ sigma, const double *__restrict__ phi, double *__restrict__ y,
-                    int kchunk, int nwc) {
+                    int kchunk, int nwc, int k_begin, int k_end) {
   typedef DcRing<RY, NWC, PARX> G;
   constexpr int RP = G::RP, RC = G::RC, S = DC_SLOTS, PP = G::PP, CP = G::CP;
   static_assert(S == 4, "the consumer loop is unrolled over a ring of four slots");
@@ -239,8 +239,8 @@ __global__ void __launch_bounds__((NWC + 1) * 32, 1)
   const int nthreads = (nwc + 1) * 32;
   const int j0 = blockIdx.y * RY;
   const int Xb = blockIdx.x * (nwc * DC_XOUT);
-  const int kb = blockIdx.z * kchunk;
-  const int ke = min(kb + kchunk, nNz);
+  const int kb = k_begin + blockIdx.z * kchunk;
+  const int ke = min(kb + kchunk, k_end);
   const int jfirst = kb - 2;  // first stage of this block
 
   for (int t = tid; t < S * G::STAGE; t += nthreads) tiles[t] = 0.0;  // tiles only ever hold finite values
@@ -419,7 +419,7 @@ extern "C" void dzb_tune_dc_variant(int variant) { g_dc_variant = variant; }
 
 template <int RY, int NWC, int PARX>
 static int launch_dc_ring_t(const TM &m, const double *sigma, const double *phi, double *y, int kchunk, int xblocks,
-                            int nwc, cudaStream_t s) {
+                            int nwc, int k_begin, int k_end, cudaStream_t s) {
   typedef DcRing<RY, NWC, PARX> G;
   static bool attr_done = false;
   if (!attr_done) {
@@ -428,15 +428,17 @@ static int launch_dc_ring_t(const TM &m, const double *sigma, const double *phi,
       return -1;
     attr_done = true;
   }
-  const int nNy = (int)m.ny + 1, nNz = (int)m.nz + 1;
-  dim3 grid((unsigned)xblocks, (unsigned)((nNy + RY - 1) / RY), (unsigned)((nNz + kchunk - 1) / kchunk));
-  k_dc_nodal_ring<RY, NWC, PARX><<<grid, dim3((nwc + 1) * 32), G::SMEM, s>>>(m, sigma, phi, y, kchunk, nwc);
+  const int nNy = (int)m.ny + 1;
+  dim3 grid((unsigned)xblocks, (unsigned)((nNy + RY - 1) / RY), (unsigned)((k_end - k_begin + kchunk - 1) / kchunk));
+  k_dc_nodal_ring<RY, NWC, PARX><<<grid, dim3((nwc + 1) * 32), G::SMEM, s>>>(m, sigma, phi, y, kchunk, nwc, k_begin,
+                                                                           k_end);
   return 0;
 }
 
 constexpr int DC_NWC_BIG = 18, DC_NWC_SMALL = 6;
 
-static int launch_dc_ring(const TM &m, const double *sigma, const double *phi, double *y, int kchunk, cudaStream_t s) {
+static int launch_dc_ring(const TM &m, const double *sigma, const double *phi, double *y, int kchunk, int k_begin,
+                          int k_end, cudaStream_t s) {
   const int nNx = (int)m.nx + 1;
   const int strips = (nNx + DC_XOUT - 1) / DC_XOUT;
   const bool small = strips <= DC_NWC_SMALL;
@@ -445,14 +447,15 @@ static int launch_dc_ring(const TM &m, const double *sigma, const double *phi, d
   const int nwc = (strips + xblocks - 1) / xblocks;  // balanced consumer warps per block
   kchunk = kchunk > DC_MAXCHUNK ? DC_MAXCHUNK : kchunk;
   const int parx = (int)(m.nx & 1);
-  if (small) return parx ? launch_dc_ring_t<4, DC_NWC_SMALL, 1>(m, sigma, phi, y, kchunk, xblocks, nwc, s)
-                         : launch_dc_ring_t<4, DC_NWC_SMALL, 0>(m, sigma, phi, y, kchunk, xblocks, nwc, s);
-  return parx ? launch_dc_ring_t<4, DC_NWC_BIG, 1>(m, sigma, phi, y, kchunk, xblocks, nwc, s)
-              : launch_dc_ring_t<4, DC_NWC_BIG, 0>(m, sigma, phi, y, kchunk, xblocks, nwc, s);
+  if (small)
+    return parx ? launch_dc_ring_t<4, DC_NWC_SMALL, 1>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s)
+                : launch_dc_ring_t<4, DC_NWC_SMALL, 0>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s);
+  return parx ? launch_dc_ring_t<4, DC_NWC_BIG, 1>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s)
+              : launch_dc_ring_t<4, DC_NWC_BIG, 0>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s);
 }
 
-extern "C" int dzb_tm_dc_nodal(const DzbTensorMesh *mm, const double *sigma, const double *phi, double *y,
-                               void *stream) {
+extern "C" int dzb_tm_dc_nodal_range(const DzbTensorMesh *mm, const double *sigma, const double *phi, double *y,
+                                     int64_t k_begin, int64_t k_end, void *stream) {
   if (!mm || mm->nx <= 0 || mm->ny <= 0 || mm->nz <= 0) {
     set_error("dzb_tm_dc_nodal: invalid mesh");
     return -1;
@@ -463,19 +466,34 @@ extern "C" int dzb_tm_dc_nodal(const DzbTensorMesh *mm, const double *sigma, con
     set_error("dzb_tm_dc_nodal: a node plane must have fewer than 2^31 entries");
     return -1;
   }
+  if (k_begin < 0 || k_end > nNz || k_begin > k_end) {
+    set_error("dzb_tm_dc_nodal_range: plane range outside [0, nz+1]");
+    return -1;
+  }
+  if (k_begin == k_end) return 0;
+  const int kb0 = (int)k_begin, ke0 = (int)k_end;
   const i64 strips = (nNx + DC_XOUT - 1) / DC_XOUT;
   const int ry = g_dc_ry;
   int kchunk = g_dc_kchunk;
-  dim3 grid((unsigned)((strips + DC_WARPS - 1) / DC_WARPS), (unsigned)((nNy + ry - 1) / ry),
-            (unsigned)((nNz + kchunk - 1) / kchunk));
-  dim3 block(DC_WARPS * 32);
   cudaStream_t s = (cudaStream_t)stream;
   if (g_dc_variant == 1 && m.ny >= 2 && m.nN() < ((i64)1 << 31)) {
-    if (launch_dc_ring(m, sigma, phi, y, kchunk, s) == 0) return check_launch("dzb_tm_dc_nodal");
+    if (launch_dc_ring(m, sigma, phi, y, kchunk, kb0, ke0, s) == 0) return check_launch("dzb_tm_dc_nodal");
     cudaGetLastError();  // fall through to the register variant
   }
-  if (ry == 2) k_dc_nodal<2, 6><<<grid, block, 0, s>>>(m, sigma, phi, y, kchunk);
-  else if (ry == 4) k_dc_nodal<4, 4><<<grid, block, 0, s>>>(m, sigma, phi, y, kchunk);
-  else k_dc_nodal<8, 2><<<grid, block, 0, s>>>(m, sigma, phi, y, kchunk);
+  dim3 grid((unsigned)((strips + DC_WARPS - 1) / DC_WARPS), (unsigned)((nNy + ry - 1) / ry),
+            (unsigned)((ke0 - kb0 + kchunk - 1) / kchunk));
+  dim3 block(DC_WARPS * 32);
+  if (ry == 2) k_dc_nodal<2, 6><<<grid, block, 0, s>>>(m, sigma, phi, y, kchunk, kb0, ke0);
+  else if (ry == 4) k_dc_nodal<4, 4><<<grid, block, 0, s>>>(m, sigma, phi, y, kchunk, kb0, ke0);
+  else k_dc_nodal<8, 2><<<grid, block, 0, s>>>(m, sigma, phi, y, kchunk, kb0, ke0);
   return check_launch("dzb_tm_dc_nodal");
+}
+
+extern "C" int dzb_tm_dc_nodal(const DzbTensorMesh *mm, const double *sigma, const double *phi, double *y,
+                               void *stream) {
+  if (!mm) {
+    set_error("dzb_tm_dc_nodal: invalid mesh");
+    return -1;
+  }
+  return dzb_tm_dc_nodal_range(mm, sigma, phi, y, 0, mm->nz + 1, stream);
 }

@@ -112,7 +112,7 @@ class Operator(LinearOperator):
         (self._dev_apply_t if transpose else self._dev_apply)(x, out)
         return out
 
-    def _apply_any(self, x, transpose):
+    def _apply_any(self, x, transpose, out=None):
         n_in = self.shape[0] if transpose else self.shape[1]
         is_torch = isinstance(x, torch.Tensor)
         if not is_torch:
@@ -123,16 +123,25 @@ class Operator(LinearOperator):
             if x.shape[0] != n_in:
                 raise ValueError(f"dimension mismatch: operator {self.shape}, input {tuple(x.shape)}")
             if is_torch and x.device.type == "cpu":
-                # host tensor in -> host tensor out (pinned in -> pinned out, async copies)
+                # host tensor in -> host tensor out; pinned buffers make both copies asynchronous DMA.
+                # `out` (a preallocated, ideally pinned, CPU tensor) avoids a page-locked allocation per call.
                 xd = x.to(device=cuda_device(), dtype=torch.float64, non_blocking=True).reshape(-1)
                 yd = self.apply_device(xd, transpose)
-                y = torch.empty(yd.shape, dtype=torch.float64, pin_memory=x.is_pinned())
-                y.copy_(yd, non_blocking=True)
+                y = out if out is not None else torch.empty(yd.shape, dtype=torch.float64, pin_memory=x.is_pinned())
+                y.reshape(-1).copy_(yd, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
-                return y.reshape(-1, 1) if x.ndim == 2 else y
+                return y.reshape(-1, 1) if (x.ndim == 2 and out is None) else y
             xd = to_device(x).reshape(-1)
+            if is_torch and out is not None:
+                return self.apply_device(xd, transpose, out=out)
             yd = self.apply_device(xd, transpose)
-            y = yd if is_torch else yd.cpu().numpy()
+            if is_torch:
+                y = yd
+            elif out is not None:
+                torch.from_numpy(out.reshape(-1)).copy_(yd)
+                return out
+            else:
+                y = yd.cpu().numpy()
             return y.reshape(-1, 1) if x.ndim == 2 else y
         if x.ndim == 2 and x.shape[0] == n_in:
             xd = to_device(x)
@@ -143,11 +152,13 @@ class Operator(LinearOperator):
         raise ValueError(f"dimension mismatch: operator {self.shape}, input {tuple(x.shape)}")
 
     # -- public LinearOperator surface ----------------------------------------------------------
-    def matvec(self, x):
-        return self._apply_any(x, False)
+    def matvec(self, x, out=None):
+        """y = A x.  numpy in -> numpy out, CUDA tensor in -> CUDA tensor out, CPU tensor in -> CPU tensor
+        out.  ``out`` optionally receives the result (same kind as ``x``)."""
+        return self._apply_any(x, False, out)
 
-    def rmatvec(self, x):
-        return self._apply_any(x, True)
+    def rmatvec(self, x, out=None):
+        return self._apply_any(x, True, out)
 
     def matmat(self, X):
         return self._apply_any(X, False)

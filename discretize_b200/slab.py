@@ -1,0 +1,136 @@
+"""z-slab decomposition of TensorMesh operators across the GPUs of one box.
+
+One process per GPU (``torch.distributed``, NCCL over NVLink/NVSwitch).  A TensorMesh shards
+naturally in z: rank p owns the cell layers ``[c0, c1)`` and the node planes ``[c0, c1)`` (the
+last rank also owns the top plane ``nz``), x and y stay whole so that rows remain contiguous.
+The only data-path communication of an apply is one nearest-neighbour exchange of boundary
+planes (``send/recv`` pairs, no collective); static cell models exchange their halo layer once
+at construction.
+
+The local problem of a rank is itself a TensorMesh (its layers plus one halo layer per
+neighbour), so the single-GPU kernels run unchanged on it; ``dzb_tm_dc_nodal_range`` restricts
+the output to the owned planes and lets interior planes be computed while halos are in flight.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def slab_bounds(nz: int, world: int, rank: int):
+    """Cell layers [c0, c1) owned by ``rank`` (balanced, contiguous)."""
+    base, rem = divmod(nz, world)
+    c0 = rank * base + min(rank, rem)
+    return c0, c0 + base + (1 if rank < rem else 0)
+
+
+class SlabLayout:
+    """Index bookkeeping of one rank's z-slab (pure host logic, no device needed)."""
+
+    def __init__(self, nx, ny, nz, rank, world):
+        if world > nz:
+            raise ValueError("more ranks than cell layers")
+        self.nx, self.ny, self.nz, self.rank, self.world = nx, ny, nz, rank, world
+        self.c0, self.c1 = slab_bounds(nz, world, rank)
+        self.has_lower, self.has_upper = rank > 0, rank < world - 1
+        # local cell layers: owned + one halo layer below (for the node plane c0)
+        self.l0 = self.c0 - (1 if self.has_lower else 0)
+        self.l1 = self.c1
+        self.nz_local = self.l1 - self.l0
+        # local node planes l0 .. l1 (nz_local + 1 of them); owned ones:
+        self.p_own0 = self.c0 - self.l0
+        self.p_own1 = self.p_own0 + (self.c1 - self.c0) + (0 if self.has_upper else 1)
+        self.plane = (nx + 1) * (ny + 1)
+        self.layer = nx * ny
+
+    @property
+    def n_owned_nodes(self):
+        return (self.p_own1 - self.p_own0) * self.plane
+
+    def owned_node_slice(self):
+        """Slice of the GLOBAL nodal vector owned by this rank."""
+        g0 = self.c0
+        g1 = self.c1 + (0 if self.has_upper else 1)
+        return slice(g0 * self.plane, g1 * self.plane)
+
+
+def exchange_node_halos(local, layout: SlabLayout, group=None):
+    """Fill the halo node planes of ``local`` (shape [(nz_local+1) * plane]) from the neighbours.
+
+    Sends the lowest owned plane down and the highest owned plane up; receives the neighbours'
+    planes into the halo slots.  Works on CPU tensors (gloo) and CUDA tensors (NCCL).
+    """
+    P = layout.plane
+    ops = []
+    if layout.has_lower:
+        ops.append(dist.P2POp(dist.isend, local[layout.p_own0 * P:(layout.p_own0 + 1) * P], layout.rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, local[(layout.p_own0 - 1) * P:layout.p_own0 * P], layout.rank - 1, group))
+    if layout.has_upper:
+        ops.append(dist.P2POp(dist.isend, local[(layout.p_own1 - 1) * P:layout.p_own1 * P], layout.rank + 1, group))
+        ops.append(dist.P2POp(dist.irecv, local[layout.p_own1 * P:(layout.p_own1 + 1) * P], layout.rank + 1, group))
+    if not ops:
+        return []
+    return dist.batch_isend_irecv(ops)
+
+
+def plane_field(seed, k, n, device, log_normal=False):
+    """Plane k of a synthetic global field: identical for every decomposition (keyed by k)."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed) * 1000003 + int(k))
+    x = torch.randn(n, dtype=torch.float64, device=device, generator=gen)
+    return torch.exp(x) if log_normal else x
+
+
+class SlabDCNodal:
+    """y = G^T Me(sigma) G phi on a z-slab decomposed TensorMesh([nx, ny, nz]) (unit cube widths).
+
+    ``step()`` performs one distributed apply: halo exchange of phi (side stream) overlapped with
+    the interior planes, then the two boundary planes.
+    """
+
+    def __init__(self, nx, ny, nz, rank, world, seed_phi=5, seed_sigma=6, h=None):
+        import discretize_b200 as dz
+
+        self.layout = L = SlabLayout(nx, ny, nz, rank, world)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        hx, hy, hz = h if h is not None else (np.ones(nx) / nx, np.ones(ny) / ny, np.ones(nz) / nz)
+        self.mesh = dz.TensorMesh([np.asarray(hx), np.asarray(hy), np.asarray(hz)[L.l0:L.l1]])
+        # static model incl. its halo layer (generated locally here; a real model would be exchanged once)
+        self.sigma = torch.cat([plane_field(seed_sigma, k, L.layer, dev, log_normal=True) for k in range(L.l0, L.l1)])
+        self.phi = torch.zeros((L.nz_local + 1) * L.plane, dtype=torch.float64, device=dev)
+        for lp in range(L.p_own0, L.p_own1):
+            self.phi[lp * L.plane:(lp + 1) * L.plane] = plane_field(seed_phi, L.l0 + lp, L.plane, dev)
+        self.out = torch.zeros_like(self.phi)
+        G = self.mesh.nodal_gradient
+        self.op = G.T @ self.mesh.get_edge_inner_product(self.sigma) @ G
+        self.comm_stream = torch.cuda.Stream(device=dev)
+        self.launches_per_step = 3 if world > 1 else 1
+
+    def step(self):
+        L, op = self.layout, self.op
+        main = torch.cuda.current_stream()
+        if L.world == 1:
+            op.apply_planes(self.phi, self.out, L.p_own0, L.p_own1)
+            return self.out
+        # halo exchange on the side stream ...
+        self.comm_stream.wait_stream(main)
+        with torch.cuda.stream(self.comm_stream):
+            reqs = exchange_node_halos(self.phi, L)
+            for r in reqs:
+                r.wait()
+        # ... overlapped with the planes that do not touch a halo
+        lo = L.p_own0 + (1 if L.has_lower else 0)
+        hi = L.p_own1 - (1 if L.has_upper else 0)
+        if hi > lo:
+            op.apply_planes(self.phi, self.out, lo, hi)
+        main.wait_stream(self.comm_stream)
+        if L.has_lower and lo > L.p_own0:
+            op.apply_planes(self.phi, self.out, L.p_own0, min(lo, L.p_own1))
+        if L.has_upper and hi < L.p_own1 and hi >= lo:
+            op.apply_planes(self.phi, self.out, max(hi, lo), L.p_own1)
+        return self.out
+
+    def owned_output(self):
+        L = self.layout
+        return self.out[L.p_own0 * L.plane:L.p_own1 * L.plane]

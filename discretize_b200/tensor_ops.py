@@ -295,6 +295,11 @@ class DCNodalOperator(Operator):
 
     _dev_apply_t = _dev_apply
 
+    def apply_planes(self, x, out, k_begin, k_end):
+        """Write only node planes k_begin <= k < k_end of y = A x (z-slab building block)."""
+        check(load().dzb_tm_dc_nodal_range(C.byref(self.mesh.device_mesh()), ptr(self.sigma), ptr(x), ptr(out),
+                                           int(k_begin), int(k_end), stream_ptr()), "dzb_tm_dc_nodal_range")
+
     def _transpose(self):
         return self
 

@@ -111,12 +111,15 @@ int dzb_tm_mass_deriv_apply(const DzbTensorMesh *m, int flags, int model_kind, c
 /* ---- fused composites -------------------------------------------------------- */
 /* y = G^T Me(sigma) G phi  (DC resistivity, nodal; tutorials/pde/3_nodal_dirichlet_poisson.py:146-160):
  * nodal_gradient (:658-664) + get_edge_inner_product (isotropic sigma, nC) in ONE kernel.
- * Slab form for z-decomposition: the local mesh `m` holds cell layers [k0,k1) of a
- * global mesh; lower/upper != 0 say that the slab has a neighbour below/above, in
- * which case phi carries one extra node plane and sigma one extra cell layer on that
- * side (halo), and y is written for the owned planes only.  lower = upper = 0 is the
- * plain single-GPU operator. */
+ * The 8 bytes following the last element of phi and of sigma must be readable (true for any
+ * CUDA allocation; the kernel stages rows with 16-byte bulk copies). */
 int dzb_tm_dc_nodal(const DzbTensorMesh *m, const double *sigma, const double *phi, double *y, void *stream);
+/* Same, writing only the node planes k_begin <= k < k_end of y (0 <= k <= nz).  This is the
+ * building block of the z-slab decomposition: a rank applies it to its local sub-mesh (its cell
+ * layers plus one halo layer / node plane per neighbour) for the planes it owns, interior
+ * planes first while the halo planes are still in flight. */
+int dzb_tm_dc_nodal_range(const DzbTensorMesh *m, const double *sigma, const double *phi, double *y, int64_t k_begin,
+                          int64_t k_end, void *stream);
 
 /* y = C^T Mf(mui) C e + Me(sigma) e  (Maxwell, E-formulation;
  * tests/boundaries/test_boundary_maxwell.py:95-99): edge_curl (:2169-2181) +
