@@ -1,0 +1,542 @@
+"""TreeMesh (OcTree): the reference's names, connectivity rebuilt from scratch, CUDA operators.
+
+Drop-in for the operator-application part of ``discretize.TreeMesh`` in 3-D
+(reference: discretize/tree_mesh.py:106-270 and discretize/_extensions/tree_ext.pyx).
+
+* refinement (``insert_cells``, ``refine_ball``, ``refine_points``, ``refine``) runs on a linear
+  octree (``octree.py``); ``finalize()`` derives nodes / edges / faces, hanging entities and the
+  reference's numbering with array sort-unique passes (``tree_build.py``);
+* every operator is assembled ONCE on the host as "total operator x deflation" exactly like
+  tree_ext.pyx:3114-4762 (hanging faces -> parent, hanging edges -> mean of two parents, hanging
+  nodes -> mean of four listed parents, repeated until only non-hanging columns remain), then
+  uploaded as CSR with one byte per entry that encodes (multiplier, row-geometry selector):
+  the values are regenerated on the fly by the ``tree_spmv`` kernel from per-row geometry.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+from .octree import LinearOctree
+from .tensor_mesh import _ALIASES, as_array_n_by_dim, is_scalar, unpack_widths
+from .tree_build import TreeTopology, key3
+
+
+class TreeMeshNotFinalizedError(RuntimeError):
+    """reference: tree_ext.pyx:7071-7080."""
+
+
+_TREE_ALIASES = dict(_ALIASES)
+_TREE_ALIASES.update({
+    "ntN": "n_total_nodes", "ntEx": "n_total_edges_x", "ntEy": "n_total_edges_y", "ntEz": "n_total_edges_z",
+    "ntE": "n_total_edges", "ntFx": "n_total_faces_x", "ntFy": "n_total_faces_y", "ntFz": "n_total_faces_z",
+    "ntF": "n_total_faces", "nhN": "n_hanging_nodes", "nhEx": "n_hanging_edges_x", "nhEy": "n_hanging_edges_y",
+    "nhEz": "n_hanging_edges_z", "nhE": "n_hanging_edges", "nhFx": "n_hanging_faces_x", "nhFy": "n_hanging_faces_y",
+    "nhFz": "n_hanging_faces_z", "nhF": "n_hanging_faces",
+})
+
+
+class TreeMesh:
+    _meshType = "TREE"
+
+    def __init__(self, h=None, origin=None, diagonal_balance=None, **kwargs):
+        if "x0" in kwargs:
+            origin = kwargs.pop("x0")
+        if kwargs:
+            raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
+        if diagonal_balance is None:
+            diagonal_balance = False  # reference default (FutureWarning there: tree_mesh.py:246-256)
+        h = list(h)
+        if len(h) != 3:
+            raise NotImplementedError("discretize_b200.TreeMesh: only 3-D OcTrees have kernels")
+        for i, h_i in enumerate(h):
+            if is_scalar(h_i) and not isinstance(h_i, np.ndarray):
+                h_i = np.ones(int(h_i)) / int(h_i)
+            elif isinstance(h_i, (list, tuple)):
+                h_i = unpack_widths(list(h_i))
+            h[i] = np.array(h_i, dtype=np.float64)
+        self._h = tuple(h)
+        self._origin = np.zeros(3)
+        if origin is not None:
+            value = list(origin)
+            for i, (val, h_i) in enumerate(zip(value, self._h)):
+                if isinstance(val, str):
+                    value[i] = {"C": -h_i.sum() * 0.5, "N": -h_i.sum(), "0": 0.0}[val]
+            self._origin = np.asarray(value, dtype=np.float64)
+        self._tree = LinearOctree([x.size for x in self._h])  # raises for non powers of two
+        self._diagonal_balance = bool(diagonal_balance)
+        # half-step coordinate arrays (tree_ext.pyx:397-421)
+        self._xs = []
+        for a in range(3):
+            n = np.cumsum(np.r_[self._origin[a], self._h[a]])
+            x = np.empty(2 * self._h[a].size + 1)
+            x[::2] = n
+            x[1::2] = (x[:-1:2] + x[2::2]) / 2
+            self._xs.append(x)
+        self._finalized = False
+        self._topo = None
+        self._cache = {}
+        self._dev = {}
+
+    def __getattr__(self, name):
+        if name in _TREE_ALIASES:
+            return getattr(self, _TREE_ALIASES[name])
+        raise AttributeError(f"'{type(self).__name__}' object has no attribute '{name}'")
+
+    # ---- description ------------------------------------------------------------------------------
+    dim = 3
+    h = property(lambda self: self._h)
+    origin = property(lambda self: self._origin)
+    shape_cells = property(lambda self: tuple(int(x.size) for x in self._h))
+    max_level = property(lambda self: self._tree.max_level)
+    finalized = property(lambda self: self._finalized)
+
+    def _parse_level(self, level):
+        if level < 0:
+            level = (self.max_level + 1) - (abs(level) % (self.max_level + 1))
+        if level > self.max_level:
+            raise IndexError(f"Level beyond max octree level, {self.max_level}")
+        return level
+
+    def _require_open(self):
+        if self._finalized:
+            raise RuntimeError("the TreeMesh is finalized; it cannot be refined any more")
+
+    # ---- refinement ----------------------------------------------------------------------------------
+    def _cell_box(self, lo, w):
+        a = np.stack([self._xs[d][2 * lo[:, d]] for d in range(3)], axis=1)
+        b = np.stack([self._xs[d][2 * (lo[:, d] + w)] for d in range(3)], axis=1)
+        return a, b
+
+    def insert_cells(self, points, levels, finalize=True, diagonal_balance=None):
+        """reference: tree_ext.pyx:1158-1215 -> tree.cpp:383-396, 910-927."""
+        self._require_open()
+        points = as_array_n_by_dim(np.asarray(points, dtype=np.float64), 3)
+        levels = np.atleast_1d(np.asarray(levels, dtype=np.int64))
+        # The reference loops over ``levels`` (tree_ext.pyx:1205-1211): a single level with many points
+        # inserts only the FIRST point, and a single point with many levels inserts it at each level.
+        # Mirrored here so that the same calls give the same mesh.
+        if levels.size == 1:
+            points = points[:1]
+        elif points.shape[0] == 1:
+            points = np.repeat(points, levels.size, axis=0)
+        elif points.shape[0] != levels.size:
+            raise ValueError("points and levels have incompatible lengths")
+        levels = np.array([self._parse_level(int(l)) for l in levels], dtype=np.int64)
+        db = self._diagonal_balance if diagonal_balance is None else diagonal_balance
+        xs = self._xs
+
+        def concerns(req, lo, w):
+            # the reference descends by `x > centre of the parent` (ties go low), starting from the root
+            # found by `x >= root edge`: a cell is on the path iff, on every axis, its interval holds the
+            # point in that sense.  Points outside the mesh clamp to the boundary cells.
+            ok = np.ones(req.size, dtype=bool)
+            for d in range(3):
+                p = points[req, d]
+                a = xs[d][2 * lo[:, d]]
+                b = xs[d][2 * (lo[:, d] + w)]
+                first = lo[:, d] == 0
+                last = lo[:, d] + w == self.shape_cells[d]
+                hi_root = (lo[:, d] + w) % self._tree.rw == 0
+                ok &= ((p > a) | first | self._root_aligned_low(lo[:, d], p, a)) & ((p < b) | last | (~hi_root & (p == b)))
+            return ok
+
+        self._tree.refine_requests(points.shape[0], levels, concerns)
+        self._tree.balance(db)
+        if finalize:
+            self.finalize()
+
+    def _root_aligned_low(self, lo_d, p, a):
+        # root selection uses `p >= root low edge` (tree.cpp:914-925); inside a root the split uses `p > centre`
+        return (lo_d % self._tree.rw == 0) & (p == a)
+
+    def refine_ball(self, points, radii, levels, finalize=True, diagonal_balance=None):
+        """reference: tree_ext.pyx:561-648 -> tree.h:149-167 + geom.cpp:35-58 (Ball::intersects_cell)."""
+        self._require_open()
+        points = as_array_n_by_dim(np.asarray(points, dtype=np.float64), 3)
+        n = points.shape[0]
+        radii = np.broadcast_to(np.atleast_1d(np.asarray(radii, dtype=np.float64)), (n,)).copy()
+        levels = np.atleast_1d(np.asarray(levels, dtype=np.int64))
+        if levels.size == 1:
+            levels = np.full(n, levels[0])
+        levels = np.array([self._parse_level(int(l)) for l in levels], dtype=np.int64)
+        db = self._diagonal_balance if diagonal_balance is None else diagonal_balance
+        rsq = radii * radii
+
+        def concerns(req, lo, w):
+            a, b = self._cell_box(lo, w)
+            x0 = points[req]
+            dx = np.maximum(a, np.minimum(x0, b)) - x0
+            return (dx * dx).sum(axis=1) < rsq[req]
+
+        self._tree.refine_requests(n, levels, concerns)
+        self._tree.balance(db)
+        if finalize:
+            self.finalize()
+
+    def refine_points(self, points, level=-1, padding_cells_by_level=None, finalize=True, diagonal_balance=None):
+        """reference: tree_mesh.py:548-636."""
+        level = self._parse_level(level)
+        if padding_cells_by_level is None:
+            padding_cells_by_level = np.array([0])
+        padding_cells_by_level = np.asarray(padding_cells_by_level)
+        if padding_cells_by_level.ndim == 0 and level > 1:
+            padding_cells_by_level = np.full(level - 1, padding_cells_by_level)
+        padding_cells_by_level = np.atleast_1d(padding_cells_by_level)
+        h_min = np.max([h.min() for h in self.h])
+        radius_at_level = 0.0
+        for lv, n_pad in zip(np.arange(level, 1, -1), padding_cells_by_level):
+            radius_at_level += n_pad * h_min * 2 ** (self.max_level - lv)
+            if radius_at_level == 0:
+                self.insert_cells(points, lv, finalize=False, diagonal_balance=diagonal_balance)
+            else:
+                self.refine_ball(points, radius_at_level, lv, finalize=False, diagonal_balance=diagonal_balance)
+        if finalize:
+            self.finalize()
+
+    def refine(self, function, finalize=True, diagonal_balance=None):
+        """Refine to a constant level (int) or to ``function(cell_centers) -> levels`` (vectorised)."""
+        self._require_open()
+        db = self._diagonal_balance if diagonal_balance is None else diagonal_balance
+        t = self._tree
+        while True:
+            w = t.width(t.lvl)
+            if callable(function):
+                c = np.stack([self._xs[d][2 * t.lo[:, d] + w] for d in range(3)], axis=1)
+                want = np.asarray(function(c), dtype=np.int64)
+            else:
+                want = np.full(t.lvl.size, self._parse_level(int(function)), dtype=np.int64)
+            mask = (want > t.lvl) & (t.lvl < t.max_level)
+            if not mask.any():
+                break
+            t.split(mask)
+        t.balance(db)
+        if finalize:
+            self.finalize()
+
+    def _set_state(self, indexes, levels):
+        """Rebuild from (cell-centre half-step locations, levels), like __setstate__ (tree_ext.pyx:6488-6507)."""
+        self._require_open()
+        indexes = np.asarray(indexes, dtype=np.int64)
+        levels = np.asarray(levels, dtype=np.int64)
+        w = self._tree.width(levels)
+        self._tree.lo = (indexes - w[:, None]) // 2
+        self._tree.lvl = levels.copy()
+        self._tree.sort()
+
+    @property
+    def cell_state(self):
+        idx, lv = self._tree.state()
+        return {"indexes": idx.tolist(), "levels": lv.tolist()}
+
+    def finalize(self):
+        """reference: tree_ext.pyx:1266-1279 -> tree.cpp:949-1451."""
+        if self._finalized:
+            return
+        centers, levels = self._tree.state()
+        half = self._tree.width(levels)
+        self._levels = levels
+        self._topo = TreeTopology(centers, half, [2 * n for n in self.shape_cells])
+        self._finalized = True
+
+    def _t(self):
+        if not self._finalized:
+            raise TreeMeshNotFinalizedError("TreeMesh must be finalized before this property is available")
+        return self._topo
+
+    # ---- counts (tree_ext.pyx:1649-2019) ------------------------------------------------------------------
+    n_cells = property(lambda self: self._t().n_cells)
+    n_nodes = property(lambda self: self._t().nodes.n)
+    n_total_nodes = property(lambda self: self._t().nodes.n_total)
+    n_hanging_nodes = property(lambda self: self._t().nodes.n_hanging)
+    n_edges_x = property(lambda self: self._t().edges[0].n)
+    n_edges_y = property(lambda self: self._t().edges[1].n)
+    n_edges_z = property(lambda self: self._t().edges[2].n)
+    n_total_edges_x = property(lambda self: self._t().edges[0].n_total)
+    n_total_edges_y = property(lambda self: self._t().edges[1].n_total)
+    n_total_edges_z = property(lambda self: self._t().edges[2].n_total)
+    n_hanging_edges_x = property(lambda self: self._t().edges[0].n_hanging)
+    n_hanging_edges_y = property(lambda self: self._t().edges[1].n_hanging)
+    n_hanging_edges_z = property(lambda self: self._t().edges[2].n_hanging)
+    n_faces_x = property(lambda self: self._t().faces[0].n)
+    n_faces_y = property(lambda self: self._t().faces[1].n)
+    n_faces_z = property(lambda self: self._t().faces[2].n)
+    n_total_faces_x = property(lambda self: self._t().faces[0].n_total)
+    n_total_faces_y = property(lambda self: self._t().faces[1].n_total)
+    n_total_faces_z = property(lambda self: self._t().faces[2].n_total)
+    n_hanging_faces_x = property(lambda self: self._t().faces[0].n_hanging)
+    n_hanging_faces_y = property(lambda self: self._t().faces[1].n_hanging)
+    n_hanging_faces_z = property(lambda self: self._t().faces[2].n_hanging)
+    n_edges = property(lambda self: sum(e.n for e in self._t().edges))
+    n_faces = property(lambda self: sum(f.n for f in self._t().faces))
+    n_total_edges = property(lambda self: sum(e.n_total for e in self._t().edges))
+    n_total_faces = property(lambda self: sum(f.n_total for f in self._t().faces))
+    n_hanging_edges = property(lambda self: sum(e.n_hanging for e in self._t().edges))
+    n_hanging_faces = property(lambda self: sum(f.n_hanging for f in self._t().faces))
+    n_edges_per_direction = property(lambda self: tuple(e.n for e in self._t().edges))
+    n_faces_per_direction = property(lambda self: tuple(f.n for f in self._t().faces))
+
+    @property
+    def cell_levels_by_index(self):
+        self._t()
+        return self._levels.copy()
+
+    # ---- geometry (tree.cpp:61-84, 109-136, 176-230; tree_ext.pyx:2021-2722) ---------------------------------
+    def _coords(self, loc):
+        return np.stack([self._xs[d][loc[:, d]] for d in range(3)], axis=1)
+
+    def _extent(self, loc, half, d):
+        return self._xs[d][loc[:, d] + half] - self._xs[d][loc[:, d] - half]
+
+    def _midpoints(self, loc, half, axes):
+        """Entity locations as the reference computes them: the mean of the corner coordinates
+        (tree.cpp:73-75, 122-124) -- not the coordinate at the middle index when h is non-uniform."""
+        out = self._coords(loc)
+        for d in axes:
+            out[:, d] = (self._xs[d][loc[:, d] - half] + self._xs[d][loc[:, d] + half]) * 0.5
+        return out
+
+    @property
+    def cell_centers(self):
+        t = self._t()
+        return self._midpoints(t.centers, t.half, (0, 1, 2))
+
+    @property
+    def h_gridded(self):
+        t = self._t()
+        return np.stack([self._extent(t.centers, t.half, d) for d in range(3)], axis=1)
+
+    @property
+    def cell_volumes(self):
+        hg = self.h_gridded
+        return (hg[:, 0] * hg[:, 1]) * hg[:, 2]
+
+    def _numbered(self, fam, values, include_hanging):
+        out = np.empty(fam.n_total)
+        out[fam.index] = values
+        return out if include_hanging else out[:fam.n]
+
+    def _edge_lengths_total(self, d):
+        e = self._t().edges[d]
+        return self._extent(e.loc, e.half, d)
+
+    def _face_areas_total(self, d):
+        f = self._t().faces[d]
+        t1, t2 = [a for a in range(3) if a != d]
+        return self._extent(f.loc, f.half, t1) * self._extent(f.loc, f.half, t2)
+
+    @property
+    def edge_lengths(self):
+        t = self._t()
+        return np.concatenate([self._numbered(t.edges[d], self._edge_lengths_total(d), False) for d in range(3)])
+
+    @property
+    def face_areas(self):
+        t = self._t()
+        return np.concatenate([self._numbered(t.faces[d], self._face_areas_total(d), False) for d in range(3)])
+
+    def _face_locations(self, fam, axes):
+        """(p1+p2+p3+p4)*0.25 in the reference's corner order (tree.cpp:109-124)."""
+        out = self._coords(fam.loc)
+        t1, t2 = axes
+        a1, b1 = self._xs[t1][fam.loc[:, t1] - fam.half], self._xs[t1][fam.loc[:, t1] + fam.half]
+        a2, b2 = self._xs[t2][fam.loc[:, t2] - fam.half], self._xs[t2][fam.loc[:, t2] + fam.half]
+        out[:, t1] = (((a1 + b1) + a1) + b1) * 0.25
+        out[:, t2] = (((a2 + a2) + b2) + b2) * 0.25
+        return out
+
+    def _grid(self, fam, include_hanging=False, axes=()):
+        if len(axes) == 2:
+            c = self._face_locations(fam, axes)
+        else:
+            c = self._midpoints(fam.loc, fam.half, axes) if axes else self._coords(fam.loc)
+        out = np.empty_like(c)
+        out[fam.index] = c
+        return out if include_hanging else out[:fam.n]
+
+    nodes = property(lambda self: self._grid(self._t().nodes))
+    hanging_nodes = property(lambda self: self._grid(self._t().nodes, True)[self._t().nodes.n:])
+    edges_x = property(lambda self: self._grid(self._t().edges[0], axes=(0,)))
+    edges_y = property(lambda self: self._grid(self._t().edges[1], axes=(1,)))
+    edges_z = property(lambda self: self._grid(self._t().edges[2], axes=(2,)))
+    faces_x = property(lambda self: self._grid(self._t().faces[0], axes=(1, 2)))
+    faces_y = property(lambda self: self._grid(self._t().faces[1], axes=(0, 2)))
+    faces_z = property(lambda self: self._grid(self._t().faces[2], axes=(0, 1)))
+
+    # ---- host assembly of the operators (once per mesh) ---------------------------------------------------------
+    def _deflate(self, fam, parents, weights):
+        """R (n_total x n): identity on non-hanging, parent weights on hanging rows, applied until no
+        hanging columns remain (tree_ext.pyx:3855-4087)."""
+        nt, n = fam.n_total, fam.n
+        hang = np.nonzero(fam.hanging)[0]
+        rows = [fam.index[~fam.hanging]]
+        cols = [fam.index[~fam.hanging]]
+        vals = [np.ones(n)]
+        for k, wgt in enumerate(weights):
+            rows.append(fam.index[hang])
+            cols.append(fam.index[parents[hang, k] if parents.ndim == 2 else parents[hang]])
+            vals.append(np.full(hang.size, wgt))
+        Rh = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nt, nt))
+        R = Rh
+        while R[:, n:].nnz:
+            R = (R @ Rh).tocsr()
+        return R[:, :n].tocsr()
+
+    def _deflate_faces(self):
+        if "Rf" not in self._cache:
+            t = self._t()
+            self._cache["Rf"] = sp.block_diag([self._deflate(t.faces[d], t.face_parents[d], [1.0]) for d in range(3)]).tocsr()
+        return self._cache["Rf"]
+
+    def _deflate_edges(self):
+        if "Re" not in self._cache:
+            t = self._t()
+            self._cache["Re"] = sp.block_diag([self._deflate(t.edges[d], t.edge_parents[d], [0.5, 0.5]) for d in range(3)]).tocsr()
+        return self._cache["Re"]
+
+    def _deflate_nodes(self):
+        if "Rn" not in self._cache:
+            t = self._t()
+            self._cache["Rn"] = self._deflate(t.nodes, t.node_parents, [0.25] * 4)
+        return self._cache["Rn"]
+
+    def _host_matrix(self, name):
+        """scipy CSR of a reference operator (canonical form)."""
+        key = "H_" + name
+        if key in self._cache:
+            return self._cache[key]
+        t = self._t()
+        nC = t.n_cells
+        ntF = [f.n_total for f in t.faces]
+        ntE = [e.n_total for e in t.edges]
+        offF = np.r_[0, np.cumsum(ntF)]
+        offE = np.r_[0, np.cumsum(ntE)]
+        cells = np.arange(nC)
+        if name == "face_divergence":  # tree_ext.pyx:3199-3234
+            V = self.cell_volumes
+            rows, cols, vals = [], [], []
+            for d in range(3):
+                A = self._face_areas_total(d)
+                for s, sign in ((0, -1.0), (1, 1.0)):
+                    pos = t.cell_faces[d][:, s]
+                    rows.append(cells); cols.append(offF[d] + t.faces[d].index[pos]); vals.append(sign * A[pos] / V)
+            M = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nC, offF[3]))
+            M = M @ self._deflate_faces()
+        elif name == "edge_curl":  # tree_ext.pyx:3236-3359
+            nF = [f.n for f in t.faces]
+            offFn = np.r_[0, np.cumsum(nF)]
+            unit = np.eye(3, dtype=np.int64)
+            rows, cols, vals = [], [], []
+            for d in range(3):
+                f = t.faces[d]
+                nh = np.nonzero(~f.hanging)[0]
+                area = self._face_areas_total(d)[nh]
+                a1, a2 = (d + 1) % 3, (d + 2) % 3   # (curl e)_d = d_{a1} e_{a2} - d_{a2} e_{a1}
+                for (de, dt, sgn) in ((a2, a1, 1.0), (a1, a2, -1.0)):
+                    e = t.edges[de]
+                    L = self._edge_lengths_total(de)
+                    for s in (-1, 1):
+                        q = f.loc[nh] + s * f.half[nh, None] * unit[dt]
+                        pos = np.searchsorted(e.keys, key3(q[:, 0], q[:, 1], q[:, 2]))
+                        rows.append(offFn[d] + f.index[nh]); cols.append(offE[de] + e.index[pos])
+                        vals.append(sgn * s * L[pos] / area)
+            M = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(offFn[3], offE[3]))
+            M = M @ self._deflate_edges()
+        elif name == "nodal_gradient":  # tree_ext.pyx:3361-3464
+            nE = [e.n for e in t.edges]
+            offEn = np.r_[0, np.cumsum(nE)]
+            unit = np.eye(3, dtype=np.int64)
+            rows, cols, vals = [], [], []
+            for d in range(3):
+                e = t.edges[d]
+                nh = np.nonzero(~e.hanging)[0]
+                L = self._edge_lengths_total(d)[nh]
+                for s in (-1, 1):
+                    q = e.loc[nh] + s * e.half[nh, None] * unit[d]
+                    pos = np.searchsorted(t.nodes.keys, key3(q[:, 0], q[:, 1], q[:, 2]))
+                    rows.append(offEn[d] + e.index[nh]); cols.append(t.nodes.index[pos]); vals.append(s / L)
+            M = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(offEn[3], t.nodes.n_total))
+            M = M @ self._deflate_nodes()
+        elif name in ("average_face_to_cell", "average_face_to_cell_vector") or name.startswith("average_face_"):
+            M = self._host_average(name, t.faces, t.cell_faces, offF, self._deflate_faces(), 0.5)
+        elif name in ("average_edge_to_cell", "average_edge_to_cell_vector") or name.startswith("average_edge_"):
+            M = self._host_average(name, t.edges, t.cell_edges, offE, self._deflate_edges(), 0.25)
+        elif name == "average_node_to_cell":  # tree_ext.pyx:4709-4762
+            rows = np.repeat(cells, 8)
+            cols = t.nodes.index[t.cell_nodes.reshape(-1)]
+            M = sp.csr_matrix((np.full(rows.size, 0.125), (rows, cols)), shape=(nC, t.nodes.n_total)) @ self._deflate_nodes()
+        else:
+            raise AttributeError(name)
+        M = sp.csr_matrix(M)
+        M.sum_duplicates()
+        M.sort_indices()
+        self._cache[key] = M
+        return M
+
+    def _host_average(self, name, fams, cell_ents, off, R, w):
+        """tree_ext.pyx:4089-4707: per cell 2 faces x 1/2 (4 edges x 1/4) per direction, then deflation."""
+        t = self._t()
+        nC = t.n_cells
+        cells = np.arange(nC)
+        k = cell_ents[0].shape[1]
+        blocks = []
+        for d in range(3):
+            rows = np.repeat(cells, k)
+            cols = fams[d].index[cell_ents[d].reshape(-1)] + off[d]
+            blocks.append(sp.csr_matrix((np.full(rows.size, w), (rows, cols)), shape=(nC, off[3])))
+        comp = {"x": 0, "y": 1, "z": 2}
+        if name.endswith("_to_cell_vector"):
+            M = sp.vstack(blocks) @ R
+        elif name.endswith("_x_to_cell") or name.endswith("_y_to_cell") or name.endswith("_z_to_cell"):
+            d = comp[name[-9]]
+            n_nh = [f.n for f in fams]
+            o = np.r_[0, np.cumsum(n_nh)]
+            M = (blocks[d] @ R)[:, o[d]:o[d + 1]]
+        else:
+            M = (1.0 / 3.0) * (blocks[0] + blocks[1] + blocks[2]) @ R
+        return M
+
+    # ---- operators -------------------------------------------------------------------------------------------
+    def _operator(self, name):
+        key = "OP_" + name
+        if key not in self._cache:
+            from .tree_ops import TreeOperator
+
+            self._cache[key] = TreeOperator(self, name)
+        return self._cache[key]
+
+    face_divergence = property(lambda self: self._operator("face_divergence"))
+    edge_curl = property(lambda self: self._operator("edge_curl"))
+    nodal_gradient = property(lambda self: self._operator("nodal_gradient"))
+    average_face_to_cell = property(lambda self: self._operator("average_face_to_cell"))
+    average_face_to_cell_vector = property(lambda self: self._operator("average_face_to_cell_vector"))
+    average_face_x_to_cell = property(lambda self: self._operator("average_face_x_to_cell"))
+    average_face_y_to_cell = property(lambda self: self._operator("average_face_y_to_cell"))
+    average_face_z_to_cell = property(lambda self: self._operator("average_face_z_to_cell"))
+    average_edge_to_cell = property(lambda self: self._operator("average_edge_to_cell"))
+    average_edge_to_cell_vector = property(lambda self: self._operator("average_edge_to_cell_vector"))
+    average_edge_x_to_cell = property(lambda self: self._operator("average_edge_x_to_cell"))
+    average_edge_y_to_cell = property(lambda self: self._operator("average_edge_y_to_cell"))
+    average_edge_z_to_cell = property(lambda self: self._operator("average_edge_z_to_cell"))
+    average_node_to_cell = property(lambda self: self._operator("average_node_to_cell"))
+
+    # ---- mass matrices (shared _fastInnerProduct: base/base_tensor_mesh.py:792-863) -----------------------------
+    def get_face_inner_product(self, model=None, invert_model=False, invert_matrix=False, do_fast=True, **kwargs):
+        return self._inner_product("F", model, invert_model, invert_matrix, do_fast, kwargs)
+
+    def get_edge_inner_product(self, model=None, invert_model=False, invert_matrix=False, do_fast=True, **kwargs):
+        return self._inner_product("E", model, invert_model, invert_matrix, do_fast, kwargs)
+
+    def _inner_product(self, proj, model, invert_model, invert_matrix, do_fast, kwargs):
+        from .tensor_mesh import TensorMesh
+        from .tree_ops import make_tree_mass_operator
+
+        TensorMesh._check_removed_kwargs(kwargs)
+        return make_tree_mass_operator(self, proj, model, invert_model, invert_matrix)
+
+    def get_interpolation_matrix(self, loc, location_type="cell_centers", zeros_outside=False, **kwargs):
+        raise NotImplementedError("TreeMesh.get_interpolation_matrix is not part of the five target configurations (SURVEY N3)")
+
+    def __repr__(self):
+        n = self._topo.n_cells if self._finalized else self._tree.lvl.size
+        return f"<discretize_b200.TreeMesh {n} cells, max_level {self.max_level}>"
