@@ -8,8 +8,9 @@ Keeps the reference's property and method names (``face_divergence``, ``edge_cur
 sm_100a CUDA kernels behind the C ABI in ``include/dzb.h``.
 """
 from .tensor_mesh import TensorMesh
+from .tree_mesh import TreeMesh, TreeMeshNotFinalizedError
 from .operators import Operator
 from ._lib import DzbError
 
-__all__ = ["TensorMesh", "Operator", "DzbError"]
+__all__ = ["TensorMesh", "TreeMesh", "TreeMeshNotFinalizedError", "Operator", "DzbError"]
 __version__ = "0.1.0"

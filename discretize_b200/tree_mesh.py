@@ -400,9 +400,11 @@ class TreeMesh:
             self._cache["Rn"] = self._deflate(t.nodes, t.node_parents, [0.25] * 4)
         return self._cache["Rn"]
 
-    def _host_matrix(self, name):
-        """scipy CSR of a reference operator (canonical form)."""
-        key = "H_" + name
+    def _host_parts(self, name):
+        """The operator as  sum_s diag(geom_s) @ M_s : ``(geoms, parts)`` with ``geoms`` a list of per-row
+        arrays and ``parts`` a list of ``(s, M_s)`` (s = 0: no geometry, s >= 1: geoms[s-1]).  M_s holds
+        pure multipliers (signs and products of hanging weights) -- what the SpMV kernel's code table stores."""
+        key = "P_" + name
         if key in self._cache:
             return self._cache[key]
         t = self._t()
@@ -412,66 +414,94 @@ class TreeMesh:
         offF = np.r_[0, np.cumsum(ntF)]
         offE = np.r_[0, np.cumsum(ntE)]
         cells = np.arange(nC)
-        if name == "face_divergence":  # tree_ext.pyx:3199-3234
-            V = self.cell_volumes
-            rows, cols, vals = [], [], []
+        unit = np.eye(3, dtype=np.int64)
+        geoms, parts = [], []
+        if name == "face_divergence":  # tree_ext.pyx:3199-3234: -+A_f/V_c = -+1/h_d(cell), then deflate faces
+            hg = self.h_gridded
+            R = self._deflate_faces()
             for d in range(3):
-                A = self._face_areas_total(d)
+                rows, cols, vals = [], [], []
                 for s, sign in ((0, -1.0), (1, 1.0)):
                     pos = t.cell_faces[d][:, s]
-                    rows.append(cells); cols.append(offF[d] + t.faces[d].index[pos]); vals.append(sign * A[pos] / V)
-            M = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nC, offF[3]))
-            M = M @ self._deflate_faces()
-        elif name == "edge_curl":  # tree_ext.pyx:3236-3359
+                    rows.append(cells); cols.append(offF[d] + t.faces[d].index[pos]); vals.append(np.full(nC, sign))
+                M = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nC, offF[3]))
+                geoms.append(1.0 / hg[:, d])
+                parts.append((d + 1, M @ R))
+        elif name == "edge_curl":  # tree_ext.pyx:3236-3359: +-L_e/A_f = +-1/(other side of the face), deflate edges
             nF = [f.n for f in t.faces]
             offFn = np.r_[0, np.cumsum(nF)]
-            unit = np.eye(3, dtype=np.int64)
-            rows, cols, vals = [], [], []
+            R = self._deflate_edges()
+            g = [np.zeros(offFn[3]), np.zeros(offFn[3])]
+            acc = [([], [], []), ([], [], [])]
             for d in range(3):
                 f = t.faces[d]
                 nh = np.nonzero(~f.hanging)[0]
-                area = self._face_areas_total(d)[nh]
                 a1, a2 = (d + 1) % 3, (d + 2) % 3   # (curl e)_d = d_{a1} e_{a2} - d_{a2} e_{a1}
-                for (de, dt, sgn) in ((a2, a1, 1.0), (a1, a2, -1.0)):
+                r = offFn[d] + f.index[nh]
+                g[0][r] = 1.0 / self._extent(f.loc[nh], f.half[nh], a1)
+                g[1][r] = 1.0 / self._extent(f.loc[nh], f.half[nh], a2)
+                for k, (de, dt, sgn) in enumerate(((a2, a1, 1.0), (a1, a2, -1.0))):
                     e = t.edges[de]
-                    L = self._edge_lengths_total(de)
                     for s in (-1, 1):
                         q = f.loc[nh] + s * f.half[nh, None] * unit[dt]
                         pos = np.searchsorted(e.keys, key3(q[:, 0], q[:, 1], q[:, 2]))
-                        rows.append(offFn[d] + f.index[nh]); cols.append(offE[de] + e.index[pos])
-                        vals.append(sgn * s * L[pos] / area)
-            M = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(offFn[3], offE[3]))
-            M = M @ self._deflate_edges()
-        elif name == "nodal_gradient":  # tree_ext.pyx:3361-3464
+                        acc[k][0].append(r); acc[k][1].append(offE[de] + e.index[pos]); acc[k][2].append(np.full(nh.size, sgn * s))
+            for k in range(2):
+                M = sp.csr_matrix((np.concatenate(acc[k][2]), (np.concatenate(acc[k][0]), np.concatenate(acc[k][1]))),
+                                  shape=(offFn[3], offE[3]))
+                geoms.append(g[k])
+                parts.append((k + 1, M @ R))
+        elif name == "nodal_gradient":  # tree_ext.pyx:3361-3464: -+1/L, deflate nodes
             nE = [e.n for e in t.edges]
             offEn = np.r_[0, np.cumsum(nE)]
-            unit = np.eye(3, dtype=np.int64)
             rows, cols, vals = [], [], []
+            g = np.zeros(offEn[3])
             for d in range(3):
                 e = t.edges[d]
                 nh = np.nonzero(~e.hanging)[0]
-                L = self._edge_lengths_total(d)[nh]
+                r = offEn[d] + e.index[nh]
+                g[r] = 1.0 / self._extent(e.loc[nh], e.half[nh], d)
                 for s in (-1, 1):
                     q = e.loc[nh] + s * e.half[nh, None] * unit[d]
                     pos = np.searchsorted(t.nodes.keys, key3(q[:, 0], q[:, 1], q[:, 2]))
-                    rows.append(offEn[d] + e.index[nh]); cols.append(t.nodes.index[pos]); vals.append(s / L)
+                    rows.append(r); cols.append(t.nodes.index[pos]); vals.append(np.full(nh.size, float(s)))
             M = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(offEn[3], t.nodes.n_total))
-            M = M @ self._deflate_nodes()
+            geoms.append(g)
+            parts.append((1, M @ self._deflate_nodes()))
         elif name in ("average_face_to_cell", "average_face_to_cell_vector") or name.startswith("average_face_"):
-            M = self._host_average(name, t.faces, t.cell_faces, offF, self._deflate_faces(), 0.5)
+            parts.append((0, self._host_average(name, t.faces, t.cell_faces, offF, self._deflate_faces(), 0.5)))
         elif name in ("average_edge_to_cell", "average_edge_to_cell_vector") or name.startswith("average_edge_"):
-            M = self._host_average(name, t.edges, t.cell_edges, offE, self._deflate_edges(), 0.25)
+            parts.append((0, self._host_average(name, t.edges, t.cell_edges, offE, self._deflate_edges(), 0.25)))
         elif name == "average_node_to_cell":  # tree_ext.pyx:4709-4762
             rows = np.repeat(cells, 8)
             cols = t.nodes.index[t.cell_nodes.reshape(-1)]
             M = sp.csr_matrix((np.full(rows.size, 0.125), (rows, cols)), shape=(nC, t.nodes.n_total)) @ self._deflate_nodes()
+            parts.append((0, M))
         else:
             raise AttributeError(name)
-        M = sp.csr_matrix(M)
-        M.sum_duplicates()
-        M.sort_indices()
-        self._cache[key] = M
-        return M
+        canon = []
+        for s_, M in parts:
+            M = sp.csr_matrix(M)
+            M.sum_duplicates()
+            M.sort_indices()
+            canon.append((s_, M))
+        self._cache[key] = (geoms, canon)
+        return self._cache[key]
+
+    def _host_matrix(self, name):
+        """scipy CSR of a reference operator (canonical form), from the same parts the kernel uses."""
+        key = "H_" + name
+        if key not in self._cache:
+            geoms, parts = self._host_parts(name)
+            acc = None
+            for s_, M in parts:
+                term = M if s_ == 0 else sp.diags(geoms[s_ - 1]) @ M
+                acc = term if acc is None else acc + term
+            acc = sp.csr_matrix(acc)
+            acc.sum_duplicates()
+            acc.sort_indices()
+            self._cache[key] = acc
+        return self._cache[key]
 
     def _host_average(self, name, fams, cell_ents, off, R, w):
         """tree_ext.pyx:4089-4707: per cell 2 faces x 1/2 (4 edges x 1/4) per direction, then deflation."""

@@ -1,0 +1,172 @@
+"""TreeMesh operators on the GPU: coded CSR connectivity + the tree_spmv kernel (K12)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from ._lib import check, load
+from .operators import Operator, cuda_device, ptr, stream_ptr, to_device
+
+
+def encode_parts(geoms, parts, shape):
+    """Merge ``sum_s diag(geom_s) @ M_s`` into one CSR with a code byte per entry.
+
+    Returns (indptr, indices int32, codes uint8, tab_mult, tab_sel).  Entries of different parts that
+    share (row, col) stay separate entries (SpMV adds them; ``tocsr`` sums them on the host)."""
+    rows, cols, mult, sel = [], [], [], []
+    for s_, M in parts:
+        coo = M.tocoo()
+        rows.append(coo.row); cols.append(coo.col); mult.append(coo.data)
+        sel.append(np.full(coo.nnz, s_, dtype=np.int64))
+    rows, cols, mult, sel = (np.concatenate(a) for a in (rows, cols, mult, sel))
+    # distinct (multiplier, selector) pairs -> table
+    mult_r = np.round(mult, 14)
+    pair_key = np.stack([mult_r, sel.astype(np.float64)], axis=1)
+    uniq, codes = np.unique(pair_key, axis=0, return_inverse=True)
+    if uniq.shape[0] > 256:
+        raise ValueError(f"operator needs {uniq.shape[0]} distinct (multiplier, selector) pairs; the code byte holds 256")
+    order = np.lexsort((cols, rows))
+    rows, cols, codes = rows[order], cols[order], codes.reshape(-1)[order]
+    indptr = np.zeros(shape[0] + 1, dtype=np.int64)
+    np.add.at(indptr, rows + 1, 1)
+    indptr = np.cumsum(indptr)
+    return indptr, cols.astype(np.int32), codes.astype(np.uint8), uniq[:, 0].copy(), uniq[:, 1].astype(np.uint8)
+
+
+class CodedCsr:
+    """Device-resident coded CSR (one direction of an operator)."""
+
+    def __init__(self, geoms, parts, shape, geom_by_col):
+        indptr, indices, codes, tmult, tsel = encode_parts(geoms, parts, shape)
+        self.shape = shape
+        self.nnz = int(indptr[-1])
+        self.is64 = self.nnz >= 2**31 - 1
+        self.indptr = to_device(indptr if self.is64 else indptr.astype(np.int32), torch.int64 if self.is64 else torch.int32)
+        self.indices = to_device(indices, torch.int32)
+        self.codes = to_device(codes, torch.uint8)
+        self.tab_mult = to_device(tmult)
+        self.tab_sel = to_device(tsel, torch.uint8)
+        self.ntab = int(tmult.size)
+        self.geoms = [to_device(g) for g in geoms] + [None] * (3 - len(geoms))
+        self.geom_by_col = int(geom_by_col)
+        avg = self.nnz / max(shape[0], 1)
+        self.lpr = 2 if avg <= 3 else 4 if avg <= 6 else 8 if avg <= 14 else 16
+
+    def apply(self, x, out):
+        g = self.geoms
+        check(load().dzb_tree_spmv(self.shape[0], ptr(self.indptr), int(self.is64), ptr(self.indices), ptr(self.codes),
+                                   ptr(self.tab_mult), ptr(self.tab_sel), self.ntab, ptr(g[0]), ptr(g[1]), ptr(g[2]),
+                                   self.geom_by_col, ptr(x), ptr(out), self.lpr, stream_ptr()), "dzb_tree_spmv")
+
+    def bytes_per_apply(self):
+        """Algorithmic bytes: vectors + int32 columns + code bytes + indptr + row geometry."""
+        n_geom = sum(g is not None for g in self.geoms)
+        gsize = (self.shape[1] if self.geom_by_col else self.shape[0]) * n_geom
+        return (8 * (self.shape[0] + self.shape[1]) + 5 * self.nnz + (8 if self.is64 else 4) * (self.shape[0] + 1) + 8 * gsize)
+
+
+class TreeOperator(Operator):
+    """A deflated OcTree operator (reference: tree_ext.pyx:3114-4762), applied by tree_spmv."""
+
+    def __init__(self, mesh, name, transposed=False, _shared=None):
+        M = mesh._host_parts(name)[1][0][1]
+        shape = M.shape
+        super().__init__((shape[1], shape[0]) if transposed else shape)
+        self.mesh, self.name, self.transposed = mesh, name, transposed
+        self._fwd_shape = shape
+        self._dev = _shared if _shared is not None else {}
+
+    def _csr(self, transposed):
+        key = "T" if transposed else "N"
+        if key not in self._dev:
+            geoms, parts = self.mesh._host_parts(self.name)
+            if transposed:
+                parts = [(s_, M.T.tocsr()) for s_, M in parts]
+                shape = (self._fwd_shape[1], self._fwd_shape[0])
+            else:
+                shape = self._fwd_shape
+            self._dev[key] = CodedCsr(geoms, parts, shape, geom_by_col=transposed)
+        return self._dev[key]
+
+    def _dev_apply(self, x, out):
+        self._csr(self.transposed).apply(x, out)
+
+    def _dev_apply_t(self, x, out):
+        self._csr(not self.transposed).apply(x, out)
+
+    def _transpose(self):
+        return TreeOperator(self.mesh, self.name, not self.transposed, self._dev)
+
+    _adjoint = _transpose
+
+    def _tocsr(self):
+        M = self.mesh._host_matrix(self.name)
+        return M.T.tocsr() if self.transposed else M.copy()
+
+    def bytes_per_apply(self):
+        return self._csr(self.transposed).bytes_per_apply()
+
+    def __repr__(self):
+        t = ".T" if self.transposed else ""
+        return f"<{self.shape[0]}x{self.shape[1]} TreeOperator {self.name}{t} (CUDA, coded CSR)>"
+
+
+class TreeMassDiag(Operator):
+    """Diagonal mass matrix on a TreeMesh: M = diag(dim * Av^T (V sigma)) (isotropic) or
+    diag(AvV^T (V sigma_cc)) (anisotropic), base/base_tensor_mesh.py:792-863 with the tree averages."""
+
+    def __init__(self, mesh, proj, model, invert_model, invert_matrix):
+        from .tensor_ops import _Model
+        from . import _lib
+
+        n = mesh.n_faces if proj == "F" else mesh.n_edges
+        super().__init__((n, n))
+        md = _Model(mesh, model)
+        if md.kind == _lib.MODEL_TENSOR:
+            raise NotImplementedError("full-tensor mass matrices on TreeMesh are not built yet (SURVEY T5 / K13)")
+        dev = cuda_device()
+        nC = mesh.n_cells
+        V = to_device(mesh.cell_volumes)
+        if md.kind == _lib.MODEL_SCALAR:
+            m = torch.full((nC,), md.scalar, dtype=torch.float64, device=dev)
+        else:
+            m = md.dev
+        if invert_model:
+            m = 1.0 / m
+        base = "average_face_to_cell" if proj == "F" else "average_edge_to_cell"
+        if m.numel() == nC:
+            Av = mesh._operator(base)
+            d = Av.apply_device(V * m, transpose=True)
+            d.mul_(3.0)
+        else:
+            Av = mesh._operator(base + "_vector")
+            d = Av.apply_device(V.repeat(3) * m, transpose=True)
+        self.invert_matrix = bool(invert_matrix)
+        self.diag = d
+
+    def _dev_apply(self, x, out):
+        check(load().dzb_diag_scale(self.shape[0], ptr(self.diag), ptr(x), ptr(out), int(self.invert_matrix), stream_ptr()),
+              "dzb_diag_scale")
+
+    _dev_apply_t = _dev_apply
+
+    def _transpose(self):
+        return self
+
+    _adjoint = _transpose
+
+    def diagonal(self):
+        d = self.diag.cpu().numpy()
+        return 1.0 / d if self.invert_matrix else d
+
+    def _tocsr(self):
+        return sp.diags(self.diagonal(), format="csr")
+
+
+def make_tree_mass_operator(mesh, proj, model, invert_model, invert_matrix):
+    if proj not in ("F", "E"):
+        raise TypeError("projection_type must be 'F' for faces or 'E' for edges")
+    return TreeMassDiag(mesh, proj, model, invert_model, invert_matrix)

@@ -151,6 +151,20 @@ int dzb_interp_fused(const double *tx, int64_t ntx, const double *ty, int64_t nt
 int dzb_points_inside(const double *pts, int64_t npts, const double *lo_host, const double *hi_host,
                       const double *tol_host, uint8_t *inside, void *stream);
 
+/* ---- TreeMesh (OcTree) operators ------------------------------------------------ */
+/* y = A x for a deflated OcTree operator (face_divergence, edge_curl, nodal_gradient, average_*:
+ * _extensions/tree_ext.pyx:3114-4762) stored as CSR connectivity + one code byte per entry.
+ * value(entry) = tab_mult[code] * (tab_sel[code] == 0 ? 1 : g{tab_sel[code]-1}[row])
+ * (geom_by_col != 0: the geometry is indexed by the column instead -- used for A^T).
+ * indptr: int32 or int64 (indptr_is64); indices int32; tab_* are DEVICE arrays of ntab entries;
+ * g0..g2 device arrays or NULL; lanes_per_row in {1,2,4,8,16,32}. */
+int dzb_tree_spmv(int64_t nrows, const void *indptr, int indptr_is64, const int32_t *indices, const uint8_t *codes,
+                  const double *tab_mult, const uint8_t *tab_sel, int ntab, const double *g0, const double *g1,
+                  const double *g2, int geom_by_col, const double *x, double *y, int lanes_per_row, void *stream);
+/* y = d .* x (invert == 0) or x ./ d: diagonal mass matrices on a TreeMesh
+ * (base/base_tensor_mesh.py:792-863 with the tree averages). */
+int dzb_diag_scale(int64_t n, const double *d, const double *x, double *y, int invert, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

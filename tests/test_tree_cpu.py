@@ -1,0 +1,98 @@
+"""CPU: the from-scratch OcTree builder (octree.py + tree_build.py + the host assembly in tree_mesh.py)
+against fixtures made by the reference (tests/golden/tree_small.npz) and, where /root/reference exists,
+against the reference itself on random trees."""
+import numpy as np
+import pytest
+
+from discretize_b200.tree_mesh import TreeMesh, TreeMeshNotFinalizedError
+from tests.golden.make_golden_tree import COUNTS, TREE_OPS
+from tests.helpers import assert_same_matrix, golden_matrix, load_golden
+
+
+def _mesh_from_fixture(g, tag, how):
+    h = [g[f"{tag}_h{a}"] for a in "xyz"]
+    m = TreeMesh(h, origin=g[f"{tag}_origin"], diagonal_balance=bool(g[f"{tag}_db"]))
+    if how == "refine":
+        m.refine_points(g[f"{tag}_pts"], -1, [1, 1], finalize=True)
+    else:
+        m._set_state(g[f"{tag}_state_indexes"], g[f"{tag}_state_levels"])
+        m.finalize()
+    return m
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return load_golden("tree_small.npz")
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+@pytest.mark.parametrize("how", ["refine", "state"])
+def test_tree_matches_reference_fixture(gold, tag, how):
+    g = gold
+    m = _mesh_from_fixture(g, tag, how)
+    idx, lev = m._tree.state()
+    np.testing.assert_array_equal(idx, g[f"{tag}_state_indexes"])   # same cells, same order
+    np.testing.assert_array_equal(lev, g[f"{tag}_state_levels"])
+    np.testing.assert_array_equal(np.array([getattr(m, c) for c in COUNTS]), g[f"{tag}_counts"])
+    for name in ("cell_volumes", "face_areas", "edge_lengths", "cell_centers", "nodes"):
+        np.testing.assert_array_equal(getattr(m, name), g[f"{tag}_{name}"])
+    for name in TREE_OPS:
+        assert_same_matrix(m._host_matrix(name), golden_matrix(g, f"{tag}_{name}"), 1e-13)
+
+
+def test_not_finalized_and_errors():
+    m = TreeMesh([8, 8, 8])
+    with pytest.raises(TreeMeshNotFinalizedError):
+        m.n_cells
+    with pytest.raises(ValueError, match="power of 2"):
+        TreeMesh([6, 8, 8])
+    m.refine(2, finalize=True)
+    assert m.n_cells == 64 and m.n_hanging_faces == 0 and m.nhN == 0
+    with pytest.raises(RuntimeError):
+        m.refine(3)
+
+
+def test_full_refinement_equals_tensor_counts():
+    """A fully refined OcTree has the TensorMesh counts (reference tests/tree/test_tree.py:161-213)."""
+    m = TreeMesh([4, 4, 4])
+    m.refine(-1, finalize=True)
+    assert (m.nC, m.nN, m.nF, m.nE) == (64, 125, 240, 300)
+    assert m.n_hanging_edges == 0
+    D = m._host_matrix("face_divergence")
+    C = m._host_matrix("edge_curl")
+    G = m._host_matrix("nodal_gradient")
+    assert abs(D @ C).max() < 1e-12 and abs(C @ G).max() < 1e-12
+
+
+def test_averages_reproduce_constants_on_refined_tree(gold):
+    # (D C = 0 / C G = 0 only hold on fully refined trees -- that is all the reference tests, too:
+    #  tests/tree/test_tree.py:215-233 -- the deflated operators of a hanging tree do not commute.)
+    m = _mesh_from_fixture(gold, "a", "state")
+    for name in ("average_face_to_cell", "average_edge_to_cell", "average_node_to_cell"):
+        A = m._host_matrix(name)
+        np.testing.assert_allclose(A @ np.ones(A.shape[1]), 1.0, atol=1e-14)  # constants are reproduced
+
+
+@pytest.mark.parametrize("db", [False, True])
+def test_random_trees_against_reference(reference, db):
+    import warnings
+
+    warnings.simplefilter("ignore")
+    rng = np.random.default_rng(5)
+    for shape in ([16, 16, 16], [32, 16, 8]):
+        h = [rng.random(s) + 0.5 for s in shape]
+        ext = np.array([x.sum() for x in h])
+        pts = (rng.random((12, 3)) * 0.8 + 0.1) * ext
+        r = reference.TreeMesh(h, diagonal_balance=db)
+        n = TreeMesh(h, diagonal_balance=db)
+        for mesh in (r, n):
+            mesh.refine_ball(pts[:4], [0.9, 1.3, 0.4, 2.0], [-1, -2, -1, 3], finalize=False)
+            mesh.insert_cells(pts[4:], np.array([-1, -1, -2, -1, 2, 3, -1, -1]), finalize=False)
+            mesh.refine_points(pts[:3], -1, [2, 1, 1], finalize=True)
+        ri, rl = r.__getstate__()
+        ni, nl = n._tree.state()
+        np.testing.assert_array_equal(ri, ni)
+        np.testing.assert_array_equal(rl, nl)
+        assert (r.nhN, r.nhEx, r.nhFz, r.nN, r.nE, r.nF) == (n.nhN, n.nhEx, n.nhFz, n.nN, n.nE, n.nF)
+        for name in ("face_divergence", "edge_curl", "nodal_gradient", "average_edge_to_cell", "average_node_to_cell"):
+            assert_same_matrix(n._host_matrix(name), getattr(r, name), 1e-13)
