@@ -1,14 +1,22 @@
-"""Linear octree of leaf cells: refinement requests and 2:1 balancing on flat arrays.
+"""Level-set octree: refinement requests and 2:1 balancing on sorted integer arrays.
 
 The reference grows a pointer tree by recursive ``Cell::divide`` calls that balance as they go
-(``discretize/_extensions/tree.cpp:459-746``).  This is a different design with the same result:
-leaves are rows of flat arrays (low corner in fine-cell units + level) kept in the reference's
-cell order (roots x-fastest, then Z-order: tree.cpp:232-344, 748-756, 949-953), refinement
-requests are processed level by level as (leaf, request) pair lists, and the 2:1 (optionally
-26-neighbour "diagonal") balance is restored afterwards by a ripple over the leaves that changed,
-using binary search in the Z-ordered key array to find the leaf that contains a probe point.
-The balanced closure of a set of refinement requests is unique, so the result does not depend on
-the order in which the reference would have processed the same requests.
+(``discretize/_extensions/tree.cpp:459-746``).  This is a different design with the same result.
+The tree is stored as, per level, the sorted set of DIVIDED cells (packed integer coordinates at
+that level); leaves are derived on demand as "children of divided cells that are not divided".
+
+* A refinement request (a point to insert, a ball, ...) is pushed down from the roots level by
+  level as a list of (cell, request) pairs; every cell a request still concerns above its target
+  level joins the divided set.  This is exactly the set of cells the reference would divide for
+  that request (``Cell::insert_cell`` tree.cpp:383-396, ``refine_geom`` tree.h:149-167).
+* Balancing is one sweep from the finest level to the coarsest: a divided cell at level l has
+  children at level l+1, so every (face-, or with ``diagonal`` also edge-/corner-) neighbouring box
+  of it at level l must exist as a cell, i.e. the PARENT of each neighbouring box joins the divided
+  set of level l-1.  Additions at level l-1 only create requirements at level l-2, so a single
+  sweep reaches the unique minimal balanced closure -- the tree the reference's ripple of
+  ``divide`` calls arrives at, independent of request order.
+* Cells are numbered in the reference's order: roots x-fastest, then depth-first with children
+  ordered by (x, y, z) bit (tree.cpp:232-344, 748-756, 949-953), i.e. Z-order within a root.
 """
 from __future__ import annotations
 
@@ -39,15 +47,121 @@ class LinearOctree:
         self.rw = 1 << min_l                              # root width in fine cells
         self.roots = tuple(s // self.rw for s in n)
         self.nbits = min_l
-        # leaves start as the roots, x fastest
-        rx, ry, rz = np.meshgrid(np.arange(self.roots[0]), np.arange(self.roots[1]), np.arange(self.roots[2]), indexing="ij")
-        lo = np.stack([rx.reshape(-1, order="F"), ry.reshape(-1, order="F"), rz.reshape(-1, order="F")], axis=1) * self.rw
-        self.lo = lo.astype(np.int64)
-        self.lvl = np.full(self.lo.shape[0], self.root_level, dtype=np.int64)
+        # divided cells per level (packed coordinates, sorted unique); levels root_level .. max_level-1
+        self.div = {l: np.zeros(0, dtype=np.int64) for l in range(self.root_level, self.max_level)}
+        self._leaves = None
 
-    # ---- helpers -----------------------------------------------------------------------------
+    # ---- per-level grids ---------------------------------------------------------------------------
+    def level_width(self, l):
+        return 1 << (self.max_level - l)
+
+    def grid(self, l):
+        w = self.level_width(l)
+        return tuple(s // w for s in self.n)
+
+    def pack(self, l, c):
+        g = self.grid(l)
+        return c[:, 0] + g[0] * (c[:, 1] + g[1] * c[:, 2])
+
+    def unpack(self, l, p):
+        g = self.grid(l)
+        return np.stack([p % g[0], (p // g[0]) % g[1], p // (g[0] * g[1])], axis=1)
+
     def width(self, lvl):
-        return np.left_shift(np.int64(1), (self.max_level - lvl).astype(np.int64))
+        return np.left_shift(np.int64(1), (self.max_level - np.asarray(lvl)).astype(np.int64))
+
+    def root_cells(self):
+        g = self.grid(self.root_level)
+        return self.unpack(self.root_level, np.arange(g[0] * g[1] * g[2], dtype=np.int64))
+
+    def _add_divided(self, l, packed):
+        if packed.size:
+            self.div[l] = np.union1d(self.div[l], packed)
+            self._leaves = None
+
+    # ---- refinement requests ---------------------------------------------------------------------------
+    def refine_requests(self, nreq, levels, concerns):
+        """``concerns(req_idx, lo, w)`` -> mask: does request req_idx still concern the cell with low
+        corner ``lo`` (fine-cell units) and width ``w``?  Every concerned cell below the request's
+        target level is divided."""
+        levels = np.minimum(np.asarray(levels, dtype=np.int64), self.max_level)
+        roots = self.root_cells()
+        cells = np.repeat(roots, nreq, axis=0)
+        req = np.tile(np.arange(nreq), roots.shape[0])
+        l = self.root_level
+        offs = np.array([[a, b, c] for c in (0, 1) for b in (0, 1) for a in (0, 1)], dtype=np.int64)
+        while cells.shape[0] and l < self.max_level:
+            w = self.level_width(l)
+            ok = (levels[req] > l) & concerns(req, cells * w, np.full(req.size, w, dtype=np.int64))
+            cells, req = cells[ok], req[ok]
+            if not cells.shape[0]:
+                break
+            self._add_divided(l, np.unique(self.pack(l, cells)))
+            # push the surviving pairs down to the 8 children
+            cells = (2 * cells[:, None, :] + offs[None, :, :]).reshape(-1, 3)
+            req = np.repeat(req, 8)
+            l += 1
+
+    def divide_leaves(self, leaf_lo, leaf_lvl):
+        """Divide the given leaves (arrays), used by ``refine(function)``."""
+        for l in np.unique(leaf_lvl):
+            if l >= self.max_level:
+                continue
+            sel = leaf_lvl == l
+            self._add_divided(int(l), np.unique(self.pack(int(l), leaf_lo[sel] // self.level_width(int(l)))))
+
+    def set_leaves(self, lo, lvl):
+        """Rebuild the divided sets from an explicit leaf list (ancestor closure)."""
+        self.div = {l: np.zeros(0, dtype=np.int64) for l in range(self.root_level, self.max_level)}
+        for l in range(self.root_level, self.max_level):
+            sel = lvl > l
+            if sel.any():
+                self.div[l] = np.unique(self.pack(l, lo[sel] // self.level_width(l)))
+        self._leaves = None
+
+    # ---- balancing -----------------------------------------------------------------------------------------
+    def balance(self, diagonal):
+        dirs = [(a, b, c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)]
+        if not diagonal:
+            dirs = [d for d in dirs if sum(abs(x) for x in d) <= 1]
+        dirs = np.array(dirs, dtype=np.int64)  # includes (0,0,0): a divided cell's own parent is divided
+        for l in range(self.max_level - 1, self.root_level, -1):
+            d = self.div[l]
+            if not d.size:
+                continue
+            c = self.unpack(l, d)
+            g = np.array(self.grid(l), dtype=np.int64)
+            need = []
+            for dv in dirs:
+                nb = c + dv[None, :]
+                inside = ((nb >= 0) & (nb < g[None, :])).all(axis=1)
+                need.append(self.pack(l - 1, nb[inside] >> 1))
+            self._add_divided(l - 1, np.unique(np.concatenate(need)))
+
+    # ---- leaves ------------------------------------------------------------------------------------------------
+    def leaves(self):
+        """(lo, lvl) of all leaves in the reference's cell order."""
+        if self._leaves is not None:
+            return self._leaves
+        offs = np.array([[a, b, c] for c in (0, 1) for b in (0, 1) for a in (0, 1)], dtype=np.int64)
+        los, lvls = [], []
+        cand = self.root_cells()  # cells existing at the current level
+        for l in range(self.root_level, self.max_level + 1):
+            if l < self.max_level and self.div[l].size:
+                isdiv = np.isin(self.pack(l, cand), self.div[l], assume_unique=False)
+            else:
+                isdiv = np.zeros(cand.shape[0], dtype=bool)
+            leaf = cand[~isdiv]
+            los.append(leaf * self.level_width(l))
+            lvls.append(np.full(leaf.shape[0], l, dtype=np.int64))
+            if not isdiv.any():
+                break
+            cand = (2 * cand[isdiv][:, None, :] + offs[None, :, :]).reshape(-1, 3)
+        lo = np.concatenate(los)
+        lvl = np.concatenate(lvls)
+        order = np.argsort(self.keys(lo), kind="stable")
+        self._leaves = (lo[order], lvl[order])
+        return self._leaves
 
     def keys(self, lo):
         """Position of a fine cell in the reference's cell order (root id, then Z-order code)."""
@@ -57,97 +171,12 @@ class LinearOctree:
         root_id = root[:, 0] + self.roots[0] * (root[:, 1] + self.roots[1] * root[:, 2])
         return root_id * (np.int64(self.rw) ** 3) + code
 
-    def sort(self):
-        order = np.argsort(self.keys(self.lo), kind="stable")
-        self.lo, self.lvl = self.lo[order], self.lvl[order]
+    @property
+    def n_leaves(self):
+        return self.leaves()[1].size
 
-    def split(self, mask):
-        """Replace the leaves selected by ``mask`` with their 8 children; returns the children rows."""
-        idx = np.nonzero(mask)[0]
-        if idx.size == 0:
-            return np.zeros(0, dtype=np.int64)
-        keep = ~mask
-        plo, plvl = self.lo[idx], self.lvl[idx]
-        hw = self.width(plvl) // 2
-        offs = np.array([[a, b, c] for c in (0, 1) for b in (0, 1) for a in (0, 1)], dtype=np.int64)
-        clo = (plo[:, None, :] + hw[:, None, None] * offs[None, :, :]).reshape(-1, 3)
-        clvl = np.repeat(plvl + 1, 8)
-        n_keep = int(keep.sum())
-        self.lo = np.concatenate([self.lo[keep], clo])
-        self.lvl = np.concatenate([self.lvl[keep], clvl])
-        return np.arange(n_keep, n_keep + clo.shape[0])
-
-    # ---- refinement requests --------------------------------------------------------------------
-    def refine_requests(self, nreq, levels, select_children):
-        """Generic top-down refinement.
-
-        ``levels[r]`` is the level request r wants; ``select_children(req_idx, child_lo, child_w)``
-        returns a boolean mask over candidate (request, child) pairs saying whether the request
-        still concerns that child cell.  Requests concern every root initially (filtered by the
-        same predicate).  Leaves are split while a request of higher level concerns them.
-        """
-        levels = np.asarray(levels, dtype=np.int64)
-        levels = np.minimum(levels, self.max_level)
-        nl = self.lo.shape[0]
-        leaf = np.repeat(np.arange(nl), nreq)
-        req = np.tile(np.arange(nreq), nl)
-        ok = select_children(req, self.lo[leaf], self.width(self.lvl[leaf])) & (levels[req] > self.lvl[leaf])
-        leaf, req = leaf[ok], req[ok]
-        while leaf.size:
-            mask = np.zeros(self.lo.shape[0], dtype=bool)
-            mask[leaf] = True
-            # children of the split leaves, 8 per parent, parents in increasing row order
-            parents = np.nonzero(mask)[0]
-            rank = np.cumsum(mask) - 1                      # parent row -> rank among split parents
-            child_rows = self.split(mask)                   # rows of children, 8 consecutive per parent
-            base = child_rows[0] if child_rows.size else 0
-            c_leaf = (base + 8 * rank[leaf])[:, None] + np.arange(8)[None, :]
-            c_req = np.repeat(req, 8)
-            c_leaf = c_leaf.reshape(-1)
-            ok = select_children(c_req, self.lo[c_leaf], self.width(self.lvl[c_leaf])) & (levels[c_req] > self.lvl[c_leaf])
-            leaf, req = c_leaf[ok], c_req[ok]
-            del parents
-
-    # ---- balancing ---------------------------------------------------------------------------------
-    def balance(self, diagonal):
-        """Restore the 2:1 condition across faces (and edges / corners when ``diagonal``)."""
-        dirs = [(a, b, c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1) if (a, b, c) != (0, 0, 0)]
-        if not diagonal:
-            dirs = [d for d in dirs if sum(abs(x) for x in d) == 1]
-        dirs = np.array(dirs, dtype=np.int64)
-        nmax = np.array(self.n, dtype=np.int64)
-        active = np.arange(self.lo.shape[0])
-        while active.size:
-            self_keys_order = np.argsort(self.keys(self.lo), kind="stable")
-            skeys = self.keys(self.lo)[self_keys_order]
-            alo, aw = self.lo[active], self.width(self.lvl[active])
-            probe = (alo[:, None, :] + aw[:, None, None] * dirs[None, :, :]).reshape(-1, 3)
-            owner = np.repeat(active, dirs.shape[0])
-            inside = ((probe >= 0) & (probe < nmax[None, :])).all(axis=1)
-            probe, owner = probe[inside], owner[inside]
-            pos = np.searchsorted(skeys, self.keys(probe), side="right") - 1
-            hit = self_keys_order[pos]                       # leaf containing the probe point
-            too_coarse = self.lvl[hit] < self.lvl[owner] - 1
-            if not too_coarse.any():
-                break
-            mask = np.zeros(self.lo.shape[0], dtype=bool)
-            mask[hit[too_coarse]] = True
-            again = np.unique(owner[too_coarse])
-            # rows shift when leaves are removed: remember the triggering leaves by key
-            again_lo = self.lo[again]
-            children = self.split(mask)
-            _, again_rows = self._rows_of(again_lo)
-            active = np.unique(np.concatenate([children, again_rows]))
-
-    def _rows_of(self, lo):
-        order = np.argsort(self.keys(self.lo), kind="stable")
-        skeys = self.keys(self.lo)[order]
-        pos = np.searchsorted(skeys, self.keys(lo), side="right") - 1
-        return skeys[pos], order[pos]
-
-    # ---- state ----------------------------------------------------------------------------------------
     def state(self):
         """(cell-centre location in half steps, level) in the reference's cell order."""
-        self.sort()
-        w = self.width(self.lvl)
-        return 2 * self.lo + w[:, None], self.lvl.copy()
+        lo, lvl = self.leaves()
+        w = self.width(lvl)
+        return 2 * lo + w[:, None], lvl.copy()

@@ -200,16 +200,17 @@ class TreeMesh:
         db = self._diagonal_balance if diagonal_balance is None else diagonal_balance
         t = self._tree
         while True:
-            w = t.width(t.lvl)
+            lo, lvl = t.leaves()
+            w = t.width(lvl)
             if callable(function):
-                c = np.stack([self._xs[d][2 * t.lo[:, d] + w] for d in range(3)], axis=1)
+                c = np.stack([(self._xs[d][2 * lo[:, d]] + self._xs[d][2 * (lo[:, d] + w)]) * 0.5 for d in range(3)], axis=1)
                 want = np.asarray(function(c), dtype=np.int64)
             else:
-                want = np.full(t.lvl.size, self._parse_level(int(function)), dtype=np.int64)
-            mask = (want > t.lvl) & (t.lvl < t.max_level)
+                want = np.full(lvl.size, self._parse_level(int(function)), dtype=np.int64)
+            mask = (want > lvl) & (lvl < t.max_level)
             if not mask.any():
                 break
-            t.split(mask)
+            t.divide_leaves(lo[mask], lvl[mask])
         t.balance(db)
         if finalize:
             self.finalize()
@@ -220,9 +221,7 @@ class TreeMesh:
         indexes = np.asarray(indexes, dtype=np.int64)
         levels = np.asarray(levels, dtype=np.int64)
         w = self._tree.width(levels)
-        self._tree.lo = (indexes - w[:, None]) // 2
-        self._tree.lvl = levels.copy()
-        self._tree.sort()
+        self._tree.set_leaves((indexes - w[:, None]) // 2, levels)
 
     @property
     def cell_state(self):
@@ -568,5 +567,5 @@ class TreeMesh:
         raise NotImplementedError("TreeMesh.get_interpolation_matrix is not part of the five target configurations (SURVEY N3)")
 
     def __repr__(self):
-        n = self._topo.n_cells if self._finalized else self._tree.lvl.size
+        n = self._topo.n_cells if self._finalized else self._tree.n_leaves
         return f"<discretize_b200.TreeMesh {n} cells, max_level {self.max_level}>"
