@@ -10,6 +10,7 @@
 // from global memory (L1/L2 serve the re-reads).  It is the simple, obviously-correct
 // form and the cross-check for the marching variant.
 #include "tm_mass_common.cuh"
+#include "tm_maxwell_ring.cuh"
 #include "tm_rowkernels.cuh"
 
 namespace dzb {
@@ -51,16 +52,83 @@ __global__ void __launch_bounds__(BX *BY *BZ)
 
 using namespace dzb;
 
-extern "C" int dzb_tm_maxwell(const DzbTensorMesh *mm, const double *mui, const double *sigma, const double *e,
-                              double *y, void *stream) {
+static int g_mx_variant = 1;   // 0 = gather (one thread per edge), 1 = warp-specialised TMA ring
+static int g_mx_kchunk = 64;
+extern "C" void dzb_tune_maxwell(int variant, int kchunk) {
+  g_mx_variant = variant;
+  if (kchunk > 0) g_mx_kchunk = kchunk > MX_MAXCHUNK ? MX_MAXCHUNK : kchunk;
+}
+
+template <int NWC, int PARX, int NSLOT>
+static int launch_mx_ring_t(const TM &m, const double *mui, const double *sigma, const double *e, double *y, int xblocks,
+                            int nwc, int k_begin, int k_end, cudaStream_t s) {
+  typedef MxRing<2, NWC, PARX, NSLOT> G;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(k_maxwell_ring<2, NWC, PARX, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)G::SMEM) != cudaSuccess)
+      return -1;
+    attr_done = true;
+  }
+  const int nNy = (int)m.ny + 1;
+  const int kchunk = g_mx_kchunk;
+  dim3 grid((unsigned)xblocks, (unsigned)((nNy + 1) / 2), (unsigned)((k_end - k_begin + kchunk - 1) / kchunk));
+  k_maxwell_ring<2, NWC, PARX, NSLOT><<<grid, dim3((nwc + 1) * 32), G::SMEM, s>>>(m, mui, sigma, e, y, kchunk, nwc,
+                                                                                   k_begin, k_end);
+  return 0;
+}
+
+static int g_mx_maxw = 12;  // consumer warps per block: 6, 9, 12 or 18 (tuning knob)
+extern "C" void dzb_tune_maxwell_warps(int w) { g_mx_maxw = w; }
+
+#define MX_LAUNCH(NWC, NS)                                                                                    \
+  return parx ? launch_mx_ring_t<NWC, 1, NS>(m, mui, sigma, e, y, xblocks, nwc, k_begin, k_end, s)            \
+              : launch_mx_ring_t<NWC, 0, NS>(m, mui, sigma, e, y, xblocks, nwc, k_begin, k_end, s)
+
+static int launch_mx_ring(const TM &m, const double *mui, const double *sigma, const double *e, double *y, int k_begin,
+                          int k_end, cudaStream_t s) {
+  const int nNx = (int)m.nx + 1;
+  const int strips = (nNx + MX_XOUT - 1) / MX_XOUT;
+  int maxw = strips <= 6 ? 6 : g_mx_maxw;
+  const int xblocks = (strips + maxw - 1) / maxw;
+  const int nwc = (strips + xblocks - 1) / xblocks;
+  const int parx = (int)(m.nx & 1);
+  if (maxw <= 6) { MX_LAUNCH(6, 4); }
+  if (maxw <= 9) { MX_LAUNCH(9, 4); }
+  if (maxw <= 12) { MX_LAUNCH(12, 4); }
+  MX_LAUNCH(18, 3);
+}
+
+extern "C" int dzb_tm_maxwell_range(const DzbTensorMesh *mm, const double *mui, const double *sigma, const double *e,
+                                    double *y, int64_t k_begin, int64_t k_end, void *stream) {
   if (!valid_mesh(mm)) return -1;
   TM m(*mm);
+  if (k_begin < 0 || k_end > m.nz + 1 || k_begin > k_end) {
+    set_error("dzb_tm_maxwell_range: plane range outside [0, nz+1]");
+    return -1;
+  }
+  if (k_begin == k_end) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool ring_ok = m.ny >= 1 && (m.nx + 1) * (m.ny + 1) < ((i64)1 << 31);
+  if (g_mx_variant == 1 && ring_ok) {
+    if (launch_mx_ring(m, mui, sigma, e, y, (int)k_begin, (int)k_end, s) == 0) return check_launch("dzb_tm_maxwell");
+    cudaGetLastError();
+  }
+  if (k_begin != 0 || k_end != m.nz + 1) {
+    set_error("dzb_tm_maxwell_range: the gather variant only supports the full plane range");
+    return -1;
+  }
   Model mu{DZB_MODEL_ISO, mui, 0.0, m.nC(), false};
   Model sg{DZB_MODEL_ISO, sigma, 0.0, m.nC(), false};
-  cudaStream_t s = (cudaStream_t)stream;
   dim3 b(BX, BY, BZ);
   k_maxwell_gather<0><<<grid_for<LOC_EX>(m), b, 0, s>>>(m, mu, sg, e, y);
   k_maxwell_gather<1><<<grid_for<LOC_EY>(m), b, 0, s>>>(m, mu, sg, e, y);
   k_maxwell_gather<2><<<grid_for<LOC_EZ>(m), b, 0, s>>>(m, mu, sg, e, y);
   return check_launch("dzb_tm_maxwell");
+}
+
+extern "C" int dzb_tm_maxwell(const DzbTensorMesh *mm, const double *mui, const double *sigma, const double *e,
+                              double *y, void *stream) {
+  if (!valid_mesh(mm)) return -1;
+  return dzb_tm_maxwell_range(mm, mui, sigma, e, y, 0, mm->nz + 1, stream);
 }

@@ -126,6 +126,11 @@ int dzb_tm_dc_nodal_range(const DzbTensorMesh *m, const double *sigma, const dou
  * get_face_inner_product(mui) + get_edge_inner_product(sigma), isotropic models. */
 int dzb_tm_maxwell(const DzbTensorMesh *m, const double *mui, const double *sigma, const double *e, double *y,
                    void *stream);
+/* Same, writing only what lives on node planes / cell layers k_begin <= k < k_end (Ex, Ey on planes k,
+ * Ez in layers k < nz): the z-slab building block, like dzb_tm_dc_nodal_range.  The 8 bytes following
+ * e, mui and sigma must be readable. */
+int dzb_tm_maxwell_range(const DzbTensorMesh *m, const double *mui, const double *sigma, const double *e, double *y,
+                         int64_t k_begin, int64_t k_end, void *stream);
 
 /* ---- interpolation: get_interpolation_matrix --------------------------------- */
 /* base/base_tensor_mesh.py:684-790 -> utils/interpolation_utils.py:44-172 ->
