@@ -78,7 +78,7 @@ static int launch_mx_ring_t(const TM &m, const double *mui, const double *sigma,
   return 0;
 }
 
-static int g_mx_maxw = 12;  // consumer warps per block: 6, 9, 12 or 18 (tuning knob)
+static int g_mx_maxw = 9;  // consumer warps per block: 6, 9, 12 or 18 (tuning knob)
 extern "C" void dzb_tune_maxwell_warps(int w) { g_mx_maxw = w; }
 
 #define MX_LAUNCH(NWC, NS)                                                                                    \

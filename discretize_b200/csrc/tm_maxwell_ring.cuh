@@ -114,44 +114,51 @@ __global__ void __launch_bounds__((NWC + 1) * 32, 1)
 
   if (warp == nwc) {
     // ================= producer warp =================
-    if (lane == 0) {
+    // Lane l owns row copy l of every stage (17 copies for RY = 2): the per-row address arithmetic runs
+    // SIMT across the lanes, lane 0 posts the stage's byte count, then every lane issues its bulk copy.
+    {
       const long long nE = nEx + nEy + (long long)nNx * nNy * nz;
       A[0].end = A[1].end = A[2].end = (eaddr + nE + 1) & ~1ll;
       A[3].end = ((long long)((unsigned long long)mui >> 3) + (long long)nx * ny * nz + 1) & ~1ll;
       A[4].end = ((long long)((unsigned long long)sigma >> 3) + (long long)nx * ny * nz + 1) & ~1ll;
       const int ncol = nwc * MX_XOUT + 2;
-      const int off[5] = {G::O_EX, G::O_EY, G::O_EZ, G::O_MU, G::O_SG};
-      const int spitch[5] = {PX, PN, PN, PX, PX};
-      const int nrow[5] = {RN, RC, RN, RC, RC};
+      // which (array, row) this lane copies
+      int a = -1, r = 0;
+      {
+        int l = lane;
+        const int nrow[5] = {RN, RC, RN, RC, RC};
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          if (a < 0 && l < nrow[q]) { a = q; r = l; }
+          if (a < 0) l -= nrow[q];
+        }
+      }
+      const bool have = a >= 0;
+      const int aa = have ? a : 0;
+      const int off = aa == 0 ? G::O_EX : aa == 1 ? G::O_EY : aa == 2 ? G::O_EZ : aa == 3 ? G::O_MU : G::O_SG;
+      const int spitch = (aa == 1 || aa == 2) ? PN : PX;
+      const int jr = j0 - 1 + r;
+      const bool row_ok = have && jr >= 0 && jr < A[aa].nrows_valid;
+      const long long rowbase = A[aa].a0 + (long long)r * A[aa].pitch;
+      const long long a0 = A[aa].a0, pstr = A[aa].pstride, aend = A[aa].end;
+      const int npl = A[aa].nplanes, ploff = aa < 2 ? 1 : 0;
+      const int soff = off + 2 + r * spitch;
       for (int q = 0; q < nq; ++q) {
         const int jst = jfirst + q, slot = q % S, n = q / S;
         if (n >= 1) mbar_wait(&empty[slot], (n - 1) & 1);
-        double *tile = tiles + slot * G::STAGE;
-        unsigned total = 0;
-        // two passes over the same arithmetic: byte count first, then the copies
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll
-          for (int a = 0; a < 5; ++a) {
-            const int pl = (a < 2) ? jst + 1 : jst;
-            if (pl < 0 || pl >= A[a].nplanes) continue;
-            const long long base = A[a].a0 + A[a].pstride * pl;
-            const int lead0 = (int)(base & 1);
-#pragma unroll
-            for (int r = 0; r < RN; ++r) {
-              if (r >= nrow[a]) continue;
-              const int jr = j0 - 1 + r;
-              if (jr < 0 || jr >= A[a].nrows_valid) continue;
-              const long long Ad = base + (long long)r * A[a].pitch, Aal = Ad & ~1ll;
-              long long nel = ((Ad - Aal) + ncol + 1) & ~1ll;
-              nel = min(nel, A[a].end - Aal);
-              if (pass == 0) total += (unsigned)(nel * 8);
-              else
-                bulk_g2s(tile + off[a] + 2 + lead0 + r * spitch[a] - (int)(Ad - Aal),
-                         reinterpret_cast<const void *>(Aal << 3), (unsigned)(nel * 8), &full[slot]);
-            }
-          }
-          if (pass == 0) mbar_arrive_expect_tx(&full[slot], total);
+        const int pl = jst + ploff;
+        const bool on = row_ok && pl >= 0 && pl < npl;
+        const long long Ad = rowbase + pstr * pl, Aal = Ad & ~1ll;
+        long long nel = ((Ad - Aal) + ncol + 1) & ~1ll;
+        nel = min(nel, aend - Aal);
+        const unsigned bytes = on ? (unsigned)(nel * 8) : 0u;
+        const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
+        if (lane == 0) mbar_arrive_expect_tx(&full[slot], total);
+        __syncwarp();
+        if (bytes) {
+          const int lead0 = (int)((a0 + pstr * pl) & 1);
+          bulk_g2s(tiles + slot * G::STAGE + soff + lead0 - (int)(Ad - Aal), reinterpret_cast<const void *>(Aal << 3),
+                   bytes, &full[slot]);
         }
       }
     }
