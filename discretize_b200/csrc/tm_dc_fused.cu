@@ -277,45 +277,37 @@ __global__ void __launch_bounds__((NWC + 1) * 32, 1)
 
   if (warp == nwc) {
     // ================= producer warp =================
-    if (lane == 0) {
-      const long long pend = (((long long)((unsigned long long)phi >> 3) + pstride * nNz) + 1) & ~1ll;
-      const long long cend = (((long long)((unsigned long long)sigma >> 3) + cstride * nz) + 1) & ~1ll;
-      const int ncp = nwc * DC_XOUT + 2, ncc = nwc * DC_XOUT + 1;
+    // Lane l owns row copy l of every stage (RP phi rows, then RC sigma rows): the address arithmetic runs
+    // SIMT across the lanes, lane 0 posts the stage's byte count, then every lane issues its bulk copy.
+    {
+      const bool isp = lane < RP;
+      const bool have = lane < RP + RC;
+      const int r = isp ? lane : lane - RP;
+      const int jr = j0 - 1 + r;
+      const bool row_ok = have && jr >= 0 && jr < (isp ? nNy : ny);
+      const long long a0 = isp ? pa0 : ca0, pstr = isp ? pstride : cstride;
+      const long long rowbase = a0 + (long long)r * (isp ? nNx : nx);
+      const long long aend = isp ? ((((long long)((unsigned long long)phi >> 3) + pstride * nNz) + 1) & ~1ll)
+                                 : ((((long long)((unsigned long long)sigma >> 3) + cstride * nz) + 1) & ~1ll);
+      const int ncol = nwc * DC_XOUT + (isp ? 2 : 1);
+      const int npl = isp ? nNz : nz, ploff = isp ? 1 : 0;
+      const int soff = (isp ? 0 : G::REGP) + 2 + r * (isp ? PP : CP);
       for (int q = 0; q < nq; ++q) {
         const int jst = jfirst + q, slot = q % S, n = q / S;
         if (n >= 1) mbar_wait(&empty[slot], (n - 1) & 1);
-        double *tp = tiles + slot * G::STAGE, *tc = tp + G::REGP;
-        const int pj = jst + 1, lj = jst;
-        const bool havep = (pj >= 0) && (pj < nNz), havel = (lj >= 0) && (lj < nz);
-        const long long pa = pa0 + pstride * pj, ca = ca0 + cstride * lj;
-        const int lead0p = (int)(pa & 1), lead0c = (int)(ca & 1);
-        long long src[RP + RC];
-        unsigned bytes[RP + RC];
-        unsigned total = 0;
-#pragma unroll
-        for (int r = 0; r < RP + RC; ++r) {
-          const bool isp = r < RP;
-          const int rr = isp ? r : r - RP;
-          const int jr = j0 - 1 + rr;
-          const bool on = isp ? (havep && jr >= 0 && jr < nNy) : (havel && jr >= 0 && jr < ny);
-          const long long A = isp ? pa + (long long)rr * nNx : ca + (long long)rr * nx;
-          const long long Aal = A & ~1ll;
-          long long nel = ((A - Aal) + (isp ? ncp : ncc) + 1) & ~1ll;
-          nel = min(nel, (isp ? pend : cend) - Aal);
-          src[r] = Aal;
-          bytes[r] = on ? (unsigned)(nel * 8) : 0u;
-          total += bytes[r];
-        }
-        mbar_arrive_expect_tx(&full[slot], total);
-#pragma unroll
-        for (int r = 0; r < RP + RC; ++r) {
-          if (bytes[r] == 0) continue;
-          const bool isp = r < RP;
-          const int rr = isp ? r : r - RP;
-          // row rr lands at  base + 2 + lead0 + rr*pitch  (minus its own lead: 16-byte aligned)
-          double *dst = isp ? tp + 2 + lead0p + rr * PP - (int)((pa + (long long)rr * nNx) & 1)
-                            : tc + 2 + lead0c + rr * CP - (int)((ca + (long long)rr * nx) & 1);
-          bulk_g2s(dst, reinterpret_cast<const void *>(src[r] << 3), bytes[r], &full[slot]);
+        const int pl = jst + ploff;
+        const bool on = row_ok && pl >= 0 && pl < npl;
+        const long long Ad = rowbase + pstr * pl, Aal = Ad & ~1ll;
+        long long nel = ((Ad - Aal) + ncol + 1) & ~1ll;
+        nel = min(nel, aend - Aal);
+        const unsigned bytes = on ? (unsigned)(nel * 8) : 0u;
+        const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
+        if (lane == 0) mbar_arrive_expect_tx(&full[slot], total);
+        __syncwarp();
+        if (bytes) {
+          const int lead0 = (int)((a0 + pstr * pl) & 1);
+          bulk_g2s(tiles + slot * G::STAGE + soff + lead0 - (int)(Ad - Aal), reinterpret_cast<const void *>(Aal << 3),
+                   bytes, &full[slot]);
         }
       }
     }
@@ -359,6 +351,7 @@ __global__ void __launch_bounds__((NWC + 1) * 32, 1)
       constexpr int dummy = 0;
       (void)dummy;
       const int slot = u, slot_prev = (u + S - 1) % S;
+      if (q == 1) mbar_wait(&full[0], 0);  // stage 0 only carries plane kb-1 (read below as P0)
       mbar_wait(&full[slot], par);
       // lead bits of the planes j (stage j-1), j+1 (stage j) and of layer j (stage j)
       const int lp0 = (l0p + pbP * j) & 1, lp1 = (l0p + pbP * (j + 1)) & 1, lc = (l0c + pbC * j) & 1;
