@@ -145,7 +145,19 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.n
-    if world == 1:
+    if args.workload == "maxwell":
+        # BASELINE config 5: C^T Mf(mui) C + Me(sigma) on n^3 (1024^3 by default for this workload), z-slabs
+        from discretize_b200.slab import SlabMaxwell
+
+        op = SlabMaxwell(n, n, n, rank, world)
+        step = op.step
+        ndof_total = n * (n + 1) * (n + 1) * 3
+        alg_bytes = 8.0 * (2 * ndof_total + 2 * n ** 3) / world
+        launches_per_step = op.launches_per_step
+        parallelism = "1 GPU" if world == 1 else f"z-slabs x{world}, NCCL halo send/recv"
+        workload_name = f"TensorMesh {n}^3 Maxwell C^T Mf(mui) C + Me(sigma) fused matrix-free apply"
+        kernel_name = "k_maxwell_ring<2,NWC,PARX,4>"
+    elif world == 1:
         mesh = dz.TensorMesh([n, n, n])
         gen = torch.Generator(device=dev); gen.manual_seed(5)
         phi = torch.randn(mesh.nN, dtype=torch.float64, device=dev, generator=gen)
@@ -160,6 +172,8 @@ def run_ours(args):
         alg_bytes = 8.0 * (2 * mesh.nN + mesh.nC)
         launches_per_step = 1
         parallelism = "1 GPU"
+        workload_name = f"TensorMesh {n}^3 DC-resistivity nodal operator G^T Me(sigma) G matrix-free apply"
+        kernel_name = "k_dc_nodal_ring<4,NWC,PARX>"
     else:
         from discretize_b200.slab import SlabDCNodal
 
@@ -169,6 +183,8 @@ def run_ours(args):
         alg_bytes = 8.0 * (2 * (n + 1) ** 3 + n ** 3) / world
         launches_per_step = op.launches_per_step
         parallelism = f"z-slabs x{world}, NCCL halo send/recv"
+        workload_name = f"TensorMesh {n}^3 DC-resistivity nodal operator G^T Me(sigma) G matrix-free apply"
+        kernel_name = "k_dc_nodal_ring<4,NWC,PARX>"
 
     def sync():
         if world > 1:
@@ -199,7 +215,7 @@ def run_ours(args):
 
     # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region
     e2e = None
-    if world == 1:
+    if world == 1 and args.workload == "dc":
         host_in = torch.empty(mesh.nN, dtype=torch.float64).pin_memory()
         host_in.copy_(phi)
         host_out = torch.empty(mesh.nN, dtype=torch.float64).pin_memory()
@@ -228,18 +244,20 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"TensorMesh {n}^3 DC-resistivity nodal operator G^T Me(sigma) G matrix-free apply",
+        "config": {"workload": workload_name,
                    "dofs_per_step": int(ndof_total), "parallelism": parallelism,
-                   "l2": "inputs (phi 1.08 GB + sigma 1.07 GB) exceed the 126 MB L2; no flush needed"},
+                   "l2": "inputs (>= 2 GB per GPU at N=1) exceed the 126 MB L2; no flush needed"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "k_dc_nodal<RY>",
+                     "traffic": 3.25e9 if (args.workload == "dc" and n == 512 and world == 1) else None,
+                     "traffic_source": "ncu --set full, profiles/r1_k8_dc_nodal_ring_ncu_full_summary.txt (dram read+write per launch)",
+                     "peak_source": peak_src, "kernel": kernel_name,
                      "algorithmic_bytes_per_launch": alg_bytes},
     }
     if e2e is not None:
         line["e2e"] = e2e
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and args.workload == "dc":
         val, dt, _ = cpu_reference_arm(args.cpu_n, 3, 1)
         line["cpu_baseline"] = {
             "value": val, "unit": UNIT, "cores": 1, "kind": "port",
@@ -257,10 +275,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=512, help="cells per axis (512 = BASELINE configs[1])")
+    ap.add_argument("--n", type=int, default=None, help="cells per axis (default 512 for dc = BASELINE configs[1], 1024 for maxwell)")
+    ap.add_argument("--workload", default="dc", choices=["dc", "maxwell"],
+                    help="dc = configs[1] (the N=1 headline); maxwell = configs[4], the 1024^3 z-slab scaling case")
     ap.add_argument("--cpu-n", type=int, default=128, help="cells per axis of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    if args.n is None:
+        args.n = 512 if args.workload == "dc" else 1024
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -134,3 +134,109 @@ class SlabDCNodal:
     def owned_output(self):
         L = self.layout
         return self.out[L.p_own0 * L.plane:L.p_own1 * L.plane]
+
+
+# ---------------------------------------------------------------------------------------------------
+# Maxwell:  y = C^T Mf(mui) C e + Me(sigma) e   (BASELINE config 5)
+# ---------------------------------------------------------------------------------------------------
+class EdgeSlab:
+    """Offsets of the local stacked edge vector [Ex; Ey; Ez] of a rank's sub-mesh."""
+
+    def __init__(self, layout: SlabLayout):
+        L = layout
+        nx, ny, nzl = L.nx, L.ny, L.nz_local
+        self.px = nx * (ny + 1)            # Ex entries per node plane
+        self.py = (nx + 1) * ny            # Ey entries per node plane
+        self.pz = (nx + 1) * (ny + 1)      # Ez entries per cell layer
+        self.off_y = self.px * (nzl + 1)
+        self.off_z = self.off_y + self.py * (nzl + 1)
+        self.n = self.off_z + self.pz * nzl
+
+    def ex(self, v, k):
+        return v[k * self.px:(k + 1) * self.px]
+
+    def ey(self, v, k):
+        return v[self.off_y + k * self.py:self.off_y + (k + 1) * self.py]
+
+    def ez(self, v, k):
+        return v[self.off_z + k * self.pz:self.off_z + (k + 1) * self.pz]
+
+
+def exchange_edge_halos(local, layout: SlabLayout, es: EdgeSlab, group=None):
+    """Halo exchange of an edge field: Ex, Ey plane c0 go down; Ex, Ey plane c1-1 and Ez layer c1-1 go up."""
+    L = layout
+    ops = []
+    if L.has_lower:
+        lo = L.p_own0
+        ops += [dist.P2POp(dist.isend, es.ex(local, lo), L.rank - 1, group),
+                dist.P2POp(dist.isend, es.ey(local, lo), L.rank - 1, group),
+                dist.P2POp(dist.irecv, es.ex(local, lo - 1), L.rank - 1, group),
+                dist.P2POp(dist.irecv, es.ey(local, lo - 1), L.rank - 1, group),
+                dist.P2POp(dist.irecv, es.ez(local, lo - 1), L.rank - 1, group)]
+    if L.has_upper:
+        hi = L.p_own1 - 1
+        ops += [dist.P2POp(dist.isend, es.ex(local, hi), L.rank + 1, group),
+                dist.P2POp(dist.isend, es.ey(local, hi), L.rank + 1, group),
+                dist.P2POp(dist.isend, es.ez(local, hi), L.rank + 1, group),
+                dist.P2POp(dist.irecv, es.ex(local, hi + 1), L.rank + 1, group),
+                dist.P2POp(dist.irecv, es.ey(local, hi + 1), L.rank + 1, group)]
+    return dist.batch_isend_irecv(ops) if ops else []
+
+
+class SlabMaxwell:
+    """y = C^T Mf(mui) C e + Me(sigma) e on a z-slab decomposed TensorMesh (fused kernel K9 per rank)."""
+
+    def __init__(self, nx, ny, nz, rank, world, seed_e=11, seed_sigma=12, seed_mui=13, h=None):
+        import discretize_b200 as dz
+
+        self.layout = L = SlabLayout(nx, ny, nz, rank, world)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        hx, hy, hz = h if h is not None else (np.ones(nx) / nx, np.ones(ny) / ny, np.ones(nz) / nz)
+        self.mesh = dz.TensorMesh([np.asarray(hx), np.asarray(hy), np.asarray(hz)[L.l0:L.l1]])
+        self.es = es = EdgeSlab(L)
+        self.sigma = torch.cat([plane_field(seed_sigma, k, L.layer, dev, log_normal=True) for k in range(L.l0, L.l1)])
+        self.mui = torch.cat([plane_field(seed_mui, k, L.layer, dev, log_normal=True) for k in range(L.l0, L.l1)])
+        self.e = torch.zeros(es.n, dtype=torch.float64, device=dev)
+        n_own_layers = L.c1 - L.c0
+        for lp in range(L.p_own0, L.p_own1):      # owned node planes: Ex, Ey
+            g = L.l0 + lp
+            es.ex(self.e, lp).copy_(plane_field(seed_e, 3 * g, es.px, dev))
+            es.ey(self.e, lp).copy_(plane_field(seed_e, 3 * g + 1, es.py, dev))
+        for lp in range(L.p_own0, L.p_own0 + n_own_layers):   # owned cell layers: Ez
+            es.ez(self.e, lp).copy_(plane_field(seed_e, 3 * (L.l0 + lp) + 2, es.pz, dev))
+        self.out = torch.zeros_like(self.e)
+        Cm = self.mesh.edge_curl
+        self.op = Cm.T @ self.mesh.get_face_inner_product(self.mui) @ Cm + self.mesh.get_edge_inner_product(self.sigma)
+        assert type(self.op).__name__ == "MaxwellOperator"
+        self.comm_stream = torch.cuda.Stream(device=dev)
+        self.launches_per_step = 3 if world > 1 else 1
+        self.n_owned_edges = ((L.p_own1 - L.p_own0) * (es.px + es.py) + n_own_layers * es.pz)
+
+    def step(self):
+        L, op = self.layout, self.op
+        main = torch.cuda.current_stream()
+        if L.world == 1:
+            op.apply_planes(self.e, self.out, L.p_own0, L.p_own1)
+            return self.out
+        self.comm_stream.wait_stream(main)
+        with torch.cuda.stream(self.comm_stream):
+            for r in exchange_edge_halos(self.e, L, self.es):
+                r.wait()
+        lo = L.p_own0 + (1 if L.has_lower else 0)
+        hi = L.p_own1 - (1 if L.has_upper else 0)
+        if hi > lo:
+            op.apply_planes(self.e, self.out, lo, hi)
+        main.wait_stream(self.comm_stream)
+        if L.has_lower and lo > L.p_own0:
+            op.apply_planes(self.e, self.out, L.p_own0, min(lo, L.p_own1))
+        if L.has_upper and hi < L.p_own1 and hi >= lo:
+            op.apply_planes(self.e, self.out, max(hi, lo), L.p_own1)
+        return self.out
+
+    def owned_parts(self, v):
+        """(Ex planes, Ey planes, Ez layers) owned by this rank, as views of a local edge vector."""
+        L, es = self.layout, self.es
+        n_own_layers = L.c1 - L.c0
+        return (v[L.p_own0 * es.px:L.p_own1 * es.px],
+                v[es.off_y + L.p_own0 * es.py:es.off_y + L.p_own1 * es.py],
+                v[es.off_z + L.p_own0 * es.pz:es.off_z + (L.p_own0 + n_own_layers) * es.pz])

@@ -329,6 +329,11 @@ class MaxwellOperator(Operator):
 
     _dev_apply_t = _dev_apply
 
+    def apply_planes(self, x, out, k_begin, k_end):
+        """Write only Ex, Ey on node planes / Ez in cell layers k_begin <= k < k_end (z-slab building block)."""
+        check(load().dzb_tm_maxwell_range(C.byref(self.mesh.device_mesh()), ptr(self.mui), ptr(self.sigma), ptr(x),
+                                          ptr(out), int(k_begin), int(k_end), stream_ptr()), "dzb_tm_maxwell_range")
+
     def _transpose(self):
         return self
 

@@ -85,3 +85,53 @@ def test_halo_exchange_gloo(world):
         assert p.exitcode == 0
     results = dict(q.get(timeout=10) for _ in range(world))
     assert all(results[r] for r in range(world)), results
+
+
+def _edge_worker(rank, world, port, nx, ny, nz, q):
+    from discretize_b200.slab import EdgeSlab, exchange_edge_halos
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = SlabLayout(nx, ny, nz, rank, world)
+        es = EdgeSlab(L)
+        # global edge field: value encodes (component, global plane / layer, index in plane)
+        def gval(comp, g, n):
+            return comp * 1e6 + g * 1e3 + torch.arange(n, dtype=torch.float64) * 1e-3
+        local = torch.full((es.n,), -1.0, dtype=torch.float64)
+        for lp in range(L.p_own0, L.p_own1):
+            es.ex(local, lp).copy_(gval(1, L.l0 + lp, es.px))
+            es.ey(local, lp).copy_(gval(2, L.l0 + lp, es.py))
+        for lp in range(L.p_own0, L.p_own0 + (L.c1 - L.c0)):
+            es.ez(local, lp).copy_(gval(3, L.l0 + lp, es.pz))
+        for r in exchange_edge_halos(local, L, es):
+            r.wait()
+        ok = True
+        if L.has_lower:
+            lp = L.p_own0 - 1
+            ok &= bool(torch.equal(es.ex(local, lp), gval(1, L.l0 + lp, es.px)))
+            ok &= bool(torch.equal(es.ey(local, lp), gval(2, L.l0 + lp, es.py)))
+            ok &= bool(torch.equal(es.ez(local, lp), gval(3, L.l0 + lp, es.pz)))
+        if L.has_upper:
+            lp = L.p_own1
+            ok &= bool(torch.equal(es.ex(local, lp), gval(1, L.l0 + lp, es.px)))
+            ok &= bool(torch.equal(es.ey(local, lp), gval(2, L.l0 + lp, es.py)))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_edge_halo_exchange_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_edge_worker, args=(r, world, port, 5, 4, 7, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    results = dict(q.get(timeout=10) for _ in range(world))
+    assert all(results[r] for r in range(world)), results
