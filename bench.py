@@ -150,7 +150,7 @@ def run_ours(args):
         from discretize_b200.slab import SlabMaxwell
 
         op = SlabMaxwell(n, n, n, rank, world)
-        step = op.step
+        step = op.step_graphed if (world > 1 and not args.eager) else op.step
         ndof_total = n * (n + 1) * (n + 1) * 3
         alg_bytes = 8.0 * (2 * ndof_total + 2 * n ** 3) / world
         launches_per_step = op.launches_per_step
@@ -178,7 +178,7 @@ def run_ours(args):
         from discretize_b200.slab import SlabDCNodal
 
         op = SlabDCNodal(n, n, n, rank, world, seed_phi=5, seed_sigma=6)
-        step = op.step
+        step = op.step_graphed if not args.eager else op.step
         ndof_total = (n + 1) ** 3
         alg_bytes = 8.0 * (2 * (n + 1) ** 3 + n ** 3) / world
         launches_per_step = op.launches_per_step
@@ -248,6 +248,8 @@ def run_ours(args):
                    "dofs_per_step": int(ndof_total), "parallelism": parallelism,
                    "l2": "inputs (>= 2 GB per GPU at N=1) exceed the 126 MB L2; no flush needed"},
         "gpu_launches": launches_per_step * args.steps,
+        "launch_mode": ("cuda-graph replay" if (world > 1 and not args.eager and not getattr(op, "_graph_failed", False))
+                        else "eager"),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": 3.25e9 if (args.workload == "dc" and n == 512 and world == 1) else None,
@@ -280,6 +282,7 @@ def main():
                     help="dc = configs[1] (the N=1 headline); maxwell = configs[4], the 1024^3 z-slab scaling case")
     ap.add_argument("--cpu-n", type=int, default=128, help="cells per axis of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--eager", action="store_true", help="multi-GPU: launch every step from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.n is None:
         args.n = 512 if args.workload == "dc" else 1024

@@ -74,6 +74,36 @@ def exchange_node_halos(local, layout: SlabLayout, group=None):
     return dist.batch_isend_irecv(ops)
 
 
+class _GraphedStep:
+    """Mixin: replay one distributed apply (NCCL halo exchange + kernels) as a CUDA graph.
+
+    At 8 GPUs a 512^3 slab apply is ~70 us of kernel time; enqueueing the exchange and three launches from
+    Python costs more than that, so the whole step is captured once and replayed (falls back to eager
+    launches if the capture is refused)."""
+
+    _graph = None
+    _graph_failed = False
+
+    def step_graphed(self):
+        if self._graph_failed:
+            return self.step()
+        if self._graph is None:
+            try:
+                self.step()                      # warm up: NCCL communicators, kernel attributes
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.step()
+                self._graph = g
+            except Exception as exc:             # pragma: no cover - depends on the NCCL / driver
+                self._graph_failed = True
+                self._graph_error = repr(exc)
+                torch.cuda.synchronize()
+                return self.step()
+        self._graph.replay()
+        return self.out
+
+
 def plane_field(seed, k, n, device, log_normal=False):
     """Plane k of a synthetic global field: identical for every decomposition (keyed by k)."""
     gen = torch.Generator(device=device)
@@ -82,7 +112,7 @@ def plane_field(seed, k, n, device, log_normal=False):
     return torch.exp(x) if log_normal else x
 
 
-class SlabDCNodal:
+class SlabDCNodal(_GraphedStep):
     """y = G^T Me(sigma) G phi on a z-slab decomposed TensorMesh([nx, ny, nz]) (unit cube widths).
 
     ``step()`` performs one distributed apply: halo exchange of phi (side stream) overlapped with
@@ -183,7 +213,7 @@ def exchange_edge_halos(local, layout: SlabLayout, es: EdgeSlab, group=None):
     return dist.batch_isend_irecv(ops) if ops else []
 
 
-class SlabMaxwell:
+class SlabMaxwell(_GraphedStep):
     """y = C^T Mf(mui) C e + Me(sigma) e on a z-slab decomposed TensorMesh (fused kernel K9 per rank)."""
 
     def __init__(self, nx, ny, nz, rank, world, seed_e=11, seed_sigma=12, seed_mui=13, h=None):
