@@ -233,9 +233,16 @@ def run_ours(args):
                "d2h_bytes_per_step": int(8 * mesh.nN), "ms_per_step": dt * 1e3,
                "api": "A = G.T @ mesh.get_edge_inner_product(sigma) @ G; A.matvec(x_host_pinned, out=y_host_pinned)"}
 
-    if rank != 0:
+    def shutdown():
+        # A process group that was captured into a CUDA graph can hang in destroy_process_group();
+        # every rank has its result by now, so leave without tearing NCCL down.
         if world > 1:
-            dist.destroy_process_group()
+            sys.stdout.flush()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        shutdown()
         return
 
     peak, peak_src = measured_peak()
@@ -267,8 +274,7 @@ def run_ours(args):
                       f"(oracle port of the reference build), 1 of {os.cpu_count()} host cores",
         }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 def main():

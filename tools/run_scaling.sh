@@ -6,9 +6,9 @@ for wl in maxwell dc; do
   : > gpurun_out/scale_$wl.jsonl
   for n in 1 2 4 8; do
     if [ "$n" = 1 ]; then
-      timeout 400 python bench.py --gpus 1 --workload $wl --steps 10 --warmup 3 --no-cpu 2>/dev/null | grep metric >> gpurun_out/scale_$wl.jsonl
+      timeout 200 python bench.py --gpus 1 --workload $wl --steps 10 --warmup 3 --no-cpu 2>/dev/null | grep metric >> gpurun_out/scale_$wl.jsonl
     else
-      timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600+n)) bench.py --gpus $n --workload $wl --steps 10 --warmup 3 2>/dev/null | grep metric >> gpurun_out/scale_$wl.jsonl
+      timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600+n)) bench.py --gpus $n --workload $wl --steps 10 --warmup 3 2>/dev/null | grep metric >> gpurun_out/scale_$wl.jsonl
     fi
   done
   python - <<PY
