@@ -422,6 +422,11 @@ static int launch_dc_ring_t(const TM &m, const double *sigma, const double *phi,
     attr_done = true;
   }
   const int nNy = (int)m.ny + 1;
+  // short plane ranges (z-slabs on many GPUs): shrink the z-chunk until the grid has ~4 waves of blocks
+  const int nxy = xblocks * ((nNy + RY - 1) / RY);
+  const int zb_target = (4 * 148 + nxy - 1) / nxy;
+  const int fair = (k_end - k_begin + zb_target - 1) / zb_target;
+  kchunk = kchunk < fair ? kchunk : (fair < 8 ? 8 : fair);
   dim3 grid((unsigned)xblocks, (unsigned)((nNy + RY - 1) / RY), (unsigned)((k_end - k_begin + kchunk - 1) / kchunk));
   k_dc_nodal_ring<RY, NWC, PARX><<<grid, dim3((nwc + 1) * 32), G::SMEM, s>>>(m, sigma, phi, y, kchunk, nwc, k_begin,
                                                                            k_end);

@@ -71,7 +71,11 @@ static int launch_mx_ring_t(const TM &m, const double *mui, const double *sigma,
     attr_done = true;
   }
   const int nNy = (int)m.ny + 1;
-  const int kchunk = g_mx_kchunk;
+  int kchunk = g_mx_kchunk;
+  const int nxy = xblocks * ((nNy + 1) / 2);
+  const int zb_target = (4 * 148 + nxy - 1) / nxy;
+  const int fair = (k_end - k_begin + zb_target - 1) / zb_target;
+  kchunk = kchunk < fair ? kchunk : (fair < 8 ? 8 : fair);
   dim3 grid((unsigned)xblocks, (unsigned)((nNy + 1) / 2), (unsigned)((k_end - k_begin + kchunk - 1) / kchunk));
   k_maxwell_ring<2, NWC, PARX, NSLOT><<<grid, dim3((nwc + 1) * 32), G::SMEM, s>>>(m, mui, sigma, e, y, kchunk, nwc,
                                                                                    k_begin, k_end);

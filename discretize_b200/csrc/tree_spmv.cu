@@ -64,6 +64,32 @@ __global__ void __launch_bounds__(256)
   if (row < nrows && l == 0) y[row] = acc;
 }
 
+// generic CSR with stored float64 values (scipy matrices mixed into operator algebra, full-tensor
+// OcTree mass matrices): same lane-group mapping, values read instead of generated
+template <int LPR, typename IP>
+__global__ void __launch_bounds__(256)
+    k_csr_spmv(i64 nrows, const IP *__restrict__ indptr, const int *__restrict__ indices, const double *__restrict__ vals,
+               const double *__restrict__ x, double *__restrict__ y) {
+  const i64 gid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const i64 row = gid / LPR;
+  const int l = (int)(gid % LPR);
+  double acc = 0.0;
+  if (row < nrows) {
+    const i64 p0 = (i64)indptr[row], p1 = (i64)indptr[row + 1];
+    for (i64 p = p0 + l; p < p1; p += LPR) acc += __ldg(vals + p) * __ldg(x + __ldg(indices + p));
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (row < nrows && l == 0) y[row] = acc;
+}
+
+template <int LPR, typename IP>
+static void launch_csr(i64 nrows, const void *indptr, const int *indices, const double *vals, const double *x, double *y,
+                       cudaStream_t s) {
+  const unsigned blocks = (unsigned)((nrows * LPR + 255) / 256);
+  k_csr_spmv<LPR, IP><<<blocks, 256, 0, s>>>(nrows, (const IP *)indptr, indices, vals, x, y);
+}
+
 // y[i] = d[i] * x[i]  or  x[i] / d[i]
 __global__ void k_diag_scale(i64 n, const double *__restrict__ d, const double *__restrict__ x, double *__restrict__ y,
                              int invert) {
@@ -118,6 +144,25 @@ extern "C" int dzb_tree_spmv(int64_t nrows, const void *indptr, int indptr_is64,
     else dispatch_lpr<false, int>(lanes_per_row, nrows, indptr, indices, codes, tab_mult, tab_sel, ntab, g0, g1, g2, x, y, s);
   }
   return check_launch("dzb_tree_spmv");
+}
+
+extern "C" int dzb_csr_spmv(int64_t nrows, const void *indptr, int indptr_is64, const int32_t *indices,
+                            const double *values, const double *x, double *y, int lanes_per_row, void *stream) {
+  if (nrows <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+#define DZB_CSR_CASE(L)                                                                   \
+  case L:                                                                                 \
+    if (indptr_is64) launch_csr<L, i64>(nrows, indptr, indices, values, x, y, s);         \
+    else launch_csr<L, int>(nrows, indptr, indices, values, x, y, s);                     \
+    break;
+  switch (lanes_per_row) {
+    DZB_CSR_CASE(1) DZB_CSR_CASE(2) DZB_CSR_CASE(4) DZB_CSR_CASE(8) DZB_CSR_CASE(16)
+    default:
+      if (indptr_is64) launch_csr<32, i64>(nrows, indptr, indices, values, x, y, s);
+      else launch_csr<32, int>(nrows, indptr, indices, values, x, y, s);
+  }
+#undef DZB_CSR_CASE
+  return check_launch("dzb_csr_spmv");
 }
 
 extern "C" int dzb_diag_scale(int64_t n, const double *d, const double *x, double *y, int invert, void *stream) {

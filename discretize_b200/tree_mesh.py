@@ -563,6 +563,16 @@ class TreeMesh:
         TensorMesh._check_removed_kwargs(kwargs)
         return make_tree_mass_operator(self, proj, model, invert_model, invert_matrix)
 
+    def get_face_inner_product_deriv(self, model, do_fast=True, invert_model=False, invert_matrix=False, **kwargs):
+        from .tree_ops import make_tree_mass_deriv
+
+        return make_tree_mass_deriv(self, "F", model, do_fast, invert_model, invert_matrix)
+
+    def get_edge_inner_product_deriv(self, model, do_fast=True, invert_model=False, invert_matrix=False, **kwargs):
+        from .tree_ops import make_tree_mass_deriv
+
+        return make_tree_mass_deriv(self, "E", model, do_fast, invert_model, invert_matrix)
+
     def get_interpolation_matrix(self, loc, location_type="cell_centers", zeros_outside=False, **kwargs):
         raise NotImplementedError("TreeMesh.get_interpolation_matrix is not part of the five target configurations (SURVEY N3)")
 

@@ -166,7 +166,143 @@ class TreeMassDiag(Operator):
         return sp.diags(self.diagonal(), format="csr")
 
 
+def _tree_corner_projections(mesh, proj):
+    """The 8 corner projection matrices P_n (3nC x n), deflated: tree_ext.pyx:5651-5763 (_getFaceP /
+    _getEdgeP) with the corner tables of operators/inner_products.py:247-269.  Corner n = (a,b,c):
+    faces  fx(a), fy(b), fz(c);  edges  ex(b,c), ey(a,c), ez(a,b)."""
+    t = mesh._t()
+    nC = t.n_cells
+    fams = t.faces if proj == "F" else t.edges
+    cell_ents = t.cell_faces if proj == "F" else t.cell_edges
+    off = np.r_[0, np.cumsum([f.n_total for f in fams])]
+    R = mesh._deflate_faces() if proj == "F" else mesh._deflate_edges()
+    rows = np.arange(3 * nC)
+    Ps = []
+    for c in (0, 1):
+        for b in (0, 1):
+            for a in (0, 1):
+                if proj == "F":
+                    local = (a, b, c)                         # which of the 2 faces per direction
+                else:
+                    local = (b + 2 * c, a + 2 * c, a + 2 * b)  # which of the 4 edges per direction
+                cols = np.concatenate([off[d] + fams[d].index[cell_ents[d][:, local[d]]] for d in range(3)])
+                P = sp.csr_matrix((np.ones(3 * nC), (rows, cols)), shape=(3 * nC, off[3]))
+                Ps.append((P @ R).tocsr())
+    return Ps
+
+
+def _tree_tensor_mass_matrix(mesh, proj, model, invert_model):
+    """M = sum_n P_n^T sqrt(V/8) Sigma sqrt(V/8) P_n  (operators/inner_products.py:147-272), host assembly."""
+    nC = mesh.n_cells
+    t = np.asarray(model, dtype=np.float64).reshape((nC, 6), order="F")
+    if invert_model:
+        a11, a22, a33, a12, a13, a23 = (t[:, q] for q in range(6))
+        det = (a11 * a22 * a33 + a12 * a23 * a13 + a13 * a12 * a23 - a13 * a22 * a13 - a12 * a12 * a33 - a11 * a23 * a23)
+        t = np.stack([(a22 * a33 - a23 * a23) / det, (a11 * a33 - a13 * a13) / det, (a11 * a22 - a12 * a12) / det,
+                      -(a12 * a33 - a13 * a23) / det, (a12 * a23 - a13 * a22) / det, -(a11 * a23 - a13 * a12) / det], axis=1)
+    d = lambda v: sp.diags(v)
+    Sigma = sp.bmat([[d(t[:, 0]), d(t[:, 3]), d(t[:, 4])],
+                     [d(t[:, 3]), d(t[:, 1]), d(t[:, 5])],
+                     [d(t[:, 4]), d(t[:, 5]), d(t[:, 2])]]).tocsr()
+    sq = sp.diags(np.tile(np.sqrt(0.125 * mesh.cell_volumes), 3))
+    acc = None
+    for P in _tree_corner_projections(mesh, proj):
+        VP = sq @ P
+        term = VP.T @ Sigma @ VP
+        acc = term if acc is None else acc + term
+    acc = sp.csr_matrix(acc)
+    acc.sum_duplicates()
+    acc.sort_indices()
+    return acc
+
+
+class TreeMassDerivDiag(Operator):
+    """F(v) = d(M(m) v)/dm for diagonal (scalar / isotropic / anisotropic) models on a TreeMesh
+    (base/base_tensor_mesh.py:865-988 with the tree averages): F(v) = diag(v r) (k Av^T) diag(V c)."""
+
+    def __init__(self, mesh, proj, md, v, invert_model, invert_matrix, ncols, scalar_mode):
+        from . import _lib
+
+        n = mesh.n_faces if proj == "F" else mesh.n_edges
+        super().__init__((n, ncols))
+        dev = cuda_device()
+        nC = mesh.n_cells
+        self.scalar_mode = scalar_mode
+        base = "average_face_to_cell" if proj == "F" else "average_edge_to_cell"
+        aniso = md.kind == _lib.MODEL_ANISO
+        self.Av = mesh._operator(base + ("_vector" if aniso else ""))
+        self.k = 1.0 if aniso else 3.0
+        V = to_device(mesh.cell_volumes)
+        m = torch.full((nC,), md.scalar, dtype=torch.float64, device=dev) if md.kind == _lib.MODEL_SCALAR else md.dev
+        self.colscale = V.repeat(3) if aniso else V.clone()
+        if invert_model:
+            self.colscale = self.colscale * ((1.0 if invert_matrix else -1.0) / (m * m))
+        self.rowscale = to_device(v).reshape(-1).clone()
+        if invert_matrix:
+            MI = TreeMassDiag(mesh, proj, md.scalar if md.kind == _lib.MODEL_SCALAR else md.dev, invert_model, False).diag
+            mi2 = 1.0 / (MI * MI)
+            self.rowscale = self.rowscale * (mi2 if invert_model else -mi2)
+        self.nC = nC
+
+    def _dev_apply(self, x, out):
+        if self.scalar_mode == "broadcast":
+            x = x.expand(self.nC)
+        tmp = self.Av.apply_device(self.colscale * x, transpose=True)
+        torch.mul(tmp, self.rowscale, out=out)
+        out.mul_(self.k)
+
+    def _dev_apply_t(self, x, out):
+        tmp = self.Av.apply_device(self.rowscale * x, transpose=False)
+        tmp.mul_(self.colscale).mul_(self.k)
+        if self.scalar_mode == "broadcast":
+            out.copy_(tmp.sum().reshape(1))
+        else:
+            out.copy_(tmp)
+
+    def _tocsr(self):
+        Av = self.Av.tocsr()
+        M = sp.diags(self.rowscale.cpu().numpy()) @ (self.k * Av.T) @ sp.diags(self.colscale.cpu().numpy())
+        if self.scalar_mode == "broadcast":
+            M = sp.csr_matrix(M @ np.ones((self.nC, 1)))
+        return sp.csr_matrix(M)
+
+
 def make_tree_mass_operator(mesh, proj, model, invert_model, invert_matrix):
+    from . import _lib
+    from .csr import CsrOperator
+    from .tensor_ops import _Model
+
     if proj not in ("F", "E"):
         raise TypeError("projection_type must be 'F' for faces or 'E' for edges")
+    md = _Model(mesh, model)
+    if md.kind == _lib.MODEL_TENSOR:
+        if invert_matrix:
+            raise Exception("Solver needed to invert A.")
+        host = model.cpu().numpy() if isinstance(model, torch.Tensor) else np.asarray(model)
+        return CsrOperator(_tree_tensor_mass_matrix(mesh, proj, host, invert_model))
     return TreeMassDiag(mesh, proj, model, invert_model, invert_matrix)
+
+
+def make_tree_mass_deriv(mesh, proj, model, do_fast, invert_model, invert_matrix):
+    from . import _lib
+    from .tensor_ops import _Model
+
+    md = _Model(mesh, model)
+    if md.tt == -1:
+        return None
+    if md.kind == _lib.MODEL_TENSOR:
+        raise NotImplementedError("full-tensor model derivatives on TreeMesh are not built yet")
+    nC = mesh.n_cells
+    if md.tt == 0:
+        if invert_model and not invert_matrix:
+            raise TypeError("Vector must be a numpy array")  # the reference raises here, too
+        ncols, mode = (nC, None) if (invert_matrix and not invert_model) else (1, "broadcast")
+    else:
+        ncols, mode = md.n_params, None
+
+    def inner_product_deriv(v=None):
+        if v is None:
+            raise Exception("v must be supplied for this implementation.")
+        return TreeMassDerivDiag(mesh, proj, md, v, invert_model, invert_matrix, ncols, mode)
+
+    return inner_product_deriv

@@ -166,6 +166,11 @@ int dzb_points_inside(const double *pts, int64_t npts, const double *lo_host, co
 int dzb_tree_spmv(int64_t nrows, const void *indptr, int indptr_is64, const int32_t *indices, const uint8_t *codes,
                   const double *tab_mult, const uint8_t *tab_sel, int ntab, const double *g0, const double *g1,
                   const double *g2, int geom_by_col, const double *x, double *y, int lanes_per_row, void *stream);
+/* y = A x for a CSR matrix with stored float64 values (int32 columns, int32 / int64 indptr): scipy
+ * matrices mixed into operator algebra and the full-tensor OcTree mass matrices
+ * (operators/inner_products.py:147-272 with tree_ext.pyx:5651-5763 projections). */
+int dzb_csr_spmv(int64_t nrows, const void *indptr, int indptr_is64, const int32_t *indices, const double *values,
+                 const double *x, double *y, int lanes_per_row, void *stream);
 /* y = d .* x (invert == 0) or x ./ d: diagonal mass matrices on a TreeMesh
  * (base/base_tensor_mesh.py:792-863 with the tree averages). */
 int dzb_diag_scale(int64_t n, const double *d, const double *x, double *y, int invert, void *stream);

@@ -64,6 +64,16 @@ def main():
         put("Me_iso_inv", mesh.get_edge_inner_product(sig, invert_model=True, invert_matrix=True))
         put("Mf_aniso", mesh.get_face_inner_product(sig3))
         put("Me_aniso", mesh.get_edge_inner_product(sig3))
+        sig6 = np.c_[rng.random((mesh.nC, 3)) + 2.0, rng.random((mesh.nC, 3)) * 0.5 - 0.25]
+        out[f"{tag}_sigma6"] = sig6
+        put("Mf_tensor", mesh.get_face_inner_product(sig6))
+        put("Me_tensor_inv", mesh.get_edge_inner_product(sig6, invert_model=True))
+        vF, vE = rng.standard_normal(mesh.nF), rng.standard_normal(mesh.nE)
+        out[f"{tag}_vF"], out[f"{tag}_vE"] = vF, vE
+        put("dMf_iso", mesh.get_face_inner_product_deriv(sig)(vF))
+        put("dMe_iso_inv", mesh.get_edge_inner_product_deriv(sig, invert_model=True, invert_matrix=True)(vE))
+        put("dMe_aniso", mesh.get_edge_inner_product_deriv(sig3)(vE))
+        put("dMf_aniso_invmat", mesh.get_face_inner_product_deriv(sig3, invert_matrix=True)(vF))
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tree_small.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

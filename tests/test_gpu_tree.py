@@ -48,6 +48,50 @@ def test_tree_mass_matrices(gold, tag):
         assert_same_matrix(op.tocsr(), ref)
 
 
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_tree_tensor_mass_and_derivs(gold, tag):
+    m = _mesh_from_fixture(gold, tag, "state")
+    rng = np.random.default_rng(10)
+    sig, sig3, sig6 = gold[f"{tag}_sigma"], gold[f"{tag}_sigma3"], gold[f"{tag}_sigma6"]
+    vF, vE = gold[f"{tag}_vF"], gold[f"{tag}_vE"]
+    cases = [
+        ("Mf_tensor", m.get_face_inner_product(sig6)),
+        ("Me_tensor_inv", m.get_edge_inner_product(sig6, invert_model=True)),
+        ("dMf_iso", m.get_face_inner_product_deriv(sig)(vF)),
+        ("dMe_iso_inv", m.get_edge_inner_product_deriv(sig, invert_model=True, invert_matrix=True)(vE)),
+        ("dMe_aniso", m.get_edge_inner_product_deriv(sig3)(vE)),
+        ("dMf_aniso_invmat", m.get_face_inner_product_deriv(sig3, invert_matrix=True)(vF)),
+    ]
+    for key, op in cases:
+        ref = golden_matrix(gold, f"{tag}_{key}")
+        assert op.shape == ref.shape, key
+        x, y = rng.standard_normal(ref.shape[1]), rng.standard_normal(ref.shape[0])
+        assert_close_vec(op @ x, ref @ x)
+        assert_close_vec(op.T @ y, ref.T @ y)
+        a, b = op.tocsr(), ref.copy()
+        a.eliminate_zeros(); b.eliminate_zeros()
+        assert_same_matrix(a, b)
+    with pytest.raises(Exception, match="Solver needed"):
+        m.get_face_inner_product(sig6, invert_matrix=True)
+
+
+def test_scipy_matrix_in_operator_algebra(gold):
+    """A scipy.sparse projection mixed into the algebra becomes a device CSR operator (dzb_csr_spmv)."""
+    import scipy.sparse as sp
+
+    m = _mesh_from_fixture(gold, "a", "state")
+    rng = np.random.default_rng(11)
+    keep = np.sort(rng.choice(m.nN, m.nN // 2, replace=False))
+    P = sp.csr_matrix((np.ones(keep.size), (keep, np.arange(keep.size))), shape=(m.nN, keep.size))
+    G = m.nodal_gradient
+    A = P.T @ (G.T @ m.get_edge_inner_product(gold["a_sigma"]) @ G) @ P
+    Gr = golden_matrix(gold, "a_nodal_gradient")
+    Ar = P.T @ Gr.T @ golden_matrix(gold, "a_Me_iso") @ Gr @ P
+    x = rng.standard_normal(keep.size)
+    assert_close_vec(A @ x, Ar @ x)
+    assert_close_vec((G @ P) @ x, Gr @ (P @ x))
+
+
 def test_tree_composite_and_aliases(gold):
     m = _mesh_from_fixture(gold, "a", "refine")
     C, Mf, Me = m.edge_curl, m.get_face_inner_product(gold["a_sigma"]), m.get_edge_inner_product(gold["a_sigma"])
