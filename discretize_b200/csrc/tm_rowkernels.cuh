@@ -27,6 +27,30 @@ __global__ void __launch_bounds__(BX *BY *BZ) k_apply(R gen, TM m, const double 
   y[R::template row_off<COMP>(m) + m.lidx<LOC>(i, j, k)] = acc;
 }
 
+// All three row blocks of a vector-valued operator in ONE launch: thread (i,j,k) emits the row of every
+// component that exists at (i,j,k).  The components read overlapping input entries (e.g. the three curl
+// components share every edge value twice), so launching them together lets L1/L2 serve the re-reads and
+// the input crosses HBM once instead of once per component.
+template <class R, int COMP>
+__device__ __forceinline__ void apply_one(const R &gen, const TM &m, i64 i, i64 j, i64 k, const double *__restrict__ x,
+                                          double *__restrict__ y) {
+  constexpr int LOC = R::template loc<COMP>();
+  if (i >= m.sx<LOC>() || j >= m.sy<LOC>() || k >= m.sz<LOC>()) return;
+  double acc = 0.0;
+  gen.template row<COMP>(m, i, j, k, [&](i64 c, double v) { acc += v * __ldg(x + c); });
+  y[R::template row_off<COMP>(m) + m.lidx<LOC>(i, j, k)] = acc;
+}
+
+template <class R>
+__global__ void __launch_bounds__(BX *BY *BZ) k_apply3(R gen, TM m, const double *__restrict__ x, double *__restrict__ y) {
+  const i64 i = (i64)blockIdx.x * BX + threadIdx.x;
+  const i64 j = (i64)blockIdx.y * BY + threadIdx.y;
+  const i64 k = (i64)blockIdx.z * BZ + threadIdx.z;
+  apply_one<R, 0>(gen, m, i, j, k, x, y);
+  apply_one<R, (R::NCOMP > 1 ? 1 : 0)>(gen, m, i, j, k, x, y);
+  apply_one<R, (R::NCOMP > 2 ? 2 : 0)>(gen, m, i, j, k, x, y);
+}
+
 template <class R, int COMP>
 __global__ void __launch_bounds__(BX *BY *BZ) k_count(R gen, TM m, i64 *__restrict__ row_nnz) {
   constexpr int LOC = R::template loc<COMP>();
@@ -89,6 +113,12 @@ template <class R, int COMP> static void launch_comp(const R &gen, int mode, con
 }
 
 template <class R> static void launch_all(const R &gen, int mode, const TM &m, const Args &a, cudaStream_t s) {
+  if (mode == MODE_APPLY && R::NCOMP == 3) {
+    // node-extent grid covers every component's extent
+    dim3 g = grid_for<LOC_N>(m), b(BX, BY, BZ);
+    k_apply3<R><<<g, b, 0, s>>>(gen, m, a.x, a.y);
+    return;
+  }
   launch_comp<R, 0>(gen, mode, m, a, s);
   if (R::NCOMP > 1) launch_comp<R, (R::NCOMP > 1 ? 1 : 0)>(gen, mode, m, a, s);
   if (R::NCOMP > 2) launch_comp<R, (R::NCOMP > 2 ? 2 : 0)>(gen, mode, m, a, s);
