@@ -20,14 +20,12 @@ __device__ __forceinline__ int sym_idx(int a, int b) {  // (a,b) -> position in 
   return a == b ? a : (a + b + 2);                        // (0,1)->3 (0,2)->4 (1,2)->5
 }
 
-// mode 0: out = diag ; mode 1: out = diag * x
+// mode 0: out = diag ; mode 1: out = diag * x.  One launch covers the three components (the cell model is
+// read once instead of once per component; neighbouring dofs share it through L1).
 template <bool EDGE, int COMP, int MODE>
-__global__ void __launch_bounds__(BX *BY *BZ)
-    k_mass_diag(TM m, Model md, bool inv_mat, const double *__restrict__ x, double *__restrict__ out) {
+__device__ __forceinline__ void mass_diag_one(const TM &m, const Model &md, bool inv_mat, i64 i, i64 j, i64 k,
+                                              const double *__restrict__ x, double *__restrict__ out) {
   constexpr int LOC = DofLoc<EDGE, COMP>::LOC;
-  const i64 i = (i64)blockIdx.x * BX + threadIdx.x;
-  const i64 j = (i64)blockIdx.y * BY + threadIdx.y;
-  const i64 k = (i64)blockIdx.z * BZ + threadIdx.z;
   if (i >= m.sx<LOC>() || j >= m.sy<LOC>() || k >= m.sz<LOC>()) return;
   double d = mass_diag_entry<EDGE, COMP>(m, md, i, j, k);
   if (inv_mat) d = 1.0 / d;
@@ -36,11 +34,19 @@ __global__ void __launch_bounds__(BX *BY *BZ)
 }
 
 template <bool EDGE, int MODE>
+__global__ void __launch_bounds__(BX *BY *BZ)
+    k_mass_diag(TM m, Model md, bool inv_mat, const double *__restrict__ x, double *__restrict__ out) {
+  const i64 i = (i64)blockIdx.x * BX + threadIdx.x;
+  const i64 j = (i64)blockIdx.y * BY + threadIdx.y;
+  const i64 k = (i64)blockIdx.z * BZ + threadIdx.z;
+  mass_diag_one<EDGE, 0, MODE>(m, md, inv_mat, i, j, k, x, out);
+  mass_diag_one<EDGE, 1, MODE>(m, md, inv_mat, i, j, k, x, out);
+  mass_diag_one<EDGE, 2, MODE>(m, md, inv_mat, i, j, k, x, out);
+}
+
+template <bool EDGE, int MODE>
 static void launch_mass_diag(const TM &m, const Model &md, bool inv_mat, const double *x, double *out, cudaStream_t s) {
-  dim3 b(BX, BY, BZ);
-  k_mass_diag<EDGE, 0, MODE><<<grid_for<DofLoc<EDGE, 0>::LOC>(m), b, 0, s>>>(m, md, inv_mat, x, out);
-  k_mass_diag<EDGE, 1, MODE><<<grid_for<DofLoc<EDGE, 1>::LOC>(m), b, 0, s>>>(m, md, inv_mat, x, out);
-  k_mass_diag<EDGE, 2, MODE><<<grid_for<DofLoc<EDGE, 2>::LOC>(m), b, 0, s>>>(m, md, inv_mat, x, out);
+  k_mass_diag<EDGE, MODE><<<grid_for<LOC_N>(m), dim3(BX, BY, BZ), 0, s>>>(m, md, inv_mat, x, out);
 }
 
 // ---- full tensor rows ------------------------------------------------------------------------

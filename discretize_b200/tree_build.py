@@ -41,12 +41,29 @@ def _lookup(sorted_keys, keys):
     return pos_c, found
 
 
+def _unique_keys(keys):
+    """np.unique(keys, return_index=True, return_inverse=True); sorts on the GPU when one is present
+    (tens of millions of keys per family: ~100x faster there), identical results either way."""
+    try:
+        import torch
+
+        if torch.cuda.is_available() and keys.size > 2_000_000:
+            k = torch.from_numpy(keys).cuda()
+            uniq, inv = torch.unique(k, sorted=True, return_inverse=True)
+            first = torch.full((uniq.numel(),), keys.size, dtype=torch.int64, device=k.device)
+            first.scatter_reduce_(0, inv, torch.arange(keys.size, device=k.device), reduce="amin")
+            return uniq.cpu().numpy(), first.cpu().numpy(), inv.cpu().numpy()
+    except Exception:  # pragma: no cover - any torch / memory problem: fall back to numpy
+        pass
+    return np.unique(keys, return_index=True, return_inverse=True)
+
+
 class Entities:
     """One family of entities (nodes, x-edges, ..., z-faces) in key order."""
 
     def __init__(self, loc):
         keys = key3(loc[:, 0], loc[:, 1], loc[:, 2])
-        self.keys, first, self.inverse = np.unique(keys, return_index=True, return_inverse=True)
+        self.keys, first, self.inverse = _unique_keys(keys)
         self.loc = loc[first]
         self.n_total = self.keys.size
         self.hanging = np.zeros(self.n_total, dtype=bool)

@@ -14,26 +14,28 @@ from .operators import Operator, cuda_device, ptr, stream_ptr, to_device
 def encode_parts(geoms, parts, shape):
     """Merge ``sum_s diag(geom_s) @ M_s`` into one CSR with a code byte per entry.
 
-    Returns (indptr, indices int32, codes uint8, tab_mult, tab_sel).  Entries of different parts that
-    share (row, col) stay separate entries (SpMV adds them; ``tocsr`` sums them on the host)."""
-    rows, cols, mult, sel = [], [], [], []
+    Returns (indptr, indices int32, codes uint8, tab_mult, tab_sel).  The parts of every reference
+    operator live in disjoint column blocks (x / y / z faces or edges), so the merge is a sparse sum of
+    "code matrices"; if two parts ever shared an entry the sum would be caught by the nnz check."""
+    tab_mult, tab_sel = [], []
+    acc = None
     for s_, M in parts:
-        coo = M.tocoo()
-        rows.append(coo.row); cols.append(coo.col); mult.append(coo.data)
-        sel.append(np.full(coo.nnz, s_, dtype=np.int64))
-    rows, cols, mult, sel = (np.concatenate(a) for a in (rows, cols, mult, sel))
-    # distinct (multiplier, selector) pairs -> table
-    mult_r = np.round(mult, 14)
-    pair_key = np.stack([mult_r, sel.astype(np.float64)], axis=1)
-    uniq, codes = np.unique(pair_key, axis=0, return_inverse=True)
-    if uniq.shape[0] > 256:
-        raise ValueError(f"operator needs {uniq.shape[0]} distinct (multiplier, selector) pairs; the code byte holds 256")
-    order = np.lexsort((cols, rows))
-    rows, cols, codes = rows[order], cols[order], codes.reshape(-1)[order]
-    indptr = np.zeros(shape[0] + 1, dtype=np.int64)
-    np.add.at(indptr, rows + 1, 1)
-    indptr = np.cumsum(indptr)
-    return indptr, cols.astype(np.int32), codes.astype(np.uint8), uniq[:, 0].copy(), uniq[:, 1].astype(np.uint8)
+        M = sp.csr_matrix(M)
+        vals, inv = np.unique(np.round(M.data, 14), return_inverse=True)
+        base = len(tab_mult)
+        tab_mult.extend(vals.tolist())
+        tab_sel.extend([s_] * vals.size)
+        code_m = sp.csr_matrix(((inv + base + 1).astype(np.float64), M.indices, M.indptr), shape=M.shape)
+        acc = code_m if acc is None else acc + code_m
+    if len(tab_mult) > 256:
+        raise ValueError(f"operator needs {len(tab_mult)} distinct (multiplier, selector) pairs; the code byte holds 256")
+    acc = sp.csr_matrix(acc)
+    if acc.nnz != sum(sp.csr_matrix(M).nnz for _, M in parts):
+        raise ValueError("operator parts overlap; cannot encode one code per entry")
+    acc.sort_indices()
+    codes = (np.rint(acc.data).astype(np.int64) - 1).astype(np.uint8)
+    return (acc.indptr.astype(np.int64), acc.indices.astype(np.int32), codes, np.array(tab_mult, dtype=np.float64),
+            np.array(tab_sel, dtype=np.uint8))
 
 
 class CodedCsr:
