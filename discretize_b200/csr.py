@@ -26,7 +26,7 @@ class _DeviceCsr:
         self.indices = to_device(m.indices.astype(np.int32), torch.int32)
         self.data = to_device(m.data.astype(np.float64))
         avg = self.nnz / max(m.shape[0], 1)
-        self.lpr = 1 if avg <= 1.5 else 2 if avg <= 3 else 4 if avg <= 6 else 8 if avg <= 14 else 16 if avg <= 40 else 32
+        self.lpr = 1 if avg <= 7 else 2 if avg <= 16 else 4 if avg <= 40 else 16
 
     def apply(self, x, out):
         check(load().dzb_csr_spmv(self.shape[0], ptr(self.indptr), int(self.is64), ptr(self.indices), ptr(self.data),

@@ -55,7 +55,8 @@ class CodedCsr:
         self.geoms = [to_device(g) for g in geoms] + [None] * (3 - len(geoms))
         self.geom_by_col = int(geom_by_col)
         avg = self.nnz / max(shape[0], 1)
-        self.lpr = 2 if avg <= 3 else 4 if avg <= 6 else 8 if avg <= 14 else 16
+        # measured (tools/sweep_tree.py, profiles/): rows are short, one thread per row wins up to ~7 nnz/row
+        self.lpr = 1 if avg <= 7 else 2 if avg <= 16 else 4 if avg <= 40 else 16
 
     def apply(self, x, out):
         g = self.geoms
