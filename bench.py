@@ -259,7 +259,7 @@ def run_ours(args):
                         else "eager"),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": 3.25e9 if (args.workload == "dc" and n == 512 and world == 1) else None,
+                     "traffic": 3.22e9 if (args.workload == "dc" and n == 512 and world == 1) else None,
                      "traffic_source": "ncu --set full, profiles/r1_k8_dc_nodal_ring_ncu_full_summary.txt (dram read+write per launch)",
                      "peak_source": peak_src, "kernel": kernel_name,
                      "algorithmic_bytes_per_launch": alg_bytes},
