@@ -263,6 +263,25 @@ def test_dc_nodal_streamed_host_path():
     np.testing.assert_array_equal(A.matvec(xh).numpy(), want)
 
 
+@pytest.mark.parametrize("shape", [(600, 5, 7), (601, 4, 9), (1100, 3, 5), (271, 6, 130)])
+def test_fused_kernels_multiple_x_blocks_and_long_z(shape):
+    """Meshes wider than one block of the ring kernels (K8: 540 node columns, K9: 270) with even and odd nx,
+    and a z-extent longer than one z-chunk: fused == unfused chain of elementary kernels."""
+    import discretize_b200 as dz
+
+    rng = np.random.default_rng(15)
+    mesh = dz.TensorMesh([rng.random(n) + 0.5 for n in shape])
+    sigma = np.exp(rng.standard_normal(mesh.nC))
+    mui = np.exp(rng.standard_normal(mesh.nC))
+    phi, e = rng.standard_normal(mesh.nN), rng.standard_normal(mesh.nE)
+    Gd, Cd = mesh.nodal_gradient, mesh.edge_curl
+    Me, Mf = mesh.get_edge_inner_product(sigma), mesh.get_face_inner_product(mui)
+    A = Gd.T @ Me @ Gd
+    B = Cd.T @ Mf @ Cd + Me
+    assert_close_vec(A @ phi, Gd.T @ (Me @ (Gd @ phi)))
+    assert_close_vec(B @ e, Cd.T @ (Mf @ (Cd @ e)) + Me @ e)
+
+
 def test_dc_nodal_128_against_chain_and_cg():
     """Size-independent checks at a larger size: fused == unfused chain; SPD => CG converges."""
     import discretize_b200 as dz
