@@ -17,9 +17,32 @@ struct AxisHit {
   double w1, w2;
 };
 
-// _bisect_right + _get_inds_ws (interputils_cython.pyx:42-67)
-__device__ __forceinline__ AxisHit locate_axis(const double *__restrict__ a, i64 n, double xp) {
+// _bisect_right + _get_inds_ws (interputils_cython.pyx:42-67).
+// bisect_right(a, x) is the unique r with a[r-1] <= x < a[r] (a sorted); any search that ends on that r
+// is bit-identical to the reference's bisection.  `inv_mean` = (n-1)/(a[n-1]-a[0]) gives a guess that is
+// exact or off by a few entries on smooth meshes; a short walk fixes it, and a bisection over the
+// remaining bracket handles arbitrary (strongly graded) arrays.
+__device__ __forceinline__ AxisHit locate_axis(const double *__restrict__ a, i64 n, double xp, double inv_mean) {
   i64 lo = 0, hi = n;
+  if (n >= 8 && xp == xp) {
+    double g = (xp - a[0]) * inv_mean;
+    g = fmin(fmax(g, -1.0), (double)n);
+    i64 r = (i64)g + 1;                       // guess for bisect_right
+    r = max(min(r, n), (i64)0);
+    // walk at most 4 entries towards the answer, then keep the tight bracket for the bisection
+    int steps = 0;
+    while (steps < 4) {
+      if (r < n && !(xp < a[r])) ++r;         // a[r] <= x  -> answer is right of r
+      else if (r > 0 && xp < a[r - 1]) --r;   // x < a[r-1] -> answer is left of r
+      else { lo = hi = r; break; }
+      ++steps;
+    }
+    if (lo != hi) {                           // not settled: bracket by which side we were moving to
+      if (r < n && !(xp < a[r])) lo = r + 1;  // still a[r] <= x
+      else if (r > 0 && xp < a[r - 1]) hi = r - 1;
+      else lo = hi = r;
+    }
+  }
   while (lo < hi) {
     const i64 mid = (lo + hi) / 2;
     if (xp < a[mid]) hi = mid;
@@ -37,7 +60,14 @@ __device__ __forceinline__ AxisHit locate_axis(const double *__restrict__ a, i64
 struct Axes {
   const double *tx, *ty, *tz;
   i64 ntx, nty, ntz;
+  double ix, iy, iz;  // (n-1)/(a[n-1]-a[0]) per axis (0 disables the guess)
 };
+
+__device__ __forceinline__ void axes_means(Axes &a) {
+  a.ix = (a.ntx >= 8 && a.tx[a.ntx - 1] > a.tx[0]) ? (double)(a.ntx - 1) / (a.tx[a.ntx - 1] - a.tx[0]) : 0.0;
+  a.iy = (a.nty >= 8 && a.ty[a.nty - 1] > a.ty[0]) ? (double)(a.nty - 1) / (a.ty[a.nty - 1] - a.ty[0]) : 0.0;
+  a.iz = (a.ntz >= 8 && a.tz[a.ntz - 1] > a.tz[0]) ? (double)(a.ntz - 1) / (a.tz[a.ntz - 1] - a.tz[0]) : 0.0;
+}
 
 // copies the three 1-D arrays into shared memory when they fit, else uses them in place
 __device__ __forceinline__ Axes stage_axes(const Axes &g, double *smem, i64 smem_doubles) {
@@ -51,6 +81,7 @@ __device__ __forceinline__ Axes stage_axes(const Axes &g, double *smem, i64 smem
     a.tz = smem + g.ntx + g.nty;
     __syncthreads();
   }
+  axes_means(a);
   return a;
 }
 
@@ -80,9 +111,9 @@ __global__ void __launch_bounds__(IT) k_interp_locate(Axes g, const double *__re
   for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const i64 p = tile * IT + threadIdx.x;
     if (p < npts) {
-      const AxisHit hx = locate_axis(a.tx, a.ntx, __ldg(pts + 3 * p));
-      const AxisHit hy = locate_axis(a.ty, a.nty, __ldg(pts + 3 * p + 1));
-      const AxisHit hz = locate_axis(a.tz, a.ntz, __ldg(pts + 3 * p + 2));
+      const AxisHit hx = locate_axis(a.tx, a.ntx, __ldg(pts + 3 * p), a.ix);
+      const AxisHit hy = locate_axis(a.ty, a.nty, __ldg(pts + 3 * p + 1), a.iy);
+      const AxisHit hz = locate_axis(a.tz, a.ntz, __ldg(pts + 3 * p + 2), a.iz);
       i64 c8[8];
       double w8[8];
       entries(hx, hy, hz, a.ntx, a.nty, col_offset, c8, w8);
@@ -151,9 +182,9 @@ __global__ void __launch_bounds__(256) k_interp_fused(Axes g, const double *__re
   const Axes a = stage_axes(g, smem, 4096);
   const i64 stride = (i64)gridDim.x * blockDim.x;
   for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += stride) {
-    const AxisHit hx = locate_axis(a.tx, a.ntx, __ldg(pts + 3 * p));
-    const AxisHit hy = locate_axis(a.ty, a.nty, __ldg(pts + 3 * p + 1));
-    const AxisHit hz = locate_axis(a.tz, a.ntz, __ldg(pts + 3 * p + 2));
+    const AxisHit hx = locate_axis(a.tx, a.ntx, __ldg(pts + 3 * p), a.ix);
+    const AxisHit hy = locate_axis(a.ty, a.nty, __ldg(pts + 3 * p + 1), a.iy);
+    const AxisHit hz = locate_axis(a.tz, a.ntz, __ldg(pts + 3 * p + 2), a.iz);
     i64 c8[8];
     double w8[8];
     entries(hx, hy, hz, a.ntx, a.nty, col_offset, c8, w8);
@@ -207,7 +238,7 @@ extern "C" int dzb_interp_locate(const double *tx, int64_t ntx, const double *ty
                                  int64_t ntz, const double *pts, int64_t npts, int64_t col_offset, int64_t *cols,
                                  double *w, void *stream) {
   if (npts == 0) return 0;
-  Axes g{tx, ty, tz, ntx, nty, ntz};
+  Axes g{tx, ty, tz, ntx, nty, ntz, 0.0, 0.0, 0.0};
   const size_t smem = (2 * IT * 9 + 4096) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
@@ -236,7 +267,7 @@ extern "C" int dzb_interp_fused(const double *tx, int64_t ntx, const double *ty,
                                 int64_t ntz, const double *pts, int64_t npts, int64_t col_offset,
                                 const double *row_scale, const double *v, double *y, void *stream) {
   if (npts == 0) return 0;
-  Axes g{tx, ty, tz, ntx, nty, ntz};
+  Axes g{tx, ty, tz, ntx, nty, ntz, 0.0, 0.0, 0.0};
   const size_t smem = 4096 * sizeof(double);
   k_interp_fused<<<blocks_for(npts, 256, 8), 256, smem, (cudaStream_t)stream>>>(g, pts, npts, col_offset, row_scale, v, y);
   return check_launch("dzb_interp_fused");

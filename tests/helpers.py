@@ -60,6 +60,10 @@ MESHES = {
     "nonuniform": lambda rng: ([rng.random(4) + 0.5, rng.random(6) + 0.5, rng.random(5) + 0.5], np.array([-1.0, 0.25, 3.0])),
     "thin": lambda rng: ([rng.random(7) + 0.5, rng.random(1) + 0.5, rng.random(2) + 0.5], None),
     "wide": lambda rng: ([rng.random(70) + 0.5, rng.random(9) + 0.5, rng.random(37) + 0.5], None),
+    # strongly graded (padding cells growing by 1.4x): defeats the interpolation kernel's index guess
+    "graded": lambda rng: ([np.r_[1.4 ** np.arange(12, 0, -1), np.ones(9), 1.4 ** np.arange(1, 13)],
+                            np.r_[np.ones(10), 1.3 ** np.arange(1, 15)], np.r_[2.0 ** np.arange(8, 0, -1), np.ones(8)]],
+                           np.array([-300.0, 0.0, -500.0])),
 }
 
 

@@ -330,7 +330,7 @@ def test_maxwell_fused(mesh_name):
 LOCS = ["CC", "N", "Fx", "Fy", "Fz", "Ex", "Ey", "Ez", "CCVx", "CCVy", "CCVz"]
 
 
-@pytest.mark.parametrize("mesh_name", ["uniform", "nonuniform", "thin"])
+@pytest.mark.parametrize("mesh_name", ["uniform", "nonuniform", "thin", "graded"])
 @pytest.mark.parametrize("loc", LOCS)
 def test_interpolation(mesh_name, loc):
     from discretize_b200.interp import make_interpolation_operator
