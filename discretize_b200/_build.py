@@ -47,12 +47,13 @@ def build(force: bool = False, verbose: bool = True) -> str:
     hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(HERE, "..", "include", "dzb.h")]
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
+    extra = os.environ.get("DZB_EXTRA_NVCC_FLAGS", "").split()   # e.g. -DDZB_APPLY_SWEEP for tools/sweep_elementary.py
     objs, procs = [], []
     for src in srcs:
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", src, "-o", obj]
             if verbose:
                 print("[dzb build]", " ".join(cmd), flush=True)
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -27,6 +27,10 @@ OP_DIV, OP_CURL, OP_GRAD = 0, 1, 2
 OP_AVE_F2CC, OP_AVE_F2CCV, OP_AVE_FX2CC, OP_AVE_FY2CC, OP_AVE_FZ2CC = 3, 4, 5, 6, 7
 OP_AVE_E2CC, OP_AVE_E2CCV, OP_AVE_EX2CC, OP_AVE_EY2CC, OP_AVE_EZ2CC = 8, 9, 10, 11, 12
 OP_AVE_N2CC = 13
+OP_AVE_CC2F, OP_AVE_CCV2F, OP_AVE_CC2E, OP_AVE_E2F, OP_AVE_N2E, OP_AVE_N2F = 14, 15, 16, 17, 18, 19
+OP_CELL_GRAD, OP_CELL_GRAD_X, OP_CELL_GRAD_Y, OP_CELL_GRAD_Z = 20, 21, 22, 23
+OP_DIV_X, OP_DIV_Y, OP_DIV_Z = 24, 25, 26
+CG_SCALE = 64  # DzbCellGradFlags: bits 0..5 = Dirichlet on x-lo, x-hi, y-lo, y-hi, z-lo, z-hi
 
 MODEL_SCALAR, MODEL_ISO, MODEL_ANISO, MODEL_TENSOR = 0, 1, 2, 3
 FLAG_INVERT_MODEL, FLAG_INVERT_MATRIX, FLAG_EDGES = 1, 2, 4
@@ -45,6 +49,9 @@ SIGNATURES = {
     "dzb_tm_shape": [_MP, _I, C.POINTER(_L), C.POINTER(_L)],
     "dzb_tm_csr_count": [_MP, _I, _I, _P, _P],
     "dzb_tm_csr_fill": [_MP, _I, _I, _P, _P, _P, _P],
+    "dzb_tm_apply_flags": [_MP, _I, _I, _I, _P, _P, _P],
+    "dzb_tm_csr_count_flags": [_MP, _I, _I, _I, _P, _P],
+    "dzb_tm_csr_fill_flags": [_MP, _I, _I, _I, _P, _P, _P, _P],
     "dzb_tm_mass_diag": [_MP, _I, _I, _P, _D, _P, _P],
     "dzb_tm_mass_apply": [_MP, _I, _I, _P, _D, _P, _P, _P],
     "dzb_tm_mass_tensor_csr_count": [_MP, _I, _P, _P],

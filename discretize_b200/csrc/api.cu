@@ -25,3 +25,15 @@ int check_launch(const char *what) {
 
 extern "C" int dzb_version(void) { return DZB_ABI_VERSION; }
 extern "C" const char *dzb_last_error(void) { return dzb::g_err; }
+
+// experiment knob (not part of the stable ABI): the L2 fetch granularity hint (32 / 64 / 128 bytes).
+// Random 8-byte gathers (interpolation, OcTree SpMV) pull a whole fetch unit per miss.
+extern "C" int dzb_tune_l2_fetch(int bytes) {
+  if (bytes > 0) {
+    cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes);
+    if (e != cudaSuccess) return -(int)e;
+  }
+  size_t v = 0;
+  cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity);
+  return (int)v;
+}

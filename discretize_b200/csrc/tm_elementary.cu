@@ -6,6 +6,8 @@
 
 namespace dzb {
 
+int g_apply_cfg = 2;
+
 template <class R> static void shape_of(const TM &m, i64 *nr, i64 *nc) {
   *nr = R::nrows(m);
   *nc = R::ncols(m);
@@ -24,6 +26,11 @@ template <class R> static void shape_of(const TM &m, i64 *nr, i64 *nc) {
     DZB_FOR_OP(DZB_OP_AVE_FY2CC, BODY) DZB_FOR_OP(DZB_OP_AVE_FZ2CC, BODY) DZB_FOR_OP(DZB_OP_AVE_E2CC, BODY) \
     DZB_FOR_OP(DZB_OP_AVE_E2CCV, BODY) DZB_FOR_OP(DZB_OP_AVE_EX2CC, BODY) DZB_FOR_OP(DZB_OP_AVE_EY2CC, BODY) \
     DZB_FOR_OP(DZB_OP_AVE_EZ2CC, BODY) DZB_FOR_OP(DZB_OP_AVE_N2CC, BODY)                                 \
+    DZB_FOR_OP(DZB_OP_AVE_CC2F, BODY) DZB_FOR_OP(DZB_OP_AVE_CCV2F, BODY) DZB_FOR_OP(DZB_OP_AVE_CC2E, BODY) \
+    DZB_FOR_OP(DZB_OP_AVE_E2F, BODY) DZB_FOR_OP(DZB_OP_AVE_N2E, BODY) DZB_FOR_OP(DZB_OP_AVE_N2F, BODY)    \
+    DZB_FOR_OP(DZB_OP_CELL_GRAD, BODY) DZB_FOR_OP(DZB_OP_CELL_GRAD_X, BODY) DZB_FOR_OP(DZB_OP_CELL_GRAD_Y, BODY) \
+    DZB_FOR_OP(DZB_OP_CELL_GRAD_Z, BODY) DZB_FOR_OP(DZB_OP_DIV_X, BODY) DZB_FOR_OP(DZB_OP_DIV_Y, BODY)    \
+    DZB_FOR_OP(DZB_OP_DIV_Z, BODY)                                                                       \
     default:                                                                       \
       set_error("unknown operator id");                                            \
       return -1;                                                                   \
@@ -32,6 +39,9 @@ template <class R> static void shape_of(const TM &m, i64 *nr, i64 *nc) {
 }  // namespace dzb
 
 using namespace dzb;
+
+// tuning knob for experiments (not part of the stable ABI): launch configuration of the apply kernels
+extern "C" void dzb_tune_elementary(int cfg) { dzb::g_apply_cfg = cfg; }
 
 extern "C" int dzb_tm_shape(const DzbTensorMesh *mm, int op, int64_t *nrows, int64_t *ncols) {
   if (!valid_mesh(mm)) return -1;
@@ -44,30 +54,51 @@ extern "C" int dzb_tm_shape(const DzbTensorMesh *mm, int op, int64_t *nrows, int
   return 0;
 }
 
-extern "C" int dzb_tm_apply(const DzbTensorMesh *mm, int op, int transpose, const double *x, double *y, void *stream) {
+template <class R> static R with_flags(int flags) {
+  R gen;
+  gen.flags = flags;
+  return gen;
+}
+
+extern "C" int dzb_tm_apply_flags(const DzbTensorMesh *mm, int op, int transpose, int flags, const double *x, double *y,
+                                  void *stream) {
   if (!valid_mesh(mm)) return -1;
   TM m(*mm);
   Args a{x, y, nullptr, nullptr, nullptr, nullptr};
   cudaStream_t s = (cudaStream_t)stream;
-  DZB_DISPATCH(launch_all(R(), MODE_APPLY, m, a, s));
+  DZB_DISPATCH(launch_all(with_flags<R>(flags), MODE_APPLY, m, a, s));
   return check_launch("dzb_tm_apply");
 }
 
-extern "C" int dzb_tm_csr_count(const DzbTensorMesh *mm, int op, int transpose, int64_t *row_nnz, void *stream) {
+extern "C" int dzb_tm_csr_count_flags(const DzbTensorMesh *mm, int op, int transpose, int flags, int64_t *row_nnz,
+                                      void *stream) {
   if (!valid_mesh(mm)) return -1;
   TM m(*mm);
   Args a{nullptr, nullptr, (i64 *)row_nnz, nullptr, nullptr, nullptr};
   cudaStream_t s = (cudaStream_t)stream;
-  DZB_DISPATCH(launch_all(R(), MODE_COUNT, m, a, s));
+  DZB_DISPATCH(launch_all(with_flags<R>(flags), MODE_COUNT, m, a, s));
   return check_launch("dzb_tm_csr_count");
 }
 
-extern "C" int dzb_tm_csr_fill(const DzbTensorMesh *mm, int op, int transpose, const int64_t *indptr, int64_t *indices,
-                               double *data, void *stream) {
+extern "C" int dzb_tm_csr_fill_flags(const DzbTensorMesh *mm, int op, int transpose, int flags, const int64_t *indptr,
+                                     int64_t *indices, double *data, void *stream) {
   if (!valid_mesh(mm)) return -1;
   TM m(*mm);
   Args a{nullptr, nullptr, nullptr, (const i64 *)indptr, (i64 *)indices, data};
   cudaStream_t s = (cudaStream_t)stream;
-  DZB_DISPATCH(launch_all(R(), MODE_FILL, m, a, s));
+  DZB_DISPATCH(launch_all(with_flags<R>(flags), MODE_FILL, m, a, s));
   return check_launch("dzb_tm_csr_fill");
+}
+
+extern "C" int dzb_tm_apply(const DzbTensorMesh *mm, int op, int transpose, const double *x, double *y, void *stream) {
+  return dzb_tm_apply_flags(mm, op, transpose, 0, x, y, stream);
+}
+
+extern "C" int dzb_tm_csr_count(const DzbTensorMesh *mm, int op, int transpose, int64_t *row_nnz, void *stream) {
+  return dzb_tm_csr_count_flags(mm, op, transpose, 0, row_nnz, stream);
+}
+
+extern "C" int dzb_tm_csr_fill(const DzbTensorMesh *mm, int op, int transpose, const int64_t *indptr, int64_t *indices,
+                               double *data, void *stream) {
+  return dzb_tm_csr_fill_flags(mm, op, transpose, 0, indptr, indices, data, stream);
 }

@@ -34,6 +34,8 @@ _ALIASES = {
     "aveE2CC": "average_edge_to_cell", "aveE2CCV": "average_edge_to_cell_vector",
     "aveEx2CC": "average_edge_x_to_cell", "aveEy2CC": "average_edge_y_to_cell", "aveEz2CC": "average_edge_z_to_cell",
     "aveN2CC": "average_node_to_cell",
+    "aveCC2F": "average_cell_to_face", "aveCCV2F": "average_cell_vector_to_face",
+    "aveN2E": "average_node_to_edge", "aveN2F": "average_node_to_face",
     "nodalGrad": "nodal_gradient", "edgeCurl": "edge_curl", "faceDiv": "face_divergence",
     "getFaceInnerProduct": "get_face_inner_product", "getEdgeInnerProduct": "get_edge_inner_product",
     "getFaceInnerProductDeriv": "get_face_inner_product_deriv",
@@ -41,6 +43,22 @@ _ALIASES = {
     "getInterpolationMat": "get_interpolation_matrix",
     "isInside": "is_inside", "getTensor": "get_tensor",
 }
+
+
+def _validate_BC(bc):
+    """reference: operators/differential_operators.py:21-38."""
+    if isinstance(bc, str):
+        bc = [bc, bc]
+    if not isinstance(bc, list):
+        raise TypeError("bc must be a single string or list of strings")
+    if not len(bc) == 2:
+        raise TypeError("bc list must have two elements, one for each side")
+    for bc_i in bc:
+        if not isinstance(bc_i, str):
+            raise TypeError("each bc must be a string")
+        if bc_i not in ["dirichlet", "neumann"]:
+            raise ValueError("each bc must be either, 'dirichlet' or 'neumann'")
+    return bc
 
 
 def is_scalar(f):
@@ -381,13 +399,14 @@ class TensorMesh:
         return _lib.DzbTensorMesh(nx, ny, nz, 0, 0, 0, 0, 0, 0)
 
     # ---- differential operators and averaging ------------------------------------------------------
-    def _stencil(self, name, op_id):
+    def _stencil(self, name, op_id, flags=0):
         self._require_3d(name)
-        if name not in self._cache:
+        key = name if flags == 0 else (name, flags)
+        if key not in self._cache:
             from .tensor_ops import StencilOperator
 
-            self._cache[name] = StencilOperator(self, op_id, name=name)
-        return self._cache[name]
+            self._cache[key] = StencilOperator(self, op_id, name=name, flags=flags)
+        return self._cache[key]
 
     face_divergence = property(lambda self: self._stencil("face_divergence", _lib.OP_DIV))
     nodal_gradient = property(lambda self: self._stencil("nodal_gradient", _lib.OP_GRAD))
@@ -402,6 +421,66 @@ class TensorMesh:
     average_edge_y_to_cell = property(lambda self: self._stencil("average_edge_y_to_cell", _lib.OP_AVE_EY2CC))
     average_edge_z_to_cell = property(lambda self: self._stencil("average_edge_z_to_cell", _lib.OP_AVE_EZ2CC))
     average_node_to_cell = property(lambda self: self._stencil("average_node_to_cell", _lib.OP_AVE_N2CC))
+
+    # ---- cell-centred side (operators/differential_operators.py:236-591, 975-2083, 2789-2892,
+    # 3205-3382): same matrix-free row generators, boundary conditions as runtime flags ------------------------
+    face_x_divergence = property(lambda self: self._stencil("face_x_divergence", _lib.OP_DIV_X))
+    face_y_divergence = property(lambda self: self._stencil("face_y_divergence", _lib.OP_DIV_Y))
+    face_z_divergence = property(lambda self: self._stencil("face_z_divergence", _lib.OP_DIV_Z))
+    average_cell_to_face = property(lambda self: self._stencil("average_cell_to_face", _lib.OP_AVE_CC2F))
+    average_cell_vector_to_face = property(lambda self: self._stencil("average_cell_vector_to_face", _lib.OP_AVE_CCV2F))
+    average_cell_to_edge = property(lambda self: self._stencil("average_cell_to_edge", _lib.OP_AVE_CC2E))
+    average_edge_to_face = property(lambda self: self._stencil("average_edge_to_face", _lib.OP_AVE_E2F))
+    average_node_to_edge = property(lambda self: self._stencil("average_node_to_edge", _lib.OP_AVE_N2E))
+    average_node_to_face = property(lambda self: self._stencil("average_node_to_face", _lib.OP_AVE_N2F))
+
+    _cell_gradient_BC_list = "neumann"
+
+    def set_cell_gradient_BC(self, BC):
+        """reference: operators/differential_operators.py:975-1046 (zero Dirichlet / Neumann per side)."""
+        if isinstance(BC, str):
+            BC = [BC] * self.dim
+        if isinstance(BC, list):
+            if len(BC) != self.dim:
+                raise ValueError("BC list must be the size of your mesh")
+        else:
+            raise TypeError("BC must be a str or a list.")
+        for i, bc_i in enumerate(BC):
+            BC[i] = _validate_BC(bc_i)
+        self._cell_gradient_BC_list = BC
+        return BC
+
+    def _cell_gradient_flags(self):
+        BC = self.set_cell_gradient_BC(self._cell_gradient_BC_list)
+        flags = 0
+        for a, (lo, hi) in enumerate(BC):
+            flags |= (1 << (2 * a)) if lo == "dirichlet" else 0
+            flags |= (2 << (2 * a)) if hi == "dirichlet" else 0
+        return flags
+
+    @property
+    def stencil_cell_gradient(self):
+        return self._stencil("stencil_cell_gradient", _lib.OP_CELL_GRAD, self._cell_gradient_flags())
+
+    @property
+    def cell_gradient(self):
+        """diag(S / (aveCC2F V)) @ stencil_cell_gradient (:1445-1595).  NOTE: the reference caches the first
+        matrix it builds until set_cell_gradient_BC is called again; here the current BC always applies."""
+        return self._stencil("cell_gradient", _lib.OP_CELL_GRAD, self._cell_gradient_flags() | _lib.CG_SCALE)
+
+    # the component operators always use Neumann conditions (:1167, 1296, 1400)
+    stencil_cell_gradient_x = property(lambda self: self._stencil("stencil_cell_gradient_x", _lib.OP_CELL_GRAD_X))
+    stencil_cell_gradient_y = property(lambda self: self._stencil("stencil_cell_gradient_y", _lib.OP_CELL_GRAD_Y))
+    stencil_cell_gradient_z = property(lambda self: self._stencil("stencil_cell_gradient_z", _lib.OP_CELL_GRAD_Z))
+    cell_gradient_x = property(lambda self: self._stencil("cell_gradient_x", _lib.OP_CELL_GRAD_X, _lib.CG_SCALE))
+    cell_gradient_y = property(lambda self: self._stencil("cell_gradient_y", _lib.OP_CELL_GRAD_Y, _lib.CG_SCALE))
+    cell_gradient_z = property(lambda self: self._stencil("cell_gradient_z", _lib.OP_CELL_GRAD_Z, _lib.CG_SCALE))
+
+    @property
+    def nodal_laplacian(self):
+        # the reference's own 3-D assembly fails with a dimension mismatch (:719-748 multiply an n_edges_x
+        # diagonal into an n_nodes-column stencil), so there is nothing to be compatible with
+        raise NotImplementedError("nodal_laplacian: the reference implementation raises for 3-D tensor meshes")
 
     @property
     def edge_curl(self):

@@ -33,7 +33,8 @@ class StencilOperator(Operator):
     (edge_curl), :658-664 (nodal_gradient), :2478-3253 (average_*).
     """
 
-    def __init__(self, mesh, op_id, transpose=False, name=None):
+    def __init__(self, mesh, op_id, transpose=False, name=None, flags=0):
+        self.flags = int(flags)
         nr, nc = C.c_int64(), C.c_int64()
         check(load().dzb_tm_shape(C.byref(mesh._host_mesh_counts()), op_id, C.byref(nr), C.byref(nc)), "dzb_tm_shape")
         shape = (nc.value, nr.value) if transpose else (nr.value, nc.value)
@@ -41,8 +42,8 @@ class StencilOperator(Operator):
         self.mesh, self.op_id, self.transposed, self.name = mesh, op_id, bool(transpose), name
 
     def _launch(self, x, out, transpose):
-        check(load().dzb_tm_apply(C.byref(self.mesh.device_mesh()), self.op_id, int(transpose), ptr(x), ptr(out),
-                                  stream_ptr()), "dzb_tm_apply")
+        check(load().dzb_tm_apply_flags(C.byref(self.mesh.device_mesh()), self.op_id, int(transpose), self.flags, ptr(x),
+                                        ptr(out), stream_ptr()), "dzb_tm_apply")
 
     def _dev_apply(self, x, out):
         self._launch(x, out, self.transposed)
@@ -51,17 +52,17 @@ class StencilOperator(Operator):
         self._launch(x, out, not self.transposed)
 
     def _transpose(self):
-        return StencilOperator(self.mesh, self.op_id, not self.transposed, self.name)
+        return StencilOperator(self.mesh, self.op_id, not self.transposed, self.name, self.flags)
 
     _adjoint = _transpose
 
     def _tocsr(self):
-        lib, dm, tr = load(), self.mesh.device_mesh(), int(self.transposed)
+        lib, dm, tr, fl = load(), self.mesh.device_mesh(), int(self.transposed), self.flags
         return _csr_two_pass(
             self.shape[0], self.shape[1],
-            lambda rn: check(lib.dzb_tm_csr_count(C.byref(dm), self.op_id, tr, ptr(rn), stream_ptr()), "csr_count"),
-            lambda ip, ix, da: check(lib.dzb_tm_csr_fill(C.byref(dm), self.op_id, tr, ptr(ip), ptr(ix), ptr(da),
-                                                         stream_ptr()), "csr_fill"),
+            lambda rn: check(lib.dzb_tm_csr_count_flags(C.byref(dm), self.op_id, tr, fl, ptr(rn), stream_ptr()), "csr_count"),
+            lambda ip, ix, da: check(lib.dzb_tm_csr_fill_flags(C.byref(dm), self.op_id, tr, fl, ptr(ip), ptr(ix), ptr(da),
+                                                               stream_ptr()), "csr_fill"),
         )
 
     def __repr__(self):

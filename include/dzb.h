@@ -53,7 +53,30 @@ enum DzbOp {
   DZB_OP_AVE_EY2CC = 11,
   DZB_OP_AVE_EZ2CC = 12,
   DZB_OP_AVE_N2CC = 13,  /* average_node_to_cell       :3236-3253 */
-  DZB_OP_COUNT = 14
+  /* cell-centred side */
+  DZB_OP_AVE_CC2F = 14,  /* average_cell_to_face        :2789-2828 */
+  DZB_OP_AVE_CCV2F = 15, /* average_cell_vector_to_face :2830-2865 */
+  DZB_OP_AVE_CC2E = 16,  /* average_cell_to_edge        :2867-2892 */
+  DZB_OP_AVE_E2F = 17,   /* average_edge_to_face        :3205-3234 */
+  DZB_OP_AVE_N2E = 18,   /* average_node_to_edge        :3254-3319 */
+  DZB_OP_AVE_N2F = 19,   /* average_node_to_face        :3321-3382 */
+  DZB_OP_CELL_GRAD = 20, /* stencil_cell_gradient :1413-1443 / cell_gradient :1445-1595 (flags: DzbCellGradFlags) */
+  DZB_OP_CELL_GRAD_X = 21, /* stencil_cell_gradient_x / cell_gradient_x :1049-1181, 1762-1877 (always Neumann) */
+  DZB_OP_CELL_GRAD_Y = 22,
+  DZB_OP_CELL_GRAD_Z = 23,
+  DZB_OP_DIV_X = 24,     /* face_x_divergence           :236-348 */
+  DZB_OP_DIV_Y = 25,     /* face_y_divergence           :350-462 */
+  DZB_OP_DIV_Z = 26,     /* face_z_divergence           :464-591 */
+  DZB_OP_COUNT = 27
+};
+
+/* `flags` of the DZB_OP_CELL_GRAD* operators (set_cell_gradient_BC, :975-1046; _ddxCellGrad, :41-82).
+ * Default (0) is zero Neumann on all six sides and the unscaled stencil. */
+enum DzbCellGradFlags {
+  DZB_CG_DIRICHLET_X_LO = 1, DZB_CG_DIRICHLET_X_HI = 2,
+  DZB_CG_DIRICHLET_Y_LO = 4, DZB_CG_DIRICHLET_Y_HI = 8,
+  DZB_CG_DIRICHLET_Z_LO = 16, DZB_CG_DIRICHLET_Z_HI = 32,
+  DZB_CG_SCALE = 64 /* cell_gradient = diag(S / aveCC2F V) stencil; Neumann boundary rows are then empty */
 };
 
 /* Physical-property layouts (utils/matrix_utils.py:1048-1068 TensorType). */
@@ -84,6 +107,12 @@ int dzb_tm_shape(const DzbTensorMesh *m_host_counts_only, int op, int64_t *nrows
 int dzb_tm_csr_count(const DzbTensorMesh *m, int op, int transpose, int64_t *row_nnz, void *stream);
 int dzb_tm_csr_fill(const DzbTensorMesh *m, int op, int transpose, const int64_t *indptr, int64_t *indices,
                     double *data, void *stream);
+/* The same three calls for operators that take runtime `flags` (DzbCellGradFlags); flags = 0 is the call above. */
+int dzb_tm_apply_flags(const DzbTensorMesh *m, int op, int transpose, int flags, const double *x, double *y,
+                       void *stream);
+int dzb_tm_csr_count_flags(const DzbTensorMesh *m, int op, int transpose, int flags, int64_t *row_nnz, void *stream);
+int dzb_tm_csr_fill_flags(const DzbTensorMesh *m, int op, int transpose, int flags, const int64_t *indptr,
+                          int64_t *indices, double *data, void *stream);
 
 /* ---- mass matrices: get_face_inner_product / get_edge_inner_product ---------- */
 /* operators/inner_products.py:35-99 -> base/base_tensor_mesh.py:792-863 (diagonal)

@@ -557,3 +557,181 @@ def interpolation_matrix(g: Grid, pts, location_type="cell_centers", zeros_outsi
                 indices[lo:hi] = np.arange(ncols)
         Q = sp.csr_matrix((data, indices, indptr), shape=(npts, ncols))
     return Q
+
+
+# ------------------------------------------------------------------------------------
+# cell-centred operators: tensor products of 1-D two-point stencils
+# ------------------------------------------------------------------------------------
+def _s_eye(n):
+    i = np.arange(n)
+    return i, i, np.ones(n)
+
+
+def _s_av(n):
+    """cells <- nodes, (1/2, 1/2)  (utils/matrix_utils.py:227-253)."""
+    i = np.arange(n)
+    return np.r_[i, i], np.r_[i, i + 1], np.full(2 * n, 0.5)
+
+
+def _s_av_extrap(n):
+    """nodes <- cells, (1/2, 1/2) inside and weight 1 on the two boundary nodes (matrix_utils.py:256-287)."""
+    i = np.arange(1, n)
+    r = np.r_[0, i, i, n]
+    c = np.r_[0, i - 1, i, n - 1]
+    v = np.r_[1.0, np.full(2 * (n - 1), 0.5), 1.0]
+    return r, c, v
+
+
+def _s_cell_grad(n, bc):
+    """nodes <- cells, (-1, +1); boundary rows by ghost point: dirichlet +-2, neumann an explicit 0
+    (operators/differential_operators.py:41-82)."""
+    i = np.arange(1, n)
+    first = {"dirichlet": 2.0, "neumann": 0.0}[bc[0]]
+    last = {"dirichlet": -2.0, "neumann": 0.0}[bc[1]]
+    r = np.r_[0, i, i, n]
+    c = np.r_[0, i - 1, i, n - 1]
+    v = np.r_[first, np.full(n - 1, -1.0), np.full(n - 1, 1.0), last]
+    return r, c, v
+
+
+def _tensor_term(g: Grid, row_kind, col_kind, sx, sy, sz, scale=1.0, row_offset=0, col_offset=None):
+    """COO triplets of kron3(sz, sy, sx) between two locations (x fastest)."""
+    (rx, cx, vx), (ry, cy, vy), (rz, cz, vz) = sx, sy, sz
+    ax, ay, az = np.meshgrid(np.arange(rx.size), np.arange(ry.size), np.arange(rz.size), indexing="ij")
+    ax, ay, az = ax.ravel(), ay.ravel(), az.ravel()
+    rsx, rsy, _ = g.shapes(row_kind)
+    csx, csy, _ = g.shapes(col_kind)
+    rows = row_offset + rx[ax] + rsx * (ry[ay] + rsy * rz[az])
+    coff = g.offset(col_kind) if col_offset is None else col_offset
+    cols = coff + cx[ax] + csx * (cy[ay] + csy * cz[az])
+    return rows, cols, scale * vx[ax] * vy[ay] * vz[az]
+
+
+def _stack(g: Grid, terms, shape):
+    rows, cols, vals = zip(*terms)
+    return _csr(list(rows), list(cols), list(vals), shape)
+
+
+_NORMAL_AXIS = {"Fx": 0, "Fy": 1, "Fz": 2}
+
+
+def _normal_stencils(g: Grid, axis, s_normal):
+    """(sx, sy, sz) with ``s_normal`` along ``axis`` and identities (cell extents) elsewhere."""
+    s = [_s_eye(n) for n in g.n]
+    s[axis] = s_normal
+    return s
+
+
+def average_cell_to_face(g: Grid):
+    """vstack of kron3(I, I, av_extrap) per direction: nF x nC (differential_operators.py:2789-2828)."""
+    terms = []
+    for kind, a in _NORMAL_AXIS.items():
+        terms.append(_tensor_term(g, kind, "C", *_normal_stencils(g, a, _s_av_extrap(g.n[a])), row_offset=g.offset(kind)))
+    return _stack(g, terms, (g.nF, g.nC))
+
+
+def average_cell_vector_to_face(g: Grid):
+    """block_diag of the three components: nF x 3nC (differential_operators.py:2830-2865)."""
+    terms = []
+    for kind, a in _NORMAL_AXIS.items():
+        terms.append(_tensor_term(g, kind, "C", *_normal_stencils(g, a, _s_av_extrap(g.n[a])), row_offset=g.offset(kind),
+                                  col_offset=a * g.nC))
+    return _stack(g, terms, (g.nF, 3 * g.nC))
+
+
+def average_cell_to_edge(g: Grid):
+    """av_extrap on the two axes transverse to the edge: nE x nC (differential_operators.py:2867-2892)."""
+    terms = []
+    for a, kind in enumerate(("Ex", "Ey", "Ez")):
+        s = [_s_av_extrap(n) for n in g.n]
+        s[a] = _s_eye(g.n[a])
+        terms.append(_tensor_term(g, kind, "C", *s, row_offset=g.offset(kind)))
+    return _stack(g, terms, (g.nE, g.nC))
+
+
+def average_edge_to_face(g: Grid):
+    """0.5 * [[0, Ey->Fx, Ez->Fx], [Ex->Fy, 0, Ez->Fy], [Ex->Fz, Ey->Fz, 0]]: each face takes the mean of the
+    four edges that bound it (differential_operators.py:3205-3234)."""
+    terms = []
+    for fa, fk in enumerate(("Fx", "Fy", "Fz")):
+        for ea, ek in enumerate(("Ex", "Ey", "Ez")):
+            if ea == fa:
+                continue
+            third = 3 - fa - ea            # the axis that is averaged (node extent on the edge, cell extent on the face)
+            fs, es = g.shapes(fk), g.shapes(ek)
+            s = []
+            for ax in range(3):
+                s.append(_s_av(g.n[ax]) if ax == third else _s_eye(fs[ax]))
+                assert ax == third or fs[ax] == es[ax]
+            terms.append(_tensor_term(g, fk, ek, *s, scale=0.5, row_offset=g.offset(fk)))
+    return _stack(g, terms, (g.nF, g.nE))
+
+
+def average_node_to_edge(g: Grid):
+    """mean of the two end nodes: nE x nN (differential_operators.py:3254-3319)."""
+    terms = []
+    sn = g.shapes("N")
+    for a, kind in enumerate(("Ex", "Ey", "Ez")):
+        s = [_s_eye(sn[ax]) for ax in range(3)]
+        s[a] = _s_av(g.n[a])
+        terms.append(_tensor_term(g, kind, "N", *s, row_offset=g.offset(kind)))
+    return _stack(g, terms, (g.nE, g.nN))
+
+
+def average_node_to_face(g: Grid):
+    """mean of the four corner nodes: nF x nN (differential_operators.py:3321-3382)."""
+    terms = []
+    sn = g.shapes("N")
+    for a, kind in enumerate(("Fx", "Fy", "Fz")):
+        s = [_s_av(g.n[ax]) for ax in range(3)]
+        s[a] = _s_eye(sn[a])
+        terms.append(_tensor_term(g, kind, "N", *s, row_offset=g.offset(kind)))
+    return _stack(g, terms, (g.nF, g.nN))
+
+
+def normalize_bc(bc):
+    """set_cell_gradient_BC / _validate_BC (differential_operators.py:21-38, 975-1046)."""
+    if isinstance(bc, str):
+        bc = [bc] * 3
+    out = []
+    for b in bc:
+        b = [b, b] if isinstance(b, str) else list(b)
+        assert len(b) == 2 and all(x in ("dirichlet", "neumann") for x in b)
+        out.append(b)
+    return out
+
+
+def stencil_cell_gradient(g: Grid, bc="neumann", axis=None):
+    """vstack of kron3(I, I, _ddxCellGrad(n, bc)) per direction: nF x nC (differential_operators.py:1413-1443);
+    ``axis`` selects one component block with Neumann conditions (stencil_cell_gradient_x/y/z, :1167-1181)."""
+    bc = normalize_bc(bc)
+    if axis is not None:
+        kind = ("Fx", "Fy", "Fz")[axis]
+        t = _tensor_term(g, kind, "C", *_normal_stencils(g, axis, _s_cell_grad(g.n[axis], ["neumann", "neumann"])))
+        return _stack(g, [t], (g.vnF[axis], g.nC))
+    terms = []
+    for kind, a in _NORMAL_AXIS.items():
+        terms.append(_tensor_term(g, kind, "C", *_normal_stencils(g, a, _s_cell_grad(g.n[a], bc[a])), row_offset=g.offset(kind)))
+    return _stack(g, terms, (g.nF, g.nC))
+
+
+def cell_gradient(g: Grid, bc="neumann", axis=None):
+    """diag(S / (aveCC2F V)) @ stencil (differential_operators.py:1445-1595, 1762-2083); the product drops the
+    explicit zeros of the Neumann rows."""
+    S = g.face_areas()
+    Vf = average_cell_to_face(g) @ g.cell_volumes()
+    scale = S / Vf
+    if axis is not None:
+        lo = g.offset(("Fx", "Fy", "Fz")[axis])
+        scale = scale[lo:lo + g.vnF[axis]]
+    G = sp.diags(scale).tocsr() @ stencil_cell_gradient(g, bc, axis)
+    G.eliminate_zeros()
+    return canonical(G)
+
+
+def face_component_divergence(g: Grid, axis):
+    """face_x/y/z_divergence: diag(1/V) Dstencil_axis diag(S_axis), nC x nF_axis (differential_operators.py:236-591)."""
+    kind = ("Fx", "Fy", "Fz")[axis]
+    D = face_divergence(g)
+    lo = g.offset(kind)
+    return canonical(D[:, lo:lo + g.vnF[axis]])

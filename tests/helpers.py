@@ -55,6 +55,26 @@ ORACLE_OPS = {
     "average_edge_z_to_cell": lambda g: T.average_component_to_cell(g, "Ez"),
 }
 
+ORACLE_N2_OPS = {
+    "average_cell_to_face": T.average_cell_to_face,
+    "average_cell_vector_to_face": T.average_cell_vector_to_face,
+    "average_cell_to_edge": T.average_cell_to_edge,
+    "average_edge_to_face": T.average_edge_to_face,
+    "average_node_to_edge": T.average_node_to_edge,
+    "average_node_to_face": T.average_node_to_face,
+    "face_x_divergence": lambda g: T.face_component_divergence(g, 0),
+    "face_y_divergence": lambda g: T.face_component_divergence(g, 1),
+    "face_z_divergence": lambda g: T.face_component_divergence(g, 2),
+    "stencil_cell_gradient_x": lambda g: T.stencil_cell_gradient(g, axis=0),
+    "stencil_cell_gradient_y": lambda g: T.stencil_cell_gradient(g, axis=1),
+    "stencil_cell_gradient_z": lambda g: T.stencil_cell_gradient(g, axis=2),
+    "cell_gradient_x": lambda g: T.cell_gradient(g, axis=0),
+    "cell_gradient_y": lambda g: T.cell_gradient(g, axis=1),
+    "cell_gradient_z": lambda g: T.cell_gradient(g, axis=2),
+}
+CELL_GRADIENT_BCS = {"neumann": "neumann", "dirichlet": "dirichlet",
+                     "mixed": ["dirichlet", ["neumann", "dirichlet"], ["dirichlet", "neumann"]]}
+
 MESHES = {
     "uniform": lambda rng: ([5, 4, 3], None),
     "nonuniform": lambda rng: ([rng.random(4) + 0.5, rng.random(6) + 0.5, rng.random(5) + 0.5], np.array([-1.0, 0.25, 3.0])),

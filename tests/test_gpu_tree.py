@@ -117,3 +117,36 @@ def test_larger_tree_device_vs_host_matrix():
         x, y = rng.standard_normal(H.shape[1]), rng.standard_normal(H.shape[0])
         assert_close_vec(op @ x, H @ x)
         assert_close_vec(op.T @ y, H.T @ y)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_tree_operators_loopback(gold, world):
+    """tree_shard on one GPU: every rank's local coded-CSR SpMV (CUDA) on [owned | ghost] vectors, the
+    exchange replayed by device copies that follow the plans (the NCCL path: tools/check_tree_shard.py)."""
+    from discretize_b200.tree_shard import OPERATOR_KINDS, ShardedTreeOperator, TreeShard
+
+    m = _mesh_from_fixture(gold, "a", "refine")
+    shards = [TreeShard(m, r, world) for r in range(world)]
+    rng = np.random.default_rng(11)
+    for name, (rk, ck) in OPERATOR_KINDS.items():
+        for tr in (False, True):
+            ref = golden_matrix(gold, f"a_{name}")
+            ref = ref.T.tocsr() if tr else ref
+            kin, kout = (rk, ck) if tr else (ck, rk)
+            x = rng.standard_normal(ref.shape[1])
+            ops = [ShardedTreeOperator(s, name, tr) for s in shards]
+            for s, op in zip(shards, ops):
+                op.buf.zero_()
+                op.buf[:op.plan.n_owned] = torch.from_numpy(s.scatter(kin, x)).cuda()
+            for p, op in enumerate(ops):
+                for q in range(world):
+                    idx = op.plan.send_idx[q]
+                    if idx.size:
+                        dst = ops[q]
+                        lo = dst.plan.n_owned + int(dst.plan.ghost_off[p])
+                        dst.buf[lo:lo + idx.size] = op.buf[torch.as_tensor(idx).cuda()]
+            y = np.zeros(ref.shape[0])
+            for s, op in zip(shards, ops):
+                op.csr.apply(op.buf, op.out)
+                y[s.owned(kout)] = op.out.cpu().numpy()
+            assert_close_vec(y, ref @ x)

@@ -1,0 +1,63 @@
+"""Launch-configuration sweep of the elementary stencil kernels (K1-K4) at 512^3, and the L2 fetch granularity
+experiment for the gather kernels.  Build with DZB_EXTRA_NVCC_FLAGS=-DDZB_APPLY_SWEEP for all configurations."""
+import ctypes as C
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import discretize_b200 as dz
+from discretize_b200._lib import load
+
+PEAK = 6541.1
+CFGS = {0: "32x4x4 zt1", 1: "32x4x4 zt2", 2: "32x4x4 zt4", 3: "64x4x2 zt4", 4: "128x2x2 zt4", 5: "32x8x2 zt4",
+        6: "64x2x2 zt4", 7: "32x4x2 zt4", 8: "32x4x4 zt8", 9: "32x2x4 zt4"}
+
+
+def timeit(fn, reps=10, warm=2):
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+    cfgs = [int(c) for c in sys.argv[2].split(",")] if len(sys.argv) > 2 else list(CFGS)
+    lib = C.CDLL(os.path.join(os.path.dirname(dz.__file__), "libdzb.so"))
+    load()
+    mesh = dz.TensorMesh([n] * 3)
+    dev = torch.device("cuda")
+    names = [("D", mesh.face_divergence), ("D.T", mesh.face_divergence.T), ("G", mesh.nodal_gradient),
+             ("G.T", mesh.nodal_gradient.T), ("C", mesh.edge_curl), ("C.T", mesh.edge_curl.T),
+             ("aveE2CC", mesh.average_edge_to_cell), ("aveF2CCV.T", mesh.average_face_to_cell_vector.T),
+             ("aveN2CC", mesh.average_node_to_cell), ("cellGrad", mesh.cell_gradient)]
+    big = torch.randn(mesh.nE, dtype=torch.float64, device=dev)
+    out = torch.empty(mesh.nE, dtype=torch.float64, device=dev)
+    ref = {}
+    for cfg in cfgs:
+        lib.dzb_tune_elementary(cfg)
+        row = {"cfg": cfg, "shape": CFGS.get(cfg, "?")}
+        for name, op in names:
+            x, y = big[:op.shape[1]], out[:op.shape[0]]
+            ms = timeit(lambda: op.apply_device(x, out=y))
+            nbytes = 8.0 * (op.shape[0] + op.shape[1])
+            row[name] = f"{ms:.3f}ms {nbytes / ms / 1e6 / PEAK:.2f}"
+            chk = float(y.double().abs().sum())
+            if name in ref and ref[name] != chk:
+                row[name] += " MISMATCH"
+            ref.setdefault(name, chk)
+        print(json.dumps(row), flush=True)
+    lib.dzb_tune_elementary(2)
+
+
+if __name__ == "__main__":
+    main()
