@@ -3,10 +3,38 @@
 // 3-D thread blocks so that the y/z neighbours of a row are served from L1).
 #include "tm_rows.cuh"
 #include "tm_rowkernels.cuh"
+#include "tm_march.cuh"
 
 namespace dzb {
 
 int g_apply_cfg = 2;
+// marching kernels for DIV / GRAD / CURL and transposes: 0 = off (generic row kernels), -1 = per-operator tuned
+// configuration (default), > 0 = one configuration for all six (sweep builds)
+static int g_march_cfg = -1;
+
+static bool try_march(int op, int transpose, int flags, const TM &m, const double *x, double *y, cudaStream_t s) {
+  if (flags != 0) return false;
+  switch (g_march_cfg) {
+    case 0: return false;
+#ifdef DZB_APPLY_SWEEP
+    case 1: return launch_march<MarchCfg<4, 32, 0>>(op, transpose, m, x, y, s);
+    case 2: return launch_march<MarchCfg<8, 32, 0>>(op, transpose, m, x, y, s);
+    case 3: return launch_march<MarchCfg<8, 16, 0>>(op, transpose, m, x, y, s);
+    case 4: return launch_march<MarchCfg<8, 16, 8>>(op, transpose, m, x, y, s);
+    case 5: return launch_march<MarchCfg<8, 32, 8>>(op, transpose, m, x, y, s);
+    case 6: return launch_march<MarchCfg<4, 32, 16>>(op, transpose, m, x, y, s);
+    case 7: return launch_march<MarchCfg<4, 16, 16>>(op, transpose, m, x, y, s);
+    case 8: return launch_march<MarchCfg<8, 8, 8>>(op, transpose, m, x, y, s);
+    case 9: return launch_march<MarchCfg<16, 16, 4>>(op, transpose, m, x, y, s);
+    case 10: return launch_march<MarchCfg<8, 16, 6>>(op, transpose, m, x, y, s);
+    case 11: return launch_march<MarchCfg<8, 64, 8>>(op, transpose, m, x, y, s);
+    case 12: return launch_march<MarchCfg<8, 16, 4>>(op, transpose, m, x, y, s);
+    case 13: return launch_march<MarchCfg<8, 16, 2>>(op, transpose, m, x, y, s);
+    case 14: return launch_march<MarchCfg<4, 16, 1>>(op, transpose, m, x, y, s);
+#endif
+    default: return launch_march_tuned(op, transpose, m, x, y, s);
+  }
+}
 
 template <class R> static void shape_of(const TM &m, i64 *nr, i64 *nc) {
   *nr = R::nrows(m);
@@ -42,6 +70,7 @@ using namespace dzb;
 
 // tuning knob for experiments (not part of the stable ABI): launch configuration of the apply kernels
 extern "C" void dzb_tune_elementary(int cfg) { dzb::g_apply_cfg = cfg; }
+extern "C" void dzb_tune_march(int cfg) { dzb::g_march_cfg = cfg; }
 
 extern "C" int dzb_tm_shape(const DzbTensorMesh *mm, int op, int64_t *nrows, int64_t *ncols) {
   if (!valid_mesh(mm)) return -1;
@@ -66,6 +95,7 @@ extern "C" int dzb_tm_apply_flags(const DzbTensorMesh *mm, int op, int transpose
   TM m(*mm);
   Args a{x, y, nullptr, nullptr, nullptr, nullptr};
   cudaStream_t s = (cudaStream_t)stream;
+  if (try_march(op, transpose, flags, m, x, y, s)) return check_launch("dzb_tm_apply (march)");
   DZB_DISPATCH(launch_all(with_flags<R>(flags), MODE_APPLY, m, a, s));
   return check_launch("dzb_tm_apply");
 }

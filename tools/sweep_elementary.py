@@ -43,6 +43,28 @@ def main():
     big = torch.randn(mesh.nE, dtype=torch.float64, device=dev)
     out = torch.empty(mesh.nE, dtype=torch.float64, device=dev)
     ref = {}
+    march = [int(c) for c in sys.argv[3].split(",")] if len(sys.argv) > 3 else [-1, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14]
+    MARCH = {-1: "per-operator tuned", 1: "by4 kc32", 2: "by8 kc32", 3: "by8 kc16", 4: "by8 kc16 minb8", 5: "by8 kc32 minb8", 6: "by4 kc32 minb16",
+             7: "by4 kc16 minb16", 8: "by8 kc8 minb8", 9: "by16 kc16 minb4", 10: "by8 kc16 minb6", 11: "by8 kc64 minb8",
+             12: "by8 kc16 minb4", 13: "by8 kc16 minb2", 14: "by4 kc16 minb1"}
+    lib.dzb_tune_march(0)
+    for name, op in names[:6]:
+        x, y = big[:op.shape[1]], out[:op.shape[0]]
+        op.apply_device(x, out=y)
+        ref["m" + name] = y.clone() if name in ("D", "G.T") else float(y.abs().sum())
+    for mc in march:
+        lib.dzb_tune_march(mc)
+        row = {"march": mc, "shape": MARCH.get(mc, "?")}
+        for name, op in names[:6]:
+            x, y = big[:op.shape[1]], out[:op.shape[0]]
+            ms = timeit(lambda: op.apply_device(x, out=y))
+            row[name] = f"{ms:.3f}ms {8.0 * (op.shape[0] + op.shape[1]) / ms / 1e6 / PEAK:.2f}"
+            r = ref["m" + name]
+            err = float((y - r).abs().max() / r.abs().max()) if torch.is_tensor(r) else abs(float(y.abs().sum()) - r) / r
+            if err > 1e-12:
+                row[name] += f" ERR {err:.1e}"
+        print(json.dumps(row), flush=True)
+    lib.dzb_tune_march(0)
     for cfg in cfgs:
         lib.dzb_tune_elementary(cfg)
         row = {"cfg": cfg, "shape": CFGS.get(cfg, "?")}
@@ -57,6 +79,7 @@ def main():
             ref.setdefault(name, chk)
         print(json.dumps(row), flush=True)
     lib.dzb_tune_elementary(2)
+    lib.dzb_tune_march(-1)
 
 
 if __name__ == "__main__":
