@@ -254,6 +254,76 @@ __global__ void DZB_MARCH_BOUNDS(CFG) k_curlT_march(TM m, const double *__restri
   DZB_MARCH_LOOP(step)
 }
 
+// ---- averages to cell centres ------------------------------------------------------------------------------------
+// average_face_to_cell: (1/3) (1/2) (the two faces per direction) -- the same walk as the divergence
+template <class CFG>
+__global__ void DZB_MARCH_BOUNDS(CFG) k_aveF2CC_march(TM m, const double *__restrict__ u, double *__restrict__ out) {
+  MarchGeom g;
+  const i64 nx = m.nx, ny = m.ny, nz = m.nz;
+  if (!g.template init<CFG>(nx, ny, nz)) return;
+  const i64 i = g.i, j = g.j;
+  const i64 pFx = nx + 1, plFx = pFx * ny, plFy = nx * (ny + 1), plC = nx * ny;
+  const double *fx = u + i + pFx * j + plFx * g.k0;
+  const double *fy = u + m.off<LOC_FY>() + i + nx * j + plFy * g.k0;
+  const double *fz = u + m.off<LOC_FZ>() + i + nx * j + plC * g.k0;
+  double *o = out + i + nx * j + plC * g.k0;
+  const double w = (1.0 / 3.0) * 0.5;
+  double z0 = __ldg(fz);
+#pragma unroll 4
+  for (i64 k = g.k0; k < g.k1; ++k) {
+    const double z1 = __ldg(fz + plC);
+    const double sx = __ldg(fx) + __ldg(fx + 1), sy = __ldg(fy) + __ldg(fy + nx);
+    *o = w * sx + w * sy + w * (z0 + z1);
+    z0 = z1;
+    fx += plFx; fy += plFy; fz += plC; o += plC;
+  }
+}
+
+// average_edge_to_cell: (1/3) (1/4) (the four edges per direction); the plane sums of Ex / Ey are carried
+template <class CFG>
+__global__ void DZB_MARCH_BOUNDS(CFG) k_aveE2CC_march(TM m, const double *__restrict__ e, double *__restrict__ out) {
+  MarchGeom g;
+  const i64 nx = m.nx, ny = m.ny, nz = m.nz;
+  if (!g.template init<CFG>(nx, ny, nz)) return;
+  const i64 i = g.i, j = g.j;
+  const i64 pN = nx + 1, plN = pN * (ny + 1), plEx = nx * (ny + 1), plEy = pN * ny, plC = nx * ny;
+  const double *ex = e + i + nx * j + plEx * g.k0;
+  const double *ey = e + m.off<LOC_EY>() + i + pN * j + plEy * g.k0;
+  const double *ez = e + m.off<LOC_EZ>() + i + pN * j + plN * g.k0;
+  double *o = out + i + nx * j + plC * g.k0;
+  const double w = (1.0 / 3.0) * 0.25;
+  double sx0 = __ldg(ex) + __ldg(ex + nx), sy0 = __ldg(ey) + __ldg(ey + 1);
+#pragma unroll 4
+  for (i64 k = g.k0; k < g.k1; ++k) {
+    const double sx1 = __ldg(ex + plEx) + __ldg(ex + plEx + nx), sy1 = __ldg(ey + plEy) + __ldg(ey + plEy + 1);
+    const double sz = (__ldg(ez) + __ldg(ez + 1)) + (__ldg(ez + pN) + __ldg(ez + pN + 1));
+    *o = w * (sx0 + sx1) + w * (sy0 + sy1) + w * sz;
+    sx0 = sx1; sy0 = sy1;
+    ex += plEx; ey += plEy; ez += plN; o += plC;
+  }
+}
+
+// average_node_to_cell: 1/8 of the eight corner nodes; the four-node sum of a plane is carried
+template <class CFG>
+__global__ void DZB_MARCH_BOUNDS(CFG) k_aveN2CC_march(TM m, const double *__restrict__ v, double *__restrict__ out) {
+  MarchGeom g;
+  const i64 nx = m.nx, ny = m.ny, nz = m.nz;
+  if (!g.template init<CFG>(nx, ny, nz)) return;
+  const i64 i = g.i, j = g.j;
+  const i64 pN = nx + 1, plN = pN * (ny + 1), plC = nx * ny;
+  const double *p = v + i + pN * j + plN * g.k0;
+  double *o = out + i + nx * j + plC * g.k0;
+  double s0 = (__ldg(p) + __ldg(p + 1)) + (__ldg(p + pN) + __ldg(p + pN + 1));
+#pragma unroll 4
+  for (i64 k = g.k0; k < g.k1; ++k) {
+    p += plN;
+    const double s1 = (__ldg(p) + __ldg(p + 1)) + (__ldg(p + pN) + __ldg(p + pN + 1));
+    *o = 0.125 * (s0 + s1);
+    s0 = s1;
+    o += plC;
+  }
+}
+
 template <class CFG> static dim3 march_grid(i64 ext_x, i64 ext_y, i64 ext_z) {
   return dim3((unsigned)((ext_x + 31) / 32), (unsigned)((ext_y + CFG::BY - 1) / CFG::BY),
               (unsigned)((ext_z + CFG::KC - 1) / CFG::KC));
@@ -270,6 +340,9 @@ static bool launch_march(int op, int transpose, const TM &m, const double *x, do
   else if (op == DZB_OP_DIV) k_divT_march<CFG><<<gn, b, 0, s>>>(m, x, y);
   else if (op == DZB_OP_CURL && !transpose) k_curl_march<CFG><<<gn, b, 0, s>>>(m, x, y);
   else if (op == DZB_OP_CURL) k_curlT_march<CFG><<<gn, b, 0, s>>>(m, x, y);
+  else if (op == DZB_OP_AVE_F2CC && !transpose) k_aveF2CC_march<CFG><<<march_grid<CFG>(m.nx, m.ny, m.nz), b, 0, s>>>(m, x, y);
+  else if (op == DZB_OP_AVE_E2CC && !transpose) k_aveE2CC_march<CFG><<<march_grid<CFG>(m.nx, m.ny, m.nz), b, 0, s>>>(m, x, y);
+  else if (op == DZB_OP_AVE_N2CC && !transpose) k_aveN2CC_march<CFG><<<march_grid<CFG>(m.nx, m.ny, m.nz), b, 0, s>>>(m, x, y);
   else return false;
   return true;
 }
@@ -289,6 +362,9 @@ static bool launch_march_tuned(int op, int transpose, const TM &m, const double 
   else if (op == DZB_OP_GRAD) k_gradT_march<Wide><<<gnW, bW, 0, s>>>(m, x, y);
   else if (op == DZB_OP_CURL && !transpose) k_curl_march<Mid32><<<march_grid<Mid32>(m.nx + 1, m.ny + 1, m.nz + 1), dim3(32, Mid32::BY, 1), 0, s>>>(m, x, y);
   else if (op == DZB_OP_CURL) k_curlT_march<Wide><<<gnW, bW, 0, s>>>(m, x, y);
+  else if (op == DZB_OP_AVE_F2CC && !transpose) k_aveF2CC_march<Wide><<<march_grid<Wide>(m.nx, m.ny, m.nz), bW, 0, s>>>(m, x, y);
+  else if (op == DZB_OP_AVE_E2CC && !transpose) k_aveE2CC_march<Wide><<<march_grid<Wide>(m.nx, m.ny, m.nz), bW, 0, s>>>(m, x, y);
+  else if (op == DZB_OP_AVE_N2CC && !transpose) k_aveN2CC_march<Wide><<<march_grid<Wide>(m.nx, m.ny, m.nz), bW, 0, s>>>(m, x, y);
   else return false;
   return true;
 }

@@ -13,6 +13,7 @@
 //       reference: base/base_tensor_mesh.py:865-988, inner_products.py:405-565.
 #include "tm_mass_common.cuh"
 #include "tm_rowkernels.cuh"
+#include "tm_mass_march.cuh"
 
 namespace dzb {
 
@@ -44,8 +45,14 @@ __global__ void __launch_bounds__(BX *BY *BZ)
   mass_diag_one<EDGE, 2, MODE>(m, md, inv_mat, i, j, k, x, out);
 }
 
+int g_mass_march = 1;  // 0: generic kernel (kept as cross-check), 1: plane-marching kernel (> 1: sweep configurations)
+
 template <bool EDGE, int MODE>
 static void launch_mass_diag(const TM &m, const Model &md, bool inv_mat, const double *x, double *out, cudaStream_t s) {
+  if (g_mass_march) {
+    launch_mass_diag_march<EDGE, MODE>(m, md, inv_mat, x, out, s);
+    return;
+  }
   k_mass_diag<EDGE, MODE><<<grid_for<LOC_N>(m), dim3(BX, BY, BZ), 0, s>>>(m, md, inv_mat, x, out);
 }
 
@@ -302,6 +309,9 @@ static int make_model(const TM &m, int flags, int kind, const double *model, dou
 }  // namespace dzb
 
 using namespace dzb;
+
+// experiment knob (not part of the stable ABI)
+extern "C" void dzb_tune_mass(int march) { dzb::g_mass_march = march; }
 
 extern "C" int dzb_tm_mass_diag(const DzbTensorMesh *mm, int flags, int model_kind, const double *model,
                                 double model_scalar, double *diag, void *stream) {

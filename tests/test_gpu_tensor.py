@@ -60,7 +60,8 @@ def test_core_operators_marching_and_generic_kernels(shape, march):
     lib = ctypes.CDLL(LIB_PATH)
     lib.dzb_tune_march(march)
     try:
-        for name in ("face_divergence", "nodal_gradient", "edge_curl"):
+        for name in ("face_divergence", "nodal_gradient", "edge_curl", "average_face_to_cell", "average_edge_to_cell",
+                     "average_node_to_cell"):
             ref = ORACLE_OPS[name](grid)
             op = getattr(mesh, name)
             x, y = rng.standard_normal(ref.shape[1]), rng.standard_normal(ref.shape[0])

@@ -39,7 +39,13 @@ def main():
     names = [("D", mesh.face_divergence), ("D.T", mesh.face_divergence.T), ("G", mesh.nodal_gradient),
              ("G.T", mesh.nodal_gradient.T), ("C", mesh.edge_curl), ("C.T", mesh.edge_curl.T),
              ("aveE2CC", mesh.average_edge_to_cell), ("aveF2CCV.T", mesh.average_face_to_cell_vector.T),
-             ("aveN2CC", mesh.average_node_to_cell), ("cellGrad", mesh.cell_gradient)]
+             ("aveN2CC", mesh.average_node_to_cell), ("aveF2CC", mesh.average_face_to_cell), ("cellGrad", mesh.cell_gradient)]
+    sig = torch.rand(mesh.nC, dtype=torch.float64, device=dev) + 0.5
+    sig3 = torch.rand((mesh.nC, 3), dtype=torch.float64, device=dev) + 0.5
+    mass = [("Mf(iso)", mesh.get_face_inner_product(sig), 8.0 * (2 * mesh.nF + mesh.nC)),
+            ("Me(iso)", mesh.get_edge_inner_product(sig), 8.0 * (2 * mesh.nE + mesh.nC)),
+            ("Me(aniso)", mesh.get_edge_inner_product(sig3), 8.0 * (2 * mesh.nE + 3 * mesh.nC)),
+            ("Mf(iso)^-1", mesh.get_face_inner_product(sig, invert_model=True, invert_matrix=True), 8.0 * (2 * mesh.nF + mesh.nC))]
     big = torch.randn(mesh.nE, dtype=torch.float64, device=dev)
     out = torch.empty(mesh.nE, dtype=torch.float64, device=dev)
     ref = {}
@@ -48,14 +54,15 @@ def main():
              7: "by4 kc16 minb16", 8: "by8 kc8 minb8", 9: "by16 kc16 minb4", 10: "by8 kc16 minb6", 11: "by8 kc64 minb8",
              12: "by8 kc16 minb4", 13: "by8 kc16 minb2", 14: "by4 kc16 minb1"}
     lib.dzb_tune_march(0)
-    for name, op in names[:6]:
+    NM = [n for n in names if n[0] in ("D", "D.T", "G", "G.T", "C", "C.T", "aveE2CC", "aveN2CC", "aveF2CC")]
+    for name, op in NM:
         x, y = big[:op.shape[1]], out[:op.shape[0]]
         op.apply_device(x, out=y)
         ref["m" + name] = y.clone() if name in ("D", "G.T") else float(y.abs().sum())
     for mc in march:
         lib.dzb_tune_march(mc)
         row = {"march": mc, "shape": MARCH.get(mc, "?")}
-        for name, op in names[:6]:
+        for name, op in NM:
             x, y = big[:op.shape[1]], out[:op.shape[0]]
             ms = timeit(lambda: op.apply_device(x, out=y))
             row[name] = f"{ms:.3f}ms {8.0 * (op.shape[0] + op.shape[1]) / ms / 1e6 / PEAK:.2f}"
@@ -63,6 +70,14 @@ def main():
             err = float((y - r).abs().max() / r.abs().max()) if torch.is_tensor(r) else abs(float(y.abs().sum()) - r) / r
             if err > 1e-12:
                 row[name] += f" ERR {err:.1e}"
+        print(json.dumps(row), flush=True)
+    for mm in (0, 1, 2, 3, 4, 5, 6, 7):
+        lib.dzb_tune_mass(mm)
+        row = {"mass_march": mm}
+        for name, op, nbytes in mass:
+            x, y = big[:op.shape[1]], out[:op.shape[0]]
+            ms = timeit(lambda: op.apply_device(x, out=y))
+            row[name] = f"{ms:.3f}ms {nbytes / ms / 1e6 / PEAK:.2f}"
         print(json.dumps(row), flush=True)
     lib.dzb_tune_march(0)
     for cfg in cfgs:
