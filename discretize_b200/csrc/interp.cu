@@ -98,15 +98,20 @@ __device__ __forceinline__ void entries(const AxisHit &hx, const AxisHit &hy, co
   }
 }
 
-// K10: locate + weights.  Persistent tiles of IT points; outputs are transposed through
-// shared memory so that the (npts x 8) tables are written with fully coalesced stores.
+// K10: locate + weights.  Persistent tiles of IT points; the (npts x 8) tables are transposed through shared
+// memory so that they are written with fully coalesced stores.  Column indices are int32 whenever the operator has
+// fewer than 2^31 columns (like scipy's index arrays): 96 instead of 128 bytes written per point.  The axes are
+// read through L1 (after the index guess a point touches ~3 entries per axis), so a block needs only the two
+// transposition buffers (13.8 KB) and 16 blocks = 64 warps stay resident per SM (the first version staged the
+// axes in 32 KB of shared memory and ran at 25 % occupancy: ncu, profiles/r1b_*).
+template <typename IDX>
 __global__ void __launch_bounds__(IT) k_interp_locate(Axes g, const double *__restrict__ pts, i64 npts, i64 col_offset,
-                                                      i64 *__restrict__ cols, double *__restrict__ w) {
+                                                      IDX *__restrict__ cols, double *__restrict__ w) {
   extern __shared__ double smem[];
   double *sw = smem;                          // IT*9 weights (padded rows)
-  i64 *sc = (i64 *)(smem + IT * 9);           // IT*9 columns
-  double *sax = smem + 2 * IT * 9;
-  const Axes a = stage_axes(g, sax, 4096);
+  IDX *sc = (IDX *)(smem + IT * 9);           // IT*9 columns
+  Axes a = g;
+  axes_means(a);
   const i64 ntiles = (npts + IT - 1) / IT;
   for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const i64 p = tile * IT + threadIdx.x;
@@ -120,7 +125,7 @@ __global__ void __launch_bounds__(IT) k_interp_locate(Axes g, const double *__re
 #pragma unroll
       for (int e = 0; e < 8; ++e) {  // row pitch 9: at most 2-way bank conflicts
         sw[threadIdx.x * 9 + e] = w8[e];
-        sc[threadIdx.x * 9 + e] = c8[e];
+        sc[threadIdx.x * 9 + e] = (IDX)c8[e];
       }
     }
     __syncthreads();
@@ -141,7 +146,8 @@ __global__ void __launch_bounds__(IT) k_interp_locate(Axes g, const double *__re
 
 // K11: y[p] = scale[p] * sum_e w[p,e] v[cols[p,e]].  Eight lanes per point: the tables are
 // read fully coalesced, the gathers run 32-wide, partial sums combine with shuffles.
-__global__ void __launch_bounds__(256) k_interp_apply(const i64 *__restrict__ cols, const double *__restrict__ w,
+template <typename IDX>
+__global__ void __launch_bounds__(256) k_interp_apply(const IDX *__restrict__ cols, const double *__restrict__ w,
                                                       const double *__restrict__ scale, i64 npts,
                                                       const double *__restrict__ v, double *__restrict__ y) {
   const i64 nent = npts * 8;
@@ -149,7 +155,7 @@ __global__ void __launch_bounds__(256) k_interp_apply(const i64 *__restrict__ co
   const i64 nent_pad = (nent + 31) / 32 * 32;
   for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < nent_pad; t += stride) {
     double part = 0.0;
-    if (t < nent) part = __ldg(w + t) * __ldg(v + __ldg(cols + t));
+    if (t < nent) part = __ldg(w + t) * __ldg(v + (i64)__ldg(cols + t));
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
     part += __shfl_xor_sync(0xffffffffu, part, 4);
@@ -161,7 +167,8 @@ __global__ void __launch_bounds__(256) k_interp_apply(const i64 *__restrict__ co
 }
 
 // y[cols[p,e]] += scale[p] w[p,e] x[p]
-__global__ void __launch_bounds__(256) k_interp_apply_t(const i64 *__restrict__ cols, const double *__restrict__ w,
+template <typename IDX>
+__global__ void __launch_bounds__(256) k_interp_apply_t(const IDX *__restrict__ cols, const double *__restrict__ w,
                                                         const double *__restrict__ scale, i64 npts,
                                                         const double *__restrict__ x, double *__restrict__ y) {
   const i64 nent = npts * 8;
@@ -170,7 +177,7 @@ __global__ void __launch_bounds__(256) k_interp_apply_t(const i64 *__restrict__ 
     const i64 p = t >> 3;
     double xv = __ldg(x + p);
     if (scale) xv *= __ldg(scale + p);
-    atomicAdd(y + __ldg(cols + t), __ldg(w + t) * xv);
+    atomicAdd(y + (i64)__ldg(cols + t), __ldg(w + t) * xv);
   }
 }
 
@@ -234,32 +241,41 @@ static unsigned blocks_for(i64 work_items, int per_block, int waves) {
 
 using namespace dzb;
 
+template <typename IDX>
+static void launch_locate(const Axes &g, const double *pts, i64 npts, i64 col_offset, void *cols, double *w, cudaStream_t s) {
+  const size_t smem = IT * 9 * (sizeof(double) + sizeof(IDX));
+  k_interp_locate<IDX><<<blocks_for(npts, IT, 16), IT, smem, s>>>(g, pts, npts, col_offset, (IDX *)cols, w);
+}
+
 extern "C" int dzb_interp_locate(const double *tx, int64_t ntx, const double *ty, int64_t nty, const double *tz,
-                                 int64_t ntz, const double *pts, int64_t npts, int64_t col_offset, int64_t *cols,
-                                 double *w, void *stream) {
+                                 int64_t ntz, const double *pts, int64_t npts, int64_t col_offset, void *cols,
+                                 int cols_is64, double *w, void *stream) {
   if (npts == 0) return 0;
-  Axes g{tx, ty, tz, ntx, nty, ntz, 0.0, 0.0, 0.0};
-  const size_t smem = (2 * IT * 9 + 4096) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_interp_locate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
+  if (!cols_is64 && col_offset + ntx * nty * ntz > 2147483647LL) {
+    set_error("dzb_interp_locate: column indices do not fit int32; pass an int64 table (cols_is64 = 1)");
+    return -1;
   }
-  k_interp_locate<<<blocks_for(npts, IT, 8), IT, smem, (cudaStream_t)stream>>>(g, pts, npts, col_offset, (i64 *)cols, w);
+  Axes g{tx, ty, tz, ntx, nty, ntz, 0.0, 0.0, 0.0};
+  if (cols_is64) launch_locate<i64>(g, pts, npts, col_offset, cols, w, (cudaStream_t)stream);
+  else launch_locate<int>(g, pts, npts, col_offset, cols, w, (cudaStream_t)stream);
   return check_launch("dzb_interp_locate");
 }
 
-extern "C" int dzb_interp_apply(const int64_t *cols, const double *w, const double *row_scale, int64_t npts,
+extern "C" int dzb_interp_apply(const void *cols, int cols_is64, const double *w, const double *row_scale, int64_t npts,
                                 const double *v, double *y, void *stream) {
   if (npts == 0) return 0;
-  k_interp_apply<<<blocks_for(npts * 8, 256, 16), 256, 0, (cudaStream_t)stream>>>((const i64 *)cols, w, row_scale, npts, v, y);
+  const unsigned nb = blocks_for(npts * 8, 256, 16);
+  if (cols_is64) k_interp_apply<i64><<<nb, 256, 0, (cudaStream_t)stream>>>((const i64 *)cols, w, row_scale, npts, v, y);
+  else k_interp_apply<int><<<nb, 256, 0, (cudaStream_t)stream>>>((const int *)cols, w, row_scale, npts, v, y);
   return check_launch("dzb_interp_apply");
 }
 
-extern "C" int dzb_interp_apply_t(const int64_t *cols, const double *w, const double *row_scale, int64_t npts,
-                                  const double *x, double *y, void *stream) {
+extern "C" int dzb_interp_apply_t(const void *cols, int cols_is64, const double *w, const double *row_scale,
+                                  int64_t npts, const double *x, double *y, void *stream) {
   if (npts == 0) return 0;
-  k_interp_apply_t<<<blocks_for(npts * 8, 256, 16), 256, 0, (cudaStream_t)stream>>>((const i64 *)cols, w, row_scale, npts, x, y);
+  const unsigned nb = blocks_for(npts * 8, 256, 16);
+  if (cols_is64) k_interp_apply_t<i64><<<nb, 256, 0, (cudaStream_t)stream>>>((const i64 *)cols, w, row_scale, npts, x, y);
+  else k_interp_apply_t<int><<<nb, 256, 0, (cudaStream_t)stream>>>((const int *)cols, w, row_scale, npts, x, y);
   return check_launch("dzb_interp_apply_t");
 }
 

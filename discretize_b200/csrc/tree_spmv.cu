@@ -64,6 +64,133 @@ __global__ void __launch_bounds__(256)
   if (row < nrows && l == 0) y[row] = acc;
 }
 
+// ---- coalesced variants ------------------------------------------------------------------------------------------
+// ncu (profiles/r1b_k12_*): the thread-per-row kernel above moves only 1.2x the algorithmic bytes through DRAM but is
+// latency-bound on its dependent loads (row pointer -> index -> gather), all of them strided across the warp.
+
+__device__ __forceinline__ double coded_value(int c, int col, const double *s_mult, const unsigned char *s_sel, bool bycol,
+                                              const double (&gr)[3], const double *__restrict__ g0,
+                                              const double *__restrict__ g1, const double *__restrict__ g2) {
+  const int s = s_sel[c];
+  double g = 1.0;
+  if (s) g = bycol ? __ldg((s == 1 ? g0 : s == 2 ? g1 : g2) + col) : gr[s - 1];
+  return s_mult[c] * g;
+}
+
+constexpr int ELL_PAD = 255;  // code of a padding slot (rows shorter than the ELL width)
+
+// ELL (column-major) layout: entry e of row r sits at e*stride + r, so a warp reads 32 consecutive indices / codes
+// per step and needs no row pointers.  On a balanced OcTree every cell-rowed operator has rows of ONE length
+// (face_divergence 6, average_face / edge / node_to_cell 6 / 12 / 8); edge_curl rows hold 4..6 entries and are
+// padded with ELL_PAD slots.  KT > 0: row length known at compile time -- fully unrolled, so the KT index loads and
+// then the KT gathers of a row are all in flight together (the gathers are latency-bound: +18..42 % over run-time K).
+template <bool BYCOL, int KT>
+__global__ void __launch_bounds__(256)
+    k_tree_ell(i64 nrows, int K, i64 stride, const int *__restrict__ indices, const unsigned char *__restrict__ codes,
+               const double *__restrict__ tab_mult, const unsigned char *__restrict__ tab_sel, int ntab,
+               const double *__restrict__ g0, const double *__restrict__ g1, const double *__restrict__ g2,
+               const double *__restrict__ x, double *__restrict__ y) {
+  __shared__ double s_mult[256];
+  __shared__ unsigned char s_sel[256];
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) {
+    s_mult[t] = t < ntab ? tab_mult[t] : 0.0;
+    s_sel[t] = t < ntab ? tab_sel[t] : 0;
+  }
+  __syncthreads();
+  const i64 row = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrows) return;
+  double gr[3] = {1.0, 1.0, 1.0};
+  if (!BYCOL) {
+    if (g0) gr[0] = __ldg(g0 + row);
+    if (g1) gr[1] = __ldg(g1 + row);
+    if (g2) gr[2] = __ldg(g2 + row);
+  }
+  double acc = 0.0;
+  const int *pi = indices + row;
+  const unsigned char *pc = codes + row;
+  if (KT > 0) {
+    int col[KT > 0 ? KT : 1], c[KT > 0 ? KT : 1];
+    double xv[KT > 0 ? KT : 1];
+#pragma unroll
+    for (int e = 0; e < KT; ++e) {
+      col[e] = __ldg(pi + e * stride);
+      c[e] = __ldg(pc + e * stride);
+    }
+#pragma unroll
+    for (int e = 0; e < KT; ++e) xv[e] = c[e] != ELL_PAD ? __ldg(x + col[e]) : 0.0;
+#pragma unroll
+    for (int e = 0; e < KT; ++e)
+      if (c[e] != ELL_PAD) acc += coded_value(c[e], col[e], s_mult, s_sel, BYCOL, gr, g0, g1, g2) * xv[e];
+  } else {
+#pragma unroll 4
+    for (int e = 0; e < K; ++e) {
+      const int col = __ldg(pi);
+      const int c = __ldg(pc);
+      if (c != ELL_PAD) acc += coded_value(c, col, s_mult, s_sel, BYCOL, gr, g0, g1, g2) * __ldg(x + col);
+      pi += stride;
+      pc += stride;
+    }
+  }
+  y[row] = acc;
+}
+
+// CSR with warp-staged entries: a warp owns 32 consecutive rows; the contiguous span of their entries is copied
+// to shared memory with coalesced loads, then every lane walks its own row out of shared memory.  (Measured SLOWER
+// than the plain kernel on OcTree operators -- the gathers, not the index loads, set the pace -- kept for comparison.)
+constexpr int STREAM_CAP = 512;   // entries staged per warp (spans longer than this read global memory directly)
+
+template <bool BYCOL, typename IP>
+__global__ void __launch_bounds__(256)
+    k_tree_stream(i64 nrows, const IP *__restrict__ indptr, const int *__restrict__ indices,
+                  const unsigned char *__restrict__ codes, const double *__restrict__ tab_mult,
+                  const unsigned char *__restrict__ tab_sel, int ntab, const double *__restrict__ g0,
+                  const double *__restrict__ g1, const double *__restrict__ g2, const double *__restrict__ x,
+                  double *__restrict__ y) {
+  __shared__ double s_mult[256];
+  __shared__ unsigned char s_sel[256];
+  __shared__ int s_idx[8][STREAM_CAP];
+  __shared__ unsigned char s_code[8][STREAM_CAP];
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) {
+    s_mult[t] = t < ntab ? tab_mult[t] : 0.0;
+    s_sel[t] = t < ntab ? tab_sel[t] : 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int *my_idx = s_idx[wib];
+  unsigned char *my_code = s_code[wib];
+  for (i64 row0 = ((i64)blockIdx.x * 8 + wib) * 32; row0 < nrows; row0 += (i64)gridDim.x * 256) {
+    const i64 row = row0 + lane;
+    const bool live = row < nrows;
+    const i64 p0 = (i64)indptr[live ? row : nrows], p1 = live ? (i64)indptr[row + 1] : p0;
+    const i64 start = __shfl_sync(0xffffffffu, p0, 0), end = __shfl_sync(0xffffffffu, p1, 31);
+    const i64 span = end - start;
+    const bool staged = span <= STREAM_CAP;
+    if (staged) {
+      for (i64 t = lane; t < span; t += 32) {
+        my_idx[t] = __ldg(indices + start + t);
+        my_code[t] = __ldg(codes + start + t);
+      }
+    }
+    __syncwarp();
+    if (live) {
+      double gr[3] = {1.0, 1.0, 1.0};
+      if (!BYCOL) {
+        if (g0) gr[0] = __ldg(g0 + row);
+        if (g1) gr[1] = __ldg(g1 + row);
+        if (g2) gr[2] = __ldg(g2 + row);
+      }
+      double acc = 0.0;
+      for (i64 p = p0; p < p1; ++p) {
+        const int col = staged ? my_idx[p - start] : __ldg(indices + p);
+        const int c = staged ? my_code[p - start] : __ldg(codes + p);
+        acc += coded_value(c, col, s_mult, s_sel, BYCOL, gr, g0, g1, g2) * __ldg(x + col);
+      }
+      y[row] = acc;
+    }
+    __syncwarp();
+  }
+}
+
 // generic CSR with stored float64 values (scipy matrices mixed into operator algebra, full-tensor
 // OcTree mass matrices): same lane-group mapping, values read instead of generated
 template <int LPR, typename IP>
@@ -136,6 +263,19 @@ extern "C" int dzb_tree_spmv(int64_t nrows, const void *indptr, int indptr_is64,
     return -1;
   }
   cudaStream_t s = (cudaStream_t)stream;
+  if (lanes_per_row == 0) {   // warp-staged CSR
+    int sm = 148;
+    const i64 need = (nrows + 255) / 256;
+    const unsigned blocks = (unsigned)(need < (i64)sm * 32 ? need : (i64)sm * 32);
+    if (geom_by_col) {
+      if (indptr_is64) k_tree_stream<true, i64><<<blocks, 256, 0, s>>>(nrows, (const i64 *)indptr, indices, codes, tab_mult, tab_sel, ntab, g0, g1, g2, x, y);
+      else k_tree_stream<true, int><<<blocks, 256, 0, s>>>(nrows, (const int *)indptr, indices, codes, tab_mult, tab_sel, ntab, g0, g1, g2, x, y);
+    } else {
+      if (indptr_is64) k_tree_stream<false, i64><<<blocks, 256, 0, s>>>(nrows, (const i64 *)indptr, indices, codes, tab_mult, tab_sel, ntab, g0, g1, g2, x, y);
+      else k_tree_stream<false, int><<<blocks, 256, 0, s>>>(nrows, (const int *)indptr, indices, codes, tab_mult, tab_sel, ntab, g0, g1, g2, x, y);
+    }
+    return check_launch("dzb_tree_spmv (stream)");
+  }
   if (geom_by_col) {
     if (indptr_is64) dispatch_lpr<true, i64>(lanes_per_row, nrows, indptr, indices, codes, tab_mult, tab_sel, ntab, g0, g1, g2, x, y, s);
     else dispatch_lpr<true, int>(lanes_per_row, nrows, indptr, indices, codes, tab_mult, tab_sel, ntab, g0, g1, g2, x, y, s);
@@ -144,6 +284,33 @@ extern "C" int dzb_tree_spmv(int64_t nrows, const void *indptr, int indptr_is64,
     else dispatch_lpr<false, int>(lanes_per_row, nrows, indptr, indices, codes, tab_mult, tab_sel, ntab, g0, g1, g2, x, y, s);
   }
   return check_launch("dzb_tree_spmv");
+}
+
+extern "C" int dzb_tree_ell_spmv(int64_t nrows, int row_len, int64_t stride, const int32_t *indices, const uint8_t *codes,
+                                 const double *tab_mult, const uint8_t *tab_sel, int ntab, const double *g0,
+                                 const double *g1, const double *g2, int geom_by_col, const double *x, double *y,
+                                 void *stream) {
+  if (nrows <= 0) return 0;
+  if (ntab < 1 || ntab > 255 || row_len < 0 || stride < nrows) {
+    set_error("dzb_tree_ell_spmv: bad table size (1..255; code 255 marks padding), row length or stride");
+    return -1;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)((nrows + 255) / 256);
+#define DZB_ELL_LAUNCH(BC, KT) \
+  k_tree_ell<BC, KT><<<blocks, 256, 0, s>>>(nrows, row_len, stride, indices, codes, tab_mult, tab_sel, ntab, g0, g1, g2, x, y)
+  if (geom_by_col) {
+    DZB_ELL_LAUNCH(true, 0);
+  } else {
+    switch (row_len) {
+      case 6: DZB_ELL_LAUNCH(false, 6); break;
+      case 8: DZB_ELL_LAUNCH(false, 8); break;
+      case 12: DZB_ELL_LAUNCH(false, 12); break;
+      default: DZB_ELL_LAUNCH(false, 0); break;
+    }
+  }
+#undef DZB_ELL_LAUNCH
+  return check_launch("dzb_tree_ell_spmv");
 }
 
 extern "C" int dzb_csr_spmv(int64_t nrows, const void *indptr, int indptr_is64, const int32_t *indices,

@@ -45,6 +45,7 @@ class InterpolationOperator(Operator):
         self.pts = pts_dev
         self.axes = [to_device(t) for t in mesh.get_tensor(key)]
         self.cols = self.w = None
+        self.cols_is64 = ncols > 2**31 - 1      # int32 column tables while they fit (like scipy's indices)
         if store:
             self._locate()
 
@@ -55,10 +56,10 @@ class InterpolationOperator(Operator):
     def _locate(self):
         npts = self.shape[0]
         dev = cuda_device()
-        self.cols = torch.empty((npts, 8), dtype=torch.int64, device=dev)
+        self.cols = torch.empty((npts, 8), dtype=torch.int64 if self.cols_is64 else torch.int32, device=dev)
         self.w = torch.empty((npts, 8), dtype=torch.float64, device=dev)
         check(load().dzb_interp_locate(*self._axes_args(), ptr(self.pts), npts, self.col_offset, ptr(self.cols),
-                                       ptr(self.w), stream_ptr()), "dzb_interp_locate")
+                                       int(self.cols_is64), ptr(self.w), stream_ptr()), "dzb_interp_locate")
 
     def _dev_apply(self, x, out):
         npts = self.shape[0]
@@ -66,15 +67,15 @@ class InterpolationOperator(Operator):
             check(load().dzb_interp_fused(*self._axes_args(), ptr(self.pts), npts, self.col_offset,
                                           ptr(self.row_scale), ptr(x), ptr(out), stream_ptr()), "dzb_interp_fused")
         else:
-            check(load().dzb_interp_apply(ptr(self.cols), ptr(self.w), ptr(self.row_scale), npts, ptr(x), ptr(out),
-                                          stream_ptr()), "dzb_interp_apply")
+            check(load().dzb_interp_apply(ptr(self.cols), int(self.cols_is64), ptr(self.w), ptr(self.row_scale), npts,
+                                          ptr(x), ptr(out), stream_ptr()), "dzb_interp_apply")
 
     def _dev_apply_t(self, x, out):
         if self.cols is None:
             self._locate()
         out.zero_()
-        check(load().dzb_interp_apply_t(ptr(self.cols), ptr(self.w), ptr(self.row_scale), self.shape[0], ptr(x),
-                                        ptr(out), stream_ptr()), "dzb_interp_apply_t")
+        check(load().dzb_interp_apply_t(ptr(self.cols), int(self.cols_is64), ptr(self.w), ptr(self.row_scale),
+                                        self.shape[0], ptr(x), ptr(out), stream_ptr()), "dzb_interp_apply_t")
 
     def _tocsr(self):
         """COO -> CSR exactly like the reference: duplicate columns summed, sorted, explicit zeros kept;
@@ -82,7 +83,7 @@ class InterpolationOperator(Operator):
         if self.cols is None:
             self._locate()
         npts, ncols = self.shape
-        cols = self.cols.cpu().numpy().reshape(-1)
+        cols = self.cols.cpu().numpy().reshape(-1).astype(np.int64)
         w = self.w.cpu().numpy().reshape(-1)
         rows = np.repeat(np.arange(npts), 8)
         Q = sp.csr_matrix((w, (rows, cols)), shape=(npts, ncols))

@@ -46,29 +46,78 @@ class CodedCsr:
         self.shape = shape
         self.nnz = int(indptr[-1])
         self.is64 = self.nnz >= 2**31 - 1
-        self.indptr = to_device(indptr if self.is64 else indptr.astype(np.int32), torch.int64 if self.is64 else torch.int32)
-        self.indices = to_device(indices, torch.int32)
-        self.codes = to_device(codes, torch.uint8)
+        self._host = (indptr, indices, codes)
+        self.indptr = self.indices = self.codes = None
         self.tab_mult = to_device(tmult)
         self.tab_sel = to_device(tsel, torch.uint8)
         self.ntab = int(tmult.size)
         self.geoms = [to_device(g) for g in geoms] + [None] * (3 - len(geoms))
         self.geom_by_col = int(geom_by_col)
+        # layout (ncu, profiles/r1b_k12_*: thread-per-row CSR is L1-bound on strided index loads):
+        #   "ell"    every row has the same length (all cell-rowed operators of a balanced OcTree): column-major
+        #            entries, no row pointers, perfectly coalesced;
+        #   "stream" anything else: CSR whose entries a warp stages through shared memory with coalesced loads;
+        #   "lpr"    the first kernel (LPR lanes per row straight from global memory), kept for comparison.
+        lens = np.diff(indptr)
+        self.row_len = -1
+        if lens.size and self.ntab <= 255:
+            kmax, avg_len = int(lens.max()), float(lens.mean())
+            # one common length (all cell-rowed operators), or mildly variable rows (edge_curl: 4..6) padded
+            if kmax > 0 and (lens.min() == kmax or (kmax <= 12 and kmax <= 1.5 * avg_len)):
+                self.row_len = kmax
+        self.layout = "ell" if self.row_len > 0 else "lpr"   # measured: "stream" loses to "lpr" (tools/sweep_tree.py)
         avg = self.nnz / max(shape[0], 1)
-        # measured (tools/sweep_tree.py, profiles/): rows are short, one thread per row wins up to ~7 nnz/row
         self.lpr = 1 if avg <= 7 else 2 if avg <= 16 else 4 if avg <= 40 else 16
+        self.ell_indices = self.ell_codes = None
+        self.use_layout(self.layout)
+
+    def use_layout(self, layout):
+        """Select (and upload on first use) one of the device layouts: "ell" (constant row length only), "stream", "lpr"."""
+        indptr, indices, codes = self._host
+        if layout == "ell":
+            if self.row_len <= 0:
+                raise ValueError("the ELL layout needs rows of one common length")
+            if self.ell_indices is None:
+                n, K = self.shape[0], self.row_len
+                self.stride = (n + 31) // 32 * 32
+                ie = np.zeros((K, self.stride), dtype=np.int32)
+                ce = np.full((K, self.stride), 255, dtype=np.uint8)      # 255 = padding slot
+                lens = np.diff(indptr)
+                rows = np.repeat(np.arange(n), lens)
+                slot = np.arange(indices.size) - np.repeat(indptr[:-1], lens)
+                ie[slot, rows] = indices
+                ce[slot, rows] = codes
+                self.ell_indices = to_device(ie.reshape(-1), torch.int32)
+                self.ell_codes = to_device(ce.reshape(-1), torch.uint8)
+        elif layout in ("stream", "lpr"):
+            if self.indices is None:
+                self.indptr = to_device(indptr if self.is64 else indptr.astype(np.int32),
+                                        torch.int64 if self.is64 else torch.int32)
+                self.indices = to_device(indices, torch.int32)
+                self.codes = to_device(codes, torch.uint8)
+        else:
+            raise ValueError(f"unknown layout {layout!r}")
+        self.layout = layout
 
     def apply(self, x, out):
         g = self.geoms
+        if self.layout == "ell":
+            check(load().dzb_tree_ell_spmv(self.shape[0], self.row_len, self.stride, ptr(self.ell_indices),
+                                           ptr(self.ell_codes), ptr(self.tab_mult), ptr(self.tab_sel), self.ntab,
+                                           ptr(g[0]), ptr(g[1]), ptr(g[2]), self.geom_by_col, ptr(x), ptr(out),
+                                           stream_ptr()), "dzb_tree_ell_spmv")
+            return
+        lpr = 0 if self.layout == "stream" else self.lpr
         check(load().dzb_tree_spmv(self.shape[0], ptr(self.indptr), int(self.is64), ptr(self.indices), ptr(self.codes),
                                    ptr(self.tab_mult), ptr(self.tab_sel), self.ntab, ptr(g[0]), ptr(g[1]), ptr(g[2]),
-                                   self.geom_by_col, ptr(x), ptr(out), self.lpr, stream_ptr()), "dzb_tree_spmv")
+                                   self.geom_by_col, ptr(x), ptr(out), lpr, stream_ptr()), "dzb_tree_spmv")
 
     def bytes_per_apply(self):
         """Algorithmic bytes: vectors + int32 columns + code bytes + indptr + row geometry."""
         n_geom = sum(g is not None for g in self.geoms)
         gsize = (self.shape[1] if self.geom_by_col else self.shape[0]) * n_geom
-        return (8 * (self.shape[0] + self.shape[1]) + 5 * self.nnz + (8 if self.is64 else 4) * (self.shape[0] + 1) + 8 * gsize)
+        ptr_bytes = 0 if self.layout == "ell" else (8 if self.is64 else 4) * (self.shape[0] + 1)
+        return 8 * (self.shape[0] + self.shape[1]) + 5 * self.nnz + ptr_bytes + 8 * gsize   # padding slots not counted
 
 
 class TreeOperator(Operator):

@@ -166,16 +166,18 @@ int dzb_tm_maxwell_range(const DzbTensorMesh *m, const double *mui, const double
  * _extensions/interputils_cython.pyx:42-182.
  * tx,ty,tz: the three 1-D sample arrays of the location grid (device, lengths
  * ntx,nty,ntz), exactly the float64 arrays the host built (bit-exact bisection).
- * pts: (npts,3) row-major.  cols[npts*8] (int64, F-order flat index + col_offset) and
+ * pts: (npts,3) row-major.  cols[npts*8] (F-order flat index + col_offset; int32 entries when
+ * cols_is64 == 0 -- allowed while every index fits, like scipy's index arrays -- else int64) and
  * w[npts*8] in the reference's entry order. */
 int dzb_interp_locate(const double *tx, int64_t ntx, const double *ty, int64_t nty, const double *tz, int64_t ntz,
-                      const double *pts, int64_t npts, int64_t col_offset, int64_t *cols, double *w, void *stream);
+                      const double *pts, int64_t npts, int64_t col_offset, void *cols, int cols_is64, double *w,
+                      void *stream);
 /* y[npts] = Q v from stored cols/w;  row_scale (may be NULL) multiplies each row (0 for zeros_outside rows). */
-int dzb_interp_apply(const int64_t *cols, const double *w, const double *row_scale, int64_t npts, const double *v,
-                     double *y, void *stream);
+int dzb_interp_apply(const void *cols, int cols_is64, const double *w, const double *row_scale, int64_t npts,
+                     const double *v, double *y, void *stream);
 /* y[ncols] += Q^T x (y must be zeroed by the caller). */
-int dzb_interp_apply_t(const int64_t *cols, const double *w, const double *row_scale, int64_t npts, const double *x,
-                       double *y, void *stream);
+int dzb_interp_apply_t(const void *cols, int cols_is64, const double *w, const double *row_scale, int64_t npts,
+                       const double *x, double *y, void *stream);
 /* Fused locate + apply: y = Q v without storing Q. */
 int dzb_interp_fused(const double *tx, int64_t ntx, const double *ty, int64_t nty, const double *tz, int64_t ntz,
                      const double *pts, int64_t npts, int64_t col_offset, const double *row_scale, const double *v,
@@ -191,10 +193,16 @@ int dzb_points_inside(const double *pts, int64_t npts, const double *lo_host, co
  * value(entry) = tab_mult[code] * (tab_sel[code] == 0 ? 1 : g{tab_sel[code]-1}[row])
  * (geom_by_col != 0: the geometry is indexed by the column instead -- used for A^T).
  * indptr: int32 or int64 (indptr_is64); indices int32; tab_* are DEVICE arrays of ntab entries;
- * g0..g2 device arrays or NULL; lanes_per_row in {1,2,4,8,16,32}. */
+ * g0..g2 device arrays or NULL; lanes_per_row in {1,2,4,8,16,32}, or 0 for the warp-staged kernel (a warp copies
+ * the contiguous entries of its 32 rows to shared memory with coalesced loads, then each lane walks one row). */
 int dzb_tree_spmv(int64_t nrows, const void *indptr, int indptr_is64, const int32_t *indices, const uint8_t *codes,
                   const double *tab_mult, const uint8_t *tab_sel, int ntab, const double *g0, const double *g1,
                   const double *g2, int geom_by_col, const double *x, double *y, int lanes_per_row, void *stream);
+/* The same operator in ELL layout, for operators whose rows ALL hold row_len entries (on a balanced OcTree: every
+ * cell-rowed operator): entry e of row r at indices[e*stride + r] / codes[e*stride + r], stride >= nrows. */
+int dzb_tree_ell_spmv(int64_t nrows, int row_len, int64_t stride, const int32_t *indices, const uint8_t *codes,
+                      const double *tab_mult, const uint8_t *tab_sel, int ntab, const double *g0, const double *g1,
+                      const double *g2, int geom_by_col, const double *x, double *y, void *stream);
 /* y = A x for a CSR matrix with stored float64 values (int32 columns, int32 / int64 indptr): scipy
  * matrices mixed into operator algebra and the full-tensor OcTree mass matrices
  * (operators/inner_products.py:147-272 with tree_ext.pyx:5651-5763 projections). */

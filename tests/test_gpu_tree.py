@@ -150,3 +150,25 @@ def test_sharded_tree_operators_loopback(gold, world):
                 op.csr.apply(op.buf, op.out)
                 y[s.owned(kout)] = op.out.cpu().numpy()
             assert_close_vec(y, ref @ x)
+
+
+@pytest.mark.parametrize("name", ["face_divergence", "average_edge_to_cell", "edge_curl", "nodal_gradient"])
+def test_tree_spmv_layouts_agree(gold, name):
+    """ELL (constant row length), warp-staged CSR and the lanes-per-row kernel are three implementations of one SpMV."""
+    m = _mesh_from_fixture(gold, "b", "refine")
+    ref = golden_matrix(gold, f"b_{name}")
+    rng = np.random.default_rng(13)
+    x, y = rng.standard_normal(ref.shape[1]), rng.standard_normal(ref.shape[0])
+    op = getattr(m, name)
+    for tr, vec, r in ((False, x, ref @ x), (True, y, ref.T @ y)):
+        csr = op._csr(tr)
+        layouts = ["stream", "lpr"] + (["ell"] if csr.row_len > 0 else [])
+        if not tr and name in ("face_divergence", "average_edge_to_cell"):
+            assert "ell" in layouts       # every cell-rowed operator has rows of one length
+        for layout in layouts:
+            csr.use_layout(layout)
+            for lpr in ((1, 2, 8) if layout == "lpr" else (0,)):
+                csr.lpr = lpr
+                out = torch.empty(csr.shape[0], dtype=torch.float64, device="cuda")
+                csr.apply(torch.from_numpy(vec).cuda(), out)
+                assert_close_vec(out.cpu().numpy(), r)

@@ -20,7 +20,9 @@ for name in ("face_divergence", "edge_curl", "average_edge_to_cell", "average_no
     out = torch.empty(op.shape[0], dtype=torch.float64, device=dev)
     csr = op._csr(False)
     res = []
-    for lpr in (1, 2, 4, 8, 16):
+    variants = [("lpr", 1), ("lpr", 2), ("lpr", 4), ("stream", 0)] + ([("ell", 0)] if csr.row_len > 0 else [])
+    for layout, lpr in variants:
+        csr.use_layout(layout)
         csr.lpr = lpr
         for _ in range(3):
             op.apply_device(x, out=out)
@@ -28,5 +30,7 @@ for name in ("face_divergence", "edge_curl", "average_edge_to_cell", "average_no
         for _ in range(20):
             op.apply_device(x, out=out)
         e1.record(); torch.cuda.synchronize()
-        res.append((lpr, e0.elapsed_time(e1) / 20))
-    print(name, "nnz/row %.2f" % (csr.nnz / op.shape[0]), " ".join(f"lpr{l}:{t*1e3:.0f}us" for l, t in res), flush=True)
+        ms = e0.elapsed_time(e1) / 20
+        res.append((layout + (str(lpr) if layout == "lpr" else ""), ms, csr.bytes_per_apply() / ms / 1e6))
+    print(name, "rows", op.shape[0], "nnz/row %.2f" % (csr.nnz / op.shape[0]),
+          " ".join(f"{l}:{t*1e3:.0f}us({b:.0f}GB/s)" for l, t, b in res), flush=True)
