@@ -84,7 +84,7 @@ constexpr int ELL_PAD = 255;  // code of a padding slot (rows shorter than the E
 // (face_divergence 6, average_face / edge / node_to_cell 6 / 12 / 8); edge_curl rows hold 4..6 entries and are
 // padded with ELL_PAD slots.  KT > 0: row length known at compile time -- fully unrolled, so the KT index loads and
 // then the KT gathers of a row are all in flight together (the gathers are latency-bound: +18..42 % over run-time K).
-template <bool BYCOL, int KT>
+template <bool BYCOL, int KT, bool PADDED>
 __global__ void __launch_bounds__(256)
     k_tree_ell(i64 nrows, int K, i64 stride, const int *__restrict__ indices, const unsigned char *__restrict__ codes,
                const double *__restrict__ tab_mult, const unsigned char *__restrict__ tab_sel, int ntab,
@@ -117,16 +117,16 @@ __global__ void __launch_bounds__(256)
       c[e] = __ldg(pc + e * stride);
     }
 #pragma unroll
-    for (int e = 0; e < KT; ++e) xv[e] = c[e] != ELL_PAD ? __ldg(x + col[e]) : 0.0;
+    for (int e = 0; e < KT; ++e) xv[e] = (!PADDED || c[e] != ELL_PAD) ? __ldg(x + col[e]) : 0.0;
 #pragma unroll
     for (int e = 0; e < KT; ++e)
-      if (c[e] != ELL_PAD) acc += coded_value(c[e], col[e], s_mult, s_sel, BYCOL, gr, g0, g1, g2) * xv[e];
+      if (!PADDED || c[e] != ELL_PAD) acc += coded_value(c[e], col[e], s_mult, s_sel, BYCOL, gr, g0, g1, g2) * xv[e];
   } else {
 #pragma unroll 4
     for (int e = 0; e < K; ++e) {
       const int col = __ldg(pi);
       const int c = __ldg(pc);
-      if (c != ELL_PAD) acc += coded_value(c, col, s_mult, s_sel, BYCOL, gr, g0, g1, g2) * __ldg(x + col);
+      if (!PADDED || c != ELL_PAD) acc += coded_value(c, col, s_mult, s_sel, BYCOL, gr, g0, g1, g2) * __ldg(x + col);
       pi += stride;
       pc += stride;
     }
@@ -288,8 +288,8 @@ extern "C" int dzb_tree_spmv(int64_t nrows, const void *indptr, int indptr_is64,
 
 extern "C" int dzb_tree_ell_spmv(int64_t nrows, int row_len, int64_t stride, const int32_t *indices, const uint8_t *codes,
                                  const double *tab_mult, const uint8_t *tab_sel, int ntab, const double *g0,
-                                 const double *g1, const double *g2, int geom_by_col, const double *x, double *y,
-                                 void *stream) {
+                                 const double *g1, const double *g2, int geom_by_col, int padded, const double *x,
+                                 double *y, void *stream) {
   if (nrows <= 0) return 0;
   if (ntab < 1 || ntab > 255 || row_len < 0 || stride < nrows) {
     set_error("dzb_tree_ell_spmv: bad table size (1..255; code 255 marks padding), row length or stride");
@@ -297,16 +297,21 @@ extern "C" int dzb_tree_ell_spmv(int64_t nrows, int row_len, int64_t stride, con
   }
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned blocks = (unsigned)((nrows + 255) / 256);
-#define DZB_ELL_LAUNCH(BC, KT) \
-  k_tree_ell<BC, KT><<<blocks, 256, 0, s>>>(nrows, row_len, stride, indices, codes, tab_mult, tab_sel, ntab, g0, g1, g2, x, y)
+#define DZB_ELL_LAUNCH(BC, KT, PD) \
+  k_tree_ell<BC, KT, PD><<<blocks, 256, 0, s>>>(nrows, row_len, stride, indices, codes, tab_mult, tab_sel, ntab, g0, g1, g2, x, y)
   if (geom_by_col) {
-    DZB_ELL_LAUNCH(true, 0);
+    DZB_ELL_LAUNCH(true, 0, true);
+  } else if (padded) {
+    switch (row_len) {
+      case 6: DZB_ELL_LAUNCH(false, 6, true); break;
+      default: DZB_ELL_LAUNCH(false, 0, true); break;
+    }
   } else {
     switch (row_len) {
-      case 6: DZB_ELL_LAUNCH(false, 6); break;
-      case 8: DZB_ELL_LAUNCH(false, 8); break;
-      case 12: DZB_ELL_LAUNCH(false, 12); break;
-      default: DZB_ELL_LAUNCH(false, 0); break;
+      case 6: DZB_ELL_LAUNCH(false, 6, false); break;
+      case 8: DZB_ELL_LAUNCH(false, 8, false); break;
+      case 12: DZB_ELL_LAUNCH(false, 12, false); break;
+      default: DZB_ELL_LAUNCH(false, 0, false); break;
     }
   }
 #undef DZB_ELL_LAUNCH

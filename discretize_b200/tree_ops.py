@@ -59,12 +59,13 @@ class CodedCsr:
         #   "stream" anything else: CSR whose entries a warp stages through shared memory with coalesced loads;
         #   "lpr"    the first kernel (LPR lanes per row straight from global memory), kept for comparison.
         lens = np.diff(indptr)
-        self.row_len = -1
+        self.row_len, self.padded = -1, 0
         if lens.size and self.ntab <= 255:
             kmax, avg_len = int(lens.max()), float(lens.mean())
             # one common length (all cell-rowed operators), or mildly variable rows (edge_curl: 4..6) padded
             if kmax > 0 and (lens.min() == kmax or (kmax <= 12 and kmax <= 1.5 * avg_len)):
                 self.row_len = kmax
+            self.padded = int(lens.min() != kmax)
         self.layout = "ell" if self.row_len > 0 else "lpr"   # measured: "stream" loses to "lpr" (tools/sweep_tree.py)
         avg = self.nnz / max(shape[0], 1)
         self.lpr = 1 if avg <= 7 else 2 if avg <= 16 else 4 if avg <= 40 else 16
@@ -104,8 +105,8 @@ class CodedCsr:
         if self.layout == "ell":
             check(load().dzb_tree_ell_spmv(self.shape[0], self.row_len, self.stride, ptr(self.ell_indices),
                                            ptr(self.ell_codes), ptr(self.tab_mult), ptr(self.tab_sel), self.ntab,
-                                           ptr(g[0]), ptr(g[1]), ptr(g[2]), self.geom_by_col, ptr(x), ptr(out),
-                                           stream_ptr()), "dzb_tree_ell_spmv")
+                                           ptr(g[0]), ptr(g[1]), ptr(g[2]), self.geom_by_col, self.padded, ptr(x),
+                                           ptr(out), stream_ptr()), "dzb_tree_ell_spmv")
             return
         lpr = 0 if self.layout == "stream" else self.lpr
         check(load().dzb_tree_spmv(self.shape[0], ptr(self.indptr), int(self.is64), ptr(self.indices), ptr(self.codes),

@@ -198,11 +198,13 @@ int dzb_points_inside(const double *pts, int64_t npts, const double *lo_host, co
 int dzb_tree_spmv(int64_t nrows, const void *indptr, int indptr_is64, const int32_t *indices, const uint8_t *codes,
                   const double *tab_mult, const uint8_t *tab_sel, int ntab, const double *g0, const double *g1,
                   const double *g2, int geom_by_col, const double *x, double *y, int lanes_per_row, void *stream);
-/* The same operator in ELL layout, for operators whose rows ALL hold row_len entries (on a balanced OcTree: every
- * cell-rowed operator): entry e of row r at indices[e*stride + r] / codes[e*stride + r], stride >= nrows. */
+/* The same operator in ELL layout: entry e of row r at indices[e*stride + r] / codes[e*stride + r], stride >= nrows,
+ * row_len slots per row.  padded == 0: every row holds exactly row_len entries (on a balanced OcTree: every
+ * cell-rowed operator); padded != 0: shorter rows are filled with slots of code 255 (edge_curl: 4..6 entries).
+ * ntab <= 255. */
 int dzb_tree_ell_spmv(int64_t nrows, int row_len, int64_t stride, const int32_t *indices, const uint8_t *codes,
                       const double *tab_mult, const uint8_t *tab_sel, int ntab, const double *g0, const double *g1,
-                      const double *g2, int geom_by_col, const double *x, double *y, void *stream);
+                      const double *g2, int geom_by_col, int padded, const double *x, double *y, void *stream);
 /* y = A x for a CSR matrix with stored float64 values (int32 columns, int32 / int64 indptr): scipy
  * matrices mixed into operator algebra and the full-tensor OcTree mass matrices
  * (operators/inner_products.py:147-272 with tree_ext.pyx:5651-5763 projections). */
