@@ -391,6 +391,17 @@ static void launch_deriv(const TM &m, const Model &md, bool inv_mat, const doubl
     }
     return;
   }
+  if (g_mass_march && !inv_mat && !md.inv) {
+    // no inversions: F(v) dm = v o diag(M(dm)) -- the diagonal mass kernel with dm as the model; and its adjoint
+    if (!transpose) {
+      Model dmodel = md;
+      dmodel.p = x;
+      launch_mass_diag_march<EDGE, 1>(m, dmodel, false, v, y, s);
+    } else {
+      launch_deriv_adj_march<EDGE>(m, md, v, x, y, s);
+    }
+    return;
+  }
   if (!transpose) {
     k_deriv_fwd<EDGE, 0><<<grid_for<DofLoc<EDGE, 0>::LOC>(m), b, 0, s>>>(m, md, inv_mat, v, x, y);
     k_deriv_fwd<EDGE, 1><<<grid_for<DofLoc<EDGE, 1>::LOC>(m), b, 0, s>>>(m, md, inv_mat, v, x, y);

@@ -145,3 +145,70 @@ static void launch_mass_diag_march(const TM &m, const Model &md, bool inv_mat, c
 }
 
 }  // namespace dzb
+
+namespace dzb {
+
+// K7 adjoint without inversions, plane-marching: y[cell] (+ comp * nC) = V_cell * sum over the cell's faces (x 1/2) or
+// edges (x 1/4) of v[f] w[f]  (base/base_tensor_mesh.py:865-988: F(v)^T w = (k Av^T diag(V))^T (v o w));
+// isotropic models sum the three components, anisotropic ones keep them apart.  The forward product without
+// inversions IS the diagonal mass kernel with the model replaced by dm (F(v) dm = v o diag(M(dm))).
+template <bool EDGE, bool ANISO, class CFG>
+__global__ void DZB_MARCH_BOUNDS(CFG)
+    k_deriv_adj_march(TM m, i64 nC, const double *__restrict__ v, const double *__restrict__ w, double *__restrict__ y) {
+  MarchGeom g;
+  const i64 nx = m.nx, ny = m.ny, nz = m.nz;
+  if (!g.template init<CFG>(nx, ny, nz)) return;
+  const i64 i = g.i, j = g.j;
+  const i64 pN = nx + 1, plC = nx * ny;
+  const double axy = __ldg(m.hx + i) * __ldg(m.hy + j);
+  double *o = y + i + nx * j + plC * g.k0;
+  auto pr = [&](i64 q) { return __ldg(v + q) * __ldg(w + q); };
+  if (!EDGE) {
+    const i64 plFx = pN * ny, plFy = nx * (ny + 1);
+    i64 qx = i + pN * j + plFx * g.k0, qy = m.off<LOC_FY>() + i + nx * j + plFy * g.k0,
+        qz = m.off<LOC_FZ>() + i + nx * j + plC * g.k0;
+    double z0 = pr(qz);
+#pragma unroll 4
+    for (i64 k = g.k0; k < g.k1; ++k) {
+      const double z1 = pr(qz + plC);
+      const double sx = 0.5 * pr(qx) + 0.5 * pr(qx + 1), sy = 0.5 * pr(qy) + 0.5 * pr(qy + nx), sz = 0.5 * z0 + 0.5 * z1;
+      const double V = axy * __ldg(m.hz + k);
+      if (ANISO) {
+        o[0] = V * sx; o[nC] = V * sy; o[2 * nC] = V * sz;
+      } else {
+        o[0] = V * ((sx + sy) + sz);
+      }
+      z0 = z1;
+      qx += plFx; qy += plFy; qz += plC; o += plC;
+    }
+  } else {
+    const i64 plN = pN * (ny + 1), plEx = nx * (ny + 1), plEy = pN * ny;
+    i64 qx = i + nx * j + plEx * g.k0, qy = m.off<LOC_EY>() + i + pN * j + plEy * g.k0,
+        qz = m.off<LOC_EZ>() + i + pN * j + plN * g.k0;
+    double sx0 = pr(qx) + pr(qx + nx), sy0 = pr(qy) + pr(qy + 1);
+#pragma unroll 2
+    for (i64 k = g.k0; k < g.k1; ++k) {
+      const double sx1 = pr(qx + plEx) + pr(qx + plEx + nx), sy1 = pr(qy + plEy) + pr(qy + plEy + 1);
+      const double sz = (pr(qz) + pr(qz + 1)) + (pr(qz + pN) + pr(qz + pN + 1));
+      const double V = axy * __ldg(m.hz + k);
+      const double ex = 0.25 * (sx0 + sx1), ey = 0.25 * (sy0 + sy1), ez = 0.25 * sz;
+      if (ANISO) {
+        o[0] = V * ex; o[nC] = V * ey; o[2 * nC] = V * ez;
+      } else {
+        o[0] = V * ((ex + ey) + ez);
+      }
+      sx0 = sx1; sy0 = sy1;
+      qx += plEx; qy += plEy; qz += plN; o += plC;
+    }
+  }
+}
+
+template <bool EDGE>
+static void launch_deriv_adj_march(const TM &m, const Model &md, const double *v, const double *w, double *y, cudaStream_t s) {
+  typedef MarchCfg<8, 16, 0> CFG;
+  const dim3 gc = march_grid<CFG>(m.nx, m.ny, m.nz), b(32, CFG::BY, 1);
+  if (md.kind == DZB_MODEL_ANISO) k_deriv_adj_march<EDGE, true, CFG><<<gc, b, 0, s>>>(m, md.nC, v, w, y);
+  else k_deriv_adj_march<EDGE, false, CFG><<<gc, b, 0, s>>>(m, md.nC, v, w, y);
+}
+
+}  // namespace dzb

@@ -239,11 +239,20 @@ class TreeShard:
         return ShardedTreeOperator(self, name, transposed)
 
 
-class ShardedTreeOperator:
+def _graphed_mixin():
+    from .slab import _GraphedStep
+
+    return _GraphedStep
+
+
+class ShardedTreeOperator(_graphed_mixin()):
     """y_owned = (A x)_owned for a distributed x: ghost exchange + local coded-CSR SpMV (K12).
 
     ``apply(x_owned, out=None)`` takes and returns CUDA float64 tensors holding this rank's owned entries
-    (``TreeShard.scatter`` / ``gather`` convert from / to replicated global vectors)."""
+    (``TreeShard.scatter`` / ``gather`` convert from / to replicated global vectors).  ``step()`` applies the
+    operator to the owned head of ``self.buf`` (write the input there, ``self.x_owned``) into ``self.out``;
+    ``step_graphed()`` replays pack + exchange + SpMV as one CUDA graph, because at a few hundred microseconds
+    per apply the Python enqueue cost of the three pieces is not negligible."""
 
     def __init__(self, shard: TreeShard, name, transposed=False):
         from .operators import cuda_device
@@ -271,8 +280,18 @@ class ShardedTreeOperator:
         self.csr.apply(self.buf, out)
         return out
 
+    @property
+    def x_owned(self):
+        return self.buf[:self.plan.n_owned]
+
+    def step(self, group=None):
+        for r in self.plan.exchange(self.buf, self.send_buf, group):
+            r.wait()
+        self.csr.apply(self.buf, self.out)
+        return self.out
+
     def bytes_per_apply(self):
-        return self.csr.bytes_per_apply() + 16 * self.plan.n_owned + 16 * int(self.plan.send_off[-1])
+        return self.csr.bytes_per_apply() + 16 * int(self.plan.send_off[-1])
 
     @property
     def T(self):

@@ -18,6 +18,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--base", type=int, default=128)
 ap.add_argument("--pts", type=int, default=2000)
 ap.add_argument("--time", action="store_true")
+ap.add_argument("--ops", default="face_divergence,edge_curl,nodal_gradient,average_face_to_cell,average_edge_to_cell,average_node_to_cell")
+ap.add_argument("--no-transposes", action="store_true")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -28,10 +30,9 @@ pts = np.random.default_rng(2024).random((a.pts, 3)) * 0.6 + 0.2
 m.refine_points(pts, -1, [2, 2, 2], finalize=True)
 shard = TreeShard(m, rank, world)
 ok = True
-for name in ("face_divergence", "edge_curl", "nodal_gradient", "average_face_to_cell", "average_edge_to_cell",
-             "average_node_to_cell"):
+for name in a.ops.split(","):
     rk, ck = OPERATOR_KINDS[name]
-    for tr in (False, True):
+    for tr in ((False,) if a.no_transposes else (False, True)):
         kin, kout = (rk, ck) if tr else (ck, rk)
         t0 = time.time()
         op = shard.operator(name, tr)
@@ -60,6 +61,20 @@ for name in ("face_divergence", "edge_curl", "nodal_gradient", "average_face_to_
             torch.cuda.synchronize()
             t = torch.tensor([e0.elapsed_time(e1) / 20], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            for _ in range(3):
+                op.step_graphed()
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(50):
+                op.step_graphed()
+            e1.record()
+            torch.cuda.synchronize()
+            tg = torch.tensor([e0.elapsed_time(e1) / 50], device=dev)
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            err_g = float((shard.gather(kout, op.out) - ref).abs().max() / ref.abs().max())
+            rec.update(ms_sharded_graph_max=float(tg), graph=op._graph is not None, rel_err_graph=err_g)
+            ok = ok and err_g <= 1e-12
             e0.record()
             for _ in range(20):
                 whole.apply_device(x, out=ref)

@@ -46,6 +46,11 @@ def main():
             ("Me(iso)", mesh.get_edge_inner_product(sig), 8.0 * (2 * mesh.nE + mesh.nC)),
             ("Me(aniso)", mesh.get_edge_inner_product(sig3), 8.0 * (2 * mesh.nE + 3 * mesh.nC)),
             ("Mf(iso)^-1", mesh.get_face_inner_product(sig, invert_model=True, invert_matrix=True), 8.0 * (2 * mesh.nF + mesh.nC))]
+    vF = torch.randn(mesh.nF, dtype=torch.float64, device=dev)
+    dMf = mesh.get_face_inner_product_deriv(sig)(vF)
+    dMe3 = mesh.get_edge_inner_product_deriv(sig3)(torch.randn(mesh.nE, dtype=torch.float64, device=dev))
+    mass += [("dMf(iso)", dMf, 8.0 * (2 * mesh.nF + mesh.nC)), ("dMf(iso).T", dMf.T, 8.0 * (2 * mesh.nF + mesh.nC)),
+             ("dMe(aniso)", dMe3, 8.0 * (2 * mesh.nE + 3 * mesh.nC)), ("dMe(aniso).T", dMe3.T, 8.0 * (2 * mesh.nE + 3 * mesh.nC))]
     big = torch.randn(mesh.nE, dtype=torch.float64, device=dev)
     out = torch.empty(mesh.nE, dtype=torch.float64, device=dev)
     ref = {}
@@ -71,7 +76,7 @@ def main():
             if err > 1e-12:
                 row[name] += f" ERR {err:.1e}"
         print(json.dumps(row), flush=True)
-    for mm in (0, 1, 2, 3, 4, 5, 6, 7):
+    for mm in (0, 1):
         lib.dzb_tune_mass(mm)
         row = {"mass_march": mm}
         for name, op, nbytes in mass:
