@@ -34,6 +34,16 @@ def timeit(fn, reps=20, warm=3):
     return e0.elapsed_time(e1) / reps
 
 
+def cpu_ms_per_dof(A, reps=3):
+    """The reference's CPU apply path: scipy csr_matvec (one thread) on the materialised matrix; ns per output row."""
+    x = np.random.default_rng(0).standard_normal(A.shape[1])
+    A @ x
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        A @ x
+    return (time.perf_counter() - t0) / reps * 1e9 / max(A.shape[0], 1)
+
+
 def report(rows, name, ndof, nbytes, ms, extra=None):
     r = {"op": name, "dofs": int(ndof), "ms": ms, "gdof_s": ndof / ms / 1e6, "alg_gb_s": nbytes / ms / 1e6,
          "frac_of_measured_hbm": nbytes / ms / 1e6 / PEAK}
@@ -54,21 +64,60 @@ def config1(rows):
     report(rows, "cfg1 64^3 face_divergence @ u (L2 resident)", mesh.nC, 8 * (mesh.nF + mesh.nC), timeit(lambda: D.apply_device(u, out=oD), 200))
     report(rows, "cfg1 64^3 edge_curl @ e (L2 resident)", mesh.nF, 8 * (mesh.nE + mesh.nF), timeit(lambda: C.apply_device(e, out=oC), 200))
     report(rows, "cfg1 64^3 Mf(sigma) @ u (L2 resident)", mesh.nF, 8 * (2 * mesh.nF + mesh.nC), timeit(lambda: Mf.apply_device(u, out=oM), 200))
-    # the same elementary kernels out of cache
+    # the same kernels out of cache: every elementary operator, mass matrix and model derivative at 512^3
     mesh = dz.TensorMesh([512, 512, 512])
-    u = torch.randn(mesh.nF, dtype=torch.float64, device=dev)
-    oD = torch.empty(mesh.nC, dtype=torch.float64, device=dev)
-    D = mesh.face_divergence
-    report(rows, "512^3 face_divergence @ u", mesh.nC, 8 * (mesh.nF + mesh.nC), timeit(lambda: D.apply_device(u, out=oD), 10))
-    del u, oD
-    phi = torch.randn(mesh.nN, dtype=torch.float64, device=dev)
-    oG = torch.empty(mesh.nE, dtype=torch.float64, device=dev)
-    G = mesh.nodal_gradient
-    report(rows, "512^3 nodal_gradient @ phi", mesh.nE, 8 * (mesh.nE + mesh.nN), timeit(lambda: G.apply_device(phi, out=oG), 10))
-    del phi
-    oC = torch.empty(mesh.nF, dtype=torch.float64, device=dev)
-    C = mesh.edge_curl
-    report(rows, "512^3 edge_curl @ e", mesh.nF, 8 * (mesh.nE + mesh.nF), timeit(lambda: C.apply_device(oG, out=oC), 10))
+    big = torch.randn(mesh.nE, dtype=torch.float64, device=dev)
+    out = torch.empty(mesh.nE, dtype=torch.float64, device=dev)
+    sig = torch.rand(mesh.nC, dtype=torch.float64, device=dev) + 0.5
+    sig3 = torch.rand((mesh.nC, 3), dtype=torch.float64, device=dev) + 0.5
+    D, G, C = mesh.face_divergence, mesh.nodal_gradient, mesh.edge_curl
+    dMf = mesh.get_face_inner_product_deriv(sig)(big[:mesh.nF].clone())
+    dMe3 = mesh.get_edge_inner_product_deriv(sig3)(big.clone())
+    nF, nE, nC = mesh.nF, mesh.nE, mesh.nC
+    ops = [("face_divergence @ u", D, None), ("face_divergence.T @ c", D.T, None), ("nodal_gradient @ phi", G, None),
+           ("nodal_gradient.T @ e", G.T, None), ("edge_curl @ e", C, None), ("edge_curl.T @ u", C.T, None),
+           ("average_face_to_cell @ u", mesh.average_face_to_cell, None),
+           ("average_edge_to_cell @ e", mesh.average_edge_to_cell, None),
+           ("average_node_to_cell @ phi", mesh.average_node_to_cell, None),
+           ("average_face_to_cell_vector.T @ c3 (generic kernel)", mesh.average_face_to_cell_vector.T, None),
+           ("average_cell_to_face @ c (generic kernel)", mesh.average_cell_to_face, None),
+           ("cell_gradient @ c (generic kernel)", mesh.cell_gradient, None),
+           ("Mf(sigma iso) @ u", mesh.get_face_inner_product(sig), 8.0 * (2 * nF + nC)),
+           ("Me(sigma iso) @ e", mesh.get_edge_inner_product(sig), 8.0 * (2 * nE + nC)),
+           ("Me(sigma aniso) @ e", mesh.get_edge_inner_product(sig3), 8.0 * (2 * nE + 3 * nC)),
+           ("Mf(1/sigma)^-1 @ u (invert_model, invert_matrix)",
+            mesh.get_face_inner_product(sig, invert_model=True, invert_matrix=True), 8.0 * (2 * nF + nC)),
+           ("dMf(sigma iso)(v) @ dm", dMf, 8.0 * (2 * nF + nC)), ("dMf(sigma iso)(v).T @ w", dMf.T, 8.0 * (2 * nF + nC)),
+           ("dMe(sigma aniso)(v) @ dm", dMe3, 8.0 * (2 * nE + 3 * nC)),
+           ("dMe(sigma aniso)(v).T @ w", dMe3.T, 8.0 * (2 * nE + 3 * nC))]
+    # CPU baseline beside every line: the same operator materialised at 96^3 (.tocsr() == the reference's matrix),
+    # applied by scipy csr_matvec on one host core, scaled per output row
+    small = dz.TensorMesh([96, 96, 96])
+    ssig = np.random.default_rng(1).random(small.nC) + 0.5
+    ssig3 = np.random.default_rng(2).random((small.nC, 3)) + 0.5
+    sv = np.random.default_rng(3).standard_normal(small.nE)
+    small_ops = {"face_divergence @ u": small.face_divergence, "face_divergence.T @ c": small.face_divergence.T,
+                 "nodal_gradient @ phi": small.nodal_gradient, "nodal_gradient.T @ e": small.nodal_gradient.T,
+                 "edge_curl @ e": small.edge_curl, "edge_curl.T @ u": small.edge_curl.T,
+                 "average_face_to_cell @ u": small.average_face_to_cell,
+                 "average_edge_to_cell @ e": small.average_edge_to_cell,
+                 "average_node_to_cell @ phi": small.average_node_to_cell,
+                 "average_cell_to_face @ c (generic kernel)": small.average_cell_to_face,
+                 "cell_gradient @ c (generic kernel)": small.cell_gradient,
+                 "Mf(sigma iso) @ u": small.get_face_inner_product(ssig),
+                 "Me(sigma iso) @ e": small.get_edge_inner_product(ssig),
+                 "Me(sigma aniso) @ e": small.get_edge_inner_product(ssig3),
+                 "dMf(sigma iso)(v) @ dm": small.get_face_inner_product_deriv(ssig)(sv[:small.nF])}
+    for name, op, nbytes in ops:
+        x, y = big[:op.shape[1]], out[:op.shape[0]]
+        ms = timeit(lambda: op.apply_device(x, out=y), 10)
+        extra = None
+        if name in small_ops and not os.environ.get("DZB_NO_CPU"):
+            ns = cpu_ms_per_dof(small_ops[name].tocsr())
+            cpu_gdofs = 1.0 / ns
+            extra = {"cpu_scipy_gdof_s": cpu_gdofs, "cpu_sample": "96^3, scipy csr_matvec, 1 core",
+                     "gpu_over_cpu": op.shape[0] / ms / 1e6 / cpu_gdofs}
+        report(rows, "512^3 " + name, op.shape[0], nbytes if nbytes else 8.0 * (op.shape[0] + op.shape[1]), ms, extra)
 
 
 def config3(rows, npts):
@@ -91,8 +140,12 @@ def config3(rows, npts):
         t_op = time.time() - t0
         csr = op._csr(False)
         ms = timeit(lambda: op.apply_device(x, out=out), 20)
-        report(rows, f"cfg3 OcTree {m.nC} cells {name}", op.shape[0], op.bytes_per_apply(), ms,
-               {"nnz": csr.nnz, "lanes_per_row": csr.lpr, "host_assembly_s": t_op})
+        extra = {"nnz": csr.nnz, "layout": csr.layout, "host_assembly_s": t_op}
+        if not os.environ.get("DZB_NO_CPU"):
+            ns = cpu_ms_per_dof(m._host_matrix(name))
+            extra.update(cpu_scipy_gdof_s=1.0 / ns, cpu_sample="the same CSR, scipy csr_matvec, 1 core, full size",
+                         cpu_ms=ns * op.shape[0] * 1e-6, gpu_over_cpu=ns * op.shape[0] * 1e-6 / ms)
+        report(rows, f"cfg3 OcTree {m.nC} cells {name}", op.shape[0], op.bytes_per_apply(), ms, extra)
         m._cache.pop("P_" + name, None); m._cache.pop("H_" + name, None); m._cache.pop("OP_" + name, None)
         del op, x, out, csr
 
@@ -115,8 +168,13 @@ def config4(rows, npts):
         v = torch.randn(Q.shape[1], dtype=torch.float64, device=dev)
         out = torch.empty(npts, dtype=torch.float64, device=dev)
         ms_apply = timeit(lambda: Q.apply_device(v, out=out), 5, 1)
-        report(rows, f"cfg4 interp apply Q@v {loc}", npts, 136.0 * npts + 8.0 * 32 * npts, ms_apply,
-               {"unit": "points", "bytes_note": "tables 128 B/pt + 8 B out + 8 gathers x 32 B sectors"})
+        extra = {"unit": "points", "bytes_note": "tables 96 B/pt + 8 B out + 8 gathers x 32 B sectors"}
+        if not os.environ.get("DZB_NO_CPU") and loc == "CC":
+            Qs = mesh.get_interpolation_matrix(pts[:1_000_000], loc).tocsr()
+            ns = cpu_ms_per_dof(Qs)
+            extra.update(cpu_scipy_gpts_s=1.0 / ns, cpu_sample="1e6 of the points, scipy csr_matvec on Q.tocsr(), 1 core",
+                         gpu_over_cpu=npts / ms_apply / 1e6 * ns)
+        report(rows, f"cfg4 interp apply Q@v {loc}", npts, 104.0 * npts + 8.0 * 32 * npts, ms_apply, extra)
         Qf = make_interpolation_operator(mesh, pts, loc, store=False)
         ms_fused = timeit(lambda: Qf.apply_device(v, out=out), 5, 1)
         report(rows, f"cfg4 interp fused locate+apply {loc}", npts, 32.0 * npts + 8.0 * 32 * npts, ms_fused,
@@ -134,7 +192,27 @@ def config5(rows, n):
     A = C.T @ mesh.get_face_inner_product(mui) @ C + mesh.get_edge_inner_product(sig)
     out = torch.empty(mesh.nE, dtype=torch.float64, device=dev)
     ms = timeit(lambda: A.apply_device(e, out=out), 5, 2)
-    report(rows, f"cfg5 {n}^3 Maxwell C^T Mf C + Me fused ({type(A).__name__})", mesh.nE, 8.0 * (2 * mesh.nE + 2 * mesh.nC), ms)
+    extra = None
+    if not os.environ.get("DZB_NO_CPU"):
+        # the reference cannot assemble this operator at 1024^3 (C alone is ~206 GB): assembled at 64^3, scaled per row
+        sm = dz.TensorMesh([64, 64, 64])
+        rng = np.random.default_rng(5)
+        Cs = sm.edge_curl.tocsr()
+        As = (Cs.T @ sm.get_face_inner_product(np.exp(rng.standard_normal(sm.nC))).tocsr() @ Cs
+              + sm.get_edge_inner_product(np.exp(rng.standard_normal(sm.nC))).tocsr()).tocsr()
+        ns = cpu_ms_per_dof(As)
+        extra = {"cpu_scipy_gdof_s": 1.0 / ns, "cpu_sample": "64^3, assembled C^T Mf C + Me, scipy csr_matvec, 1 core",
+                 "gpu_over_cpu": mesh.nE / ms / 1e6 * ns}
+    report(rows, f"cfg5 {n}^3 Maxwell C^T Mf C + Me fused ({type(A).__name__})", mesh.nE, 8.0 * (2 * mesh.nE + 2 * mesh.nC), ms, extra)
+    # the 512^3 DC operator of config 2 (the bench.py workload) beside it
+    if n == 1024:
+        return
+    phi = torch.randn(mesh.nN, dtype=torch.float64, device=dev)
+    G = mesh.nodal_gradient
+    Adc = G.T @ mesh.get_edge_inner_product(sig) @ G
+    o2 = torch.empty(mesh.nN, dtype=torch.float64, device=dev)
+    ms = timeit(lambda: Adc.apply_device(phi, out=o2), 10, 3)
+    report(rows, f"cfg2 {n}^3 DC G^T Me G fused ({type(Adc).__name__})", mesh.nN, 8.0 * (2 * mesh.nN + mesh.nC), ms)
 
 
 if __name__ == "__main__":
