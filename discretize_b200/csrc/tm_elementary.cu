@@ -13,6 +13,7 @@ int g_apply_cfg = 2;
 static int g_march_cfg = -1;
 
 static bool try_march(int op, int transpose, int flags, const TM &m, const double *x, double *y, cudaStream_t s) {
+  if (g_march_cfg != 0 && launch_c2f_march(op, transpose, flags, m, x, y, s)) return true;
   if (flags != 0) return false;
   switch (g_march_cfg) {
     case 0: return false;

@@ -12,6 +12,7 @@
 // reference's  (-rh) x0 + rh x1  and well inside the 1e-12 parity tolerance.
 #pragma once
 #include "tm_common.cuh"
+#include "tm_rows.cuh"
 
 namespace dzb {
 
@@ -254,6 +255,66 @@ __global__ void DZB_MARCH_BOUNDS(CFG) k_curlT_march(TM m, const double *__restri
   DZB_MARCH_LOOP(step)
 }
 
+// ---- the cell -> face family: face_divergence^T, (stencil_)cell_gradient with boundary conditions,
+// average_cell_to_face (operators/differential_operators.py:41-82, 1413-1595, 2789-2828) -------------------------
+// Every one of them is  face(p) = a_lo(p) * cell(p - 1) + a_hi(p) * cell(p)  along the face normal, with weights that
+// depend on the position p along that axis only.  The x / y weights are per-thread constants, the z weights are
+// computed once per plane; the walk is the one of k_divT_march.
+enum C2FKind { C2F_DIVT = 0, C2F_CELL_GRAD = 1, C2F_AVE = 2 };
+
+// weights at node position p of an axis with n cells; flags: GcFlags of that axis (C2F_CELL_GRAD only)
+template <int KIND>
+__device__ __forceinline__ void c2f_weights(i64 p, i64 n, const double *__restrict__ h, const double *__restrict__ rh,
+                                            int flags, double &a_lo, double &a_hi) {
+  const bool lo = p >= 1, hi = p < n;
+  if (KIND == C2F_DIVT) {
+    a_lo = lo ? __ldg(rh + p - 1) : 0.0;
+    a_hi = hi ? -__ldg(rh + p) : 0.0;
+  } else if (KIND == C2F_AVE) {
+    a_lo = lo ? (hi ? 0.5 : 1.0) : 0.0;
+    a_hi = hi ? (lo ? 0.5 : 1.0) : 0.0;
+  } else {
+    bool keep;
+    a_lo = lo ? gc_value(p, p - 1, n, h, rh, flags, &keep) : 0.0;
+    a_hi = hi ? gc_value(p, p, n, h, rh, flags, &keep) : 0.0;
+  }
+}
+
+template <int KIND, class CFG>
+__global__ void DZB_MARCH_BOUNDS(CFG) k_c2f_march(TM m, int fx, int fy, int fz, const double *__restrict__ c, double *__restrict__ u) {
+  MarchGeom g;
+  const i64 nx = m.nx, ny = m.ny, nz = m.nz;
+  if (!g.template init<CFG>(nx + 1, ny + 1, nz + 1)) return;
+  const i64 i = g.i, j = g.j;
+  const bool hx = i < nx, hy = j < ny, lx = i >= 1, ly = j >= 1;
+  double ax_lo, ax_hi, ay_lo, ay_hi;
+  c2f_weights<KIND>(i, nx, m.hx, m.rhx, fx, ax_lo, ax_hi);
+  c2f_weights<KIND>(j, ny, m.hy, m.rhy, fy, ay_lo, ay_hi);
+  const i64 pFx = nx + 1, plFx = pFx * ny, plFy = nx * (ny + 1), plC = nx * ny;
+  const double *pc = c + i + nx * j + plC * g.k0;          // cell (i,j,k); only dereferenced where it exists
+  double *px = u + i + pFx * j + plFx * g.k0;
+  double *py = u + m.off<LOC_FY>() + i + nx * j + plFy * g.k0;
+  double *pz = u + m.off<LOC_FZ>() + i + nx * j + plC * g.k0;
+  const bool in_xy = hx && hy, lxy = lx && hy, lyx = ly && hx;
+  double cm = (g.k0 >= 1 && in_xy) ? __ldg(pc - plC) : 0.0;   // cell (i,j,k-1)
+  auto step = [&](auto hz_tag, i64 k) {
+    constexpr bool HZ = decltype(hz_tag)::value;
+    double az_lo, az_hi;
+    c2f_weights<KIND>(k, nz, m.hz, m.rhz, fz, az_lo, az_hi);
+    double c0 = 0.0;
+    if (HZ) {
+      c0 = ldp(pc, in_xy);
+      const double cxm = ldp(pc - 1, lxy), cym = ldp(pc - nx, lyx);
+      if (hy) *px = ax_lo * cxm + ax_hi * c0;     // x-face (i,j,k), j < ny   (c0 = 0 where i == nx)
+      if (hx) *py = ay_lo * cym + ay_hi * c0;     // y-face (i,j,k), i < nx   (c0 = 0 where j == ny)
+    }
+    if (in_xy) *pz = az_lo * cm + az_hi * c0;     // z-face (i,j,k), k <= nz
+    cm = c0;
+    pc += plC; px += plFx; py += plFy; pz += plC;
+  };
+  DZB_MARCH_LOOP(step)
+}
+
 // ---- averages to cell centres ------------------------------------------------------------------------------------
 // average_face_to_cell: (1/3) (1/2) (the two faces per direction) -- the same walk as the divergence
 template <class CFG>
@@ -366,6 +427,22 @@ static bool launch_march_tuned(int op, int transpose, const TM &m, const double 
   else if (op == DZB_OP_AVE_E2CC && !transpose) k_aveE2CC_march<Wide><<<march_grid<Wide>(m.nx, m.ny, m.nz), bW, 0, s>>>(m, x, y);
   else if (op == DZB_OP_AVE_N2CC && !transpose) k_aveN2CC_march<Wide><<<march_grid<Wide>(m.nx, m.ny, m.nz), bW, 0, s>>>(m, x, y);
   else return false;
+  return true;
+}
+
+// cell -> face family with run-time flags (cell-gradient boundary conditions): returns true when launched
+static bool launch_c2f_march(int op, int transpose, int flags, const TM &m, const double *x, double *y, cudaStream_t s) {
+  typedef MarchCfg<4, 32, 0> CFG;
+  if (transpose) return false;
+  const dim3 gn = march_grid<CFG>(m.nx + 1, m.ny + 1, m.nz + 1), b(32, CFG::BY, 1);
+  if (op == DZB_OP_AVE_CC2F) {
+    k_c2f_march<C2F_AVE, CFG><<<gn, b, 0, s>>>(m, 0, 0, 0, x, y);
+  } else if (op == DZB_OP_CELL_GRAD) {
+    const int sc = (flags & DZB_CG_SCALED) ? GC_SCALED : 0;
+    k_c2f_march<C2F_CELL_GRAD, CFG><<<gn, b, 0, s>>>(m, (flags & 3) | sc, ((flags >> 2) & 3) | sc, ((flags >> 4) & 3) | sc, x, y);
+  } else {
+    return false;
+  }
   return true;
 }
 

@@ -47,6 +47,29 @@ def test_cell_gradient_boundary_conditions(mesh_name, tag):
     _check(mesh.cell_gradient, T.cell_gradient(grid, bc))
 
 
+@pytest.mark.parametrize("march", [0, -1])
+def test_cell_to_face_family_marching_and_generic(march):
+    """average_cell_to_face and (stencil_)cell_gradient have a plane-marching kernel and the generic row kernel."""
+    import ctypes
+
+    from discretize_b200._lib import LIB_PATH
+
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.dzb_tune_march(march)
+    try:
+        for mesh_name in ("wide", "thin"):
+            mesh, grid = make_pair(mesh_name)
+            rng = np.random.default_rng(5)
+            x = rng.standard_normal(mesh.nC)
+            assert_close_vec(mesh.average_cell_to_face @ x, T.average_cell_to_face(grid) @ x)
+            for bc in CELL_GRADIENT_BCS.values():
+                mesh.set_cell_gradient_BC(copy.deepcopy(bc))
+                assert_close_vec(mesh.cell_gradient @ x, T.cell_gradient(grid, bc) @ x)
+                assert_close_vec(mesh.stencil_cell_gradient @ x, T.stencil_cell_gradient(grid, bc) @ x)
+    finally:
+        lib.dzb_tune_march(-1)
+
+
 def test_n2_vs_reference_fixture():
     import discretize_b200 as dz
 

@@ -80,8 +80,8 @@ def config1(rows):
            ("average_edge_to_cell @ e", mesh.average_edge_to_cell, None),
            ("average_node_to_cell @ phi", mesh.average_node_to_cell, None),
            ("average_face_to_cell_vector.T @ c3 (generic kernel)", mesh.average_face_to_cell_vector.T, None),
-           ("average_cell_to_face @ c (generic kernel)", mesh.average_cell_to_face, None),
-           ("cell_gradient @ c (generic kernel)", mesh.cell_gradient, None),
+           ("average_cell_to_face @ c", mesh.average_cell_to_face, None),
+           ("cell_gradient @ c (Neumann)", mesh.cell_gradient, None),
            ("Mf(sigma iso) @ u", mesh.get_face_inner_product(sig), 8.0 * (2 * nF + nC)),
            ("Me(sigma iso) @ e", mesh.get_edge_inner_product(sig), 8.0 * (2 * nE + nC)),
            ("Me(sigma aniso) @ e", mesh.get_edge_inner_product(sig3), 8.0 * (2 * nE + 3 * nC)),
@@ -102,8 +102,8 @@ def config1(rows):
                  "average_face_to_cell @ u": small.average_face_to_cell,
                  "average_edge_to_cell @ e": small.average_edge_to_cell,
                  "average_node_to_cell @ phi": small.average_node_to_cell,
-                 "average_cell_to_face @ c (generic kernel)": small.average_cell_to_face,
-                 "cell_gradient @ c (generic kernel)": small.cell_gradient,
+                 "average_cell_to_face @ c": small.average_cell_to_face,
+                 "cell_gradient @ c (Neumann)": small.cell_gradient,
                  "Mf(sigma iso) @ u": small.get_face_inner_product(ssig),
                  "Me(sigma iso) @ e": small.get_edge_inner_product(ssig),
                  "Me(sigma aniso) @ e": small.get_edge_inner_product(ssig3),

@@ -72,7 +72,7 @@ def main():
         m = dz.TreeMesh([512, 512, 512], diagonal_balance=True)
         pts = np.random.default_rng(2024).random((a.tree_pts, 3)) * 0.6 + 0.2
         m.refine_points(pts, -1, [2, 2, 2], finalize=True)
-        for name in ("face_divergence", "edge_curl", "average_edge_to_cell", "nodal_gradient"):
+        for name in ("face_divergence", "edge_curl", "average_node_to_cell", "nodal_gradient"):
             op = getattr(m, name)
             twice(op, torch.randn(op.shape[1], dtype=torch.float64, device=dev))
             m._cache.pop("P_" + name, None); m._cache.pop("H_" + name, None); m._cache.pop("OP_" + name, None)
