@@ -467,6 +467,53 @@ class TreeMesh:
             M = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(offEn[3], t.nodes.n_total))
             geoms.append(g)
             parts.append((1, M @ self._deflate_nodes()))
+        elif name == "average_node_to_edge":  # tree_ext.pyx:4765-4918: 1/2 at the two end nodes, deflate nodes
+            nE = [e.n for e in t.edges]
+            offEn = np.r_[0, np.cumsum(nE)]
+            rows, cols = [], []
+            for d in range(3):
+                e = t.edges[d]
+                nh = np.nonzero(~e.hanging)[0]
+                r = offEn[d] + e.index[nh]
+                for s in (-1, 1):
+                    q = e.loc[nh] + s * e.half[nh, None] * unit[d]
+                    rows.append(r); cols.append(t.nodes.index[np.searchsorted(t.nodes.keys, key3(q[:, 0], q[:, 1], q[:, 2]))])
+            rows, cols = np.concatenate(rows), np.concatenate(cols)
+            M = sp.csr_matrix((np.full(rows.size, 0.5), (rows, cols)), shape=(offEn[3], t.nodes.n_total))
+            parts.append((0, M @ self._deflate_nodes()))
+        elif name == "average_node_to_face":  # tree_ext.pyx:4920-5078: 1/4 at the four corner nodes, deflate nodes
+            nF = [f.n for f in t.faces]
+            offFn = np.r_[0, np.cumsum(nF)]
+            rows, cols = [], []
+            for d in range(3):
+                f = t.faces[d]
+                nh = np.nonzero(~f.hanging)[0]
+                a1, a2 = (d + 1) % 3, (d + 2) % 3
+                r = offFn[d] + f.index[nh]
+                for s1 in (-1, 1):
+                    for s2 in (-1, 1):
+                        q = f.loc[nh] + s1 * f.half[nh, None] * unit[a1] + s2 * f.half[nh, None] * unit[a2]
+                        rows.append(r); cols.append(t.nodes.index[np.searchsorted(t.nodes.keys, key3(q[:, 0], q[:, 1], q[:, 2]))])
+            rows, cols = np.concatenate(rows), np.concatenate(cols)
+            M = sp.csr_matrix((np.full(rows.size, 0.25), (rows, cols)), shape=(offFn[3], t.nodes.n_total))
+            parts.append((0, M @ self._deflate_nodes()))
+        elif name == "average_edge_to_face":  # tree_ext.pyx:4350-4440: 1/4 of the four bounding edges, deflate edges
+            nF = [f.n for f in t.faces]
+            offFn = np.r_[0, np.cumsum(nF)]
+            rows, cols = [], []
+            for d in range(3):
+                f = t.faces[d]
+                nh = np.nonzero(~f.hanging)[0]
+                a1, a2 = (d + 1) % 3, (d + 2) % 3
+                r = offFn[d] + f.index[nh]
+                for de, dt in ((a2, a1), (a1, a2)):      # edges along `de`, displaced along `dt`
+                    e = t.edges[de]
+                    for s in (-1, 1):
+                        q = f.loc[nh] + s * f.half[nh, None] * unit[dt]
+                        rows.append(r); cols.append(offE[de] + e.index[np.searchsorted(e.keys, key3(q[:, 0], q[:, 1], q[:, 2]))])
+            rows, cols = np.concatenate(rows), np.concatenate(cols)
+            M = sp.csr_matrix((np.full(rows.size, 0.25), (rows, cols)), shape=(offFn[3], offE[3]))
+            parts.append((0, M @ self._deflate_edges()))
         elif name in ("average_face_to_cell", "average_face_to_cell_vector") or name.startswith("average_face_"):
             parts.append((0, self._host_average(name, t.faces, t.cell_faces, offF, self._deflate_faces(), 0.5)))
         elif name in ("average_edge_to_cell", "average_edge_to_cell_vector") or name.startswith("average_edge_"):
@@ -548,6 +595,9 @@ class TreeMesh:
     average_edge_y_to_cell = property(lambda self: self._operator("average_edge_y_to_cell"))
     average_edge_z_to_cell = property(lambda self: self._operator("average_edge_z_to_cell"))
     average_node_to_cell = property(lambda self: self._operator("average_node_to_cell"))
+    average_node_to_edge = property(lambda self: self._operator("average_node_to_edge"))
+    average_node_to_face = property(lambda self: self._operator("average_node_to_face"))
+    average_edge_to_face = property(lambda self: self._operator("average_edge_to_face"))
 
     # ---- mass matrices (shared _fastInnerProduct: base/base_tensor_mesh.py:792-863) -----------------------------
     def get_face_inner_product(self, model=None, invert_model=False, invert_matrix=False, do_fast=True, **kwargs):

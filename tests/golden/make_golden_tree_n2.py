@@ -1,0 +1,43 @@
+"""Generates tests/golden/tree_n2_small.npz (OcTree node->edge, node->face, edge->face averages) from the UNMODIFIED
+reference, on the two trees of tree_small.npz (rebuilt from their stored refinement points)."""
+import os
+import sys
+import warnings
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.refload import load_reference  # noqa: E402
+
+TREE_N2_OPS = ["average_node_to_edge", "average_node_to_face", "average_edge_to_face"]
+
+
+def main():
+    warnings.simplefilter("ignore")
+    ref = load_reference()
+    assert ref is not None
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tree_small.npz"))
+    out = {}
+    for tag in ("a", "b"):
+        h = [g[f"{tag}_h{a}"] for a in "xyz"]
+        mesh = ref.TreeMesh(h, origin=g[f"{tag}_origin"], diagonal_balance=bool(g[f"{tag}_db"]))
+        mesh.refine_points(g[f"{tag}_pts"], -1, [1, 1], finalize=True)
+        idx, lev = mesh.__getstate__()
+        assert np.array_equal(idx, g[f"{tag}_state_indexes"]) and np.array_equal(lev, g[f"{tag}_state_levels"])
+        for name in TREE_N2_OPS:
+            m = sp.csr_matrix(getattr(mesh, name)).copy()
+            m.sum_duplicates()
+            m.sort_indices()
+            out[f"{tag}_{name}__indptr"] = m.indptr.astype(np.int64)
+            out[f"{tag}_{name}__indices"] = m.indices.astype(np.int64)
+            out[f"{tag}_{name}__data"] = m.data
+            out[f"{tag}_{name}__shape"] = np.array(m.shape, dtype=np.int64)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tree_n2_small.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

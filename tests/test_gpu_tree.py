@@ -172,3 +172,19 @@ def test_tree_spmv_layouts_agree(gold, name):
                 out = torch.empty(csr.shape[0], dtype=torch.float64, device="cuda")
                 csr.apply(torch.from_numpy(vec).cuda(), out)
                 assert_close_vec(out.cpu().numpy(), r)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_tree_node_and_edge_to_face_averages(gold, tag):
+    from tests.golden.make_golden_tree_n2 import TREE_N2_OPS
+
+    g2 = load_golden("tree_n2_small.npz")
+    m = _mesh_from_fixture(gold, tag, "refine")
+    rng = np.random.default_rng(14)
+    for name in TREE_N2_OPS:
+        ref = golden_matrix(g2, f"{tag}_{name}")
+        op = getattr(m, name)
+        x, y = rng.standard_normal(ref.shape[1]), rng.standard_normal(ref.shape[0])
+        assert_close_vec(op @ x, ref @ x)
+        assert_close_vec(op.T @ y, ref.T @ y)
+        assert_same_matrix(op.tocsr(), ref)

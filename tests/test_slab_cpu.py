@@ -135,3 +135,15 @@ def test_edge_halo_exchange_gloo():
         assert p.exitcode == 0
     results = dict(q.get(timeout=10) for _ in range(world))
     assert all(results[r] for r in range(world)), results
+
+
+def test_interpolation_point_ranges_partition_all_points():
+    from discretize_b200.interp_shard import point_range
+
+    for npts in (0, 1, 7, 100, 10**8 + 3):
+        for world in (1, 2, 3, 8):
+            cuts = [point_range(npts, world, r) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == npts
+            assert all(a[1] == b[0] for a, b in zip(cuts[:-1], cuts[1:]))
+            sizes = [b - a for a, b in cuts]
+            assert max(sizes) - min(sizes) <= 1

@@ -96,3 +96,16 @@ def test_random_trees_against_reference(reference, db):
         assert (r.nhN, r.nhEx, r.nhFz, r.nN, r.nE, r.nF) == (n.nhN, n.nhEx, n.nhFz, n.nN, n.nE, n.nF)
         for name in ("face_divergence", "edge_curl", "nodal_gradient", "average_edge_to_cell", "average_node_to_cell"):
             assert_same_matrix(n._host_matrix(name), getattr(r, name), 1e-13)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_tree_node_and_edge_to_face_averages_match_reference_fixture(gold, tag):
+    """average_node_to_edge / average_node_to_face / average_edge_to_face (tree_ext.pyx:4350-5078)."""
+    from tests.golden.make_golden_tree_n2 import TREE_N2_OPS
+
+    g2 = load_golden("tree_n2_small.npz")
+    m = _mesh_from_fixture(gold, tag, "refine")
+    for name in TREE_N2_OPS:
+        A = m._host_matrix(name)
+        assert_same_matrix(A, golden_matrix(g2, f"{tag}_{name}"), 1e-13)
+        np.testing.assert_allclose(A @ np.ones(A.shape[1]), 1.0, rtol=1e-13)   # averages reproduce constants
