@@ -107,13 +107,18 @@ def config1(rows):
                  "Mf(sigma iso) @ u": small.get_face_inner_product(ssig),
                  "Me(sigma iso) @ e": small.get_edge_inner_product(ssig),
                  "Me(sigma aniso) @ e": small.get_edge_inner_product(ssig3),
-                 "dMf(sigma iso)(v) @ dm": small.get_face_inner_product_deriv(ssig)(sv[:small.nF])}
+                 }
+    import scipy.sparse as sp
+    AvF = small.average_face_to_cell.tocsr()
+    # the reference's own formula for the isotropic derivative: diag(v) (3 Av^T diag(V))  (base_tensor_mesh.py:865-988)
+    dM_small = (sp.diags(sv[:small.nF]) @ (3.0 * AvF.T) @ sp.diags(small.cell_volumes)).tocsr()
+    small_csr = {"dMf(sigma iso)(v) @ dm": dM_small, "dMf(sigma iso)(v).T @ w": dM_small.T.tocsr()}
     for name, op, nbytes in ops:
         x, y = big[:op.shape[1]], out[:op.shape[0]]
         ms = timeit(lambda: op.apply_device(x, out=y), 10)
         extra = None
-        if name in small_ops and not os.environ.get("DZB_NO_CPU"):
-            ns = cpu_ms_per_dof(small_ops[name].tocsr())
+        if (name in small_ops or name in small_csr) and not os.environ.get("DZB_NO_CPU"):
+            ns = cpu_ms_per_dof(small_csr[name] if name in small_csr else small_ops[name].tocsr())
             cpu_gdofs = 1.0 / ns
             extra = {"cpu_scipy_gdof_s": cpu_gdofs, "cpu_sample": "96^3, scipy csr_matvec, 1 core",
                      "gpu_over_cpu": op.shape[0] / ms / 1e6 / cpu_gdofs}
