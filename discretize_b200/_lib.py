@@ -30,6 +30,7 @@ OP_AVE_N2CC = 13
 OP_AVE_CC2F, OP_AVE_CCV2F, OP_AVE_CC2E, OP_AVE_E2F, OP_AVE_N2E, OP_AVE_N2F = 14, 15, 16, 17, 18, 19
 OP_CELL_GRAD, OP_CELL_GRAD_X, OP_CELL_GRAD_Y, OP_CELL_GRAD_Z = 20, 21, 22, 23
 OP_DIV_X, OP_DIV_Y, OP_DIV_Z = 24, 25, 26
+OP_GRAD_SQ, OP_CURL_SQ = 27, 28
 CG_SCALE = 64  # DzbCellGradFlags: bits 0..5 = Dirichlet on x-lo, x-hi, y-lo, y-hi, z-lo, z-hi
 
 MODEL_SCALAR, MODEL_ISO, MODEL_ANISO, MODEL_TENSOR = 0, 1, 2, 3
@@ -69,9 +70,13 @@ SIGNATURES = {
     "dzb_tree_ell_spmv": [_L, _I, _L, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P],
     "dzb_csr_spmv": [_L, _P, _I, _P, _P, _P, _P, _I, _P],
     "dzb_diag_scale": [_L, _P, _P, _P, _I, _P],
+    "dzb_solver_workspace_bytes": [],
+    "dzb_dot": [_L, _P, _P, _P, _P, _I, _P],
+    "dzb_cg_update": [_L, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "dzb_cg_direction": [_L, _P, _P, _P, _P, _P],
     "dzb_points_inside": [_P, _L, C.POINTER(_D), C.POINTER(_D), C.POINTER(_D), _P, _P],
 }
-_RESTYPES = {"dzb_last_error": C.c_char_p}
+_RESTYPES = {"dzb_last_error": C.c_char_p, "dzb_solver_workspace_bytes": C.c_int64}
 
 _lib = None
 

@@ -59,7 +59,7 @@ template <class R> static void shape_of(const TM &m, i64 *nr, i64 *nc) {
     DZB_FOR_OP(DZB_OP_AVE_E2F, BODY) DZB_FOR_OP(DZB_OP_AVE_N2E, BODY) DZB_FOR_OP(DZB_OP_AVE_N2F, BODY)    \
     DZB_FOR_OP(DZB_OP_CELL_GRAD, BODY) DZB_FOR_OP(DZB_OP_CELL_GRAD_X, BODY) DZB_FOR_OP(DZB_OP_CELL_GRAD_Y, BODY) \
     DZB_FOR_OP(DZB_OP_CELL_GRAD_Z, BODY) DZB_FOR_OP(DZB_OP_DIV_X, BODY) DZB_FOR_OP(DZB_OP_DIV_Y, BODY)    \
-    DZB_FOR_OP(DZB_OP_DIV_Z, BODY)                                                                       \
+    DZB_FOR_OP(DZB_OP_DIV_Z, BODY) DZB_FOR_OP(DZB_OP_GRAD_SQ, BODY) DZB_FOR_OP(DZB_OP_CURL_SQ, BODY)      \
     default:                                                                       \
       set_error("unknown operator id");                                            \
       return -1;                                                                   \

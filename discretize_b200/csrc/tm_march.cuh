@@ -282,9 +282,20 @@ __device__ __forceinline__ void c2f_weights(i64 p, i64 n, const double *__restri
 
 template <int KIND, class CFG>
 __global__ void DZB_MARCH_BOUNDS(CFG) k_c2f_march(TM m, int fx, int fy, int fz, const double *__restrict__ c, double *__restrict__ u) {
+  // the z weights depend on k only: the block computes them once (the cell-gradient ones cost an FP64 division each)
+  __shared__ double s_lo[CFG::KC], s_hi[CFG::KC];
   MarchGeom g;
   const i64 nx = m.nx, ny = m.ny, nz = m.nz;
-  if (!g.template init<CFG>(nx + 1, ny + 1, nz + 1)) return;
+  const bool live = g.template init<CFG>(nx + 1, ny + 1, nz + 1);
+  for (int t = threadIdx.y * 32 + threadIdx.x; t < CFG::KC; t += CFG::THREADS) {
+    const i64 k = (i64)blockIdx.z * CFG::KC + t;
+    double lo = 0.0, hi = 0.0;
+    if (k <= nz) c2f_weights<KIND>(k, nz, m.hz, m.rhz, fz, lo, hi);
+    s_lo[t] = lo;
+    s_hi[t] = hi;
+  }
+  __syncthreads();
+  if (!live) return;
   const i64 i = g.i, j = g.j;
   const bool hx = i < nx, hy = j < ny, lx = i >= 1, ly = j >= 1;
   double ax_lo, ax_hi, ay_lo, ay_hi;
@@ -299,8 +310,7 @@ __global__ void DZB_MARCH_BOUNDS(CFG) k_c2f_march(TM m, int fx, int fy, int fz, 
   double cm = (g.k0 >= 1 && in_xy) ? __ldg(pc - plC) : 0.0;   // cell (i,j,k-1)
   auto step = [&](auto hz_tag, i64 k) {
     constexpr bool HZ = decltype(hz_tag)::value;
-    double az_lo, az_hi;
-    c2f_weights<KIND>(k, nz, m.hz, m.rhz, fz, az_lo, az_hi);
+    const double az_lo = s_lo[k - g.k0], az_hi = s_hi[k - g.k0];
     double c0 = 0.0;
     if (HZ) {
       c0 = ldp(pc, in_xy);

@@ -24,7 +24,9 @@ enum Ax : int {
   AX_AE = 5,  // node i  <- cells i-1, i : (1/2, 1/2), weight 1 on the two boundary nodes  (av_extrap)
   AX_AET = 6, // cell i  <- nodes i, i+1 : av_extrap^T
   AX_GC = 7,  // node i  <- cells i-1, i : cell gradient (-s, +s) with ghost-point boundary rows (_ddxCellGrad)
-  AX_GCT = 8  // cell i  <- nodes i, i+1 : its transpose
+  AX_GCT = 8, // cell i  <- nodes i, i+1 : its transpose
+  AX_D2 = 9,  // cell i  <- nodes i, i+1 : (1/h_i^2, 1/h_i^2)          entrywise square of ddx
+  AX_DT2 = 10 // node i  <- cells i-1, i : (1/h_{i-1}^2, 1/h_i^2)      entrywise square of ddx^T
 };
 
 // flags of AX_GC / AX_GCT for one axis
@@ -76,6 +78,17 @@ __device__ __forceinline__ int ax_entries(i64 i, i64 n, const double *__restrict
     const bool lo = i >= 1, hi = i < n;
     ix[0] = i - 1; w[0] = lo ? __ldg(rh + i - 1) : 0.0;
     ix[1] = i; w[1] = hi ? -__ldg(rh + i) : 0.0;
+    return (lo ? 1 : 0) | (hi ? 2 : 0);
+  } else if (OP == AX_D2) {
+    const double r = __ldg(rh + i);
+    ix[0] = i; w[0] = r * r;
+    ix[1] = i + 1; w[1] = r * r;
+    return 3;
+  } else if (OP == AX_DT2) {
+    const bool lo = i >= 1, hi = i < n;
+    const double a = lo ? __ldg(rh + i - 1) : 0.0, b = hi ? __ldg(rh + i) : 0.0;
+    ix[0] = i - 1; w[0] = a * a;
+    ix[1] = i; w[1] = b * b;
     return (lo ? 1 : 0) | (hi ? 2 : 0);
   } else if (OP == AX_AT) {
     ix[0] = i - 1; w[0] = 0.5;
@@ -606,5 +619,78 @@ template <> struct Rows<DZB_OP_DIV_Y, false> : RowsDivComp<1> {};
 template <> struct Rows<DZB_OP_DIV_Y, true> : RowsDivCompT<1> {};
 template <> struct Rows<DZB_OP_DIV_Z, false> : RowsDivComp<2> {};
 template <> struct Rows<DZB_OP_DIV_Z, true> : RowsDivCompT<2> {};
+
+// ---- entrywise squares of nodal_gradient and edge_curl --------------------------------------------------------------
+// diag(G^T W G) = (G o G)^T w  and  diag(C^T W C) = (C o C)^T w  for diagonal W: the Jacobi preconditioners of the fused
+// DC and Maxwell operators are ONE apply of these with the mass diagonal as input.
+template <> struct Rows<DZB_OP_GRAD_SQ, false> : RowsBase {
+  static constexpr int NCOMP = 3;
+  static constexpr int MAXNNZ = 2;
+  template <int COMP> static constexpr int loc() { return EdgeOf<COMP>::LOC; }
+  template <int COMP> __host__ __device__ static i64 row_off(const TM &m) { return m.off<loc<COMP>()>(); }
+  __host__ __device__ static i64 nrows(const TM &m) { return m.nE(); }
+  __host__ __device__ static i64 ncols(const TM &m) { return m.nN(); }
+  template <int COMP, class E> __device__ void row(const TM &m, i64 i, i64 j, i64 k, E &&emit) const {
+    term<(COMP == 0 ? AX_D2 : AX_ID), (COMP == 1 ? AX_D2 : AX_ID), (COMP == 2 ? AX_D2 : AX_ID)>(m, i, j, k, 1.0,
+                                                                                                 DZB_EMIT(LOC_N, 0));
+  }
+};
+template <> struct Rows<DZB_OP_GRAD_SQ, true> : RowsBase {
+  static constexpr int NCOMP = 1;
+  static constexpr int MAXNNZ = 6;
+  template <int COMP> static constexpr int loc() { return LOC_N; }
+  template <int COMP> __host__ __device__ static i64 row_off(const TM &m) { return 0; }
+  __host__ __device__ static i64 nrows(const TM &m) { return m.nN(); }
+  __host__ __device__ static i64 ncols(const TM &m) { return m.nE(); }
+  template <int COMP, class E> __device__ void row(const TM &m, i64 i, i64 j, i64 k, E &&emit) const {
+    term<AX_DT2, AX_ID, AX_ID>(m, i, j, k, 1.0, DZB_EMIT(LOC_EX, m.off<LOC_EX>()));
+    term<AX_ID, AX_DT2, AX_ID>(m, i, j, k, 1.0, DZB_EMIT(LOC_EY, m.off<LOC_EY>()));
+    term<AX_ID, AX_ID, AX_DT2>(m, i, j, k, 1.0, DZB_EMIT(LOC_EZ, m.off<LOC_EZ>()));
+  }
+};
+template <> struct Rows<DZB_OP_CURL_SQ, false> : RowsBase {
+  static constexpr int NCOMP = 3;
+  static constexpr int MAXNNZ = 4;
+  template <int COMP> static constexpr int loc() { return FaceOf<COMP>::LOC; }
+  template <int COMP> __host__ __device__ static i64 row_off(const TM &m) { return m.off<loc<COMP>()>(); }
+  __host__ __device__ static i64 nrows(const TM &m) { return m.nF(); }
+  __host__ __device__ static i64 ncols(const TM &m) { return m.nE(); }
+  template <int COMP, class E> __device__ void row(const TM &m, i64 i, i64 j, i64 k, E &&emit) const {
+    if (COMP == 0) {
+      term<AX_ID, AX_ID, AX_D2>(m, i, j, k, 1.0, DZB_EMIT(LOC_EY, m.off<LOC_EY>()));
+      term<AX_ID, AX_D2, AX_ID>(m, i, j, k, 1.0, DZB_EMIT(LOC_EZ, m.off<LOC_EZ>()));
+    }
+    if (COMP == 1) {
+      term<AX_ID, AX_ID, AX_D2>(m, i, j, k, 1.0, DZB_EMIT(LOC_EX, m.off<LOC_EX>()));
+      term<AX_D2, AX_ID, AX_ID>(m, i, j, k, 1.0, DZB_EMIT(LOC_EZ, m.off<LOC_EZ>()));
+    }
+    if (COMP == 2) {
+      term<AX_ID, AX_D2, AX_ID>(m, i, j, k, 1.0, DZB_EMIT(LOC_EX, m.off<LOC_EX>()));
+      term<AX_D2, AX_ID, AX_ID>(m, i, j, k, 1.0, DZB_EMIT(LOC_EY, m.off<LOC_EY>()));
+    }
+  }
+};
+template <> struct Rows<DZB_OP_CURL_SQ, true> : RowsBase {
+  static constexpr int NCOMP = 3;
+  static constexpr int MAXNNZ = 4;
+  template <int COMP> static constexpr int loc() { return EdgeOf<COMP>::LOC; }
+  template <int COMP> __host__ __device__ static i64 row_off(const TM &m) { return m.off<loc<COMP>()>(); }
+  __host__ __device__ static i64 nrows(const TM &m) { return m.nE(); }
+  __host__ __device__ static i64 ncols(const TM &m) { return m.nF(); }
+  template <int COMP, class E> __device__ void row(const TM &m, i64 i, i64 j, i64 k, E &&emit) const {
+    if (COMP == 0) {
+      term<AX_ID, AX_ID, AX_DT2>(m, i, j, k, 1.0, DZB_EMIT(LOC_FY, m.off<LOC_FY>()));
+      term<AX_ID, AX_DT2, AX_ID>(m, i, j, k, 1.0, DZB_EMIT(LOC_FZ, m.off<LOC_FZ>()));
+    }
+    if (COMP == 1) {
+      term<AX_ID, AX_ID, AX_DT2>(m, i, j, k, 1.0, DZB_EMIT(LOC_FX, m.off<LOC_FX>()));
+      term<AX_DT2, AX_ID, AX_ID>(m, i, j, k, 1.0, DZB_EMIT(LOC_FZ, m.off<LOC_FZ>()));
+    }
+    if (COMP == 2) {
+      term<AX_ID, AX_DT2, AX_ID>(m, i, j, k, 1.0, DZB_EMIT(LOC_FX, m.off<LOC_FX>()));
+      term<AX_DT2, AX_ID, AX_ID>(m, i, j, k, 1.0, DZB_EMIT(LOC_FY, m.off<LOC_FY>()));
+    }
+  }
+};
 
 }  // namespace dzb

@@ -67,7 +67,10 @@ enum DzbOp {
   DZB_OP_DIV_X = 24,     /* face_x_divergence           :236-348 */
   DZB_OP_DIV_Y = 25,     /* face_y_divergence           :350-462 */
   DZB_OP_DIV_Z = 26,     /* face_z_divergence           :464-591 */
-  DZB_OP_COUNT = 27
+  /* entrywise squares: diag(G^T W G) = (G o G)^T w, diag(C^T W C) = (C o C)^T w (Jacobi preconditioners) */
+  DZB_OP_GRAD_SQ = 27,
+  DZB_OP_CURL_SQ = 28,
+  DZB_OP_COUNT = 29
 };
 
 /* `flags` of the DZB_OP_CELL_GRAD* operators (set_cell_gradient_BC, :975-1046; _ddxCellGrad, :41-82).
@@ -213,6 +216,21 @@ int dzb_csr_spmv(int64_t nrows, const void *indptr, int indptr_is64, const int32
 /* y = d .* x (invert == 0) or x ./ d: diagonal mass matrices on a TreeMesh
  * (base/base_tensor_mesh.py:792-863 with the tree averages). */
 int dzb_diag_scale(int64_t n, const double *d, const double *x, double *y, int invert, void *stream);
+
+/* ---- solver-side vector kernels ------------------------------------ */
+/* One Jacobi-preconditioned CG iteration on an operator A is: Ap = A p (any apply above), dzb_dot(p, Ap -> scal[1]),
+ * dzb_cg_update, dzb_cg_direction.  All scalars live in the DEVICE array scal[6]:
+ * scal[0] = r.z (current), scal[1] = p.Ap, scal[2] = r.z (new), scal[3] = r.r.  `workspace`: device memory of
+ * dzb_solver_workspace_bytes() bytes, zeroed once by the caller.  Reductions are deterministic. */
+int64_t dzb_solver_workspace_bytes(void);
+/* scal[slot] = a . b */
+int dzb_dot(int64_t n, const double *a, const double *b, void *workspace, double *scal, int slot, void *stream);
+/* alpha = scal[0]/scal[1]; x += alpha p; r -= alpha Ap; z = dinv ? dinv*r : r (z may alias r when dinv == NULL);
+ * scal[2] = r.z, scal[3] = r.r */
+int dzb_cg_update(int64_t n, double *x, double *r, const double *p, const double *Ap, const double *dinv, double *z,
+                  void *workspace, double *scal, void *stream);
+/* beta = scal[2]/scal[0]; p = z + beta p; scal[0] = scal[2] */
+int dzb_cg_direction(int64_t n, double *p, const double *z, void *workspace, double *scal, void *stream);
 
 #ifdef __cplusplus
 }
