@@ -317,6 +317,17 @@ class DCNodalOperator(Operator):
 
     _dev_apply_t = _dev_apply
 
+    def diagonal_device(self):
+        """diag(G^T Me G) = (G o G)^T diag(Me): one apply of the entrywise-squared gradient to the edge mass
+        diagonal (the Jacobi preconditioner of ``solvers.pcg``)."""
+        me = torch.empty(self.mesh.n_edges, dtype=torch.float64, device=cuda_device())
+        check(load().dzb_tm_mass_diag(C.byref(self.mesh.device_mesh()), _lib.FLAG_EDGES, _lib.MODEL_ISO, ptr(self.sigma),
+                                      0.0, ptr(me), stream_ptr()), "dzb_tm_mass_diag")
+        return StencilOperator(self.mesh, _lib.OP_GRAD_SQ, transpose=True, name="grad_sq").apply_device(me)
+
+    def diagonal(self):
+        return self.diagonal_device().cpu().numpy()
+
     def apply_planes(self, x, out, k_begin, k_end):
         """Write only node planes k_begin <= k < k_end of y = A x (z-slab building block)."""
         check(load().dzb_tm_dc_nodal_range(C.byref(self.mesh.device_mesh()), ptr(self.sigma), ptr(x), ptr(out),
@@ -399,6 +410,20 @@ class MaxwellOperator(Operator):
                                     stream_ptr()), "dzb_tm_maxwell")
 
     _dev_apply_t = _dev_apply
+
+    def diagonal_device(self):
+        """diag(C^T Mf C + Me) = (C o C)^T diag(Mf) + diag(Me)."""
+        dm = C.byref(self.mesh.device_mesh())
+        mf = torch.empty(self.mesh.n_faces, dtype=torch.float64, device=cuda_device())
+        me = torch.empty(self.mesh.n_edges, dtype=torch.float64, device=cuda_device())
+        check(load().dzb_tm_mass_diag(dm, 0, _lib.MODEL_ISO, ptr(self.mui), 0.0, ptr(mf), stream_ptr()), "dzb_tm_mass_diag")
+        check(load().dzb_tm_mass_diag(dm, _lib.FLAG_EDGES, _lib.MODEL_ISO, ptr(self.sigma), 0.0, ptr(me), stream_ptr()),
+              "dzb_tm_mass_diag")
+        d = StencilOperator(self.mesh, _lib.OP_CURL_SQ, transpose=True, name="curl_sq").apply_device(mf)
+        return d.add_(me)
+
+    def diagonal(self):
+        return self.diagonal_device().cpu().numpy()
 
     def apply_planes(self, x, out, k_begin, k_end):
         """Write only Ex, Ey on node planes / Ez in cell layers k_begin <= k < k_end (z-slab building block)."""

@@ -1,0 +1,97 @@
+"""GPU tests of the solver-side pieces: analytic Jacobi diagonals of the fused operators, the
+entrywise-squared stencils behind them, the device-resident CG vector kernels and the PCG driver."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse.linalg as sla
+
+from oracle import tensor_ops as T
+from tests.helpers import assert_close_vec, assert_same_matrix, make_pair
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.fail("gpu tests need a CUDA device (no CPU fallback exists)")
+
+
+def _fused(mesh, grid, seed=3):
+    rng = np.random.default_rng(seed)
+    sig, mui = np.exp(rng.standard_normal(mesh.nC)), np.exp(rng.standard_normal(mesh.nC))
+    G, Cc = mesh.nodal_gradient, mesh.edge_curl
+    Adc = G.T @ mesh.get_edge_inner_product(sig) @ G
+    Amx = Cc.T @ mesh.get_face_inner_product(mui) @ Cc + mesh.get_edge_inner_product(sig)
+    Gr, Cr = T.nodal_gradient(grid), T.edge_curl(grid)
+    Rdc = (Gr.T @ T.inner_product(grid, "E", sig) @ Gr).tocsr()
+    Rmx = (Cr.T @ T.inner_product(grid, "F", mui) @ Cr + T.inner_product(grid, "E", sig)).tocsr()
+    return Adc, Amx, Rdc, Rmx
+
+
+@pytest.mark.parametrize("mesh_name", ["nonuniform", "wide", "thin"])
+def test_squared_stencils_and_fused_diagonals(mesh_name):
+    from discretize_b200 import _lib
+    from discretize_b200.tensor_ops import StencilOperator
+
+    mesh, grid = make_pair(mesh_name)
+    for op_id, ref in ((_lib.OP_GRAD_SQ, T.nodal_gradient(grid)), (_lib.OP_CURL_SQ, T.edge_curl(grid))):
+        sq = ref.multiply(ref).tocsr()
+        op = StencilOperator(mesh, op_id, name="sq")
+        assert_same_matrix(op.tocsr(), sq)
+        assert_same_matrix(op.T.tocsr(), sq.T.tocsr())
+        x = np.random.default_rng(1).standard_normal(sq.shape[0])
+        assert_close_vec(op.T @ x, sq.T @ x)
+    Adc, Amx, Rdc, Rmx = _fused(mesh, grid)
+    assert type(Adc).__name__ == "DCNodalOperator" and type(Amx).__name__ == "MaxwellOperator"
+    assert_close_vec(Adc.diagonal(), Rdc.diagonal())
+    assert_close_vec(Amx.diagonal(), Rmx.diagonal())
+
+
+def test_dot_kernel_is_deterministic_and_exact_enough():
+    from discretize_b200._lib import load
+    from discretize_b200.operators import ptr, stream_ptr
+
+    lib = load()
+    n = 3_000_017
+    gen = torch.Generator(device="cuda"); gen.manual_seed(4)
+    a = torch.randn(n, dtype=torch.float64, device="cuda", generator=gen)
+    b = torch.randn(n, dtype=torch.float64, device="cuda", generator=gen)
+    ws = torch.zeros(int(lib.dzb_solver_workspace_bytes()), dtype=torch.uint8, device="cuda")
+    scal = torch.zeros(6, dtype=torch.float64, device="cuda")
+    vals = []
+    for _ in range(3):
+        assert lib.dzb_dot(n, ptr(a), ptr(b), ptr(ws), ptr(scal), 1, stream_ptr()) == 0
+        vals.append(float(scal[1]))
+    assert vals[0] == vals[1] == vals[2]                       # block-ordered reduction: bitwise repeatable
+    ref = float(torch.dot(a, b))
+    assert abs(vals[0] - ref) <= 1e-12 * float(a.norm() * b.norm())
+
+
+@pytest.mark.parametrize("jacobi", [False, True])
+def test_pcg_on_fused_maxwell_and_dc(jacobi):
+    from discretize_b200.solvers import pcg
+
+    mesh, grid = make_pair("wide")          # 70 x 9 x 37, strongly varying sigma / mu
+    Adc, Amx, Rdc, Rmx = _fused(mesh, grid)
+    rng = np.random.default_rng(9)
+    # Maxwell (SPD): against a direct solve of the oracle's matrix
+    b = rng.standard_normal(mesh.nE)
+    dinv = 1.0 / Amx.diagonal_device() if jacobi else None
+    x, info = pcg(Amx, b, inv_diag=dinv, rtol=1e-11, maxiter=5000, check_every=25)
+    assert info.converged, info
+    xr = sla.spsolve(Rmx.tocsc(), b)
+    assert_close_vec(x.cpu().numpy(), xr, 1e-8)
+    assert np.linalg.norm(Rmx @ x.cpu().numpy() - b) <= 1e-10 * np.linalg.norm(b)
+    # DC (singular: constants in the null space) with a right-hand side in the range
+    xt = rng.standard_normal(mesh.nN)
+    bdc = Rdc @ xt
+    dinv = 1.0 / Adc.diagonal_device() if jacobi else None
+    x, info = pcg(Adc, bdc, inv_diag=dinv, rtol=1e-10, maxiter=8000, check_every=25)
+    assert info.converged, info
+    assert np.linalg.norm(Rdc @ x.cpu().numpy() - bdc) <= 1e-9 * np.linalg.norm(bdc)
+    if jacobi:
+        _, plain = pcg(Adc, bdc, rtol=1e-10, maxiter=8000, check_every=25)
+        assert info.iterations <= plain.iterations          # the preconditioner must not hurt on a graded mesh
