@@ -220,6 +220,34 @@ def config5(rows, n):
     report(rows, f"cfg2 {n}^3 DC G^T Me G fused ({type(Adc).__name__})", mesh.nN, 8.0 * (2 * mesh.nN + mesh.nC), ms)
 
 
+def config_solver(rows, n):
+    """Jacobi-PCG on the fused DC operator: time per iteration = apply + dot + update + direction."""
+    from discretize_b200.solvers import pcg
+
+    mesh = dz.TensorMesh([n, n, n])
+    dev = torch.device("cuda")
+    sig = torch.exp(torch.randn(mesh.nC, dtype=torch.float64, device=dev))
+    G = mesh.nodal_gradient
+    A = G.T @ mesh.get_edge_inner_product(sig) @ G
+    xt = torch.randn(mesh.nN, dtype=torch.float64, device=dev)
+    b = A.apply_device(xt)
+    dinv = 1.0 / A.diagonal_device()
+    del xt
+    iters = 60
+    pcg(A, b, inv_diag=dinv, rtol=0.0, maxiter=10, check_every=10)          # warm-up
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    x, info = pcg(A, b, inv_diag=dinv, rtol=0.0, maxiter=iters, check_every=iters)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    # per iteration: apply 24 B/node + dot 16 + update 64 (x rw, r rw, p, Ap, dinv, z) + direction 24
+    report(rows, f"cfg2 {n}^3 Jacobi-PCG iteration on fused G^T Me G (apply + 3 vector kernels)", mesh.nN,
+           8.0 * (2 * mesh.nN + mesh.nC) + 104.0 * mesh.nN, ms,
+           {"iterations": info.iterations, "residual_drop": info.history[-1] / info.history[0]})
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,4,5,3")
@@ -233,6 +261,7 @@ if __name__ == "__main__":
         if c == "1": config1(rows)
         if c == "3": config3(rows, a.tree_pts)
         if c == "4": config4(rows, a.interp_pts)
+        if c == "s": config_solver(rows, 512)
         if c == "5": config5(rows, a.maxwell_n)
         torch.cuda.empty_cache()
     if a.out:
