@@ -307,6 +307,35 @@ class TransposedOperator(Operator):
         return self.base.tocsr().T.tocsr()
 
 
+class DiagonalOperator(Operator):
+    """diag(d) as an operator (one streaming kernel); ``d``: numpy array or CUDA tensor."""
+
+    def __init__(self, diag):
+        self.diag = to_device(diag).reshape(-1)
+        n = self.diag.numel()
+        super().__init__((n, n))
+
+    def _dev_apply(self, x, out):
+        from ._lib import check, load
+
+        check(load().dzb_diag_scale(self.shape[0], ptr(self.diag), ptr(x), ptr(out), 0, stream_ptr()), "dzb_diag_scale")
+
+    _dev_apply_t = _dev_apply
+
+    def _transpose(self):
+        return self
+
+    _adjoint = _transpose
+
+    def diagonal(self):
+        return self.diag.cpu().numpy()
+
+    def _tocsr(self):
+        import scipy.sparse as sp
+
+        return sp.diags(self.diagonal(), format="csr")
+
+
 class ScaledOperator(Operator):
     def __init__(self, base, alpha):
         if isinstance(base, ScaledOperator):

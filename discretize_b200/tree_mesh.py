@@ -467,6 +467,16 @@ class TreeMesh:
             M = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(offEn[3], t.nodes.n_total))
             geoms.append(g)
             parts.append((1, M @ self._deflate_nodes()))
+        elif name in ("face_x_divergence", "face_y_divergence", "face_z_divergence"):
+            # tree_mesh.py:961-982: the column block of one face direction of face_divergence
+            d = "xyz".index(name[5])
+            g_all, p_all = self._host_parts("face_divergence")
+            o = np.r_[0, np.cumsum([f.n for f in t.faces])]
+            geoms.append(g_all[d])
+            parts.append((1, p_all[d][1][:, o[d]:o[d + 1]]))
+        elif name.startswith("stencil_cell_gradient") or name.startswith("average_cell_to_total_face_") \
+                or name.startswith("average_cell_to_face") or name == "average_cell_vector_to_face":
+            parts.append((0, self._host_cell_to_face(name)))
         elif name == "average_node_to_edge":  # tree_ext.pyx:4765-4918: 1/2 at the two end nodes, deflate nodes
             nE = [e.n for e in t.edges]
             offEn = np.r_[0, np.cumsum(nE)]
@@ -549,6 +559,95 @@ class TreeMesh:
             self._cache[key] = acc
         return self._cache[key]
 
+    def _face_sides(self, d):
+        """(minus cell, plus cell) of every TOTAL face of direction d (-1: none).  A hanging face inherits the side it
+        lacks from its parent (the big neighbour lists the parent face); a face with hanging children keeps its
+        missing side -- the reference writes the rows of the children instead (tree_ext.pyx:3641-3853)."""
+        t = self._t()
+        f = t.faces[d]
+        cells = np.arange(t.n_cells)
+        minus = np.full(f.n_total, -1, dtype=np.int64)
+        plus = np.full(f.n_total, -1, dtype=np.int64)
+        minus[t.cell_faces[d][:, 1]] = cells      # the cell whose + face this is sits on the minus side
+        plus[t.cell_faces[d][:, 0]] = cells
+        par = t.face_parents[d]
+        h = np.nonzero(f.hanging)[0]
+        need = h[minus[h] < 0]
+        minus[need] = minus[par[need]]
+        need = h[plus[h] < 0]
+        plus[need] = plus[par[need]]
+        return minus, plus
+
+    def _host_cell_to_face(self, name):
+        """Cell -> face operators of the cell-centred formulation (tree_ext.pyx:3471-3853, 5080-5512).
+
+        All of them walk the (minus cell, plus cell) pairs across the total faces.  The reference fills
+        preallocated zero triplet arrays, so every slot it does not write lands on entry (0, 0) with value 0:
+        mirrored by an explicit zero there."""
+        t = self._t()
+        nC = t.n_cells
+        if name in ("stencil_cell_gradient", "average_cell_to_face"):
+            return sp.vstack([self._host_cell_to_face(f"{name}_{c}") for c in "xyz"]).tocsr()
+        if name == "average_cell_vector_to_face":   # tree_ext.pyx:5131-5190
+            return sp.block_diag([self._host_cell_to_face(f"average_cell_to_face_{c}") for c in "xyz"]).tocsr()
+        d = "xyz".index(name[-1])
+        f = t.faces[d]
+        minus, plus = self._face_sides(d)
+        both = np.nonzero((minus >= 0) & (plus >= 0))[0]
+        zero = (np.zeros(1, dtype=np.int64), np.zeros(1, dtype=np.int64), np.zeros(1))
+        if name.startswith("stencil_cell_gradient_") or name.startswith("average_cell_to_total_face_"):
+            lo, hi = (-1.0, 1.0) if name.startswith("stencil") else (0.5, 0.5)
+            rows = np.r_[f.index[both], f.index[both], zero[0]]
+            cols = np.r_[minus[both], plus[both], zero[1]]
+            vals = np.r_[np.full(both.size, lo), np.full(both.size, hi), zero[2]]
+            return sp.csr_matrix((vals, (rows, cols)), shape=(f.n_total, nC))
+        # average_cell_to_face_{x,y,z}: distance weights, hanging faces accumulate a quarter each into their parent,
+        # boundary faces take the adjacent cell
+        xc = self.cell_centers[:, d]
+        xf = self._xs[d][f.loc[both, d]]
+        w = (xc[plus[both]] - xf) / (xc[plus[both]] - xc[minus[both]])
+        hang = f.hanging[both]
+        row = np.where(hang, f.index[t.face_parents[d][both]], f.index[both])
+        k = np.where(hang, 4.0, 1.0)
+        bnd = np.nonzero(~f.hanging & ((minus < 0) ^ (plus < 0)) & ~self._has_hanging_children(d))[0]
+        bcell = np.where(minus[bnd] >= 0, minus[bnd], plus[bnd])
+        # reference quirk (tree_ext.pyx:5219-5236): a cell without a + neighbour writes its + face and `continue`s,
+        # so the - boundary face of a cell that spans the whole axis is never written
+        spans = (minus[bnd] < 0) & (t.centers[bcell, d] + t.half[bcell] == t.shape_half[d])
+        bnd, bcell = bnd[~spans], bcell[~spans]
+        rows = np.r_[row, row, f.index[bnd], zero[0]]
+        cols = np.r_[minus[both], plus[both], bcell, zero[1]]
+        vals = np.r_[w / k, (1.0 - w) / k, np.ones(bnd.size), zero[2]]
+        return sp.csr_matrix((vals, (rows, cols)), shape=(f.n, nC))
+
+    def _has_hanging_children(self, d):
+        t = self._t()
+        f = t.faces[d]
+        out = np.zeros(f.n_total, dtype=bool)
+        out[t.face_parents[d][f.hanging]] = True
+        return out
+
+    @property
+    def cell_boundary_indices(self):
+        """Cells touching the -x, +x, -y, +y, -z, +z boundary, in cell order (tree_ext.pyx:2700-2822)."""
+        t = self._t()
+        out = []
+        for d in range(3):
+            out.append(np.nonzero(t.centers[:, d] - t.half == 0)[0])
+            out.append(np.nonzero(t.centers[:, d] + t.half == t.shape_half[d])[0])
+        return tuple(out)
+
+    @property
+    def face_boundary_indices(self):
+        """Per-direction indices of the boundary faces, in the order of their cells (tree_ext.pyx:2824-2920)."""
+        t = self._t()
+        cb = self.cell_boundary_indices
+        out = []
+        for d in range(3):
+            out.append(t.faces[d].index[t.cell_faces[d][cb[2 * d], 0]])
+            out.append(t.faces[d].index[t.cell_faces[d][cb[2 * d + 1], 1]])
+        return tuple(out)
+
     def _host_average(self, name, fams, cell_ents, off, R, w):
         """tree_ext.pyx:4089-4707: per cell 2 faces x 1/2 (4 edges x 1/4) per direction, then deflation."""
         t = self._t()
@@ -595,6 +694,56 @@ class TreeMesh:
     average_edge_y_to_cell = property(lambda self: self._operator("average_edge_y_to_cell"))
     average_edge_z_to_cell = property(lambda self: self._operator("average_edge_z_to_cell"))
     average_node_to_cell = property(lambda self: self._operator("average_node_to_cell"))
+    face_x_divergence = property(lambda self: self._operator("face_x_divergence"))
+    face_y_divergence = property(lambda self: self._operator("face_y_divergence"))
+    face_z_divergence = property(lambda self: self._operator("face_z_divergence"))
+    stencil_cell_gradient = property(lambda self: self._operator("stencil_cell_gradient"))
+    stencil_cell_gradient_x = property(lambda self: self._operator("stencil_cell_gradient_x"))
+    stencil_cell_gradient_y = property(lambda self: self._operator("stencil_cell_gradient_y"))
+    stencil_cell_gradient_z = property(lambda self: self._operator("stencil_cell_gradient_z"))
+    average_cell_to_face = property(lambda self: self._operator("average_cell_to_face"))
+    average_cell_to_face_x = property(lambda self: self._operator("average_cell_to_face_x"))
+    average_cell_to_face_y = property(lambda self: self._operator("average_cell_to_face_y"))
+    average_cell_to_face_z = property(lambda self: self._operator("average_cell_to_face_z"))
+    average_cell_vector_to_face = property(lambda self: self._operator("average_cell_vector_to_face"))
+
+    # plain methods in the reference (tree_ext.pyx:3471-3640 carry no @property)
+    def average_cell_to_total_face_x(self):
+        return self._operator("average_cell_to_total_face_x")
+
+    def average_cell_to_total_face_y(self):
+        return self._operator("average_cell_to_total_face_y")
+
+    def average_cell_to_total_face_z(self):
+        return self._operator("average_cell_to_total_face_z")
+
+    def _cell_gradient_component(self, d):
+        """-Pa Mf^-1 D_d^T diag(V) (tree_mesh.py:860-958): composed lazily from the CUDA operators; d = None: all faces."""
+        from .operators import DiagonalOperator
+
+        key = "OP_cell_gradient" + ("" if d is None else "_" + "xyz"[d])
+        if key not in self._cache:
+            t = self._t()
+            nF = [f.n for f in t.faces]
+            o = np.r_[0, np.cumsum(nF)]
+            fb = self.face_boundary_indices
+            mask = np.ones(o[3])
+            for dd in range(3):
+                mask[o[dd] + fb[2 * dd]] = 0.0
+                mask[o[dd] + fb[2 * dd + 1]] = 0.0
+            mfi = self.get_face_inner_product(invert_matrix=True).diag           # device diagonal of Mf(1)
+            if d is None:
+                D, pa, mi = self.face_divergence, mask, 1.0 / mfi
+            else:
+                D = self._operator("face_%s_divergence" % "xyz"[d])
+                pa, mi = mask[o[d]:o[d + 1]], 1.0 / mfi[int(o[d]):int(o[d + 1])]
+            self._cache[key] = -(DiagonalOperator(pa) @ DiagonalOperator(mi) @ D.T @ DiagonalOperator(self.cell_volumes))
+        return self._cache[key]
+
+    cell_gradient = property(lambda self: self._cell_gradient_component(None))
+    cell_gradient_x = property(lambda self: self._cell_gradient_component(0))
+    cell_gradient_y = property(lambda self: self._cell_gradient_component(1))
+    cell_gradient_z = property(lambda self: self._cell_gradient_component(2))
     average_node_to_edge = property(lambda self: self._operator("average_node_to_edge"))
     average_node_to_face = property(lambda self: self._operator("average_node_to_face"))
     average_edge_to_face = property(lambda self: self._operator("average_edge_to_face"))

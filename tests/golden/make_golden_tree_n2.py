@@ -12,6 +12,12 @@ sys.path.insert(0, ROOT)
 from oracle.refload import load_reference  # noqa: E402
 
 TREE_N2_OPS = ["average_node_to_edge", "average_node_to_face", "average_edge_to_face"]
+# cell-centred side (tree_ext.pyx:3471-3853, 5080-5512; tree_mesh.py:846-982)
+TREE_CC_OPS = ["face_x_divergence", "face_y_divergence", "face_z_divergence", "stencil_cell_gradient",
+               "stencil_cell_gradient_x", "stencil_cell_gradient_y", "stencil_cell_gradient_z", "average_cell_to_face",
+               "average_cell_to_face_x", "average_cell_to_face_y", "average_cell_to_face_z", "average_cell_vector_to_face"]
+TREE_CC_COMPOSITES = ["cell_gradient", "cell_gradient_x", "cell_gradient_y", "cell_gradient_z"]
+TREE_CC_METHODS = ["average_cell_to_total_face_x", "average_cell_to_total_face_y", "average_cell_to_total_face_z"]
 
 
 def main():
@@ -26,8 +32,12 @@ def main():
         mesh.refine_points(g[f"{tag}_pts"], -1, [1, 1], finalize=True)
         idx, lev = mesh.__getstate__()
         assert np.array_equal(idx, g[f"{tag}_state_indexes"]) and np.array_equal(lev, g[f"{tag}_state_levels"])
-        for name in TREE_N2_OPS:
-            m = sp.csr_matrix(getattr(mesh, name)).copy()
+        mats = [(name, getattr(mesh, name)) for name in TREE_N2_OPS + TREE_CC_OPS + TREE_CC_COMPOSITES]
+        mats += [(name, getattr(mesh, name)()) for name in TREE_CC_METHODS]
+        for k, ind in enumerate(mesh.face_boundary_indices):
+            out[f"{tag}_face_boundary_{k}"] = np.asarray(ind, dtype=np.int64)
+        for name, mat in mats:
+            m = sp.csr_matrix(mat).copy()
             m.sum_duplicates()
             m.sort_indices()
             out[f"{tag}_{name}__indptr"] = m.indptr.astype(np.int64)

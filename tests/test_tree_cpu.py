@@ -109,3 +109,19 @@ def test_tree_node_and_edge_to_face_averages_match_reference_fixture(gold, tag):
         A = m._host_matrix(name)
         assert_same_matrix(A, golden_matrix(g2, f"{tag}_{name}"), 1e-13)
         np.testing.assert_allclose(A @ np.ones(A.shape[1]), 1.0, rtol=1e-13)   # averages reproduce constants
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_tree_cell_centred_operators_match_reference_fixture(gold, tag):
+    """stencil_cell_gradient*, average_cell_to_face*, average_cell_to_total_face_*, face_*_divergence and the boundary
+    face indices (tree_ext.pyx:2824-2920, 3471-3853, 5080-5512), explicit (0, 0) zero of the reference included."""
+    from tests.golden.make_golden_tree_n2 import TREE_CC_METHODS, TREE_CC_OPS
+
+    g2 = load_golden("tree_n2_small.npz")
+    m = _mesh_from_fixture(gold, tag, "refine")
+    for name in TREE_CC_OPS + TREE_CC_METHODS:
+        assert_same_matrix(m._host_matrix(name), golden_matrix(g2, f"{tag}_{name}"), 1e-13)
+    for k, ind in enumerate(m.face_boundary_indices):
+        np.testing.assert_array_equal(ind, g2[f"{tag}_face_boundary_{k}"])
+    A = m._host_matrix("average_cell_to_face")
+    np.testing.assert_allclose(A @ np.ones(m.nC), 1.0, rtol=1e-13)
