@@ -95,3 +95,30 @@ def test_pcg_on_fused_maxwell_and_dc(jacobi):
     if jacobi:
         _, plain = pcg(Adc, bdc, rtol=1e-10, maxiter=8000, check_every=25)
         assert info.iterations <= plain.iterations          # the preconditioner must not hurt on a graded mesh
+
+
+def test_pcg_cell_centred_dc_on_octree():
+    """The cell-centred DC system of SimPEG on an OcTree, V D Mf(rho)^-1 D^T V (+ eps V to pin the constant), composed
+    lazily from the CUDA OcTree operators and solved by the device-resident PCG; checked against spsolve of the host
+    matrices (which are the reference's, tests/test_tree_cpu.py)."""
+    import scipy.sparse as sp
+
+    import discretize_b200 as dz
+    from discretize_b200.operators import DiagonalOperator
+    from discretize_b200.solvers import pcg
+
+    m = dz.TreeMesh([16, 16, 16], diagonal_balance=True)
+    rng = np.random.default_rng(21)
+    m.refine_points(rng.random((5, 3)) * 0.6 + 0.2, -1, [1, 1], finalize=True)
+    rho = np.exp(rng.standard_normal(m.nC))
+    V = m.cell_volumes
+    D = m.face_divergence
+    MfI = m.get_face_inner_product(rho, invert_matrix=True)
+    Vop = DiagonalOperator(V)
+    A = Vop @ D @ MfI @ D.T @ Vop + DiagonalOperator(1e-3 * V)
+    Dh = m._host_matrix("face_divergence")
+    Ah = (sp.diags(V) @ Dh @ sp.diags(1.0 / MfI.diag.cpu().numpy()) @ Dh.T @ sp.diags(V) + sp.diags(1e-3 * V)).tocsc()
+    b = rng.standard_normal(m.nC)
+    x, info = pcg(A, b, inv_diag=1.0 / Ah.diagonal(), rtol=1e-11, maxiter=4000, check_every=20)
+    assert info.converged, info
+    assert_close_vec(x.cpu().numpy(), sla.spsolve(Ah, b), 1e-8)
