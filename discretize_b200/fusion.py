@@ -24,11 +24,22 @@ def _plain_iso_mass(op, proj):
             and not op.invert_model and not op.invert_matrix)
 
 
+def _inverse_iso_face_mass(op):
+    """Mf(rho)^-1: diagonal face mass matrix of an isotropic nC model, invert_matrix only."""
+    from .tensor_ops import MassOperator
+
+    return (isinstance(op, MassOperator) and op.proj == "F" and op.model.kind == _lib.MODEL_ISO
+            and not op.invert_model and op.invert_matrix)
+
+
 def fuse_product(factors):
-    from .tensor_ops import DCNodalOperator
+    from .tensor_ops import DCCellOperator, DCNodalOperator
 
     if len(factors) == 3:
         a, m, b = factors
+        if (_is_stencil(a, _lib.OP_DIV, False) and _is_stencil(b, _lib.OP_DIV, True)
+                and _inverse_iso_face_mass(m) and a.mesh is b.mesh is m.mesh):
+            return DCCellOperator(m.mesh, m.model.dev)
         if (_is_stencil(a, _lib.OP_GRAD, True) and _is_stencil(b, _lib.OP_GRAD, False)
                 and _plain_iso_mass(m, "E") and a.mesh is b.mesh is m.mesh):
             return DCNodalOperator(m.mesh, m.model.dev)

@@ -394,6 +394,59 @@ class DCNodalOperator(Operator):
         return (G.T @ Me @ G).tocsr()
 
 
+class DCCellOperator(Operator):
+    """D Mf(rho)^-1 D^T in one kernel (cell-centred DC, SimPEG's default formulation); symmetric.
+
+    reference composition: examples/plot_dc_resistivity.py:23-30.  ``neumann=True`` drops the boundary faces
+    (zero-flux boundary); the plain product keeps them (homogeneous Dirichlet)."""
+
+    def __init__(self, mesh, rho_dev, neumann=False, cache_inverse_mass=True):
+        n = mesh.n_cells
+        super().__init__((n, n))
+        self.mesh, self.rho, self.neumann = mesh, rho_dev, bool(neumann)
+        # cache_inverse_mass: keep 1/diag(Mf) (nF values) and run the division-free kernel (40 B/cell); False: generate
+        # the face masses on the fly from rho (24 B/cell + five FP64 divisions per cell, no extra memory)
+        self.cache_inverse_mass = bool(cache_inverse_mass)
+        self._mi = None
+
+    def _dev_apply(self, x, out):
+        dm = C.byref(self.mesh.device_mesh())
+        if not self.cache_inverse_mass:
+            check(load().dzb_tm_dc_cell(dm, ptr(self.rho), int(self.neumann), ptr(x), ptr(out), stream_ptr()), "dzb_tm_dc_cell")
+            return
+        if self._mi is None:
+            self._mi = torch.empty(self.mesh.n_faces, dtype=torch.float64, device=cuda_device())
+            check(load().dzb_tm_mass_diag(dm, _lib.FLAG_INVERT_MATRIX, _lib.MODEL_ISO, ptr(self.rho), 0.0, ptr(self._mi),
+                                          stream_ptr()), "dzb_tm_mass_diag")
+        check(load().dzb_tm_dc_cell_mi(dm, ptr(self._mi), int(self.neumann), ptr(x), ptr(out), stream_ptr()),
+              "dzb_tm_dc_cell_mi")
+
+    _dev_apply_t = _dev_apply
+
+    def _transpose(self):
+        return self
+
+    _adjoint = _transpose
+
+    def _tocsr(self):
+        D = self.mesh.face_divergence.tocsr()
+        mfi = MassOperator(self.mesh, "F", _ModelFromDevice(self.mesh, self.rho), False, True).diagonal()   # 1 / diag(Mf)
+        if self.neumann:  # boundary faces (a single adjacent cell) carry no flux
+            mfi = np.where(np.diff(D.tocsc().indptr) == 2, mfi, 0.0)
+        A = (D @ sp.diags(mfi) @ D.T).tocsr()
+        if self.neumann:
+            A.eliminate_zeros()
+        A.sort_indices()
+        return A
+
+
+def _ModelFromDevice(mesh, dev_tensor):
+    md = _Model(mesh, None)
+    md.tt, md.kind, md.dev, md.scalar = 1, _lib.MODEL_ISO, dev_tensor, 0.0
+    md.n_params = mesh.n_cells
+    return md
+
+
 class MaxwellOperator(Operator):
     """C^T Mf(mui) C + Me(sigma) in one kernel (K9); symmetric.
 

@@ -153,6 +153,16 @@ int dzb_tm_dc_nodal(const DzbTensorMesh *m, const double *sigma, const double *p
 int dzb_tm_dc_nodal_range(const DzbTensorMesh *m, const double *sigma, const double *phi, double *y, int64_t k_begin,
                           int64_t k_end, void *stream);
 
+/* y = D Mf(rho)^-1 D^T x  (DC resistivity, cell-centred: examples/plot_dc_resistivity.py:23-30;
+ * face_divergence :225-235 + get_face_inner_product(rho, invert_matrix=True), isotropic rho of nC values) in ONE
+ * kernel.  flags: DZB_DC_CELL_NEUMANN drops the boundary faces (zero-flux boundary) -- default keeps them, which is
+ * what the plain product D Mf^-1 D^T does (homogeneous Dirichlet ghost values). */
+enum DzbDcCellFlags { DZB_DC_CELL_NEUMANN = 1 };
+int dzb_tm_dc_cell(const DzbTensorMesh *m, const double *rho, int flags, const double *x, double *y, void *stream);
+/* The same with mi[nF] = 1 / diag(Mf(rho)) precomputed (dzb_tm_mass_diag with DZB_INVERT_MATRIX): no divisions in the
+ * apply, 40 B per cell. */
+int dzb_tm_dc_cell_mi(const DzbTensorMesh *m, const double *mi, int flags, const double *x, double *y, void *stream);
+
 /* y = C^T Mf(mui) C e + Me(sigma) e  (Maxwell, E-formulation;
  * tests/boundaries/test_boundary_maxwell.py:95-99): edge_curl (:2169-2181) +
  * get_face_inner_product(mui) + get_edge_inner_product(sigma), isotropic models. */

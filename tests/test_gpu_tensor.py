@@ -484,3 +484,44 @@ def test_aliases_and_counts():
     np.testing.assert_array_equal(mesh.cell_volumes, grid.cell_volumes())
     np.testing.assert_array_equal(mesh.face_areas, grid.face_areas())
     np.testing.assert_array_equal(mesh.edge_lengths, grid.edge_lengths())
+
+
+@pytest.mark.parametrize("mesh_name", list(MESHES))
+def test_dc_cell_fused(mesh_name):
+    """D Mf(rho)^-1 D^T is recognised and replaced by ONE kernel (cell-centred DC); Dirichlet (the plain product) and
+    Neumann (boundary faces dropped) variants against the oracle product."""
+    from discretize_b200.tensor_ops import DCCellOperator
+
+    mesh, grid = make_pair(mesh_name)
+    rng = np.random.default_rng(17)
+    rho = np.exp(rng.standard_normal(mesh.nC))
+    D = mesh.face_divergence
+    A = D @ mesh.get_face_inner_product(rho, invert_matrix=True) @ D.T
+    assert isinstance(A, DCCellOperator)
+    Dr = T.face_divergence(grid)
+    MfI = T.inner_product(grid, "F", rho, invert_matrix=True)
+    ref = (Dr @ MfI @ Dr.T).tocsr()
+    x = rng.standard_normal(mesh.nC)
+    assert_close_vec(A @ x, ref @ x)
+    assert_close_vec(A.T @ x, ref @ x)
+    assert_same_matrix(A.tocsr(), ref)
+    # Neumann: the same with the boundary-face fluxes removed
+    interior = np.diff(Dr.tocsc().indptr) == 2
+    refn = (Dr @ sp.diags(MfI.diagonal() * interior) @ Dr.T).tocsr()
+    An = DCCellOperator(mesh, A.rho, neumann=True)
+    assert_close_vec(An @ x, refn @ x)
+    assert_same_matrix(An.tocsr(), refn)
+    # the on-the-fly variant (face masses generated from rho inside the kernel)
+    assert_close_vec(DCCellOperator(mesh, A.rho, cache_inverse_mass=False) @ x, ref @ x)
+    assert_close_vec(DCCellOperator(mesh, A.rho, neumann=True, cache_inverse_mass=False) @ x, refn @ x)
+    # several z-chunks and x-blocks
+    if mesh_name == "wide":
+        h = [rng.random(n) + 0.5 for n in (70, 9, 70)]
+        import discretize_b200 as dz
+
+        m2, g2 = dz.TensorMesh(h), T.Grid(h)
+        rho2 = np.exp(rng.standard_normal(m2.nC))
+        A2 = m2.face_divergence @ m2.get_face_inner_product(rho2, invert_matrix=True) @ m2.face_divergence.T
+        D2 = T.face_divergence(g2)
+        x2 = rng.standard_normal(m2.nC)
+        assert_close_vec(A2 @ x2, D2 @ (T.inner_product(g2, "F", rho2, invert_matrix=True) @ (D2.T @ x2)))

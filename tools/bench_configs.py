@@ -218,6 +218,27 @@ def config5(rows, n):
     o2 = torch.empty(mesh.nN, dtype=torch.float64, device=dev)
     ms = timeit(lambda: Adc.apply_device(phi, out=o2), 10, 3)
     report(rows, f"cfg2 {n}^3 DC G^T Me G fused ({type(Adc).__name__})", mesh.nN, 8.0 * (2 * mesh.nN + mesh.nC), ms)
+    D = mesh.face_divergence
+    Acc = D @ mesh.get_face_inner_product(sig, invert_matrix=True) @ D.T
+    xc = torch.randn(mesh.nC, dtype=torch.float64, device=dev)
+    o3 = torch.empty(mesh.nC, dtype=torch.float64, device=dev)
+    ms = timeit(lambda: Acc.apply_device(xc, out=o3), 10, 3)
+    report(rows, f"{n}^3 cell-centred DC D Mf(rho)^-1 D^T fused, cached 1/Mf ({type(Acc).__name__})", mesh.nC,
+           16.0 * mesh.nC + 8.0 * mesh.nF, ms)
+    Acc.cache_inverse_mass = False
+    ms = timeit(lambda: Acc.apply_device(xc, out=o3), 10, 3)
+    report(rows, f"{n}^3 cell-centred DC D Mf(rho)^-1 D^T fused, masses on the fly", mesh.nC, 24.0 * mesh.nC, ms)
+    MfI = mesh.get_face_inner_product(sig, invert_matrix=True)
+    t1 = torch.empty(mesh.nF, dtype=torch.float64, device=dev)
+    t2 = torch.empty(mesh.nF, dtype=torch.float64, device=dev)
+
+    def chain():
+        D.apply_device(xc, transpose=True, out=t1)
+        MfI.apply_device(t1, out=t2)
+        D.apply_device(t2, out=o3)
+
+    ms = timeit(chain, 10, 3)
+    report(rows, f"{n}^3 cell-centred DC as three applies (D, Mf^-1, D^T)", mesh.nC, 24.0 * mesh.nC, ms)
 
 
 def config_solver(rows, n):
