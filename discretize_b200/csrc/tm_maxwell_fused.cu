@@ -71,7 +71,9 @@ static int launch_mx_ring_t(const TM &m, const double *mui, const double *sigma,
     attr_done = true;
   }
   const int nNy = (int)m.ny + 1;
-  int kchunk = g_mx_kchunk;
+  // 64 planes per block is best at 512^3, 128 at 1024^3 (profiles/r1b_k9_sweep_1024.log): with four times as many
+  // (x, y) blocks the longer march amortises the ring fill without starving the grid
+  int kchunk = (g_mx_kchunk == 64 && xblocks * ((nNy + 1) / 2) >= 1500) ? 128 : g_mx_kchunk;
   const int nxy = xblocks * ((nNy + 1) / 2);
   const int zb_target = (4 * 148 + nxy - 1) / nxy;
   const int fair = (k_end - k_begin + zb_target - 1) / zb_target;

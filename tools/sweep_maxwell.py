@@ -26,7 +26,7 @@ lib.dzb_tune_maxwell_warps.restype = None
 alg = 8.0 * (2 * mesh.nE + 2 * mesh.nC)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ref = None
-cases = [(0, 0, 64)] + [(1, w, kc) for w in (9, 12, 18) for kc in (32, 64, 128)]
+cases = ([(0, 0, 64)] if n <= 512 else []) + [(1, w, kc) for w in ((9, 12, 18) if n <= 512 else (6, 9)) for kc in ((32, 64, 128) if n <= 512 else (32, 64, 128, 256))]
 for variant, w, kc in cases:
     lib.dzb_tune_maxwell(variant, kc)
     if w:
