@@ -11,6 +11,9 @@
 namespace dzb {
 
 constexpr int IT = 128;  // threads (= points) per tile
+#ifndef LOCATE_MINB
+#define LOCATE_MINB 8   // 64 registers; capping at 40 (12 blocks) spills and runs 17 % slower
+#endif
 
 struct AxisHit {
   i64 i1, i2;
@@ -105,7 +108,7 @@ __device__ __forceinline__ void entries(const AxisHit &hx, const AxisHit &hy, co
 // transposition buffers (13.8 KB) and 16 blocks = 64 warps stay resident per SM (the first version staged the
 // axes in 32 KB of shared memory and ran at 25 % occupancy: ncu, profiles/r1b_*).
 template <typename IDX>
-__global__ void __launch_bounds__(IT) k_interp_locate(Axes g, const double *__restrict__ pts, i64 npts, i64 col_offset,
+__global__ void __launch_bounds__(IT, LOCATE_MINB) k_interp_locate(Axes g, const double *__restrict__ pts, i64 npts, i64 col_offset,
                                                       IDX *__restrict__ cols, double *__restrict__ w) {
   extern __shared__ double smem[];
   double *sw = smem;                          // IT*9 weights (padded rows)
