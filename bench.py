@@ -7,8 +7,10 @@ apply over one synthetic field (phi ~ N(0,1), sigma log-normal).  "dof" = one ou
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 512]
 
-Under torchrun (N>1) every rank owns a z-slab of the same global mesh (strong scaling),
-halos exchanged over NCCL; timing = barrier + cuda sync, CUDA events, max over ranks.
+Under torchrun (N>1) every rank owns a z-slab: by default WEAK scaling -- each GPU keeps the N=1 workload (a 512^3
+slab of a 512 x 512 x 512N mesh) and exchanges one node plane with each neighbour per apply over NCCL; `--scaling
+strong` splits the 512^3 mesh itself; `--workload maxwell` is BASELINE config 5 (1024^3, strong scaling by
+definition).  Timing = barrier + cuda sync, CUDA events, max over ranks.
 `--impl reference` times the reference's own CPU path (scipy csr_matvec on the assembled
 G^T Me G) on a bounded sample of the same workload on the host cores.
 """
@@ -117,7 +119,7 @@ def run_reference(args):
     line = {
         "metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"TensorMesh 512^3 DC nodal G^T Me(sigma) G apply (CPU sample at {n_sample}^3)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -177,13 +179,19 @@ def run_ours(args):
     else:
         from discretize_b200.slab import SlabDCNodal
 
-        op = SlabDCNodal(n, n, n, rank, world, seed_phi=5, seed_sigma=6)
+        # weak scaling (default): every rank owns the N=1 workload, a 512^3 slab of a 512 x 512 x (512 N) mesh, and
+        # exchanges one node plane with each neighbour per apply; --scaling strong splits the 512^3 mesh itself
+        # (66 us of kernel time per rank at N=8: latency-bound, profiles/r1_scale_dc_512_n1248.jsonl)
+        nz_global = n * world if args.scaling == "weak" else n
+        op = SlabDCNodal(n, n, nz_global, rank, world, seed_phi=5, seed_sigma=6)
         step = op.step_graphed if not args.eager else op.step
-        ndof_total = (n + 1) ** 3
-        alg_bytes = 8.0 * (2 * (n + 1) ** 3 + n ** 3) / world
+        ndof_total = (n + 1) ** 2 * (nz_global + 1)
+        alg_bytes = 8.0 * (2 * ndof_total + n * n * nz_global) / world
         launches_per_step = op.launches_per_step
-        parallelism = f"z-slabs x{world}, NCCL halo send/recv"
-        workload_name = f"TensorMesh {n}^3 DC-resistivity nodal operator G^T Me(sigma) G matrix-free apply"
+        parallelism = f"z-slabs x{world} ({args.scaling} scaling), NCCL halo send/recv"
+        workload_name = (f"TensorMesh {n}x{n}x{nz_global} DC-resistivity nodal operator G^T Me(sigma) G matrix-free apply"
+                         f" ({n}^3 per GPU)" if args.scaling == "weak" else
+                         f"TensorMesh {n}^3 DC-resistivity nodal operator G^T Me(sigma) G matrix-free apply")
         kernel_name = "k_dc_nodal_ring<4,NWC,PARX>"
 
     def sync():
@@ -233,6 +241,37 @@ def run_ours(args):
                "d2h_bytes_per_step": int(8 * mesh.nN), "ms_per_step": dt * 1e3,
                "api": "A = G.T @ mesh.get_edge_inner_product(sigma) @ G; A.matvec(x_host_pinned, out=y_host_pinned)"}
 
+    if world > 1 and args.workload == "dc":
+        # every rank streams ITS slab from / to pinned host memory: H2D of the owned planes, the distributed apply
+        # (halo exchange + kernels, eager launches), D2H of the owned result -- wall clock, max over ranks
+        L = op.layout
+        own = slice(L.p_own0 * L.plane, L.p_own1 * L.plane)
+        host_in = torch.empty(op.phi[own].numel(), dtype=torch.float64).pin_memory()
+        host_in.copy_(op.phi[own])
+        host_out = torch.empty_like(host_in).pin_memory()
+        e2e_steps = max(2, min(args.steps, 10))
+
+        def e2e_step():
+            op.phi[own].copy_(host_in, non_blocking=True)
+            op.step()
+            host_out.copy_(op.owned_output(), non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        sync()
+        tt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+        nb = torch.tensor([8.0 * host_in.numel()], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nb)
+        dt = float(tt.item())
+        e2e = {"value": ndof_total / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(nb.item()),
+               "d2h_bytes_per_step": int(nb.item()), "ms_per_step": dt * 1e3,
+               "api": "per rank: slab.phi[owned] <- pinned host, SlabDCNodal.step() (NCCL halo + K8), pinned host <- owned output"}
+
     def shutdown():
         # A process group that was captured into a CUDA graph can hang in destroy_process_group();
         # every rank has its result by now, so leave without tearing NCCL down.
@@ -249,7 +288,8 @@ def run_ours(args):
     achieved = alg_bytes / (ms_step * 1e-3) / 1e9  # per-GPU GB/s of the dominant kernel's algorithmic bytes
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name,
                    "dofs_per_step": int(ndof_total), "parallelism": parallelism,
@@ -288,10 +328,15 @@ def main():
                     help="dc = configs[1] (the N=1 headline); maxwell = configs[4], the 1024^3 z-slab scaling case")
     ap.add_argument("--cpu-n", type=int, default=128, help="cells per axis of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="N > 1: weak = every GPU owns the N=1 workload (default for dc), strong = the N=1 mesh is split "
+                         "(default for maxwell: BASELINE config 5 is the 1024^3 mesh on 2/4/8 GPUs)")
     ap.add_argument("--eager", action="store_true", help="multi-GPU: launch every step from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.n is None:
         args.n = 512 if args.workload == "dc" else 1024
+    if args.scaling is None:
+        args.scaling = "weak" if args.workload == "dc" else "strong"
     if args.impl == "reference":
         run_reference(args)
     else:
