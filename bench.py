@@ -252,9 +252,7 @@ def run_ours(args):
         e2e_steps = max(2, min(args.steps, 10))
 
         def e2e_step():
-            op.phi[own].copy_(host_in, non_blocking=True)
-            op.step()
-            host_out.copy_(op.owned_output(), non_blocking=True)
+            op.step_from_host(host_in, host_out)
 
         for _ in range(2):
             e2e_step()
@@ -270,7 +268,8 @@ def run_ours(args):
         dt = float(tt.item())
         e2e = {"value": ndof_total / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(nb.item()),
                "d2h_bytes_per_step": int(nb.item()), "ms_per_step": dt * 1e3,
-               "api": "per rank: slab.phi[owned] <- pinned host, SlabDCNodal.step() (NCCL halo + K8), pinned host <- owned output"}
+               "api": "per rank: SlabDCNodal.step_from_host(x_host_pinned, y_host_pinned): outer planes up, NCCL halo "
+                      "exchange, then H2D / K8 / D2H pipelined over z-chunks"}
 
     def shutdown():
         # A process group that was captured into a CUDA graph can hang in destroy_process_group();

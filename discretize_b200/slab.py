@@ -165,6 +165,57 @@ class SlabDCNodal(_GraphedStep):
         L = self.layout
         return self.out[L.p_own0 * L.plane:L.p_own1 * L.plane]
 
+    def step_from_host(self, host_in, host_out, nchunks=16):
+        """One distributed apply with this rank's owned planes in PINNED HOST memory (``host_in`` -> ``host_out``, both
+        ``n_owned_nodes`` long): the two outermost owned planes go up first so that the halo exchange can start,
+        then z-chunks stream through -- H2D of chunk c+1, kernel on chunk c, D2H of chunk c-1 overlap."""
+        L, op, P = self.layout, self.op, self.layout.plane
+        if getattr(self, "_host_streams", None) is None:
+            dev = self.phi.device
+            self._host_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        s_in, s_out = self._host_streams
+        main = torch.cuda.current_stream()
+        o0, o1 = L.p_own0, L.p_own1
+        nchunks = max(1, min(nchunks, o1 - o0))
+        cuts = [o0 + round(c * (o1 - o0) / nchunks) for c in range(nchunks + 1)]
+
+        def h2d(a, b):   # local planes [a, b)
+            self.phi[a * P:b * P].copy_(host_in[(a - o0) * P:(b - o0) * P], non_blocking=True)
+
+        s_in.wait_stream(main)
+        copied = []
+        with torch.cuda.stream(s_in):
+            h2d(o0, o0 + 1)
+            if o1 - 1 > o0:
+                h2d(o1 - 1, o1)
+            edge = torch.cuda.Event()
+            edge.record(s_in)
+        if L.world > 1:
+            self.comm_stream.wait_event(edge)
+            with torch.cuda.stream(self.comm_stream):
+                for r in exchange_node_halos(self.phi, L):
+                    r.wait()
+        with torch.cuda.stream(s_in):
+            for c in range(nchunks):
+                h2d(cuts[c], cuts[c + 1])
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+                copied.append(ev)
+        s_out.wait_stream(main)
+        for c in range(nchunks):
+            main.wait_event(copied[min(c + 1, nchunks - 1)])     # chunk c reads the first plane of chunk c + 1
+            if L.world > 1 and (c == 0 or c == nchunks - 1):
+                main.wait_stream(self.comm_stream)               # the halo planes border the first / last chunk
+            op.apply_planes(self.phi, self.out, cuts[c], cuts[c + 1])
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                host_out[(cuts[c] - o0) * P:(cuts[c + 1] - o0) * P].copy_(self.out[cuts[c] * P:cuts[c + 1] * P],
+                                                                          non_blocking=True)
+        main.wait_stream(s_out)
+        return host_out
+
 
 # ---------------------------------------------------------------------------------------------------
 # Maxwell:  y = C^T Mf(mui) C e + Me(sigma) e   (BASELINE config 5)

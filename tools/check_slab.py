@@ -28,6 +28,20 @@ for (nx, ny, nz) in ((40, 33, 29), (70, 20, 64), (512, 64, 96)):
     err = float((got - ref).abs().max() / ref.abs().max())
     print(f"rank {rank}/{world} mesh {nx}x{ny}x{nz} owned planes {part.layout.p_own1 - part.layout.p_own0} rel err {err:.2e}", flush=True)
     ok = ok and err == 0.0
+    # the same apply with the owned planes living in pinned host memory (bench.py's e2e leg at N > 1)
+    L = part.layout
+    own = slice(L.p_own0 * L.plane, L.p_own1 * L.plane)
+    host_in = torch.empty(part.phi[own].numel(), dtype=torch.float64).pin_memory()
+    host_in.copy_(part.phi[own])
+    host_out = torch.empty_like(host_in).pin_memory()
+    part.phi.zero_()
+    part.out.zero_()
+    torch.cuda.synchronize()
+    part.step_from_host(host_in, host_out, nchunks=5)
+    torch.cuda.synchronize()
+    err_h = float((host_out - ref.cpu()).abs().max() / ref.abs().max())
+    print(f"rank {rank}/{world} mesh {nx}x{ny}x{nz} step_from_host rel err {err_h:.2e}", flush=True)
+    ok = ok and err_h == 0.0
 for (nx, ny, nz) in ((40, 33, 29), (70, 20, 64), (300, 64, 96)):
     rng = np.random.default_rng(2)
     h = (rng.random(nx) + 0.5, rng.random(ny) + 0.5, rng.random(nz) + 0.5)
