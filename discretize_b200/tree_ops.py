@@ -11,6 +11,29 @@ from ._lib import check, load
 from .operators import Operator, cuda_device, ptr, stream_ptr, to_device
 
 
+def encode_parts_raw(geoms, parts, shape):
+    """Like ``encode_parts`` for parts that hold DUPLICATE (row, column) pairs on purpose (ghost columns redirected by
+    ``tree_shard``): entries are concatenated row by row, never summed."""
+    tab_mult, tab_sel = [], []
+    rows, cols, codes = [], [], []
+    for s_, M in parts:
+        M = sp.csr_matrix(M)
+        vals, inv = np.unique(np.round(M.data, 14), return_inverse=True)
+        base = len(tab_mult)
+        tab_mult.extend(vals.tolist())
+        tab_sel.extend([s_] * vals.size)
+        rows.append(np.repeat(np.arange(M.shape[0]), np.diff(M.indptr)))
+        cols.append(M.indices)
+        codes.append(inv + base)
+    if len(tab_mult) > 256:
+        raise ValueError(f"operator needs {len(tab_mult)} distinct (multiplier, selector) pairs; the code byte holds 256")
+    rows, cols, codes = np.concatenate(rows), np.concatenate(cols), np.concatenate(codes)
+    order = np.lexsort((cols, rows))
+    indptr = np.r_[0, np.cumsum(np.bincount(rows, minlength=shape[0]))].astype(np.int64)
+    return (indptr, cols[order].astype(np.int32), codes[order].astype(np.uint8), np.array(tab_mult, dtype=np.float64),
+            np.array(tab_sel, dtype=np.uint8))
+
+
 def encode_parts(geoms, parts, shape):
     """Merge ``sum_s diag(geom_s) @ M_s`` into one CSR with a code byte per entry.
 
@@ -41,8 +64,8 @@ def encode_parts(geoms, parts, shape):
 class CodedCsr:
     """Device-resident coded CSR (one direction of an operator)."""
 
-    def __init__(self, geoms, parts, shape, geom_by_col):
-        indptr, indices, codes, tmult, tsel = encode_parts(geoms, parts, shape)
+    def __init__(self, geoms, parts, shape, geom_by_col, canonical=True):
+        indptr, indices, codes, tmult, tsel = (encode_parts if canonical else encode_parts_raw)(geoms, parts, shape)
         self.shape = shape
         self.nnz = int(indptr[-1])
         self.is64 = self.nnz >= 2**31 - 1

@@ -231,12 +231,18 @@ class TreeShard:
         else:
             lgeoms = [np.ascontiguousarray(g[rows]) for g in geoms]
         lo = LocalOperator(lgeoms, lparts, (rows.size, local_cols_global.size), plan, bool(transposed))
+        # rows that read a ghost column: the only ones that have to wait for the exchange
+        touches = np.zeros(rows.size, dtype=bool)
+        for _, Ml in lparts:
+            ghost_entry = Ml.indices >= cols_owned.size
+            touches |= np.add.reduceat(np.r_[ghost_entry, False].astype(np.int64), Ml.indptr[:-1])[:rows.size] * (np.diff(Ml.indptr) > 0) > 0
+        lo.boundary_rows = np.nonzero(touches)[0]
         self._local_ops[key] = lo
         return lo
 
-    def operator(self, name, transposed=False):
+    def operator(self, name, transposed=False, overlap=True):
         """The device operator of this rank (CUDA): ``ShardedTreeOperator``."""
-        return ShardedTreeOperator(self, name, transposed)
+        return ShardedTreeOperator(self, name, transposed, overlap)
 
 
 def _graphed_mixin():
@@ -254,7 +260,7 @@ class ShardedTreeOperator(_graphed_mixin()):
     ``step_graphed()`` replays pack + exchange + SpMV as one CUDA graph, because at a few hundred microseconds
     per apply the Python enqueue cost of the three pieces is not negligible."""
 
-    def __init__(self, shard: TreeShard, name, transposed=False):
+    def __init__(self, shard: TreeShard, name, transposed=False, overlap=True):
         from .operators import cuda_device
         from .tree_ops import CodedCsr
 
@@ -267,6 +273,26 @@ class ShardedTreeOperator(_graphed_mixin()):
         self.buf = torch.zeros(lo.shape[1], dtype=torch.float64, device=dev)
         self.send_buf = torch.empty(int(lo.plan.send_off[-1]), dtype=torch.float64, device=dev)
         self.out = torch.empty(lo.shape[0], dtype=torch.float64, device=dev)
+        # Overlap of the ghost exchange with the SpMV: `csr_early` is the local operator with every ghost column
+        # redirected to column 0 (same row lengths, so the ELL layout survives; it never reads the ghost tail), run
+        # while the exchange is in flight; the few rows that really touch a ghost (`bnd_rows`, a surface effect) are
+        # then recomputed by `csr_bnd` and scattered over the early result.
+        self.csr_early = self.csr_bnd = self.bnd_rows = None
+        nb = lo.boundary_rows.size
+        if overlap and lo.plan.n_ghost > 0 and 0 < nb < lo.shape[0]:
+            n_owned = lo.plan.n_owned
+            early = []
+            for s_, M in lo.parts:
+                Me = sp.csr_matrix((M.data, np.where(M.indices >= n_owned, 0, M.indices), M.indptr), shape=M.shape)
+                early.append((s_, Me))
+            self.csr_early = CodedCsr(lo.geoms, early, lo.shape, geom_by_col=lo.geom_by_col, canonical=False)
+            br = lo.boundary_rows
+            bgeoms = lo.geoms if lo.geom_by_col else [np.ascontiguousarray(g[br]) for g in lo.geoms]
+            self.csr_bnd = CodedCsr(bgeoms, [(s_, sp.csr_matrix(M[br])) for s_, M in lo.parts], (nb, lo.shape[1]),
+                                    geom_by_col=lo.geom_by_col)
+            self.bnd_rows = torch.as_tensor(br.astype(np.int64), device=dev)
+            self.out_bnd = torch.empty(nb, dtype=torch.float64, device=dev)
+            self.comm_stream = torch.cuda.Stream(device=dev)
 
     def apply(self, x_owned, out=None, group=None):
         if out is None:
@@ -275,6 +301,11 @@ class ShardedTreeOperator(_graphed_mixin()):
         if x_owned.numel() != n:
             raise ValueError(f"expected this rank's {n} owned entries, got {x_owned.numel()}")
         self.buf[:n].copy_(x_owned)
+        if self.csr_early is not None:
+            res = self.step(group)
+            if out is not self.out:
+                out.copy_(res)
+            return out
         for r in self.plan.exchange(self.buf, self.send_buf, group):
             r.wait()
         self.csr.apply(self.buf, out)
@@ -285,9 +316,20 @@ class ShardedTreeOperator(_graphed_mixin()):
         return self.buf[:self.plan.n_owned]
 
     def step(self, group=None):
-        for r in self.plan.exchange(self.buf, self.send_buf, group):
-            r.wait()
-        self.csr.apply(self.buf, self.out)
+        if self.csr_early is None:
+            for r in self.plan.exchange(self.buf, self.send_buf, group):
+                r.wait()
+            self.csr.apply(self.buf, self.out)
+            return self.out
+        main = torch.cuda.current_stream()
+        self.comm_stream.wait_stream(main)
+        with torch.cuda.stream(self.comm_stream):
+            for r in self.plan.exchange(self.buf, self.send_buf, group):
+                r.wait()
+        self.csr_early.apply(self.buf, self.out)              # all rows, ghost columns redirected: no ghost reads
+        main.wait_stream(self.comm_stream)
+        self.csr_bnd.apply(self.buf, self.out_bnd)             # the rows that need the ghosts
+        self.out.index_copy_(0, self.bnd_rows, self.out_bnd)
         return self.out
 
     def bytes_per_apply(self):
@@ -295,4 +337,4 @@ class ShardedTreeOperator(_graphed_mixin()):
 
     @property
     def T(self):
-        return ShardedTreeOperator(self.shard, self.name, not self.transposed)
+        return ShardedTreeOperator(self.shard, self.name, not self.transposed, self.csr_early is not None)

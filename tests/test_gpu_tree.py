@@ -146,10 +146,18 @@ def test_sharded_tree_operators_loopback(gold, world):
                         lo = dst.plan.n_owned + int(dst.plan.ghost_off[p])
                         dst.buf[lo:lo + idx.size] = op.buf[torch.as_tensor(idx).cuda()]
             y = np.zeros(ref.shape[0])
+            y2 = np.zeros(ref.shape[0])
             for s, op in zip(shards, ops):
                 op.csr.apply(op.buf, op.out)
                 y[s.owned(kout)] = op.out.cpu().numpy()
+                if op.csr_early is not None:       # the overlap path: early pass without ghost reads + boundary rows
+                    op.out.fill_(float("nan"))
+                    op.csr_early.apply(op.buf, op.out)
+                    op.csr_bnd.apply(op.buf, op.out_bnd)
+                    op.out.index_copy_(0, op.bnd_rows, op.out_bnd)
+                y2[s.owned(kout)] = op.out.cpu().numpy()
             assert_close_vec(y, ref @ x)
+            assert_close_vec(y2, ref @ x)
 
 
 @pytest.mark.parametrize("name", ["face_divergence", "average_edge_to_cell", "edge_curl", "nodal_gradient"])
