@@ -772,8 +772,93 @@ class TreeMesh:
 
         return make_tree_mass_deriv(self, "E", model, do_fast, invert_model, invert_matrix)
 
+    # ---- point location and interpolation (node variant) -----------------------------------------------
+    def _containing_cells(self, points):
+        """Index of the leaf that contains (or is closest to) each point -- tree.cpp:758-766, 1499-1516: the root is
+        found with ``x >= upper edge -> next root`` (ties go high), the descent with ``x > centre -> high child``
+        (ties go low); points outside the mesh end in a boundary cell.  Vectorised level by level."""
+        tr = self._tree
+        pts = np.asarray(points, dtype=np.float64)
+        n = pts.shape[0]
+        c = np.zeros((n, 3), dtype=np.int64)
+        for d in range(3):
+            edges = self._xs[d][2 * tr.rw * np.arange(1, tr.roots[d])]          # interior root boundaries
+            c[:, d] = np.searchsorted(edges, pts[:, d], side="right")
+        lo = np.zeros((n, 3), dtype=np.int64)
+        done = np.zeros(n, dtype=bool)
+        for l in range(tr.root_level, tr.max_level + 1):
+            w = tr.level_width(l)
+            act = np.nonzero(~done)[0]
+            if not act.size:
+                break
+            if l < tr.max_level and tr.div[l].size:
+                isdiv = np.isin(tr.pack(l, c[act]), tr.div[l])
+            else:
+                isdiv = np.zeros(act.size, dtype=bool)
+            leaf = act[~isdiv]
+            lo[leaf] = c[leaf] * w
+            done[leaf] = True
+            go = act[isdiv]
+            if go.size:
+                for d in range(3):
+                    mid = self._xs[d][2 * c[go, d] * w + w]                       # the node in the middle of the cell
+                    c[go, d] = 2 * c[go, d] + (pts[go, d] > mid)
+        leaf_lo, _ = tr.leaves()
+        return np.searchsorted(tr.keys(leaf_lo), tr.keys(lo))
+
+    def point2index(self, locs):
+        """reference: tree_mesh.py:984-986 (index of the cell containing each point)."""
+        return self._containing_cells(as_array_n_by_dim(np.asarray(locs, dtype=np.float64), 3))
+
     def get_interpolation_matrix(self, loc, location_type="cell_centers", zeros_outside=False, **kwargs):
-        raise NotImplementedError("TreeMesh.get_interpolation_matrix is not part of the five target configurations (SURVEY N3)")
+        """Trilinear interpolation from the NODES of the containing cell, hanging nodes eliminated (``_getNodeIntMat``,
+        tree_ext.pyx:6116-6179).  The edge / face / cell-centre variants of the reference depend on the order of the
+        points (direction-swap state carried across loop iterations) and leave rows uninitialised with
+        ``zeros_outside``: not reproduced."""
+        if "locType" in kwargs:
+            raise TypeError("The locType keyword argument has been removed, please use location_type. "
+                            "This will be removed in discretize 1.0.0")
+        if "zerosOutside" in kwargs:
+            raise TypeError("The zerosOutside keyword argument has been removed, please use zeros_outside. "
+                            "This will be removed in discretize 1.0.0")
+        if kwargs:
+            raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
+        lt = {"N": "nodes", "nodes": "nodes"}.get(location_type)
+        if lt is None:
+            raise NotImplementedError(
+                f"TreeMesh.get_interpolation_matrix(location_type={location_type!r}): only 'nodes' is built (SURVEY N3)")
+        from .csr import CsrOperator
+
+        return CsrOperator(self._host_node_interpolation(loc, zeros_outside))
+
+    def _host_node_interpolation(self, loc, zeros_outside):
+        t = self._t()
+        pts = as_array_n_by_dim(np.asarray(loc, dtype=np.float64), 3)
+        npts = pts.shape[0]
+        cell = self._containing_cells(pts)
+        cen, hw = t.centers[cell], t.half[cell]
+        w = []
+        for d in range(3):
+            x0, x1 = self._xs[d][cen[:, d] - hw], self._xs[d][cen[:, d] + hw]
+            w.append((x1 - pts[:, d]) / (x1 - x0))
+        eps = 100 * np.finfo(float).eps
+        outside = np.zeros(npts, dtype=bool)
+        if zeros_outside:
+            for wd in w:
+                outside |= (wd < -eps) | (wd > 1 + eps)
+        w = [np.clip(wd, 0.0, 1.0) for wd in w]
+        rows = np.repeat(np.arange(npts), 8)
+        cols = t.nodes.index[t.cell_nodes[cell]]                                  # (npts, 8), x fastest
+        vals = np.empty((npts, 8))
+        for ii in range(8):
+            fx = w[0] if not (ii & 1) else 1.0 - w[0]
+            fy = w[1] if not (ii & 2) else 1.0 - w[1]
+            fz = w[2] if not (ii & 4) else 1.0 - w[2]
+            vals[:, ii] = fx * fy * fz
+        cols = np.where(outside[:, None], 0, cols)
+        vals = np.where(outside[:, None], 0.0, vals)
+        A = sp.csr_matrix((vals.reshape(-1), (rows, cols.reshape(-1))), shape=(npts, t.nodes.n_total))
+        return (A @ self._deflate_nodes()).tocsr()
 
     def __repr__(self):
         n = self._topo.n_cells if self._finalized else self._tree.n_leaves

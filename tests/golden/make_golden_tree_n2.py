@@ -36,6 +36,17 @@ def main():
         mats += [(name, getattr(mesh, name)()) for name in TREE_CC_METHODS]
         for k, ind in enumerate(mesh.face_boundary_indices):
             out[f"{tag}_face_boundary_{k}"] = np.asarray(ind, dtype=np.int64)
+        # node interpolation and point location (tree_ext.pyx:6116-6179, tree.cpp:758-766): random points, some outside
+        # the mesh, some exactly on nodes / cell centres
+        rng = np.random.default_rng(123 + len(out))
+        ext = np.array([x.sum() for x in h])
+        ipts = g[f"{tag}_origin"] + ext * (rng.random((120, 3)) * 1.2 - 0.1)
+        ipts[:20] = mesh.nodes[rng.integers(0, mesh.nN, 20)]
+        ipts[20:40] = mesh.cell_centers[rng.integers(0, mesh.nC, 20)]
+        out[f"{tag}_interp_pts"] = ipts
+        out[f"{tag}_point2index"] = np.asarray(mesh.point2index(ipts), dtype=np.int64)
+        mats += [("interp_N", mesh.get_interpolation_matrix(ipts, "N")),
+                 ("interp_N_zeros_outside", mesh.get_interpolation_matrix(ipts, "N", zeros_outside=True))]
         for name, mat in mats:
             m = sp.csr_matrix(mat).copy()
             m.sum_duplicates()

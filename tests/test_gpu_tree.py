@@ -219,3 +219,18 @@ def test_tree_cell_centred_operators(gold, tag):
         if name in TREE_CC_COMPOSITES:      # products: compare without stored zeros (scipy prunes differently per route)
             a.eliminate_zeros(); b.eliminate_zeros()
         assert_same_matrix(a, b)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_tree_node_interpolation(gold, tag):
+    g2 = load_golden("tree_n2_small.npz")
+    m = _mesh_from_fixture(gold, tag, "refine")
+    pts = g2[f"{tag}_interp_pts"]
+    rng = np.random.default_rng(16)
+    for zo, key in ((False, "interp_N"), (True, "interp_N_zeros_outside")):
+        ref = golden_matrix(g2, f"{tag}_{key}")
+        Q = m.get_interpolation_matrix(pts, "N", zeros_outside=zo)
+        x, y = rng.standard_normal(ref.shape[1]), rng.standard_normal(ref.shape[0])
+        assert_close_vec(Q @ x, ref @ x)
+        assert_close_vec(Q.T @ y, ref.T @ y)
+        assert_same_matrix(Q.tocsr(), ref)

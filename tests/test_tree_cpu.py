@@ -125,3 +125,19 @@ def test_tree_cell_centred_operators_match_reference_fixture(gold, tag):
         np.testing.assert_array_equal(ind, g2[f"{tag}_face_boundary_{k}"])
     A = m._host_matrix("average_cell_to_face")
     np.testing.assert_allclose(A @ np.ones(m.nC), 1.0, rtol=1e-13)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_tree_point_location_and_node_interpolation_match_reference_fixture(gold, tag):
+    """point2index (tree.cpp:758-766, 1499-1516: ties go high between roots, low inside) and the node interpolation
+    matrix with hanging nodes eliminated (tree_ext.pyx:6116-6179), points on nodes / centres / outside included."""
+    g2 = load_golden("tree_n2_small.npz")
+    m = _mesh_from_fixture(gold, tag, "refine")
+    pts = g2[f"{tag}_interp_pts"]
+    np.testing.assert_array_equal(m.point2index(pts), g2[f"{tag}_point2index"])
+    assert_same_matrix(m._host_node_interpolation(pts, False), golden_matrix(g2, f"{tag}_interp_N"), 1e-13)
+    assert_same_matrix(m._host_node_interpolation(pts, True), golden_matrix(g2, f"{tag}_interp_N_zeros_outside"), 1e-13)
+    with pytest.raises(NotImplementedError):
+        m.get_interpolation_matrix(pts, "Ex")
+    with pytest.raises(TypeError):
+        m.get_interpolation_matrix(pts, "N", locType="N")
