@@ -292,6 +292,31 @@ def _tree_tensor_mass_matrix(mesh, proj, model, invert_model):
     return acc
 
 
+def _tree_tensor_mass_deriv_matrix(mesh, proj, v):
+    """d(M(m) v)/dm for a full-tensor model on a TreeMesh: n x 6 nC (operators/inner_products.py:459-565, 3-D tensorType 3,
+    with the OcTree corner projections of tree_ext.pyx:5651-5763), host assembly.  With VP_n = sqrt(V/8) P_n and
+    (y1, y2, y3) = VP_n v the six column blocks are  VP_n^T [y1;0;0], [0;y2;0], [0;0;y3], [y2;y1;0], [y3;0;y1], [0;y3;y2]."""
+    nC = mesh.n_cells
+    v = np.asarray(v, dtype=np.float64).reshape(-1)
+    sq = sp.diags(np.tile(np.sqrt(0.125 * mesh.cell_volumes), 3))
+    d = lambda a: sp.diags(a)
+    Z = sp.csr_matrix((nC, nC))
+    blocks = [None] * 6
+    for P in _tree_corner_projections(mesh, proj):
+        VP = (sq @ P).tocsr()
+        Y = VP @ v
+        y1, y2, y3 = Y[:nC], Y[nC:2 * nC], Y[2 * nC:]
+        stacks = [sp.vstack((d(y1), Z, Z)), sp.vstack((Z, d(y2), Z)), sp.vstack((Z, Z, d(y3))),
+                  sp.vstack((d(y2), d(y1), Z)), sp.vstack((d(y3), Z, d(y1))), sp.vstack((Z, d(y3), d(y2)))]
+        for q in range(6):
+            term = VP.T @ stacks[q]
+            blocks[q] = term if blocks[q] is None else blocks[q] + term
+    out = sp.hstack(blocks).tocsr()
+    out.sum_duplicates()
+    out.sort_indices()
+    return out
+
+
 class TreeMassDerivDiag(Operator):
     """F(v) = d(M(m) v)/dm for diagonal (scalar / isotropic / anisotropic) models on a TreeMesh
     (base/base_tensor_mesh.py:865-988 with the tree averages): F(v) = diag(v r) (k Av^T) diag(V c)."""
@@ -367,7 +392,18 @@ def make_tree_mass_deriv(mesh, proj, model, do_fast, invert_model, invert_matrix
     if md.tt == -1:
         return None
     if md.kind == _lib.MODEL_TENSOR:
-        raise NotImplementedError("full-tensor model derivatives on TreeMesh are not built yet")
+        if invert_model or invert_matrix:
+            raise NotImplementedError(
+                "inverting the property or the matrix is not yet implemented for this mesh/tensorType. You should write it!")
+        from .csr import CsrOperator
+
+        def tensor_deriv(v=None):
+            if v is None:
+                raise Exception("v must be supplied for this implementation.")
+            host = v.cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+            return CsrOperator(_tree_tensor_mass_deriv_matrix(mesh, proj, host))
+
+        return tensor_deriv
     nC = mesh.n_cells
     if md.tt == 0:
         if invert_model and not invert_matrix:

@@ -47,6 +47,9 @@ def main():
         out[f"{tag}_point2index"] = np.asarray(mesh.point2index(ipts), dtype=np.int64)
         mats += [("interp_N", mesh.get_interpolation_matrix(ipts, "N")),
                  ("interp_N_zeros_outside", mesh.get_interpolation_matrix(ipts, "N", zeros_outside=True))]
+        # full-tensor model derivatives (operators/inner_products.py:459-565 with the OcTree corner projections)
+        mats += [("dMf_tensor", mesh.get_face_inner_product_deriv(g[f"{tag}_sigma6"])(g[f"{tag}_vF"])),
+                 ("dMe_tensor", mesh.get_edge_inner_product_deriv(g[f"{tag}_sigma6"])(g[f"{tag}_vE"]))]
         for name, mat in mats:
             m = sp.csr_matrix(mat).copy()
             m.sum_duplicates()

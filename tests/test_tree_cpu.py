@@ -141,3 +141,16 @@ def test_tree_point_location_and_node_interpolation_match_reference_fixture(gold
         m.get_interpolation_matrix(pts, "Ex")
     with pytest.raises(TypeError):
         m.get_interpolation_matrix(pts, "N", locType="N")
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_tree_tensor_model_derivative_matches_reference_fixture(gold, tag):
+    from discretize_b200.tree_ops import _tree_tensor_mass_deriv_matrix
+
+    g2 = load_golden("tree_n2_small.npz")
+    m = _mesh_from_fixture(gold, tag, "state")
+    for proj, key, v in (("F", "dMf_tensor", gold[f"{tag}_vF"]), ("E", "dMe_tensor", gold[f"{tag}_vE"])):
+        a = _tree_tensor_mass_deriv_matrix(m, proj, v)
+        b = golden_matrix(g2, f"{tag}_{key}")
+        a.eliminate_zeros(); b.eliminate_zeros()     # the reference's sums of products keep some exact zeros
+        assert_same_matrix(a, b, 1e-12)
