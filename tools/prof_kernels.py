@@ -1,4 +1,4 @@
-"""Two launches of every non-fused kernel family at out-of-cache sizes, for `ncu --set full -k regex:...`.
+"""One launch of every non-fused kernel family at out-of-cache sizes, for `ncu --set full -k regex:...`.
 
   python tools/prof_kernels.py [--which elem,mass,interp,tree] [--n 512] [--tree-pts 48000] [--interp-pts 20000000]
 """
@@ -13,7 +13,7 @@ import torch
 import discretize_b200 as dz
 
 
-def twice(op, x):
+def once(op, x):
     out = torch.empty(op.shape[0], dtype=torch.float64, device=x.device)
     for _ in range(1):
         op.apply_device(x, out=out)
@@ -33,25 +33,25 @@ def main():
     mesh = dz.TensorMesh([a.n] * 3)
     if "elem" in which:
         u = torch.randn(mesh.nF, dtype=torch.float64, device=dev)
-        twice(mesh.face_divergence, u)                       # k_apply<DIV>
-        e = twice(mesh.face_divergence.T, torch.randn(mesh.nC, dtype=torch.float64, device=dev))  # k_apply3<DIV^T>
+        once(mesh.face_divergence, u)                       # k_apply<DIV>
+        e = once(mesh.face_divergence.T, torch.randn(mesh.nC, dtype=torch.float64, device=dev))  # k_apply3<DIV^T>
         del e
         phi = torch.randn(mesh.nN, dtype=torch.float64, device=dev)
-        e = twice(mesh.nodal_gradient, phi)                  # k_apply3<GRAD>
+        e = once(mesh.nodal_gradient, phi)                  # k_apply3<GRAD>
         del phi
-        twice(mesh.edge_curl, e)                             # k_apply3<CURL>
-        twice(mesh.nodal_gradient.T, e)                      # k_apply<GRAD^T>
-        twice(mesh.average_edge_to_cell, e)
+        once(mesh.edge_curl, e)                             # k_apply3<CURL>
+        once(mesh.nodal_gradient.T, e)                      # k_apply<GRAD^T>
+        once(mesh.average_edge_to_cell, e)
         del e, u
         torch.cuda.empty_cache()
     if "mass" in which:
         sig = torch.rand(mesh.nC, dtype=torch.float64, device=dev) + 0.5
         u = torch.randn(mesh.nF, dtype=torch.float64, device=dev)
-        twice(mesh.get_face_inner_product(sig), u)
-        twice(mesh.get_face_inner_product(torch.rand((mesh.nC, 3), dtype=torch.float64, device=dev) + 0.5), u)
+        once(mesh.get_face_inner_product(sig), u)
+        once(mesh.get_face_inner_product(torch.rand((mesh.nC, 3), dtype=torch.float64, device=dev) + 0.5), u)
         dM = mesh.get_face_inner_product_deriv(sig)(u)
-        twice(dM, torch.randn(mesh.nC, dtype=torch.float64, device=dev))
-        twice(dM.T, u)
+        once(dM, torch.randn(mesh.nC, dtype=torch.float64, device=dev))
+        once(dM.T, u)
         del sig, u, dM
         torch.cuda.empty_cache()
     if "interp" in which:
@@ -63,9 +63,9 @@ def main():
         Q = mesh.get_interpolation_matrix(pts, "Ex")
         Q._locate()
         v = torch.randn(Q.shape[1], dtype=torch.float64, device=dev)
-        twice(Q, v)
-        twice(Q.T, torch.randn(a.interp_pts, dtype=torch.float64, device=dev))
-        twice(make_interpolation_operator(mesh, pts, "Ex", store=False), v)
+        once(Q, v)
+        once(Q.T, torch.randn(a.interp_pts, dtype=torch.float64, device=dev))
+        once(make_interpolation_operator(mesh, pts, "Ex", store=False), v)
         del Q, v, pts
         torch.cuda.empty_cache()
     if "tree" in which:
@@ -74,7 +74,7 @@ def main():
         m.refine_points(pts, -1, [2, 2, 2], finalize=True)
         for name in ("face_divergence", "edge_curl", "average_node_to_cell", "nodal_gradient"):
             op = getattr(m, name)
-            twice(op, torch.randn(op.shape[1], dtype=torch.float64, device=dev))
+            once(op, torch.randn(op.shape[1], dtype=torch.float64, device=dev))
             m._cache.pop("P_" + name, None); m._cache.pop("H_" + name, None); m._cache.pop("OP_" + name, None)
             del op
     print("prof_kernels done")
