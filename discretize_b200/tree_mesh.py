@@ -174,6 +174,57 @@ class TreeMesh:
         if finalize:
             self.finalize()
 
+    def refine_box(self, x0s, x1s, levels, finalize=True, diagonal_balance=None):
+        """Refine every cell that intersects the axis-aligned box(es) [x0, x1] (closed intervals) to ``levels``.
+        reference: tree_ext.pyx:650-730 -> geom.cpp:102-112 (Box::intersects_cell)."""
+        self._require_open()
+        x0s = as_array_n_by_dim(np.asarray(x0s, dtype=np.float64), 3)
+        x1s = as_array_n_by_dim(np.asarray(x1s, dtype=np.float64), 3)
+        levels = np.atleast_1d(np.asarray(levels, dtype=np.int64))
+        n = max(x0s.shape[0], x1s.shape[0], levels.size)
+        for name, arr_n in (("x0s", x0s.shape[0]), ("x1s", x1s.shape[0]), ("levels", levels.size)):
+            if arr_n not in (1, n):
+                raise ValueError(f"First dimensions of x0s, x1s, levels are incompatible ({name} has {arr_n}, expected 1 or {n})")
+        x0s = np.broadcast_to(x0s, (n, 3))
+        x1s = np.broadcast_to(x1s, (n, 3))
+        levels = np.array([self._parse_level(int(l)) for l in np.broadcast_to(levels, (n,))], dtype=np.int64)
+        db = self._diagonal_balance if diagonal_balance is None else diagonal_balance
+        lo_box, hi_box = np.minimum(x0s, x1s), np.maximum(x0s, x1s)
+
+        def concerns(req, lo, w):
+            a, b = self._cell_box(lo, w)
+            return ((hi_box[req] >= a) & (lo_box[req] <= b)).all(axis=1)
+
+        self._tree.refine_requests(n, levels, concerns)
+        self._tree.balance(db)
+        if finalize:
+            self.finalize()
+
+    def refine_bounding_box(self, points, level=-1, padding_cells_by_level=None, finalize=True, diagonal_balance=None):
+        """Refine within the bounding box of ``points``, padded by a number of cells per level.
+        reference: tree_mesh.py:443-546 (a sequence of growing boxes handed to ``refine_box``)."""
+        points = np.atleast_2d(np.asarray(points, dtype=np.float64))
+        bsw, tnw = points.min(axis=0), points.max(axis=0)
+        if level < 0:
+            level = (self.max_level + 1) - (abs(level) % (self.max_level + 1))
+        if level > self.max_level:
+            raise IndexError(f"Level beyond max octree level, {self.max_level}")
+        if padding_cells_by_level is None:
+            padding_cells_by_level = np.array([0])
+        padding_cells_by_level = np.asarray(padding_cells_by_level)
+        if padding_cells_by_level.ndim == 0 and level > 1:
+            padding_cells_by_level = np.full(level - 1, padding_cells_by_level)
+        padding_cells_by_level = np.atleast_1d(padding_cells_by_level)
+        if padding_cells_by_level.ndim == 2 and padding_cells_by_level.shape[1] != self.dim:
+            raise ValueError("incorrect dimension for padding_cells_by_level.")
+        h_min = np.array([h.min() for h in self.h])
+        x0, x1, ls = [], [], []
+        for lv, n_pad in zip(np.arange(level, 1, -1), padding_cells_by_level):   # stops with the shorter sequence
+            pad = n_pad * h_min * 2 ** (self.max_level - lv)
+            bsw, tnw = bsw - pad, tnw + pad
+            x0.append(bsw); x1.append(tnw); ls.append(lv)
+        self.refine_box(np.array(x0), np.array(x1), np.array(ls), finalize=finalize, diagonal_balance=diagonal_balance)
+
     def refine_points(self, points, level=-1, padding_cells_by_level=None, finalize=True, diagonal_balance=None):
         """reference: tree_mesh.py:548-636."""
         level = self._parse_level(level)

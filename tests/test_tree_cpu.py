@@ -154,3 +154,45 @@ def test_tree_tensor_model_derivative_matches_reference_fixture(gold, tag):
         b = golden_matrix(g2, f"{tag}_{key}")
         a.eliminate_zeros(); b.eliminate_zeros()     # the reference's sums of products keep some exact zeros
         assert_same_matrix(a, b, 1e-12)
+
+
+def test_refine_box_and_bounding_box():
+    """refine_box (closed-interval box/cell intersection, geom.cpp:102-112) and refine_bounding_box
+    (tree_mesh.py:443-546): cell for cell the reference's tree where it is available; always: every leaf that
+    intersects the box is at the requested level."""
+    import warnings
+
+    from oracle.refload import load_reference
+
+    rng = np.random.default_rng(8)
+    ref = load_reference()
+    for shape, db in (((16, 16, 16), True), ((16, 8, 32), False)):
+        h = [rng.random(s) + 0.5 for s in shape]
+        ext = np.array([x.sum() for x in h])
+        x0 = ext * rng.random((2, 3)) * 0.5
+        x1 = x0 + ext * rng.random((2, 3)) * 0.4
+        pts = ext * (rng.random((20, 3)) * 0.3 + 0.3)
+        m1 = TreeMesh(h, diagonal_balance=db)
+        m1.refine_box(x0, x1, [-1, -2], finalize=True)
+        m2 = TreeMesh(h, diagonal_balance=db)
+        m2.refine_bounding_box(pts, -1, [1, 2, 1], finalize=True)
+        # property: leaves intersecting box 0 sit at the finest level
+        t = m1._t()
+        a = np.stack([m1._xs[d][t.centers[:, d] - t.half] for d in range(3)], axis=1)
+        b = np.stack([m1._xs[d][t.centers[:, d] + t.half] for d in range(3)], axis=1)
+        hit = ((np.maximum(x0[0], x1[0]) >= a) & (np.minimum(x0[0], x1[0]) <= b)).all(axis=1)
+        assert hit.any() and (t.half[hit] == 1).all()
+        if ref is not None:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                r1 = ref.TreeMesh(h, diagonal_balance=db)
+                r1.refine_box(x0, x1, [-1, -2], finalize=True)
+                r2 = ref.TreeMesh(h, diagonal_balance=db)
+                r2.refine_bounding_box(pts, -1, [1, 2, 1], finalize=True)
+            for ours, theirs in ((m1, r1), (m2, r2)):
+                idx, lev = ours._tree.state()
+                ridx, rlev = theirs.__getstate__()
+                np.testing.assert_array_equal(idx, ridx)
+                np.testing.assert_array_equal(lev, rlev)
+    with pytest.raises(ValueError):
+        TreeMesh([8, 8, 8]).refine_box(np.zeros((2, 3)), np.ones((3, 3)), [1, 2, 3])
