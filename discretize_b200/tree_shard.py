@@ -36,6 +36,10 @@ OPERATOR_KINDS = {
     "average_node_to_cell": ("C", "N"),
     "average_face_to_cell_vector": ("C3", "F"),
     "average_edge_to_cell_vector": ("C3", "E"),
+    "average_node_to_edge": ("E", "N"),
+    "average_node_to_face": ("F", "N"),
+    "average_edge_to_face": ("F", "E"),
+    "average_cell_to_face": ("F", "C"),
 }
 
 
