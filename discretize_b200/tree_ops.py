@@ -11,6 +11,22 @@ from ._lib import check, load
 from .operators import Operator, cuda_device, ptr, stream_ptr, to_device
 
 
+def _unique_small(values):
+    """np.unique(values, return_inverse=True) for arrays that hold only a handful of distinct values (the multipliers
+    of an OcTree operator: signs times products of 1/2 hanging weights): candidates from a sample, a binary search
+    of every entry in that tiny table, and a second round for whatever the sample missed -- O(n log k) instead of a
+    full sort of 10^8 entries."""
+    if values.size == 0:
+        return values.copy(), np.zeros(0, dtype=np.int64)
+    cand = np.unique(values[: min(values.size, 1 << 16)])
+    while True:
+        pos = np.minimum(np.searchsorted(cand, values), cand.size - 1)
+        miss = cand[pos] != values
+        if not miss.any():
+            return cand, pos
+        cand = np.unique(np.r_[cand, np.unique(values[miss])])
+
+
 def encode_parts_raw(geoms, parts, shape):
     """Like ``encode_parts`` for parts that hold DUPLICATE (row, column) pairs on purpose (ghost columns redirected by
     ``tree_shard``): entries are concatenated row by row, never summed."""
@@ -18,7 +34,7 @@ def encode_parts_raw(geoms, parts, shape):
     rows, cols, codes = [], [], []
     for s_, M in parts:
         M = sp.csr_matrix(M)
-        vals, inv = np.unique(np.round(M.data, 14), return_inverse=True)
+        vals, inv = _unique_small(np.round(M.data, 14))
         base = len(tab_mult)
         tab_mult.extend(vals.tolist())
         tab_sel.extend([s_] * vals.size)
@@ -44,7 +60,7 @@ def encode_parts(geoms, parts, shape):
     acc = None
     for s_, M in parts:
         M = sp.csr_matrix(M)
-        vals, inv = np.unique(np.round(M.data, 14), return_inverse=True)
+        vals, inv = _unique_small(np.round(M.data, 14))
         base = len(tab_mult)
         tab_mult.extend(vals.tolist())
         tab_sel.extend([s_] * vals.size)
