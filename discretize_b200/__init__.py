@@ -11,6 +11,7 @@ from .tensor_mesh import TensorMesh
 from .tree_mesh import TreeMesh, TreeMeshNotFinalizedError
 from .operators import Operator
 from ._lib import DzbError
+from . import utils
 
-__all__ = ["TensorMesh", "TreeMesh", "TreeMeshNotFinalizedError", "Operator", "DzbError"]
+__all__ = ["TensorMesh", "TreeMesh", "TreeMeshNotFinalizedError", "Operator", "DzbError", "utils"]
 __version__ = "0.1.0"
