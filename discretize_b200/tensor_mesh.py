@@ -358,7 +358,10 @@ class TensorMesh:
 
     @property
     def face_areas(self):
-        self._require_3d("face_areas")
+        if self.dim < 3:
+            from . import lowdim
+
+            return lowdim.face_areas(self)
         hx, hy, hz = self._h
         nx, ny, nz = self.shape_cells
         return np.r_[self._outer(np.ones(nx + 1), self._outer(hy, hz)),
@@ -367,7 +370,10 @@ class TensorMesh:
 
     @property
     def edge_lengths(self):
-        self._require_3d("edge_lengths")
+        if self.dim < 3:
+            from . import lowdim
+
+            return lowdim.edge_lengths(self)
         hx, hy, hz = self._h
         nx, ny, nz = self.shape_cells
         return np.r_[self._outer(hx, np.ones((ny + 1) * (nz + 1))),
@@ -399,8 +405,22 @@ class TensorMesh:
         return _lib.DzbTensorMesh(nx, ny, nz, 0, 0, 0, 0, 0, 0)
 
     # ---- differential operators and averaging ------------------------------------------------------
+    def _lowdim_operator(self, name):
+        """1-D / 2-D meshes: the operator assembled on the host (lowdim.py) and applied by the generic CSR kernel."""
+        key = ("lowdim", name)
+        if key not in self._cache:
+            from . import lowdim
+            from .csr import CsrOperator
+
+            self._cache[key] = CsrOperator(lowdim.build(self, name))
+        return self._cache[key]
+
     def _stencil(self, name, op_id, flags=0):
-        self._require_3d(name)
+        if self.dim < 3:
+            if flags or "cell_gradient" in name:
+                raise NotImplementedError(
+                    f"discretize_b200.TensorMesh.{name}: only 3-D meshes have cell-gradient kernels (mesh.dim == {self.dim})")
+            return self._lowdim_operator(name)
         key = name if flags == 0 else (name, flags)
         if key not in self._cache:
             from .tensor_ops import StencilOperator
@@ -509,7 +529,14 @@ class TensorMesh:
 
     def _inner_product(self, proj, model, invert_model, invert_matrix, do_fast, kwargs):
         self._check_removed_kwargs(kwargs)
-        self._require_3d("get_%s_inner_product" % ("face" if proj == "F" else "edge"))
+        if self.dim < 3:
+            import torch
+
+            from . import lowdim
+            from .operators import DiagonalOperator
+
+            host = model.cpu().numpy() if isinstance(model, torch.Tensor) else model
+            return DiagonalOperator(lowdim.mass_diagonal(self, proj, host, invert_model, invert_matrix))
         from .tensor_ops import make_mass_operator
 
         return make_mass_operator(self, proj, model, invert_model, invert_matrix, do_fast)
@@ -541,7 +568,14 @@ class TensorMesh:
             )
         if kwargs:
             raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
-        self._require_3d("get_interpolation_matrix")
+        if self.dim < 3:
+            import torch
+
+            from . import lowdim
+            from .csr import CsrOperator
+
+            host = loc.cpu().numpy() if isinstance(loc, torch.Tensor) else loc
+            return CsrOperator(lowdim.interpolation_matrix(self, host, location_type, zeros_outside))
         from .interp import make_interpolation_operator
 
         return make_interpolation_operator(self, loc, location_type, zeros_outside)

@@ -85,11 +85,15 @@ def test_constructor_forms():
         dz.TensorMesh([2, 2, 2, 2])
     with pytest.raises(ValueError):
         dz.TensorMesh([2, 2, 2], origin=[0, 0])
-    # lower dimensions construct, operators refuse loudly
+    # lower dimensions construct; their operators are host-assembled CSR (lowdim.py), what has no 1-D / 2-D meaning or
+    # no kernel refuses loudly
     m2 = dz.TensorMesh([4, 3])
     assert m2.dim == 2 and m2.nC == 12 and m2.nN == 20
+    assert m2.face_divergence.shape == (12, 31) and m2.edge_curl.shape == (12, 31)
     with pytest.raises(NotImplementedError):
-        m2.face_divergence
+        m2.cell_gradient
+    with pytest.raises(NotImplementedError):
+        m2.get_face_inner_product_deriv(np.ones(12))
     with pytest.raises(NotImplementedError):
         dz.TensorMesh([4]).edge_curl
 

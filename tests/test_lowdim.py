@@ -1,0 +1,85 @@
+"""1-D / 2-D TensorMesh (SURVEY 8a "Dimension coverage"): host assembly (lowdim.py) against the reference-made fixture on
+the CPU; the same operators through the mesh API on the GPU (generic CSR kernel)."""
+import numpy as np
+import pytest
+
+import discretize_b200 as dz
+from discretize_b200 import lowdim
+from tests.golden.make_golden_lowdim import LOCS, MASS_CASES, ops_for
+from tests.helpers import assert_close_vec, assert_same_matrix, golden_matrix, load_golden
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return load_golden("tensor_lowdim_small.npz")
+
+
+def _mesh(g, tag):
+    d = int(tag[1])
+    return dz.TensorMesh([g[f"{tag}_h{a}"] for a in range(d)], origin=g[f"{tag}_origin"])
+
+
+@pytest.mark.parametrize("tag", ["d1", "d2"])
+def test_host_assembly_matches_reference_fixture(gold, tag):
+    m = _mesh(gold, tag)
+    for name in ops_for(m.dim):
+        assert_same_matrix(lowdim.build(m, name), golden_matrix(gold, f"{tag}_{name}"), 1e-13)
+        assert_same_matrix(getattr(m, name).tocsr(), golden_matrix(gold, f"{tag}_{name}"), 1e-13)   # no GPU needed
+    for arr in ("cell_volumes", "face_areas", "edge_lengths"):
+        np.testing.assert_array_equal(getattr(m, arr), gold[f"{tag}_{arr}"])
+    for proj in "FE":
+        for mk, im, ix in MASS_CASES:
+            d = lowdim.mass_diagonal(m, proj, gold[f"{tag}_model_{mk}"], im, ix)
+            assert_close_vec(d, gold[f"{tag}_mass_{proj}_{mk}_{int(im)}{int(ix)}"], 1e-13)
+    for loc in LOCS[m.dim]:
+        assert_same_matrix(lowdim.interpolation_matrix(m, gold[f"{tag}_pts"], loc), golden_matrix(gold, f"{tag}_interp_{loc}"), 1e-13)
+    assert_same_matrix(lowdim.interpolation_matrix(m, gold[f"{tag}_pts_out"], "CC", zeros_outside=True),
+                       golden_matrix(gold, f"{tag}_interp_zo_CC"), 1e-13)
+    with pytest.raises(ValueError, match="outside"):
+        lowdim.interpolation_matrix(m, gold[f"{tag}_pts_out"], "CC")
+
+
+def test_errors_keep_the_reference_behaviour():
+    with pytest.raises(NotImplementedError, match="Edge Curl"):
+        dz.TensorMesh([5]).edge_curl
+    with pytest.raises(NotImplementedError):
+        dz.TensorMesh([5, 4]).cell_gradient
+    with pytest.raises(NotImplementedError):
+        dz.TensorMesh([5]).average_face_y_to_cell
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["d1", "d2"])
+def test_lowdim_operators_on_gpu(gold, tag):
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("gpu tests need a CUDA device")
+    m = _mesh(gold, tag)
+    rng = np.random.default_rng(3)
+    for name in ops_for(m.dim):
+        ref = golden_matrix(gold, f"{tag}_{name}")
+        op = getattr(m, name)
+        x, y = rng.standard_normal(ref.shape[1]), rng.standard_normal(ref.shape[0])
+        assert_close_vec(op @ x, ref @ x)
+        assert_close_vec(op.T @ y, ref.T @ y)
+    n = {"F": m.n_faces, "E": m.n_edges}
+    for proj, get in (("F", m.get_face_inner_product), ("E", m.get_edge_inner_product)):
+        for mk, im, ix in MASS_CASES:
+            M = get(gold[f"{tag}_model_{mk}"], invert_model=im, invert_matrix=ix)
+            x = rng.standard_normal(n[proj])
+            assert_close_vec(M @ x, gold[f"{tag}_mass_{proj}_{mk}_{int(im)}{int(ix)}"] * x)
+    for loc in LOCS[m.dim]:
+        ref = golden_matrix(gold, f"{tag}_interp_{loc}")
+        Q = m.get_interpolation_matrix(gold[f"{tag}_pts"], loc)
+        x = rng.standard_normal(ref.shape[1])
+        assert_close_vec(Q @ x, ref @ x)
+        assert_same_matrix(Q.tocsr(), ref)
+    # a 2-D composite through the operator algebra: G^T Me G
+    if m.dim == 2:
+        sig = gold[f"{tag}_model_iso"]
+        G = m.nodal_gradient
+        A = G.T @ m.get_edge_inner_product(sig) @ G
+        Gr = golden_matrix(gold, f"{tag}_nodal_gradient")
+        Ar = Gr.T @ np.diag(gold[f"{tag}_mass_E_iso_00"]) @ Gr
+        x = rng.standard_normal(m.n_nodes)
+        assert_close_vec(A @ x, Ar @ x)
