@@ -11,6 +11,7 @@ meshes construct (counts, geometry) but their operators raise NotImplementedErro
 from __future__ import annotations
 
 import numpy as np
+import scipy.sparse as sp
 
 from . import _lib
 from .operators import to_device, cuda_device
@@ -495,6 +496,101 @@ class TensorMesh:
     cell_gradient_x = property(lambda self: self._stencil("cell_gradient_x", _lib.OP_CELL_GRAD_X, _lib.CG_SCALE))
     cell_gradient_y = property(lambda self: self._stencil("cell_gradient_y", _lib.OP_CELL_GRAD_Y, _lib.CG_SCALE))
     cell_gradient_z = property(lambda self: self._stencil("cell_gradient_z", _lib.OP_CELL_GRAD_Z, _lib.CG_SCALE))
+
+    # ---- boundary (base/base_tensor_mesh.py:300-310, 423-560; operators/differential_operators.py:2183-2197,
+    # 3384-3430): index selections, assembled on the host and applied by the generic CSR kernel ----------------
+    @staticmethod
+    def _boundary_mask(shape, axes):
+        """Flattened (x fastest) mask of the entries of a tensor of ``shape`` that sit on its first or last index along
+        any of ``axes`` (utils/matrix_utils.py: make_boundary_bool)."""
+        mask = np.zeros(shape, dtype=bool)
+        for a in axes:
+            sel = [slice(None)] * len(shape)
+            for end in (0, -1):
+                sel[a] = end
+                mask[tuple(sel)] = True
+        return mask.reshape(-1, order="F")
+
+    def _boundary_masks(self):
+        d = self.dim
+        face = np.concatenate([self._boundary_mask(self._shape((a,)), (a,)) for a in range(d)])
+        edge = None
+        if d > 1:
+            edge = np.concatenate([self._boundary_mask(self._shape(tuple(b for b in range(d) if b != a)),
+                                                       tuple(b for b in range(d) if b != a)) for a in range(d)])
+        node = self._boundary_mask(self.shape_nodes, tuple(range(d)))
+        return face, edge, node
+
+    def _selection(self, key, mask):
+        if key not in self._cache:
+            from .csr import CsrOperator
+
+            idx = np.nonzero(mask)[0]
+            P = sp.csr_matrix((np.ones(idx.size), (np.arange(idx.size), idx)), shape=(idx.size, mask.size))
+            self._cache[key] = CsrOperator(P)
+        return self._cache[key]
+
+    @property
+    def project_face_to_boundary_face(self):
+        return self._selection("P_bf", self._boundary_masks()[0])
+
+    @property
+    def project_edge_to_boundary_edge(self):
+        if self.dim == 1:
+            return None  # no edges are on the boundary in 1-D
+        return self._selection("P_be", self._boundary_masks()[1])
+
+    @property
+    def project_node_to_boundary_node(self):
+        return self._selection("P_bn", self._boundary_masks()[2])
+
+    @property
+    def boundary_nodes(self):
+        if self.dim == 1:
+            return self.nodes_x[[0, -1]]
+        return self.nodes[self._boundary_masks()[2]]
+
+    def _face_grids(self):
+        return [self._grid("faces_" + "xyz"[a]) for a in range(self.dim)]
+
+    @property
+    def boundary_faces(self):
+        if self.dim == 1:
+            return self.nodes_x[[0, -1]]
+        return np.concatenate(self._face_grids())[self._boundary_masks()[0]]
+
+    @property
+    def boundary_edges(self):
+        if self.dim == 1:
+            return None
+        grids = np.concatenate([self._grid("edges_" + "xyz"[a]) for a in range(self.dim)])
+        return grids[self._boundary_masks()[1]]
+
+    @property
+    def boundary_face_outward_normals(self):
+        d = self.dim
+        if d == 1:
+            return np.array([-1, 1])
+        out = []
+        for a in range(d):
+            shp = self._shape((a,))
+            idx = np.indices(shp)[a].reshape(-1, order="F")
+            on = self._boundary_mask(shp, (a,))
+            nrm = np.zeros((int(on.sum()), d))
+            nrm[:, a] = np.where(idx[on] == 0, -1.0, 1.0)
+            out.append(nrm)
+        return np.concatenate(out)
+
+    @property
+    def boundary_face_scalar_integral(self):
+        """diag(face_areas) P^T diag(+-1): nF x n_boundary_faces (differential_operators.py:2183-2197)."""
+        from .csr import CsrOperator
+
+        if self.dim == 1:
+            return CsrOperator(sp.csr_matrix(([-1.0, 1.0], ([0, self.n_faces_x - 1], [0, 1])), shape=(self.n_faces_x, 2)))
+        P = self.project_face_to_boundary_face.tocsr()
+        sign = self.boundary_face_outward_normals.sum(axis=1)       # the one non-zero component: -1 (low side) or +1
+        return CsrOperator((sp.diags(self.face_areas) @ P.T @ sp.diags(sign)).tocsr())
 
     @property
     def nodal_laplacian(self):

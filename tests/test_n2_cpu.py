@@ -60,3 +60,45 @@ def test_known_properties():
     Gd = T.cell_gradient(g, "dirichlet")
     first_x_face = Gd[0].toarray().ravel()
     assert first_x_face[0] == pytest.approx(2.0 / 1.0)
+
+
+def test_boundary_projections_and_integrals():
+    """project_*_to_boundary_*, boundary_faces / nodes / edges / outward normals, boundary_face_scalar_integral
+    (base_tensor_mesh.py:300-310, 423-560; differential_operators.py:2183-2197, 3384-3430): against the reference where
+    it is available, and by their defining properties everywhere."""
+    import discretize_b200 as dz
+
+    ref = load_reference()
+    rng = np.random.default_rng(2)
+    for h, o in (([rng.random(4) + .5, rng.random(3) + .5, rng.random(5) + .5], np.array([1., 2., 3.])),
+                 ([rng.random(5) + .5, rng.random(4) + .5], None), ([6], None), ([1, 1, 1], None)):
+        m = dz.TensorMesh(h, origin=o)
+        n = m.shape_cells
+        Pf = m.project_face_to_boundary_face.tocsr()
+        n_bf = 2 * sum(int(np.prod([n[b] for b in range(m.dim) if b != a])) for a in range(m.dim))
+        assert Pf.shape == (n_bf, m.n_faces) and np.array_equal((Pf @ Pf.T).toarray(), np.eye(n_bf))
+        Pn = m.project_node_to_boundary_node.tocsr()
+        interior = int(np.prod([max(k - 1, 0) for k in n]))
+        assert Pn.shape[0] == m.n_nodes - interior
+        normals = m.boundary_face_outward_normals
+        assert np.asarray(normals).shape[0] == n_bf
+        A = m.boundary_face_scalar_integral.tocsr()
+        if m.dim > 1:   # each boundary face carries +-(its area): the sign of its outward normal
+            flux = Pf @ (A @ np.ones(n_bf))
+            np.testing.assert_allclose(flux, (Pf @ m.face_areas) * np.asarray(normals).sum(axis=1))
+        if ref is None:
+            continue
+        mr = ref.TensorMesh(h, origin=o)
+        for name in ("project_face_to_boundary_face", "project_edge_to_boundary_edge", "project_node_to_boundary_node",
+                     "boundary_face_scalar_integral"):
+            a, b = getattr(m, name), getattr(mr, name)
+            if b is None:
+                assert a is None
+            else:
+                assert_same_matrix(a.tocsr(), b, 1e-14)
+        for name in ("boundary_nodes", "boundary_faces", "boundary_edges", "boundary_face_outward_normals"):
+            a, b = getattr(m, name), getattr(mr, name)
+            if b is None:
+                assert a is None
+            else:
+                np.testing.assert_array_equal(np.asarray(a, dtype=float), np.asarray(b, dtype=float))
