@@ -302,3 +302,35 @@ def interpolation_matrix(mesh, pts, location_type, zeros_outside=False):
                 indices[lo:hi] = np.arange(ncols)
         Q = sp.csr_matrix((data, indices, indptr), shape=(npts, ncols))
     return Q
+
+
+# ---- model derivatives of the diagonal mass matrices -----------------------------------------------------------------
+
+
+def mass_deriv_matrix(mesh, proj, model, v, invert_model=False, invert_matrix=False):
+    """d(M(m) v)/dm for scalar / isotropic / anisotropic models on 1-D / 2-D meshes (base/base_tensor_mesh.py:865-988):
+    ``diag(v) @ dMdprop`` with ``dMdprop = r (k Av^T) diag(V) c`` -- r = +-MI^2 rows for ``invert_matrix``, c = +-1/m^2
+    columns for ``invert_model``; a scalar model gives an n x 1 matrix (n x nC in the reference's invert_matrix-only
+    branch, which skips the sum over cells)."""
+    d, nC = mesh.dim, mesh.n_cells
+    V = cell_volumes(mesh)
+    model = np.asarray(model, dtype=np.float64)
+    scalar = model.size == 1
+    m = np.full(nC, float(model.reshape(-1)[0])) if scalar else model.reshape(-1, order="F")
+    base = "average_face_to_cell" if proj == "F" else "average_edge_to_cell"
+    if m.size == nC:
+        core = d * build(mesh, base).T @ sp.diags(V)
+    elif m.size == nC * d:
+        core = build(mesh, base + "_vector").T @ sp.diags(np.tile(V, d))
+    else:
+        raise NotImplementedError("full-tensor models on 1-D / 2-D meshes are not built")
+    if invert_matrix:
+        mi = mass_diagonal(mesh, proj, model, invert_model, True)
+        core = sp.diags((1.0 if invert_model else -1.0) * mi * mi) @ core
+    if invert_model:
+        if scalar:
+            raise TypeError("Vector must be a numpy array")     # the reference fails here, too (sdiag of a bare float)
+        core = core @ sp.diags((1.0 if invert_matrix else -1.0) / (m * m))
+    if scalar and not (invert_matrix and not invert_model):
+        core = sp.csr_matrix(core @ np.ones((nC, 1)))
+    return (sp.diags(np.asarray(v, dtype=np.float64).reshape(-1)) @ core).tocsr()

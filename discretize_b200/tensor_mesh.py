@@ -645,7 +645,25 @@ class TensorMesh:
 
     def _inner_product_deriv(self, proj, model, do_fast, invert_model, invert_matrix, kwargs):
         self._check_removed_kwargs(kwargs)
-        self._require_3d("get_%s_inner_product_deriv" % ("face" if proj == "F" else "edge"))
+        if self.dim < 3:
+            if model is None:
+                return None
+            import torch
+
+            from . import lowdim
+            from .csr import CsrOperator
+
+            host = model.cpu().numpy() if isinstance(model, torch.Tensor) else model
+            if np.asarray(host).size not in (1, self.n_cells, self.n_cells * self.dim):
+                raise NotImplementedError("full-tensor model derivatives are only built for 3-D meshes")
+
+            def inner_product_deriv(v=None):
+                if v is None:
+                    raise Exception("v must be supplied for this implementation.")
+                vh = v.cpu().numpy() if isinstance(v, torch.Tensor) else v
+                return CsrOperator(lowdim.mass_deriv_matrix(self, proj, host, vh, invert_model, invert_matrix))
+
+            return inner_product_deriv
         from .tensor_ops import make_mass_deriv
 
         return make_mass_deriv(self, proj, model, do_fast, invert_model, invert_matrix)

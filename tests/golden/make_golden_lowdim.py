@@ -52,6 +52,11 @@ def main():
         for proj, get in (("F", mesh.get_face_inner_product), ("E", mesh.get_edge_inner_product)):
             for mk, im, ix in MASS_CASES:
                 out[f"{tag}_mass_{proj}_{mk}_{int(im)}{int(ix)}"] = get(models[mk], invert_model=im, invert_matrix=ix).diagonal()
+        v = {"F": rng.standard_normal(mesh.nF), "E": rng.standard_normal(mesh.nE)}
+        out[f"{tag}_vF"], out[f"{tag}_vE"] = v["F"], v["E"]
+        for proj, get in (("F", mesh.get_face_inner_product_deriv), ("E", mesh.get_edge_inner_product_deriv)):
+            for mk, im, ix in MASS_CASES:
+                put(f"deriv_{proj}_{mk}_{int(im)}{int(ix)}", get(models[mk], invert_model=im, invert_matrix=ix)(v[proj]))
         ext = np.array([x.sum() for x in h])
         pts = origin + ext * rng.random((40, d))
         pts[0], pts[1] = origin, origin + ext

@@ -93,7 +93,7 @@ def test_constructor_forms():
     with pytest.raises(NotImplementedError):
         m2.cell_gradient
     with pytest.raises(NotImplementedError):
-        m2.get_face_inner_product_deriv(np.ones(12))
+        m2.get_face_inner_product_deriv(np.ones((12, 3)))      # full tensor: 3-D only
     with pytest.raises(NotImplementedError):
         dz.TensorMesh([4]).edge_curl
 

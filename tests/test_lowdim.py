@@ -31,6 +31,12 @@ def test_host_assembly_matches_reference_fixture(gold, tag):
         for mk, im, ix in MASS_CASES:
             d = lowdim.mass_diagonal(m, proj, gold[f"{tag}_model_{mk}"], im, ix)
             assert_close_vec(d, gold[f"{tag}_mass_{proj}_{mk}_{int(im)}{int(ix)}"], 1e-13)
+    for proj in "FE":
+        for mk, im, ix in MASS_CASES:
+            a = lowdim.mass_deriv_matrix(m, proj, gold[f"{tag}_model_{mk}"], gold[f"{tag}_v{proj}"], im, ix)
+            b = golden_matrix(gold, f"{tag}_deriv_{proj}_{mk}_{int(im)}{int(ix)}")
+            a.eliminate_zeros(); b.eliminate_zeros()
+            assert_same_matrix(a, b, 1e-12)
     for loc in LOCS[m.dim]:
         assert_same_matrix(lowdim.interpolation_matrix(m, gold[f"{tag}_pts"], loc), golden_matrix(gold, f"{tag}_interp_{loc}"), 1e-13)
     assert_same_matrix(lowdim.interpolation_matrix(m, gold[f"{tag}_pts_out"], "CC", zeros_outside=True),
