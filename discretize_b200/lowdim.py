@@ -211,7 +211,56 @@ def build(mesh, name):
             r, c, v = g.term(g.face[a], g.node, st)
             blocks.append((r + offF[a], c, v))
         return _assemble((offF[-1], g.count(g.node)), blocks)
+    if name == "average_cell_to_edge":       # av_extrap across the edge (differential_operators.py:2867-2892); 1-D: identity
+        if d == 1:
+            return sp.identity(n[0], format="csr")
+        blocks = []
+        for a in range(d):
+            st = [_eye(n[b]) if b == a else _av_extrap(n[b]) for b in range(d)]
+            r, c, v = g.term(g.edge[a], g.cell, st)
+            blocks.append((r + offE[a], c, v))
+        return _assemble((offE[-1], nC), blocks)
+    if name == "average_edge_to_face":       # 1-D: average_cell_to_face; 2-D: x-faces ARE y-edges and vice versa (:3205-3217)
+        if d == 1:
+            return build(mesh, "average_cell_to_face")
+        nFx, nFy = g.count(g.face[0]), g.count(g.face[1])
+        return sp.diags([1, 1], [-nFx, nFy], shape=(nFx + nFy, offE[-1])).tocsr()
     raise NotImplementedError(f"discretize_b200.TensorMesh.{name} is not available for mesh.dim == {d}")
+
+
+def _cell_grad_1d(n, bc):
+    """nodes <- cells: (-1, +1); ghost-point boundary rows: Dirichlet +-2, Neumann an explicit 0
+    (operators/differential_operators.py:41-82)."""
+    i = np.arange(1, n)
+    first = {"dirichlet": 2.0, "neumann": 0.0}[bc[0]]
+    last = {"dirichlet": -2.0, "neumann": 0.0}[bc[1]]
+    return np.r_[0, i, i, n], np.r_[0, i - 1, i, n - 1], np.r_[first, np.full(n - 1, -1.0), np.full(n - 1, 1.0), last]
+
+
+def cell_gradient(mesh, bcs, scaled, axis=None):
+    """stencil_cell_gradient (``scaled=False``) / cell_gradient = diag(S / aveCC2F V) stencil (:1413-1595); ``axis``: one
+    component block with Neumann conditions (:1049-1411, 1762-2083).  The product drops the Neumann rows' explicit zeros."""
+    g = _Grid(mesh)
+    d, n = g.dim, g.n
+    offF = g.offsets(g.face)
+    axes = range(d) if axis is None else [axis]
+    blocks = []
+    for a in axes:
+        bc = bcs[a] if axis is None else ["neumann", "neumann"]
+        st = [_cell_grad_1d(n[b], bc) if b == a else _eye(n[b]) for b in range(d)]
+        r, c, v = g.term(g.face[a], g.cell, st)
+        blocks.append((r + (offF[a] if axis is None else 0), c, v))
+    nrows = offF[-1] if axis is None else g.count(g.face[axis])
+    G = _assemble((nrows, g.count(g.cell)), blocks)
+    if not scaled:
+        return G
+    scale = face_areas(mesh) / (build(mesh, "average_cell_to_face") @ cell_volumes(mesh))
+    if axis is not None:
+        scale = scale[offF[axis]:offF[axis + 1]]
+    G = (sp.diags(scale) @ G).tocsr()
+    G.eliminate_zeros()
+    G.sort_indices()
+    return G
 
 
 # ---- diagonal mass matrices ----------------------------------------------------------------------------------------

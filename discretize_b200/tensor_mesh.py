@@ -416,11 +416,23 @@ class TensorMesh:
             self._cache[key] = CsrOperator(lowdim.build(self, name))
         return self._cache[key]
 
+    def _lowdim_cell_gradient(self, name):
+        from . import lowdim
+        from .csr import CsrOperator
+
+        axis = "xyz".index(name[-1]) if name[-2:] in ("_x", "_y", "_z") else None
+        if axis is not None and axis >= self.dim:
+            raise NotImplementedError(f"discretize_b200.TensorMesh.{name} is not available for mesh.dim == {self.dim}")
+        bcs = self.set_cell_gradient_BC(self._cell_gradient_BC_list)
+        key = ("lowdim", name, str(bcs))
+        if key not in self._cache:
+            self._cache[key] = CsrOperator(lowdim.cell_gradient(self, bcs, not name.startswith("stencil"), axis))
+        return self._cache[key]
+
     def _stencil(self, name, op_id, flags=0):
         if self.dim < 3:
-            if flags or "cell_gradient" in name:
-                raise NotImplementedError(
-                    f"discretize_b200.TensorMesh.{name}: only 3-D meshes have cell-gradient kernels (mesh.dim == {self.dim})")
+            if "cell_gradient" in name:
+                return self._lowdim_cell_gradient(name)
             return self._lowdim_operator(name)
         key = name if flags == 0 else (name, flags)
         if key not in self._cache:

@@ -12,8 +12,15 @@ from oracle.refload import load_reference  # noqa: E402
 OPS_ANY = ["face_divergence", "face_x_divergence", "nodal_gradient", "average_face_to_cell", "average_face_to_cell_vector",
            "average_edge_to_cell", "average_edge_to_cell_vector", "average_face_x_to_cell", "average_edge_x_to_cell",
            "average_node_to_cell", "average_cell_to_face", "average_cell_vector_to_face", "average_node_to_edge",
-           "average_node_to_face"]
-OPS_2D = ["face_y_divergence", "edge_curl", "average_face_y_to_cell", "average_edge_y_to_cell"]
+           "average_node_to_face", "average_cell_to_edge", "average_edge_to_face", "stencil_cell_gradient_x", "cell_gradient_x"]
+OPS_2D = ["face_y_divergence", "edge_curl", "average_face_y_to_cell", "average_edge_y_to_cell", "stencil_cell_gradient_y",
+          "cell_gradient_y"]
+BCS = {"neumann": "neumann", "dirichlet": "dirichlet", "mixed": [["dirichlet", "neumann"], "dirichlet"]}
+
+
+def bc_for(dim, tag):
+    bc = BCS[tag]
+    return bc if isinstance(bc, str) else list(bc[:dim])
 LOCS = {1: ["CC", "N", "Fx", "Ex", "CCVx"], 2: ["CC", "N", "Fx", "Fy", "Ex", "Ey", "CCVx", "CCVy"]}
 MASS_CASES = [(mk, im, ix) for mk in ("iso", "aniso") for im in (False, True) for ix in (False, True)]
 
@@ -46,6 +53,11 @@ def main():
             put(name, getattr(mesh, name))
         for arr in ("cell_volumes", "face_areas", "edge_lengths"):
             out[f"{tag}_{arr}"] = getattr(mesh, arr)
+        import copy
+        for bct in BCS:
+            mesh.set_cell_gradient_BC(copy.deepcopy(bc_for(d, bct)))
+            put("stencil_cell_gradient_" + bct, mesh.stencil_cell_gradient)
+            put("cell_gradient_" + bct, mesh.cell_gradient)
         models = {"iso": rng.random(mesh.nC) + .5, "aniso": rng.random((mesh.nC, d)) + .5}
         for k, v in models.items():
             out[f"{tag}_model_{k}"] = v

@@ -90,8 +90,7 @@ def test_constructor_forms():
     m2 = dz.TensorMesh([4, 3])
     assert m2.dim == 2 and m2.nC == 12 and m2.nN == 20
     assert m2.face_divergence.shape == (12, 31) and m2.edge_curl.shape == (12, 31)
-    with pytest.raises(NotImplementedError):
-        m2.cell_gradient
+    assert m2.cell_gradient.shape == (31, 12)
     with pytest.raises(NotImplementedError):
         m2.get_face_inner_product_deriv(np.ones((12, 3)))      # full tensor: 3-D only
     with pytest.raises(NotImplementedError):

@@ -5,7 +5,9 @@ import pytest
 
 import discretize_b200 as dz
 from discretize_b200 import lowdim
-from tests.golden.make_golden_lowdim import LOCS, MASS_CASES, ops_for
+import copy
+
+from tests.golden.make_golden_lowdim import BCS, LOCS, MASS_CASES, bc_for, ops_for
 from tests.helpers import assert_close_vec, assert_same_matrix, golden_matrix, load_golden
 
 
@@ -23,10 +25,15 @@ def _mesh(g, tag):
 def test_host_assembly_matches_reference_fixture(gold, tag):
     m = _mesh(gold, tag)
     for name in ops_for(m.dim):
-        assert_same_matrix(lowdim.build(m, name), golden_matrix(gold, f"{tag}_{name}"), 1e-13)
+        if "cell_gradient" not in name:     # those go through lowdim.cell_gradient (boundary conditions)
+            assert_same_matrix(lowdim.build(m, name), golden_matrix(gold, f"{tag}_{name}"), 1e-13)
         assert_same_matrix(getattr(m, name).tocsr(), golden_matrix(gold, f"{tag}_{name}"), 1e-13)   # no GPU needed
     for arr in ("cell_volumes", "face_areas", "edge_lengths"):
         np.testing.assert_array_equal(getattr(m, arr), gold[f"{tag}_{arr}"])
+    for bct in BCS:
+        m.set_cell_gradient_BC(copy.deepcopy(bc_for(m.dim, bct)))
+        assert_same_matrix(m.stencil_cell_gradient.tocsr(), golden_matrix(gold, f"{tag}_stencil_cell_gradient_{bct}"), 1e-13)
+        assert_same_matrix(m.cell_gradient.tocsr(), golden_matrix(gold, f"{tag}_cell_gradient_{bct}"), 1e-13)
     for proj in "FE":
         for mk, im, ix in MASS_CASES:
             d = lowdim.mass_diagonal(m, proj, gold[f"{tag}_model_{mk}"], im, ix)
@@ -49,9 +56,11 @@ def test_errors_keep_the_reference_behaviour():
     with pytest.raises(NotImplementedError, match="Edge Curl"):
         dz.TensorMesh([5]).edge_curl
     with pytest.raises(NotImplementedError):
-        dz.TensorMesh([5, 4]).cell_gradient
+        dz.TensorMesh([5, 4]).cell_gradient_z
     with pytest.raises(NotImplementedError):
         dz.TensorMesh([5]).average_face_y_to_cell
+    with pytest.raises(NotImplementedError):
+        dz.TensorMesh([5, 4]).get_face_inner_product(np.ones((20, 3)))       # full tensor: 3-D only
 
 
 @pytest.mark.gpu
