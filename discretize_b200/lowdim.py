@@ -61,9 +61,9 @@ class _Grid:
     def offsets(self, locs):
         return np.r_[0, np.cumsum([self.count(l) for l in locs])]
 
-    def term(self, row_loc, col_loc, stencils, scale=1.0):
+    def term(self, row_loc, col_loc, stencils, scale=1.0, row_shape=None):
         """COO triplets (local to the two blocks) of the tensor product of per-axis stencils, x fastest."""
-        rs, cs = self.shape(row_loc), self.shape(col_loc)
+        rs, cs = (row_shape or self.shape(row_loc)), self.shape(col_loc)
         rows = np.zeros(1, dtype=np.int64)
         cols = np.zeros(1, dtype=np.int64)
         vals = np.full(1, float(scale))
@@ -223,9 +223,69 @@ def build(mesh, name):
     if name == "average_edge_to_face":       # 1-D: average_cell_to_face; 2-D: x-faces ARE y-edges and vice versa (:3205-3217)
         if d == 1:
             return build(mesh, "average_cell_to_face")
+        if d == 3:           # a face <- its four edges, 1/4 each: the two tangent directions, averaged across the face
+            blocks = []
+            for a in range(d):
+                for b in range(d):
+                    if b != a:
+                        st = [_eye(n[c] + 1) if c == a else _eye(n[c]) if c == b else _av(n[c]) for c in range(d)]
+                        r, c, v = g.term(g.face[a], g.edge[b], st, 0.5)
+                        blocks.append((r + offF[a], c + offE[b], v))
+            return _assemble((offF[-1], offE[-1]), blocks)
         nFx, nFy = g.count(g.face[0]), g.count(g.face[1])
-        return sp.diags([1, 1], [-nFx, nFy], shape=(nFx + nFy, offE[-1])).tocsr()
+        return sp.diags([1.0, 1.0], [-nFx, nFy], shape=(nFx + nFy, offE[-1])).tocsr()
     raise NotImplementedError(f"discretize_b200.TensorMesh.{name} is not available for mesh.dim == {d}")
+
+
+def _end_rows(st, n_rows):
+    """Keep the first and last row of a 1-D stencil, renumbered 0 and 1."""
+    r, c, v = st
+    keep = (r == 0) | (r == n_rows - 1)
+    return (r[keep] != 0).astype(np.int64), c[keep], v[keep]
+
+
+def boundary_face_rows(mesh, name):
+    """``project_face_to_boundary_face @ mesh.<name>`` for the three averages the boundary integrals need, any dimension,
+    assembled from the boundary rows only (O(boundary) work): the 1-D stencil along the face normal is cut down to its
+    two end rows, which keeps the boundary faces in their global order."""
+    g = _Grid(mesh)
+    d, n = g.dim, g.n
+    blocks, row0 = [], 0
+    if name == "average_edge_to_face" and d == 2:       # a boundary x-face IS a y-edge and vice versa
+        offE = g.offsets(g.edge)
+        for a in range(d):
+            st = [_end_rows(_eye(n[b] + 1), n[b] + 1) if b == a else _eye(n[b]) for b in range(d)]
+            shape = tuple(2 if b == a else n[b] for b in range(d))
+            r, c, v = g.term(g.face[a], g.edge[1 - a], st, row_shape=shape)
+            blocks.append((r + row0, c + offE[1 - a], v))
+            row0 += int(np.prod(shape))
+        return _assemble((row0, offE[-1]), blocks)
+    for a in range(d):
+        shape = tuple(2 if b == a else n[b] for b in range(d))
+        if name == "average_cell_to_face":
+            st = [_end_rows(_av_extrap(n[b]), n[b] + 1) if b == a else _eye(n[b]) for b in range(d)]
+            r, c, v = g.term(g.face[a], g.cell, st, row_shape=shape)
+            blocks.append((r + row0, c, v))
+        elif name == "average_node_to_face":
+            st = [_end_rows(_eye(n[b] + 1), n[b] + 1) if b == a else _av(n[b]) for b in range(d)]
+            r, c, v = g.term(g.face[a], g.node, st, row_shape=shape)
+            blocks.append((r + row0, c, v))
+        elif name == "average_edge_to_face":
+            if d == 1:
+                return boundary_face_rows(mesh, "average_cell_to_face")
+            offE = g.offsets(g.edge)
+            for b in range(d):       # the two edge directions tangent to the face, two edges of each
+                if b == a:
+                    continue
+                st = [_end_rows(_eye(n[c] + 1), n[c] + 1) if c == a else _eye(n[c]) if c == b else _av(n[c]) for c in range(d)]
+                r, c, v = g.term(g.face[a], g.edge[b], st, 0.5, row_shape=shape)
+                blocks.append((r + row0, c + offE[b], v))
+        else:
+            raise KeyError(name)
+        row0 += int(np.prod(shape))
+    ncols = {"average_cell_to_face": g.count(g.cell), "average_node_to_face": g.count(g.node),
+             "average_edge_to_face": int(g.offsets(g.edge)[-1])}[name]
+    return _assemble((row0, ncols), blocks)
 
 
 def _cell_grad_1d(n, bc):

@@ -5,8 +5,9 @@ Drop-in for the operator-application part of ``discretize.TensorMesh``
 are host-side numpy exactly like the reference; every operator property returns a
 CUDA-backed :class:`~discretize_b200.operators.Operator`.
 
-Only 3-D meshes have kernels (the five target configurations are 3-D); 1-D/2-D
-meshes construct (counts, geometry) but their operators raise NotImplementedError.
+The hand-written stencil kernels are 3-D (the five target configurations are 3-D); 1-D/2-D
+meshes and the boundary / surface / line terms are assembled on the host (lowdim.py,
+boundary_ops.py, surface_products.py) and applied on the GPU by the generic CSR kernel.
 """
 from __future__ import annotations
 
@@ -25,11 +26,8 @@ _ALIASES = {
     "vnEx": "shape_edges_x", "vnEy": "shape_edges_y", "vnEz": "shape_edges_z",
     "vnFx": "shape_faces_x", "vnFy": "shape_faces_y", "vnFz": "shape_faces_z",
     "vnE": "n_edges_per_direction", "vnF": "n_faces_per_direction",
-    "x0": "origin", "vol": "cell_volumes", "area": "face_areas", "edge": "edge_lengths",
+    "x0": "origin",
     "gridCC": "cell_centers", "gridN": "nodes",
-    "vectorNx": "nodes_x", "vectorNy": "nodes_y", "vectorNz": "nodes_z",
-    "vectorCCx": "cell_centers_x", "vectorCCy": "cell_centers_y", "vectorCCz": "cell_centers_z",
-    "hx": "h_x", "hy": "h_y", "hz": "h_z",
     "aveF2CC": "average_face_to_cell", "aveF2CCV": "average_face_to_cell_vector",
     "aveFx2CC": "average_face_x_to_cell", "aveFy2CC": "average_face_y_to_cell", "aveFz2CC": "average_face_z_to_cell",
     "aveE2CC": "average_edge_to_cell", "aveE2CCV": "average_edge_to_cell_vector",
@@ -37,13 +35,45 @@ _ALIASES = {
     "aveN2CC": "average_node_to_cell",
     "aveCC2F": "average_cell_to_face", "aveCCV2F": "average_cell_vector_to_face",
     "aveN2E": "average_node_to_edge", "aveN2F": "average_node_to_face",
-    "nodalGrad": "nodal_gradient", "edgeCurl": "edge_curl", "faceDiv": "face_divergence",
+    "gridFx": "faces_x", "gridFy": "faces_y", "gridFz": "faces_z", "gridEx": "edges_x", "gridEy": "edges_y", "gridEz": "edges_z",
+    "setCellGradBC": "set_cell_gradient_BC",
+    "projectFaceVector": "project_face_vector", "projectEdgeVector": "project_edge_vector",
+    "getBCProjWF": "get_BC_projections", "getBCProjWF_simple": "get_BC_projections_simple",
     "getFaceInnerProduct": "get_face_inner_product", "getEdgeInnerProduct": "get_edge_inner_product",
     "getFaceInnerProductDeriv": "get_face_inner_product_deriv",
     "getEdgeInnerProductDeriv": "get_edge_inner_product_deriv",
     "getInterpolationMat": "get_interpolation_matrix",
     "isInside": "is_inside", "getTensor": "get_tensor",
 }
+
+# names the reference has removed: they raise NotImplementedError pointing at the new name (utils/code_utils.py:225-245)
+_REMOVED = {
+    "area": "face_areas", "areaFx": "face_x_areas", "areaFy": "face_y_areas", "areaFz": "face_z_areas",
+    "cellBoundaryInd": "cell_boundary_indices", "cellGrad": "cell_gradient", "cellGradBC": "cell_gradient_BC",
+    "cellGradx": "cell_gradient_x", "cellGrady": "cell_gradient_y", "cellGradz": "cell_gradient_z",
+    "edge": "edge_lengths", "edgeCurl": "edge_curl", "edgeEx": "edge_x_lengths", "edgeEy": "edge_y_lengths",
+    "edgeEz": "edge_z_lengths", "faceBoundaryInd": "face_boundary_indices", "faceDiv": "face_divergence",
+    "faceDivx": "face_x_divergence", "faceDivy": "face_y_divergence", "faceDivz": "face_z_divergence",
+    "nodalGrad": "nodal_gradient", "nodalLaplacian": "nodal_laplacian", "normals": "face_normals",
+    "tangents": "edge_tangents", "vectorCCx": "cell_centers_x", "vectorCCy": "cell_centers_y",
+    "vectorCCz": "cell_centers_z", "vectorNx": "nodes_x", "vectorNy": "nodes_y", "vectorNz": "nodes_z",
+    "vol": "cell_volumes",
+}
+_REMOVED_INDEXED = {       # base/base_regular_mesh.py / base_tensor_mesh.py: removed per-axis shorthands
+    **{"h" + c: f"mesh.h[{i}]" for i, c in enumerate("xyz")},
+    **{"nC" + c: f"mesh.shape_cells[{i}]" for i, c in enumerate("xyz")},
+    **{"nN" + c: f"mesh.shape_nodes[{i}]" for i, c in enumerate("xyz")},
+}
+
+
+def removed_name(cls_name, name, table=_REMOVED):
+    """NotImplementedError for a name the reference has removed, or None."""
+    if name in table:
+        return NotImplementedError(f"{cls_name}.{name} has been removed, please use {cls_name}.{table[name]}.")
+    if name in _REMOVED_INDEXED:
+        return NotImplementedError(f"The {name} property is removed, please access as {_REMOVED_INDEXED[name]}. "
+                                   "This message will be removed in discretize 1.0.0.")
+    return None
 
 
 def _validate_BC(bc):
@@ -143,6 +173,9 @@ class TensorMesh:
         # alias table, like BaseMesh.__getattr__ (base/base_mesh.py:24-48)
         if name in _ALIASES:
             return getattr(self, _ALIASES[name])
+        err = removed_name(type(self).__name__, name)
+        if err is not None:
+            raise err
         raise AttributeError(f"'{type(self).__name__}' object has no attribute '{name}'")
 
     # ---- basic description ---------------------------------------------------------------
@@ -324,6 +357,8 @@ class TensorMesh:
 
     def _grid(self, key):
         t = self.get_tensor(key)
+        if self.dim == 1:  # the reference returns flat arrays for 1-D meshes (base_tensor_mesh.py:735-741)
+            return np.asarray(t[0], dtype=np.float64).copy()
         mesh = np.meshgrid(*t, indexing="ij")
         return np.stack([m.reshape(-1, order="F") for m in mesh], axis=1)
 
@@ -380,6 +415,218 @@ class TensorMesh:
         return np.r_[self._outer(hx, np.ones((ny + 1) * (nz + 1))),
                      self._outer(np.ones(nx + 1), self._outer(hy, np.ones(nz + 1))),
                      self._outer(np.ones((nx + 1) * (ny + 1)), hz)]
+
+    # ---- small host-side conveniences of the reference (base_regular_mesh.py:130-330, base_tensor_mesh.py:311-356,
+    # tensor_mesh.py:312-517, 518-760) ----------------------------------------------------------------------
+
+    def _split(self, vec, counts, a, what="faces"):
+        if a >= self.dim:   # tensor_mesh.py:366-367, 398-399, 466-467, 499-500 (the z-edge message says "y-edges" there too)
+            label = "xyz"[a] if what == "faces" else "y"
+            raise Exception("{}D meshes do not have {}-{}".format(self.dim, label, what.capitalize() if what == "faces" else what))
+        o = np.r_[0, np.cumsum(counts)]
+        return vec[o[a]:o[a + 1]]
+
+    face_x_areas = property(lambda self: self._split(self.face_areas, self.n_faces_per_direction, 0))
+    face_y_areas = property(lambda self: self._split(self.face_areas, self.n_faces_per_direction, 1))
+    face_z_areas = property(lambda self: self._split(self.face_areas, self.n_faces_per_direction, 2))
+    edge_x_lengths = property(lambda self: self._split(self.edge_lengths, self.n_edges_per_direction, 0, "edges"))
+    edge_y_lengths = property(lambda self: self._split(self.edge_lengths, self.n_edges_per_direction, 1, "edges"))
+    edge_z_lengths = property(lambda self: self._split(self.edge_lengths, self.n_edges_per_direction, 2, "edges"))
+
+    @property
+    def h_gridded(self):
+        """(n_cells, dim) widths of every cell."""
+        if self.dim == 1:
+            return self.h[0][:, None]
+        grids = np.meshgrid(*self.h, indexing="ij")
+        return np.stack([g.reshape(-1, order="F") for g in grids], axis=1)
+
+    @property
+    def faces(self):
+        if self.dim == 1:
+            return self._grid("faces_x")
+        return np.concatenate([self._grid("faces_" + "xyz"[a]) for a in range(self.dim)])
+
+    @property
+    def edges(self):
+        if self.dim == 1:
+            return self._grid("edges_x")
+        return np.concatenate([self._grid("edges_" + "xyz"[a]) for a in range(self.dim)])
+
+    def _unit_vectors(self, counts):
+        if self.dim == 1:
+            return None  # the reference defines these for 2-D and 3-D only (base_rectangular_mesh.py:588-660)
+        out = np.zeros((int(sum(counts)), self.dim))
+        o = np.r_[0, np.cumsum(counts)]
+        for a in range(self.dim):
+            out[o[a]:o[a + 1], a] = 1.0
+        return out
+
+    face_normals = property(lambda self: self._unit_vectors(self.n_faces_per_direction))
+    edge_tangents = property(lambda self: self._unit_vectors(self.n_edges_per_direction))
+
+    @property
+    def cell_boundary_indices(self):
+        """Boolean masks of the cells touching the -x, +x, (-y, +y, (-z, +z)) boundary (tensor_mesh.py:677-760)."""
+        idx = np.indices(self.shape_cells)
+        out = []
+        for a in range(self.dim):
+            ia = idx[a].reshape(-1, order="F")
+            out += [ia == 0, ia == self.shape_cells[a] - 1]
+        return tuple(out)
+
+    @property
+    def face_boundary_indices(self):
+        """Boolean masks over the faces of each direction that lie on the lower / upper boundary (tensor_mesh.py:518-594)."""
+        out = []
+        for a in range(self.dim):
+            shp = self._shape((a,))
+            ia = np.indices(shp)[a].reshape(-1, order="F")
+            out += [ia == 0, ia == shp[a] - 1]
+        return tuple(out)
+
+    @property
+    def cell_bounds(self):
+        """(n_cells, 2 dim): x1, x2, (y1, y2, (z1, z2)) of every cell (tensor_mesh.py:597-614)."""
+        cols = []
+        for a in range(self.dim):
+            x = self.get_tensor("nodes")[a]
+            for side in (x[:-1], x[1:]):
+                grids = np.meshgrid(*[side if b == a else np.zeros(self.shape_cells[b]) for b in range(self.dim)], indexing="ij")
+                cols.append(grids[a].reshape(-1, order="F"))
+        return np.stack(cols, axis=1)
+
+    @property
+    def cell_nodes(self):
+        """(n_cells, 2**dim) node numbers of every cell, x fastest within a cell (tensor_mesh.py:617-674)."""
+        idx = np.arange(self.n_nodes).reshape(self.shape_nodes, order="F")
+        corners = []
+        for c in range(2 ** self.dim):
+            sl = tuple(slice(1, None) if (c >> a) & 1 else slice(None, -1) for a in range(self.dim))
+            corners.append(idx[sl].reshape(-1, order="F"))
+        return np.stack(corners, axis=-1)
+
+    def point2index(self, locs):
+        """Index of the cell containing (or nearest to) each point (tensor_mesh.py:759-784)."""
+        locs = as_array_n_by_dim(locs, self.dim)
+        tensors = self.get_tensor("nodes")
+        multi = tuple(np.clip(np.searchsorted(n, p) - 1, 0, len(n) - 2) for n, p in zip(tensors, locs.T))
+        if self.dim == 1:
+            return multi[0]
+        return np.ravel_multi_index(multi, self.shape_cells, order="F")
+
+    def closest_points_index(self, locations, grid_loc="CC", discard=False):
+        """Index of the closest grid location to each point (base/base_mesh.py:3999-4064)."""
+        from scipy.spatial import KDTree
+
+        locations = as_array_n_by_dim(locations, self.dim)
+        grid_loc = self._parse_location_type(grid_loc)
+        key = f"_{grid_loc}_tree"
+        tree = self._cache.get(key)
+        if tree is None:
+            tree = KDTree(as_array_n_by_dim(getattr(self, grid_loc), self.dim))
+        if not discard:
+            self._cache[key] = tree
+        return tree.query(locations)[1]
+
+    def project_face_vector(self, face_vectors):
+        """Dot product of one vector per face with the face normals (base/base_mesh.py:627-655)."""
+        if not isinstance(face_vectors, np.ndarray):
+            raise Exception("face_vectors must be an ndarray")
+        if not (face_vectors.ndim == 2 and face_vectors.shape == (self.n_faces, self.dim)):
+            raise Exception("face_vectors must be an ndarray of shape (n_faces, dim)")
+        return np.sum(face_vectors * self.face_normals, 1)
+
+    def project_edge_vector(self, edge_vectors):
+        """Dot product of one vector per edge with the edge tangents (base/base_mesh.py:657-685)."""
+        if not isinstance(edge_vectors, np.ndarray):
+            raise Exception("edge_vectors must be an ndarray")
+        if not (edge_vectors.ndim == 2 and edge_vectors.shape == (self.n_edges, self.dim)):
+            raise Exception("edge_vectors must be an ndarray of shape (nE, dim)")
+        return np.sum(edge_vectors * self.edge_tangents, 1)
+
+    # ---- host matrices for the host-assembled operators (boundary terms, surface / line inner products) ------------
+    def _host_matrix(self, name):
+        """scipy CSR of ``self.<name>`` assembled on the host (any dimension), cached; no GPU involved."""
+        key = ("host", name)
+        if key not in self._cache:
+            from . import lowdim
+
+            self._cache[key] = lowdim.build(self, name)
+        return self._cache[key]
+
+    def _boundary_indices(self):
+        face, edge, node = self._boundary_masks()
+        return np.nonzero(face)[0], (None if edge is None else np.nonzero(edge)[0]), np.nonzero(node)[0]
+
+    def _boundary_face_rows(self, name):
+        from . import lowdim
+
+        return lowdim.boundary_face_rows(self, name)
+
+    # ---- weak-form boundary pieces (boundary_ops.py) ------------------------------------------------------------
+    def edge_divergence_weak_form_robin(self, alpha=0.0, beta=1.0, gamma=0.0):
+        from . import boundary_ops
+
+        return boundary_ops.edge_divergence_weak_form_robin(self, alpha, beta, gamma)
+
+    def cell_gradient_weak_form_robin(self, alpha=0.0, beta=1.0, gamma=0.0):
+        from . import boundary_ops
+
+        return boundary_ops.cell_gradient_weak_form_robin(self, alpha, beta, gamma)
+
+    @property
+    def boundary_edge_vector_integral(self):
+        from . import boundary_ops
+
+        return boundary_ops.boundary_edge_vector_integral(self)
+
+    @property
+    def boundary_node_vector_integral(self):
+        from . import boundary_ops
+
+        return boundary_ops.boundary_node_vector_integral(self)
+
+    def get_BC_projections(self, BC, discretization="CC"):
+        from . import boundary_ops
+
+        return boundary_ops.get_BC_projections(self, BC, discretization)
+
+    def get_BC_projections_simple(self, discretization="CC"):
+        from . import boundary_ops
+
+        return boundary_ops.get_BC_projections_simple(self, discretization)
+
+    # ---- face / edge hosted properties (surface_products.py) -------------------------------------------------------
+    def get_face_inner_product_surface(self, model=None, invert_model=False, invert_matrix=False, **kwargs):
+        from . import surface_products
+
+        return surface_products.inner_product(self, "face_surface", model, invert_model, invert_matrix)
+
+    def get_edge_inner_product_surface(self, model=None, invert_model=False, invert_matrix=False, **kwargs):
+        from . import surface_products
+
+        return surface_products.inner_product(self, "edge_surface", model, invert_model, invert_matrix)
+
+    def get_edge_inner_product_line(self, model=None, invert_model=False, invert_matrix=False, **kwargs):
+        from . import surface_products
+
+        return surface_products.inner_product(self, "edge_line", model, invert_model, invert_matrix)
+
+    def get_face_inner_product_surface_deriv(self, model, invert_model=False, invert_matrix=False, **kwargs):
+        from . import surface_products
+
+        return surface_products.inner_product_deriv(self, "face_surface", model, invert_model, invert_matrix)
+
+    def get_edge_inner_product_surface_deriv(self, model, invert_model=False, invert_matrix=False, **kwargs):
+        from . import surface_products
+
+        return surface_products.inner_product_deriv(self, "edge_surface", model, invert_model, invert_matrix)
+
+    def get_edge_inner_product_line_deriv(self, model, invert_model=False, invert_matrix=False, **kwargs):
+        from . import surface_products
+
+        return surface_products.inner_product_deriv(self, "edge_line", model, invert_model, invert_matrix)
 
     # ---- device state ---------------------------------------------------------------------------
     def _require_3d(self, what):

@@ -18,7 +18,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from .octree import LinearOctree
-from .tensor_mesh import _ALIASES, as_array_n_by_dim, is_scalar, unpack_widths
+from .tensor_mesh import TensorMesh, _ALIASES, _REMOVED, as_array_n_by_dim, is_scalar, removed_name, unpack_widths
 from .tree_build import TreeTopology, key3
 
 
@@ -36,8 +36,15 @@ _TREE_ALIASES.update({
 })
 
 
+_TREE_REMOVED = dict(_REMOVED)
+_TREE_REMOVED.update({"cellGradStencil": "cell_gradient_stencil", "maxLevel": "max_used_level",
+                      "permuteCC": "permute_cells", "permuteE": "permute_edges", "permuteF": "permute_faces"})
+
+
 class TreeMesh:
     _meshType = "TREE"
+    _LOC_NAMES = TensorMesh._LOC_NAMES
+    _parse_location_type = TensorMesh._parse_location_type
 
     def __init__(self, h=None, origin=None, diagonal_balance=None, **kwargs):
         if "x0" in kwargs:
@@ -81,6 +88,9 @@ class TreeMesh:
     def __getattr__(self, name):
         if name in _TREE_ALIASES:
             return getattr(self, _TREE_ALIASES[name])
+        err = removed_name(type(self).__name__, name, _TREE_REMOVED)
+        if err is not None:
+            raise err
         raise AttributeError(f"'{type(self).__name__}' object has no attribute '{name}'")
 
     # ---- description ------------------------------------------------------------------------------
@@ -413,6 +423,160 @@ class TreeMesh:
     faces_y = property(lambda self: self._grid(self._t().faces[1], axes=(0, 2)))
     faces_z = property(lambda self: self._grid(self._t().faces[2], axes=(0, 1)))
 
+    hanging_edges_x = property(lambda self: self._grid(self._t().edges[0], True, axes=(0,))[self._t().edges[0].n:])
+    hanging_edges_y = property(lambda self: self._grid(self._t().edges[1], True, axes=(1,))[self._t().edges[1].n:])
+    hanging_edges_z = property(lambda self: self._grid(self._t().edges[2], True, axes=(2,))[self._t().edges[2].n:])
+    hanging_faces_x = property(lambda self: self._grid(self._t().faces[0], True, axes=(1, 2))[self._t().faces[0].n:])
+    hanging_faces_y = property(lambda self: self._grid(self._t().faces[1], True, axes=(0, 2))[self._t().faces[1].n:])
+    hanging_faces_z = property(lambda self: self._grid(self._t().faces[2], True, axes=(0, 1))[self._t().faces[2].n:])
+    total_nodes = property(lambda self: np.vstack((self.nodes, self.hanging_nodes)))        # tree_mesh.py:801-814
+    faces = property(lambda self: np.r_[self.faces_x, self.faces_y, self.faces_z])
+    edges = property(lambda self: np.r_[self.edges_x, self.edges_y, self.edges_z])
+    vntF = property(lambda self: [self.n_total_faces_x, self.n_total_faces_y, self.n_total_faces_z])
+    vntE = property(lambda self: [self.n_total_edges_x, self.n_total_edges_y, self.n_total_edges_z])
+    nodes_x = property(lambda self: self._xs[0][::2].copy())         # the underlying tensor grid (base_tensor_mesh.py:89-155)
+    nodes_y = property(lambda self: self._xs[1][::2].copy())
+    nodes_z = property(lambda self: self._xs[2][::2].copy())
+    cell_centers_x = property(lambda self: (self.nodes_x[1:] + self.nodes_x[:-1]) / 2)
+    cell_centers_y = property(lambda self: (self.nodes_y[1:] + self.nodes_y[:-1]) / 2)
+    cell_centers_z = property(lambda self: (self.nodes_z[1:] + self.nodes_z[:-1]) / 2)
+
+    @property
+    def max_used_level(self):
+        """Finest level any cell is refined to (tree_ext.pyx:1611-1626)."""
+        self._t()
+        return int(self._levels.max())
+
+    def _unit_vectors(self, counts):
+        out = np.zeros((int(sum(counts)), 3))
+        o = np.r_[0, np.cumsum(counts)]
+        for a in range(3):
+            out[o[a]:o[a + 1], a] = 1.0
+        return out
+
+    face_normals = property(lambda self: self._unit_vectors(self.n_faces_per_direction))
+    edge_tangents = property(lambda self: self._unit_vectors(self.n_edges_per_direction))
+
+    @property
+    def cell_bounds(self):
+        """(n_cells, 6): x1, x2, y1, y2, z1, z2 of every cell (tree_ext.pyx:1302-1314)."""
+        t = self._t()
+        cols = []
+        for d in range(3):
+            cols += [self._xs[d][t.centers[:, d] - t.half], self._xs[d][t.centers[:, d] + t.half]]
+        return np.stack(cols, axis=1)
+
+    @property
+    def cell_nodes(self):
+        """(n_cells, 8) node numbers of every cell, hanging nodes included (tree_ext.pyx:6407-6430)."""
+        t = self._t()
+        return t.nodes.index[t.cell_nodes]
+
+    @property
+    def edge_nodes(self):
+        """Per direction, (n_total_edges_d, 2) numbers of the two end nodes of every edge (tree_ext.pyx:6433-6470)."""
+        t = self._t()
+        unit = np.eye(3, dtype=np.int64)
+        out = []
+        for d in range(3):
+            e = t.edges[d]
+            ends = np.empty((e.n_total, 2), dtype=np.int64)
+            for k, sgn in enumerate((-1, 1)):
+                q = e.loc + sgn * e.half[:, None] * unit[d]
+                ends[e.index, k] = t.nodes.index[np.searchsorted(t.nodes.keys, key3(q[:, 0], q[:, 1], q[:, 2]))]
+            out.append(ends)
+        return tuple(out)
+
+    def is_inside(self, pts, location_type="nodes", **kwargs):
+        """Whether points are inside the domain (base_tensor_mesh.py:638-682, on the underlying tensor grid)."""
+        pts = as_array_n_by_dim(pts, 3)
+        tensors = [self.nodes_x, self.nodes_y, self.nodes_z]
+        inside = np.ones(pts.shape[0], dtype=bool)
+        for i, tensor in enumerate(tensors):
+            tol = (tensor.max() - tensor.min()) * 1.0e-10       # TOL of base_tensor_mesh.py
+            inside = inside & (pts[:, i] >= tensor.min() - tol) & (pts[:, i] <= tensor.max() + tol)
+        return inside
+
+    def _lexsorted(self, grids):
+        o, out = 0, []
+        for g in grids:
+            out.append(np.lexsort(g.T) + o)
+            o += g.shape[0]
+        p = np.concatenate(out)
+        from .csr import CsrOperator
+
+        return CsrOperator(sp.csr_matrix((np.ones(p.size), (np.arange(p.size), p)), shape=(p.size, p.size)))
+
+    # permutations that sort by x, then y, then z (tree_mesh.py:1037-1083)
+    permute_cells = property(lambda self: self._lexsorted([self.cell_centers]))
+    permute_faces = property(lambda self: self._lexsorted([self.faces_x, self.faces_y, self.faces_z]))
+    permute_edges = property(lambda self: self._lexsorted([self.edges_x, self.edges_y, self.edges_z]))
+
+    # ---- boundary (tree_ext.pyx:2104-2125, 2328-2370, 2543-2610, 5514-5628) ------------------------------------------
+    def _boundary_masks(self):
+        """Masks over the non-hanging faces / edges / nodes on the domain boundary, in the reference's numbering."""
+        if "bmask" not in self._cache:
+            t = self._t()
+            lim = t.shape_half
+
+            def at_limit(fam, axes):
+                m = np.zeros(fam.n_total, dtype=bool)
+                for a in axes:
+                    m |= (fam.loc[:, a] == 0) | (fam.loc[:, a] == lim[a])
+                out = np.empty(fam.n_total, dtype=bool)
+                out[fam.index] = m
+                return out[:fam.n]
+
+            face = np.concatenate([at_limit(t.faces[d], (d,)) for d in range(3)])
+            edge = np.concatenate([at_limit(t.edges[d], [a for a in range(3) if a != d]) for d in range(3)])
+            node = at_limit(t.nodes, (0, 1, 2))
+            self._cache["bmask"] = (face, edge, node)
+        return self._cache["bmask"]
+
+    def _boundary_indices(self):
+        return tuple(np.nonzero(m)[0] for m in self._boundary_masks())
+
+    def _selection(self, key, mask):
+        if key not in self._cache:
+            from .csr import CsrOperator
+
+            idx = np.nonzero(mask)[0]
+            self._cache[key] = CsrOperator(sp.csr_matrix((np.ones(idx.size), (np.arange(idx.size), idx)),
+                                                         shape=(idx.size, mask.size)))
+        return self._cache[key]
+
+    project_face_to_boundary_face = property(lambda self: self._selection("P_bf", self._boundary_masks()[0]))
+    project_edge_to_boundary_edge = property(lambda self: self._selection("P_be", self._boundary_masks()[1]))
+    project_node_to_boundary_node = property(lambda self: self._selection("P_bn", self._boundary_masks()[2]))
+    boundary_faces = property(lambda self: self.faces[self._boundary_masks()[0]])
+    boundary_edges = property(lambda self: self.edges[self._boundary_masks()[1]])
+    boundary_nodes = property(lambda self: self.nodes[self._boundary_masks()[2]])
+
+    @property
+    def boundary_face_outward_normals(self):
+        t = self._t()
+        normals = self.face_normals
+        low = []
+        for d in range(3):
+            f = t.faces[d]
+            m = np.empty(f.n_total, dtype=bool)
+            m[f.index] = f.loc[:, d] == 0
+            low.append(m[:f.n])
+        normals[np.concatenate(low)] *= -1
+        return normals[self._boundary_masks()[0]]
+
+    @property
+    def boundary_face_scalar_integral(self):
+        """diag(face_areas) P^T diag(+-1) (differential_operators.py:2183-2197)."""
+        from .csr import CsrOperator
+
+        bf = self._boundary_indices()[0]
+        sign = self.boundary_face_outward_normals.sum(axis=1)
+        return CsrOperator(sp.csr_matrix((self.face_areas[bf] * sign, (bf, np.arange(bf.size))), shape=(self.n_faces, bf.size)))
+
+    def _boundary_face_rows(self, name):
+        return self._host_matrix(name)[self._boundary_indices()[0]]
+
     # ---- host assembly of the operators (once per mesh) ---------------------------------------------------------
     def _deflate(self, fam, parents, weights):
         """R (n_total x n): identity on non-hanging, parent weights on hanging rows, applied until no
@@ -528,6 +692,11 @@ class TreeMesh:
         elif name.startswith("stencil_cell_gradient") or name.startswith("average_cell_to_total_face_") \
                 or name.startswith("average_cell_to_face") or name == "average_cell_vector_to_face":
             parts.append((0, self._host_cell_to_face(name)))
+        elif name[:-2] in ("average_node_to_edge", "average_node_to_face") and name[-2] == "_":
+            # tree_ext.pyx:4765-4875, 4920-5040: the row block of one direction
+            d = "xyz".index(name[-1])
+            o = np.r_[0, np.cumsum([f.n for f in (t.edges if "edge" in name else t.faces)])]
+            parts.append((0, self._host_parts(name[:-2])[1][0][1][o[d]:o[d + 1]]))
         elif name == "average_node_to_edge":  # tree_ext.pyx:4765-4918: 1/2 at the two end nodes, deflate nodes
             nE = [e.n for e in t.edges]
             offEn = np.r_[0, np.cumsum(nE)]
@@ -798,6 +967,12 @@ class TreeMesh:
     average_node_to_edge = property(lambda self: self._operator("average_node_to_edge"))
     average_node_to_face = property(lambda self: self._operator("average_node_to_face"))
     average_edge_to_face = property(lambda self: self._operator("average_edge_to_face"))
+    average_node_to_edge_x = property(lambda self: self._operator("average_node_to_edge_x"))
+    average_node_to_edge_y = property(lambda self: self._operator("average_node_to_edge_y"))
+    average_node_to_edge_z = property(lambda self: self._operator("average_node_to_edge_z"))
+    average_node_to_face_x = property(lambda self: self._operator("average_node_to_face_x"))
+    average_node_to_face_y = property(lambda self: self._operator("average_node_to_face_y"))
+    average_node_to_face_z = property(lambda self: self._operator("average_node_to_face_z"))
 
     # ---- mass matrices (shared _fastInnerProduct: base/base_tensor_mesh.py:792-863) -----------------------------
     def get_face_inner_product(self, model=None, invert_model=False, invert_matrix=False, do_fast=True, **kwargs):
@@ -824,6 +999,86 @@ class TreeMesh:
         return make_tree_mass_deriv(self, "E", model, do_fast, invert_model, invert_matrix)
 
     # ---- point location and interpolation (node variant) -----------------------------------------------
+    # ---- weak-form boundary pieces and face / edge hosted properties: shared with TensorMesh -----------------------
+    def project_face_vector(self, face_vectors):
+        if not isinstance(face_vectors, np.ndarray):
+            raise Exception("face_vectors must be an ndarray")
+        if not (face_vectors.ndim == 2 and face_vectors.shape == (self.n_faces, 3)):
+            raise Exception("face_vectors must be an ndarray of shape (n_faces, dim)")
+        return np.sum(face_vectors * self.face_normals, 1)
+
+    def project_edge_vector(self, edge_vectors):
+        if not isinstance(edge_vectors, np.ndarray):
+            raise Exception("edge_vectors must be an ndarray")
+        if not (edge_vectors.ndim == 2 and edge_vectors.shape == (self.n_edges, 3)):
+            raise Exception("edge_vectors must be an ndarray of shape (nE, dim)")
+        return np.sum(edge_vectors * self.edge_tangents, 1)
+
+    def closest_points_index(self, locations, grid_loc="CC", discard=False):
+        from scipy.spatial import KDTree
+
+        locations = as_array_n_by_dim(locations, 3)
+        grid_loc = self._parse_location_type(grid_loc)
+        key = f"_{grid_loc}_tree"
+        tree = self._cache.get(key)
+        if tree is None:
+            tree = KDTree(getattr(self, grid_loc))
+        if not discard:
+            self._cache[key] = tree
+        return tree.query(locations)[1]
+
+    def edge_divergence_weak_form_robin(self, alpha=0.0, beta=1.0, gamma=0.0):
+        from . import boundary_ops
+
+        return boundary_ops.edge_divergence_weak_form_robin(self, alpha, beta, gamma)
+
+    def cell_gradient_weak_form_robin(self, alpha=0.0, beta=1.0, gamma=0.0):
+        from . import boundary_ops
+
+        return boundary_ops.cell_gradient_weak_form_robin(self, alpha, beta, gamma)
+
+    @property
+    def boundary_edge_vector_integral(self):
+        from . import boundary_ops
+
+        return boundary_ops.boundary_edge_vector_integral(self)
+
+    @property
+    def boundary_node_vector_integral(self):
+        from . import boundary_ops
+
+        return boundary_ops.boundary_node_vector_integral(self)
+
+    def get_face_inner_product_surface(self, model=None, invert_model=False, invert_matrix=False, **kwargs):
+        from . import surface_products
+
+        return surface_products.inner_product(self, "face_surface", model, invert_model, invert_matrix)
+
+    def get_edge_inner_product_surface(self, model=None, invert_model=False, invert_matrix=False, **kwargs):
+        from . import surface_products
+
+        return surface_products.inner_product(self, "edge_surface", model, invert_model, invert_matrix)
+
+    def get_edge_inner_product_line(self, model=None, invert_model=False, invert_matrix=False, **kwargs):
+        from . import surface_products
+
+        return surface_products.inner_product(self, "edge_line", model, invert_model, invert_matrix)
+
+    def get_face_inner_product_surface_deriv(self, model, invert_model=False, invert_matrix=False, **kwargs):
+        from . import surface_products
+
+        return surface_products.inner_product_deriv(self, "face_surface", model, invert_model, invert_matrix)
+
+    def get_edge_inner_product_surface_deriv(self, model, invert_model=False, invert_matrix=False, **kwargs):
+        from . import surface_products
+
+        return surface_products.inner_product_deriv(self, "edge_surface", model, invert_model, invert_matrix)
+
+    def get_edge_inner_product_line_deriv(self, model, invert_model=False, invert_matrix=False, **kwargs):
+        from . import surface_products
+
+        return surface_products.inner_product_deriv(self, "edge_line", model, invert_model, invert_matrix)
+
     def _containing_cells(self, points):
         """Index of the leaf that contains (or is closest to) each point -- tree.cpp:758-766, 1499-1516: the root is
         found with ``x >= upper edge -> next root`` (ties go high), the descent with ``x > centre -> high child``
