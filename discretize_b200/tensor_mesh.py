@@ -331,14 +331,19 @@ class TensorMesh:
     }
 
     def _parse_location_type(self, location_type):
-        # reference: base/base_mesh.py:4182-4203
+        """Short names -> long names by their first letter; anything else passes through (base/base_mesh.py:4182-4203)."""
         if len(location_type) == 0:
             return location_type
-        if location_type in self._LOC_NAMES.values():
-            return location_type
-        if location_type in self._LOC_NAMES:
-            return self._LOC_NAMES[location_type]
-        raise ValueError(f"Unrecognized location type {location_type}")
+        first = location_type[0]
+        if first == "F":
+            return "faces_" + location_type[-1] if len(location_type) > 1 else "faces"
+        if first == "E":
+            return "edges_" + location_type[-1] if len(location_type) > 1 else "edges"
+        if first == "N":
+            return "nodes"
+        if first == "C":
+            return "cell_centers_" + location_type[-1] if len(location_type) > 2 else "cell_centers"
+        return location_type
 
     def get_tensor(self, key):
         """The 1-D sample vectors of a location grid (base/base_tensor_mesh.py:567-634)."""

@@ -1117,10 +1117,9 @@ class TreeMesh:
         return self._containing_cells(as_array_n_by_dim(np.asarray(locs, dtype=np.float64), 3))
 
     def get_interpolation_matrix(self, loc, location_type="cell_centers", zeros_outside=False, **kwargs):
-        """Trilinear interpolation from the NODES of the containing cell, hanging nodes eliminated (``_getNodeIntMat``,
-        tree_ext.pyx:6116-6179).  The edge / face / cell-centre variants of the reference depend on the order of the
-        points (direction-swap state carried across loop iterations) and leave rows uninitialised with
-        ``zeros_outside``: not reproduced."""
+        """Interpolation from nodes (``_getNodeIntMat``, tree_ext.pyx:6116-6179), edges, faces or cell centres
+        (tree_interp.py; tree_ext.pyx:5765-6404) to arbitrary points, hanging entities eliminated; routing and errors of
+        tree_mesh.py:1003-1034.  Assembled on the host, applied on the GPU by ``dzb_csr_spmv``."""
         if "locType" in kwargs:
             raise TypeError("The locType keyword argument has been removed, please use location_type. "
                             "This will be removed in discretize 1.0.0")
@@ -1129,13 +1128,22 @@ class TreeMesh:
                             "This will be removed in discretize 1.0.0")
         if kwargs:
             raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
-        lt = {"N": "nodes", "nodes": "nodes"}.get(location_type)
-        if lt is None:
-            raise NotImplementedError(
-                f"TreeMesh.get_interpolation_matrix(location_type={location_type!r}): only 'nodes' is built (SURVEY N3)")
+        from . import tree_interp
         from .csr import CsrOperator
 
-        return CsrOperator(self._host_node_interpolation(loc, zeros_outside))
+        location_type = self._parse_location_type(location_type)
+        pts = as_array_n_by_dim(np.asarray(loc, dtype=np.float64), 3)
+        if location_type == "nodes":
+            A = self._host_node_interpolation(pts, zeros_outside)
+        elif location_type in ("edges_x", "edges_y", "edges_z"):
+            A = tree_interp.edge_interpolation(self, pts, zeros_outside, location_type[-1])
+        elif location_type in ("faces_x", "faces_y", "faces_z"):
+            A = tree_interp.face_interpolation(self, pts, zeros_outside, location_type[-1])
+        elif location_type == "cell_centers":
+            A = tree_interp.cell_interpolation(self, pts, zeros_outside)
+        else:
+            raise ValueError("Location must be a grid location, not {}".format(location_type))
+        return CsrOperator(A)
 
     def _host_node_interpolation(self, loc, zeros_outside):
         t = self._t()

@@ -238,6 +238,32 @@ def test_tree_node_interpolation(gold, tag):
         assert_same_matrix(Q.tocsr(), ref)
 
 
+@pytest.mark.parametrize("loc", ["Ex", "Fy", "CC"])
+def test_tree_edge_face_cell_interpolation(loc):
+    """Edge / face / cell-centre interpolation (tree_interp.py) applied on the GPU against the reference's matrix
+    (tests/golden/tree_interp_small.npz, bit-exact on the host in test_tree_interp_cpu.py)."""
+    import os
+    import sys
+
+    import scipy.sparse as sp
+
+    import discretize_b200 as dz
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import boundary_cases as bc
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tree_interp_small.npz"))
+    tag, h, origin = bc.tree_specs()[1]
+    m = bc.build_tree(dz.TreeMesh, h, origin)
+    ref = sp.csr_matrix((g[f"{tag}|{loc}|data"], g[f"{tag}|{loc}|indices"], g[f"{tag}|{loc}|indptr"]),
+                        shape=tuple(g[f"{tag}|{loc}|shape"]))
+    Q = m.get_interpolation_matrix(g[f"{tag}|points"], loc)
+    rng = np.random.default_rng(19)
+    x, y = rng.standard_normal(ref.shape[1]), rng.standard_normal(ref.shape[0])
+    assert_close_vec(Q @ x, ref @ x)
+    assert_close_vec(Q.T @ y, ref.T @ y)
+
+
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_tree_tensor_model_derivative(gold, tag):
     g2 = load_golden("tree_n2_small.npz")
