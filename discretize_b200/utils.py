@@ -1,9 +1,16 @@
 """Utilities that sit next to the operator path (reference: ``discretize.utils``).
 
-``volume_average`` -- conservative model transfer between two TensorMeshes: every output cell takes the
-overlap-volume weighted mean of the input cells it intersects (``utils/interpolation_utils.py:175-287`` ->
-``_extensions/interputils_cython.pyx:186-332``).  The operator is separable, so it is assembled on the host from three
-1-D overlap lists with array passes (no per-entry loop) and applied on the GPU by the generic CSR kernel.
+``volume_average`` -- conservative model transfer between meshes: every output cell takes the
+overlap-volume weighted mean of the input cells it intersects (``utils/interpolation_utils.py:175-287``).
+
+* TensorMesh -> TensorMesh (``_extensions/interputils_cython.pyx:186-332``): the operator is separable, so it is assembled
+  from three 1-D overlap lists with array passes (no per-entry loop);
+* any pairing with a TreeMesh (``_extensions/tree_ext.pyx:6573-7053``): output boxes are clamped to the input domain, the
+  input cells overlapping each box are collected for ALL boxes at once -- index ranges on a tensor input, a level-by-level
+  descent of the linear octree on a tree input -- and weighted by the product of their 1-D overlaps, normalised per row.
+  Meshes on the same underlying tensor grid take the reference's shortcut (volume ratios / containing cells).
+
+Host assembly, applied on the GPU by the generic CSR kernel.
 """
 from __future__ import annotations
 
@@ -47,6 +54,151 @@ def _tensor_volume_average_matrix(mesh_in, mesh_out):
     return sp.csr_matrix((W, (Io, Ii)), shape=(mesh_out.n_cells, mesh_in.n_cells))
 
 
+# ---- pairings that involve a TreeMesh --------------------------------------------------------------------------------
+
+
+def _base_nodes(mesh):
+    if mesh._meshType == "TREE":
+        return [mesh.nodes_x, mesh.nodes_y, mesh.nodes_z]
+    return [mesh._nodes_1d(a) for a in range(mesh.dim)]
+
+
+def _same_base(mesh_a, mesh_b):
+    try:
+        return all(np.allclose(a, b) for a, b in zip(_base_nodes(mesh_a), _base_nodes(mesh_b)))
+    except ValueError:
+        return False
+
+
+def _expand_ranges(lo, hi):
+    """All index triples of the boxes [lo, hi) (one box per row), x fastest within a box: (box id, (n, 3) indices)."""
+    ext = np.maximum(hi - lo, 0)
+    cnt = ext[:, 0] * ext[:, 1] * ext[:, 2]
+    box = np.repeat(np.arange(lo.shape[0]), cnt)
+    local = np.arange(int(cnt.sum())) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+    ex, ey = ext[box, 0], ext[box, 1]
+    idx = np.stack([local % ex, (local // ex) % ey, local // (ex * ey)], axis=1) + lo[box]
+    return box, idx
+
+
+def _touching(lo, hi, a, b, active):
+    """Box [lo, hi] against cell [a, b], per axis: a genuine overlap where the axis is active, contact where the box
+    was collapsed onto the domain boundary (the reference tests closed intervals everywhere and then drops the
+    zero-volume pairs; this keeps the same pairs)."""
+    return np.where(active, (hi > a) & (lo < b), (hi >= a) & (lo <= b)).all(axis=1)
+
+
+def _tree_candidates(mesh_in, lo, hi, active):
+    """(box id, input cell) of every leaf of ``mesh_in`` that overlaps each box: descend the octree with all boxes
+    at once, one level per pass (tree.h:170-182 does the same per box, recursively)."""
+    tr = mesh_in._tree
+    xs = mesh_in._xs
+
+    def bounds(c, w):
+        a = np.stack([xs[d][2 * c[:, d] * w] for d in range(3)], axis=1)
+        b = np.stack([xs[d][2 * (c[:, d] + 1) * w] for d in range(3)], axis=1)
+        return a, b
+
+    w = tr.level_width(tr.root_level)
+    g = tr.grid(tr.root_level)
+    # roots: index ranges per axis (closed contact), then the exact test
+    r_lo = np.empty(lo.shape, dtype=np.int64)
+    r_hi = np.empty(lo.shape, dtype=np.int64)
+    for d in range(3):
+        nodes = xs[d][::2 * w]
+        r_lo[:, d] = np.clip(np.searchsorted(nodes, lo[:, d], side="left") - 1, 0, g[d])
+        r_hi[:, d] = np.clip(np.searchsorted(nodes, hi[:, d], side="right"), 0, g[d])
+    box, c = _expand_ranges(r_lo, r_hi)
+    offs = np.array([[i, j, k] for k in (0, 1) for j in (0, 1) for i in (0, 1)], dtype=np.int64)
+    out_box, out_lo = [], []
+    for l in range(tr.root_level, tr.max_level + 1):
+        if not box.size:
+            break
+        w = tr.level_width(l)
+        a, b = bounds(c, w)
+        keep = _touching(lo[box], hi[box], a, b, active[box])
+        box, c = box[keep], c[keep]
+        if l < tr.max_level and tr.div[l].size:
+            isdiv = np.isin(tr.pack(l, c), tr.div[l])
+        else:
+            isdiv = np.zeros(box.size, dtype=bool)
+        out_box.append(box[~isdiv])
+        out_lo.append(c[~isdiv] * w)
+        box = np.repeat(box[isdiv], 8)
+        c = (2 * c[isdiv][:, None, :] + offs[None, :, :]).reshape(-1, 3)
+    box = np.concatenate(out_box)
+    leaf_lo = np.concatenate(out_lo)
+    all_lo, _ = tr.leaves()
+    return box, np.searchsorted(tr.keys(all_lo), tr.keys(leaf_lo))
+
+
+def _tensor_candidates(mesh_in, lo, hi, active):
+    nodes = _base_nodes(mesh_in)
+    n = mesh_in.shape_cells
+    i_lo = np.empty(lo.shape, dtype=np.int64)
+    i_hi = np.empty(lo.shape, dtype=np.int64)
+    for d in range(3):       # tree_ext.pyx:6969-6979
+        i_lo[:, d] = np.maximum(np.searchsorted(nodes[d], lo[:, d], side="left") - 1, 0)
+        i_hi[:, d] = np.minimum(np.searchsorted(nodes[d], hi[:, d], side="right"), n[d])
+    box, idx = _expand_ranges(i_lo, i_hi)
+    a = np.stack([nodes[d][idx[:, d]] for d in range(3)], axis=1)
+    b = np.stack([nodes[d][idx[:, d] + 1] for d in range(3)], axis=1)
+    keep = _touching(lo[box], hi[box], a, b, active[box])
+    idx = idx[keep]
+    return box[keep], idx[:, 0] + n[0] * (idx[:, 1] + n[1] * idx[:, 2])
+
+
+def _overlap_volume_average_matrix(mesh_in, mesh_out):
+    if mesh_in.dim != 3:
+        raise NotImplementedError("volume_average with a TreeMesh is built for 3-D meshes")
+    base_in = _base_nodes(mesh_in)
+    origin = np.array([x[0] for x in base_in])
+    x_end = np.array([x[-1] for x in base_in])
+    bounds_out = np.asarray(mesh_out.cell_bounds)
+    lo = np.minimum(bounds_out[:, 0::2], x_end)           # a box beyond the input mesh collapses onto its boundary
+    hi = np.maximum(bounds_out[:, 1::2], origin)
+    active = (lo < x_end) & (hi > origin)
+    if mesh_in._meshType == "TREE":
+        box, cell = _tree_candidates(mesh_in, lo, hi, active)
+    else:
+        box, cell = _tensor_candidates(mesh_in, lo, hi, active)
+    bounds_in = np.asarray(mesh_in.cell_bounds)
+    a, b = bounds_in[cell, 0::2], bounds_in[cell, 1::2]
+    length = np.where(active[box], np.minimum(hi[box], b) - np.maximum(lo[box], a), 1.0)
+    weight = length[:, 0] * length[:, 1] * length[:, 2]
+    nz = weight != 0.0
+    box, cell, weight = box[nz], cell[nz], weight[nz]
+    total = np.bincount(box, weights=weight, minlength=mesh_out.n_cells)
+    return sp.csr_matrix((weight / total[box], (box, cell)), shape=(mesh_out.n_cells, mesh_in.n_cells))
+
+
+def _same_base_volume_average_matrix(mesh_in, mesh_out):
+    """Meshes refined from one tensor grid: nested cells, so weights are volume ratios or 1 (tree_ext.pyx:6627-6680,
+    6762-6775, 6900-6912)."""
+    n_in, n_out = mesh_in.n_cells, mesh_out.n_cells
+    if mesh_in._meshType == "TENSOR":                      # fine tensor cells -> the tree cell that contains them
+        rows = mesh_out.point2index(mesh_in.cell_centers)
+        w = mesh_in.cell_volumes / mesh_out.cell_volumes[rows]
+        return sp.csr_matrix((w, (rows, np.arange(n_in))), shape=(n_out, n_in))
+    if mesh_out._meshType == "TENSOR":                     # every fine tensor cell sits inside one tree cell
+        cols = mesh_in.point2index(mesh_out.cell_centers)
+        return sp.csr_matrix((np.ones(n_out), (np.arange(n_out), cols)), shape=(n_out, n_in))
+    # tree -> tree: input cells finer than their output cell contribute their volume share; output cells no input
+    # cell is finer than copy the input cell that contains them
+    rows = mesh_out.point2index(mesh_in.cell_centers)
+    lvl_in, lvl_out = mesh_in.cell_levels_by_index, mesh_out.cell_levels_by_index
+    finer = lvl_out[rows] < lvl_in
+    w = np.where(finer, mesh_in.cell_volumes / mesh_out.cell_volumes[rows], 0.0)
+    P = sp.csr_matrix((w, (rows, np.arange(n_in))), shape=(n_out, n_in))
+    visited = np.zeros(n_out, dtype=bool)
+    visited[rows[finer]] = True
+    rest = np.nonzero(~visited)[0]
+    if rest.size:
+        cols = mesh_in.point2index(mesh_out.cell_centers[rest])
+        P = P + sp.csr_matrix((np.ones(rest.size), (rest, cols)), shape=(n_out, n_in))
+    return sp.csr_matrix(P)
+
+
 def volume_average(mesh_in, mesh_out, values=None, output=None):
     """Volume-averaging interpolation between two meshes (reference: utils/interpolation_utils.py:175-287).
 
@@ -67,11 +219,15 @@ def volume_average(mesh_in, mesh_out, values=None, output=None):
         raise ValueError("Input array does not have the same length as the number of cells in input mesh")
     if output is not None and len(output) != mesh_out.n_cells:
         raise ValueError("Output array does not have the same length as the number of cells in output mesh")
-    if in_type != "TENSOR" or out_type != "TENSOR":
-        raise NotImplementedError("discretize_b200.utils.volume_average: only TensorMesh -> TensorMesh is built")
     from .csr import CsrOperator
 
-    op = CsrOperator(_tensor_volume_average_matrix(mesh_in, mesh_out))
+    if in_type == "TENSOR" and out_type == "TENSOR":
+        matrix = _tensor_volume_average_matrix(mesh_in, mesh_out)
+    elif _same_base(mesh_in, mesh_out):
+        matrix = _same_base_volume_average_matrix(mesh_in, mesh_out)
+    else:
+        matrix = _overlap_volume_average_matrix(mesh_in, mesh_out)
+    op = CsrOperator(matrix)
     if values is None:
         return op
     result = op @ values
