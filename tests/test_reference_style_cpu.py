@@ -1,0 +1,113 @@
+"""Tests in the style of the reference's own suite, on the host-assembled matrices of this package:
+mimetic identities on an OcTree with hanging entities (tests/tree/test_tree.py:215-233), equivalence of a fully refined
+OcTree with the TensorMesh after ``permute_*`` (tests/tree/test_tree.py:161-213), order of accuracy of OcTree
+interpolation (tests/tree/test_tree_interpolation.py:39-215) and Taylor tests of the surface / line inner-product
+derivatives (tests/base/test_tensor_innerproduct_derivs.py harness).  No GPU: ``_host_matrix`` / ``.tocsr()`` of
+host-assembled operators only."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import discretize_b200 as dz
+from oracle import tensor_ops as oracle
+
+
+def hanging_tree(n=16, levels=(3, 4)):
+    m = dz.TreeMesh([np.full(n, 1.0 / n)] * 3)
+    m.refine_ball(np.array([[0.3, 0.4, 0.5], [0.7, 0.6, 0.4]]), [0.2, 0.15], list(levels))
+    assert m.n_hanging_faces > 0 and m.n_hanging_edges > 0
+    return m
+
+
+def test_tree_mimetic_identities():
+    m = hanging_tree()
+    D, C, G = m._host_matrix("face_divergence"), m._host_matrix("edge_curl"), m._host_matrix("nodal_gradient")
+    scale = abs(D).max() * abs(C).max()
+    assert abs(D @ C).max() <= 1e-13 * scale
+    assert abs(C @ G).max() <= 1e-13 * abs(C).max() * abs(G).max()
+
+
+def test_fully_refined_tree_is_the_tensor_mesh_after_permutation():
+    h = [np.array([1.0, 2.0, 1.5, 0.5]), np.array([0.7, 1.1, 0.9, 1.3]), np.array([2.0, 1.0, 0.5, 1.5])]
+    t = dz.TreeMesh(h)
+    t.refine(-1)
+    assert t.n_cells == 64 and t.n_hanging_faces == 0
+    Pc, Pf, Pe = (t.permute_cells.tocsr(), t.permute_faces.tocsr(), t.permute_edges.tocsr())
+    g = oracle.Grid(h)
+    vol, area, length = g.cell_volumes(), g.face_areas(), g.edge_lengths()
+    assert np.abs(Pc @ t.cell_volumes - vol).max() <= 1e-14 * vol.max()
+    assert np.abs(Pf @ t.face_areas - area).max() <= 1e-14 * area.max()
+    assert np.abs(Pe @ t.edge_lengths - length).max() <= 1e-14 * length.max()
+    D = Pc @ t._host_matrix("face_divergence") @ Pf.T
+    C = Pf @ t._host_matrix("edge_curl") @ Pe.T
+    assert abs(D - oracle.face_divergence(g)).max() <= 1e-13 * abs(D).max()
+    assert abs(C - oracle.edge_curl(g)).max() <= 1e-13 * abs(C).max()
+    Ae = Pc @ t._host_matrix("average_edge_to_cell") @ Pe.T
+    assert abs(Ae - oracle.average_edge_to_cell(g)).max() <= 1e-14
+
+
+FIELDS = {
+    "CC": lambda x: np.cos(2 * np.pi * x[:, 0]) * np.sin(np.pi * x[:, 1]) + x[:, 2] ** 2,
+    "N": lambda x: np.cos(2 * np.pi * x[:, 0]) * np.sin(np.pi * x[:, 1]) + x[:, 2] ** 2,
+    "Ex": lambda x: np.cos(2 * np.pi * x[:, 1]) + np.sin(np.pi * x[:, 2]) * x[:, 0],
+    "Fz": lambda x: np.cos(2 * np.pi * x[:, 0]) * x[:, 1] + np.sin(np.pi * x[:, 2]),
+}
+
+
+@pytest.mark.parametrize("loc", sorted(FIELDS))
+def test_tree_interpolation_order_of_accuracy(loc):
+    """Max error at random interior points drops ~4x per halving of h on meshes refined to the finest level around the
+    probe region (second order), like the reference's OrderTest for OcTree interpolation."""
+    rng = np.random.default_rng(9)
+    pts = 0.35 + 0.3 * rng.random((200, 3))
+    errs = []
+    for n in (8, 16, 32):
+        m = dz.TreeMesh([np.full(n, 1.0 / n)] * 3)
+        m.refine_box(np.array([[0.2, 0.2, 0.2]]), np.array([[0.8, 0.8, 0.8]]), [-1])
+        grid = {"CC": m.cell_centers, "N": m.nodes, "Ex": m.edges_x, "Fz": m.faces_z}[loc]
+        off = {"CC": 0, "N": 0, "Ex": 0, "Fz": m.n_faces_x + m.n_faces_y}[loc]
+        Q = m.get_interpolation_matrix(pts, loc).tocsr()
+        f = np.zeros(Q.shape[1])
+        f[off:off + grid.shape[0]] = FIELDS[loc](grid)
+        errs.append(np.abs(Q @ f - FIELDS[loc](pts)).max())
+    orders = np.log2(np.array(errs[:-1]) / np.array(errs[1:]))
+    assert orders.min() > 1.7, (errs, orders)
+
+
+@pytest.mark.parametrize("kind", ["get_face_inner_product_surface", "get_edge_inner_product_surface",
+                                  "get_edge_inner_product_line"])
+@pytest.mark.parametrize("invert_model", [False, True])
+@pytest.mark.parametrize("invert_matrix", [False, True])
+@pytest.mark.parametrize("mesh_kind", ["tensor", "tree"])
+def test_surface_and_line_inner_product_derivatives_taylor(kind, invert_model, invert_matrix, mesh_kind):
+    """f(m) = M(m) v: the first-order Taylor remainder with the derivative drops at second order."""
+    rng = np.random.default_rng(4)
+    mesh = dz.TensorMesh([rng.random(4) + .5, rng.random(3) + .5, rng.random(5) + .5]) if mesh_kind == "tensor" \
+        else hanging_tree(8, (2, 3))
+    n = mesh.n_edges if kind.endswith("line") else mesh.n_faces
+    v = rng.random(mesh.n_faces if kind.startswith("get_face") else mesh.n_edges)
+    m0, dm = rng.random(n) + 1.0, rng.random(n) * 0.5
+
+    def f(model):
+        return getattr(mesh, kind)(model, invert_model=invert_model, invert_matrix=invert_matrix).tocsr() @ v
+
+    J = getattr(mesh, kind + "_deriv")(m0, invert_model=invert_model, invert_matrix=invert_matrix)(v).tocsr()
+    e = [np.linalg.norm(f(m0 + s * dm) - f(m0) - s * (J @ dm)) for s in (1e-1, 1e-2, 1e-3)]
+    if max(e) > 1e-13 * np.linalg.norm(f(m0)):         # linear in the model: the remainder is rounding only
+        orders = np.log10(np.array(e[:-1]) / np.array(e[1:]))
+        assert orders.min() > 1.9, (e, orders)
+
+
+def test_robin_pieces_reduce_to_neumann_and_scale_with_alpha():
+    """beta = 1, alpha = gamma = 0 is the natural (Neumann) condition: B = 0 and b = 0; B is linear in alpha."""
+    for mesh in (dz.TensorMesh([5, 4, 3]), hanging_tree(8, (2, 3))):
+        B, b = mesh.edge_divergence_weak_form_robin(0.0, 1.0, 0.0)
+        assert B.tocsr().nnz == 0 or abs(B.tocsr()).max() == 0.0
+        assert np.abs(b).max() == 0.0
+        B1, _ = mesh.edge_divergence_weak_form_robin(1.0, 2.0, 0.0)
+        B3, _ = mesh.edge_divergence_weak_form_robin(3.0, 2.0, 0.0)
+        assert abs(3.0 * B1.tocsr() - B3.tocsr()).max() <= 1e-14 * abs(B3.tocsr()).max()
+        # the boundary areas seen through the nodes add up to the surface area of the box
+        total = -np.asarray(B1.tocsr().diagonal()).sum() * 2.0
+        ext = [np.sum(x) for x in mesh.h]
+        assert abs(total - 2 * (ext[0] * ext[1] + ext[1] * ext[2] + ext[0] * ext[2])) <= 1e-12 * total
