@@ -348,6 +348,69 @@ def mass_diagonal(mesh, proj, model, invert_model=False, invert_matrix=False):
     return 1.0 / diag if invert_matrix else diag
 
 
+# ---- full-tensor models in 2-D (operators/inner_products.py:147-272, 459-565; 2-D tables :599-669, 750-790) ---------
+
+
+def _corner_entities_2d(mesh, proj):
+    """For each of the four cell corners (x low/high, y low/high): the global numbers of the x- and the y-entity
+    (face or edge) of every cell that touch that corner, in the reference's corner order 000, 100, 010, 110."""
+    nx, ny = mesh.shape_cells
+    i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    i, j = i.reshape(-1, order="F"), j.reshape(-1, order="F")
+    out = []
+    for sy in (0, 1):
+        for sx in (0, 1):
+            if proj == "F":      # x-face on the corner's x side, y-face on its y side
+                a = (i + sx) + (nx + 1) * j
+                b = (nx + 1) * ny + i + nx * (j + sy)
+            else:                # x-edge on the corner's y side, y-edge on its x side
+                a = i + nx * (j + sy)
+                b = nx * (ny + 1) + (i + sx) + (nx + 1) * j
+            out.append((a, b))
+    return out
+
+
+def _tensor_model_2d(mesh, model, invert_model):
+    m = np.asarray(model, dtype=np.float64).reshape(mesh.n_cells, 3, order="F")
+    xx, yy, xy = m[:, 0], m[:, 1], m[:, 2]
+    if invert_model:             # closed-form inverse of [[xx, xy], [xy, yy]] per cell (utils/matrix_utils.py:1246-1434)
+        det = xx * yy - xy * xy
+        xx, yy, xy = yy / det, xx / det, -xy / det
+    return xx, yy, xy
+
+
+def mass_tensor_matrix(mesh, proj, model, invert_model=False):
+    """sum over corners of P^T sqrt(V/4) Sigma sqrt(V/4) P for a 2-D model given as (nC, 3) = [xx, yy, xy]."""
+    if mesh.dim != 2:
+        raise NotImplementedError("full-tensor models exist for 2-D and 3-D meshes only")
+    xx, yy, xy = _tensor_model_2d(mesh, model, invert_model)
+    w = 0.25 * cell_volumes(mesh)
+    n = mesh.n_faces if proj == "F" else mesh.n_edges
+    rows, cols, vals = [], [], []
+    for a, b in _corner_entities_2d(mesh, proj):
+        rows += [a, a, b, b]
+        cols += [a, b, a, b]
+        vals += [w * xx, w * xy, w * xy, w * yy]
+    return _assemble((n, n), [(np.concatenate(rows), np.concatenate(cols), np.concatenate(vals))])
+
+
+def mass_tensor_deriv_matrix(mesh, proj, v):
+    """d(M(m) v)/dm for the 2-D full-tensor model: n x 3 nC, column blocks [xx | yy | xy]."""
+    if mesh.dim != 2:
+        raise NotImplementedError("full-tensor models exist for 2-D and 3-D meshes only")
+    nC = mesh.n_cells
+    n = mesh.n_faces if proj == "F" else mesh.n_edges
+    v = np.asarray(v, dtype=np.float64).reshape(-1)
+    w = 0.25 * cell_volumes(mesh)
+    c = np.arange(nC)
+    rows, cols, vals = [], [], []
+    for a, b in _corner_entities_2d(mesh, proj):
+        rows += [a, b, a, b]
+        cols += [c, c + nC, c + 2 * nC, c + 2 * nC]
+        vals += [w * v[a], w * v[b], w * v[b], w * v[a]]
+    return _assemble((n, 3 * nC), [(np.concatenate(rows), np.concatenate(cols), np.concatenate(vals))])
+
+
 # ---- interpolation -------------------------------------------------------------------------------------------------
 
 

@@ -896,6 +896,12 @@ class TensorMesh:
             from .operators import DiagonalOperator
 
             host = model.cpu().numpy() if isinstance(model, torch.Tensor) else model
+            if self.dim == 2 and host is not None and np.asarray(host).size == 3 * self.n_cells:
+                from .csr import CsrOperator
+
+                if invert_matrix:
+                    raise Exception("Solver needed to invert A.")       # inner_products.py:216-217
+                return CsrOperator(lowdim.mass_tensor_matrix(self, proj, host, invert_model))
             return DiagonalOperator(lowdim.mass_diagonal(self, proj, host, invert_model, invert_matrix))
         from .tensor_ops import make_mass_operator
 
@@ -918,8 +924,20 @@ class TensorMesh:
             from .csr import CsrOperator
 
             host = model.cpu().numpy() if isinstance(model, torch.Tensor) else model
+            if self.dim == 2 and np.asarray(host).size == 3 * self.n_cells:
+                if invert_model or invert_matrix:
+                    raise NotImplementedError("inverting the property or the matrix is not yet implemented for this "
+                                              "mesh/tensorType. You should write it!")
+
+                def tensor_deriv(v=None):
+                    if v is None:
+                        raise Exception("v must be supplied for this implementation.")
+                    vh = v.cpu().numpy() if isinstance(v, torch.Tensor) else v
+                    return CsrOperator(lowdim.mass_tensor_deriv_matrix(self, proj, vh))
+
+                return tensor_deriv
             if np.asarray(host).size not in (1, self.n_cells, self.n_cells * self.dim):
-                raise NotImplementedError("full-tensor model derivatives are only built for 3-D meshes")
+                raise NotImplementedError("unexpected model size for a %d-D mesh" % self.dim)
 
             def inner_product_deriv(v=None):
                 if v is None:

@@ -77,6 +77,15 @@ def main():
         for loc in LOCS[d]:
             put("interp_" + loc, mesh.get_interpolation_matrix(pts, loc))
         put("interp_zo_CC", mesh.get_interpolation_matrix(pts_out, "CC", zeros_outside=True))
+        if d == 2:      # full-tensor model (nC, 3) = [xx, yy, xy]; own generator so the entries above keep their values
+            rng_t = np.random.default_rng(97)
+            sig = rng_t.random((mesh.nC, 3)) + np.array([2.0, 2.0, 0.0])
+            out[f"{tag}_model_tensor"] = sig
+            for proj, get, getd in (("F", mesh.get_face_inner_product, mesh.get_face_inner_product_deriv),
+                                    ("E", mesh.get_edge_inner_product, mesh.get_edge_inner_product_deriv)):
+                for im in (False, True):
+                    put(f"mass_{proj}_tensor_{int(im)}0", get(sig, invert_model=im))
+                put(f"deriv_{proj}_tensor_00", getd(sig)(v[proj]))
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tensor_lowdim_small.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

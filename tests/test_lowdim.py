@@ -44,6 +44,22 @@ def test_host_assembly_matches_reference_fixture(gold, tag):
             b = golden_matrix(gold, f"{tag}_deriv_{proj}_{mk}_{int(im)}{int(ix)}")
             a.eliminate_zeros(); b.eliminate_zeros()
             assert_same_matrix(a, b, 1e-12)
+    if m.dim == 2:      # full-tensor model (nC, 3): the generic corner sum (inner_products.py:147-272, 459-565)
+        sig = gold[f"{tag}_model_tensor"]
+        for proj in "FE":
+            for im in (False, True):
+                a = lowdim.mass_tensor_matrix(m, proj, sig, im)
+                b = golden_matrix(gold, f"{tag}_mass_{proj}_tensor_{int(im)}0")
+                a.eliminate_zeros(); b.eliminate_zeros()
+                assert_same_matrix(a, b, 1e-13)
+            a = lowdim.mass_tensor_deriv_matrix(m, proj, gold[f"{tag}_v{proj}"])
+            b = golden_matrix(gold, f"{tag}_deriv_{proj}_tensor_00")
+            a.eliminate_zeros(); b.eliminate_zeros()
+            assert_same_matrix(a, b, 1e-13)
+        with pytest.raises(Exception, match="Solver needed to invert A."):
+            m.get_face_inner_product(sig, invert_matrix=True)
+        with pytest.raises(NotImplementedError):
+            m.get_edge_inner_product_deriv(sig, invert_model=True)
     for loc in LOCS[m.dim]:
         assert_same_matrix(lowdim.interpolation_matrix(m, gold[f"{tag}_pts"], loc), golden_matrix(gold, f"{tag}_interp_{loc}"), 1e-13)
     assert_same_matrix(lowdim.interpolation_matrix(m, gold[f"{tag}_pts_out"], "CC", zeros_outside=True),
@@ -60,7 +76,7 @@ def test_errors_keep_the_reference_behaviour():
     with pytest.raises(NotImplementedError):
         dz.TensorMesh([5]).average_face_y_to_cell
     with pytest.raises(NotImplementedError):
-        dz.TensorMesh([5, 4]).get_face_inner_product(np.ones((20, 3)))       # full tensor: 3-D only
+        dz.TensorMesh([5]).get_face_inner_product(np.ones((5, 3)))           # no full tensor in 1-D
 
 
 @pytest.mark.gpu
@@ -98,3 +114,8 @@ def test_lowdim_operators_on_gpu(gold, tag):
         Ar = Gr.T @ np.diag(gold[f"{tag}_mass_E_iso_00"]) @ Gr
         x = rng.standard_normal(m.n_nodes)
         assert_close_vec(A @ x, Ar @ x)
+        # full-tensor model: host-assembled, applied by the CSR kernel
+        ref = golden_matrix(gold, f"{tag}_mass_E_tensor_00")
+        M = m.get_edge_inner_product(gold[f"{tag}_model_tensor"])
+        x = rng.standard_normal(m.n_edges)
+        assert_close_vec(M @ x, ref @ x)
