@@ -91,8 +91,9 @@ def test_constructor_forms():
     assert m2.dim == 2 and m2.nC == 12 and m2.nN == 20
     assert m2.face_divergence.shape == (12, 31) and m2.edge_curl.shape == (12, 31)
     assert m2.cell_gradient.shape == (31, 12)
+    assert callable(m2.get_face_inner_product_deriv(np.ones((12, 3))))    # 2-D full tensor (lowdim.mass_tensor_deriv_matrix)
     with pytest.raises(NotImplementedError):
-        m2.get_face_inner_product_deriv(np.ones((12, 3)))      # full tensor: 3-D only
+        m2.get_face_inner_product_deriv(np.ones((12, 3)), invert_model=True)
     with pytest.raises(NotImplementedError):
         dz.TensorMesh([4]).edge_curl
 
