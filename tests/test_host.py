@@ -34,6 +34,27 @@ def test_library_exports_every_declared_symbol():
     assert lib.dzb_version() == _lib.ABI_VERSION
 
 
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
+    """The boundary is a C ABI: include/dzb.h compiles as C99 with no C++ or torch types, and a C program that calls
+    an entry point links against libdzb.so and runs (dzb_version needs no GPU)."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "dzb.h"\nint main(void) { printf("%d\\n", dzb_version()); return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)],
+                   check=True)
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-ldzb",
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert int(out) == _lib.ABI_VERSION
+
+
 def test_shapes_through_the_abi():
     lib = _lib.load()
     mesh = dz.TensorMesh([5, 4, 3])
