@@ -23,25 +23,34 @@ from __future__ import annotations
 import numpy as np
 
 
-def _spread3(v, nbits):
+def _spread(v, nbits, stride):
+    """Bit b of ``v`` moved to bit ``stride * b`` (Morton interleave helper)."""
     out = np.zeros_like(v)
     for b in range(nbits):
-        out |= ((v >> b) & 1) << (3 * b)
+        out |= ((v >> b) & 1) << (stride * b)
     return out
+
+
+def _child_offsets(dim):
+    """Children in the reference's order: x bit fastest, then y, (then z)."""
+    if dim == 2:
+        return np.array([[a, b] for b in (0, 1) for a in (0, 1)], dtype=np.int64)
+    return np.array([[a, b, c] for c in (0, 1) for b in (0, 1) for a in (0, 1)], dtype=np.int64)
 
 
 class LinearOctree:
     def __init__(self, shape_cells):
         n = tuple(int(s) for s in shape_cells)
-        if len(n) != 3:
-            raise NotImplementedError("only 3-D OcTrees are built (QuadTree: not part of the five configurations)")
+        if len(n) not in (2, 3):
+            raise NotImplementedError("TreeMesh is 2-D (QuadTree) or 3-D (OcTree)")
+        self.dim = len(n)
         for s in n:
             if s <= 0 or (s & (s - 1)) != 0:
                 raise ValueError("length of cell width vectors must be a power of 2")
         self.n = n
         ls = [s.bit_length() - 1 for s in n]
         min_l = min(ls)
-        cubic = ls[0] == ls[1] == ls[2]
+        cubic = all(l == ls[0] for l in ls)
         self.max_level = min_l + (0 if cubic else 1)      # tree.cpp:789-793
         self.root_level = 0 if cubic else 1               # tree.cpp:874-878
         self.rw = 1 << min_l                              # root width in fine cells
@@ -61,10 +70,14 @@ class LinearOctree:
 
     def pack(self, l, c):
         g = self.grid(l)
+        if self.dim == 2:
+            return c[:, 0] + g[0] * c[:, 1]
         return c[:, 0] + g[0] * (c[:, 1] + g[1] * c[:, 2])
 
     def unpack(self, l, p):
         g = self.grid(l)
+        if self.dim == 2:
+            return np.stack([p % g[0], p // g[0]], axis=1)
         return np.stack([p % g[0], (p // g[0]) % g[1], p // (g[0] * g[1])], axis=1)
 
     def width(self, lvl):
@@ -72,7 +85,7 @@ class LinearOctree:
 
     def root_cells(self):
         g = self.grid(self.root_level)
-        return self.unpack(self.root_level, np.arange(g[0] * g[1] * g[2], dtype=np.int64))
+        return self.unpack(self.root_level, np.arange(int(np.prod(g)), dtype=np.int64))
 
     def _add_divided(self, l, packed):
         if packed.size:
@@ -89,7 +102,7 @@ class LinearOctree:
         cells = np.repeat(roots, nreq, axis=0)
         req = np.tile(np.arange(nreq), roots.shape[0])
         l = self.root_level
-        offs = np.array([[a, b, c] for c in (0, 1) for b in (0, 1) for a in (0, 1)], dtype=np.int64)
+        offs = _child_offsets(self.dim)
         while cells.shape[0] and l < self.max_level:
             w = self.level_width(l)
             ok = (levels[req] > l) & concerns(req, cells * w, np.full(req.size, w, dtype=np.int64))
@@ -97,9 +110,9 @@ class LinearOctree:
             if not cells.shape[0]:
                 break
             self._add_divided(l, np.unique(self.pack(l, cells)))
-            # push the surviving pairs down to the 8 children
-            cells = (2 * cells[:, None, :] + offs[None, :, :]).reshape(-1, 3)
-            req = np.repeat(req, 8)
+            # push the surviving pairs down to the 2^dim children
+            cells = (2 * cells[:, None, :] + offs[None, :, :]).reshape(-1, self.dim)
+            req = np.repeat(req, offs.shape[0])
             l += 1
 
     def divide_leaves(self, leaf_lo, leaf_lvl):
@@ -121,7 +134,9 @@ class LinearOctree:
 
     # ---- balancing -----------------------------------------------------------------------------------------
     def balance(self, diagonal):
-        dirs = [(a, b, c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)]
+        import itertools
+
+        dirs = list(itertools.product((-1, 0, 1), repeat=self.dim))
         if not diagonal:
             dirs = [d for d in dirs if sum(abs(x) for x in d) <= 1]
         dirs = np.array(dirs, dtype=np.int64)  # includes (0,0,0): a divided cell's own parent is divided
@@ -143,7 +158,7 @@ class LinearOctree:
         """(lo, lvl) of all leaves in the reference's cell order."""
         if self._leaves is not None:
             return self._leaves
-        offs = np.array([[a, b, c] for c in (0, 1) for b in (0, 1) for a in (0, 1)], dtype=np.int64)
+        offs = _child_offsets(self.dim)
         los, lvls = [], []
         cand = self.root_cells()  # cells existing at the current level
         for l in range(self.root_level, self.max_level + 1):
@@ -156,7 +171,7 @@ class LinearOctree:
             lvls.append(np.full(leaf.shape[0], l, dtype=np.int64))
             if not isdiv.any():
                 break
-            cand = (2 * cand[isdiv][:, None, :] + offs[None, :, :]).reshape(-1, 3)
+            cand = (2 * cand[isdiv][:, None, :] + offs[None, :, :]).reshape(-1, self.dim)
         lo = np.concatenate(los)
         lvl = np.concatenate(lvls)
         order = np.argsort(self.keys(lo), kind="stable")
@@ -167,9 +182,15 @@ class LinearOctree:
         """Position of a fine cell in the reference's cell order (root id, then Z-order code)."""
         root = lo // self.rw
         rel = lo - root * self.rw
-        code = _spread3(rel[:, 0], self.nbits) | (_spread3(rel[:, 1], self.nbits) << 1) | (_spread3(rel[:, 2], self.nbits) << 2)
-        root_id = root[:, 0] + self.roots[0] * (root[:, 1] + self.roots[1] * root[:, 2])
-        return root_id * (np.int64(self.rw) ** 3) + code
+        d = self.dim
+        code = _spread(rel[:, 0], self.nbits, d)
+        root_id = root[:, 0]
+        stride = self.roots[0]
+        for a in range(1, d):
+            code = code | (_spread(rel[:, a], self.nbits, d) << a)
+            root_id = root_id + stride * root[:, a]
+            stride = stride * self.roots[a]
+        return root_id * (np.int64(self.rw) ** d) + code
 
     @property
     def n_leaves(self):

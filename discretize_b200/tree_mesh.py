@@ -42,9 +42,20 @@ _TREE_REMOVED.update({"cellGradStencil": "cell_gradient_stencil", "maxLevel": "m
 
 
 class TreeMesh:
+    """3-D OcTree.  ``TreeMesh([hx, hy])`` gives the 2-D QuadTree (``quad_mesh.QuadTreeMesh``, a subclass that shares
+    the constructor and every refinement method, and assembles its operators on the host)."""
+
     _meshType = "TREE"
     _LOC_NAMES = TensorMesh._LOC_NAMES
     _parse_location_type = TensorMesh._parse_location_type
+    dim = 3
+
+    def __new__(cls, h=None, *args, **kwargs):
+        if cls is TreeMesh and h is not None and len(list(h)) == 2:
+            from .quad_mesh import QuadTreeMesh
+
+            return object.__new__(QuadTreeMesh)
+        return object.__new__(cls)
 
     def __init__(self, h=None, origin=None, diagonal_balance=None, **kwargs):
         if "x0" in kwargs:
@@ -54,8 +65,8 @@ class TreeMesh:
         if diagonal_balance is None:
             diagonal_balance = False  # reference default (FutureWarning there: tree_mesh.py:246-256)
         h = list(h)
-        if len(h) != 3:
-            raise NotImplementedError("discretize_b200.TreeMesh: only 3-D OcTrees have kernels")
+        if len(h) != self.dim:
+            raise ValueError(f"{type(self).__name__} is {self.dim}-D but {len(h)} width vectors were given")
         for i, h_i in enumerate(h):
             if is_scalar(h_i) and not isinstance(h_i, np.ndarray):
                 h_i = np.ones(int(h_i)) / int(h_i)
@@ -63,7 +74,7 @@ class TreeMesh:
                 h_i = unpack_widths(list(h_i))
             h[i] = np.array(h_i, dtype=np.float64)
         self._h = tuple(h)
-        self._origin = np.zeros(3)
+        self._origin = np.zeros(self.dim)
         if origin is not None:
             value = list(origin)
             for i, (val, h_i) in enumerate(zip(value, self._h)):
@@ -74,7 +85,7 @@ class TreeMesh:
         self._diagonal_balance = bool(diagonal_balance)
         # half-step coordinate arrays (tree_ext.pyx:397-421)
         self._xs = []
-        for a in range(3):
+        for a in range(self.dim):
             n = np.cumsum(np.r_[self._origin[a], self._h[a]])
             x = np.empty(2 * self._h[a].size + 1)
             x[::2] = n
@@ -94,7 +105,6 @@ class TreeMesh:
         raise AttributeError(f"'{type(self).__name__}' object has no attribute '{name}'")
 
     # ---- description ------------------------------------------------------------------------------
-    dim = 3
     h = property(lambda self: self._h)
     origin = property(lambda self: self._origin)
     shape_cells = property(lambda self: tuple(int(x.size) for x in self._h))
@@ -114,14 +124,14 @@ class TreeMesh:
 
     # ---- refinement ----------------------------------------------------------------------------------
     def _cell_box(self, lo, w):
-        a = np.stack([self._xs[d][2 * lo[:, d]] for d in range(3)], axis=1)
-        b = np.stack([self._xs[d][2 * (lo[:, d] + w)] for d in range(3)], axis=1)
+        a = np.stack([self._xs[d][2 * lo[:, d]] for d in range(self.dim)], axis=1)
+        b = np.stack([self._xs[d][2 * (lo[:, d] + w)] for d in range(self.dim)], axis=1)
         return a, b
 
     def insert_cells(self, points, levels, finalize=True, diagonal_balance=None):
         """reference: tree_ext.pyx:1158-1215 -> tree.cpp:383-396, 910-927."""
         self._require_open()
-        points = as_array_n_by_dim(np.asarray(points, dtype=np.float64), 3)
+        points = as_array_n_by_dim(np.asarray(points, dtype=np.float64), self.dim)
         levels = np.atleast_1d(np.asarray(levels, dtype=np.int64))
         # The reference loops over ``levels`` (tree_ext.pyx:1205-1211): a single level with many points
         # inserts only the FIRST point, and a single point with many levels inserts it at each level.
@@ -141,7 +151,7 @@ class TreeMesh:
             # found by `x >= root edge`: a cell is on the path iff, on every axis, its interval holds the
             # point in that sense.  Points outside the mesh clamp to the boundary cells.
             ok = np.ones(req.size, dtype=bool)
-            for d in range(3):
+            for d in range(self.dim):
                 p = points[req, d]
                 a = xs[d][2 * lo[:, d]]
                 b = xs[d][2 * (lo[:, d] + w)]
@@ -163,7 +173,7 @@ class TreeMesh:
     def refine_ball(self, points, radii, levels, finalize=True, diagonal_balance=None):
         """reference: tree_ext.pyx:561-648 -> tree.h:149-167 + geom.cpp:35-58 (Ball::intersects_cell)."""
         self._require_open()
-        points = as_array_n_by_dim(np.asarray(points, dtype=np.float64), 3)
+        points = as_array_n_by_dim(np.asarray(points, dtype=np.float64), self.dim)
         n = points.shape[0]
         radii = np.broadcast_to(np.atleast_1d(np.asarray(radii, dtype=np.float64)), (n,)).copy()
         levels = np.atleast_1d(np.asarray(levels, dtype=np.int64))
@@ -188,15 +198,15 @@ class TreeMesh:
         """Refine every cell that intersects the axis-aligned box(es) [x0, x1] (closed intervals) to ``levels``.
         reference: tree_ext.pyx:650-730 -> geom.cpp:102-112 (Box::intersects_cell)."""
         self._require_open()
-        x0s = as_array_n_by_dim(np.asarray(x0s, dtype=np.float64), 3)
-        x1s = as_array_n_by_dim(np.asarray(x1s, dtype=np.float64), 3)
+        x0s = as_array_n_by_dim(np.asarray(x0s, dtype=np.float64), self.dim)
+        x1s = as_array_n_by_dim(np.asarray(x1s, dtype=np.float64), self.dim)
         levels = np.atleast_1d(np.asarray(levels, dtype=np.int64))
         n = max(x0s.shape[0], x1s.shape[0], levels.size)
         for name, arr_n in (("x0s", x0s.shape[0]), ("x1s", x1s.shape[0]), ("levels", levels.size)):
             if arr_n not in (1, n):
                 raise ValueError(f"First dimensions of x0s, x1s, levels are incompatible ({name} has {arr_n}, expected 1 or {n})")
-        x0s = np.broadcast_to(x0s, (n, 3))
-        x1s = np.broadcast_to(x1s, (n, 3))
+        x0s = np.broadcast_to(x0s, (n, self.dim))
+        x1s = np.broadcast_to(x1s, (n, self.dim))
         levels = np.array([self._parse_level(int(l)) for l in np.broadcast_to(levels, (n,))], dtype=np.int64)
         db = self._diagonal_balance if diagonal_balance is None else diagonal_balance
         lo_box, hi_box = np.minimum(x0s, x1s), np.maximum(x0s, x1s)
@@ -264,7 +274,7 @@ class TreeMesh:
             lo, lvl = t.leaves()
             w = t.width(lvl)
             if callable(function):
-                c = np.stack([(self._xs[d][2 * lo[:, d]] + self._xs[d][2 * (lo[:, d] + w)]) * 0.5 for d in range(3)], axis=1)
+                c = np.stack([(self._xs[d][2 * lo[:, d]] + self._xs[d][2 * (lo[:, d] + w)]) * 0.5 for d in range(self.dim)], axis=1)
                 want = np.asarray(function(c), dtype=np.int64)
             else:
                 want = np.full(lvl.size, self._parse_level(int(function)), dtype=np.int64)
@@ -336,10 +346,18 @@ class TreeMesh:
     n_edges_per_direction = property(lambda self: tuple(e.n for e in self._t().edges))
     n_faces_per_direction = property(lambda self: tuple(f.n for f in self._t().faces))
 
-    @property
-    def cell_levels_by_index(self):
+    def _cell_levels_by_indexes(self, index=None):
+        """Levels of all cells (``index is None``) or of the given ones; one index gives a scalar (tree_ext.pyx:5630-5649)."""
         self._t()
-        return self._levels.copy()
+        if index is None:
+            out = self._levels.copy()
+        else:
+            out = self._levels[np.atleast_1d(np.asarray(index, dtype=np.int64))]
+        return out[0] if out.size == 1 else out
+
+    def cell_levels_by_index(self, indices):
+        """reference: tree_mesh.py:988-1001."""
+        return self._cell_levels_by_indexes(indices)
 
     # ---- geometry (tree.cpp:61-84, 109-136, 176-230; tree_ext.pyx:2021-2722) ---------------------------------
     def _coords(self, loc):

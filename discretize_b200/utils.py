@@ -186,7 +186,7 @@ def _same_base_volume_average_matrix(mesh_in, mesh_out):
     # tree -> tree: input cells finer than their output cell contribute their volume share; output cells no input
     # cell is finer than copy the input cell that contains them
     rows = mesh_out.point2index(mesh_in.cell_centers)
-    lvl_in, lvl_out = mesh_in.cell_levels_by_index, mesh_out.cell_levels_by_index
+    lvl_in, lvl_out = mesh_in._levels, mesh_out._levels
     finer = lvl_out[rows] < lvl_in
     w = np.where(finer, mesh_in.cell_volumes / mesh_out.cell_volumes[rows], 0.0)
     P = sp.csr_matrix((w, (rows, np.arange(n_in))), shape=(n_out, n_in))
