@@ -118,6 +118,9 @@ class QuadTreeMesh(TreeMesh):
     def faces_z(self):
         return self.cell_centers
 
+    permute_faces = property(lambda self: self._lexsorted([self.faces_x, self.faces_y]))
+    permute_edges = property(lambda self: self._lexsorted([self.edges_x, self.edges_y]))
+
     def _unit_vectors(self, counts):
         out = np.zeros((int(sum(counts)), 2))
         o = np.r_[0, np.cumsum(counts)]
@@ -221,6 +224,27 @@ class QuadTreeMesh(TreeMesh):
         if name == "average_edge_to_face":      # faces ARE the other direction's edges: a permutation (tree_ext.pyx:4350-4360)
             nx, ny = self.n_edges_x, self.n_edges_y
             return sp.diags([1.0, 1.0], [-ny, nx], shape=(nx + ny, nx + ny)).tocsr()
+        if name[:-2] in ("average_node_to_edge", "average_node_to_face") and name[-2:] in ("_x", "_y"):
+            d = "xy".index(name[-1])
+            per = self.n_edges_per_direction if "edge" in name else self.n_faces_per_direction
+            o = np.r_[0, np.cumsum(per)]
+            return self._host_matrix(name[:-2])[o[d]:o[d + 1]]
+        if name.startswith(("stencil_cell_gradient", "average_cell_to_total_face_", "average_cell_to_face")) \
+                or name == "average_cell_vector_to_face":
+            return self._host_cell_to_face(name)       # the (minus cell, plus cell) walk of tree_mesh.py, 2-D faces
+        if name.startswith("cell_gradient"):           # -Pa Mf^-1 D^T diag(V) (tree_mesh.py:860-958)
+            o = np.r_[0, np.cumsum(self.n_faces_per_direction)]
+            mask = np.ones(o[2])
+            fb = self.face_boundary_indices
+            for dd in range(2):
+                mask[o[dd] + fb[2 * dd]] = 0.0
+                mask[o[dd] + fb[2 * dd + 1]] = 0.0
+            mf = 2.0 * (self._host_matrix("average_face_to_cell").T @ self.cell_volumes)
+            G = -(sp.diags(mask / mf) @ self._host_matrix("face_divergence").T @ sp.diags(self.cell_volumes))
+            if name == "cell_gradient":
+                return G
+            d = "xy".index(name[-1])
+            return G.tocsr()[o[d]:o[d + 1]]
         raise NotImplementedError(f"discretize_b200 QuadTree: {name} is not built")
 
     @staticmethod
@@ -242,7 +266,7 @@ class QuadTreeMesh(TreeMesh):
         return self._cache[key]
 
     def _cell_gradient_component(self, d):
-        raise NotImplementedError("discretize_b200 QuadTree: cell-centred gradients are not built")
+        return self._operator("cell_gradient" if d is None else "cell_gradient_" + "xyz"[d])
 
     # ---- mass matrices (base_tensor_mesh.py:792-988 with the tree's averages; inner_products.py:147-272, 459-565) ----------
     def _mass_setup(self, proj):
@@ -444,21 +468,11 @@ class QuadTreeMesh(TreeMesh):
             raise NotImplementedError(f"discretize_b200 QuadTree: {name} is not built")
         return raiser
 
-    for _n in ("stencil_cell_gradient", "stencil_cell_gradient_x", "stencil_cell_gradient_y", "stencil_cell_gradient_z",
-               "average_cell_to_face", "average_cell_to_face_x", "average_cell_to_face_y", "average_cell_to_face_z",
-               "average_cell_vector_to_face", "cell_gradient", "cell_gradient_x", "cell_gradient_y", "cell_gradient_z",
-               "average_face_z_to_cell", "average_edge_z_to_cell", "face_z_divergence", "cell_boundary_indices",
-               "face_boundary_indices", "edge_nodes", "average_node_to_edge_x", "average_node_to_edge_y",
-               "average_node_to_edge_z", "average_node_to_face_x", "average_node_to_face_y", "average_node_to_face_z",
-               "boundary_edge_vector_integral", "boundary_node_vector_integral", "boundary_face_scalar_integral",
-               "boundary_faces", "boundary_edges", "boundary_nodes", "boundary_face_outward_normals",
-               "project_face_to_boundary_face", "project_edge_to_boundary_edge", "project_node_to_boundary_node",
-               "permute_cells", "permute_faces", "permute_edges", "hanging_edges_z", "hanging_faces_z"):
+    for _n in ("stencil_cell_gradient_z", "average_cell_to_face_z", "cell_gradient_z", "average_face_z_to_cell",
+               "average_edge_z_to_cell", "face_z_divergence", "average_node_to_edge_z", "average_node_to_face_z",
+               "hanging_edges_z", "hanging_faces_z"):
         locals()[_n] = property(_not_built(_n))
-    for _n in ("average_cell_to_total_face_x", "average_cell_to_total_face_y", "average_cell_to_total_face_z",
-               "edge_divergence_weak_form_robin", "cell_gradient_weak_form_robin", "get_face_inner_product_surface",
-               "get_edge_inner_product_surface", "get_edge_inner_product_line", "get_face_inner_product_surface_deriv",
-               "get_edge_inner_product_surface_deriv", "get_edge_inner_product_line_deriv"):
+    for _n in ("average_cell_to_total_face_z",):
         locals()[_n] = _not_built(_n)
     del _n, _not_built
 

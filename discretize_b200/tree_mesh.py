@@ -496,7 +496,7 @@ class TreeMesh:
         t = self._t()
         unit = np.eye(3, dtype=np.int64)
         out = []
-        for d in range(3):
+        for d in range(self.dim):
             e = t.edges[d]
             ends = np.empty((e.n_total, 2), dtype=np.int64)
             for k, sgn in enumerate((-1, 1)):
@@ -545,9 +545,10 @@ class TreeMesh:
                 out[fam.index] = m
                 return out[:fam.n]
 
-            face = np.concatenate([at_limit(t.faces[d], (d,)) for d in range(3)])
-            edge = np.concatenate([at_limit(t.edges[d], [a for a in range(3) if a != d]) for d in range(3)])
-            node = at_limit(t.nodes, (0, 1, 2))
+            dims = range(self.dim)
+            face = np.concatenate([at_limit(t.faces[d], (d,)) for d in dims])
+            edge = np.concatenate([at_limit(t.edges[d], [a for a in dims if a != d]) for d in dims])
+            node = at_limit(t.nodes, tuple(dims))
             self._cache["bmask"] = (face, edge, node)
         return self._cache["bmask"]
 
@@ -575,7 +576,7 @@ class TreeMesh:
         t = self._t()
         normals = self.face_normals
         low = []
-        for d in range(3):
+        for d in range(self.dim):
             f = t.faces[d]
             m = np.empty(f.n_total, dtype=bool)
             m[f.index] = f.loc[:, d] == 0
@@ -824,10 +825,11 @@ class TreeMesh:
         mirrored by an explicit zero there."""
         t = self._t()
         nC = t.n_cells
+        axes = "xyz"[:self.dim]
         if name in ("stencil_cell_gradient", "average_cell_to_face"):
-            return sp.vstack([self._host_cell_to_face(f"{name}_{c}") for c in "xyz"]).tocsr()
+            return sp.vstack([self._host_cell_to_face(f"{name}_{c}") for c in axes]).tocsr()
         if name == "average_cell_vector_to_face":   # tree_ext.pyx:5131-5190
-            return sp.block_diag([self._host_cell_to_face(f"average_cell_to_face_{c}") for c in "xyz"]).tocsr()
+            return sp.block_diag([self._host_cell_to_face(f"average_cell_to_face_{c}") for c in axes]).tocsr()
         d = "xyz".index(name[-1])
         f = t.faces[d]
         minus, plus = self._face_sides(d)
@@ -839,14 +841,14 @@ class TreeMesh:
             cols = np.r_[minus[both], plus[both], zero[1]]
             vals = np.r_[np.full(both.size, lo), np.full(both.size, hi), zero[2]]
             return sp.csr_matrix((vals, (rows, cols)), shape=(f.n_total, nC))
-        # average_cell_to_face_{x,y,z}: distance weights, hanging faces accumulate a quarter each into their parent,
-        # boundary faces take the adjacent cell
+        # average_cell_to_face_{x,y,z}: distance weights, hanging faces accumulate a quarter (2-D: a half) each into
+        # their parent, boundary faces take the adjacent cell
         xc = self.cell_centers[:, d]
         xf = self._xs[d][f.loc[both, d]]
         w = (xc[plus[both]] - xf) / (xc[plus[both]] - xc[minus[both]])
         hang = f.hanging[both]
         row = np.where(hang, f.index[t.face_parents[d][both]], f.index[both])
-        k = np.where(hang, 4.0, 1.0)
+        k = np.where(hang, float(2 ** (self.dim - 1)), 1.0)
         bnd = np.nonzero(~f.hanging & ((minus < 0) ^ (plus < 0)) & ~self._has_hanging_children(d))[0]
         bcell = np.where(minus[bnd] >= 0, minus[bnd], plus[bnd])
         # reference quirk (tree_ext.pyx:5219-5236): a cell without a + neighbour writes its + face and `continue`s,
@@ -870,7 +872,7 @@ class TreeMesh:
         """Cells touching the -x, +x, -y, +y, -z, +z boundary, in cell order (tree_ext.pyx:2700-2822)."""
         t = self._t()
         out = []
-        for d in range(3):
+        for d in range(self.dim):
             out.append(np.nonzero(t.centers[:, d] - t.half == 0)[0])
             out.append(np.nonzero(t.centers[:, d] + t.half == t.shape_half[d])[0])
         return tuple(out)
@@ -881,7 +883,7 @@ class TreeMesh:
         t = self._t()
         cb = self.cell_boundary_indices
         out = []
-        for d in range(3):
+        for d in range(self.dim):
             out.append(t.faces[d].index[t.cell_faces[d][cb[2 * d], 0]])
             out.append(t.faces[d].index[t.cell_faces[d][cb[2 * d + 1], 1]])
         return tuple(out)
@@ -1021,21 +1023,21 @@ class TreeMesh:
     def project_face_vector(self, face_vectors):
         if not isinstance(face_vectors, np.ndarray):
             raise Exception("face_vectors must be an ndarray")
-        if not (face_vectors.ndim == 2 and face_vectors.shape == (self.n_faces, 3)):
+        if not (face_vectors.ndim == 2 and face_vectors.shape == (self.n_faces, self.dim)):
             raise Exception("face_vectors must be an ndarray of shape (n_faces, dim)")
         return np.sum(face_vectors * self.face_normals, 1)
 
     def project_edge_vector(self, edge_vectors):
         if not isinstance(edge_vectors, np.ndarray):
             raise Exception("edge_vectors must be an ndarray")
-        if not (edge_vectors.ndim == 2 and edge_vectors.shape == (self.n_edges, 3)):
+        if not (edge_vectors.ndim == 2 and edge_vectors.shape == (self.n_edges, self.dim)):
             raise Exception("edge_vectors must be an ndarray of shape (nE, dim)")
         return np.sum(edge_vectors * self.edge_tangents, 1)
 
     def closest_points_index(self, locations, grid_loc="CC", discard=False):
         from scipy.spatial import KDTree
 
-        locations = as_array_n_by_dim(locations, 3)
+        locations = as_array_n_by_dim(locations, self.dim)
         grid_loc = self._parse_location_type(grid_loc)
         key = f"_{grid_loc}_tree"
         tree = self._cache.get(key)

@@ -66,11 +66,13 @@ def evaluate(mesh, tree=False):
     if d > 1:
         geom += ["boundary_edges", "project_edge_to_boundary_edge", "boundary_edge_vector_integral"]
     if tree:
-        geom += ["hanging_edges_x", "hanging_edges_y", "hanging_edges_z", "hanging_faces_x", "hanging_faces_y",
-                 "hanging_faces_z", "total_nodes", "vntF", "vntE", "nodes_x", "cell_centers_z", "max_used_level",
+        geom += ["hanging_edges_x", "hanging_edges_y", "hanging_faces_x", "hanging_faces_y",
+                 "total_nodes", "vntF", "vntE", "nodes_x", "max_used_level",
                  "permute_cells", "permute_faces", "permute_edges", "edge_nodes",
-                 "average_node_to_edge_x", "average_node_to_edge_y", "average_node_to_edge_z",
-                 "average_node_to_face_x", "average_node_to_face_y", "average_node_to_face_z"]
+                 "average_node_to_edge_x", "average_node_to_edge_y", "average_node_to_face_x", "average_node_to_face_y"]
+        if d == 3:
+            geom += ["hanging_edges_z", "hanging_faces_z", "cell_centers_z", "average_node_to_edge_z",
+                     "average_node_to_face_z"]
     else:
         geom += ["h_gridded", "face_x_areas", "face_y_areas", "face_z_areas", "edge_x_lengths", "edge_y_lengths",
                  "edge_z_lengths", "cell_boundary_indices", "face_boundary_indices"]
@@ -102,7 +104,7 @@ def evaluate(mesh, tree=False):
             pts = pts[:, 0]
         put("point2index", lambda: mesh.point2index(pts))
     else:
-        pts = rng.random((30, 3)) * 4 - 1 + np.asarray(mesh.origin)
+        pts = rng.random((30, d)) * 4 - 1 + np.asarray(mesh.origin)
         put("is_inside", lambda: mesh.is_inside(pts))
     for loc in ("CC", "N", "Fx", "Ex"):
         put("closest_" + loc, lambda: mesh.closest_points_index(pts, loc))

@@ -7,7 +7,11 @@ import scipy.sparse as sp
 OPERATORS = ["face_divergence", "edge_curl", "nodal_gradient", "average_face_to_cell", "average_face_to_cell_vector",
              "average_face_x_to_cell", "average_face_y_to_cell", "average_edge_to_cell", "average_edge_to_cell_vector",
              "average_edge_x_to_cell", "average_edge_y_to_cell", "average_node_to_cell", "average_node_to_edge",
-             "average_node_to_face", "average_edge_to_face", "face_x_divergence", "face_y_divergence"]
+             "average_node_to_face", "average_edge_to_face", "face_x_divergence", "face_y_divergence",
+             "stencil_cell_gradient", "stencil_cell_gradient_x", "stencil_cell_gradient_y", "cell_gradient",
+             "cell_gradient_x", "cell_gradient_y", "average_cell_to_face", "average_cell_to_face_x",
+             "average_cell_to_face_y", "average_cell_vector_to_face", "average_cell_to_total_face_x",
+             "average_cell_to_total_face_y"]
 COUNTS = ["n_cells", "n_nodes", "n_total_nodes", "n_hanging_nodes", "n_edges_x", "n_edges_y", "n_total_edges_x",
           "n_total_edges_y", "n_hanging_edges_x", "n_hanging_edges_y", "n_faces_x", "n_faces_y", "n_total_faces_x",
           "n_total_faces_y", "n_hanging_faces_x", "n_hanging_faces_y", "n_edges", "n_faces", "n_total_edges",
@@ -75,7 +79,11 @@ def points_for(mesh_ref_like, h, origin):
 def evaluate(mesh, pts, host_matrix=None):
     """name -> array for every case.  ``host_matrix(name)``: how to get an operator's matrix (default: the property)."""
     rng = np.random.default_rng(3)
-    get = host_matrix or (lambda name: getattr(mesh, name))
+    def reference_matrix(name):
+        m = getattr(mesh, name)
+        return m() if callable(m) else m        # average_cell_to_total_face_* are plain methods in the reference
+
+    get = host_matrix or reference_matrix
     out = {}
     for n in COUNTS:
         out["count:" + n] = np.asarray(getattr(mesh, n), dtype=np.int64)
@@ -105,4 +113,12 @@ def evaluate(mesh, pts, host_matrix=None):
         out["interp:" + lt] = _dense(mesh.get_interpolation_matrix(pts, lt))
     out["interp:N:zeros_outside"] = _dense(mesh.get_interpolation_matrix(pts, "N", zeros_outside=True))
     out["interp:Fz"] = _guard(lambda: mesh.get_interpolation_matrix(pts, "Fz"))
+    for n in ("cell_boundary_indices", "face_boundary_indices"):
+        for i, idx in enumerate(getattr(mesh, n)):
+            out[f"index:{n}#{i}"] = np.asarray(idx, dtype=np.int64)
+    # boundary projections / integrals, Robin pieces, surface and line inner products: the recipe of boundary_cases.py
+    import boundary_cases
+
+    for k, v in boundary_cases.evaluate(mesh, tree=True).items():
+        out["boundary:" + k] = v
     return out
