@@ -59,7 +59,7 @@ def _tensor_volume_average_matrix(mesh_in, mesh_out):
 
 def _base_nodes(mesh):
     if mesh._meshType == "TREE":
-        return [mesh.nodes_x, mesh.nodes_y, mesh.nodes_z]
+        return [mesh.nodes_x, mesh.nodes_y, mesh.nodes_z][:mesh.dim]
     return [mesh._nodes_1d(a) for a in range(mesh.dim)]
 
 
@@ -73,12 +73,15 @@ def _same_base(mesh_a, mesh_b):
 def _expand_ranges(lo, hi):
     """All index triples of the boxes [lo, hi) (one box per row), x fastest within a box: (box id, (n, 3) indices)."""
     ext = np.maximum(hi - lo, 0)
-    cnt = ext[:, 0] * ext[:, 1] * ext[:, 2]
+    cnt = np.prod(ext, axis=1)
     box = np.repeat(np.arange(lo.shape[0]), cnt)
     local = np.arange(int(cnt.sum())) - np.repeat(np.cumsum(cnt) - cnt, cnt)
-    ex, ey = ext[box, 0], ext[box, 1]
-    idx = np.stack([local % ex, (local // ex) % ey, local // (ex * ey)], axis=1) + lo[box]
-    return box, idx
+    cols = []
+    for d in range(lo.shape[1]):
+        e = ext[box, d]
+        cols.append(local % e)
+        local = local // e
+    return box, np.stack(cols, axis=1) + lo[box]
 
 
 def _touching(lo, hi, a, b, active):
@@ -93,10 +96,11 @@ def _tree_candidates(mesh_in, lo, hi, active):
     at once, one level per pass (tree.h:170-182 does the same per box, recursively)."""
     tr = mesh_in._tree
     xs = mesh_in._xs
+    dim = mesh_in.dim
 
     def bounds(c, w):
-        a = np.stack([xs[d][2 * c[:, d] * w] for d in range(3)], axis=1)
-        b = np.stack([xs[d][2 * (c[:, d] + 1) * w] for d in range(3)], axis=1)
+        a = np.stack([xs[d][2 * c[:, d] * w] for d in range(dim)], axis=1)
+        b = np.stack([xs[d][2 * (c[:, d] + 1) * w] for d in range(dim)], axis=1)
         return a, b
 
     w = tr.level_width(tr.root_level)
@@ -104,12 +108,14 @@ def _tree_candidates(mesh_in, lo, hi, active):
     # roots: index ranges per axis (closed contact), then the exact test
     r_lo = np.empty(lo.shape, dtype=np.int64)
     r_hi = np.empty(lo.shape, dtype=np.int64)
-    for d in range(3):
+    for d in range(dim):
         nodes = xs[d][::2 * w]
         r_lo[:, d] = np.clip(np.searchsorted(nodes, lo[:, d], side="left") - 1, 0, g[d])
         r_hi[:, d] = np.clip(np.searchsorted(nodes, hi[:, d], side="right"), 0, g[d])
     box, c = _expand_ranges(r_lo, r_hi)
-    offs = np.array([[i, j, k] for k in (0, 1) for j in (0, 1) for i in (0, 1)], dtype=np.int64)
+    from .octree import _child_offsets
+
+    offs = _child_offsets(dim)
     out_box, out_lo = [], []
     for l in range(tr.root_level, tr.max_level + 1):
         if not box.size:
@@ -124,8 +130,8 @@ def _tree_candidates(mesh_in, lo, hi, active):
             isdiv = np.zeros(box.size, dtype=bool)
         out_box.append(box[~isdiv])
         out_lo.append(c[~isdiv] * w)
-        box = np.repeat(box[isdiv], 8)
-        c = (2 * c[isdiv][:, None, :] + offs[None, :, :]).reshape(-1, 3)
+        box = np.repeat(box[isdiv], offs.shape[0])
+        c = (2 * c[isdiv][:, None, :] + offs[None, :, :]).reshape(-1, dim)
     box = np.concatenate(out_box)
     leaf_lo = np.concatenate(out_lo)
     all_lo, _ = tr.leaves()
@@ -137,20 +143,25 @@ def _tensor_candidates(mesh_in, lo, hi, active):
     n = mesh_in.shape_cells
     i_lo = np.empty(lo.shape, dtype=np.int64)
     i_hi = np.empty(lo.shape, dtype=np.int64)
-    for d in range(3):       # tree_ext.pyx:6969-6979
+    dim = mesh_in.dim
+    for d in range(dim):       # tree_ext.pyx:6969-6979
         i_lo[:, d] = np.maximum(np.searchsorted(nodes[d], lo[:, d], side="left") - 1, 0)
         i_hi[:, d] = np.minimum(np.searchsorted(nodes[d], hi[:, d], side="right"), n[d])
     box, idx = _expand_ranges(i_lo, i_hi)
-    a = np.stack([nodes[d][idx[:, d]] for d in range(3)], axis=1)
-    b = np.stack([nodes[d][idx[:, d] + 1] for d in range(3)], axis=1)
+    a = np.stack([nodes[d][idx[:, d]] for d in range(dim)], axis=1)
+    b = np.stack([nodes[d][idx[:, d] + 1] for d in range(dim)], axis=1)
     keep = _touching(lo[box], hi[box], a, b, active[box])
     idx = idx[keep]
-    return box[keep], idx[:, 0] + n[0] * (idx[:, 1] + n[1] * idx[:, 2])
+    flat, stride = idx[:, 0].copy(), n[0]
+    for d in range(1, dim):
+        flat += stride * idx[:, d]
+        stride *= n[d]
+    return box[keep], flat
 
 
 def _overlap_volume_average_matrix(mesh_in, mesh_out):
-    if mesh_in.dim != 3:
-        raise NotImplementedError("volume_average with a TreeMesh is built for 3-D meshes")
+    if mesh_in.dim not in (2, 3):
+        raise NotImplementedError("volume_average with a TreeMesh needs 2-D or 3-D meshes")
     base_in = _base_nodes(mesh_in)
     origin = np.array([x[0] for x in base_in])
     x_end = np.array([x[-1] for x in base_in])
@@ -165,7 +176,7 @@ def _overlap_volume_average_matrix(mesh_in, mesh_out):
     bounds_in = np.asarray(mesh_in.cell_bounds)
     a, b = bounds_in[cell, 0::2], bounds_in[cell, 1::2]
     length = np.where(active[box], np.minimum(hi[box], b) - np.maximum(lo[box], a), 1.0)
-    weight = length[:, 0] * length[:, 1] * length[:, 2]
+    weight = np.prod(length, axis=1) if length.shape[1] == 2 else length[:, 0] * length[:, 1] * length[:, 2]
     nz = weight != 0.0
     box, cell, weight = box[nz], cell[nz], weight[nz]
     total = np.bincount(box, weights=weight, minlength=mesh_out.n_cells)

@@ -6,7 +6,8 @@ import numpy as np
 def _tree(lib, h, origin, balls, levels):
     m = lib.TreeMesh(h, origin=origin)
     b = np.array(balls)
-    m.refine_ball(b[:, :3] + origin, b[:, 3], levels, finalize=True)
+    d = len(h)
+    m.refine_ball(b[:, :d] + origin, b[:, d], levels, finalize=True)
     return m
 
 
@@ -31,6 +32,42 @@ def build(lib):
     def S():
         return _tree(lib, hs, o1, b1, [3, 4])
 
+    # QuadTrees (2-D): the same pairings; drawn after the 3-D widths so those keep their values
+    q16 = [np.full(16, 0.25)] * 2
+    p0 = np.zeros(2)
+    qs = [rng.random(16) * .2 + .15, rng.random(8) * .3 + .3]
+    p1 = np.array([-0.3, 0.2])
+    c1 = [[1., 1., .8], [3., 2.5, .6]]
+    c2 = [[2., 2., 1.0], [.5, .5, .5]]
+    qt = [rng.random(11) * .3 + .3, rng.random(7) * .5 + .4]
+    pt = np.array([-0.5, -0.4])
+
+    def QA():
+        return _tree(lib, q16, p0, c1, [3, 4])
+
+    def QB():
+        return _tree(lib, q16, p0, c2, [4, 3])
+
+    def QS():
+        return _tree(lib, qs, p1, c1, [3, 4])
+
+    quad = {
+        "quad_quad_same_base": (QA(), QB()),
+        "tensor_quad_same_base": (lib.TensorMesh(q16, origin=p0), QA()),
+        "quad_tensor_same_base": (QA(), lib.TensorMesh(q16, origin=p0)),
+        "quad_quad_general": (QS(), QB()),
+        "quad_quad_general_rev": (QB(), QS()),
+        "tensor_quad_general": (lib.TensorMesh(qt, origin=pt), QA()),
+        "quad_tensor_general": (QA(), lib.TensorMesh(qt, origin=pt)),
+        "quad_quad_disjoint": (QA(), _tree(lib, qs, np.array([5.5, -7.0]), c1, [3, 4])),
+    }
+    return {
+        **_three_d(lib, A, B, S, h16, o0, ht, ot, hs, far, b1),
+        **quad,
+    }
+
+
+def _three_d(lib, A, B, S, h16, o0, ht, ot, hs, far, b1):
     return {
         "tree_tree_same_base": (A(), B()),
         "tree_tree_same_base_rev": (B(), A()),
