@@ -10,7 +10,10 @@ Drop-in for the operator-application part of ``discretize.TreeMesh`` in 3-D
   tree_ext.pyx:3114-4762 (hanging faces -> parent, hanging edges -> mean of two parents, hanging
   nodes -> mean of four listed parents, repeated until only non-hanging columns remain), then
   uploaded as CSR with one byte per entry that encodes (multiplier, row-geometry selector):
-  the values are regenerated on the fly by the ``tree_spmv`` kernel from per-row geometry.
+  the values are regenerated on the fly by the ``tree_spmv`` kernel from per-row geometry;
+* cell-centred operators, boundary terms, interpolation (``tree_interp.py``) and the QuadTree
+  (``quad_mesh.QuadTreeMesh``, returned by ``TreeMesh([hx, hy])``) are host-assembled CSR applied by
+  ``dzb_csr_spmv``.
 """
 from __future__ import annotations
 
