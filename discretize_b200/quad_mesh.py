@@ -432,7 +432,8 @@ class QuadTreeMesh(TreeMesh):
         return np.searchsorted(tr.keys(leaf_lo), tr.keys(lo))
 
     def point2index(self, locs):
-        return self._containing_cells(as_array_n_by_dim(np.asarray(locs, dtype=np.float64), 2))
+        out = self._containing_cells(as_array_n_by_dim(np.asarray(locs, dtype=np.float64), 2))
+        return out[0] if out.size == 1 else out      # one point gives a scalar (tree_ext.pyx:1350-1352)
 
     def get_interpolation_matrix(self, loc, location_type="cell_centers", zeros_outside=False, **kwargs):
         if "locType" in kwargs:

@@ -289,6 +289,253 @@ class TreeMesh:
         if finalize:
             self.finalize()
 
+    # ---- geometric refinement and cell queries (tree_ext.pyx:735-1150, 1354-1510; predicates in tree_geometry.py) -------
+    def _wrap_level(self, level):
+        level = int(level)
+        return (self.max_level + 1) - (abs(level) % (self.max_level + 1)) if level < 0 else level
+
+    @staticmethod
+    def _broadcast_first(**arrays):
+        """Number of items of first-dimension broadcasting; the reference's message when they do not agree."""
+        n = 1
+        for arr in arrays.values():
+            k = arr.shape[0]
+            if k != 1:
+                if n == 1:
+                    n = k
+                elif k != n:
+                    msg = "First dimensions of" + ",".join(f" {key}: {a.shape}" for key, a in arrays.items())
+                    raise ValueError(msg + " do not broadcast.")
+        return n
+
+    def _array_with_dim(self, name, arr, ndim):
+        arr = np.asarray(arr, dtype=np.float64)
+        while arr.ndim < ndim:
+            arr = arr[None]
+        if arr.ndim != ndim or arr.shape[-1] != self.dim:
+            raise ValueError(f"Expected the last dimension of {name}.shape={arr.shape} to be {self.dim}.")
+        return arr
+
+    def _refine_geometric(self, predicate, n, levels, finalize, diagonal_balance):
+        self._require_open()
+        levels = np.atleast_1d(np.asarray(levels, dtype=np.int64))
+        levels = np.array([self._wrap_level(l) for l in np.broadcast_to(levels, (n,))], dtype=np.int64)
+        db = self._diagonal_balance if diagonal_balance is None else diagonal_balance
+
+        def concerns(req, lo, w):
+            a, b = self._cell_box(lo, w)
+            return predicate(req, a, b)
+
+        self._tree.refine_requests(n, levels, concerns)
+        self._tree.balance(db)
+        if finalize:
+            self.finalize()
+
+    def refine_line(self, path, levels, finalize=True, diagonal_balance=None):
+        """Refine every cell a segment of the polyline ``path`` passes through (tree_ext.pyx:735-809)."""
+        from . import tree_geometry as tg
+
+        path = self._array_with_dim("path", path, 2)
+        levels = np.atleast_1d(np.asarray(levels, dtype=np.int64))
+        n = self._broadcast_first(path=path[:-1], levels=levels)
+        starts = np.broadcast_to(path[:-1], (n, self.dim)) if path.shape[0] == 2 else path[:-1]
+        ends = np.broadcast_to(path[1:], (n, self.dim)) if path.shape[0] == 2 else path[1:]
+        self._refine_geometric(tg.line(starts, ends), n, levels, finalize, diagonal_balance)
+
+    def refine_plane(self, origins, normals, levels, finalize=True, diagonal_balance=None):
+        """reference: tree_ext.pyx:812-894."""
+        from . import tree_geometry as tg
+
+        origins = self._array_with_dim("origins", origins, 2)
+        normals = self._array_with_dim("normals", normals, 2)
+        levels = np.atleast_1d(np.asarray(levels, dtype=np.int64))
+        n = self._broadcast_first(origins=origins, normals=normals, levels=levels)
+        pred = tg.plane(np.broadcast_to(origins, (n, self.dim)), np.broadcast_to(normals, (n, self.dim)))
+        self._refine_geometric(pred, n, levels, finalize, diagonal_balance)
+
+    def refine_triangle(self, triangle, levels, finalize=True, diagonal_balance=None):
+        """reference: tree_ext.pyx:897-972."""
+        from . import tree_geometry as tg
+
+        triangle = self._array_with_dim("triangle", triangle, 3)
+        if triangle.shape[-2] != 3:
+            raise ValueError(f"triangle array must be (N, 3, {self.dim})")
+        levels = np.atleast_1d(np.asarray(levels, dtype=np.int64))
+        n = self._broadcast_first(triangle=triangle, levels=levels)
+        self._refine_geometric(tg.triangle(np.broadcast_to(triangle, (n, 3, self.dim))), n, levels, finalize, diagonal_balance)
+
+    def refine_vertical_trianglular_prism(self, triangle, h, levels, finalize=True, diagonal_balance=None):
+        """reference: tree_ext.pyx:975-1069 (3-D only)."""
+        from . import tree_geometry as tg
+
+        if self.dim == 2:
+            raise NotImplementedError("refine_vertical_trianglular_prism only implemented in 3D.")
+        triangle = self._array_with_dim("triangle", triangle, 3)
+        if triangle.shape[-2] != 3:
+            raise ValueError(f"triangle array must be (N, 3, {self.dim})")
+        h = np.atleast_1d(np.asarray(h, dtype=np.float64))
+        if np.any(h < 0):
+            raise ValueError("All heights must be positive.")
+        levels = np.atleast_1d(np.asarray(levels, dtype=np.int64))
+        n = self._broadcast_first(triangle=triangle, h=h, levels=levels)
+        pred = tg.vertical_triangular_prism(np.broadcast_to(triangle, (n, 3, 3)), np.broadcast_to(h, (n,)))
+        self._refine_geometric(pred, n, levels, finalize, diagonal_balance)
+
+    def refine_tetrahedron(self, tetra, levels, finalize=True, diagonal_balance=None):
+        """reference: tree_ext.pyx:1072-1150 (3-D; in 2-D the reference refines the triangle)."""
+        from . import tree_geometry as tg
+
+        if self.dim == 2:
+            return self.refine_triangle(tetra, levels, finalize=finalize, diagonal_balance=diagonal_balance)
+        tetra = self._array_with_dim("tetra", tetra, 3)
+        if tetra.shape[-2] != 4:
+            raise ValueError(f"tetra array must be (N, {self.dim + 1}, {self.dim})")
+        levels = np.atleast_1d(np.asarray(levels, dtype=np.int64))
+        n = self._broadcast_first(tetra=tetra, levels=levels)
+        self._refine_geometric(tg.tetrahedron(np.broadcast_to(tetra, (n, 4, 3))), n, levels, finalize, diagonal_balance)
+
+    def refine_surface(self, xyz, level=-1, padding_cells_by_level=None, pad_up=False, pad_down=True, finalize=True,
+                       diagonal_balance=None):
+        """Refine along the surface triangulated from ``xyz`` (or ``(xyz, simplices)``), padded per level by stretching
+        its bounding box and thickening it downward / upward (tree_mesh.py:638-797)."""
+        level = self._parse_level(self._wrap_level(level))
+        if padding_cells_by_level is None:
+            padding_cells_by_level = np.array([0])
+        padding_cells_by_level = np.asarray(padding_cells_by_level)
+        if padding_cells_by_level.ndim == 0 and level > 1:
+            padding_cells_by_level = np.full(level - 1, padding_cells_by_level)
+        padding_cells_by_level = np.atleast_1d(padding_cells_by_level)
+        if padding_cells_by_level.ndim == 2 and padding_cells_by_level.shape[1] != self.dim:
+            raise ValueError("incorrect dimension for padding_cells_by_level.")
+        if self.dim == 2:
+            xyz = np.asarray(xyz)
+            xyz = xyz[np.argsort(xyz[:, 0])]
+            n_ps = len(xyz)
+            inds = np.arange(n_ps)
+            # each segment of the polyline becomes two triangles between the curve and its thickened copy
+            simps = np.r_[np.c_[inds[:-1], inds[1:], inds[:-1]] + [0, 0, n_ps],
+                          np.c_[inds[:-1], inds[1:], inds[1:]] + [n_ps, n_ps, 0]]
+        else:
+            if isinstance(xyz, tuple):
+                xyz, simps = np.asarray(xyz[0]), np.asarray(xyz[1])
+            else:
+                from scipy.spatial import Delaunay
+
+                xyz = np.asarray(xyz)
+                simps = Delaunay(xyz[:, :2]).simplices
+            n_ps = len(xyz)
+        bb_min, bb_max = np.min(xyz, axis=0)[:-1], np.max(xyz, axis=0)[:-1]
+        half_width, center = (bb_max - bb_min) / 2, (bb_max + bb_min) / 2
+        points = np.empty((n_ps, self.dim))
+        points[:, -1] = xyz[:, -1]
+        h_min = np.r_[[h.min() for h in self.h]]
+        pad = 0.0
+        for lv, n_pad in zip(np.arange(level, 1, -1), padding_cells_by_level):
+            pad = pad + n_pad * h_min * 2 ** (self.max_level - lv)
+            h = 0
+            if pad_up:
+                h += pad[-1]
+            if pad_down:
+                h += pad[-1]
+                points[:, -1] = xyz[:, -1] - pad[-1]
+            points[:, :-1] = (half_width + pad[:-1]) / half_width * (xyz[:, :-1] - center) + center
+            if self.dim == 2:
+                self.refine_triangle(np.r_[points, points + [0, h]][simps], lv, finalize=False,
+                                     diagonal_balance=diagonal_balance)
+            else:
+                self.refine_vertical_trianglular_prism(points[simps], h, lv, finalize=False,
+                                                       diagonal_balance=diagonal_balance)
+        if finalize:
+            self.finalize()
+
+    def _find_cells(self, predicate):
+        """Indices of the leaves whose box satisfies ``predicate`` (one primitive), ascending -- the traversal order of
+        ``find_cells_geom`` (tree.h:170-182, 232-242) is the cell order."""
+        self._t()
+        tr = self._tree
+        from .octree import _child_offsets
+
+        offs = _child_offsets(self.dim)
+        c = tr.root_cells()
+        found = []
+        for l in range(tr.root_level, tr.max_level + 1):
+            if not c.shape[0]:
+                break
+            w = tr.level_width(l)
+            a, b = self._cell_box(c * w, w)
+            c = c[predicate(np.zeros(c.shape[0], dtype=np.int64), a, b)]
+            if l < tr.max_level and tr.div[l].size:
+                isdiv = np.isin(tr.pack(l, c), tr.div[l])
+            else:
+                isdiv = np.zeros(c.shape[0], dtype=bool)
+            found.append(c[~isdiv] * w)
+            c = (2 * c[isdiv][:, None, :] + offs[None, :, :]).reshape(-1, self.dim)
+        lo = np.concatenate(found) if found else np.zeros((0, self.dim), dtype=np.int64)
+        all_lo, _ = tr.leaves()
+        return np.sort(np.searchsorted(tr.keys(all_lo), tr.keys(lo)))
+
+    def get_cells_in_ball(self, center, radius):
+        from . import tree_geometry as tg
+
+        return self._find_cells(tg.ball(self._array_with_dim("center", center, 2), np.array([float(radius)])))
+
+    def get_cells_on_line(self, segment):
+        from . import tree_geometry as tg
+
+        segment = self._array_with_dim("segment", segment, 2)
+        if segment.shape[0] != 2:
+            raise ValueError(f"A line segment has two points, not {segment.shape[0]}")
+        return self._find_cells(tg.line(segment[:1], segment[1:]))
+
+    def get_cells_in_aabb(self, x_min, x_max):
+        from . import tree_geometry as tg
+
+        return self._find_cells(tg.box(self._array_with_dim("x_min", x_min, 2), self._array_with_dim("x_max", x_max, 2)))
+
+    def get_cells_on_plane(self, origin, normal):
+        from . import tree_geometry as tg
+
+        return self._find_cells(tg.plane(self._array_with_dim("origin", origin, 2), self._array_with_dim("normal", normal, 2)))
+
+    def get_cells_in_triangle(self, triangle):
+        from . import tree_geometry as tg
+
+        triangle = self._array_with_dim("triangle", triangle, 2)
+        if triangle.shape[0] != 3:
+            raise ValueError(f"Triangle array must have three points, saw {triangle.shape[0]}")
+        return self._find_cells(tg.triangle(triangle[None]))
+
+    def get_cells_in_vertical_trianglular_prism(self, triangle, h):
+        from . import tree_geometry as tg
+
+        if self.dim == 2:
+            raise NotImplementedError("vertical_trianglular_prism only valid in 3D")
+        triangle = self._array_with_dim("triangle", triangle, 2)
+        if triangle.shape[0] != 3:
+            raise ValueError(f"Triangle array must have three points, saw {triangle.shape[0]}")
+        if h < 0:
+            raise ValueError("h must be greater than or equal to 0")
+        return self._find_cells(tg.vertical_triangular_prism(triangle[None], np.array([float(h)])))
+
+    def get_cells_in_tetrahedron(self, tetra):
+        from . import tree_geometry as tg
+
+        if self.dim == 2:
+            return self.get_cells_in_triangle(tetra)
+        tetra = self._array_with_dim("tetra", tetra, 2)
+        if tetra.shape[0] != 4:
+            raise ValueError(f"A tetrahedron is defined by 4 points in 3D, not {tetra.shape[0]}.")
+        return self._find_cells(tg.tetrahedron(tetra[None]))
+
+    def get_containing_cells(self, points):
+        """Index of the cell containing each point; a single point gives a scalar (tree_ext.pyx:5596-5628)."""
+        return self.point2index(points)
+
+    def get_overlapping_cells(self, rectangle):
+        """Cells intersecting the box ``[xmin, xmax, ymin, ymax, (zmin, zmax)]`` (tree_ext.pyx:7055-7068)."""
+        r = np.asarray(rectangle, dtype=np.float64)
+        return self.get_cells_in_aabb(r[0::2], r[1::2])
+
     def _set_state(self, indexes, levels):
         """Rebuild from (cell-centre half-step locations, levels), like __setstate__ (tree_ext.pyx:6488-6507)."""
         self._require_open()
@@ -1137,7 +1384,8 @@ class TreeMesh:
 
     def point2index(self, locs):
         """reference: tree_mesh.py:984-986 (index of the cell containing each point)."""
-        return self._containing_cells(as_array_n_by_dim(np.asarray(locs, dtype=np.float64), 3))
+        out = self._containing_cells(as_array_n_by_dim(np.asarray(locs, dtype=np.float64), 3))
+        return out[0] if out.size == 1 else out      # one point gives a scalar (tree_ext.pyx:1350-1352)
 
     def get_interpolation_matrix(self, loc, location_type="cell_centers", zeros_outside=False, **kwargs):
         """Interpolation from nodes (``_getNodeIntMat``, tree_ext.pyx:6116-6179), edges, faces or cell centres
