@@ -183,20 +183,25 @@ def _overlap_volume_average_matrix(mesh_in, mesh_out):
     return sp.csr_matrix((weight / total[box], (box, cell)), shape=(mesh_out.n_cells, mesh_in.n_cells))
 
 
+def _cells_of(mesh, points):
+    """Containing cell of each point, always as an array (TreeMesh.point2index gives a scalar for one point)."""
+    return np.atleast_1d(mesh.point2index(points))
+
+
 def _same_base_volume_average_matrix(mesh_in, mesh_out):
     """Meshes refined from one tensor grid: nested cells, so weights are volume ratios or 1 (tree_ext.pyx:6627-6680,
     6762-6775, 6900-6912)."""
     n_in, n_out = mesh_in.n_cells, mesh_out.n_cells
     if mesh_in._meshType == "TENSOR":                      # fine tensor cells -> the tree cell that contains them
-        rows = mesh_out.point2index(mesh_in.cell_centers)
+        rows = _cells_of(mesh_out, mesh_in.cell_centers)
         w = mesh_in.cell_volumes / mesh_out.cell_volumes[rows]
         return sp.csr_matrix((w, (rows, np.arange(n_in))), shape=(n_out, n_in))
     if mesh_out._meshType == "TENSOR":                     # every fine tensor cell sits inside one tree cell
-        cols = mesh_in.point2index(mesh_out.cell_centers)
+        cols = _cells_of(mesh_in, mesh_out.cell_centers)
         return sp.csr_matrix((np.ones(n_out), (np.arange(n_out), cols)), shape=(n_out, n_in))
     # tree -> tree: input cells finer than their output cell contribute their volume share; output cells no input
     # cell is finer than copy the input cell that contains them
-    rows = mesh_out.point2index(mesh_in.cell_centers)
+    rows = _cells_of(mesh_out, mesh_in.cell_centers)
     lvl_in, lvl_out = mesh_in._levels, mesh_out._levels
     finer = lvl_out[rows] < lvl_in
     w = np.where(finer, mesh_in.cell_volumes / mesh_out.cell_volumes[rows], 0.0)
@@ -205,7 +210,7 @@ def _same_base_volume_average_matrix(mesh_in, mesh_out):
     visited[rows[finer]] = True
     rest = np.nonzero(~visited)[0]
     if rest.size:
-        cols = mesh_in.point2index(mesh_out.cell_centers[rest])
+        cols = _cells_of(mesh_in, mesh_out.cell_centers[rest])
         P = P + sp.csr_matrix((np.ones(rest.size), (rest, cols)), shape=(n_out, n_in))
     return sp.csr_matrix(P)
 
