@@ -76,6 +76,103 @@ def removed_name(cls_name, name, table=_REMOVED):
     return None
 
 
+def _check_reference_system(value):
+    """reference: base/base_regular_mesh.py:238-262 (names and abbreviations)."""
+    if value is None:
+        return "cartesian"
+    choices = {"cartesian": "cartesian", "car": "cartesian", "cartesian": "cartesian", "cylindrical": "cylindrical",
+               "cyl": "cylindrical", "spherical": "spherical", "sph": "spherical"}
+    if not isinstance(value, str) or value.lower() not in choices:
+        raise ValueError("Coordinate system ({}) unknown.".format(value))
+    return choices[value.lower()]
+
+
+def _check_orientation(value, dim):
+    """Only the identity orientation is supported: the kernels address an axis-aligned grid."""
+    if value is None:
+        return
+    value = np.asarray(value, dtype=np.float64)
+    if value.shape != (dim, dim):
+        raise ValueError(f"orientation must have shape ({dim}, {dim}), got {value.shape}")
+    if not np.allclose(value, np.eye(dim)):
+        raise NotImplementedError("discretize_b200: rotated meshes (orientation != identity) are not supported")
+
+
+class _MeshPersistence:
+    """to_dict / serialize / deserialize / save / copy / equals of the reference (base/base_mesh.py:50-197), shared by
+    TensorMesh and TreeMesh.  The dictionaries (and the JSON written by ``save``) are the reference's, so meshes saved by
+    either library load in the other (``utils.load_mesh``)."""
+
+    _items = ()
+    _ref_module = "discretize"
+
+    orientation = property(lambda self: np.eye(self.dim))
+    rotation_matrix = property(lambda self: np.eye(self.dim))
+    reference_is_rotated = property(lambda self: False)
+    reference_system = property(lambda self: getattr(self, "_reference_system", "cartesian"))
+
+    def to_dict(self):
+        out = {"__module__": type(self).__module__, "__class__": type(self).__name__}
+        for item in self._items:
+            attr = getattr(self, item, None)
+            if attr is None:
+                continue
+            if isinstance(attr, np.ndarray):
+                attr = attr.tolist()
+            elif isinstance(attr, tuple):
+                attr = [a.tolist() if isinstance(a, np.ndarray) else a for a in attr]
+            out[item] = attr
+        return out
+
+    serialize = to_dict
+
+    @classmethod
+    def deserialize(cls, items, **kwargs):
+        items = dict(items)
+        items.pop("__module__", None)
+        items.pop("__class__", None)
+        return cls(**items)
+
+    def save(self, file_name="mesh.json", verbose=False, **kwargs):
+        import json
+        import os
+
+        if "filename" in kwargs:
+            raise TypeError("The filename keyword argument has been removed, please use file_name. "
+                            "This will be removed in discretize 1.0.0")
+        f = os.path.abspath(file_name)
+        with open(f, "w") as outfile:
+            json.dump(self.to_dict(), outfile)
+        if verbose:
+            print("Saved {}".format(f))
+        return f
+
+    def copy(self):
+        return type(self).deserialize(self.to_dict())
+
+    def validate(self):
+        return True
+
+    def equals(self, other_mesh):
+        if type(self) is not type(other_mesh):
+            return False
+        a, b = self.to_dict(), other_mesh.to_dict()
+        if a.keys() != b.keys():
+            return False
+        for key in a:
+            try:
+                same = np.array_equal(np.asarray(a[key], dtype=object if key == "cell_state" else None),
+                                      np.asarray(b[key], dtype=object if key == "cell_state" else None)) \
+                    if not isinstance(a[key], (str, dict)) else a[key] == b[key]
+            except Exception:
+                same = False
+            if key == "h":
+                same = len(a[key]) == len(b[key]) and all(np.array_equal(x, y) for x, y in zip(a[key], b[key]))
+            if not same:
+                return False
+        return True
+
+
 def _validate_BC(bc):
     """reference: operators/differential_operators.py:21-38."""
     if isinstance(bc, str):
@@ -135,8 +232,10 @@ def as_array_n_by_dim(pts, dim):
     return pts
 
 
-class TensorMesh:
+class TensorMesh(_MeshPersistence):
     """Tensor-product mesh with CUDA operators (reference: discretize/tensor_mesh.py)."""
+
+    _items = ("h", "origin", "shape_cells", "orientation", "reference_system")
 
     _meshType = "TENSOR"
 
@@ -144,6 +243,9 @@ class TensorMesh:
         # reference: base/base_tensor_mesh.py:86-114
         if "x0" in kwargs:
             origin = kwargs.pop("x0")
+        kwargs.pop("shape_cells", None)                 # written by to_dict; implied by h (base_tensor_mesh.py:110-111)
+        orientation = kwargs.pop("orientation", None)
+        self._reference_system = _check_reference_system(kwargs.pop("reference_system", None))
         if kwargs:
             raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
         try:
@@ -168,6 +270,7 @@ class TensorMesh:
             self.origin = origin
         self._cache = {}
         self._dev = None
+        _check_orientation(orientation, len(h))
 
     def __getattr__(self, name):
         # alias table, like BaseMesh.__getattr__ (base/base_mesh.py:24-48)

@@ -21,7 +21,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from .octree import LinearOctree
-from .tensor_mesh import TensorMesh, _ALIASES, _REMOVED, as_array_n_by_dim, is_scalar, removed_name, unpack_widths
+from .tensor_mesh import TensorMesh, _ALIASES, _MeshPersistence, _REMOVED, as_array_n_by_dim, is_scalar, removed_name, unpack_widths
 from .tree_build import TreeTopology, key3
 
 
@@ -44,11 +44,12 @@ _TREE_REMOVED.update({"cellGradStencil": "cell_gradient_stencil", "maxLevel": "m
                       "permuteCC": "permute_cells", "permuteE": "permute_edges", "permuteF": "permute_faces"})
 
 
-class TreeMesh:
+class TreeMesh(_MeshPersistence):
     """3-D OcTree.  ``TreeMesh([hx, hy])`` gives the 2-D QuadTree (``quad_mesh.QuadTreeMesh``, a subclass that shares
     the constructor and every refinement method, and assembles its operators on the host)."""
 
     _meshType = "TREE"
+    _items = ("h", "origin", "cell_state")
     _LOC_NAMES = TensorMesh._LOC_NAMES
     _parse_location_type = TensorMesh._parse_location_type
     dim = 3
@@ -63,6 +64,10 @@ class TreeMesh:
     def __init__(self, h=None, origin=None, diagonal_balance=None, **kwargs):
         if "x0" in kwargs:
             origin = kwargs.pop("x0")
+        cell_state = kwargs.pop("cell_state", None)
+        cell_indexes, cell_levels = kwargs.pop("cell_indexes", None), kwargs.pop("cell_levels", None)
+        if cell_state is None and cell_indexes is not None and cell_levels is not None:
+            cell_state = {"indexes": cell_indexes, "levels": cell_levels}
         if kwargs:
             raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
         if diagonal_balance is None:
@@ -98,6 +103,8 @@ class TreeMesh:
         self._topo = None
         self._cache = {}
         self._dev = {}
+        if cell_state is not None:       # tree_mesh.py:258-270: rebuild a saved mesh
+            self.__setstate__((cell_state["indexes"], cell_state["levels"]))
 
     def __getattr__(self, name):
         if name in _TREE_ALIASES:
@@ -535,6 +542,32 @@ class TreeMesh:
         """Cells intersecting the box ``[xmin, xmax, ymin, ymax, (zmin, zmax)]`` (tree_ext.pyx:7055-7068)."""
         r = np.asarray(rectangle, dtype=np.float64)
         return self.get_cells_in_aabb(r[0::2], r[1::2])
+
+    # ---- persistence (tree_mesh.py:1085-1118, tree_ext.pyx:6472-6507) --------------------------------------------
+    def __getstate__(self):
+        idx, lv = self._tree.state()
+        return idx, lv
+
+    def __setstate__(self, state):
+        """Rebuild from (cell-centre half-step indexes, levels).  The saved cells already carry whatever balancing the
+        mesh had, so they are taken as they are (the reference re-inserts them with ``diagonal_balance=False``)."""
+        indexes, levels = state
+        self._set_state(np.asarray(indexes, dtype=np.int64).reshape(-1, self.dim), np.asarray(levels, dtype=np.int64))
+        self.finalize()
+
+    def __reduce__(self):
+        return TreeMesh, (self.h, self.origin, False), self.__getstate__()
+
+    def validate(self):
+        return self.finalized
+
+    def equals(self, other):
+        try:
+            if self.finalized and other.finalized:
+                return super().equals(other)
+        except AttributeError:
+            pass
+        return False
 
     def _set_state(self, indexes, levels):
         """Rebuild from (cell-centre half-step locations, levels), like __setstate__ (tree_ext.pyx:6488-6507)."""

@@ -251,3 +251,22 @@ def volume_average(mesh_in, mesh_out, values=None, output=None):
         output[...] = result
         return output
     return result
+
+
+def load_mesh(file_name):
+    """Load a mesh saved by ``mesh.save()`` of this package OR of the reference (utils/io_utils.py:8-40): the JSON names
+    the class; ``discretize.TensorMesh`` / ``discretize.TreeMesh`` map to the classes of this package."""
+    import json
+
+    from . import TensorMesh, TreeMesh
+
+    with open(file_name, "r") as f:
+        items = json.load(f)
+    items.pop("__module__", None)
+    name = items.pop("__class__")
+    classes = {"TensorMesh": TensorMesh, "TreeMesh": TreeMesh, "QuadTreeMesh": TreeMesh}
+    if name not in classes:
+        raise NotImplementedError(f"discretize_b200.load_mesh: {name} is not a mesh type of this package")
+    if "_n" in items:
+        items["shape_cells"] = items.pop("_n")
+    return classes[name](**items)
