@@ -272,6 +272,10 @@ class TensorMesh(_MeshPersistence):
         self._dev = None
         _check_orientation(orientation, len(h))
 
+    def __reduce__(self):
+        # pickle / copy rebuild from the defining data; cached operators and device arrays are not carried along
+        return type(self), (self.h, self.origin)
+
     def __getattr__(self, name):
         # alias table, like BaseMesh.__getattr__ (base/base_mesh.py:24-48)
         if name in _ALIASES:
