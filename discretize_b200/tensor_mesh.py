@@ -272,6 +272,28 @@ class TensorMesh(_MeshPersistence):
         self._dev = None
         _check_orientation(orientation, len(h))
 
+    # ---- UBC-GIF files (mixins/mesh_io.py:15-420; ubc_io.py) ---------------------------------------------------------
+    @classmethod
+    def read_UBC(cls, file_name, directory=None):
+        from . import ubc_io
+
+        return ubc_io.read_tensor_mesh(cls, file_name, directory)
+
+    def write_UBC(self, file_name, models=None, directory=None, comment_lines=""):
+        from . import ubc_io
+
+        ubc_io.write_tensor_mesh(self, file_name, models, directory, comment_lines)
+
+    def read_model_UBC(self, file_name, directory=None):
+        from . import ubc_io
+
+        return ubc_io.read_tensor_model(self, file_name, directory)
+
+    def write_model_UBC(self, file_name, model, directory=None):
+        from . import ubc_io
+
+        ubc_io.write_tensor_model(self, file_name, model, directory)
+
     def __reduce__(self):
         # pickle / copy rebuild from the defining data; cached operators and device arrays are not carried along
         return type(self), (self.h, self.origin)

@@ -543,6 +543,30 @@ class TreeMesh(_MeshPersistence):
         r = np.asarray(rectangle, dtype=np.float64)
         return self.get_cells_in_aabb(r[0::2], r[1::2])
 
+    # ---- UBC-GIF files (mixins/mesh_io.py:440-615; ubc_io.py) ----------------------------------------------------
+    @classmethod
+    def read_UBC(cls, file_name, directory=None):
+        from . import ubc_io
+
+        return ubc_io.read_tree_mesh(TreeMesh, file_name, directory)      # TreeMesh(...) picks Quad / OcTree
+
+    def write_UBC(self, file_name, models=None, directory=None):
+        from . import ubc_io
+
+        ubc_io.write_tree_mesh(self, file_name, models, directory)
+
+    def read_model_UBC(self, file_name, directory=None):
+        from . import ubc_io
+
+        return ubc_io.read_tree_model(self, file_name, directory)
+
+    def write_model_UBC(self, file_name, model, directory=None):
+        from . import ubc_io
+
+        ubc_io.write_tree_model(self, file_name, model, directory)
+
+    _ubc_order = property(lambda self: __import__("discretize_b200.ubc_io", fromlist=["x"]).tree_ubc_order(self))
+
     # ---- persistence (tree_mesh.py:1085-1118, tree_ext.pyx:6472-6507) --------------------------------------------
     def __getstate__(self):
         idx, lv = self._tree.state()
