@@ -91,7 +91,16 @@ class TreeMesh(_MeshPersistence):
             self._origin = np.asarray(value, dtype=np.float64)
         self._tree = LinearOctree([x.size for x in self._h])  # raises for non powers of two
         self._diagonal_balance = bool(diagonal_balance)
-        # half-step coordinate arrays (tree_ext.pyx:397-421)
+        self._build_coordinates()
+        self._finalized = False
+        self._topo = None
+        self._cache = {}
+        self._dev = {}
+        if cell_state is not None:       # tree_mesh.py:258-270: rebuild a saved mesh
+            self.__setstate__((cell_state["indexes"], cell_state["levels"]))
+
+    def _build_coordinates(self):
+        """Half-step coordinate arrays: nodes at even, midpoints at odd positions (tree_ext.pyx:397-421)."""
         self._xs = []
         for a in range(self.dim):
             n = np.cumsum(np.r_[self._origin[a], self._h[a]])
@@ -99,12 +108,21 @@ class TreeMesh(_MeshPersistence):
             x[::2] = n
             x[1::2] = (x[:-1:2] + x[2::2]) / 2
             self._xs.append(x)
-        self._finalized = False
-        self._topo = None
+
+    def _set_origin(self, value):
+        """Move the mesh: the cells stay, every coordinate-dependent cache is dropped (tree_ext.pyx:1512-1540)."""
+        if not isinstance(value, (list, tuple, np.ndarray)):
+            raise ValueError("origin must be a list, tuple or numpy array")
+        value = list(value)
+        if len(value) != self.dim:
+            raise ValueError("Dimension mismatch. len(origin) != len(h)")
+        for i, (val, h_i) in enumerate(zip(value, self._h)):
+            if isinstance(val, str):
+                value[i] = {"C": -h_i.sum() * 0.5, "N": -h_i.sum(), "0": 0.0}[val]
+        self._origin = np.asarray(value, dtype=np.float64)
+        self._build_coordinates()
         self._cache = {}
         self._dev = {}
-        if cell_state is not None:       # tree_mesh.py:258-270: rebuild a saved mesh
-            self.__setstate__((cell_state["indexes"], cell_state["levels"]))
 
     def __getattr__(self, name):
         if name in _TREE_ALIASES:
@@ -116,7 +134,7 @@ class TreeMesh(_MeshPersistence):
 
     # ---- description ------------------------------------------------------------------------------
     h = property(lambda self: self._h)
-    origin = property(lambda self: self._origin)
+    origin = property(lambda self: self._origin, lambda self, value: self._set_origin(value))
     shape_cells = property(lambda self: tuple(int(x.size) for x in self._h))
     max_level = property(lambda self: self._tree.max_level)
     finalized = property(lambda self: self._finalized)

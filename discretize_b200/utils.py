@@ -270,3 +270,7 @@ def load_mesh(file_name):
     if "_n" in items:
         items["shape_cells"] = items.pop("_n")
     return classes[name](**items)
+
+
+from .mesh_utils import (active_from_xyz, as_array_n_by_dim, closest_points_index, extract_core_mesh, is_scalar,  # noqa: E402,F401
+                         mesh_builder_xyz, mkvc, ndgrid, refine_tree_xyz, unpack_widths)
