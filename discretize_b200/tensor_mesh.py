@@ -272,6 +272,77 @@ class TensorMesh(_MeshPersistence):
         self._dev = None
         _check_orientation(orientation, len(h))
 
+    def reshape(self, x, x_type="cell_centers", out_type="cell_centers", return_format="V", **kwargs):
+        """Reshape a discrete quantity between vectors and tensor-shaped arrays, or pick a component of a face / edge
+        vector (base/base_regular_mesh.py:817-1001).  Same argument checks and messages as the reference; like there, a
+        list input is refused (its element check tests the list itself)."""
+        if "xType" in kwargs:
+            raise TypeError("The xType keyword argument has been removed, please use x_type. "
+                            "This will be removed in discretize 1.0.0")
+        if "outType" in kwargs:
+            raise TypeError("The outType keyword argument has been removed, please use out_type. "
+                            "This will be removed in discretize 1.0.0")
+        if "format" in kwargs:
+            raise TypeError("The format keyword argument has been removed, please use return_format. "
+                            "This will be removed in discretize 1.0.0")
+        x_type = self._parse_location_type(x_type)
+        out_type = self._parse_location_type(out_type)
+        allowed = ["cell_centers", "nodes", "faces", "faces_x", "faces_y", "faces_z", "edges", "edges_x", "edges_y", "edges_z"]
+        if not isinstance(x, (list, np.ndarray)):
+            raise TypeError("x must be either a list or a ndarray")
+        if x_type not in allowed:
+            raise ValueError("x_type must be either '" + "', '".join(allowed) + "'")
+        if out_type not in allowed:
+            raise ValueError("out_type must be either '" + "', '".join(allowed) + "'")
+        if return_format not in ["M", "V"]:
+            raise ValueError("return_format must be either 'M' or 'V'")
+        if out_type[: len(x_type)] != x_type:
+            raise ValueError("You cannot change types when reshaping.")
+        if x_type not in out_type:
+            raise ValueError("You cannot change type of components.")
+        if isinstance(x, list):
+            raise TypeError("x[0] must be a numpy array")
+        x = x[:]
+        d = self.dim
+        family = "faces" if x_type.startswith("faces") else "edges"
+        shapes = [getattr(self, f"shape_{family}_{c}", None) if i < d else None for i, c in enumerate("xyz")]
+
+        def shaped(xx, nn):
+            return xx.reshape(nn, order="F") if return_format == "M" else xx.reshape(-1, order="F")
+
+        def one(xx, out_type):
+            if x_type in ("cell_centers", "nodes"):
+                nn = self.shape_cells if x_type == "cell_centers" else self.shape_nodes
+                if xx.size != np.prod(nn):
+                    raise ValueError("Number of elements must not change.")
+                return shaped(xx, nn)
+            if x_type in ("faces", "edges"):          # a component of a full face / edge vector
+                xx = xx.reshape(-1, order="F")
+                counts = (self.n_faces_per_direction if x_type == "faces" else self.n_edges_per_direction)[:d]
+                off = np.r_[0, np.cumsum(counts)]
+                for a, c in enumerate("xyz"):
+                    if c in out_type:
+                        if d <= a:
+                            raise ValueError("Dimensions of mesh not great enough for {}_{}".format(x_type, c))
+                        if xx.size != off[-1]:
+                            raise ValueError("Vector is not the right size.")
+                        return shaped(xx[off[a]:off[a + 1]], shapes[a])
+                return None
+            a = 0 if "x" in x_type else 1 if "y" in x_type else 2     # faces_x ... edges_z: one component on its own
+            nn = shapes[a]
+            if xx.size != np.prod(nn):
+                raise ValueError(f"Vector is not the right size. Expected {np.prod(nn)}, got {xx.size}")
+            return shaped(xx, nn)
+
+        is_vector_quantity = x.ndim == 2 and x.shape[1] == d
+        if out_type in ("faces", "edges"):
+            if is_vector_quantity:
+                raise ValueError("Not sure what to do with a vector vector quantity..")
+            return tuple(one(x, out_type + "_" + c) for c in "xyz"[:d])
+        if is_vector_quantity:
+            return tuple(one(x[:, k], out_type) for k in range(x.shape[1]))
+        return one(x, out_type)
+
     # ---- UBC-GIF files (mixins/mesh_io.py:15-420; ubc_io.py) ---------------------------------------------------------
     @classmethod
     def read_UBC(cls, file_name, directory=None):
