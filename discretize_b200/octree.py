@@ -123,6 +123,58 @@ class LinearOctree:
             sel = leaf_lvl == l
             self._add_divided(int(l), np.unique(self.pack(int(l), leaf_lo[sel] // self.level_width(int(l)))))
 
+    def refine_sequential(self, ask, diagonal):
+        """The reference's ``refine(function)`` exactly (tree.cpp:398-419 with the in-flight balancing of
+        ``Cell::divide`` :459-746): one depth-first pass in cell order; a LEAF reached by the pass is asked for its level
+        and divided if it wants more; dividing a cell immediately divides every coarser (face-, with ``diagonal`` also
+        edge- / corner-) neighbour, recursively.  Cells that such a ripple creates AHEAD of the pass are asked when the
+        pass reaches them, cells it creates behind the pass never are -- the result depends on that order, so this path is
+        sequential (it calls a Python function per cell anyway).  ``ask(level, coords_tuple) -> level``."""
+        import itertools
+
+        dim = self.dim
+        divided = {l: set(self.div[l].tolist()) for l in self.div}
+        grids = {l: self.grid(l) for l in range(self.root_level, self.max_level + 1)}
+        dirs = [v for v in itertools.product((-1, 0, 1), repeat=dim) if any(v)]
+        if not diagonal:
+            dirs = [v for v in dirs if sum(abs(x) for x in v) == 1]
+        offs = [tuple(int(x) for x in o) for o in _child_offsets(dim)]
+
+        def pack(l, c):
+            g = grids[l]
+            return c[0] + g[0] * c[1] if dim == 2 else c[0] + g[0] * (c[1] + g[1] * c[2])
+
+        def divide(l, c):
+            p = pack(l, c)
+            if l >= self.max_level or p in divided[l]:
+                return
+            divided[l].add(p)
+            if l > self.root_level:
+                g = grids[l]
+                for v in dirs:
+                    nb = tuple(a + b for a, b in zip(c, v))
+                    if all(0 <= x < n for x, n in zip(nb, g)):
+                        divide(l - 1, tuple(x >> 1 for x in nb))       # no-op unless that neighbour is coarser
+
+        def visit(l, c):
+            if l == self.max_level:
+                return
+            if pack(l, c) not in divided[l]:
+                want = int(ask(l, c))
+                if want < 0:
+                    want = (self.max_level + 1) - (abs(want) % (self.max_level + 1))
+                if want <= l:
+                    return
+                divide(l, c)
+            for o in offs:
+                visit(l + 1, tuple(2 * a + b for a, b in zip(c, o)))
+
+        for root in self.root_cells():
+            visit(self.root_level, tuple(int(x) for x in root))
+        for l in self.div:
+            self.div[l] = np.array(sorted(divided[l]), dtype=np.int64)
+        self._leaves = None
+
     def set_leaves(self, lo, lvl):
         """Rebuild the divided sets from an explicit leaf list (ancestor closure)."""
         self.div = {l: np.zeros(0, dtype=np.int64) for l in range(self.root_level, self.max_level)}

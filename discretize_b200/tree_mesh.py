@@ -39,6 +39,82 @@ _TREE_ALIASES.update({
 })
 
 
+class TreeCell:
+    """One cell of a TreeMesh: what ``mesh[i]`` returns and what a ``refine(function)`` callback receives
+    (reference: ``TreeCell``, tree_ext.pyx:23-345).  During refinement the cell is not numbered yet: ``index`` is -1 and
+    the connectivity properties are unavailable, as they would be meaningless in the reference at that point."""
+
+    __slots__ = ("_mesh", "_lo", "_width", "_lvl", "_idx")
+
+    def __init__(self, mesh, lo, width, level, index=-1):
+        self._mesh, self._lo, self._width, self._lvl, self._idx = mesh, np.asarray(lo, dtype=np.int64), int(width), int(level), int(index)
+
+    def _corner(self, side):
+        xs = self._mesh._xs
+        return np.array([xs[d][2 * (self._lo[d] + side * self._width)] for d in range(self._mesh.dim)])
+
+    dim = property(lambda self: self._mesh.dim)
+    index = property(lambda self: self._idx)
+    _level = property(lambda self: self._lvl)
+    _index_loc = property(lambda self: tuple(int(2 * l + self._width) for l in self._lo))
+    origin = property(lambda self: self._corner(0))
+    x0 = property(lambda self: self._corner(0))
+    h = property(lambda self: self._corner(1) - self._corner(0))
+    center = property(lambda self: (self._corner(0) + self._corner(1)) * 0.5)
+
+    @property
+    def bounds(self):
+        a, b = self._corner(0), self._corner(1)
+        return np.stack([a, b], axis=1).reshape(-1)
+
+    def _topology(self):
+        if self._idx < 0:
+            raise TreeMeshNotFinalizedError("cell connectivity is available once the TreeMesh is finalized")
+        return self._mesh._t()
+
+    @property
+    def nodes(self):
+        t = self._topology()
+        return [int(i) for i in t.nodes.index[t.cell_nodes[self._idx]]]
+
+    @property
+    def edges(self):
+        t = self._topology()
+        return [int(i) for d in range(self._mesh.dim) for i in t.edges[d].index[t.cell_edges[d][self._idx]]]
+
+    @property
+    def faces(self):
+        t = self._topology()
+        return [int(i) for d in range(self._mesh.dim) for i in t.faces[d].index[t.cell_faces[d][self._idx]]]
+
+    @property
+    def neighbors(self):
+        """[-x, +x, -y, +y, (-z, +z)]: a cell index, -1 outside the mesh, or the list of the finer cells across that
+        face (lower tangential axis fastest)."""
+        self._topology()
+        m = self._mesh
+        dim = m.dim
+        c, h = self.center, self.h
+        out = []
+        for axis in range(dim):
+            tang = [a for a in range(dim) if a != axis]
+            for sign in (-1.0, 1.0):
+                pts = []
+                for corner in range(2 ** (dim - 1)):
+                    p = c.copy()
+                    p[axis] += sign * 0.75 * h[axis]
+                    for k, a in enumerate(tang):
+                        p[a] += (0.25 if (corner >> k) & 1 else -0.25) * h[a]
+                    pts.append(p)
+                pts = np.array(pts)
+                if not m.is_inside(pts)[0]:
+                    out.append(-1)
+                    continue
+                idx = m._containing_cells(pts)
+                out.append(int(idx[0]) if np.all(idx == idx[0]) else [int(i) for i in idx])
+        return out
+
+
 _TREE_REMOVED = dict(_REMOVED)
 _TREE_REMOVED.update({"cellGradStencil": "cell_gradient_stencil", "maxLevel": "max_used_level",
                       "permuteCC": "permute_cells", "permuteE": "permute_edges", "permuteF": "permute_faces"})
@@ -293,24 +369,35 @@ class TreeMesh(_MeshPersistence):
         if finalize:
             self.finalize()
 
-    def refine(self, function, finalize=True, diagonal_balance=None):
-        """Refine to a constant level (int) or to ``function(cell_centers) -> levels`` (vectorised)."""
+    def refine(self, function, finalize=True, diagonal_balance=None, vectorized=False):
+        """Refine to a constant level (int) or with ``function(cell) -> level``, called with a :class:`TreeCell` for the
+        cells a depth-first pass reaches as leaves -- the reference's semantics, including its dependence on the order in
+        which balancing creates cells (tree_ext.pyx:494-558, tree.cpp:398-419).  ``vectorized=True`` (an extension) calls
+        ``function(cell_centers) -> levels`` on all current cells per pass instead and balances at the end."""
         self._require_open()
         db = self._diagonal_balance if diagonal_balance is None else diagonal_balance
         t = self._tree
-        while True:
-            lo, lvl = t.leaves()
-            w = t.width(lvl)
-            if callable(function):
-                c = np.stack([(self._xs[d][2 * lo[:, d]] + self._xs[d][2 * (lo[:, d] + w)]) * 0.5 for d in range(self.dim)], axis=1)
-                want = np.asarray(function(c), dtype=np.int64)
-            else:
-                want = np.full(lvl.size, self._parse_level(int(function)), dtype=np.int64)
-            mask = (want > lvl) & (lvl < t.max_level)
-            if not mask.any():
-                break
-            t.divide_leaves(lo[mask], lvl[mask])
-        t.balance(db)
+        if callable(function) and not vectorized:
+            def ask(level, coords):
+                w = t.level_width(level)
+                return function(TreeCell(self, [c * w for c in coords], w, level))
+
+            t.refine_sequential(ask, db)
+        else:
+            while True:
+                lo, lvl = t.leaves()
+                w = t.width(lvl)
+                if callable(function):
+                    c = np.stack([(self._xs[d][2 * lo[:, d]] + self._xs[d][2 * (lo[:, d] + w)]) * 0.5
+                                  for d in range(self.dim)], axis=1)
+                    want = np.asarray(function(c), dtype=np.int64)
+                else:
+                    want = np.full(lvl.size, self._parse_level(int(function)), dtype=np.int64)
+                mask = (want > lvl) & (lvl < t.max_level)
+                if not mask.any():
+                    break
+                t.divide_leaves(lo[mask], lvl[mask])
+            t.balance(db)
         if finalize:
             self.finalize()
 
@@ -584,6 +671,26 @@ class TreeMesh(_MeshPersistence):
         ubc_io.write_tree_model(self, file_name, model, directory)
 
     _ubc_order = property(lambda self: __import__("discretize_b200.ubc_io", fromlist=["x"]).tree_ubc_order(self))
+
+    # ---- cells as objects (tree_ext.pyx:6509-6533) ---------------------------------------------------------------
+    def __len__(self):
+        return self.n_cells
+
+    def __getitem__(self, key):
+        if isinstance(key, slice):
+            return [self[ii] for ii in range(*key.indices(len(self)))]
+        if isinstance(key, (int, np.integer)):
+            if key < 0:
+                key += len(self)
+            if key >= len(self):
+                raise IndexError("The index ({0:d}) is out of range.".format(key))
+            lo, lvl = self._tree.leaves()
+            return TreeCell(self, lo[key], self._tree.width(lvl[key]), lvl[key], key)
+        raise TypeError("Invalid argument type.")
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
 
     # ---- persistence (tree_mesh.py:1085-1118, tree_ext.pyx:6472-6507) --------------------------------------------
     def __getstate__(self):
