@@ -66,6 +66,22 @@ _REMOVED_INDEXED = {       # base/base_regular_mesh.py / base_tensor_mesh.py: re
 }
 
 
+# removed METHODS: the attribute exists, calling it raises (utils/code_utils.py: deprecate_method(..., error=True))
+_REMOVED_METHODS = {"readUBC": "read_UBC", "readModelUBC": "read_model_UBC", "writeUBC": "write_UBC",
+                    "writeModelUBC": "write_model_UBC", "r": "reshape"}
+
+
+def removed_method(cls_name, name):
+    """A callable that raises like the reference's removed methods, or None."""
+    if name not in _REMOVED_METHODS:
+        return None
+
+    def removed(*args, **kwargs):
+        raise NotImplementedError(f"{cls_name}.{name} has been removed, please use {cls_name}.{_REMOVED_METHODS[name]}.")
+
+    return removed
+
+
 def removed_name(cls_name, name, table=_REMOVED):
     """NotImplementedError for a name the reference has removed, or None."""
     if name in table:
@@ -376,6 +392,9 @@ class TensorMesh(_MeshPersistence):
         err = removed_name(type(self).__name__, name)
         if err is not None:
             raise err
+        method = removed_method(type(self).__name__, name)
+        if method is not None:
+            return method
         raise AttributeError(f"'{type(self).__name__}' object has no attribute '{name}'")
 
     # ---- basic description ---------------------------------------------------------------

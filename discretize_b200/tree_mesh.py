@@ -21,7 +21,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from .octree import LinearOctree
-from .tensor_mesh import TensorMesh, _ALIASES, _MeshPersistence, _REMOVED, as_array_n_by_dim, is_scalar, removed_name, unpack_widths
+from .tensor_mesh import TensorMesh, _ALIASES, _MeshPersistence, _REMOVED, as_array_n_by_dim, is_scalar, removed_method, removed_name, unpack_widths
 from .tree_build import TreeTopology, key3
 
 
@@ -206,6 +206,9 @@ class TreeMesh(_MeshPersistence):
         err = removed_name(type(self).__name__, name, _TREE_REMOVED)
         if err is not None:
             raise err
+        method = None if name == "r" else removed_method("TreeMesh", name)
+        if method is not None:
+            return method
         raise AttributeError(f"'{type(self).__name__}' object has no attribute '{name}'")
 
     # ---- description ------------------------------------------------------------------------------
@@ -671,6 +674,90 @@ class TreeMesh(_MeshPersistence):
         ubc_io.write_tree_model(self, file_name, model, directory)
 
     _ubc_order = property(lambda self: __import__("discretize_b200.ubc_io", fromlist=["x"]).tree_ubc_order(self))
+
+    # ---- remaining small pieces of the reference's TreeMesh ----------------------------------------------------------
+    def refine_image(self, image, finalize=True, diagonal_balance=None):
+        """Divide every cell whose block of the base-mesh image is not constant (tree_ext.pyx:1217-1264,
+        tree.cpp:421-457).  A block that is constant has constant sub-blocks, so the set of divided cells does not depend
+        on the traversal: per level, a min / max pooling of the image marks the boxes to divide."""
+        self._require_open()
+        db = self._diagonal_balance if diagonal_balance is None else diagonal_balance
+        image = np.asarray(image, dtype=np.float64)
+        n_expected = int(np.prod(self.shape_cells))
+        if image.size != n_expected:
+            raise ValueError(f"image array size: {image.size} must match the total number of cells in the base tensor "
+                             f"mesh: {n_expected}")
+        if image.ndim == 1:
+            image = image.reshape(self.shape_cells, order="F")
+        if image.shape != tuple(self.shape_cells):
+            raise ValueError(f"image array shape: {image.shape} must match the base cell shapes: {self.shape_cells}")
+        t = self._tree
+        for l in range(t.root_level, t.max_level):
+            w = t.level_width(l)
+            g = t.grid(l)
+            blocks = image.reshape([x for n in g for x in (n, w)])
+            axes = tuple(range(1, 2 * self.dim, 2))
+            mixed = blocks.max(axis=axes) != blocks.min(axis=axes)
+            coords = np.stack(np.nonzero(mixed), axis=1).astype(np.int64)
+            if coords.shape[0]:
+                t._add_divided(l, np.unique(t.pack(l, coords)))
+        t.balance(db)
+        if finalize:
+            self.finalize()
+
+    @property
+    def fill(self):
+        """Number of cells over the number of cells of the underlying tensor mesh (tree_ext.pyx:1590-1608)."""
+        return float(self.n_cells) / float(np.prod(self.shape_cells))
+
+    def number(self):
+        """Numbering happens in ``finalize``; kept for scripts that call it (tree_ext.pyx:1316-1318)."""
+        self._t()
+
+    def get_tensor(self, key):
+        """1-D sample vectors of the UNDERLYING tensor grid for a location type (base_tensor_mesh.py:567-634)."""
+        key = self._parse_location_type(key)
+        nodes = [self.nodes_x, self.nodes_y, self.nodes_z][:self.dim]
+        centers = [(n[1:] + n[:-1]) / 2 for n in nodes]
+        if key == "cell_centers":
+            on_nodes = ()
+        elif key == "nodes":
+            on_nodes = tuple(range(self.dim))
+        elif key.startswith("faces_"):
+            on_nodes = ("xyz".index(key[-1]),)
+        elif key.startswith("edges_"):
+            on_nodes = tuple(a for a in range(self.dim) if a != "xyz".index(key[-1]))
+        else:
+            raise ValueError(f"Unrecognized location type {key}")
+        return [nodes[a] if a in on_nodes else centers[a] for a in range(self.dim)]
+
+    @property
+    def nodal_laplacian(self):
+        raise NotImplementedError("Nodal Laplacian has not been implemented for TreeMesh")
+
+    def get_boundary_cells(self, active_ind=None, direction="zu"):
+        """Cells on the outer boundary in ``direction`` ('xd', 'xu', 'yd', 'yu', 'zd', 'zu'), or -- with ``active_ind`` -- the
+        active cells whose neighbour(s) in that direction are missing or inactive (tree_ext.pyx:2923-2986)."""
+        direction = direction.lower()
+        if direction[0] == "z" and self.dim == 2:
+            direction = "y" + direction[1]
+        dir_ind = {"xd": 0, "xu": 1, "yd": 2, "yu": 3, "zd": 4, "zu": 5}[direction]
+        if active_ind is None:
+            return self.cell_boundary_indices[dir_ind]
+        act = np.asarray(active_ind).astype(bool)
+        axis, sign = dir_ind // 2, (1.0 if dir_ind % 2 else -1.0)
+        cc, hg = self.cell_centers, self.h_gridded
+        tang = [a for a in range(self.dim) if a != axis]
+        bound = np.zeros(self.n_cells, dtype=bool)
+        for corner in range(2 ** (self.dim - 1)):          # the (up to) 2 / 4 finer neighbours across the face
+            p = cc.copy()
+            p[:, axis] += sign * 0.75 * hg[:, axis]
+            for k, a in enumerate(tang):
+                p[:, a] += (0.25 if (corner >> k) & 1 else -0.25) * hg[:, a]
+            inside = self.is_inside(p)
+            nb = self._containing_cells(p)
+            bound |= ~inside | ~act[nb]
+        return np.where(bound & act)
 
     # ---- cells as objects (tree_ext.pyx:6509-6533) ---------------------------------------------------------------
     def __len__(self):

@@ -22,6 +22,9 @@ def main():
     for case in gc.cases():
         for k, v in gc.evaluate(ref, case).items():
             out[f"{case[0]}|{k}"] = v
+    for case in gc.image_cases():
+        for k, v in gc.evaluate_image(ref, case).items():
+            out[f"{case[0]}|{k}"] = v
     path = os.path.join(HERE, "tree_geometry_small.npz")
     np.savez_compressed(path, **out)
     print(len(out), "entries ->", path, os.path.getsize(path) // 1024, "KiB")

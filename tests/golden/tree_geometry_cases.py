@@ -53,3 +53,36 @@ def evaluate(lib, case):
     if d == 3:
         out["prism"] = np.sort(m.get_cells_in_vertical_trianglular_prism(q["tri"], 0.2))
     return {k: np.asarray(v) for k, v in out.items()}
+
+
+def image_cases():
+    out = []
+    for seed in range(8):
+        rng = np.random.default_rng(100 + seed)
+        d = 2 + seed % 2
+        n = [2 ** int(rng.integers(2, 5 if d == 3 else 6)) for _ in range(d)]
+        h = [rng.random(k) * .5 + .5 for k in n]
+        o = rng.random(d)
+        img = np.zeros(n)
+        for _ in range(3):
+            lo = [int(rng.integers(0, k)) for k in n]
+            hi = [int(rng.integers(a + 1, k + 1)) for a, k in zip(lo, n)]
+            img[tuple(slice(a, b) for a, b in zip(lo, hi))] = rng.integers(1, 4)
+        out.append((f"img{seed}_{d}d", h, o, bool(seed % 3 == 0), img if seed % 2 else img.reshape(-1, order="F"), seed))
+    return out
+
+
+def evaluate_image(lib, case):
+    tag, h, o, db, img, seed = case
+    m = lib.TreeMesh(h, origin=o, diagonal_balance=db)
+    m.refine_image(img)
+    act = np.random.default_rng(seed).random(m.n_cells) > 0.3
+    out = {"cell_centers": m.cell_centers, "levels": np.asarray(m._cell_levels_by_indexes(), dtype=np.int64),
+           "fill": np.array(m.fill)}
+    for direction in ("xd", "xu", "yd", "yu", "zd", "zu"):
+        out["boundary_" + direction] = np.asarray(m.get_boundary_cells(direction=direction))
+        out["active_boundary_" + direction] = np.asarray(m.get_boundary_cells(act, direction)[0])
+    for key in ("CC", "N", "Fx", "Ey"):
+        for a, t in enumerate(m.get_tensor(key)):
+            out[f"tensor_{key}_{a}"] = np.asarray(t)
+    return out

@@ -27,6 +27,19 @@ def test_refinement_and_queries_match_reference(case):
         assert np.array_equal(got, ref), k
 
 
+IMAGE_CASES = gc.image_cases()
+
+
+@pytest.mark.parametrize("case", IMAGE_CASES, ids=[c[0] for c in IMAGE_CASES])
+def test_refine_image_boundary_cells_and_tensors_match_reference(case):
+    ours = gc.evaluate_image(dz, case)
+    keys = [k for k in GOLD.files if k.startswith(case[0] + "|")]
+    assert sorted(k.split("|", 1)[1] for k in keys) == sorted(ours)
+    for k in keys:
+        ref, got = GOLD[k], ours[k.split("|", 1)[1]]
+        assert got.shape == ref.shape and np.array_equal(got, ref), k
+
+
 def test_argument_checks():
     m = dz.TreeMesh([8, 8, 8])
     with pytest.raises(ValueError, match="do not broadcast"):
@@ -40,6 +53,12 @@ def test_argument_checks():
         m.refine_line(np.zeros((2, 3)), 1)
     with pytest.raises(ValueError, match="A line segment has two points"):
         m.get_cells_on_line(np.zeros((3, 3)))
+    with pytest.raises(ValueError, match="image array size"):
+        dz.TreeMesh([8, 8]).refine_image(np.zeros(10))
+    with pytest.raises(NotImplementedError, match="has been removed"):
+        m.readUBC("x")
+    with pytest.raises(NotImplementedError, match="Nodal Laplacian"):
+        m.nodal_laplacian
     with pytest.raises(NotImplementedError):
         q = dz.TreeMesh([8, 8])
         q.refine(1)
