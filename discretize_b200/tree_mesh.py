@@ -759,6 +759,87 @@ class TreeMesh(_MeshPersistence):
             bound |= ~inside | ~act[nb]
         return np.where(bound & act)
 
+    def get_cells_along_line(self, x0, x1):
+        """Indices of the cells a segment passes through, in order from ``x0`` to ``x1`` (tree_ext.pyx:2989-3112): from
+        the cell containing ``x0``, repeatedly leave through the face(s) the segment crosses first -- several at once when
+        it leaves through an edge or a corner -- into the neighbour at the same or a coarser level, then descend to the
+        leaf nearest the crossing point.  A short sequential walk; cells are handled as (level, integer coordinates)."""
+        self._t()
+        tr = self._tree
+        dim = self.dim
+        a = np.asarray(x0, dtype=np.float64).reshape(-1)
+        b = np.asarray(x1, dtype=np.float64).reshape(-1)
+        if "div_sets" not in self._cache:
+            self._cache["div_sets"] = {l: set(tr.div[l].tolist()) for l in tr.div}
+        divided = self._cache["div_sets"]
+        leaf_lo, _ = tr.leaves()
+        leaf_keys = tr.keys(leaf_lo)
+
+        def pack(l, c):
+            g = tr.grid(l)
+            return c[0] + g[0] * c[1] if dim == 2 else c[0] + g[0] * (c[1] + g[1] * c[2])
+
+        def is_divided(l, c):
+            return l < tr.max_level and pack(l, c) in divided[l]
+
+        def exists(l, c):
+            return l == tr.root_level or is_divided(l - 1, tuple(x >> 1 for x in c))
+
+        def neighbour(l, c, axis, sign):
+            nb = list(c)
+            nb[axis] += sign
+            if not 0 <= nb[axis] < tr.grid(l)[axis]:
+                return None
+            nb = tuple(nb)
+            while not exists(l, nb):                 # the coarser leaf that covers the box
+                l, nb = l - 1, tuple(x >> 1 for x in nb)
+            return l, nb
+
+        def index_of(l, c):
+            w = tr.level_width(l)
+            lo = np.array([[x * w for x in c]], dtype=np.int64)
+            return int(np.searchsorted(leaf_keys, tr.keys(lo))[0])
+
+        def cell_of_point(p):
+            i = int(self._containing_cells(p[None])[0])
+            lo, lvl = tr.leaves()
+            w = int(tr.width(lvl[i]))
+            return int(lvl[i]), tuple(int(x) // w for x in lo[i])
+
+        cur = cell_of_point(a)
+        last = cell_of_point(b)
+        out = [index_of(*cur)]
+        while cur != last:
+            l, c = cur
+            w = tr.level_width(l)
+            lo = np.array([self._xs[d][2 * c[d] * w] for d in range(dim)])
+            hi = np.array([self._xs[d][2 * (c[d] + 1) * w] for d in range(dim)])
+            t_axis = np.full(dim, np.inf)
+            for d in range(dim):
+                if a[d] > b[d]:
+                    t_axis[d] = (lo[d] - a[d]) / (b[d] - a[d])
+                elif a[d] < b[d]:
+                    t_axis[d] = (hi[d] - a[d]) / (b[d] - a[d])
+            t = t_axis.min()
+            if t >= 1:
+                break
+            ip = (b - a) * t + a
+            nxt = cur
+            for d in range(dim):
+                if nxt is not None and t == t_axis[d]:
+                    nxt = neighbour(nxt[0], nxt[1], d, -1 if a[d] > b[d] else 1)
+            if nxt is None:
+                break
+            l, c = nxt
+            while is_divided(l, c):
+                w = tr.level_width(l)
+                centre = [self._xs[d][2 * c[d] * w + w] for d in range(dim)]
+                bits = [int(ip[d] > centre[d] or (ip[d] == centre[d] and a[d] < b[d])) for d in range(dim)]
+                l, c = l + 1, tuple(2 * c[d] + bits[d] for d in range(dim))
+            cur = (l, c)
+            out.append(index_of(l, c))
+        return out
+
     # ---- cells as objects (tree_ext.pyx:6509-6533) ---------------------------------------------------------------
     def __len__(self):
         return self.n_cells

@@ -52,6 +52,11 @@ def evaluate(lib, case):
            "overlapping": np.sort(m.get_overlapping_cells(np.stack(q["aabb"], axis=1).reshape(-1)))}
     if d == 3:
         out["prism"] = np.sort(m.get_cells_in_vertical_trianglular_prism(q["tri"], 0.2))
+    # ordered walks: a generic segment, one that leaves the mesh, one from node to node (crosses edges / corners exactly)
+    out["along_line"] = np.asarray(m.get_cells_along_line(q["line"][0], q["line"][1]), dtype=np.int64)
+    out["along_line_reversed"] = np.asarray(m.get_cells_along_line(q["line"][1], q["line"][0]), dtype=np.int64)
+    nodes = m.nodes
+    out["along_line_nodes"] = np.asarray(m.get_cells_along_line(nodes[len(nodes) // 7], nodes[(5 * len(nodes)) // 7]), dtype=np.int64)
     return {k: np.asarray(v) for k, v in out.items()}
 
 
