@@ -1,0 +1,25 @@
+"""Generates tests/golden/matrix_utils_small.npz with the UNMODIFIED reference's discretize.utils (cases in
+matrix_utils_cases.py)."""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+from oracle.refload import load_reference  # noqa: E402
+import matrix_utils_cases as mc  # noqa: E402
+
+if __name__ == "__main__":
+    warnings.simplefilter("ignore")
+    ref = load_reference()
+    assert ref is not None
+    import discretize.utils as ru
+
+    out = mc.evaluate(ru, ref)
+    path = os.path.join(HERE, "matrix_utils_small.npz")
+    np.savez_compressed(path, **out)
+    print(len(out), "entries ->", path, os.path.getsize(path) // 1024, "KiB")
