@@ -12,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 from oracle.refload import load_reference  # noqa: E402
+import _pack  # noqa: E402
 import boundary_cases as bc  # noqa: E402
 
 
@@ -29,7 +30,7 @@ def main():
         for k, v in bc.evaluate(mesh, tree=True).items():
             out[f"{tag}|{k}"] = v
     path = os.path.join(HERE, "boundary_small.npz")
-    np.savez_compressed(path, **out)
+    _pack.save(path, out)
     print(len(out), "entries ->", path, os.path.getsize(path) // 1024, "KiB")
 
 

@@ -11,6 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 from oracle.refload import load_reference  # noqa: E402
+import _pack  # noqa: E402
 import quadtree_cases as qc  # noqa: E402
 
 
@@ -30,7 +31,7 @@ def main():
     mesh = qc.build(ref, h, origin, kind, diagonal_balance=True)
     out["diag|cell_centers"], out["diag|levels"] = mesh.cell_centers, np.asarray(mesh._cell_levels_by_indexes())
     path = os.path.join(HERE, "quadtree_small.npz")
-    np.savez_compressed(path, **out)
+    _pack.save(path, out)
     print(len(out), "entries ->", path, os.path.getsize(path) // 1024, "KiB")
 
 

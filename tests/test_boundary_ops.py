@@ -14,9 +14,10 @@ import pytest
 import discretize_b200 as dz
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import _pack  # noqa: E402
 import boundary_cases as bc  # noqa: E402
 
-GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "boundary_small.npz"))
+GOLD = _pack.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "boundary_small.npz"))
 RTOL = 1e-13
 
 

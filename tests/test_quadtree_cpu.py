@@ -14,9 +14,10 @@ import pytest
 import discretize_b200 as dz
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import _pack  # noqa: E402
 import quadtree_cases as qc  # noqa: E402
 
-GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "quadtree_small.npz"))
+GOLD = _pack.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "quadtree_small.npz"))
 SPECS = {s[0]: s for s in qc.specs()}
 EXACT = ("count:", "array:", "levels", "point2index", "interp:", "index:")
 
