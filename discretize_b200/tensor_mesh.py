@@ -288,6 +288,56 @@ class TensorMesh(_MeshPersistence):
         self._dev = None
         _check_orientation(orientation, len(h))
 
+    # ---- cells as objects (tensor_mesh.py:160-310; tensor_cell.py) -----------------------------------------------------
+    def __len__(self):
+        return self.n_cells
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def _sanitize_indices(self, indices, dim=None):
+        if isinstance(indices, tuple):
+            return tuple(i if i >= 0 else i + self.shape_cells[a] for a, i in enumerate(indices))
+        if indices < 0:
+            return indices + (self.n_cells if dim is None else self.shape_cells[dim])
+        return indices
+
+    def _get_cell(self, indices):
+        from .tensor_cell import TensorCell
+
+        assert all(index >= 0 for index in indices)
+        nodes = [self._nodes_1d(a) for a in range(self.dim)]
+        origin = np.array([nodes[a][i] for a, i in enumerate(indices)])
+        h = np.array([nodes[a][i + 1] - nodes[a][i] for a, i in enumerate(indices)])
+        return TensorCell(h, origin, tuple(indices), self.shape_cells)
+
+    def __getitem__(self, indices):
+        """A TensorCell for an int (ravelled) or a tuple of ints; a list of cells when slices are involved."""
+        import itertools
+
+        def span(sl, end):
+            start = 0 if sl.start is None else sl.start
+            stop = end if sl.stop is None else sl.stop
+            step = 1 if sl.step is None else sl.step
+            start, stop = (start + end if start < 0 else start), (stop + end if stop < 0 else stop)
+            return reversed(range(start, stop, abs(step))) if step < 0 else range(start, stop, step)
+
+        if isinstance(indices, slice):
+            return [self[i] for i in span(indices, len(self))]
+        if np.issubdtype(type(indices), np.integer):
+            indices = np.unravel_index(self._sanitize_indices(indices), self.shape_cells, order="F")
+        if not isinstance(indices, tuple):
+            raise ValueError(f"Invalid indices '{indices}'. It should be an int, a slice or a tuple of int and slices.")
+        if len(indices) != self.dim:
+            raise ValueError(f"Invalid number of indices '{len(indices)}'. "
+                             f"It should match the number of dimensions of the mesh ({self.dim}).")
+        if all(np.issubdtype(type(i), np.integer) for i in indices):
+            return self._get_cell(self._sanitize_indices(tuple(indices)))
+        per_axis = [list(span(i, self.shape_cells[a])) if isinstance(i, slice) else [self._sanitize_indices(i, dim=a)]
+                    for a, i in enumerate(indices)]
+        cells = [self._get_cell(i[::-1]) for i in itertools.product(*per_axis[::-1])]      # first axis fastest
+        return cells if cells else None
+
     def reshape(self, x, x_type="cell_centers", out_type="cell_centers", return_format="V", **kwargs):
         """Reshape a discrete quantity between vectors and tensor-shaped arrays, or pick a component of a face / edge
         vector (base/base_regular_mesh.py:817-1001).  Same argument checks and messages as the reference; like there, a
