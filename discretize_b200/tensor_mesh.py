@@ -89,6 +89,10 @@ def removed_name(cls_name, name, table=_REMOVED):
     if name in _REMOVED_INDEXED:
         return NotImplementedError(f"The {name} property is removed, please access as {_REMOVED_INDEXED[name]}. "
                                    "This message will be removed in discretize 1.0.0.")
+    if name in ("axis_u", "axis_v", "axis_w"):      # base_regular_mesh.py: the first message carries the reference's typo
+        word = "rmoved" if name == "axis_u" else "removed"
+        return NotImplementedError(f"The {name} property is {word}, please access as self.orientation[{'uvw'.index(name[-1])}]. "
+                                   "This will be removed in discretize 1.0.0.")
     return None
 
 
