@@ -296,6 +296,9 @@ class TensorMesh(_MeshPersistence):
     def __len__(self):
         return self.n_cells
 
+    def __bool__(self):
+        return True          # a mesh is not "empty"; len() of an unfinalized tree must not be consulted for truth
+
     def __iter__(self):
         return (self[i] for i in range(len(self)))
 

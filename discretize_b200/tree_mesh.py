@@ -844,6 +844,9 @@ class TreeMesh(_MeshPersistence):
     def __len__(self):
         return self.n_cells
 
+    def __bool__(self):
+        return True          # a mesh is not "empty"; len() of an unfinalized tree must not be consulted for truth
+
     def __getitem__(self, key):
         if isinstance(key, slice):
             return [self[ii] for ii in range(*key.indices(len(self)))]
