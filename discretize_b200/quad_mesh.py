@@ -20,9 +20,7 @@ import scipy.sparse as sp
 from .quad_build import QuadTopology
 from .tensor_mesh import as_array_n_by_dim, is_scalar
 from .tree_build import key3
-from .tree_mesh import TreeMesh, TreeMeshNotFinalizedError
-
-_EPS = 100 * np.finfo(float).eps
+from .tree_mesh import TreeMesh
 
 
 def _csr(rows, cols, vals, shape):

@@ -1,7 +1,6 @@
 """TreeMesh operators on the GPU: coded CSR connectivity + the tree_spmv kernel (K12)."""
 from __future__ import annotations
 
-import ctypes as C
 
 import numpy as np
 import scipy.sparse as sp
