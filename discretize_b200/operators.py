@@ -308,12 +308,23 @@ class TransposedOperator(Operator):
 
 
 class DiagonalOperator(Operator):
-    """diag(d) as an operator (one streaming kernel); ``d``: numpy array or CUDA tensor."""
+    """diag(d) as an operator (one streaming kernel); ``d``: numpy array or CUDA tensor.  A numpy diagonal is uploaded on
+    first use, so operators built from host data (1-D / 2-D meshes) can be composed and ``.tocsr()``-ed without a GPU."""
 
     def __init__(self, diag):
-        self.diag = to_device(diag).reshape(-1)
-        n = self.diag.numel()
+        if isinstance(diag, torch.Tensor):
+            self._host, self._dev = None, to_device(diag).reshape(-1)
+            n = self._dev.numel()
+        else:
+            self._host, self._dev = np.ascontiguousarray(np.asarray(diag, dtype=np.float64).reshape(-1)), None
+            n = self._host.size
         super().__init__((n, n))
+
+    @property
+    def diag(self):
+        if self._dev is None:
+            self._dev = to_device(self._host).reshape(-1)
+        return self._dev
 
     def _dev_apply(self, x, out):
         from ._lib import check, load
@@ -328,7 +339,7 @@ class DiagonalOperator(Operator):
     _adjoint = _transpose
 
     def diagonal(self):
-        return self.diag.cpu().numpy()
+        return self._host.copy() if self._host is not None else self._dev.cpu().numpy()
 
     def _tocsr(self):
         import scipy.sparse as sp

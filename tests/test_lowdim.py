@@ -68,6 +68,21 @@ def test_host_assembly_matches_reference_fixture(gold, tag):
         lowdim.interpolation_matrix(m, gold[f"{tag}_pts_out"], "CC")
 
 
+def test_composites_assemble_without_a_gpu(gold):
+    """Host-assembled operators (CSR and numpy diagonals) compose and materialise on the CPU: system matrices for a direct
+    solver do not need the device."""
+    m = _mesh(gold, "d2")
+    Gr = golden_matrix(gold, "d2_nodal_gradient")
+    Dr = golden_matrix(gold, "d2_face_divergence")
+    sig = gold["d2_model_iso"]
+    A = (m.nodal_gradient.T @ m.get_edge_inner_product(sig) @ m.nodal_gradient).tocsr()
+    Ar = Gr.T @ np.diag(gold["d2_mass_E_iso_00"]) @ Gr
+    assert np.abs(A.toarray() - Ar).max() <= 1e-13 * np.abs(Ar).max()
+    B = (m.face_divergence @ m.get_face_inner_product(sig, invert_matrix=True) @ m.face_divergence.T).tocsr()
+    Br = Dr @ np.diag(gold["d2_mass_F_iso_01"]) @ Dr.T
+    assert np.abs(B.toarray() - Br).max() <= 1e-13 * np.abs(Br).max()
+
+
 def test_errors_keep_the_reference_behaviour():
     with pytest.raises(NotImplementedError, match="Edge Curl"):
         dz.TensorMesh([5]).edge_curl
