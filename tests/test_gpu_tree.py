@@ -238,6 +238,23 @@ def test_tree_node_interpolation(gold, tag):
         assert_same_matrix(Q.tocsr(), ref)
 
 
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_tree_tensor_model_derivative(gold, tag):
+    g2 = load_golden("tree_n2_small.npz")
+    m = _mesh_from_fixture(gold, tag, "state")
+    rng = np.random.default_rng(18)
+    sig6 = gold[f"{tag}_sigma6"]
+    for get, key, v in ((m.get_face_inner_product_deriv, "dMf_tensor", gold[f"{tag}_vF"]),
+                        (m.get_edge_inner_product_deriv, "dMe_tensor", gold[f"{tag}_vE"])):
+        ref = golden_matrix(g2, f"{tag}_{key}")
+        op = get(sig6)(v)
+        x, y = rng.standard_normal(ref.shape[1]), rng.standard_normal(ref.shape[0])
+        assert_close_vec(op @ x, ref @ x)
+        assert_close_vec(op.T @ y, ref.T @ y)
+    with pytest.raises(NotImplementedError):
+        m.get_face_inner_product_deriv(sig6, invert_model=True)
+
+
 @pytest.mark.parametrize("loc", ["Ex", "Fy", "CC"])
 def test_tree_edge_face_cell_interpolation(loc):
     """Edge / face / cell-centre interpolation (tree_interp.py) applied on the GPU against the reference's matrix
@@ -262,20 +279,3 @@ def test_tree_edge_face_cell_interpolation(loc):
     x, y = rng.standard_normal(ref.shape[1]), rng.standard_normal(ref.shape[0])
     assert_close_vec(Q @ x, ref @ x)
     assert_close_vec(Q.T @ y, ref.T @ y)
-
-
-@pytest.mark.parametrize("tag", ["a", "b"])
-def test_tree_tensor_model_derivative(gold, tag):
-    g2 = load_golden("tree_n2_small.npz")
-    m = _mesh_from_fixture(gold, tag, "state")
-    rng = np.random.default_rng(18)
-    sig6 = gold[f"{tag}_sigma6"]
-    for get, key, v in ((m.get_face_inner_product_deriv, "dMf_tensor", gold[f"{tag}_vF"]),
-                        (m.get_edge_inner_product_deriv, "dMe_tensor", gold[f"{tag}_vE"])):
-        ref = golden_matrix(g2, f"{tag}_{key}")
-        op = get(sig6)(v)
-        x, y = rng.standard_normal(ref.shape[1]), rng.standard_normal(ref.shape[0])
-        assert_close_vec(op @ x, ref @ x)
-        assert_close_vec(op.T @ y, ref.T @ y)
-    with pytest.raises(NotImplementedError):
-        m.get_face_inner_product_deriv(sig6, invert_model=True)
