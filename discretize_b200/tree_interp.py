@@ -36,8 +36,9 @@ class _Neighbours:
         keys = key3(topo.centers[:, 0], topo.centers[:, 1], topo.centers[:, 2])
         self.order = np.argsort(keys, kind="stable")
         self.keys = keys[self.order]
+        self.table = None
 
-    def step(self, cells, axes, sign):
+    def _lookup(self, cells, axes, sign):
         """cells: (n,) leaf indices; axes: int or (n,) ints; sign: -1 / +1."""
         t = self.t
         axes = np.broadcast_to(np.asarray(axes, dtype=np.int64), cells.shape)
@@ -51,6 +52,14 @@ class _Neighbours:
         nb = self.order[pos]
         ok = inside & (self.keys[pos] == k) & (t.half[nb] == t.half[cells])
         return np.where(ok, nb, -1)
+
+    def step(self, cells, axes, sign):
+        """Neighbour of each cell along its axis (int or per-cell array) on side ``sign``: a table built once per mesh."""
+        if self.table is None:
+            everyone = np.arange(self.t.n_cells)
+            self.table = np.stack([self._lookup(everyone, a, s) for a in range(3) for s in (-1, 1)], axis=1)
+        axes = np.broadcast_to(np.asarray(axes, dtype=np.int64), cells.shape)
+        return self.table[cells, 2 * axes + (1 if sign > 0 else 0)]
 
 
 def _clip01(w):
