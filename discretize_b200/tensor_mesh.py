@@ -1254,3 +1254,13 @@ class TensorMesh(_MeshPersistence):
 
     def __repr__(self):
         return f"<discretize_b200.TensorMesh {'x'.join(str(n) for n in self.shape_cells)} cells>"
+
+    def __str__(self):
+        """One line per axis: cells, extent, smallest / largest width, largest ratio between neighbouring widths."""
+        lines = [f"TensorMesh: {self.n_cells:,} cells ({' x '.join(str(n) for n in self.shape_cells)})",
+                 f"  {'axis':<5}{'cells':>8}{'from':>14}{'to':>14}{'h min':>12}{'h max':>12}{'max ratio':>11}"]
+        for a, name in enumerate("xyz"[:self.dim]):
+            x, h = self._nodes_1d(a), self._h[a]
+            ratio = 1.0 if h.size < 2 else float(np.max(np.r_[h[:-1] / h[1:], h[1:] / h[:-1]]))
+            lines.append(f"  {name:<5}{h.size:>8}{x[0]:>14.6g}{x[-1]:>14.6g}{h.min():>12.6g}{h.max():>12.6g}{ratio:>11.3f}")
+        return "\n".join(lines)

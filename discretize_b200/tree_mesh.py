@@ -1801,3 +1801,21 @@ class TreeMesh(_MeshPersistence):
     def __repr__(self):
         n = self._topo.n_cells if self._finalized else self._tree.n_leaves
         return f"<discretize_b200.TreeMesh {n} cells, max_level {self.max_level}>"
+
+    def __str__(self):
+        """Cells per level, extent and cell widths per axis; usable before ``finalize`` (counts from the leaf list)."""
+        kind = "OcTree" if self.dim == 3 else "QuadTree"
+        lo, lvl = self._tree.leaves()
+        state = "" if self._finalized else ", not finalized"
+        fill = 100.0 * lvl.size / float(np.prod(self.shape_cells))
+        lines = [f"TreeMesh ({kind}): {lvl.size:,} cells, {fill:.2f}% of the {' x '.join(str(n) for n in self.shape_cells)} "
+                 f"base grid{state}", "  level   cells"]
+        for level, count in zip(*np.unique(lvl, return_counts=True)):
+            lines.append(f"  {int(level):>5}{int(count):>8,}")
+        lines.append(f"  {'axis':<5}{'from':>14}{'to':>14}{'h min':>12}{'h max':>12}")
+        w = self._tree.width(lvl)
+        for a, name in enumerate("xyz"[:self.dim]):
+            x = self._xs[a]
+            h = x[2 * (lo[:, a] + w)] - x[2 * lo[:, a]]
+            lines.append(f"  {name:<5}{x[0]:>14.6g}{x[-1]:>14.6g}{h.min():>12.6g}{h.max():>12.6g}")
+        return "\n".join(lines)
