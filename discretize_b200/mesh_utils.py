@@ -42,6 +42,44 @@ def ndgrid(*args, vector=True, order="F"):
     return tuple(grids)
 
 
+def random_model(shape, random_seed=None, anisotropy=None, its=100, bounds=None, seed=None):
+    """A smooth random model: uniform noise passed ``its`` times through a small averaging kernel (1-4-1 per axis by
+    default), rescaled to ``bounds`` (mesh_utils.py:21-114).  Same generator and kernel as the reference, so a seed gives
+    the same model."""
+    import scipy.ndimage as ndi
+
+    if bounds is None:
+        bounds = [0, 1]
+    if seed is not None:
+        warnings.warn("Deprecated in version 0.11.0. The `seed` keyword argument has been renamed to `random_seed` for "
+                      "consistency across the package. Please update your code to use the new keyword argument.",
+                      FutureWarning, stacklevel=2)
+        random_seed = seed
+    rng = np.random.default_rng(random_seed)
+    if random_seed is None:
+        print("Using a seed of: ", rng.bit_generator.seed_seq)
+    if isinstance(shape, (int, np.integer)):
+        shape = (shape,)
+    model = rng.random(shape)
+    if anisotropy is None:
+        if len(shape) == 1:
+            kernel = np.array([1, 10.0, 1], dtype=float)
+        elif len(shape) == 2:
+            kernel = np.array([[1, 7, 1], [2, 10, 2], [1, 7, 1]], dtype=float)
+        else:
+            k = np.array([1.0, 4.0, 1.0])
+            kernel = np.kron(np.kron(k.reshape(1, 3), k.reshape(3, 1)), k.reshape(1, 3)).reshape((3, 3, 3))
+    else:
+        if len(anisotropy.shape) != len(shape):
+            raise ValueError("Anisotropy must be the same shape.")
+        kernel = np.array(anisotropy, dtype=float)
+    kernel = kernel / kernel.sum()
+    for _ in range(its):
+        model = ndi.convolve(model, kernel)
+    model = (model - model.min()) / (model.max() - model.min())
+    return model * (bounds[1] - bounds[0]) + bounds[0]
+
+
 def closest_points_index(mesh, pts, grid_loc="CC", **kwargs):
     if "gridLoc" in kwargs:
         raise TypeError("The gridLoc keyword argument has been removed, please use grid_loc. "

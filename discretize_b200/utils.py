@@ -273,7 +273,7 @@ def load_mesh(file_name):
 
 
 from .mesh_utils import (active_from_xyz, as_array_n_by_dim, closest_points_index, extract_core_mesh, is_scalar,  # noqa: E402,F401
-                         mesh_builder_xyz, mkvc, ndgrid, refine_tree_xyz, unpack_widths)
+                         mesh_builder_xyz, mkvc, ndgrid, random_model, refine_tree_xyz, unpack_widths)
 from .matrix_utils import (Identity, TensorType, Zero, av, av_extrap, cart2cyl, cartesian_to_cylindrical, cross2d,  # noqa: E402,F401
                            cyl2cart, cylindrical_to_cartesian, ddx, get_subarray, ind2sub, interpolation_matrix,
                            inverse_2x2_block_diagonal, inverse_3x3_block_diagonal, inverse_property_tensor, invert_blocks,

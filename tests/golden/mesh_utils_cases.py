@@ -46,4 +46,6 @@ def evaluate(u):
     out["mkvc"], out["mkvc2"] = u.mkvc(x), u.mkvc(x, 2)
     out["ndgrid"] = u.ndgrid(np.r_[1., 2.], np.r_[3., 4., 5.])
     out["unpack_widths"] = u.unpack_widths([(10.0, 3, -1.5), (10.0, 2), (10.0, 3, 1.5)])
+    for shape in (20, (12, 9), (6, 7, 5)):
+        out[f"random_model_{np.size(shape)}d"] = u.random_model(shape, random_seed=3, its=30, bounds=[1, 5])
     return out
