@@ -138,3 +138,36 @@ def test_operator_algebra_shapes_without_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(dz.DzbError, match="no CUDA device"):
             D @ np.ones(mesh.nF)
+
+
+def test_operator_algebra_values_without_gpu():
+    """Sums, products, scalings and transposes of host-assembled operators materialise to the scipy expression (the
+    same algebra layer composes the CUDA operators; here it runs on QuadTree matrices, which need no device)."""
+    import scipy.sparse as sp
+
+    m = dz.TreeMesh([16, 8])
+    m.refine_ball(np.array([[0.4, 0.5]]), [0.25], [-1])
+    assert m.n_hanging_edges > 0
+    rng = np.random.default_rng(0)
+    sig = rng.random(m.n_cells) + 0.5
+    D, G, C = m.face_divergence, m.nodal_gradient, m.edge_curl
+    Ds, Gs, Cs = (sp.csr_matrix(x.tocsr()) for x in (D, G, C))
+    Me, Mf = m.get_edge_inner_product(sig), m.get_face_inner_product(sig, invert_matrix=True)
+    Mes, Mfs = Me.tocsr(), Mf.tocsr()
+
+    def close(op, ref):
+        got = op.tocsr()
+        assert got.shape == ref.shape
+        assert abs(got - ref).max() <= 1e-13 * max(1.0, abs(ref).max())
+
+    close(G.T @ Me @ G, Gs.T @ Mes @ Gs)
+    close(D @ Mf @ D.T, Ds @ Mfs @ Ds.T)
+    close(2.5 * (C.T @ C) + Me, 2.5 * (Cs.T @ Cs) + Mes)
+    close((C.T @ C + Me).T, (Cs.T @ Cs + Mes).T)
+    close(-(D @ D.T) + 3.0 * sp.identity(m.n_cells, format="csr"), -(Ds @ Ds.T) + 3.0 * sp.identity(m.n_cells))
+    close(G.T.T, Gs)
+    close((G.T @ Me) @ G - 0.5 * (G.T @ Me @ G), 0.5 * (Gs.T @ Mes @ Gs))
+    close(Gs.T @ Me @ G, Gs.T @ Mes @ Gs)                      # a scipy matrix on the left joins the algebra
+    with pytest.raises(ValueError):
+        D @ D                                                  # (nC x nF) @ (nC x nF): shapes do not chain
+    assert (G.T @ Me @ G).shape == (m.n_nodes, m.n_nodes)
