@@ -111,3 +111,53 @@ def test_robin_pieces_reduce_to_neumann_and_scale_with_alpha():
         total = -np.asarray(B1.tocsr().diagonal()).sum() * 2.0
         ext = [np.sum(x) for x in mesh.h]
         assert abs(total - 2 * (ext[0] * ext[1] + ext[1] * ext[2] + ext[0] * ext[2])) <= 1e-12 * total
+
+
+KNOWN_2D = {1: 144877.0 / 360, 2: 189959.0 / 120, 3: 781427.0 / 360}      # tests/base/test_tensor_innerproduct.py:424-430
+
+
+def _mesh_2d(kind, n):
+    if kind == "tensor":
+        return dz.TensorMesh([n, n])
+    m = dz.TreeMesh([n, n])
+    if kind == "quadtree_uniform":
+        m.refine(-1)
+    else:                      # finest level in a band, one level coarser elsewhere: hanging edges along the interface
+        m.refine(lambda cell: m.max_level if abs(cell.center[1] - 0.5) < 0.2 else m.max_level - 1)
+    return m
+
+
+@pytest.mark.parametrize("kind", ["tensor", "quadtree_uniform", "quadtree_hanging"])
+@pytest.mark.parametrize("location", ["edges", "faces"])
+@pytest.mark.parametrize("sigma_test", [1, 2, 3])
+@pytest.mark.parametrize("invert_model", [False, True])
+def test_known_2d_inner_product_integrals(kind, location, sigma_test, invert_model):
+    """The reference's own known-answer test in 2-D (TestInnerProducts2D): u^T M(sigma) u converges at second order to
+    the sympy-derived integral over the unit square, for isotropic, anisotropic and full-tensor sigma, on a TensorMesh
+    and on QuadTrees with and without hanging edges."""
+    z = 5.0
+    ex = lambda x, y: x ** 2 + y * z                      # noqa: E731
+    ey = lambda x, y: (z ** 2) * x + y * z                # noqa: E731
+    s1 = lambda x, y: x * y + 1                           # noqa: E731
+    s2 = lambda x, y: x * z + 2                           # noqa: E731
+    s3 = lambda x, y: 3 + z * y                           # noqa: E731
+    errs = []
+    for n in (8, 16, 32):
+        m = _mesh_2d(kind, n)
+        cc = m.cell_centers
+        cols = [f(cc[:, 0], cc[:, 1]) for f in (s1, s2, s3)[:sigma_test]]
+        sigma = np.c_[tuple(cols)] if sigma_test < 3 else np.r_[tuple(cols)]
+        vec = lambda g: np.c_[ex(g[:, 0], g[:, 1]), ey(g[:, 0], g[:, 1])]      # noqa: E731
+        if location == "edges":
+            u = m.project_edge_vector(np.vstack((vec(m.edges_x), vec(m.edges_y))))
+            get = m.get_edge_inner_product
+        else:
+            u = m.project_face_vector(np.vstack((vec(m.faces_x), vec(m.faces_y))))
+            get = m.get_face_inner_product
+        if invert_model:
+            A = get(dz.utils.inverse_property_tensor(m, sigma), invert_model=True)
+        else:
+            A = get(sigma)
+        errs.append(abs(u @ (A.tocsr() @ u) - KNOWN_2D[sigma_test]))
+    orders = np.log2(np.array(errs[:-1]) / np.array(errs[1:]))
+    assert orders.min() > 0.8 * 2, (errs, orders)          # the reference's OrderTest tolerance (0.85) on order 2
