@@ -161,3 +161,25 @@ def test_known_2d_inner_product_integrals(kind, location, sigma_test, invert_mod
         errs.append(abs(u @ (A.tocsr() @ u) - KNOWN_2D[sigma_test]))
     orders = np.log2(np.array(errs[:-1]) / np.array(errs[1:]))
     assert orders.min() > 0.8 * 2, (errs, orders)          # the reference's OrderTest tolerance (0.85) on order 2
+
+
+@pytest.mark.parametrize("kind,expected", [("tensor", 2.0), ("quadtree_uniform", 2.0), ("quadtree_hanging", 1.0)])
+def test_2d_operator_order_of_accuracy(kind, expected):
+    """DIV, GRAD and CURL against analytic fields in the max norm (tests/base/test_operators.py:45-100,
+    tests/tree/test_tree_operators.py:110-292): second order on uniform cells, first order across hanging interfaces."""
+    tau = 2 * np.pi
+    err = {"div": [], "grad": [], "curl": []}
+    for n in (16, 32, 64):
+        m = _mesh_2d(kind, n)
+        fx, fy, ex_, ey_, cc, nd = m.faces_x, m.faces_y, m.edges_x, m.edges_y, m.cell_centers, m.nodes
+        D, G, C = (getattr(m, name).tocsr() for name in ("face_divergence", "nodal_gradient", "edge_curl"))
+        u = np.r_[np.sin(tau * fx[:, 0]), np.sin(tau * fy[:, 1])]
+        err["div"].append(np.abs(D @ u - tau * (np.cos(tau * cc[:, 0]) + np.cos(tau * cc[:, 1]))).max())
+        phi = np.cos(tau * nd[:, 0]) * np.sin(tau * nd[:, 1])
+        want = np.r_[-tau * np.sin(tau * ex_[:, 0]) * np.sin(tau * ex_[:, 1]), tau * np.cos(tau * ey_[:, 0]) * np.cos(tau * ey_[:, 1])]
+        err["grad"].append(np.abs(G @ phi - want).max())
+        e = np.r_[np.cos(tau * ex_[:, 1]), np.sin(tau * ey_[:, 0])]               # e = (cos 2 pi y, sin 2 pi x)
+        err["curl"].append(np.abs(C @ e - tau * (np.cos(tau * cc[:, 0]) + np.sin(tau * cc[:, 1]))).max())
+    for name, e in err.items():
+        orders = np.log2(np.array(e[:-1]) / np.array(e[1:]))
+        assert orders.min() > 0.85 * expected, (name, e, orders)
