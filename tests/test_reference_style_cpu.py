@@ -123,7 +123,7 @@ def _mesh_2d(kind, n):
     if kind == "quadtree_uniform":
         m.refine(-1)
     else:                      # finest level in a band, one level coarser elsewhere: hanging edges along the interface
-        m.refine(lambda cell: m.max_level if abs(cell.center[1] - 0.5) < 0.2 else m.max_level - 1)
+        m.refine(lambda cell: m.max_level if abs(cell.center[1] - 0.5) < 0.25 else m.max_level - 1)
     return m
 
 
@@ -180,6 +180,35 @@ def test_2d_operator_order_of_accuracy(kind, expected):
         err["grad"].append(np.abs(G @ phi - want).max())
         e = np.r_[np.cos(tau * ex_[:, 1]), np.sin(tau * ey_[:, 0])]               # e = (cos 2 pi y, sin 2 pi x)
         err["curl"].append(np.abs(C @ e - tau * (np.cos(tau * cc[:, 0]) + np.sin(tau * cc[:, 1]))).max())
+    for name, e in err.items():
+        orders = np.log2(np.array(e[:-1]) / np.array(e[1:]))
+        assert orders.min() > 0.85 * expected, (name, e, orders)
+
+
+@pytest.mark.parametrize("hanging,expected", [(False, 2.0), (True, 1.0)])
+def test_octree_operator_order_of_accuracy(hanging, expected):
+    """DIV, CURL and GRAD of the OcTree host matrices against analytic fields in the max norm
+    (tests/tree/test_tree_operators.py:110-292)."""
+    tau = 2 * np.pi
+    err = {"div": [], "curl": [], "grad": []}
+    for n in ((16, 32, 64) if hanging else (8, 16, 32)):      # the interface error only settles to first order later
+        m = dz.TreeMesh([n, n, n])
+        if hanging:
+            m.refine(lambda cc: np.where(np.abs(cc[:, 2] - 0.5) < 0.25, m.max_level, m.max_level - 1), vectorized=True)
+        else:
+            m.refine(-1)
+        D, C, G = (m._host_matrix(k) for k in ("face_divergence", "edge_curl", "nodal_gradient"))
+        fx, fy, fz, cc, nd = m.faces_x, m.faces_y, m.faces_z, m.cell_centers, m.nodes
+        ex_, ey_, ez_ = m.edges_x, m.edges_y, m.edges_z
+        u = np.r_[np.sin(tau * fx[:, 0]), np.sin(tau * fy[:, 1]), np.sin(tau * fz[:, 2])]
+        err["div"].append(np.abs(D @ u - tau * np.cos(tau * cc).sum(axis=1)).max())
+        # e = (cos 2 pi y, cos 2 pi z, cos 2 pi x)  ->  curl e = 2 pi (sin 2 pi z, sin 2 pi x, sin 2 pi y)
+        e = np.r_[np.cos(tau * ex_[:, 1]), np.cos(tau * ey_[:, 2]), np.cos(tau * ez_[:, 0])]
+        want = tau * np.r_[np.sin(tau * fx[:, 2]), np.sin(tau * fy[:, 0]), np.sin(tau * fz[:, 1])]
+        err["curl"].append(np.abs(C @ e - want).max())
+        phi = np.cos(tau * nd[:, 0]) * np.cos(tau * nd[:, 1]) * np.cos(tau * nd[:, 2])
+        g = lambda p, a: -tau * np.prod([np.sin(tau * p[:, b]) if b == a else np.cos(tau * p[:, b]) for b in range(3)], axis=0)  # noqa: E731
+        err["grad"].append(np.abs(G @ phi - np.r_[g(ex_, 0), g(ey_, 1), g(ez_, 2)]).max())
     for name, e in err.items():
         orders = np.log2(np.array(e[:-1]) / np.array(e[1:]))
         assert orders.min() > 0.85 * expected, (name, e, orders)
