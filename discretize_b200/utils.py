@@ -279,3 +279,28 @@ from .matrix_utils import (Identity, TensorType, Zero, av, av_extrap, cart2cyl, 
                            inverse_2x2_block_diagonal, inverse_3x3_block_diagonal, inverse_property_tensor, invert_blocks,
                            kron3, make_boundary_bool, make_property_tensor, rotate_points_from_normals,
                            rotation_matrix_from_normals, sdiag, sdinv, speye, spzeros, sub2ind)
+
+
+# camelCase names the reference has removed: calling them raises with the pointer to the new name
+# (utils/code_utils.py: deprecate_function(..., error=True))
+_REMOVED_FUNCTIONS = {
+    "isScalar": "is_scalar", "asArray_N_x_Dim": "as_array_n_by_dim", "sdInv": "sdinv", "getSubArray": "get_subarray",
+    "inv3X3BlockDiagonal": "inverse_3x3_block_diagonal", "inv2X2BlockDiagonal": "inverse_2x2_block_diagonal",
+    "makePropertyTensor": "make_property_tensor", "invPropertyTensor": "inverse_property_tensor",
+    "meshTensor": "unpack_widths", "closestPoints": "closest_points_index", "ExtractCoreMesh": "extract_core_mesh",
+    "interpmat": "interpolation_matrix", "rotationMatrixFromNormals": "rotation_matrix_from_normals",
+    "rotatePointsFromNormals": "rotate_points_from_normals",
+}
+
+
+def _removed_function(old, new):
+    def removed(*args, **kwargs):
+        raise NotImplementedError(f"{old} has been removed, please use {new}.")
+
+    removed.__name__ = old
+    return removed
+
+
+for _old, _new in _REMOVED_FUNCTIONS.items():
+    globals()[_old] = _removed_function(_old, _new)
+del _old, _new

@@ -30,3 +30,12 @@ def test_matrix_utils_match_reference_fixture():
             assert np.array_equal(got, ref), k
         elif ref.size:
             assert np.abs(got - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max()), (k, np.abs(got - ref).max())
+
+
+def test_removed_function_names_raise_with_a_pointer():
+    import pytest
+
+    with pytest.raises(NotImplementedError, match="sdInv has been removed, please use sdinv."):
+        dz.utils.sdInv(1)
+    with pytest.raises(NotImplementedError, match="meshTensor has been removed, please use unpack_widths."):
+        dz.utils.meshTensor([(1.0, 2)])
