@@ -279,6 +279,7 @@ from .matrix_utils import (Identity, TensorType, Zero, av, av_extrap, cart2cyl, 
                            inverse_2x2_block_diagonal, inverse_3x3_block_diagonal, inverse_property_tensor, invert_blocks,
                            kron3, make_boundary_bool, make_property_tensor, rotate_points_from_normals,
                            rotation_matrix_from_normals, sdiag, sdinv, speye, spzeros, sub2ind)
+from .curvilinear_utils import example_curvilinear_grid, face_info, index_cube, volume_tetrahedron  # noqa: E402,F401
 
 
 # camelCase names the reference has removed: calling them raises with the pointer to the new name
@@ -289,7 +290,8 @@ _REMOVED_FUNCTIONS = {
     "makePropertyTensor": "make_property_tensor", "invPropertyTensor": "inverse_property_tensor",
     "meshTensor": "unpack_widths", "closestPoints": "closest_points_index", "ExtractCoreMesh": "extract_core_mesh",
     "interpmat": "interpolation_matrix", "rotationMatrixFromNormals": "rotation_matrix_from_normals",
-    "rotatePointsFromNormals": "rotate_points_from_normals",
+    "rotatePointsFromNormals": "rotate_points_from_normals", "exampleLrmGrid": "example_curvilinear_grid",
+    "volTetra": "volume_tetrahedron", "indexCube": "index_cube", "faceInfo": "face_info",
 }
 
 
