@@ -107,7 +107,7 @@ def evaluate(u, lib):
     put("index_cube_bad", lambda: u.index_cube("Z", (3, 3)))
     put("curv_grid_bad", lambda: u.example_curvilinear_grid([3, 3], "torus"))
     xyz = rng.random((30, 3))
-    idx = [rng.integers(0, 30, 8) for _ in range(4)]
+    idx = list(np.array([rng.permutation(30)[:4] for _ in range(8)]).T)      # four distinct corners per face
     put("volume_tetrahedron", lambda: u.volume_tetrahedron(xyz, *idx))
     put("face_info_avg_normals", lambda: u.face_info(xyz, *idx)[0])
     put("face_info_avg_area", lambda: u.face_info(xyz, *idx)[1])
