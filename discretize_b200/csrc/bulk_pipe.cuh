@@ -53,4 +53,46 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                : "memory");
 }
 
+
+// non-blocking probe: issue early, test the predicate after independent work, fall back to mbar_wait
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// Exact staging of the global elements [lo, hi) of an array that occupies exactly [abeg, aend) (all four are
+// absolute element addresses = byte address / 8; hi is clamped to aend here).  A bulk copy needs 16-byte aligned
+// ends, so it covers the widest even-aligned range that stays INSIDE the array; the at most one element that
+// range misses at either end (only when the array itself starts / ends on an odd element address) is flagged for
+// a plain 8-byte load + shared store by the calling lane.  Nothing outside [abeg, aend) is ever read.
+struct RowCopy {
+  long long tlo;     // first element of the bulk copy (even)
+  unsigned bytes;    // size of the bulk copy (multiple of 16, may be 0)
+  bool head, tail;   // element lo / element hi-1 must be copied by hand
+  long long hi;      // clamped end
+};
+__device__ __forceinline__ RowCopy plan_row_copy(long long lo, long long hi, long long abeg, long long aend) {
+  RowCopy c;
+  hi = hi < aend ? hi : aend;
+  long long tlo = lo & ~1ll;
+  if (tlo < abeg) tlo += 2;
+  long long thi = (hi + 1) & ~1ll;
+  if (thi > aend) thi -= 2;
+  c.tlo = tlo;
+  c.bytes = thi > tlo ? (unsigned)((thi - tlo) << 3) : 0u;
+  c.head = (lo < tlo) && (lo < hi);
+  c.tail = hi > (thi > tlo ? thi : tlo);
+  c.hi = hi;
+  return c;
+}
+
 }  // namespace dzb

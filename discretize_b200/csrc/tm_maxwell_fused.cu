@@ -11,6 +11,7 @@
 // form and the cross-check for the marching variant.
 #include "tm_mass_common.cuh"
 #include "tm_maxwell_ring.cuh"
+#include "tm_maxwell_rows.cuh"
 #include "tm_rowkernels.cuh"
 
 namespace dzb {
@@ -52,24 +53,84 @@ __global__ void __launch_bounds__(BX *BY *BZ)
 
 using namespace dzb;
 
-static int g_mx_variant = 1;   // 0 = gather (one thread per edge), 1 = warp-specialised TMA ring
+static int g_mx_variant = 1;   // 0 = gather (one thread per edge), 1 = first TMA ring (2 rows / lane), 2 = row-per-warp ring
 static int g_mx_kchunk = 64;
+static int g_m2_kchunk = 0;    // 0 = automatic (~128 planes per block)
+static int g_m2_dbg = 0;   // experiments only: 1 = consumers skip the arithmetic, 2 = producers skip the copies
+extern "C" void dzb_tune_maxwell_debug(int d) { g_m2_dbg = d; }
+static int g_m2_xs = 2, g_m2_r = 4, g_m2_ns = 4, g_m2_np = 2;
 extern "C" void dzb_tune_maxwell(int variant, int kchunk) {
   g_mx_variant = variant;
   if (kchunk > 0) g_mx_kchunk = kchunk > MX_MAXCHUNK ? MX_MAXCHUNK : kchunk;
+  g_m2_kchunk = kchunk > 0 ? (kchunk > M2_MAXCHUNK ? M2_MAXCHUNK : kchunk) : 0;
+}
+// block shape of variant 2: strips x rows, one of (1,8) (2,4) (4,2) (4,4); producer warps 1 or 2
+extern "C" void dzb_tune_maxwell_rows(int xs, int r, int nslot, int nprod) {
+  g_m2_xs = xs;
+  g_m2_r = r;
+  g_m2_ns = nslot;
+  g_m2_np = nprod;
+}
+
+template <int XS, int R, int PARX, int NSLOT, int NPROD, int MINB>
+static int launch_m2_t(const TM &m, const double *mui, const double *sigma, const double *e, double *y, int k_begin,
+                       int k_end, cudaStream_t s) {
+  typedef Mx2<XS, R, PARX, NSLOT, NPROD> G;
+  // the attribute is per device; setting it is cheap, so no process-wide "done" flag
+  if (cudaFuncSetAttribute(k_maxwell_rows<XS, R, PARX, NSLOT, NPROD, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)G::SMEM) != cudaSuccess)
+    return -1;
+  const int nNx = (int)m.nx + 1, nNy = (int)m.ny + 1, planes = k_end - k_begin;
+  const int xblocks = (nNx + XS * M2_XOUT - 1) / (XS * M2_XOUT), yblocks = (nNy + R - 1) / R;
+  // ~128 planes per block amortise the two warm-up stages; short plane ranges (z-slabs on many GPUs, small meshes) are
+  // cut finer until the grid has about four waves of blocks
+  int nchunks = g_m2_kchunk > 0 ? (planes + g_m2_kchunk - 1) / g_m2_kchunk : (planes + 143) / 144;
+  if (g_m2_kchunk == 0) {
+    const long long nxy = (long long)xblocks * yblocks;
+    const long long want = (4ll * 148 * MINB + nxy - 1) / nxy;
+    if (nchunks < want) nchunks = (int)(want < (planes + 7) / 8 ? want : (planes + 7) / 8);
+    if (nchunks < 1) nchunks = 1;
+  }
+  const int kchunk = (planes + nchunks - 1) / nchunks;
+  dim3 grid((unsigned)xblocks, (unsigned)yblocks, (unsigned)((planes + kchunk - 1) / kchunk));
+  k_maxwell_rows<XS, R, PARX, NSLOT, NPROD, MINB><<<grid, dim3(G::NT), G::SMEM, s>>>(m, mui, sigma, e, y, kchunk, k_begin, k_end, g_m2_dbg);
+  return 0;
+}
+
+#define M2_LAUNCH(XS, R, NS, NP, MINB)                                                         \
+  return parx ? launch_m2_t<XS, R, 1, NS, NP, MINB>(m, mui, sigma, e, y, k_begin, k_end, s)    \
+              : launch_m2_t<XS, R, 0, NS, NP, MINB>(m, mui, sigma, e, y, k_begin, k_end, s)
+
+static int launch_m2(const TM &m, const double *mui, const double *sigma, const double *e, double *y, int k_begin,
+                     int k_end, cudaStream_t s) {
+  const int parx = (int)(m.nx & 1);
+  const int key = g_m2_xs * 1000 + g_m2_r * 100 + g_m2_ns * 10 + g_m2_np;
+  switch (key) {
+    case 2441: M2_LAUNCH(2, 4, 4, 1, 2);
+    case 2442: M2_LAUNCH(2, 4, 4, 2, 2);
+    case 2444: M2_LAUNCH(2, 4, 4, 4, 2);
+    case 2461: M2_LAUNCH(2, 4, 6, 1, 2);
+    case 2462: M2_LAUNCH(2, 4, 6, 2, 2);
+    case 4241: M2_LAUNCH(4, 2, 4, 1, 2);
+    case 4242: M2_LAUNCH(4, 2, 4, 2, 2);
+    case 4244: M2_LAUNCH(4, 2, 4, 4, 2);
+    case 4442: M2_LAUNCH(4, 4, 4, 2, 1);
+    case 4444: M2_LAUNCH(4, 4, 4, 4, 1);
+    case 4464: M2_LAUNCH(4, 4, 6, 4, 1);
+    case 1842: M2_LAUNCH(1, 8, 4, 2, 2);
+    default: break;
+  }
+  M2_LAUNCH(2, 4, 4, 2, 2);
 }
 
 template <int NWC, int PARX, int NSLOT>
 static int launch_mx_ring_t(const TM &m, const double *mui, const double *sigma, const double *e, double *y, int xblocks,
                             int nwc, int k_begin, int k_end, cudaStream_t s) {
   typedef MxRing<2, NWC, PARX, NSLOT> G;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(k_maxwell_ring<2, NWC, PARX, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)G::SMEM) != cudaSuccess)
-      return -1;
-    attr_done = true;
-  }
+  // the attribute is per device; setting it is cheap, so no process-wide "done" flag
+  if (cudaFuncSetAttribute(k_maxwell_ring<2, NWC, PARX, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)G::SMEM) != cudaSuccess)
+    return -1;
   const int nNy = (int)m.ny + 1;
   // 64 planes per block is best at 512^3, 128 at 1024^3 (profiles/r1b_k9_sweep_1024.log): with four times as many
   // (x, y) blocks the longer march amortises the ring fill without starving the grid
@@ -116,7 +177,11 @@ extern "C" int dzb_tm_maxwell_range(const DzbTensorMesh *mm, const double *mui, 
   if (k_begin == k_end) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   const bool ring_ok = m.ny >= 1 && (m.nx + 1) * (m.ny + 1) < ((i64)1 << 31);
-  if (g_mx_variant == 1 && ring_ok) {
+  if (g_mx_variant == 2 && ring_ok) {
+    if (launch_m2(m, mui, sigma, e, y, (int)k_begin, (int)k_end, s) == 0) return check_launch("dzb_tm_maxwell");
+    cudaGetLastError();
+  }
+  if (g_mx_variant >= 1 && ring_ok) {
     if (launch_mx_ring(m, mui, sigma, e, y, (int)k_begin, (int)k_end, s) == 0) return check_launch("dzb_tm_maxwell");
     cudaGetLastError();
   }

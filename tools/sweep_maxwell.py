@@ -1,4 +1,8 @@
-"""Tuning sweep for the fused Maxwell kernel (K9): variant / warps per block / z-chunk."""
+"""Tuning sweep for the fused Maxwell kernel (K9): variant / block shape / z-chunk.
+
+variant 1 = first TMA ring (two rows + a recomputed halo row per lane), variant 2 = row-per-warp ring with mailboxes.
+  python tools/sweep_maxwell.py [n] [v1|v2|all]
+"""
 import ctypes
 import os
 import sys
@@ -10,6 +14,8 @@ import discretize_b200 as dz
 from discretize_b200._lib import load
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+which = sys.argv[2] if len(sys.argv) > 2 else "all"
+dbg = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 mesh = dz.TensorMesh([n, n, n])
 dev = torch.device("cuda")
 e = torch.randn(mesh.nE, dtype=torch.float64, device=dev)
@@ -23,17 +29,30 @@ lib.dzb_tune_maxwell.argtypes = [ctypes.c_int, ctypes.c_int]
 lib.dzb_tune_maxwell.restype = None
 lib.dzb_tune_maxwell_warps.argtypes = [ctypes.c_int]
 lib.dzb_tune_maxwell_warps.restype = None
+lib.dzb_tune_maxwell_rows.argtypes = [ctypes.c_int] * 4
+lib.dzb_tune_maxwell_rows.restype = None
+lib.dzb_tune_maxwell_debug.argtypes = [ctypes.c_int]
+lib.dzb_tune_maxwell_debug.restype = None
+lib.dzb_tune_maxwell_debug(dbg)
 alg = 8.0 * (2 * mesh.nE + 2 * mesh.nC)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ref = None
-cases = ([(0, 0, 64)] if n <= 512 else []) + [(1, w, kc) for w in ((9, 12, 18) if n <= 512 else (6, 9)) for kc in ((32, 64, 128) if n <= 512 else (32, 64, 128, 256))]
-for variant, w, kc in cases:
+cases = []
+if which in ("v1", "all"):
+    cases += [(1, 9, 0, 128 if n > 512 else 64)]
+if which in ("v2", "all"):
+    shapes = ((2, 4, 4, 1), (2, 4, 4, 2), (2, 4, 4, 4), (2, 4, 6, 1), (2, 4, 6, 2), (4, 2, 4, 1), (4, 2, 4, 2), (4, 2, 4, 4),
+              (4, 4, 4, 2), (4, 4, 4, 4), (4, 4, 6, 4), (1, 8, 4, 2))
+    cases += [(2, sh, 0, 0) for sh in shapes]
+for variant, a, b, kc in cases:
     lib.dzb_tune_maxwell(variant, kc)
-    if w:
-        lib.dzb_tune_maxwell_warps(w)
+    if variant == 1:
+        lib.dzb_tune_maxwell_warps(a)
+    else:
+        lib.dzb_tune_maxwell_rows(*a)
     for _ in range(2):
         A.apply_device(e, out=out)
-    reps = 3 if variant == 0 else 10
+    reps = 10
     e0.record()
     for _ in range(reps):
         A.apply_device(e, out=out)
@@ -42,5 +61,5 @@ for variant, w, kc in cases:
     if ref is None:
         ref = out.clone()
     err = float((out - ref).abs().max() / ref.abs().max())
-    print(f"variant={variant} warps={w:2d} kchunk={kc:3d} err={err:.1e} {ms:.3f} ms {mesh.nE/ms/1e6:.1f} Gdof/s {alg/ms/1e6:.0f} GB/s frac {alg/ms/1e6/6541.1:.3f}", flush=True)
-lib.dzb_tune_maxwell(1, 64); lib.dzb_tune_maxwell_warps(12)
+    print(f"variant={variant} shape={a} kchunk={kc:3d} err={err:.1e} {ms:.3f} ms {mesh.nE/ms/1e6:.1f} Gdof/s {alg/ms/1e6:.0f} GB/s frac {alg/ms/1e6/6541.1:.3f}", flush=True)
+lib.dzb_tune_maxwell(1, 64); lib.dzb_tune_maxwell_rows(2, 4, 4, 2)
