@@ -12,6 +12,8 @@
 #include "tm_mass_common.cuh"
 #include "tm_maxwell_ring.cuh"
 #include "tm_maxwell_rows.cuh"
+#include "tm_maxwell_tmap.cuh"
+#include <cudaTypedefs.h>
 #include "tm_rowkernels.cuh"
 
 namespace dzb {
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(BX *BY *BZ)
 
 using namespace dzb;
 
-static int g_mx_variant = 1;   // 0 = gather (one thread per edge), 1 = first TMA ring (2 rows / lane), 2 = row-per-warp ring
+static int g_mx_variant = 3;   // 0 = gather (one thread per edge), 1 = first TMA ring (2 rows / lane), 2 = row-per-warp ring (bulk copies), 3 = same with tensor maps
 static int g_mx_kchunk = 64;
 static int g_m2_kchunk = 0;    // 0 = automatic (~128 planes per block)
 static int g_m2_dbg = 0;   // experiments only: 1 = consumers skip the arithmetic, 2 = producers skip the copies
@@ -123,6 +125,129 @@ static int launch_m2(const TM &m, const double *mui, const double *sigma, const 
   M2_LAUNCH(2, 4, 4, 2, 2);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// variant 3: the same ring fed by tensor-map TMA (tm_maxwell_tmap.cuh)
+// ---------------------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled tmap_encoder() {
+  static PFN_cuTensorMapEncodeTiled fn = []() -> PFN_cuTensorMapEncodeTiled {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+  }();
+  return fn;
+}
+
+static int g_m3_xs = 2, g_m3_r = 8, g_m3_ns = 6;
+extern "C" void dzb_tune_maxwell_tmap(int xs, int r, int nslot) {
+  g_m3_xs = xs;
+  g_m3_r = r;
+  g_m3_ns = nslot;
+}
+
+// one (pointers, mesh, box shape) -> tensor maps entry per host thread: re-encoding costs a few microseconds per map
+struct M3Key {
+  const void *e, *mu, *sg;
+  i64 nx, ny, nz;
+  int w, r;
+  bool operator==(const M3Key &o) const {
+    return e == o.e && mu == o.mu && sg == o.sg && nx == o.nx && ny == o.ny && nz == o.nz && w == o.w && r == o.r;
+  }
+};
+
+// returns 0 and fills `maps`, or -1 if this mesh / these pointers cannot be described (caller falls back to bulk copies)
+template <typename G>
+static int m3_encode(const TM &m, const double *mui, const double *sigma, const double *e, M3Maps &maps) {
+  static thread_local M3Key last_key = {};
+  static thread_local M3Maps last_maps;
+  static thread_local bool have = false;
+  const M3Key key{e, mui, sigma, m.nx, m.ny, m.nz, G::W, G::RN};
+  if (have && key == last_key) {
+    maps = last_maps;
+    return 0;
+  }
+  PFN_cuTensorMapEncodeTiled enc = tmap_encoder();
+  if (!enc) return -1;
+  const i64 nx = m.nx, ny = m.ny, nz = m.nz, nNx = nx + 1, nNy = ny + 1, nNz = nz + 1;
+  const i64 nEx = nx * nNy * nNz, nEy = nNx * ny * nNz;
+  const double *base[5] = {e, e + nEx, e + nEx + nEy, mui, sigma};
+  const i64 pitch[5] = {nx, nNx, nNx, nx, nx};
+  const i64 rows[5] = {nNy * nNz, ny * nNz, nNy * nz, ny * nz, ny * nz};
+  for (int a = 0; a < 5; ++a) {
+    if (reinterpret_cast<uintptr_t>(base[a]) & 15) return -1;
+    if (rows[a] >= ((i64)1 << 31) || 2 * pitch[a] >= ((i64)1 << 31)) return -1;
+    const bool odd = (pitch[a] & 1) != 0;
+    if (odd && (rows[a] & 1)) return -1;     // the last super-row would reach past the array
+    cuuint64_t gdim[2] = {(cuuint64_t)(odd ? 2 * pitch[a] : pitch[a]), (cuuint64_t)(odd ? rows[a] / 2 : rows[a])};
+    cuuint64_t gstr[1] = {(cuuint64_t)(odd ? 16 * pitch[a] : 8 * pitch[a])};
+    cuuint32_t box[2] = {(cuuint32_t)G::W, (cuuint32_t)G::hbox(a)};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&maps.m[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base[a]), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return -1;
+  }
+  last_key = key;
+  last_maps = maps;
+  have = true;
+  return 0;
+}
+
+template <int XS, int R, int PARX, int NSLOT, int MINB>
+static int launch_m3_t(const TM &m, const double *mui, const double *sigma, const double *e, double *y, int k_begin,
+                       int k_end, cudaStream_t s) {
+  typedef Mx3<XS, R, PARX, NSLOT> G;
+  M3Maps maps;
+  if (m3_encode<G>(m, mui, sigma, e, maps) != 0) return -1;
+  if (cudaFuncSetAttribute(k_maxwell_tmap<XS, R, PARX, NSLOT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)G::SMEM) != cudaSuccess)
+    return -1;
+  const int nNx = (int)m.nx + 1, nNy = (int)m.ny + 1, planes = k_end - k_begin;
+  const int xblocks = (nNx + XS * M3_XOUT - 1) / (XS * M3_XOUT), yblocks = (nNy + R - 1) / R;
+  int nchunks = g_m2_kchunk > 0 ? (planes + g_m2_kchunk - 1) / g_m2_kchunk : (planes + 143) / 144;
+  if (g_m2_kchunk == 0) {
+    const long long nxy = (long long)xblocks * yblocks;
+    const long long want = (4ll * 148 * MINB + nxy - 1) / nxy;
+    if (nchunks < want) nchunks = (int)(want < (planes + 7) / 8 ? want : (planes + 7) / 8);
+    if (nchunks < 1) nchunks = 1;
+  }
+  const int kchunk = (planes + nchunks - 1) / nchunks;
+  dim3 grid((unsigned)xblocks, (unsigned)yblocks, (unsigned)((planes + kchunk - 1) / kchunk));
+  k_maxwell_tmap<XS, R, PARX, NSLOT, MINB><<<grid, dim3(G::NT), G::SMEM, s>>>(m, maps, y, kchunk, k_begin, k_end);
+  return 0;
+}
+
+#define M3_LAUNCH(XS, R, NS, MINB)                                                        \
+  return parx ? launch_m3_t<XS, R, 1, NS, MINB>(m, mui, sigma, e, y, k_begin, k_end, s)   \
+              : launch_m3_t<XS, R, 0, NS, MINB>(m, mui, sigma, e, y, k_begin, k_end, s)
+
+static int launch_m3(const TM &m, const double *mui, const double *sigma, const double *e, double *y, int k_begin,
+                     int k_end, cudaStream_t s) {
+  const int parx = (int)(m.nx & 1);
+  switch (g_m3_xs * 100 + g_m3_r * 10 + g_m3_ns) {
+    case 144: M3_LAUNCH(1, 4, 4, 3);
+    case 146: M3_LAUNCH(1, 4, 6, 3);
+    case 154: M3_LAUNCH(1, 5, 4, 3);
+    case 156: M3_LAUNCH(1, 5, 6, 3);
+    case 164: M3_LAUNCH(1, 6, 4, 2);
+    case 166: M3_LAUNCH(1, 6, 6, 2);
+    case 168: M3_LAUNCH(1, 6, 8, 2);
+    case 184: M3_LAUNCH(1, 8, 4, 2);
+    case 186: M3_LAUNCH(1, 8, 6, 2);
+    case 244: M3_LAUNCH(2, 4, 4, 2);
+    case 246: M3_LAUNCH(2, 4, 6, 2);
+    case 264: M3_LAUNCH(2, 6, 4, 1);
+    case 266: M3_LAUNCH(2, 6, 6, 1);
+    case 284: M3_LAUNCH(2, 8, 4, 1);
+    case 286: M3_LAUNCH(2, 8, 6, 1);
+    case 444: M3_LAUNCH(4, 4, 4, 1);
+    default: break;
+  }
+  M3_LAUNCH(2, 8, 4, 1);
+}
+
 template <int NWC, int PARX, int NSLOT>
 static int launch_mx_ring_t(const TM &m, const double *mui, const double *sigma, const double *e, double *y, int xblocks,
                             int nwc, int k_begin, int k_end, cudaStream_t s) {
@@ -177,7 +302,11 @@ extern "C" int dzb_tm_maxwell_range(const DzbTensorMesh *mm, const double *mui, 
   if (k_begin == k_end) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   const bool ring_ok = m.ny >= 1 && (m.nx + 1) * (m.ny + 1) < ((i64)1 << 31);
-  if (g_mx_variant == 2 && ring_ok) {
+  if (g_mx_variant == 3 && ring_ok) {
+    if (launch_m3(m, mui, sigma, e, y, (int)k_begin, (int)k_end, s) == 0) return check_launch("dzb_tm_maxwell");
+    cudaGetLastError();
+  }
+  if (g_mx_variant >= 2 && ring_ok) {
     if (launch_m2(m, mui, sigma, e, y, (int)k_begin, (int)k_end, s) == 0) return check_launch("dzb_tm_maxwell");
     cudaGetLastError();
   }

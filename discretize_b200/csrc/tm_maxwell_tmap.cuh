@@ -1,0 +1,338 @@
+// K9 "tmap": y = C^T Mf(mui) C e + Me(sigma) e -- the row-per-warp ring of tm_maxwell_rows.cuh fed by tensor-map TMA.
+//
+// Why: with row-wise bulk copies (UBLKCP) a stage of the ring costs 17-47 copy instructions, each issued from uniform
+// registers by ONE warp at ~65 cycles apiece; measured at 1024^3 the copy pipeline alone (no arithmetic) then needs
+// 14.2 ms with one producer warp and the arithmetic alone 8.3-9.7 ms, and the two do not overlap (15.4 ms together).
+// A tensor map moves a whole (rows x columns) box with one instruction (SASS UTMALDG), needs no 16-byte aligned row
+// starts (only a 16-byte aligned base address and row pitch) and zero-fills everything outside the array.
+//
+// The reference's layouts have row pitches of nx (ex, mui, sigma) and nx+1 (ey, ez) doubles, so one of the two groups has
+// an odd pitch = a byte pitch that is not a multiple of 16.  Those arrays are described as matrices of SUPER-ROWS (two
+// consecutive rows, pitch 2(nx+1) doubles = a multiple of 16 bytes): the rows J0 .. J0+H-1 a stage needs are fetched as
+// two boxes, the even rows (x in [c, c+W)) and the odd rows (x in [P+c, P+c+W)); the producer steers them so that the
+// staged rows rr = 0, 2, 4, .. land in sub-tile 0 and rr = 1, 3, .. in sub-tile 1, each at box row rr>>1, whatever the
+// parity of J0 (derivation in DESIGN.md).  Every array is one 2-D matrix of
+// (rows per plane x planes) rows, because planes follow each other without padding.
+//
+// Used when all five base addresses are 16-byte aligned and every odd-pitch array has an even number of rows (true for
+// every even-sized mesh, e.g. all BASELINE configs); otherwise the launcher falls back to the bulk-copy ring.
+// The arithmetic, the mailboxes and the halo warps are those of tm_maxwell_rows.cuh (see there for the formulas).
+#pragma once
+#include <cuda.h>
+#include "bulk_pipe.cuh"
+#include "tm_common.cuh"
+
+namespace dzb {
+
+__device__ __forceinline__ void tmap_load_2d(void *dst_smem, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tmap_prefetch(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+constexpr int M3_XOUT = 31;       // output columns per strip: lanes 1..31 (lane 0 = left halo)
+constexpr int M3_MAXCHUNK = 160;  // max z-planes per block (size of the hz tables)
+
+// compile-time geometry: XS strips x R rows per block, PARX = nx & 1, NSLOT ring slots
+template <int XS, int R, int PARX, int NSLOT> struct Mx3 {
+  static constexpr int NCONS = XS * R, NHALO = XS, NWARPS = NCONS + NHALO + 1, NT = NWARPS * 32;
+  static constexpr int RN = R + 2, RC = R + 1;          // staged node rows j0-1 .. j0+R, cell rows j0-1 .. j0+R-1
+  // box width: the box starts at the even column <= Xb-1 (the TMA unit wants 16-byte aligned inner coordinates: an odd
+  // start raises an illegal-instruction fault, tools/tma_probe) and must reach column Xb+XS*31
+  static constexpr int W = (XS * M3_XOUT + 3 + 1) & ~1;
+  static constexpr int pad16(int n) { return (n + 15) & ~15; }          // boxes start on 128-byte boundaries
+  // array a: 0 ex (pitch nx, RN rows) 1 ey (nx+1, RC) 2 ez (nx+1, RN) 3 mui (nx, RC) 4 sigma (nx, RC)
+  static constexpr bool odd(int a) { return ((a == 1 || a == 2) ? (PARX + 1) & 1 : PARX) != 0; }
+  static constexpr int rows(int a) { return (a == 0 || a == 2) ? RN : RC; }
+  static constexpr int hbox(int a) { return odd(a) ? (rows(a) + 1) / 2 : rows(a); }   // box height
+  static constexpr int sub(int a) { return pad16(W * hbox(a)); }                        // one box in smem (doubles)
+  static constexpr int size(int a) { return odd(a) ? 2 * sub(a) : sub(a); }
+  // (no recursion: these are also called with unrolled-loop indices in device code)
+  static constexpr int off(int a) {
+    return (a > 0 ? size(0) : 0) + (a > 1 ? size(1) : 0) + (a > 2 ? size(2) : 0) + (a > 3 ? size(3) : 0);
+  }
+  static constexpr int STAGE = size(0) + size(1) + size(2) + size(3) + size(4);
+  static constexpr unsigned bytes(int a) { return (unsigned)(W * hbox(a) * 8 * (odd(a) ? 2 : 1)); }
+  static constexpr int XROWS = R;                       // mailbox rows: 0 = halo row j0-1, rr = row j0+rr-1
+  static constexpr int XCH = NSLOT * XROWS * XS * 64;   // doubles: [slot][rr][strip][G_FX | G_FZ][lane]
+  static constexpr int NBAR = 2 * NSLOT + NSLOT * XROWS * XS;
+  static constexpr size_t SMEM = (size_t)(NSLOT * STAGE + XCH) * 8 + (size_t)NBAR * 8 + 2 * (M3_MAXCHUNK + 2) * 8 + 128;
+};
+
+struct M3Maps {
+  CUtensorMap m[5];
+};
+
+template <int XS, int R, int PARX, int NSLOT, int MINB>
+__global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
+    k_maxwell_tmap(TM m, const __grid_constant__ M3Maps maps, double *__restrict__ y, int kchunk, int k_begin, int k_end) {
+  typedef Mx3<XS, R, PARX, NSLOT> G;
+  constexpr int S = NSLOT, W = G::W;
+  static_assert(S % 2 == 0, "the row-parity bookkeeping assumes an even ring depth");
+  // boxes must start on 128-byte boundaries.  (No pointer arithmetic through integers here: that would turn every tile
+  // access into a generic LD / ST instead of LDS / STS.)
+  extern __shared__ __align__(1024) unsigned char m3_smem_raw[];
+  double *tiles = reinterpret_cast<double *>(m3_smem_raw);          // [S][STAGE]
+  if ((smem_u32(tiles) & 127u) != 0u) __trap();
+  double *xch = tiles + S * G::STAGE;                               // mailboxes
+  uint64_t *full = reinterpret_cast<uint64_t *>(xch + G::XCH);      // [S]
+  uint64_t *empty = full + S;                                       // [S]
+  uint64_t *xready = empty + S;                                     // [S][XROWS][XS]
+  double *s_hz = reinterpret_cast<double *>(xready + S * G::XROWS * XS);   // layers kb-1 .. ke-1 (0 outside)
+  double *s_rzh = s_hz + (M3_MAXCHUNK + 2);                         // 0.5 / hz
+
+  const int nx = (int)m.nx, ny = (int)m.ny, nz = (int)m.nz;
+  const int nNx = nx + 1, nNy = ny + 1, nNz = nz + 1;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
+  const int j0 = blockIdx.y * R;
+  const int Xb = blockIdx.x * (XS * M3_XOUT);
+  const int kb = k_begin + blockIdx.z * kchunk;     // output planes kb .. ke-1 (layers kb .. min(ke, nz)-1)
+  const int ke = min(kb + kchunk, k_end);
+  const int jfirst = kb - 2;                        // stage q holds ex, ey on plane jfirst+q+1 and ez, mui, sigma on layer jfirst+q
+  const int nq = ke - jfirst;
+
+  for (int t = tid; t < S * G::STAGE + G::XCH; t += G::NT) tiles[t] = 0.0;
+  for (int t = tid; t <= ke - kb; t += G::NT) {
+    const int k = kb - 1 + t;
+    const bool ok = (k >= 0) && (k < nz);
+    s_hz[t] = ok ? m.hz[k] : 0.0;
+    s_rzh[t] = ok ? 0.5 * m.rhz[k] : 0.0;
+  }
+  if (tid == 0) {
+    for (int q = 0; q < S; ++q) {
+      mbar_init(&full[q], 1);
+      mbar_init(&empty[q], G::NCONS + G::NHALO);
+    }
+    for (int q = 0; q < S * G::XROWS * XS; ++q) mbar_init(&xready[q], 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  // rows per plane of the five staged arrays; row J = plane * rpp + (row inside the plane)
+  const int rpp[5] = {nNy, ny, nNy, ny, ny};
+
+  if (warp == G::NWARPS - 1) {
+    // ================= producer warp: one elected lane, <= 7 box copies per stage =================
+    if (lane == 0) {
+#pragma unroll
+      for (int a = 0; a < 5; ++a) tmap_prefetch(&maps.m[a]);
+      const int npl[5] = {nNz, nNz, nz, nz, nz};
+      const int gp[5] = {nx, nNx, nNx, nx, nx};
+      for (int q = 0; q < nq; ++q) {
+        const int slot = q % S, n = q / S;
+        if (n >= 1) mbar_wait(&empty[slot], (n - 1) & 1);
+        bool on[5];
+        unsigned total = 0;
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+          const int pl = jfirst + q + (a < 2 ? 1 : 0);
+          on[a] = pl >= 0 && pl < npl[a] && !(q == 0 && a >= 2);   // ez / mui / sigma of the first stage are never read
+          total += on[a] ? G::bytes(a) : 0u;
+        }
+        mbar_arrive_expect_tx(&full[slot], total);
+        double *T = tiles + slot * G::STAGE;
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+          if (on[a]) {
+            const int pl = jfirst + q + (a < 2 ? 1 : 0);
+            const int J0 = pl * rpp[a] + j0 - 1;       // first staged row (may be -1: zero-filled / previous plane)
+            if (G::odd(a)) {
+              // sub-tile 0 holds the staged rows rr = 0, 2, 4, .., sub-tile 1 the rows rr = 1, 3, ..: global row J0 + rr is
+              // even for the rr of parity t = J0 & 1, so the even-row box goes to sub-tile t and the odd-row box to 1 - t
+              const int t = J0 & 1;
+              tmap_load_2d(T + G::off(a) + t * G::sub(a), &maps.m[a], (Xb - 1) & ~1, (J0 + 1) >> 1, &full[slot]);
+              tmap_load_2d(T + G::off(a) + (t ^ 1) * G::sub(a), &maps.m[a], (gp[a] + Xb - 1) & ~1, J0 >> 1, &full[slot]);
+            } else {
+              tmap_load_2d(T + G::off(a), &maps.m[a], (Xb - 1) & ~1, J0, &full[slot]);
+            }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ================= consumer / halo warps =================
+  const bool halo = warp >= G::NCONS;
+  const int s = halo ? warp - G::NCONS : warp % XS;   // strip
+  const int r = halo ? -1 : warp / XS;                // row inside the block (-1: the halo row below it)
+  const int i = Xb + s * M3_XOUT + lane - 1;          // node column and cell column of this lane
+  const int j = j0 + r;                               // node row and cell row
+  const bool ci = (i >= 0) && (i < nx), cil = (i >= 1) && (i <= nx);
+  const bool cj = (j >= 0) && (j < ny), cjd = (j >= 1) && (j <= ny);
+  const double hx = ci ? __ldg(m.hx + i) : 0.0, rx = ci ? __ldg(m.rhx + i) : 0.0;
+  const double hxl = cil ? __ldg(m.hx + i - 1) : 0.0;
+  const double hy = cj ? __ldg(m.hy + j) : 0.0, ry = cj ? __ldg(m.rhy + j) : 0.0;
+  const double hyd = cjd ? __ldg(m.hy + j - 1) : 0.0;
+  const double cfz = 0.5 * rx * ry;
+
+  // shared-memory addressing: thread part (column) + warp-uniform part (slot, array, row; for odd-pitch arrays the
+  // sub-tile of a row depends on the parity of its global row number, which is fixed per ring slot because S is even)
+  const double *tcol = tiles + (s * M3_XOUT + lane);
+  // element offset of (column Xb-1, staged row rr) of array a inside the stage that holds its plane / layer pl (row 0 =
+  // row j0-1).  Odd-pitch arrays keep their even / odd staged rows in two sub-tiles (the producer sorts the boxes
+  // accordingly).  Boxes start on even columns: column Xb-1 sits at box column leadE = (Xb-1)&1 in boxes of even global
+  // rows and -- the pitch being odd -- at 1-leadE in boxes of odd global rows.
+  const int leadE = (Xb - 1) & 1;
+  auto rowoff = [&](int a, int rr, int pl) -> int {
+    if (G::odd(a)) {
+      const int Jodd = (pl * rpp[a] + j0 - 1 + rr) & 1;
+      return G::off(a) + (rr & 1) * G::sub(a) + (rr >> 1) * W + (leadE ^ Jodd);
+    }
+    return G::off(a) + rr * W + leadE;
+  };
+
+  const long long nEx = (long long)nx * nNy * nNz, nEy = (long long)nNx * ny * nNz;
+  const long long pEx = (long long)nx * nNy, pEy = (long long)nNx * ny, pEz = (long long)nNx * nNy;
+
+  if (halo) {
+    // ---- halo warp: G_FX and G_FZ of cell row j0-1 for the block's bottom row of consumers ----
+    double ex0 = 0.0, ex0u = 0.0, ey0 = 0.0, ey0r = 0.0, mzp = 0.0;
+    double *xw = xch + s * 64 + lane;
+    uint64_t *xw_bar = xready + s;
+    for (int qb = 0; qb < nq; qb += S) {
+      const unsigned par = (unsigned)(qb / S) & 1u;
+#pragma unroll
+      for (int u = 0; u < S; ++u) {
+        const int q = qb + u;
+        if (q >= nq) break;
+        const int ku = jfirst + u;   // S is even: the plane parity of slot u is the same in every ring cycle
+        mbar_wait(&full[u], par);
+        const double *T = tcol + u * G::STAGE;
+        const double ex1 = T[rowoff(0, 0, ku + 1)], ex1u = T[rowoff(0, 1, ku + 1)];
+        const double *tEY = T + rowoff(1, 0, ku + 1);
+        const double ey1 = tEY[0], ey1r = tEY[1];
+        if (q >= 1) {
+          const double *tMU = T + rowoff(3, 0, ku);
+          const int t = q - 1;
+          const double hz = s_hz[t], rzh = s_rzh[t];
+          const double ez0 = T[rowoff(2, 0, ku)], ezu = T[rowoff(2, 1, ku)];
+          const double mu0 = tMU[0], mul = tMU[-1];
+          const double circx = hz * (ezu - ez0) - hy * (ey1 - ey0);
+          const double circz = hy * (ey0r - ey0) - hx * (ex0u - ex0);
+          const double mz = hz * mu0;
+          const double gfz = ((mzp + mz) * cfz) * circz;
+          const double gfx = ((hxl * mul + hx * mu0) * (ry * rzh)) * circx;
+          mzp = mz;
+          double *X = xw + u * (G::XROWS * XS * 64);
+          X[0] = gfx;
+          X[32] = gfz;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(xw_bar + u * (G::XROWS * XS));
+        }
+        ex0 = ex1;
+        ex0u = ex1u;
+        ey0 = ey1;
+        ey0r = ey1r;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[u]);
+      }
+    }
+    return;
+  }
+
+  // ---- consumer warp: row j of strip s ----
+  const double vxy4 = 0.25 * hx * hy, vxyd4 = 0.25 * hx * hyd;   // quarter of the x-y cell areas (rows j, j-1)
+  double ex0 = 0.0, ex0u = 0.0, ey0 = 0.0, ey0r = 0.0;   // ex(i,j), ex(i,j+1), ey(i,j), ey(i+1,j) on plane k
+  double gfxp = 0.0, gfyp = 0.0, mzp = 0.0, ap = 0.0, bp = 0.0;
+
+  // output addressing: warp-uniform plane pointers (advanced on the uniform datapath) + a 32-bit in-plane offset per thread
+  const int ic = min(max(i, 0), nx - 1), in_ = min(max(i, 0), nNx - 1), jc = min(j, ny - 1), jn = min(j, nNy - 1);
+  const unsigned ox = (unsigned)(ic + nx * jn), oy = (unsigned)(in_ + nNx * jc), oz = (unsigned)(in_ + nNx * jn);
+  double *yx = y + (long long)(kb - 1) * pEx;
+  double *yy = y + (nEx + (long long)(kb - 1) * pEy);
+  double *yz = y + (nEx + nEy + (long long)(kb - 1) * pEz);
+  const bool lane_out = lane >= 1;
+  const bool wx = lane_out && ci && (j < nNy);
+  const bool wy = lane_out && (i >= 0) && (i < nNx) && cj;
+  const bool wz = lane_out && (i >= 0) && (i < nNx) && (j < nNy);
+
+  double *xw = xch + ((r + 1) * XS + s) * 64 + lane;     // mailbox this warp fills (rows 0 .. R-2)
+  const double *xr = xch + (r * XS + s) * 64 + lane;      // mailbox of the row below (or of the halo warp)
+  uint64_t *xw_bar = xready + (r + 1) * XS + s;
+  uint64_t *xr_bar = xready + r * XS + s;
+  const bool publish = r < R - 1;
+
+  for (int qb = 0; qb < nq; qb += S) {
+    const unsigned par = (unsigned)(qb / S) & 1u;
+#pragma unroll
+    for (int u = 0; u < S; ++u) {
+      const int q = qb + u;
+      if (q >= nq) break;
+      const int ku = jfirst + u;
+      mbar_wait(&full[u], par);
+      const double *T = tcol + u * G::STAGE;
+      const double ex1 = T[rowoff(0, r + 1, ku + 1)], ex1u = T[rowoff(0, r + 2, ku + 1)];
+      const double *tEY = T + rowoff(1, r + 1, ku + 1);
+      const double ey1 = tEY[0], ey1r = tEY[1];
+      if (q >= 1) {
+        const int k = jfirst + q;          // this step works on plane k / layer k
+        const double *tEZ = T + rowoff(2, r + 1, ku);
+        const double *tMU = T + rowoff(3, r + 1, ku);
+        const int t = q - 1;
+        const double hz = s_hz[t], rzh = s_rzh[t];
+        const double ez0 = tEZ[0], ezu = T[rowoff(2, r + 2, ku)];
+        const double mu0 = tMU[0], mul = tMU[-1];
+        const double circx = hz * (ezu - ez0) - hy * (ey1 - ey0);
+        const double circz = hy * (ey0r - ey0) - hx * (ex0u - ex0);
+        const double mz = hz * mu0;
+        const double gfz = ((mzp + mz) * cfz) * circz;
+        const double gfx = ((hxl * mul + hx * mu0) * (ry * rzh)) * circx;
+        mzp = mz;
+        if (publish) {
+          double *X = xw + u * (G::XROWS * XS * 64);
+          X[0] = gfx;
+          X[32] = gfz;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(xw_bar + u * (G::XROWS * XS));
+        }
+        const unsigned xpar = (u == 0) ? (par ^ 1u) : par;   // slot 0 carries no fluxes in the first ring cycle
+        const bool xok = mbar_test_wait(xr_bar + u * (G::XROWS * XS), xpar);   // probe now, consume after the y-face work
+        const double ezr = tEZ[1], mud = T[rowoff(3, r, ku)];
+        const double sg0 = T[rowoff(4, r + 1, ku)], sgd = T[rowoff(4, r, ku)];
+        const double circy = hx * (ex1 - ex0) - hz * (ezr - ez0);
+        const double gfy = ((hyd * mud + hy * mu0) * (rx * rzh)) * circy;
+        const double gfzl = __shfl_up_sync(0xffffffffu, gfz, 1);
+        const double gfyl = __shfl_up_sync(0xffffffffu, gfy, 1);
+        const double sp = sg0 * vxy4, sdp = sgd * vxyd4;
+        const double a = hz * (sp + sdp);
+        const double slp = __shfl_up_sync(0xffffffffu, sp, 1);
+        const double b = hz * (sp + slp);
+        const double al = __shfl_up_sync(0xffffffffu, a, 1);
+        if (!xok) mbar_wait(xr_bar + u * (G::XROWS * XS), xpar);
+        const double *X = xr + u * (G::XROWS * XS * 64);
+        const double gfxd = X[0], gfzd = X[32];
+        const double vx = hx * ((gfyp - gfy) + (gfz - gfzd)) + (ap + a) * ex0;
+        const double vy = hy * ((gfx - gfxp) + (gfzl - gfz)) + (bp + b) * ey0;
+        const double vz = hz * ((gfxd - gfx) + (gfy - gfyl)) + (a + al) * ez0;
+        gfyp = gfy;
+        gfxp = gfx;
+        ap = a;
+        bp = b;
+        if (k >= kb) {
+          if (wx) yx[ox] = vx;
+          if (wy) yy[oy] = vy;
+          if (wz && k < nz) yz[oz] = vz;
+        }
+        yx += pEx;
+        yy += pEy;
+        yz += pEz;
+      }
+      ex0 = ex1;
+      ex0u = ex1u;
+      ey0 = ey1;
+      ey0r = ey1r;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[u]);
+    }
+  }
+}
+
+}  // namespace dzb

@@ -29,10 +29,14 @@ lib.dzb_tune_maxwell_warps.restype = None
 lib.dzb_tune_maxwell_rows.argtypes = [ctypes.c_int] * 4
 lib.dzb_tune_maxwell_rows.restype = None
 lib.dzb_tune_maxwell(variant, kc)
+lib.dzb_tune_maxwell_tmap.argtypes = [ctypes.c_int] * 3
+lib.dzb_tune_maxwell_tmap.restype = None
 if variant == 1:
     lib.dzb_tune_maxwell_warps(a)
-else:
+elif variant == 2:
     lib.dzb_tune_maxwell_rows(a, b, ns, np_)
+else:
+    lib.dzb_tune_maxwell_tmap(a, b, ns)
 for _ in range(launches):
     A.apply_device(e, out=out)
 torch.cuda.synchronize()
