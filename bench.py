@@ -1,22 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- operator-apply throughput (Gdof/s) and HBM-roofline fraction on B200.
 
-Workload at N=1 = BASELINE.json configs[1]: TensorMesh 512^3 DC-resistivity nodal operator
-y = G^T Me(sigma) G phi, applied matrix-free by ONE fused kernel (K8).  A "step" is one
-apply over one synthetic field (phi ~ N(0,1), sigma log-normal).  "dof" = one output row.
+Workload (every N) = BASELINE.json configs[4], the configuration the north-star targets are quoted on:
+TensorMesh 1024^3 Maxwell operator  y = C^T Mf(mui) C e + Me(sigma) e  (tests/boundaries/test_boundary_maxwell.py:95-99
+in the reference), applied matrix-free by ONE fused kernel (K9) per rank.  It fits one B200 (68.8 GB), so N=1 runs the
+same mesh and N = 2/4/8 split it into z-slabs (STRONG scaling: efficiency = v_N / (N v_1) is the north-star figure).
+A "step" is one apply over one synthetic field (e ~ N(0,1), sigma and mui log-normal); "dof" = one output row.
+At N=1 the line also carries `secondary`: BASELINE configs[1] (512^3 DC nodal operator G^T Me(sigma) G, kernel K8).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 512]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload maxwell|dc] [--n N]
 
-Under torchrun (N>1) every rank owns a z-slab: by default WEAK scaling -- each GPU keeps the N=1 workload (a 512^3
-slab of a 512 x 512 x 512N mesh) and exchanges one node plane with each neighbour per apply over NCCL; `--scaling
-strong` splits the 512^3 mesh itself; `--workload maxwell` is BASELINE config 5 (1024^3, strong scaling by
-definition).  Timing = barrier + cuda sync, CUDA events, max over ranks.
-`--impl reference` times the reference's own CPU path (scipy csr_matvec on the assembled
-G^T Me G) on a bounded sample of the same workload on the host cores.
+Timing: W warm-up steps, then R (--repeats, default 5) blocks of EXACTLY K steps, each block bracketed by a barrier +
+cuda synchronize, CUDA events on the launching stream, max over ranks per block; `ms_per_step` is the MEDIAN block
+(best and all blocks are reported next to it).  Inputs (>= 8 GB per GPU) exceed the 126 MB L2, so no flush is needed.
+`--impl reference` times the reference's own CPU path (scipy csr_matvec, one thread) on a bounded sample of the same
+workload on the host cores: both the chain C^T (Mf (C e)) + Me e and the pre-assembled A.
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -41,6 +44,22 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(kernel_key, n):
+    """dram read + write bytes per launch of the dominant kernel at mesh size n, read from the committed ncu capture
+    (profiles/r2_*ncu*.json, written by tools/ncu_to_json.py from the .ncu-rep), or (None, reason)."""
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r2_*ncu*.json"))):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+        except Exception:
+            continue
+        for k in d.get("kernels", []):
+            if kernel_key in k.get("name", "") and int(k.get("n", -1)) == int(n):
+                best = (float(k["dram_bytes_read"]) + float(k["dram_bytes_write"]), os.path.relpath(path, ROOT))
+    return best if best else (None, "no committed ncu capture for this kernel / size")
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -53,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -89,23 +108,75 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the reference's scipy path on a bounded sample
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_arm(n_sample, steps, warmup):
-    """scipy csr_matvec on the assembled A = G^T Me(sigma) G (what the reference/SimPEG applies)."""
-    from oracle import tensor_ops as T  # the checker; allowed here (cpu_baseline leg only)
+def cpu_maxwell_arm(n_sample, steps, warmup):
+    """scipy csr_matvec on the reference's matrices for C^T Mf(mui) C + Me(sigma): chain and pre-assembled A."""
+    from oracle import tensor_ops as T  # the checker; allowed here (cpu_baseline / --impl reference legs only)
+
+    g = T.Grid([n_sample] * 3)
+    sigma = np.exp(np.random.default_rng(12).standard_normal(g.nC))
+    mui = np.exp(np.random.default_rng(13).standard_normal(g.nC))
+    e = np.random.default_rng(11).standard_normal(g.nE)
+    t0 = time.perf_counter()
+    Cm = T.edge_curl(g)
+    Mf, Me = T.inner_product(g, "F", mui), T.inner_product(g, "E", sigma)
+    CT = Cm.T.tocsr()
+    A = (CT @ Mf @ Cm + Me).tocsr()
+    t_build = time.perf_counter() - t0
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        return (time.perf_counter() - t0) / steps
+
+    dt_chain = timed(lambda: CT @ (Mf @ (Cm @ e)) + Me @ e)
+    dt_asm = timed(lambda: A @ e)
+    return {"ndof": g.nE, "dt_chain": dt_chain, "dt_assembled": dt_asm, "build_s": t_build,
+            "gdof_chain": g.nE / dt_chain / 1e9, "gdof_assembled": g.nE / dt_asm / 1e9}
+
+
+def cpu_dc_arm(n_sample, steps, warmup):
+    """scipy csr_matvec for G^T Me(sigma) G: the 3-SpMV chain reference users run and the pre-assembled A."""
+    from oracle import tensor_ops as T
 
     g = T.Grid([n_sample] * 3)
     sigma = np.exp(np.random.default_rng(6).standard_normal(g.nC))
     phi = np.random.default_rng(5).standard_normal(g.nN)
+    t0 = time.perf_counter()
     G = T.nodal_gradient(g)
     Me = T.inner_product(g, "E", sigma)
-    A = (G.T @ Me @ G).tocsr()
-    for _ in range(warmup):
-        A @ phi
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        A @ phi
-    dt = (time.perf_counter() - t0) / steps
-    return g.nN / dt / 1e9, dt, g.nN
+    GT = G.T.tocsr()
+    A = (GT @ Me @ G).tocsr()
+    t_build = time.perf_counter() - t0
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        return (time.perf_counter() - t0) / steps
+
+    dt_chain = timed(lambda: GT @ (Me @ (G @ phi)))
+    dt_asm = timed(lambda: A @ phi)
+    return {"ndof": g.nN, "dt_chain": dt_chain, "dt_assembled": dt_asm, "build_s": t_build,
+            "gdof_chain": g.nN / dt_chain / 1e9, "gdof_assembled": g.nN / dt_asm / 1e9}
+
+
+def cpu_baseline_object(res, what, n_sample, n_full):
+    import scipy
+
+    return {
+        "value": res["gdof_assembled"], "unit": UNIT, "cores": 1, "kind": "port",
+        "chain_value": res["gdof_chain"], "chain_ms": res["dt_chain"] * 1e3, "assembled_ms": res["dt_assembled"] * 1e3,
+        "assembly_s": res["build_s"],
+        "sample": (f"{n_sample}^3 sample of the {n_full}^3 workload (per-dof normalised; the reference cannot assemble "
+                   f"{n_full}^3): {what}; value = pre-assembled A @ x, chain_value = the SpMV chain reference users run; "
+                   f"scipy {scipy.__version__} csr_matvec is single-threaded: 1 of {os.cpu_count()} host cores; matrices "
+                   f"assembled by the oracle port of the reference (oracle/tensor_ops.py, pinned against the reference)"),
+    }
 
 
 def run_reference(args):
@@ -113,16 +184,23 @@ def run_reference(args):
     if rank != 0:
         return
     n_sample = args.cpu_n
-    val, dt, ndof = cpu_reference_arm(n_sample, max(args.steps, 1), max(args.warmup, 1))
-    sample = (f"TensorMesh {n_sample}^3 (of the 512^3 workload), assembled A=G^T Me(sigma) G as scipy CSR, "
-              f"A @ phi via scipy csr_matvec, 1 thread (scipy SpMV is single-threaded) of {os.cpu_count()} cores")
+    steps, warmup = max(args.steps, 1), max(args.warmup, 1)
+    if args.workload == "maxwell":
+        res = cpu_maxwell_arm(n_sample, steps, warmup)
+        what = "C^T Mf(mui) C + Me(sigma) as scipy CSR"
+        workload = f"TensorMesh {args.n}^3 Maxwell C^T Mf(mui) C + Me(sigma) apply (CPU sample at {n_sample}^3)"
+    else:
+        res = cpu_dc_arm(n_sample, steps, warmup)
+        what = "G^T Me(sigma) G as scipy CSR"
+        workload = f"TensorMesh {args.n}^3 DC nodal G^T Me(sigma) G apply (CPU sample at {n_sample}^3)"
+    cb = cpu_baseline_object(res, what, n_sample, args.n)
     line = {
-        "metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"TensorMesh 512^3 DC nodal G^T Me(sigma) G apply (CPU sample at {n_sample}^3)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "metric": METRIC, "value": cb["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["dt_assembled"] * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "dofs_per_step": int(res["ndof"])},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
@@ -130,11 +208,79 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
-def run_ours(args):
+def timed_blocks(step, steps, repeats, sync, world, dev):
+    """R blocks of exactly `steps` steps; returns per-block ms (max over ranks)."""
     import torch
     import torch.distributed as dist
 
+    out = []
+    for _ in range(repeats):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync()
+        ev0.record()
+        for _ in range(steps):
+            step()
+        ev1.record()
+        sync()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        out.append(ms)
+    return out
+
+
+def secondary_dc(args, dev, peak):
+    """BASELINE configs[1] on one GPU: 512^3 DC nodal operator, device-resident + end to end."""
+    import torch
+
     import discretize_b200 as dz
+
+    n = 512
+    mesh = dz.TensorMesh([n, n, n])
+    gen = torch.Generator(device=dev); gen.manual_seed(5)
+    phi = torch.randn(mesh.nN, dtype=torch.float64, device=dev, generator=gen)
+    gen.manual_seed(6)
+    sigma = torch.exp(torch.randn(mesh.nC, dtype=torch.float64, device=dev, generator=gen))
+    G = mesh.nodal_gradient
+    A = G.T @ mesh.get_edge_inner_product(sigma) @ G
+    assert type(A).__name__ == "DCNodalOperator"
+    out = torch.empty(mesh.nN, dtype=torch.float64, device=dev)
+    step = lambda: A.apply_device(phi, out=out)
+    for _ in range(3):
+        step()
+    blocks = timed_blocks(step, args.steps, 3, torch.cuda.synchronize, 1, dev)
+    ms = float(np.median(blocks)) / args.steps
+    alg = 8.0 * (2 * mesh.nN + mesh.nC)
+    host_in = torch.empty(mesh.nN, dtype=torch.float64).pin_memory()
+    host_in.copy_(phi)
+    host_out = torch.empty(mesh.nN, dtype=torch.float64).pin_memory()
+    for _ in range(2):
+        A.matvec(host_in, out=host_out)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        A.matvec(host_in, out=host_out)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 5
+    traffic, src = ncu_traffic("k_dc_nodal_ring", 512)
+    return {
+        "workload": "TensorMesh 512^3 DC-resistivity nodal operator G^T Me(sigma) G matrix-free apply (BASELINE configs[1])",
+        "value": mesh.nN / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "steps": args.steps,
+        "block_ms": blocks, "dofs_per_step": int(mesh.nN),
+        "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": traffic, "traffic_source": src,
+                     "kernel": "k_dc_nodal_ring<4,NWC,PARX>", "algorithmic_bytes_per_launch": alg},
+        "e2e": {"value": mesh.nN / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": int(8 * mesh.nN),
+                "d2h_bytes_per_step": int(8 * mesh.nN),
+                "api": "A = G.T @ mesh.get_edge_inner_product(sigma) @ G; A.matvec(x_host_pinned, out=y_host_pinned)"},
+    }
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -148,130 +294,99 @@ def run_ours(args):
 
     n = args.n
     if args.workload == "maxwell":
-        # BASELINE config 5: C^T Mf(mui) C + Me(sigma) on n^3 (1024^3 by default for this workload), z-slabs
+        # BASELINE configs[4]: C^T Mf(mui) C + Me(sigma) on n^3, z-slabs across the ranks (strong scaling)
         from discretize_b200.slab import SlabMaxwell
 
         op = SlabMaxwell(n, n, n, rank, world)
-        step = op.step_graphed if (world > 1 and not args.eager) else op.step
         ndof_total = n * (n + 1) * (n + 1) * 3
         alg_bytes = 8.0 * (2 * ndof_total + 2 * n ** 3) / world
-        launches_per_step = op.launches_per_step
-        parallelism = "1 GPU" if world == 1 else f"z-slabs x{world}, NCCL halo send/recv"
-        workload_name = f"TensorMesh {n}^3 Maxwell C^T Mf(mui) C + Me(sigma) fused matrix-free apply"
-        kernel_name = "k_maxwell_ring<2,NWC,PARX,4>"
-    elif world == 1:
-        mesh = dz.TensorMesh([n, n, n])
-        gen = torch.Generator(device=dev); gen.manual_seed(5)
-        phi = torch.randn(mesh.nN, dtype=torch.float64, device=dev, generator=gen)
-        gen.manual_seed(6)
-        sigma = torch.exp(torch.randn(mesh.nC, dtype=torch.float64, device=dev, generator=gen))
-        G = mesh.nodal_gradient
-        A = G.T @ mesh.get_edge_inner_product(sigma) @ G  # fuses into the single K8 kernel
-        assert type(A).__name__ == "DCNodalOperator"
-        out = torch.empty(mesh.nN, dtype=torch.float64, device=dev)
-        step = lambda: A.apply_device(phi, out=out)
-        ndof_total = mesh.nN
-        alg_bytes = 8.0 * (2 * mesh.nN + mesh.nC)
-        launches_per_step = 1
-        parallelism = "1 GPU"
-        workload_name = f"TensorMesh {n}^3 DC-resistivity nodal operator G^T Me(sigma) G matrix-free apply"
-        kernel_name = "k_dc_nodal_ring<4,NWC,PARX>"
+        workload_name = f"TensorMesh {n}^3 Maxwell C^T Mf(mui) C + Me(sigma) fused matrix-free apply (BASELINE configs[4])"
+        kernel_name, kernel_key = "k_maxwell_tmap<XS,R,PARX,NSLOT> (tensor-map TMA ring)", "k_maxwell_tmap"
     else:
         from discretize_b200.slab import SlabDCNodal
 
-        # weak scaling (default): every rank owns the N=1 workload, a 512^3 slab of a 512 x 512 x (512 N) mesh, and
-        # exchanges one node plane with each neighbour per apply; --scaling strong splits the 512^3 mesh itself
-        # (66 us of kernel time per rank at N=8: latency-bound, profiles/r1_scale_dc_512_n1248.jsonl)
-        nz_global = n * world if args.scaling == "weak" else n
-        op = SlabDCNodal(n, n, nz_global, rank, world, seed_phi=5, seed_sigma=6)
-        step = op.step_graphed if not args.eager else op.step
-        ndof_total = (n + 1) ** 2 * (nz_global + 1)
-        alg_bytes = 8.0 * (2 * ndof_total + n * n * nz_global) / world
-        launches_per_step = op.launches_per_step
-        parallelism = f"z-slabs x{world} ({args.scaling} scaling), NCCL halo send/recv"
-        workload_name = (f"TensorMesh {n}x{n}x{nz_global} DC-resistivity nodal operator G^T Me(sigma) G matrix-free apply"
-                         f" ({n}^3 per GPU)" if args.scaling == "weak" else
-                         f"TensorMesh {n}^3 DC-resistivity nodal operator G^T Me(sigma) G matrix-free apply")
-        kernel_name = "k_dc_nodal_ring<4,NWC,PARX>"
+        op = SlabDCNodal(n, n, n, rank, world, seed_phi=5, seed_sigma=6)
+        ndof_total = (n + 1) ** 3
+        alg_bytes = 8.0 * (2 * ndof_total + n ** 3) / world
+        workload_name = f"TensorMesh {n}^3 DC-resistivity nodal operator G^T Me(sigma) G matrix-free apply (BASELINE configs[1])"
+        kernel_name, kernel_key = "k_dc_nodal_ring<4,NWC,PARX>", "k_dc_nodal_ring"
+    step = op.step_graphed if (world > 1 and not args.eager) else op.step
+    launches_per_step = op.launches_per_step
+    parallelism = "1 GPU" if world == 1 else f"z-slabs x{world} (strong scaling), NCCL halo send/recv, no collective"
 
     def sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
         step()
     sync()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    sync()
-    ms_total = ev0.elapsed_time(ev1)
+    blocks = timed_blocks(step, args.steps, args.repeats, sync, world, dev)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    ms_step = float(np.median(blocks)) / args.steps
     value = ndof_total / (ms_step * 1e-3) / 1e9
 
-    # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region
-    e2e = None
-    if world == 1 and args.workload == "dc":
-        host_in = torch.empty(mesh.nN, dtype=torch.float64).pin_memory()
-        host_in.copy_(phi)
-        host_out = torch.empty(mesh.nN, dtype=torch.float64).pin_memory()
-        e2e_steps = max(2, min(args.steps, 10))
-        for _ in range(2):  # warm-up (public API: pinned CPU tensor in -> pinned CPU tensor out)
-            y = A.matvec(host_in, out=host_out)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            y = A.matvec(host_in, out=host_out)
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / e2e_steps
-        assert y.device.type == "cpu" and y.shape[0] == mesh.nN
-        e2e = {"value": ndof_total / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(8 * mesh.nN),
-               "d2h_bytes_per_step": int(8 * mesh.nN), "ms_per_step": dt * 1e3,
-               "api": "A = G.T @ mesh.get_edge_inner_product(sigma) @ G; A.matvec(x_host_pinned, out=y_host_pinned)"}
-
-    e2e_error = None
-    if world > 1 and args.workload == "dc":
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    e2e, e2e_error = None, None
+    if not args.no_e2e:
         try:
-            # every rank streams ITS slab from / to pinned host memory: H2D of the owned planes, the distributed apply
-            # (halo exchange + kernels, eager launches), D2H of the owned result -- wall clock, max over ranks
-            L = op.layout
-            own = slice(L.p_own0 * L.plane, L.p_own1 * L.plane)
-            host_in = torch.empty(op.phi[own].numel(), dtype=torch.float64).pin_memory()
-            host_in.copy_(op.phi[own])
-            host_out = torch.empty_like(host_in).pin_memory()
-            e2e_steps = max(2, min(args.steps, 10))
-
-            def e2e_step():
+            e2e_steps = max(2, min(args.steps, args.e2e_steps))
+            if world == 1:
+                A = op.op                                      # the operator a user builds: C.T @ Mf @ C + Me (fused)
+                nvec = A.shape[0]
+                host_in = torch.empty(nvec, dtype=torch.float64).pin_memory()
+                host_in.copy_(op.e if args.workload == "maxwell" else op.phi)
+                host_out = torch.empty(nvec, dtype=torch.float64).pin_memory()
+                A.matvec(host_in, out=host_out)                # warm-up (allocates the device staging buffers)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    y = A.matvec(host_in, out=host_out)
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) / e2e_steps
+                assert y.device.type == "cpu" and y.shape[0] == nvec
+                # the streamed result must be the device-resident one
+                dev_out = op.out if world == 1 else None
+                chk = float((host_out[:4096].to(dev) - dev_out[:4096]).abs().max())
+                api = ("A = C.T @ mesh.get_face_inner_product(mui) @ C + mesh.get_edge_inner_product(sigma); "
+                       "A.matvec(x_host_pinned, out=y_host_pinned)") if args.workload == "maxwell" else \
+                      "A = G.T @ mesh.get_edge_inner_product(sigma) @ G; A.matvec(x_host_pinned, out=y_host_pinned)"
+                e2e = {"value": ndof_total / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(8 * nvec),
+                       "d2h_bytes_per_step": int(8 * nvec), "ms_per_step": dt * 1e3, "steps": e2e_steps, "api": api,
+                       "max_abs_diff_vs_device_resident_first_4096": chk}
+                del host_in, host_out
+            else:
+                if args.workload == "maxwell":
+                    nown = sum(op.owned_sizes())
+                    host_in = torch.empty(nown, dtype=torch.float64).pin_memory()
+                    op.owned_to_host(op.e, host_in)
+                else:
+                    L = op.layout
+                    own = slice(L.p_own0 * L.plane, L.p_own1 * L.plane)
+                    nown = op.phi[own].numel()
+                    host_in = torch.empty(nown, dtype=torch.float64).pin_memory()
+                    host_in.copy_(op.phi[own])
+                host_out = torch.empty_like(host_in).pin_memory()
                 op.step_from_host(host_in, host_out)
-
-            for _ in range(2):
-                e2e_step()
-            sync()
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                e2e_step()
-            sync()
-            tt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
-            nb = torch.tensor([8.0 * host_in.numel()], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dist.all_reduce(nb)
-            dt = float(tt.item())
-            e2e = {"value": ndof_total / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(nb.item()),
-                   "d2h_bytes_per_step": int(nb.item()), "ms_per_step": dt * 1e3,
-                   "api": "per rank: SlabDCNodal.step_from_host(x_host_pinned, y_host_pinned): outer planes up, NCCL halo "
-                          "exchange, then H2D / K8 / D2H pipelined over z-chunks"}
+                sync()
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    op.step_from_host(host_in, host_out)
+                sync()
+                tt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+                nb = torch.tensor([8.0 * nown], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dist.all_reduce(nb)
+                dt = float(tt.item())
+                e2e = {"value": ndof_total / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(nb.item()),
+                       "d2h_bytes_per_step": int(nb.item()), "ms_per_step": dt * 1e3, "steps": e2e_steps,
+                       "api": "per rank: Slab operator .step_from_host(x_host_pinned, y_host_pinned): boundary planes up, NCCL "
+                              "halo exchange, then H2D / fused kernel / D2H pipelined over z-chunks"}
         except Exception as exc:  # the device-timed line must survive a failure of the host-path leg
             e2e, e2e_error = None, repr(exc)[:300]
 
@@ -289,21 +404,24 @@ def run_ours(args):
 
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (ms_step * 1e-3) / 1e9  # per-GPU GB/s of the dominant kernel's algorithmic bytes
+    traffic, traffic_src = ncu_traffic(kernel_key, n) if world == 1 else (None, "single-GPU captures only")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": args.scaling,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name,
                    "dofs_per_step": int(ndof_total), "parallelism": parallelism,
-                   "l2": "inputs (>= 2 GB per GPU at N=1) exceed the 126 MB L2; no flush needed"},
+                   "l2": "inputs (>= 8 GB per GPU) exceed the 126 MB L2; no flush needed"},
+        "timing": {"blocks": len(blocks), "steps_per_block": args.steps, "block_ms": blocks,
+                   "ms_per_step_median": ms_step, "ms_per_step_best": min(blocks) / args.steps,
+                   "note": "each block = exactly `steps` applies between barrier + synchronize; median block reported"},
         "gpu_launches": launches_per_step * args.steps,
         "launch_mode": ("cuda-graph replay" if (world > 1 and not args.eager and not getattr(op, "_graph_failed", False))
                         else "eager"),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": 3.22e9 if (args.workload == "dc" and n == 512 and world == 1) else None,
-                     "traffic_source": "ncu --set full, profiles/r1_k8_dc_nodal_ring_ncu_full_summary.txt (dram read+write per launch)",
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peak_src, "kernel": kernel_name,
                      "algorithmic_bytes_per_launch": alg_bytes},
     }
@@ -311,13 +429,21 @@ def run_ours(args):
         line["e2e"] = e2e
     elif e2e_error is not None:
         line["e2e_error"] = e2e_error
-    if world == 1 and not args.no_cpu and args.workload == "dc":
-        val, dt, _ = cpu_reference_arm(args.cpu_n, 3, 1)
-        line["cpu_baseline"] = {
-            "value": val, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{args.cpu_n}^3 sample of the workload: scipy csr_matvec on the assembled G^T Me G "
-                      f"(oracle port of the reference build), 1 of {os.cpu_count()} host cores",
-        }
+    if world == 1:
+        del op
+        torch.cuda.empty_cache()
+        if args.workload == "maxwell" and not args.no_secondary:
+            try:
+                line["secondary"] = secondary_dc(args, dev, peak)
+            except Exception as exc:
+                line["secondary_error"] = repr(exc)[:300]
+        if not args.no_cpu:
+            if args.workload == "maxwell":
+                res = cpu_maxwell_arm(args.cpu_n_inline, 3, 1)
+                line["cpu_baseline"] = cpu_baseline_object(res, "C^T Mf(mui) C + Me(sigma) as scipy CSR", args.cpu_n_inline, n)
+            else:
+                res = cpu_dc_arm(args.cpu_n_inline, 3, 1)
+                line["cpu_baseline"] = cpu_baseline_object(res, "G^T Me(sigma) G as scipy CSR", args.cpu_n_inline, n)
     print(json.dumps(line), flush=True)
     shutdown()
 
@@ -327,21 +453,21 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--repeats", type=int, default=5, help="timed blocks of `steps` steps (median reported)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=None, help="cells per axis (default 512 for dc = BASELINE configs[1], 1024 for maxwell)")
-    ap.add_argument("--workload", default="dc", choices=["dc", "maxwell"],
-                    help="dc = configs[1] (the N=1 headline); maxwell = configs[4], the 1024^3 z-slab scaling case")
-    ap.add_argument("--cpu-n", type=int, default=128, help="cells per axis of the bounded CPU sample")
+    ap.add_argument("--workload", default="maxwell", choices=["maxwell", "dc"],
+                    help="maxwell = BASELINE configs[4] (default, every N); dc = configs[1]")
+    ap.add_argument("--n", type=int, default=None, help="cells per axis (default 1024 for maxwell, 512 for dc)")
+    ap.add_argument("--cpu-n", type=int, default=256, help="cells per axis of the CPU sample of --impl reference")
+    ap.add_argument("--cpu-n-inline", type=int, default=128, help="cells per axis of the cpu_baseline leg of the default run")
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
-                    help="N > 1: weak = every GPU owns the N=1 workload (default for dc), strong = the N=1 mesh is split "
-                         "(default for maxwell: BASELINE config 5 is the 1024^3 mesh on 2/4/8 GPUs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the 512^3 DC object at N=1")
     ap.add_argument("--eager", action="store_true", help="multi-GPU: launch every step from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.n is None:
-        args.n = 512 if args.workload == "dc" else 1024
-    if args.scaling is None:
-        args.scaling = "weak" if args.workload == "dc" else "strong"
+        args.n = 1024 if args.workload == "maxwell" else 512
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -10,7 +10,6 @@
 // from global memory (L1/L2 serve the re-reads).  It is the simple, obviously-correct
 // form and the cross-check for the marching variant.
 #include "tm_mass_common.cuh"
-#include "tm_maxwell_ring.cuh"
 #include "tm_maxwell_rows.cuh"
 #include "tm_maxwell_tmap.cuh"
 #include <cudaTypedefs.h>
@@ -55,15 +54,15 @@ __global__ void __launch_bounds__(BX *BY *BZ)
 
 using namespace dzb;
 
-static int g_mx_variant = 3;   // 0 = gather (one thread per edge), 1 = first TMA ring (2 rows / lane), 2 = row-per-warp ring (bulk copies), 3 = same with tensor maps
-static int g_mx_kchunk = 64;
+static int g_mx_variant = 3;   // 0 = gather (one thread per edge, cross-check), 2 = row-per-warp ring fed by row-wise bulk copies, 3 = same ring fed by tensor maps
+static int g_mx_last_path = -1;   // which variant served the last call (tests assert that even-sized meshes take the tensor-map path)
+extern "C" int dzb_tm_maxwell_last_path(void) { return g_mx_last_path; }
 static int g_m2_kchunk = 0;    // 0 = automatic (~128 planes per block)
 static int g_m2_dbg = 0;   // experiments only: 1 = consumers skip the arithmetic, 2 = producers skip the copies
 extern "C" void dzb_tune_maxwell_debug(int d) { g_m2_dbg = d; }
 static int g_m2_xs = 2, g_m2_r = 4, g_m2_ns = 4, g_m2_np = 2;
 extern "C" void dzb_tune_maxwell(int variant, int kchunk) {
   g_mx_variant = variant;
-  if (kchunk > 0) g_mx_kchunk = kchunk > MX_MAXCHUNK ? MX_MAXCHUNK : kchunk;
   g_m2_kchunk = kchunk > 0 ? (kchunk > M2_MAXCHUNK ? M2_MAXCHUNK : kchunk) : 0;
 }
 // block shape of variant 2: strips x rows, one of (1,8) (2,4) (4,2) (4,4); producer warps 1 or 2
@@ -179,15 +178,27 @@ static int m3_encode(const TM &m, const double *mui, const double *sigma, const 
     if (reinterpret_cast<uintptr_t>(base[a]) & 15) return -1;
     if (rows[a] >= ((i64)1 << 31) || 2 * pitch[a] >= ((i64)1 << 31)) return -1;
     const bool odd = (pitch[a] & 1) != 0;
-    if (odd && (rows[a] & 1)) return -1;     // the last super-row would reach past the array
-    cuuint64_t gdim[2] = {(cuuint64_t)(odd ? 2 * pitch[a] : pitch[a]), (cuuint64_t)(odd ? rows[a] / 2 : rows[a])};
-    cuuint64_t gstr[1] = {(cuuint64_t)(odd ? 16 * pitch[a] : 8 * pitch[a])};
     cuuint32_t box[2] = {(cuuint32_t)G::W, (cuuint32_t)G::hbox(a)};
     cuuint32_t estr[2] = {1, 1};
+    // even pitch: the array as it is.  Odd pitch: m[a] = its EVEN rows (width = one row, row stride = two rows),
+    // o[a] = super-rows of two rows, of which the boxes take the second half: both stay inside the array whatever the
+    // parity of its row count, and a box never reads past the end of a row it was not asked for.
+    cuuint64_t gdim[2] = {(cuuint64_t)pitch[a], (cuuint64_t)(odd ? (rows[a] + 1) / 2 : rows[a])};
+    cuuint64_t gstr[1] = {(cuuint64_t)(odd ? 16 * pitch[a] : 8 * pitch[a])};
     if (enc(&maps.m[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base[a]), gdim, gstr, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return -1;
+    if (odd) {
+      cuuint64_t odim[2] = {(cuuint64_t)(2 * pitch[a]), (cuuint64_t)(rows[a] / 2)};
+      if (odim[1] == 0) odim[1] = 1, odim[0] = (cuuint64_t)pitch[a];   // a one-row array has no odd rows: everything the box asks for is out of bounds
+      if (enc(&maps.o[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base[a]), odim, gstr, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return -1;
+    } else {
+      maps.o[a] = maps.m[a];
+    }
   }
   last_key = key;
   last_maps = maps;
@@ -197,34 +208,37 @@ static int m3_encode(const TM &m, const double *mui, const double *sigma, const 
 
 template <int XS, int R, int PARX, int NSLOT, int MINB>
 static int launch_m3_t(const TM &m, const double *mui, const double *sigma, const double *e, double *y, int k_begin,
-                       int k_end, cudaStream_t s) {
+                       int k_end, int k_begin2, int k_end2, cudaStream_t s) {
   typedef Mx3<XS, R, PARX, NSLOT> G;
   M3Maps maps;
   if (m3_encode<G>(m, mui, sigma, e, maps) != 0) return -1;
   if (cudaFuncSetAttribute(k_maxwell_tmap<XS, R, PARX, NSLOT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)G::SMEM) != cudaSuccess)
     return -1;
-  const int nNx = (int)m.nx + 1, nNy = (int)m.ny + 1, planes = k_end - k_begin;
+  const int nNx = (int)m.nx + 1, nNy = (int)m.ny + 1, planes = k_end - k_begin, planes2 = k_end2 - k_begin2;
+  const int longest = planes > planes2 ? planes : planes2;
   const int xblocks = (nNx + XS * M3_XOUT - 1) / (XS * M3_XOUT), yblocks = (nNy + R - 1) / R;
-  int nchunks = g_m2_kchunk > 0 ? (planes + g_m2_kchunk - 1) / g_m2_kchunk : (planes + 143) / 144;
+  int nchunks = g_m2_kchunk > 0 ? (longest + g_m2_kchunk - 1) / g_m2_kchunk : (longest + 143) / 144;
   if (g_m2_kchunk == 0) {
     const long long nxy = (long long)xblocks * yblocks;
     const long long want = (4ll * 148 * MINB + nxy - 1) / nxy;
-    if (nchunks < want) nchunks = (int)(want < (planes + 7) / 8 ? want : (planes + 7) / 8);
+    if (nchunks < want) nchunks = (int)(want < (longest + 7) / 8 ? want : (longest + 7) / 8);
     if (nchunks < 1) nchunks = 1;
   }
-  const int kchunk = (planes + nchunks - 1) / nchunks;
-  dim3 grid((unsigned)xblocks, (unsigned)yblocks, (unsigned)((planes + kchunk - 1) / kchunk));
-  k_maxwell_tmap<XS, R, PARX, NSLOT, MINB><<<grid, dim3(G::NT), G::SMEM, s>>>(m, maps, y, kchunk, k_begin, k_end);
+  const int kchunk = (longest + nchunks - 1) / nchunks;
+  const int nzb0 = (planes + kchunk - 1) / kchunk, nzb1 = (planes2 + kchunk - 1) / kchunk;
+  dim3 grid((unsigned)xblocks, (unsigned)yblocks, (unsigned)(nzb0 + nzb1));
+  k_maxwell_tmap<XS, R, PARX, NSLOT, MINB><<<grid, dim3(G::NT), G::SMEM, s>>>(m, maps, y, kchunk, k_begin, k_end, nzb0,
+                                                                              k_begin2, k_end2);
   return 0;
 }
 
-#define M3_LAUNCH(XS, R, NS, MINB)                                                        \
-  return parx ? launch_m3_t<XS, R, 1, NS, MINB>(m, mui, sigma, e, y, k_begin, k_end, s)   \
-              : launch_m3_t<XS, R, 0, NS, MINB>(m, mui, sigma, e, y, k_begin, k_end, s)
+#define M3_LAUNCH(XS, R, NS, MINB)                                                                             \
+  return parx ? launch_m3_t<XS, R, 1, NS, MINB>(m, mui, sigma, e, y, k_begin, k_end, k_begin2, k_end2, s)      \
+              : launch_m3_t<XS, R, 0, NS, MINB>(m, mui, sigma, e, y, k_begin, k_end, k_begin2, k_end2, s)
 
 static int launch_m3(const TM &m, const double *mui, const double *sigma, const double *e, double *y, int k_begin,
-                     int k_end, cudaStream_t s) {
+                     int k_end, int k_begin2, int k_end2, cudaStream_t s) {
   const int parx = (int)(m.nx & 1);
   switch (g_m3_xs * 100 + g_m3_r * 10 + g_m3_ns) {
     case 144: M3_LAUNCH(1, 4, 4, 3);
@@ -248,47 +262,30 @@ static int launch_m3(const TM &m, const double *mui, const double *sigma, const 
   M3_LAUNCH(2, 8, 4, 1);
 }
 
-template <int NWC, int PARX, int NSLOT>
-static int launch_mx_ring_t(const TM &m, const double *mui, const double *sigma, const double *e, double *y, int xblocks,
-                            int nwc, int k_begin, int k_end, cudaStream_t s) {
-  typedef MxRing<2, NWC, PARX, NSLOT> G;
-  // the attribute is per device; setting it is cheap, so no process-wide "done" flag
-  if (cudaFuncSetAttribute(k_maxwell_ring<2, NWC, PARX, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)G::SMEM) != cudaSuccess)
+extern "C" int dzb_tm_maxwell_range(const DzbTensorMesh *mm, const double *mui, const double *sigma, const double *e,
+                                    double *y, int64_t k_begin, int64_t k_end, void *stream);
+
+// two disjoint plane ranges in ONE launch (the two boundary planes of a z-slab, once its halos have arrived)
+extern "C" int dzb_tm_maxwell_range2(const DzbTensorMesh *mm, const double *mui, const double *sigma, const double *e,
+                                     double *y, int64_t k_begin, int64_t k_end, int64_t k_begin2, int64_t k_end2,
+                                     void *stream) {
+  if (!valid_mesh(mm)) return -1;
+  TM m(*mm);
+  if (k_begin < 0 || k_end > m.nz + 1 || k_begin > k_end || k_begin2 < 0 || k_end2 > m.nz + 1 || k_begin2 > k_end2) {
+    set_error("dzb_tm_maxwell_range2: plane range outside [0, nz+1]");
     return -1;
-  const int nNy = (int)m.ny + 1;
-  // 64 planes per block is best at 512^3, 128 at 1024^3 (profiles/r1b_k9_sweep_1024.log): with four times as many
-  // (x, y) blocks the longer march amortises the ring fill without starving the grid
-  int kchunk = (g_mx_kchunk == 64 && xblocks * ((nNy + 1) / 2) >= 1500) ? 128 : g_mx_kchunk;
-  const int nxy = xblocks * ((nNy + 1) / 2);
-  const int zb_target = (4 * 148 + nxy - 1) / nxy;
-  const int fair = (k_end - k_begin + zb_target - 1) / zb_target;
-  kchunk = kchunk < fair ? kchunk : (fair < 8 ? 8 : fair);
-  dim3 grid((unsigned)xblocks, (unsigned)((nNy + 1) / 2), (unsigned)((k_end - k_begin + kchunk - 1) / kchunk));
-  k_maxwell_ring<2, NWC, PARX, NSLOT><<<grid, dim3((nwc + 1) * 32), G::SMEM, s>>>(m, mui, sigma, e, y, kchunk, nwc,
-                                                                                   k_begin, k_end);
-  return 0;
-}
-
-static int g_mx_maxw = 9;  // consumer warps per block: 6, 9, 12 or 18 (tuning knob)
-extern "C" void dzb_tune_maxwell_warps(int w) { g_mx_maxw = w; }
-
-#define MX_LAUNCH(NWC, NS)                                                                                    \
-  return parx ? launch_mx_ring_t<NWC, 1, NS>(m, mui, sigma, e, y, xblocks, nwc, k_begin, k_end, s)            \
-              : launch_mx_ring_t<NWC, 0, NS>(m, mui, sigma, e, y, xblocks, nwc, k_begin, k_end, s)
-
-static int launch_mx_ring(const TM &m, const double *mui, const double *sigma, const double *e, double *y, int k_begin,
-                          int k_end, cudaStream_t s) {
-  const int nNx = (int)m.nx + 1;
-  const int strips = (nNx + MX_XOUT - 1) / MX_XOUT;
-  int maxw = strips <= 6 ? 6 : g_mx_maxw;
-  const int xblocks = (strips + maxw - 1) / maxw;
-  const int nwc = (strips + xblocks - 1) / xblocks;
-  const int parx = (int)(m.nx & 1);
-  if (maxw <= 6) { MX_LAUNCH(6, 4); }
-  if (maxw <= 9) { MX_LAUNCH(9, 4); }
-  if (maxw <= 12) { MX_LAUNCH(12, 4); }
-  MX_LAUNCH(18, 3);
+  }
+  if (k_begin == k_end) return dzb_tm_maxwell_range(mm, mui, sigma, e, y, k_begin2, k_end2, stream);
+  if (k_begin2 == k_end2) return dzb_tm_maxwell_range(mm, mui, sigma, e, y, k_begin, k_end, stream);
+  const bool ring_ok = m.ny >= 1 && (m.nx + 1) * (m.ny + 1) < ((i64)1 << 31);
+  if (g_mx_variant == 3 && ring_ok) {
+    g_mx_last_path = 3;
+    if (launch_m3(m, mui, sigma, e, y, (int)k_begin, (int)k_end, (int)k_begin2, (int)k_end2, (cudaStream_t)stream) == 0)
+      return check_launch("dzb_tm_maxwell");
+    cudaGetLastError();
+  }
+  const int rc = dzb_tm_maxwell_range(mm, mui, sigma, e, y, k_begin, k_end, stream);
+  return rc ? rc : dzb_tm_maxwell_range(mm, mui, sigma, e, y, k_begin2, k_end2, stream);
 }
 
 extern "C" int dzb_tm_maxwell_range(const DzbTensorMesh *mm, const double *mui, const double *sigma, const double *e,
@@ -303,17 +300,16 @@ extern "C" int dzb_tm_maxwell_range(const DzbTensorMesh *mm, const double *mui, 
   cudaStream_t s = (cudaStream_t)stream;
   const bool ring_ok = m.ny >= 1 && (m.nx + 1) * (m.ny + 1) < ((i64)1 << 31);
   if (g_mx_variant == 3 && ring_ok) {
-    if (launch_m3(m, mui, sigma, e, y, (int)k_begin, (int)k_end, s) == 0) return check_launch("dzb_tm_maxwell");
+    g_mx_last_path = 3;
+    if (launch_m3(m, mui, sigma, e, y, (int)k_begin, (int)k_end, 0, 0, s) == 0) return check_launch("dzb_tm_maxwell");
     cudaGetLastError();
   }
   if (g_mx_variant >= 2 && ring_ok) {
+    g_mx_last_path = 2;
     if (launch_m2(m, mui, sigma, e, y, (int)k_begin, (int)k_end, s) == 0) return check_launch("dzb_tm_maxwell");
     cudaGetLastError();
   }
-  if (g_mx_variant >= 1 && ring_ok) {
-    if (launch_mx_ring(m, mui, sigma, e, y, (int)k_begin, (int)k_end, s) == 0) return check_launch("dzb_tm_maxwell");
-    cudaGetLastError();
-  }
+  g_mx_last_path = 0;
   if (k_begin != 0 || k_end != m.nz + 1) {
     set_error("dzb_tm_maxwell_range: the gather variant only supports the full plane range");
     return -1;

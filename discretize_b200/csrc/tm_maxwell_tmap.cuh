@@ -14,8 +14,10 @@
 // parity of J0 (derivation in DESIGN.md).  Every array is one 2-D matrix of
 // (rows per plane x planes) rows, because planes follow each other without padding.
 //
-// Used when all five base addresses are 16-byte aligned and every odd-pitch array has an even number of rows (true for
-// every even-sized mesh, e.g. all BASELINE configs); otherwise the launcher falls back to the bulk-copy ring.
+// Two maps per odd-pitch array keep every read inside the array: one over its even rows only (width = one row, row
+// stride = two rows) and one over the super-rows, from which the boxes take the odd rows.  Used when the five base
+// addresses are 16-byte aligned (e.g. nx and ny even: all BASELINE configs and their z-slabs); otherwise the launcher
+// falls back to the bulk-copy ring.
 // The arithmetic, the mailboxes and the halo warps are those of tm_maxwell_rows.cuh (see there for the formulas).
 #pragma once
 #include <cuda.h>
@@ -65,12 +67,14 @@ template <int XS, int R, int PARX, int NSLOT> struct Mx3 {
 };
 
 struct M3Maps {
-  CUtensorMap m[5];
+  CUtensorMap m[5];   // whole array (even pitch) or its even rows (odd pitch)
+  CUtensorMap o[5];   // odd pitch: super-rows, used for the odd rows
 };
 
 template <int XS, int R, int PARX, int NSLOT, int MINB>
 __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
-    k_maxwell_tmap(TM m, const __grid_constant__ M3Maps maps, double *__restrict__ y, int kchunk, int k_begin, int k_end) {
+    k_maxwell_tmap(TM m, const __grid_constant__ M3Maps maps, double *__restrict__ y, int kchunk, int k_begin, int k_end,
+                   int nzb0, int k_begin2, int k_end2) {
   typedef Mx3<XS, R, PARX, NSLOT> G;
   constexpr int S = NSLOT, W = G::W;
   static_assert(S % 2 == 0, "the row-parity bookkeeping assumes an even ring depth");
@@ -92,8 +96,11 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
   const int j0 = blockIdx.y * R;
   const int Xb = blockIdx.x * (XS * M3_XOUT);
-  const int kb = k_begin + blockIdx.z * kchunk;     // output planes kb .. ke-1 (layers kb .. min(ke, nz)-1)
-  const int ke = min(kb + kchunk, k_end);
+  // blocks z < nzb0 serve the plane range [k_begin, k_end), the others a second range [k_begin2, k_end2) (the two
+  // boundary planes of a z-slab in one launch)
+  const bool second = (int)blockIdx.z >= nzb0;
+  const int kb = second ? k_begin2 + ((int)blockIdx.z - nzb0) * kchunk : k_begin + (int)blockIdx.z * kchunk;
+  const int ke = min(kb + kchunk, second ? k_end2 : k_end);   // output planes kb .. ke-1 (layers kb .. min(ke, nz)-1)
   const int jfirst = kb - 2;                        // stage q holds ex, ey on plane jfirst+q+1 and ez, mui, sigma on layer jfirst+q
   const int nq = ke - jfirst;
 
@@ -122,7 +129,10 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
     // ================= producer warp: one elected lane, <= 7 box copies per stage =================
     if (lane == 0) {
 #pragma unroll
-      for (int a = 0; a < 5; ++a) tmap_prefetch(&maps.m[a]);
+      for (int a = 0; a < 5; ++a) {
+        tmap_prefetch(&maps.m[a]);
+        if (G::odd(a)) tmap_prefetch(&maps.o[a]);
+      }
       const int npl[5] = {nNz, nNz, nz, nz, nz};
       const int gp[5] = {nx, nNx, nNx, nx, nx};
       for (int q = 0; q < nq; ++q) {
@@ -148,7 +158,7 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
               // even for the rr of parity t = J0 & 1, so the even-row box goes to sub-tile t and the odd-row box to 1 - t
               const int t = J0 & 1;
               tmap_load_2d(T + G::off(a) + t * G::sub(a), &maps.m[a], (Xb - 1) & ~1, (J0 + 1) >> 1, &full[slot]);
-              tmap_load_2d(T + G::off(a) + (t ^ 1) * G::sub(a), &maps.m[a], (gp[a] + Xb - 1) & ~1, J0 >> 1, &full[slot]);
+              tmap_load_2d(T + G::off(a) + (t ^ 1) * G::sub(a), &maps.o[a], (gp[a] + Xb - 1) & ~1, J0 >> 1, &full[slot]);
             } else {
               tmap_load_2d(T + G::off(a), &maps.m[a], (Xb - 1) & ~1, J0, &full[slot]);
             }

@@ -290,7 +290,7 @@ class SlabMaxwell(_GraphedStep):
         self.op = Cm.T @ self.mesh.get_face_inner_product(self.mui) @ Cm + self.mesh.get_edge_inner_product(self.sigma)
         assert type(self.op).__name__ == "MaxwellOperator"
         self.comm_stream = torch.cuda.Stream(device=dev)
-        self.launches_per_step = 3 if world > 1 else 1
+        self.launches_per_step = 2 if world > 1 else 1
         self.n_owned_edges = ((L.p_own1 - L.p_own0) * (es.px + es.py) + n_own_layers * es.pz)
 
     def step(self):
@@ -308,10 +308,11 @@ class SlabMaxwell(_GraphedStep):
         if hi > lo:
             op.apply_planes(self.e, self.out, lo, hi)
         main.wait_stream(self.comm_stream)
-        if L.has_lower and lo > L.p_own0:
-            op.apply_planes(self.e, self.out, L.p_own0, min(lo, L.p_own1))
-        if L.has_upper and hi < L.p_own1 and hi >= lo:
-            op.apply_planes(self.e, self.out, max(hi, lo), L.p_own1)
+        # the planes next to a halo, once it has arrived: both ends in ONE launch
+        a0, a1 = (L.p_own0, min(lo, L.p_own1)) if (L.has_lower and lo > L.p_own0) else (0, 0)
+        b0, b1 = (max(hi, lo), L.p_own1) if (L.has_upper and hi < L.p_own1 and hi >= lo) else (0, 0)
+        if a1 > a0 or b1 > b0:
+            op.apply_planes2(self.e, self.out, a0, a1, b0, b1)
         return self.out
 
     def owned_parts(self, v):
@@ -321,3 +322,89 @@ class SlabMaxwell(_GraphedStep):
         return (v[L.p_own0 * es.px:L.p_own1 * es.px],
                 v[es.off_y + L.p_own0 * es.py:es.off_y + L.p_own1 * es.py],
                 v[es.off_z + L.p_own0 * es.pz:es.off_z + (L.p_own0 + n_own_layers) * es.pz])
+
+    # --- end to end from / to pinned host memory ------------------------------------------------------------
+    def owned_sizes(self):
+        """Lengths of the three owned parts (Ex planes, Ey planes, Ez layers) -- the layout of the host buffers."""
+        L, es = self.layout, self.es
+        npl, nly = L.p_own1 - L.p_own0, L.c1 - L.c0
+        return npl * es.px, npl * es.py, nly * es.pz
+
+    def step_from_host(self, host_in, host_out, nchunks=16):
+        """One distributed apply with this rank's owned edges in PINNED HOST memory.
+
+        ``host_in`` / ``host_out`` hold ``[Ex owned planes | Ey owned planes | Ez owned layers]`` (``owned_sizes``).  The
+        planes the neighbours need go up first so that the halo exchange can start, then z-chunks stream through:
+        H2D of chunk c+1, the fused kernel on chunk c and D2H of chunk c-1 overlap (PCIe is full duplex)."""
+        L, op, es = self.layout, self.op, self.es
+        if getattr(self, "_host_streams", None) is None:
+            dev = self.e.device
+            self._host_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        s_in, s_out = self._host_streams
+        main = torch.cuda.current_stream()
+        o0, o1 = L.p_own0, L.p_own1
+        nly = L.c1 - L.c0                       # owned Ez layers: local layers o0 .. o0 + nly - 1
+        sx, sy, _ = self.owned_sizes()
+        hx_in, hy_in, hz_in = host_in[:sx], host_in[sx:sx + sy], host_in[sx + sy:]
+        hx_out, hy_out, hz_out = host_out[:sx], host_out[sx:sx + sy], host_out[sx + sy:]
+        nchunks = max(1, min(nchunks, o1 - o0))
+        cuts = [o0 + round(c * (o1 - o0) / nchunks) for c in range(nchunks + 1)]
+
+        def h2d(a, b):   # local node planes [a, b) of Ex, Ey and cell layers [a, min(b, top)) of Ez
+            self.e[a * es.px:b * es.px].copy_(hx_in[(a - o0) * es.px:(b - o0) * es.px], non_blocking=True)
+            self.e[es.off_y + a * es.py:es.off_y + b * es.py].copy_(hy_in[(a - o0) * es.py:(b - o0) * es.py], non_blocking=True)
+            bz = min(b, o0 + nly)
+            if bz > a:
+                self.e[es.off_z + a * es.pz:es.off_z + bz * es.pz].copy_(hz_in[(a - o0) * es.pz:(bz - o0) * es.pz],
+                                                                          non_blocking=True)
+
+        def d2h(a, b):
+            hx_out[(a - o0) * es.px:(b - o0) * es.px].copy_(self.out[a * es.px:b * es.px], non_blocking=True)
+            hy_out[(a - o0) * es.py:(b - o0) * es.py].copy_(self.out[es.off_y + a * es.py:es.off_y + b * es.py], non_blocking=True)
+            bz = min(b, o0 + nly)
+            if bz > a:
+                hz_out[(a - o0) * es.pz:(bz - o0) * es.pz].copy_(self.out[es.off_z + a * es.pz:es.off_z + bz * es.pz],
+                                                                  non_blocking=True)
+
+        s_in.wait_stream(main)
+        copied = []
+        with torch.cuda.stream(s_in):
+            if L.world > 1:
+                h2d(o0, o0 + 1)
+                if o1 - 1 > o0:
+                    h2d(o1 - 1, o1)
+                edge = torch.cuda.Event()
+                edge.record(s_in)
+        if L.world > 1:
+            self.comm_stream.wait_event(edge)
+            with torch.cuda.stream(self.comm_stream):
+                for r in exchange_edge_halos(self.e, L, es):
+                    r.wait()
+        with torch.cuda.stream(s_in):
+            for c in range(nchunks):
+                h2d(cuts[c], cuts[c + 1])
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+                copied.append(ev)
+        s_out.wait_stream(main)
+        for c in range(nchunks):
+            main.wait_event(copied[min(c + 1, nchunks - 1)])     # chunk c reads the first plane of chunk c + 1
+            if L.world > 1 and (c == 0 or c == nchunks - 1):
+                main.wait_stream(self.comm_stream)               # the halo planes border the first / last chunk
+            op.apply_planes(self.e, self.out, cuts[c], cuts[c + 1])
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                d2h(cuts[c], cuts[c + 1])
+        main.wait_stream(s_out)
+        return host_out
+
+    def owned_to_host(self, v, host):
+        """Copy the owned parts of a local edge vector into a host buffer laid out like ``owned_sizes``."""
+        sx, sy, _ = self.owned_sizes()
+        px, py, pz = self.owned_parts(v)
+        host[:sx].copy_(px)
+        host[sx:sx + sy].copy_(py)
+        host[sx + sy:].copy_(pz)
+        return host

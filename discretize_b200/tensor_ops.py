@@ -483,6 +483,67 @@ class MaxwellOperator(Operator):
         check(load().dzb_tm_maxwell_range(C.byref(self.mesh.device_mesh()), ptr(self.mui), ptr(self.sigma), ptr(x),
                                           ptr(out), int(k_begin), int(k_end), stream_ptr()), "dzb_tm_maxwell_range")
 
+    def apply_planes2(self, x, out, a0, a1, b0, b1):
+        """Two disjoint plane ranges [a0, a1) and [b0, b1) in one launch (the boundary planes of a z-slab)."""
+        check(load().dzb_tm_maxwell_range2(C.byref(self.mesh.device_mesh()), ptr(self.mui), ptr(self.sigma), ptr(x),
+                                           ptr(out), int(a0), int(a1), int(b0), int(b1), stream_ptr()),
+              "dzb_tm_maxwell_range2")
+
+    def matvec(self, x, out=None):
+        # pinned host input: stream z-chunks (H2D of chunk c+1, kernel on chunk c, D2H of chunk c-1 overlap)
+        if isinstance(x, torch.Tensor) and x.device.type == "cpu" and x.ndim == 1 and x.is_pinned():
+            return self._matvec_streamed(x, out)
+        return super().matvec(x, out)
+
+    rmatvec = matvec
+
+    def _matvec_streamed(self, x, out, nchunks=32):
+        n = self.shape[0]
+        if x.numel() != n:
+            raise ValueError(f"dimension mismatch: operator {self.shape}, input {tuple(x.shape)}")
+        dev = cuda_device()
+        nx, ny, nz = self.mesh.shape_cells
+        px, py, pz = nx * (ny + 1), (nx + 1) * ny, (nx + 1) * (ny + 1)     # Ex, Ey entries per node plane, Ez per layer
+        off_y, off_z = px * (nz + 1), px * (nz + 1) + py * (nz + 1)
+        if out is None:
+            out = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        if getattr(self, "_stage", None) is None or self._stage[0].device != dev:
+            self._stage = (torch.empty(n, dtype=torch.float64, device=dev), torch.empty(n, dtype=torch.float64, device=dev),
+                           torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        xd, yd, s_in, s_out = self._stage
+        main = torch.cuda.current_stream()
+        nchunks = max(1, min(nchunks, nz + 1))
+        cuts = [round(c * (nz + 1) / nchunks) for c in range(nchunks + 1)]
+
+        def segments(a, b):   # node planes [a, b) of Ex and Ey, cell layers [a, min(b, nz)) of Ez
+            segs = [(a * px, b * px), (off_y + a * py, off_y + b * py)]
+            if min(b, nz) > a:
+                segs.append((off_z + a * pz, off_z + min(b, nz) * pz))
+            return segs
+
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        copied = []
+        with torch.cuda.stream(s_in):
+            for c in range(nchunks):
+                for lo, hi in segments(cuts[c], cuts[c + 1]):
+                    xd[lo:hi].copy_(x[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+                copied.append(ev)
+        for c in range(nchunks):
+            main.wait_event(copied[min(c + 1, nchunks - 1)])   # chunk c needs the first plane of chunk c+1
+            self.apply_planes(xd, yd, cuts[c], cuts[c + 1])
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                for lo, hi in segments(cuts[c], cuts[c + 1]):
+                    out[lo:hi].copy_(yd[lo:hi], non_blocking=True)
+        main.wait_stream(s_out)
+        main.synchronize()
+        return out
+
     def _transpose(self):
         return self
 

@@ -169,10 +169,13 @@ int dzb_tm_dc_cell_mi(const DzbTensorMesh *m, const double *mi, int flags, const
 int dzb_tm_maxwell(const DzbTensorMesh *m, const double *mui, const double *sigma, const double *e, double *y,
                    void *stream);
 /* Same, writing only what lives on node planes / cell layers k_begin <= k < k_end (Ex, Ey on planes k,
- * Ez in layers k < nz): the z-slab building block, like dzb_tm_dc_nodal_range.  The 8 bytes following
- * e, mui and sigma must be readable. */
+ * Ez in layers k < nz): the z-slab building block, like dzb_tm_dc_nodal_range.  Nothing outside
+ * e[0, nE), mui[0, nC), sigma[0, nC) is read. */
 int dzb_tm_maxwell_range(const DzbTensorMesh *m, const double *mui, const double *sigma, const double *e, double *y,
                          int64_t k_begin, int64_t k_end, void *stream);
+/* Two disjoint plane ranges in one launch: the two boundary planes of a z-slab once its halos have arrived. */
+int dzb_tm_maxwell_range2(const DzbTensorMesh *m, const double *mui, const double *sigma, const double *e, double *y,
+                          int64_t k_begin, int64_t k_end, int64_t k_begin2, int64_t k_end2, void *stream);
 
 /* ---- interpolation: get_interpolation_matrix --------------------------------- */
 /* base/base_tensor_mesh.py:684-790 -> utils/interpolation_utils.py:44-172 ->

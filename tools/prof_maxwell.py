@@ -24,16 +24,12 @@ out = torch.empty(mesh.nE, dtype=torch.float64, device=dev)
 lib = load()
 lib.dzb_tune_maxwell.argtypes = [ctypes.c_int, ctypes.c_int]
 lib.dzb_tune_maxwell.restype = None
-lib.dzb_tune_maxwell_warps.argtypes = [ctypes.c_int]
-lib.dzb_tune_maxwell_warps.restype = None
 lib.dzb_tune_maxwell_rows.argtypes = [ctypes.c_int] * 4
 lib.dzb_tune_maxwell_rows.restype = None
 lib.dzb_tune_maxwell(variant, kc)
 lib.dzb_tune_maxwell_tmap.argtypes = [ctypes.c_int] * 3
 lib.dzb_tune_maxwell_tmap.restype = None
-if variant == 1:
-    lib.dzb_tune_maxwell_warps(a)
-elif variant == 2:
+if variant == 2:
     lib.dzb_tune_maxwell_rows(a, b, ns, np_)
 else:
     lib.dzb_tune_maxwell_tmap(a, b, ns)

@@ -1,7 +1,7 @@
 """Tuning sweep for the fused Maxwell kernel (K9): variant / block shape / z-chunk.
 
-variant 1 = first TMA ring (two rows + a recomputed halo row per lane), variant 2 = row-per-warp ring with mailboxes.
-  python tools/sweep_maxwell.py [n] [v1|v2|all]
+variant 2 = row-per-warp ring fed by row-wise bulk copies, variant 3 = the same ring fed by tensor-map TMA.
+  python tools/sweep_maxwell.py [n] [v2|v3|all] [debug mode]
 """
 import ctypes
 import os
@@ -27,8 +27,6 @@ out = torch.empty(mesh.nE, dtype=torch.float64, device=dev)
 lib = load()
 lib.dzb_tune_maxwell.argtypes = [ctypes.c_int, ctypes.c_int]
 lib.dzb_tune_maxwell.restype = None
-lib.dzb_tune_maxwell_warps.argtypes = [ctypes.c_int]
-lib.dzb_tune_maxwell_warps.restype = None
 lib.dzb_tune_maxwell_rows.argtypes = [ctypes.c_int] * 4
 lib.dzb_tune_maxwell_rows.restype = None
 lib.dzb_tune_maxwell_debug.argtypes = [ctypes.c_int]
@@ -37,13 +35,11 @@ lib.dzb_tune_maxwell_debug(dbg)
 alg = 8.0 * (2 * mesh.nE + 2 * mesh.nC)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 cases = []
-# reference result from the first ring kernel (variant 1), which the test-suite pins against the oracle
-lib.dzb_tune_maxwell(1, 64)
-ref = torch.empty_like(out)
-A.apply_device(e, out=ref)
+# reference result: the elementary chain C^T (Mf (C e)) + Me e (separate kernels, pinned against the oracle by the tests)
+Mf, Me = mesh.get_face_inner_product(mui), mesh.get_edge_inner_product(sig)
+ref = C.T.apply_device(Mf.apply_device(C.apply_device(e)))
+ref += Me.apply_device(e)
 torch.cuda.synchronize()
-if which in ("v1", "all"):
-    cases += [(1, 9, 0, 128 if n > 512 else 64)]
 if which in ("v2", "all"):
     shapes = ((2, 4, 4, 1), (2, 4, 4, 2), (2, 4, 4, 4), (2, 4, 6, 1), (2, 4, 6, 2), (4, 2, 4, 1), (4, 2, 4, 2), (4, 2, 4, 4),
               (4, 4, 4, 2), (4, 4, 4, 4), (4, 4, 6, 4), (1, 8, 4, 2))
@@ -56,9 +52,7 @@ if which in ("v3", "all"):
     cases += [(3, sh, 0, 0) for sh in shapes3]
 for variant, a, b, kc in cases:
     lib.dzb_tune_maxwell(variant, kc)
-    if variant == 1:
-        lib.dzb_tune_maxwell_warps(a)
-    elif variant == 2:
+    if variant == 2:
         lib.dzb_tune_maxwell_rows(*a)
     else:
         lib.dzb_tune_maxwell_tmap(*a)
