@@ -76,7 +76,10 @@ __global__ void __launch_bounds__(SOLVER_THREADS)
                 const double *__restrict__ Ap, const double *__restrict__ dinv, double *z,
                 double *partials, unsigned *ticket, double *scal) {
   __shared__ double smem[SOLVER_THREADS / 32];
-  const double alpha = scal[0] / scal[1];
+  // breakdown guard: once r.z or p.Ap is zero (exact solution reached inside a blind window of iterations, or an
+  // underflow) the update becomes a no-op instead of 0/0 = NaN poisoning x, r and p
+  const double rz0 = scal[0], pAp = scal[1];
+  const double alpha = (rz0 == 0.0 || pAp == 0.0) ? 0.0 : rz0 / pAp;
   double rz = 0.0, rr = 0.0;
   const i64 stride = (i64)gridDim.x * SOLVER_THREADS;
   for (i64 t = (i64)blockIdx.x * SOLVER_THREADS + threadIdx.x; t < n; t += stride) {
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS)
 // beta = scal[2] / scal[0];  p = z + beta p;  then scal[0] = scal[2]
 __global__ void __launch_bounds__(SOLVER_THREADS)
     k_cg_direction(i64 n, double *__restrict__ p, const double *__restrict__ z, double *scal, unsigned *ticket) {
-  const double beta = scal[2] / scal[0];
+  const double beta = scal[0] == 0.0 ? 0.0 : scal[2] / scal[0];   // converged: keep p finite (see k_cg_update)
   const i64 stride = (i64)gridDim.x * SOLVER_THREADS;
   for (i64 t = (i64)blockIdx.x * SOLVER_THREADS + threadIdx.x; t < n; t += stride) p[t] = __ldg(z + t) + beta * p[t];
   // every block has read scal[0] before the last one overwrites it

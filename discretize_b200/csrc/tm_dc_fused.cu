@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(DC_WARPS * 32, MINB)
 // pitch, every row of a stage lands at  base + lead + r*pitch + c  with ONE lead bit per stage.
 // Rows / planes outside the mesh are not copied at all: the tiles are zero-initialised, hold only
 // finite values, and everything outside the mesh is multiplied by a zero cell measure.
-// Requirement (dzb.h): the 8 bytes following the last element of phi / sigma are readable.
+// The copies never leave the arrays: where an array starts / ends on an odd element address, the one element a 16-byte
+// aligned copy cannot reach is staged by a plain load + shared store of the producer lane (bulk_pipe.cuh: plan_row_copy).
 // ---------------------------------------------------------------------------------------------
 constexpr int DC_SLOTS = 4;       // ring depth: stage j-1 and j in use, j+1 and j+2 in flight
 constexpr int DC_MAXCHUNK = 128;  // max z-planes per block (size of the hz table)
@@ -287,8 +288,9 @@ __global__ void __launch_bounds__((NWC + 1) * 32, 1)
       const bool row_ok = have && jr >= 0 && jr < (isp ? nNy : ny);
       const long long a0 = isp ? pa0 : ca0, pstr = isp ? pstride : cstride;
       const long long rowbase = a0 + (long long)r * (isp ? nNx : nx);
-      const long long aend = isp ? ((((long long)((unsigned long long)phi >> 3) + pstride * nNz) + 1) & ~1ll)
-                                 : ((((long long)((unsigned long long)sigma >> 3) + cstride * nz) + 1) & ~1ll);
+      // exact extent of the array this lane copies from: nothing outside [abeg, aend) is ever read (plan_row_copy)
+      const long long abeg = isp ? (long long)((unsigned long long)phi >> 3) : (long long)((unsigned long long)sigma >> 3);
+      const long long aend = abeg + (isp ? pstride * nNz : cstride * nz);
       const int ncol = nwc * DC_XOUT + (isp ? 2 : 1);
       const int npl = isp ? nNz : nz, ploff = isp ? 1 : 0;
       const int soff = (isp ? 0 : G::REGP) + 2 + r * (isp ? PP : CP);
@@ -297,18 +299,25 @@ __global__ void __launch_bounds__((NWC + 1) * 32, 1)
         if (n >= 1) mbar_wait(&empty[slot], (n - 1) & 1);
         const int pl = jst + ploff;
         const bool on = row_ok && pl >= 0 && pl < npl;
-        const long long Ad = rowbase + pstr * pl, Aal = Ad & ~1ll;
-        long long nel = ((Ad - Aal) + ncol + 1) & ~1ll;
-        nel = min(nel, aend - Aal);
-        const unsigned bytes = on ? (unsigned)(nel * 8) : 0u;
-        const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
+        const long long lo = rowbase + pstr * pl;
+        RowCopy rc = plan_row_copy(lo, lo + ncol, abeg, aend);
+        if (!on) {
+          rc.bytes = 0;
+          rc.head = rc.tail = false;
+        }
+        double *T = tiles + slot * G::STAGE;
+        const int dst0 = soff + (int)((a0 + pstr * pl) & 1);   // element lo lands here: one lead bit per stage
+        const unsigned total = __reduce_add_sync(0xffffffffu, rc.bytes);
+        if (__any_sync(0xffffffffu, rc.head | rc.tail)) {   // only the rows that hold the first / last element of an odd-aligned array
+          if (rc.head) T[dst0] = *reinterpret_cast<const double *>(lo << 3);
+          if (rc.tail) T[dst0 + (int)(rc.hi - 1 - lo)] = *reinterpret_cast<const double *>((rc.hi - 1) << 3);
+          fence_proxy_async_smem();
+        }
+        __syncwarp();
         if (lane == 0) mbar_arrive_expect_tx(&full[slot], total);
         __syncwarp();
-        if (bytes) {
-          const int lead0 = (int)((a0 + pstr * pl) & 1);
-          bulk_g2s(tiles + slot * G::STAGE + soff + lead0 - (int)(Ad - Aal), reinterpret_cast<const void *>(Aal << 3),
-                   bytes, &full[slot]);
-        }
+        if (rc.bytes)
+          bulk_g2s(T + dst0 + (int)(rc.tlo - lo), reinterpret_cast<const void *>(rc.tlo << 3), rc.bytes, &full[slot]);
       }
     }
     return;
@@ -414,13 +423,10 @@ template <int RY, int NWC, int PARX>
 static int launch_dc_ring_t(const TM &m, const double *sigma, const double *phi, double *y, int kchunk, int xblocks,
                             int nwc, int k_begin, int k_end, cudaStream_t s) {
   typedef DcRing<RY, NWC, PARX> G;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(k_dc_nodal_ring<RY, NWC, PARX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)G::SMEM) != cudaSuccess)
-      return -1;
-    attr_done = true;
-  }
+  // the attribute is per device (a process may drive several GPUs); setting it is cheap, so no process-wide flag
+  if (cudaFuncSetAttribute(k_dc_nodal_ring<RY, NWC, PARX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)G::SMEM) != cudaSuccess)
+    return -1;
   const int nNy = (int)m.ny + 1;
   // short plane ranges (z-slabs on many GPUs): shrink the z-chunk until the grid has ~4 waves of blocks
   const int nxy = xblocks * ((nNy + RY - 1) / RY);

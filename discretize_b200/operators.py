@@ -112,13 +112,33 @@ class Operator(LinearOperator):
         (self._dev_apply_t if transpose else self._dev_apply)(x, out)
         return out
 
+    @staticmethod
+    def _check_out(out, n_out, x):
+        """``out`` receives raw 8-byte writes: it must be float64, contiguous, of the right length and of x's kind."""
+        if isinstance(out, torch.Tensor):
+            if not isinstance(x, torch.Tensor) or out.device.type != x.device.type:
+                raise TypeError("out must be the same kind of array as x (numpy / CPU tensor / CUDA tensor)")
+            ok = out.dtype == torch.float64 and out.is_contiguous() and out.numel() == n_out
+        elif isinstance(out, np.ndarray):
+            if isinstance(x, torch.Tensor):
+                raise TypeError("out must be the same kind of array as x (numpy / CPU tensor / CUDA tensor)")
+            ok = out.dtype == np.float64 and out.flags.c_contiguous and out.size == n_out and out.flags.writeable
+        else:
+            raise TypeError("out must be a numpy array or a torch tensor")
+        if not ok:
+            raise ValueError(f"out must be a contiguous float64 array with {n_out} entries")
+
     def _apply_any(self, x, transpose, out=None):
         n_in = self.shape[0] if transpose else self.shape[1]
         is_torch = isinstance(x, torch.Tensor)
         if not is_torch:
             x = np.asarray(x)
             if np.iscomplexobj(x):
+                if out is not None:
+                    raise TypeError("out is not supported for complex input (the result is a new complex array)")
                 return self._apply_any(x.real, transpose) + 1j * self._apply_any(x.imag, transpose)
+        if out is not None:
+            self._check_out(out, self.shape[1] if transpose else self.shape[0], x)
         if x.ndim == 1 or (x.ndim == 2 and x.shape[1] == 1 and x.shape[0] == n_in):
             if x.shape[0] != n_in:
                 raise ValueError(f"dimension mismatch: operator {self.shape}, input {tuple(x.shape)}")

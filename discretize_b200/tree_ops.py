@@ -26,6 +26,29 @@ def _unique_small(values):
         cand = np.unique(np.r_[cand, np.unique(values[miss])])
 
 
+class CodeTableOverflow(ValueError):
+    """More distinct (multiplier, selector) pairs than a code byte can name: the caller stores the values instead."""
+
+
+MAX_CODES = 255          # code 255 marks the padding slots of the ELL layout
+
+
+def _group_values(data):
+    """(table values, code per entry) for the multipliers of one operator part.
+
+    The table holds EXACT entries of the matrix.  Values that differ by a rounding error only (1/6 computed along two
+    paths) share a code: neighbours of the sorted distinct values are merged when they agree to 1e-15 relative, and the
+    smaller one represents the group -- so the applied values are within 1e-15 of the reference's, not within the 2e-14
+    an absolute np.round(., 14) used to leave, and tiny values are not rounded away."""
+    vals, inv = _unique_small(np.asarray(data, dtype=np.float64))
+    if vals.size <= 1:
+        return vals, inv
+    gap = np.abs(np.diff(vals)) > 1e-15 * np.maximum(np.abs(vals[:-1]), np.abs(vals[1:]))
+    group = np.r_[0, np.cumsum(gap)]                      # group id of every distinct value (sorted)
+    rep = vals[np.r_[True, gap]]                          # first (smallest) member represents its group
+    return rep, group[inv]
+
+
 def encode_parts_raw(geoms, parts, shape):
     """Like ``encode_parts`` for parts that hold DUPLICATE (row, column) pairs on purpose (ghost columns redirected by
     ``tree_shard``): entries are concatenated row by row, never summed."""
@@ -33,15 +56,15 @@ def encode_parts_raw(geoms, parts, shape):
     rows, cols, codes = [], [], []
     for s_, M in parts:
         M = sp.csr_matrix(M)
-        vals, inv = _unique_small(np.round(M.data, 14))
+        vals, inv = _group_values(M.data)
         base = len(tab_mult)
         tab_mult.extend(vals.tolist())
         tab_sel.extend([s_] * vals.size)
+        if len(tab_mult) > MAX_CODES:
+            raise CodeTableOverflow(f"operator needs more than {MAX_CODES} distinct (multiplier, selector) pairs")
         rows.append(np.repeat(np.arange(M.shape[0]), np.diff(M.indptr)))
         cols.append(M.indices)
         codes.append(inv + base)
-    if len(tab_mult) > 256:
-        raise ValueError(f"operator needs {len(tab_mult)} distinct (multiplier, selector) pairs; the code byte holds 256")
     rows, cols, codes = np.concatenate(rows), np.concatenate(cols), np.concatenate(codes)
     order = np.lexsort((cols, rows))
     indptr = np.r_[0, np.cumsum(np.bincount(rows, minlength=shape[0]))].astype(np.int64)
@@ -59,14 +82,14 @@ def encode_parts(geoms, parts, shape):
     acc = None
     for s_, M in parts:
         M = sp.csr_matrix(M)
-        vals, inv = _unique_small(np.round(M.data, 14))
+        vals, inv = _group_values(M.data)
         base = len(tab_mult)
         tab_mult.extend(vals.tolist())
         tab_sel.extend([s_] * vals.size)
+        if len(tab_mult) > MAX_CODES:
+            raise CodeTableOverflow(f"operator needs more than {MAX_CODES} distinct (multiplier, selector) pairs")
         code_m = sp.csr_matrix(((inv + base + 1).astype(np.float64), M.indices, M.indptr), shape=M.shape)
         acc = code_m if acc is None else acc + code_m
-    if len(tab_mult) > 256:
-        raise ValueError(f"operator needs {len(tab_mult)} distinct (multiplier, selector) pairs; the code byte holds 256")
     acc = sp.csr_matrix(acc)
     if acc.nnz != sum(sp.csr_matrix(M).nnz for _, M in parts):
         raise ValueError("operator parts overlap; cannot encode one code per entry")
@@ -159,6 +182,22 @@ class CodedCsr:
         return 8 * (self.shape[0] + self.shape[1]) + 5 * self.nnz + ptr_bytes + 8 * gsize   # padding slots not counted
 
 
+class _StoredCsr:
+    """Stored-value fallback with the interface TreeOperator needs of a CodedCsr."""
+
+    layout = "stored"
+
+    def __init__(self, dev_csr):
+        self.m = dev_csr
+        self.shape, self.nnz = dev_csr.shape, dev_csr.nnz
+
+    def apply(self, x, out):
+        self.m.apply(x, out)
+
+    def bytes_per_apply(self):
+        return 8 * (self.shape[0] + self.shape[1]) + 12 * self.nnz + 4 * (self.shape[0] + 1)
+
+
 class TreeOperator(Operator):
     """A deflated OcTree operator (reference: tree_ext.pyx:3114-4762), applied by tree_spmv."""
 
@@ -179,7 +218,15 @@ class TreeOperator(Operator):
                 shape = (self._fwd_shape[1], self._fwd_shape[0])
             else:
                 shape = self._fwd_shape
-            self._dev[key] = CodedCsr(geoms, parts, shape, geom_by_col=transposed)
+            try:
+                self._dev[key] = CodedCsr(geoms, parts, shape, geom_by_col=transposed)
+            except CodeTableOverflow:
+                # geometry-dependent weights (the distance weights of average_cell_to_face on non-uniform base widths):
+                # apply the reference's matrix with stored values, 12 B per entry instead of 5
+                from .csr import _DeviceCsr
+
+                M = self.mesh._host_matrix(self.name)
+                self._dev[key] = _StoredCsr(_DeviceCsr(M.T.tocsr() if transposed else M))
         return self._dev[key]
 
     def _dev_apply(self, x, out):

@@ -143,8 +143,9 @@ int dzb_tm_mass_deriv_apply(const DzbTensorMesh *m, int flags, int model_kind, c
 /* ---- fused composites -------------------------------------------------------- */
 /* y = G^T Me(sigma) G phi  (DC resistivity, nodal; tutorials/pde/3_nodal_dirichlet_poisson.py:146-160):
  * nodal_gradient (:658-664) + get_edge_inner_product (isotropic sigma, nC) in ONE kernel.
- * The 8 bytes following the last element of phi and of sigma must be readable (true for any
- * CUDA allocation; the kernel stages rows with 16-byte bulk copies). */
+ * phi and sigma only need their natural 8-byte alignment and nothing outside phi[0, nN) / sigma[0, nC) is read
+ * (rows are staged with 16-byte bulk copies that stop at the aligned bounds inside the arrays; the at most
+ * one element left at an odd-aligned end is staged by a plain load). */
 int dzb_tm_dc_nodal(const DzbTensorMesh *m, const double *sigma, const double *phi, double *y, void *stream);
 /* Same, writing only the node planes k_begin <= k < k_end of y (0 <= k <= nz).  This is the
  * building block of the z-slab decomposition: a rank applies it to its local sub-mesh (its cell

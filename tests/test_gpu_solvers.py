@@ -122,3 +122,21 @@ def test_pcg_cell_centred_dc_on_octree():
     x, info = pcg(A, b, inv_diag=1.0 / Ah.diagonal(), rtol=1e-11, maxiter=4000, check_every=20)
     assert info.converged, info
     assert_close_vec(x.cpu().numpy(), sla.spsolve(Ah, b), 1e-8)
+
+
+def test_pcg_survives_convergence_inside_a_blind_window():
+    """A diagonal system with the exact Jacobi preconditioner converges in ONE iteration; the remaining iterations of the
+    check_every window then see r.z = p.Ap = 0 and must be no-ops instead of 0/0 (NaN solution)."""
+    from discretize_b200.solvers import pcg
+
+    mesh, grid = make_pair("wide")
+    rng = np.random.default_rng(8)
+    sig = np.exp(rng.standard_normal(mesh.nC))
+    Me = mesh.get_edge_inner_product(sig)
+    d = T.inner_product(grid, "E", sig).diagonal()
+    b = rng.standard_normal(mesh.nE)
+    for x0 in (None, b / d):                      # cold start and an exact initial guess
+        x, info = pcg(Me, b, x0=x0, inv_diag=1.0 / d, rtol=1e-12, maxiter=40, check_every=10)
+        xs = x.cpu().numpy()
+        assert np.isfinite(xs).all() and info.converged
+        assert_close_vec(xs, b / d)

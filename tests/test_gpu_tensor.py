@@ -352,6 +352,80 @@ def test_maxwell_fused(mesh_name):
     assert_same_matrix(A.tocsr(), ref)
 
 
+def _guarded(values, lead, dev):
+    """A CUDA view that starts `lead` elements into a buffer whose every other entry is NaN: a kernel that reads even one
+    element before or after its arrays (or multiplies such an element by zero) turns the result into NaN."""
+    buf = torch.full((values.size + lead + 3,), float("nan"), dtype=torch.float64, device=dev)
+    view = buf[lead:lead + values.size]
+    view.copy_(torch.as_tensor(values))
+    return view
+
+
+@pytest.mark.parametrize("lead", [0, 1, 2, 3])
+@pytest.mark.parametrize("shape", [(33, 18, 7), (40, 24, 36), (5, 4, 3), (64, 31, 12)])
+def test_fused_kernels_never_read_outside_their_arrays(shape, lead):
+    """K8 and K9 stage rows with 16-byte copies although the reference's layouts only give 8-byte alignment: with the
+    arrays placed at even and odd element offsets between NaNs the results must not change (the ring
+    kernels used to over-read 8 bytes and to multiply the stray value by a zero measure)."""
+    import discretize_b200 as dz
+
+    rng = np.random.default_rng(31)
+    h = [rng.random(n) + 0.5 for n in shape]
+    mesh, grid = dz.TensorMesh(h), T.Grid(h)
+    dev = torch.device("cuda")
+    sigma, mui = np.exp(rng.standard_normal(grid.nC)), np.exp(rng.standard_normal(grid.nC))
+    phi, e = rng.standard_normal(grid.nN), rng.standard_normal(grid.nE)
+    sig_d, mui_d = _guarded(sigma, lead, dev), _guarded(mui, lead + 1, dev)
+    G, C = T.nodal_gradient(grid), T.edge_curl(grid)
+    Gd, Cd = mesh.nodal_gradient, mesh.edge_curl
+    A = Gd.T @ mesh.get_edge_inner_product(sig_d) @ Gd
+    y = A.apply_device(_guarded(phi, lead, dev), out=_guarded(np.zeros(grid.nN), lead, dev))
+    assert_close_vec(y.cpu().numpy(), G.T @ (T.inner_product(grid, "E", sigma) @ (G @ phi)))
+    B = Cd.T @ mesh.get_face_inner_product(mui_d) @ Cd + mesh.get_edge_inner_product(sig_d)
+    z = B.apply_device(_guarded(e, lead, dev), out=_guarded(np.zeros(grid.nE), lead, dev))
+    assert_close_vec(z.cpu().numpy(), C.T @ (T.inner_product(grid, "F", mui) @ (C @ e)) + T.inner_product(grid, "E", sigma) @ e)
+
+
+def test_maxwell_tensor_map_path_and_two_ranges():
+    """Even-sized meshes (all BASELINE configs, and their z-slabs whatever the slab height) take the tensor-map TMA path;
+    a two-range launch writes exactly the planes of its two ranges."""
+    import ctypes
+
+    import discretize_b200 as dz
+    from discretize_b200._lib import load
+
+    lib = load()
+    lib.dzb_tm_maxwell_last_path.restype = ctypes.c_int
+    rng = np.random.default_rng(32)
+    for shape, want in (((64, 32, 17), 3), ((64, 32, 16), 3), ((33, 17, 9), 3), ((129, 66, 20), 2)):
+        h = [rng.random(n) + 0.5 for n in shape]
+        mesh, grid = dz.TensorMesh(h), T.Grid(h)
+        sigma, mui = np.exp(rng.standard_normal(grid.nC)), np.exp(rng.standard_normal(grid.nC))
+        e = rng.standard_normal(grid.nE)
+        Cd, C = mesh.edge_curl, T.edge_curl(grid)
+        A = Cd.T @ mesh.get_face_inner_product(mui) @ Cd + mesh.get_edge_inner_product(sigma)
+        ref = C.T @ (T.inner_product(grid, "F", mui) @ (C @ e)) + T.inner_product(grid, "E", sigma) @ e
+        assert_close_vec(A @ e, ref)
+        assert lib.dzb_tm_maxwell_last_path() == want, (shape, lib.dzb_tm_maxwell_last_path())
+        # planes [0, 1) and [nz - 1, nz + 1) in one launch; everything else stays NaN
+        ed = torch.as_tensor(e).cuda()
+        out = torch.full((grid.nE,), float("nan"), dtype=torch.float64, device="cuda")
+        nz = shape[2]
+        A.apply_planes2(ed, out, 0, 1, nz - 1, nz + 1)
+        got = out.cpu().numpy()
+        nx, ny = shape[0], shape[1]
+        px, py, pz = nx * (ny + 1), (nx + 1) * ny, (nx + 1) * (ny + 1)
+        offy, offz = px * (nz + 1), px * (nz + 1) + py * (nz + 1)
+        written = np.zeros(grid.nE, dtype=bool)
+        for k in (0, nz - 1, nz):
+            written[k * px:(k + 1) * px] = True
+            written[offy + k * py:offy + (k + 1) * py] = True
+            if k < nz:
+                written[offz + k * pz:offz + (k + 1) * pz] = True
+        assert np.isnan(got[~written]).all() and not np.isnan(got[written]).any()
+        assert_close_vec(got[written], ref[written])
+
+
 # ------------------------------------------------------------------------------------------
 # interpolation
 # ------------------------------------------------------------------------------------------

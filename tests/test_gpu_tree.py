@@ -279,3 +279,21 @@ def test_tree_edge_face_cell_interpolation(loc):
     x, y = rng.standard_normal(ref.shape[1]), rng.standard_normal(ref.shape[0])
     assert_close_vec(Q @ x, ref @ x)
     assert_close_vec(Q.T @ y, ref.T @ y)
+
+
+def test_tree_operators_with_many_distinct_weights_fall_back_to_stored_values():
+    """average_cell_to_face carries distance weights that depend on the base widths: with random widths there are more
+    distinct values than codes, and the operator must then apply the reference's matrix with stored values (ADVICE r1:
+    it used to raise)."""
+    from discretize_b200.tree_mesh import TreeMesh
+
+    rng = np.random.default_rng(5)
+    h = [rng.random(16) + 0.5 for _ in range(3)]
+    mesh = TreeMesh(h)
+    mesh.refine_points(np.array([[4.0, 5.0, 6.0], [9.0, 3.0, 7.0]]), -1, finalize=True)
+    for name in ("average_cell_to_face", "average_cell_vector_to_face", "average_face_to_cell", "face_divergence"):
+        op = getattr(mesh, name)
+        M = op.tocsr()
+        x, y = rng.standard_normal(M.shape[1]), rng.standard_normal(M.shape[0])
+        assert_close_vec(op @ x, M @ x)
+        assert_close_vec(op.T @ y, M.T @ y)

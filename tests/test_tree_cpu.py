@@ -195,3 +195,32 @@ def test_refine_box_and_bounding_box():
                 np.testing.assert_array_equal(lev, rlev)
     with pytest.raises(ValueError):
         TreeMesh([8, 8, 8]).refine_box(np.zeros((2, 3)), np.ones((3, 3)), [1, 2, 3])
+
+
+def test_code_table_holds_exact_values_and_overflow_is_signalled():
+    """The multiplier table of a coded OcTree operator holds entries of the matrix itself (values that differ by a
+    rounding error share a code, to 1e-15 relative -- not the 2e-14 of an absolute rounding), and an operator with more
+    distinct weights than a code byte can name raises CodeTableOverflow so that the caller stores the values instead."""
+    from discretize_b200.tree_ops import CodeTableOverflow, _group_values, encode_parts
+
+    rng = np.random.default_rng(3)
+    base = np.array([1.0 / 6.0, 1.0 / 3.0, 1.0 / 12.0, 0.5, -0.25, 1e-9 / 3.0])
+    data = np.r_[base, base * (1 + 2.2e-16), base[rng.integers(0, base.size, 500)]]
+    tab, code = _group_values(data)
+    assert tab.size == base.size
+    assert np.isin(tab, data).all()
+    assert np.abs(tab[code] - data).max() <= 1e-15 * np.abs(data).max()
+    assert (np.abs(tab[code] - data) <= 1e-15 * np.abs(data)).all()
+
+    mesh = TreeMesh([8, 8, 8])
+    mesh.refine_points(np.array([[0.3, 0.3, 0.3]]), -1, finalize=True)
+    for name in ("face_divergence", "average_face_to_cell", "average_edge_to_cell", "average_node_to_cell"):
+        geoms, parts = mesh._host_parts(name)
+        M = mesh._host_matrix(name)
+        indptr, indices, codes, tmult, tsel = encode_parts(geoms, parts, M.shape)
+        assert np.isin(tmult, np.concatenate([np.asarray(P.data) for _, P in parts])).all()   # exact entries, never rounded
+    import scipy.sparse as sp
+
+    wide = sp.csr_matrix(np.diag(rng.random(300) + 0.5))
+    with pytest.raises(CodeTableOverflow):
+        encode_parts([], [(0, wide)], wide.shape)
