@@ -272,14 +272,12 @@ def load_mesh(file_name):
     return classes[name](**items)
 
 
-from .mesh_utils import (active_from_xyz, as_array_n_by_dim, closest_points_index, extract_core_mesh, is_scalar,  # noqa: E402,F401
-                         mesh_builder_xyz, mkvc, ndgrid, random_model, refine_tree_xyz, unpack_widths)
+from .mesh_utils import as_array_n_by_dim, is_scalar, mkvc, ndgrid, unpack_widths  # noqa: E402,F401
 from .matrix_utils import (Identity, TensorType, Zero, av, av_extrap, cart2cyl, cartesian_to_cylindrical, cross2d,  # noqa: E402,F401
                            cyl2cart, cylindrical_to_cartesian, ddx, get_subarray, ind2sub, interpolation_matrix,
                            inverse_2x2_block_diagonal, inverse_3x3_block_diagonal, inverse_property_tensor, invert_blocks,
                            kron3, make_boundary_bool, make_property_tensor, rotate_points_from_normals,
                            rotation_matrix_from_normals, sdiag, sdinv, speye, spzeros, sub2ind)
-from .curvilinear_utils import example_curvilinear_grid, face_info, index_cube, volume_tetrahedron  # noqa: E402,F401
 
 
 # camelCase names the reference has removed: calling them raises with the pointer to the new name
@@ -288,10 +286,9 @@ _REMOVED_FUNCTIONS = {
     "isScalar": "is_scalar", "asArray_N_x_Dim": "as_array_n_by_dim", "sdInv": "sdinv", "getSubArray": "get_subarray",
     "inv3X3BlockDiagonal": "inverse_3x3_block_diagonal", "inv2X2BlockDiagonal": "inverse_2x2_block_diagonal",
     "makePropertyTensor": "make_property_tensor", "invPropertyTensor": "inverse_property_tensor",
-    "meshTensor": "unpack_widths", "closestPoints": "closest_points_index", "ExtractCoreMesh": "extract_core_mesh",
+    "meshTensor": "unpack_widths",
     "interpmat": "interpolation_matrix", "rotationMatrixFromNormals": "rotation_matrix_from_normals",
-    "rotatePointsFromNormals": "rotate_points_from_normals", "exampleLrmGrid": "example_curvilinear_grid",
-    "volTetra": "volume_tetrahedron", "indexCube": "index_cube", "faceInfo": "face_info",
+    "rotatePointsFromNormals": "rotate_points_from_normals",
 }
 
 

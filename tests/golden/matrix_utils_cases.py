@@ -97,23 +97,6 @@ def evaluate(u, lib):
     put("rotation_same", lambda: u.rotation_matrix_from_normals(v0, 2 * v0))
     put("rotation_bad", lambda: u.rotation_matrix_from_normals(v0[:2], v1))
     put("rotate_points", lambda: u.rotate_points_from_normals(vecs, v0, v1, x0=np.r_[1.0, 2.0, 3.0]))
-    # geometry helpers for general quadrilateral / hexahedral cells
-    for nC in ([4, 3], [3, 4, 2]):
-        d = len(nC)
-        for kind in ("rect", "rotate", "sphere"):
-            put(f"curv_grid_{d}_{kind}", lambda: np.stack(u.example_curvilinear_grid(nC, kind)))
-        shape = tuple(k + 1 for k in nC)
-        put(f"index_cube_{d}", lambda: np.stack(u.index_cube("ABCD" if d == 2 else "ABCDEFGH", shape)))
-    put("index_cube_bad", lambda: u.index_cube("Z", (3, 3)))
-    put("curv_grid_bad", lambda: u.example_curvilinear_grid([3, 3], "torus"))
-    xyz = rng.random((30, 3))
-    idx = list(np.array([rng.permutation(30)[:4] for _ in range(8)]).T)      # four distinct corners per face
-    put("volume_tetrahedron", lambda: u.volume_tetrahedron(xyz, *idx))
-    put("face_info_avg_normals", lambda: u.face_info(xyz, *idx)[0])
-    put("face_info_avg_area", lambda: u.face_info(xyz, *idx)[1])
-    put("face_info_corner_normals", lambda: np.stack(u.face_info(xyz, *idx, average=False)[0]))
-    put("face_info_raw_normals", lambda: np.stack(u.face_info(xyz, *idx, average=False, normalize_normals=False)[0]))
-    put("face_info_bad", lambda: u.face_info(xyz, *idx, average=1))
     # symbolic zero / identity
     Z, I, w = u.Zero(), u.Identity(), np.arange(4.0) + 1
     S = sp.identity(3, format="csr") * 2.0
