@@ -149,10 +149,14 @@ __global__ void __launch_bounds__(IT, LOCATE_MINB) k_interp_locate(Axes g, const
 
 // K11: y[p] = scale[p] * sum_e w[p,e] v[cols[p,e]].  Eight lanes per point: the tables are
 // read fully coalesced, the gathers run 32-wide, partial sums combine with shuffles.
+// With `perm` the table rows are in BUCKET order (sorted by the flat index of their first grid sample, built once by
+// the host side): consecutive rows then gather from neighbouring grid entries, so the gathers stream through the grid
+// vector instead of paying one 128-byte DRAM fetch per 8-byte value (ncu: 635 B / point unsorted); row p of the table
+// belongs to point perm[p], where the result is scattered.  `scale` is in table order.
 template <typename IDX>
 __global__ void __launch_bounds__(256) k_interp_apply(const IDX *__restrict__ cols, const double *__restrict__ w,
-                                                      const double *__restrict__ scale, i64 npts,
-                                                      const double *__restrict__ v, double *__restrict__ y) {
+                                                      const double *__restrict__ scale, const int *__restrict__ perm,
+                                                      i64 npts, const double *__restrict__ v, double *__restrict__ y) {
   const i64 nent = npts * 8;
   const i64 stride = (i64)gridDim.x * blockDim.x;
   const i64 nent_pad = (nent + 31) / 32 * 32;
@@ -164,21 +168,39 @@ __global__ void __launch_bounds__(256) k_interp_apply(const IDX *__restrict__ co
     part += __shfl_xor_sync(0xffffffffu, part, 4);
     if ((t & 7) == 0 && t < nent) {
       const i64 p = t >> 3;
-      y[p] = scale ? part * __ldg(scale + p) : part;
+      const double r = scale ? part * __ldg(scale + p) : part;
+      y[perm ? (i64)__ldg(perm + p) : p] = r;
     }
   }
+}
+
+// dst[i] = src[idx[i]]: brings a result computed in bucket order back to point order.  A random 8-byte READ costs one
+// 32-byte sector; the equivalent scatter (dst[perm[p]] = ..) costs a sector fill plus a sector write-back per value.
+__global__ void __launch_bounds__(256) k_gather_rows(i64 n, const double *__restrict__ src, const int *__restrict__ idx,
+                                                     double *__restrict__ dst) {
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    const int a = __ldg(idx + i), b = __ldg(idx + i + stride), c = __ldg(idx + i + 2 * stride), d = __ldg(idx + i + 3 * stride);
+    const double va = __ldg(src + a), vb = __ldg(src + b), vc = __ldg(src + c), vd = __ldg(src + d);
+    dst[i] = va;
+    dst[i + stride] = vb;
+    dst[i + 2 * stride] = vc;
+    dst[i + 3 * stride] = vd;
+  }
+  for (; i < n; i += stride) dst[i] = __ldg(src + __ldg(idx + i));
 }
 
 // y[cols[p,e]] += scale[p] w[p,e] x[p]
 template <typename IDX>
 __global__ void __launch_bounds__(256) k_interp_apply_t(const IDX *__restrict__ cols, const double *__restrict__ w,
-                                                        const double *__restrict__ scale, i64 npts,
-                                                        const double *__restrict__ x, double *__restrict__ y) {
+                                                        const double *__restrict__ scale, const int *__restrict__ perm,
+                                                        i64 npts, const double *__restrict__ x, double *__restrict__ y) {
   const i64 nent = npts * 8;
   const i64 stride = (i64)gridDim.x * blockDim.x;
   for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < nent; t += stride) {
     const i64 p = t >> 3;
-    double xv = __ldg(x + p);
+    double xv = __ldg(x + (perm ? (i64)__ldg(perm + p) : p));
     if (scale) xv *= __ldg(scale + p);
     atomicAdd(y + (i64)__ldg(cols + t), __ldg(w + t) * xv);
   }
@@ -264,22 +286,46 @@ extern "C" int dzb_interp_locate(const double *tx, int64_t ntx, const double *ty
   return check_launch("dzb_interp_locate");
 }
 
+extern "C" int dzb_interp_apply_perm(const void *cols, int cols_is64, const double *w, const double *row_scale,
+                                     const int32_t *perm, int64_t npts, const double *v, double *y, void *stream) {
+  if (npts == 0) return 0;
+  if (perm && npts >= ((int64_t)1 << 31)) {
+    set_error("dzb_interp_apply_perm: bucketed tables are limited to 2^31 - 1 points");
+    return -1;
+  }
+  const unsigned nb = blocks_for(npts * 8, 256, 16);
+  if (cols_is64) k_interp_apply<i64><<<nb, 256, 0, (cudaStream_t)stream>>>((const i64 *)cols, w, row_scale, perm, npts, v, y);
+  else k_interp_apply<int><<<nb, 256, 0, (cudaStream_t)stream>>>((const int *)cols, w, row_scale, perm, npts, v, y);
+  return check_launch("dzb_interp_apply");
+}
+
+extern "C" int dzb_gather_rows(int64_t n, const double *src, const int32_t *idx, double *dst, void *stream) {
+  if (n == 0) return 0;
+  k_gather_rows<<<blocks_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(n, src, idx, dst);
+  return check_launch("dzb_gather_rows");
+}
+
 extern "C" int dzb_interp_apply(const void *cols, int cols_is64, const double *w, const double *row_scale, int64_t npts,
                                 const double *v, double *y, void *stream) {
+  return dzb_interp_apply_perm(cols, cols_is64, w, row_scale, nullptr, npts, v, y, stream);
+}
+
+extern "C" int dzb_interp_apply_t_perm(const void *cols, int cols_is64, const double *w, const double *row_scale,
+                                       const int32_t *perm, int64_t npts, const double *x, double *y, void *stream) {
   if (npts == 0) return 0;
+  if (perm && npts >= ((int64_t)1 << 31)) {
+    set_error("dzb_interp_apply_t_perm: bucketed tables are limited to 2^31 - 1 points");
+    return -1;
+  }
   const unsigned nb = blocks_for(npts * 8, 256, 16);
-  if (cols_is64) k_interp_apply<i64><<<nb, 256, 0, (cudaStream_t)stream>>>((const i64 *)cols, w, row_scale, npts, v, y);
-  else k_interp_apply<int><<<nb, 256, 0, (cudaStream_t)stream>>>((const int *)cols, w, row_scale, npts, v, y);
-  return check_launch("dzb_interp_apply");
+  if (cols_is64) k_interp_apply_t<i64><<<nb, 256, 0, (cudaStream_t)stream>>>((const i64 *)cols, w, row_scale, perm, npts, x, y);
+  else k_interp_apply_t<int><<<nb, 256, 0, (cudaStream_t)stream>>>((const int *)cols, w, row_scale, perm, npts, x, y);
+  return check_launch("dzb_interp_apply_t");
 }
 
 extern "C" int dzb_interp_apply_t(const void *cols, int cols_is64, const double *w, const double *row_scale,
                                   int64_t npts, const double *x, double *y, void *stream) {
-  if (npts == 0) return 0;
-  const unsigned nb = blocks_for(npts * 8, 256, 16);
-  if (cols_is64) k_interp_apply_t<i64><<<nb, 256, 0, (cudaStream_t)stream>>>((const i64 *)cols, w, row_scale, npts, x, y);
-  else k_interp_apply_t<int><<<nb, 256, 0, (cudaStream_t)stream>>>((const int *)cols, w, row_scale, npts, x, y);
-  return check_launch("dzb_interp_apply_t");
+  return dzb_interp_apply_t_perm(cols, cols_is64, w, row_scale, nullptr, npts, x, y, stream);
 }
 
 extern "C" int dzb_interp_fused(const double *tx, int64_t ntx, const double *ty, int64_t nty, const double *tz,

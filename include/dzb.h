@@ -195,6 +195,16 @@ int dzb_interp_apply(const void *cols, int cols_is64, const double *w, const dou
 /* y[ncols] += Q^T x (y must be zeroed by the caller). */
 int dzb_interp_apply_t(const void *cols, int cols_is64, const double *w, const double *row_scale, int64_t npts,
                        const double *x, double *y, void *stream);
+/* The same two applies on BUCKETED tables: the host side sorts the table rows once by the flat index of their first
+ * grid sample (so that consecutive rows gather from neighbouring grid entries) and passes perm[p] = the point row p
+ * of the table belongs to; row_scale is in table order.  perm == NULL: tables in point order (the calls above). */
+int dzb_interp_apply_perm(const void *cols, int cols_is64, const double *w, const double *row_scale, const int32_t *perm,
+                          int64_t npts, const double *v, double *y, void *stream);
+int dzb_interp_apply_t_perm(const void *cols, int cols_is64, const double *w, const double *row_scale,
+                            const int32_t *perm, int64_t npts, const double *x, double *y, void *stream);
+/* dst[i] = src[idx[i]], i < n: returns a result computed in bucket order (dzb_interp_apply on bucketed tables with
+ * perm == NULL) to point order with random READS, which cost half of what the scattered writes of *_perm cost. */
+int dzb_gather_rows(int64_t n, const double *src, const int32_t *idx, double *dst, void *stream);
 /* Fused locate + apply: y = Q v without storing Q. */
 int dzb_interp_fused(const double *tx, int64_t ntx, const double *ty, int64_t nty, const double *tz, int64_t ntz,
                      const double *pts, int64_t npts, int64_t col_offset, const double *row_scale, const double *v,

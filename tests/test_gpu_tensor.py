@@ -599,3 +599,27 @@ def test_dc_cell_fused(mesh_name):
         D2 = T.face_divergence(g2)
         x2 = rng.standard_normal(m2.nC)
         assert_close_vec(A2 @ x2, D2 @ (T.inner_product(g2, "F", rho2, invert_matrix=True) @ (D2.T @ x2)))
+
+
+@pytest.mark.parametrize("loc", ["CC", "N", "Ey", "Fx", "CCVz"])
+@pytest.mark.parametrize("zeros_outside", [False, True])
+def test_interpolation_bucketed_tables(loc, zeros_outside):
+    """K11 sorts the table rows of large operators by grid index before the first apply; the operator, its transpose
+    and its matrix must not change (here the sort is forced on a small operator)."""
+    mesh, grid = make_pair("graded")
+    rng = np.random.default_rng(41)
+    lo = np.array([t[0] for t in grid.nodes]) - (5.0 if zeros_outside else 0.0)
+    hi = np.array([t[-1] for t in grid.nodes]) + (5.0 if zeros_outside else 0.0)
+    pts = lo + rng.random((3000, 3)) * (hi - lo)
+    Q = mesh.get_interpolation_matrix(pts, loc, zeros_outside=zeros_outside)
+    v, x = rng.standard_normal(Q.shape[1]), rng.standard_normal(Q.shape[0])
+    y0, z0, M0 = Q @ v, Q.T @ x, Q.tocsr()
+    Q.bucket()
+    assert Q.perm is not None and not np.array_equal(Q.perm.cpu().numpy(), np.arange(pts.shape[0]))
+    assert np.array_equal(Q @ v, y0)                      # same products, same order of the 8 terms: bitwise
+    Q.unpermute = "scatter"
+    assert np.array_equal(Q @ v, y0)
+    Q.unpermute = "gather"
+    assert_close_vec(Q.T @ x, z0)                         # atomics: order of the additions differs
+    assert_same_matrix(Q.tocsr(), M0)
+    assert_same_matrix(M0, T.interpolation_matrix(grid, pts, loc, zeros_outside=zeros_outside))

@@ -179,7 +179,15 @@ def config4(rows, npts):
             ns = cpu_ms_per_dof(Qs)
             extra.update(cpu_scipy_gpts_s=1.0 / ns, cpu_sample="1e6 of the points, scipy csr_matvec on Q.tocsr(), 1 core",
                          gpu_over_cpu=npts / ms_apply / 1e6 * ns)
-        report(rows, f"cfg4 interp apply Q@v {loc}", npts, 104.0 * npts + 8.0 * 32 * npts, ms_apply, extra)
+        report(rows, f"cfg4 interp apply Q@v {loc} (bucketed tables, gather un-permute)", npts, 104.0 * npts + 8.0 * 32 * npts, ms_apply, extra)
+        Q.unpermute = "scatter"
+        report(rows, f"cfg4 interp apply Q@v {loc} (bucketed tables, scatter)", npts, 104.0 * npts + 8.0 * 32 * npts,
+               timeit(lambda: Q.apply_device(v, out=out), 5, 1))
+        xt = torch.randn(npts, dtype=torch.float64, device=dev)
+        ot = torch.empty(Q.shape[1], dtype=torch.float64, device=dev)
+        report(rows, f"cfg4 interp apply Q.T@x {loc} (bucketed tables)", npts, 104.0 * npts + 8.0 * 32 * npts,
+               timeit(lambda: Q.apply_device(xt, transpose=True, out=ot), 5, 1))
+        del xt, ot
         Qf = make_interpolation_operator(mesh, pts, loc, store=False)
         ms_fused = timeit(lambda: Qf.apply_device(v, out=out), 5, 1)
         report(rows, f"cfg4 interp fused locate+apply {loc}", npts, 32.0 * npts + 8.0 * 32 * npts, ms_fused,
