@@ -64,6 +64,12 @@ def _is_scalar(x):
     return np.isscalar(x) or (isinstance(x, (np.ndarray, torch.Tensor)) and x.ndim == 0)
 
 
+def _scalar_value(x):
+    """float for real scalars, complex for complex ones (1j * omega * Me is what SimPEG's Maxwell systems add)."""
+    v = x.item() if isinstance(x, (np.ndarray, np.generic, torch.Tensor)) else x
+    return complex(v) if isinstance(v, complex) and v.imag != 0.0 else float(v.real if isinstance(v, complex) else v)
+
+
 # ----------------------------------------------------------------------------------------
 # base class
 # ----------------------------------------------------------------------------------------
@@ -75,8 +81,16 @@ class Operator(LinearOperator):
     ``_tocsr()``.
     """
 
-    def __init__(self, shape):
-        LinearOperator.__init__(self, np.dtype(np.float64), tuple(int(s) for s in shape))
+    #: complex-valued operators (a complex scalar times a real operator, and sums / products containing one) have no real
+    #: kernel of their own: they implement ``_apply_complex`` on top of the real kernels of their parts
+    is_complex = False
+
+    def __init__(self, shape, is_complex=False):
+        LinearOperator.__init__(self, np.dtype(np.complex128 if is_complex else np.float64), tuple(int(s) for s in shape))
+        self.is_complex = bool(is_complex)
+
+    def _apply_complex(self, x, transpose):  # pragma: no cover - only complex operators define it
+        raise NotImplementedError
 
     # -- kernels -------------------------------------------------------------------------
     def _dev_apply(self, x, out):  # pragma: no cover - abstract
@@ -129,8 +143,14 @@ class Operator(LinearOperator):
             raise ValueError(f"out must be a contiguous float64 array with {n_out} entries")
 
     def _apply_any(self, x, transpose, out=None):
+        if self.is_complex:
+            if out is not None:
+                raise TypeError("out is not supported for complex operators (the result is a new complex array)")
+            return self._apply_complex(x, transpose)
         n_in = self.shape[0] if transpose else self.shape[1]
         is_torch = isinstance(x, torch.Tensor)
+        if is_torch and x.is_complex():
+            return torch.complex(self._apply_any(x.real.contiguous(), transpose), self._apply_any(x.imag.contiguous(), transpose))
         if not is_torch:
             x = np.asarray(x)
             if np.iscomplexobj(x):
@@ -192,7 +212,7 @@ class Operator(LinearOperator):
         if sp.issparse(x):
             return ProductOperator.make([self, as_operator(x)])
         if _is_scalar(x):
-            return ScaledOperator(self, float(x))
+            return ScaledOperator(self, _scalar_value(x))
         return self._apply_any(x, False)
 
     __mul__ = dot
@@ -207,7 +227,7 @@ class Operator(LinearOperator):
 
     def __rmul__(self, x):
         if _is_scalar(x):
-            return ScaledOperator(self, float(x))
+            return ScaledOperator(self, _scalar_value(x))
         return self.__rmatmul__(x)
 
     def __rmatmul__(self, x):
@@ -243,7 +263,7 @@ class Operator(LinearOperator):
     def __truediv__(self, other):
         if not _is_scalar(other):
             raise ValueError("Can only divide a linear operator by a scalar.")
-        return ScaledOperator(self, 1.0 / float(other))
+        return ScaledOperator(self, 1.0 / _scalar_value(other))
 
     def _transpose(self):
         return TransposedOperator(self)
@@ -254,7 +274,7 @@ class Operator(LinearOperator):
         return self._transpose()
 
     def adjoint(self):
-        return self._transpose()
+        return self._adjoint()
 
     @property
     def T(self):
@@ -262,7 +282,7 @@ class Operator(LinearOperator):
 
     @property
     def H(self):
-        return self._transpose()
+        return self._adjoint()        # == .T for the real operators; conjugate transpose for complex ones
 
     # -- matrix forms -----------------------------------------------------------------------------
     def tocsr(self):
@@ -309,8 +329,11 @@ def csr_from_device(indptr, indices, data, shape):
 # ----------------------------------------------------------------------------------------
 class TransposedOperator(Operator):
     def __init__(self, base):
-        super().__init__((base.shape[1], base.shape[0]))
+        super().__init__((base.shape[1], base.shape[0]), base.is_complex)
         self.base = base
+
+    def _apply_complex(self, x, transpose):
+        return self.base._apply_any(x, not transpose)
 
     def _dev_apply(self, x, out):
         self.base._dev_apply_t(x, out)
@@ -321,7 +344,8 @@ class TransposedOperator(Operator):
     def _transpose(self):
         return self.base
 
-    _adjoint = _transpose
+    def _adjoint(self):
+        return self.base if not self.is_complex else TransposedOperator(self.base.H.T)
 
     def _tocsr(self):
         return self.base.tocsr().T.tocsr()
@@ -368,11 +392,14 @@ class DiagonalOperator(Operator):
 
 
 class ScaledOperator(Operator):
+    """alpha * A; alpha real or complex (``1j * omega * Me``: the result is then a complex operator)."""
+
     def __init__(self, base, alpha):
         if isinstance(base, ScaledOperator):
             base, alpha = base.base, alpha * base.alpha
-        super().__init__(base.shape)
-        self.base, self.alpha = base, float(alpha)
+        alpha = _scalar_value(alpha)
+        super().__init__(base.shape, base.is_complex or isinstance(alpha, complex))
+        self.base, self.alpha = base, alpha
 
     def _dev_apply(self, x, out):
         self.base._dev_apply(x, out)
@@ -382,10 +409,14 @@ class ScaledOperator(Operator):
         self.base._dev_apply_t(x, out)
         out.mul_(self.alpha)
 
+    def _apply_complex(self, x, transpose):
+        return self.alpha * self.base._apply_any(x, transpose)     # .T is the plain transpose: alpha is not conjugated
+
     def _transpose(self):
         return ScaledOperator(self.base.T, self.alpha)
 
-    _adjoint = _transpose
+    def _adjoint(self):
+        return ScaledOperator(self.base.H, self.alpha.conjugate() if isinstance(self.alpha, complex) else self.alpha)
 
     def _tocsr(self):
         return (self.base.tocsr() * self.alpha).tocsr()
@@ -397,8 +428,14 @@ class SumOperator(Operator):
         for t in terms:
             if t.shape != shape:
                 raise ValueError(f"cannot add operators of shapes {shape} and {t.shape}")
-        super().__init__(shape)
+        super().__init__(shape, any(t.is_complex for t in terms))
         self.terms = list(terms)
+
+    def _apply_complex(self, x, transpose):
+        acc = self.terms[0]._apply_any(x, transpose)
+        for t in self.terms[1:]:
+            acc = acc + t._apply_any(x, transpose)
+        return acc
 
     @staticmethod
     def make(terms):
@@ -427,7 +464,8 @@ class SumOperator(Operator):
     def _transpose(self):
         return SumOperator.make([t.T for t in self.terms])
 
-    _adjoint = _transpose
+    def _adjoint(self):
+        return SumOperator.make([t.H for t in self.terms])
 
     def _tocsr(self):
         acc = self.terms[0].tocsr()
@@ -443,8 +481,14 @@ class ProductOperator(Operator):
         for a, b in zip(factors[:-1], factors[1:]):
             if a.shape[1] != b.shape[0]:
                 raise ValueError(f"cannot multiply operators of shapes {a.shape} and {b.shape}")
-        super().__init__((factors[0].shape[0], factors[-1].shape[1]))
+        super().__init__((factors[0].shape[0], factors[-1].shape[1]), any(f.is_complex for f in factors))
         self.factors = list(factors)
+
+    def _apply_complex(self, x, transpose):
+        cur = x
+        for f in (self.factors if transpose else reversed(self.factors)):
+            cur = f._apply_any(cur, transpose)
+        return cur
 
     @staticmethod
     def make(factors):
@@ -476,7 +520,8 @@ class ProductOperator(Operator):
     def _transpose(self):
         return ProductOperator.make([f.T for f in reversed(self.factors)])
 
-    _adjoint = _transpose
+    def _adjoint(self):
+        return ProductOperator.make([f.H for f in reversed(self.factors)])
 
     def _tocsr(self):
         acc = self.factors[0].tocsr()

@@ -112,6 +112,23 @@ def plane_field(seed, k, n, device, log_normal=False):
     return torch.exp(x) if log_normal else x
 
 
+def _local_cell_model(model, layout, seed, dev):
+    """This rank's cell layers [l0, l1) of a cell model as a device tensor.
+
+    ``model``: None (synthetic log-normal field keyed by the layer index, the benchmark's choice), or the GLOBAL model in
+    the reference's cell order (x fastest; numpy array or torch tensor with nx*ny*nz entries) -- every rank passes the
+    same array (or a memory map of it) and keeps only its own layers plus the halo layer."""
+    L = layout
+    if model is None:
+        return torch.cat([plane_field(seed, k, L.layer, dev, log_normal=True) for k in range(L.l0, L.l1)])
+    flat = model.reshape(-1) if isinstance(model, torch.Tensor) else np.asarray(model).reshape(-1)
+    if flat.shape[0] != L.nx * L.ny * L.nz:
+        raise ValueError(f"cell model must have {L.nx * L.ny * L.nz} entries, got {flat.shape[0]}")
+    part = flat[L.l0 * L.layer:L.l1 * L.layer]
+    part = part if isinstance(part, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(part, dtype=np.float64))
+    return part.to(device=dev, dtype=torch.float64).contiguous()
+
+
 class SlabDCNodal(_GraphedStep):
     """y = G^T Me(sigma) G phi on a z-slab decomposed TensorMesh([nx, ny, nz]) (unit cube widths).
 
@@ -119,15 +136,17 @@ class SlabDCNodal(_GraphedStep):
     the interior planes, then the two boundary planes.
     """
 
-    def __init__(self, nx, ny, nz, rank, world, seed_phi=5, seed_sigma=6, h=None):
+    def __init__(self, nx, ny, nz, rank, world, seed_phi=5, seed_sigma=6, h=None, sigma=None):
+        """``sigma``: the global conductivity model (nC entries, reference order) or None for the synthetic benchmark
+        field; ``h``: the three global width arrays (default: unit cube)."""
         import discretize_b200 as dz
 
         self.layout = L = SlabLayout(nx, ny, nz, rank, world)
         dev = torch.device("cuda", torch.cuda.current_device())
         hx, hy, hz = h if h is not None else (np.ones(nx) / nx, np.ones(ny) / ny, np.ones(nz) / nz)
         self.mesh = dz.TensorMesh([np.asarray(hx), np.asarray(hy), np.asarray(hz)[L.l0:L.l1]])
-        # static model incl. its halo layer (generated locally here; a real model would be exchanged once)
-        self.sigma = torch.cat([plane_field(seed_sigma, k, L.layer, dev, log_normal=True) for k in range(L.l0, L.l1)])
+        # static model incl. its halo layer
+        self.sigma = _local_cell_model(sigma, L, seed_sigma, dev)
         self.phi = torch.zeros((L.nz_local + 1) * L.plane, dtype=torch.float64, device=dev)
         for lp in range(L.p_own0, L.p_own1):
             self.phi[lp * L.plane:(lp + 1) * L.plane] = plane_field(seed_phi, L.l0 + lp, L.plane, dev)
@@ -164,6 +183,19 @@ class SlabDCNodal(_GraphedStep):
     def owned_output(self):
         L = self.layout
         return self.out[L.p_own0 * L.plane:L.p_own1 * L.plane]
+
+    def set_field(self, phi_global):
+        """Load this rank's owned node planes from a GLOBAL nodal vector (numpy / torch, nN entries)."""
+        L = self.layout
+        part = phi_global[L.owned_node_slice()]
+        part = part if isinstance(part, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(part, dtype=np.float64))
+        self.phi[L.p_own0 * L.plane:L.p_own1 * L.plane].copy_(part)
+
+    def matvec_global(self, phi_global):
+        """y = A phi for a global nodal vector every rank holds: returns (slice of the global result, owned values)."""
+        self.set_field(phi_global)
+        self.step()
+        return self.layout.owned_node_slice(), self.owned_output()
 
     def step_from_host(self, host_in, host_out, nchunks=16):
         """One distributed apply with this rank's owned planes in PINNED HOST memory (``host_in`` -> ``host_out``, both
@@ -267,7 +299,9 @@ def exchange_edge_halos(local, layout: SlabLayout, es: EdgeSlab, group=None):
 class SlabMaxwell(_GraphedStep):
     """y = C^T Mf(mui) C e + Me(sigma) e on a z-slab decomposed TensorMesh (fused kernel K9 per rank)."""
 
-    def __init__(self, nx, ny, nz, rank, world, seed_e=11, seed_sigma=12, seed_mui=13, h=None):
+    def __init__(self, nx, ny, nz, rank, world, seed_e=11, seed_sigma=12, seed_mui=13, h=None, sigma=None, mui=None):
+        """``sigma`` / ``mui``: the global cell models (nC entries, reference order) or None for the synthetic benchmark
+        fields; ``h``: the three global width arrays (default: unit cube)."""
         import discretize_b200 as dz
 
         self.layout = L = SlabLayout(nx, ny, nz, rank, world)
@@ -275,8 +309,8 @@ class SlabMaxwell(_GraphedStep):
         hx, hy, hz = h if h is not None else (np.ones(nx) / nx, np.ones(ny) / ny, np.ones(nz) / nz)
         self.mesh = dz.TensorMesh([np.asarray(hx), np.asarray(hy), np.asarray(hz)[L.l0:L.l1]])
         self.es = es = EdgeSlab(L)
-        self.sigma = torch.cat([plane_field(seed_sigma, k, L.layer, dev, log_normal=True) for k in range(L.l0, L.l1)])
-        self.mui = torch.cat([plane_field(seed_mui, k, L.layer, dev, log_normal=True) for k in range(L.l0, L.l1)])
+        self.sigma = _local_cell_model(sigma, L, seed_sigma, dev)
+        self.mui = _local_cell_model(mui, L, seed_mui, dev)
         self.e = torch.zeros(es.n, dtype=torch.float64, device=dev)
         n_own_layers = L.c1 - L.c0
         for lp in range(L.p_own0, L.p_own1):      # owned node planes: Ex, Ey
@@ -322,6 +356,29 @@ class SlabMaxwell(_GraphedStep):
         return (v[L.p_own0 * es.px:L.p_own1 * es.px],
                 v[es.off_y + L.p_own0 * es.py:es.off_y + L.p_own1 * es.py],
                 v[es.off_z + L.p_own0 * es.pz:es.off_z + (L.p_own0 + n_own_layers) * es.pz])
+
+    # --- global vectors -----------------------------------------------------------------------------------
+    def owned_global_slices(self):
+        """Where this rank's (Ex planes, Ey planes, Ez layers) sit in the GLOBAL stacked edge vector [Ex; Ey; Ez]."""
+        L = self.layout
+        nx, ny, nz = L.nx, L.ny, L.nz
+        px, py, pz = nx * (ny + 1), (nx + 1) * ny, (nx + 1) * (ny + 1)
+        offy, offz = px * (nz + 1), px * (nz + 1) + py * (nz + 1)
+        g0, g1 = L.c0, L.c1 + (0 if L.has_upper else 1)
+        return (slice(g0 * px, g1 * px), slice(offy + g0 * py, offy + g1 * py), slice(offz + L.c0 * pz, offz + L.c1 * pz))
+
+    def set_field(self, e_global):
+        """Load this rank's owned edges from a GLOBAL edge vector (numpy / torch, nE entries)."""
+        for dst, sl in zip(self.owned_parts(self.e), self.owned_global_slices()):
+            part = e_global[sl]
+            part = part if isinstance(part, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(part, dtype=np.float64))
+            dst.copy_(part)
+
+    def matvec_global(self, e_global):
+        """y = A e for a global edge vector every rank holds: returns (three slices of the global result, owned values)."""
+        self.set_field(e_global)
+        self.step()
+        return self.owned_global_slices(), self.owned_parts(self.out)
 
     # --- end to end from / to pinned host memory ------------------------------------------------------------
     def owned_sizes(self):

@@ -623,3 +623,59 @@ def test_interpolation_bucketed_tables(loc, zeros_outside):
     assert_close_vec(Q.T @ x, z0)                         # atomics: order of the additions differs
     assert_same_matrix(Q.tocsr(), M0)
     assert_same_matrix(M0, T.interpolation_matrix(grid, pts, loc, zeros_outside=zeros_outside))
+
+
+def test_model_less_and_scalar_composites_fuse():
+    """The reference's own Maxwell composition uses get_face_inner_product() with NO model
+    (tests/boundaries/test_boundary_maxwell.py:95-99): it must reach the fused kernels, like scalar models."""
+    from discretize_b200.tensor_ops import DCNodalOperator, MaxwellOperator
+
+    mesh, grid = make_pair("wide")
+    rng = np.random.default_rng(51)
+    sigma = np.exp(rng.standard_normal(grid.nC))
+    e, phi = rng.standard_normal(grid.nE), rng.standard_normal(grid.nN)
+    C, G = T.edge_curl(grid), T.nodal_gradient(grid)
+    Cd, Gd = mesh.edge_curl, mesh.nodal_gradient
+    ones = np.ones(grid.nC)
+    A = Cd.T @ mesh.get_face_inner_product() @ Cd + mesh.get_edge_inner_product(sigma)
+    assert isinstance(A, MaxwellOperator)
+    assert_close_vec(A @ e, C.T @ (T.inner_product(grid, "F", ones) @ (C @ e)) + T.inner_product(grid, "E", sigma) @ e)
+    B = Cd.T @ mesh.get_face_inner_product(2.5) @ Cd + 3.0 * mesh.get_edge_inner_product()
+    assert isinstance(B, MaxwellOperator)
+    assert_close_vec(B @ e, C.T @ (T.inner_product(grid, "F", 2.5 * ones) @ (C @ e)) + 3.0 * (T.inner_product(grid, "E", ones) @ e))
+    D = Gd.T @ mesh.get_edge_inner_product(0.7) @ Gd
+    assert isinstance(D, DCNodalOperator)
+    assert_close_vec(D @ phi, G.T @ (T.inner_product(grid, "E", 0.7 * ones) @ (G @ phi)))
+
+
+def test_frequency_domain_maxwell_operator():
+    """A = C^T Mf(mui) C + 1j omega Me(sigma), the system SimPEG's frequency-domain Maxwell solves apply: complex scalars
+    in the operator algebra, fused form, complex / real inputs, transpose, adjoint and matrix."""
+    from discretize_b200.tensor_ops import ComplexMaxwellOperator
+
+    mesh, grid = make_pair("nonuniform")
+    rng = np.random.default_rng(52)
+    sigma, mui = np.exp(rng.standard_normal(grid.nC)), np.exp(rng.standard_normal(grid.nC))
+    omega = 2 * np.pi * 3.0
+    C = T.edge_curl(grid)
+    K, M = (C.T @ T.inner_product(grid, "F", mui) @ C).tocsr(), T.inner_product(grid, "E", sigma)
+    ref = (K + 1j * omega * M).tocsr()
+    Cd = mesh.edge_curl
+    A = Cd.T @ mesh.get_face_inner_product(mui) @ Cd + 1j * omega * mesh.get_edge_inner_product(sigma)
+    assert isinstance(A, ComplexMaxwellOperator) and A.dtype == np.complex128
+    e = rng.standard_normal(grid.nE) + 1j * rng.standard_normal(grid.nE)
+    assert_close_vec(A @ e, ref @ e)
+    assert_close_vec(A @ e.real, ref @ e.real)
+    assert_close_vec(A.T @ e, ref.T @ e)
+    assert_close_vec(A.H @ e, ref.conj().T @ e)
+    et = torch.as_tensor(e).cuda()
+    assert_close_vec((A @ et).cpu().numpy(), ref @ e)
+    got = A.tocsr()
+    assert np.abs((got - ref)).max() <= 1e-12 * np.abs(ref).max()
+    # (0.5 - 2j) Me inside a generic (unfused) complex composite, and a complex multiple of a real operator
+    Me = mesh.get_edge_inner_product(sigma)
+    S = Me + (0.5 - 2j) * Me
+    assert S.is_complex
+    assert_close_vec(S @ e, (1.5 - 2j) * (M @ e))
+    assert_close_vec((S.H @ e), (1.5 + 2j) * (M @ e))
+    assert_close_vec(((2j * Cd) @ e), 2j * (C @ e))
