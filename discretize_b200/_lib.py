@@ -76,6 +76,8 @@ SIGNATURES = {
     "dzb_tree_ell_spmv": [_L, _I, _L, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P],
     "dzb_csr_spmv": [_L, _P, _I, _P, _P, _P, _P, _I, _P],
     "dzb_diag_scale": [_L, _P, _P, _P, _I, _P],
+    "dzb_tree_mass_tensor": [_L, _I, _P, _P, _P, _P, _P, _P],
+    "dzb_tree_mass_tensor_adj": [_L, _I, _P, _P, _P, _P, _P, _P],
     "dzb_solver_workspace_bytes": [],
     "dzb_dot": [_L, _P, _P, _P, _P, _I, _P],
     "dzb_cg_update": [_L, _P, _P, _P, _P, _P, _P, _P, _P, _P],

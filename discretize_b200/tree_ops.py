@@ -329,6 +329,101 @@ def _tree_corner_projections(mesh, proj):
     return Ps
 
 
+def _tree_cell_entities(mesh, proj):
+    """(ent int32 [slots, nC] on the device, R, R^T as device CSR, n_total) for the matrix-free tensor mass kernels:
+    the TOTAL entity numbers of every cell in the slot order of dzb_tree_mass_tensor, and the deflation matrix."""
+    key = "TMT_" + proj
+    if key not in mesh._cache:
+        from .csr import _DeviceCsr
+
+        t = mesh._t()
+        fams = t.faces if proj == "F" else t.edges
+        cell_ents = t.cell_faces if proj == "F" else t.cell_edges
+        off = np.r_[0, np.cumsum([f.n_total for f in fams])]
+        per = 2 if proj == "F" else 4
+        ent = np.stack([off[d] + fams[d].index[cell_ents[d][:, l]] for d in range(3) for l in range(per)])
+        R = (mesh._deflate_faces() if proj == "F" else mesh._deflate_edges()).tocsr()
+        mesh._cache[key] = (to_device(ent.astype(np.int32), torch.int32), _DeviceCsr(R), _DeviceCsr(R.T.tocsr()), int(off[3]))
+    return mesh._cache[key]
+
+
+def _invert_tensor6(t):
+    """Closed-form inverse of the symmetric 3x3 tensors [xx, yy, zz, xy, xz, yz] (utils/matrix_utils.py:1246-1434)."""
+    a11, a22, a33, a12, a13, a23 = (t[q] for q in range(6))
+    det = (a11 * a22 * a33 + a12 * a23 * a13 + a13 * a12 * a23 - a13 * a22 * a13 - a12 * a12 * a33 - a11 * a23 * a23)
+    return torch.stack([(a22 * a33 - a23 * a23) / det, (a11 * a33 - a13 * a13) / det, (a11 * a22 - a12 * a12) / det,
+                        -(a12 * a33 - a13 * a23) / det, (a12 * a23 - a13 * a22) / det, -(a11 * a23 - a13 * a12) / det])
+
+
+class TreeMassTensor(Operator):
+    """get_face / get_edge_inner_product with a full-tensor model on an OcTree, matrix-free (kernel K13t):
+    M x = R^T A(Sigma) (R x) -- deflation, one cell loop with the 8 corner contractions, inflation.  Symmetric."""
+
+    def __init__(self, mesh, proj, model_dev6, invert_model):
+        n = mesh.n_faces if proj == "F" else mesh.n_edges
+        super().__init__((n, n))
+        self.mesh, self.proj, self.invert_model = mesh, proj, bool(invert_model)
+        self.ent, self.R, self.RT, self.n_total = _tree_cell_entities(mesh, proj)
+        self.model_raw = model_dev6                                   # [6, nC]: xx yy zz xy xz yz
+        self.model = _invert_tensor6(model_dev6) if invert_model else model_dev6
+        self.model = self.model.contiguous()
+        self.vol = to_device(mesh.cell_volumes)
+
+    def apply_total(self, model6, x, out):
+        """out = R^T A(model6) R x"""
+        dev = x.device
+        xt = torch.empty(self.n_total, dtype=torch.float64, device=dev)
+        yt = torch.zeros(self.n_total, dtype=torch.float64, device=dev)
+        self.R.apply(x, xt)
+        check(load().dzb_tree_mass_tensor(self.mesh.n_cells, int(self.proj == "E"), ptr(self.ent), ptr(model6), ptr(self.vol),
+                                          ptr(xt), ptr(yt), stream_ptr()), "dzb_tree_mass_tensor")
+        self.RT.apply(yt, out)
+
+    def _dev_apply(self, x, out):
+        self.apply_total(self.model, x, out)
+
+    _dev_apply_t = _dev_apply
+
+    def _transpose(self):
+        return self
+
+    _adjoint = _transpose
+
+    def _tocsr(self):
+        host = self.model_raw.cpu().numpy().T                       # (nC, 6)
+        return _tree_tensor_mass_matrix(self.mesh, self.proj, host.reshape(-1, order="F"), self.invert_model)
+
+
+class TreeMassTensorDeriv(Operator):
+    """F(v) = d(M(m) v)/dm for a full-tensor model on an OcTree (n x 6 nC), matrix-free: forward = the mass kernel with dm
+    as the model, adjoint = the cell-wise contraction kernel (operators/inner_products.py:459-565)."""
+
+    def __init__(self, mesh, proj, v):
+        n = mesh.n_faces if proj == "F" else mesh.n_edges
+        super().__init__((n, 6 * mesh.n_cells))
+        self.mesh, self.proj = mesh, proj
+        self.ent, self.R, self.RT, self.n_total = _tree_cell_entities(mesh, proj)
+        self.v = to_device(v).reshape(-1).clone()
+        self.vol = to_device(mesh.cell_volumes)
+        self.vt = torch.empty(self.n_total, dtype=torch.float64, device=self.v.device)
+        self.R.apply(self.v, self.vt)
+
+    def _dev_apply(self, x, out):          # x = dm (6 nC, columns xx yy zz xy xz yz in F order = [6, nC] row-major)
+        yt = torch.zeros(self.n_total, dtype=torch.float64, device=x.device)
+        check(load().dzb_tree_mass_tensor(self.mesh.n_cells, int(self.proj == "E"), ptr(self.ent), ptr(x), ptr(self.vol),
+                                          ptr(self.vt), ptr(yt), stream_ptr()), "dzb_tree_mass_tensor")
+        self.RT.apply(yt, out)
+
+    def _dev_apply_t(self, x, out):        # x = w (n) -> 6 nC
+        wt = torch.empty(self.n_total, dtype=torch.float64, device=x.device)
+        self.R.apply(x, wt)
+        check(load().dzb_tree_mass_tensor_adj(self.mesh.n_cells, int(self.proj == "E"), ptr(self.ent), ptr(self.vol),
+                                              ptr(self.vt), ptr(wt), ptr(out), stream_ptr()), "dzb_tree_mass_tensor_adj")
+
+    def _tocsr(self):
+        return _tree_tensor_mass_deriv_matrix(self.mesh, self.proj, self.v.cpu().numpy())
+
+
 def _tree_tensor_mass_matrix(mesh, proj, model, invert_model):
     """M = sum_n P_n^T sqrt(V/8) Sigma sqrt(V/8) P_n  (operators/inner_products.py:147-272), host assembly."""
     nC = mesh.n_cells
@@ -441,8 +536,7 @@ def make_tree_mass_operator(mesh, proj, model, invert_model, invert_matrix):
     if md.kind == _lib.MODEL_TENSOR:
         if invert_matrix:
             raise Exception("Solver needed to invert A.")
-        host = model.cpu().numpy() if isinstance(model, torch.Tensor) else np.asarray(model)
-        return CsrOperator(_tree_tensor_mass_matrix(mesh, proj, host, invert_model))
+        return TreeMassTensor(mesh, proj, md.dev.reshape(6, mesh.n_cells), invert_model)      # md.dev: F-ordered columns
     return TreeMassDiag(mesh, proj, model, invert_model, invert_matrix)
 
 
@@ -457,13 +551,10 @@ def make_tree_mass_deriv(mesh, proj, model, do_fast, invert_model, invert_matrix
         if invert_model or invert_matrix:
             raise NotImplementedError(
                 "inverting the property or the matrix is not yet implemented for this mesh/tensorType. You should write it!")
-        from .csr import CsrOperator
-
         def tensor_deriv(v=None):
             if v is None:
                 raise Exception("v must be supplied for this implementation.")
-            host = v.cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
-            return CsrOperator(_tree_tensor_mass_deriv_matrix(mesh, proj, host))
+            return TreeMassTensorDeriv(mesh, proj, v)
 
         return tensor_deriv
     nC = mesh.n_cells

@@ -240,6 +240,18 @@ int dzb_csr_spmv(int64_t nrows, const void *indptr, int indptr_is64, const int32
 /* y = d .* x (invert == 0) or x ./ d: diagonal mass matrices on a TreeMesh
  * (base/base_tensor_mesh.py:792-863 with the tree averages). */
 int dzb_diag_scale(int64_t n, const double *d, const double *x, double *y, int invert, void *stream);
+/* Full-tensor mass matrices on an OcTree, matrix-free: M x = R^T A (R x) with R the deflation matrix (applied by
+ * dzb_csr_spmv around this call) and A = sum over the 8 cell corners of P_n^T (V/8) Sigma P_n on TOTAL entities
+ * (operators/inner_products.py:147-272, corner tables of _extensions/tree_ext.pyx:5651-5763).
+ * ent: int32 [slots][n_cells] (slot-major) total entity numbers of every cell, slots = fx0 fx1 fy0 fy1 fz0 fz1 (edges == 0)
+ * or ex(b+2c) x4, ey(a+2c) x4, ez(a+2b) x4 (edges != 0); model6: [6][n_cells] = xx yy zz xy xz yz;
+ * y_total must be zeroed by the caller (the kernel accumulates with atomics). */
+int dzb_tree_mass_tensor(int64_t n_cells, int edges, const int32_t *ent, const double *model6, const double *cell_volumes,
+                         const double *x_total, double *y_total, void *stream);
+/* Adjoint of the model derivative of the above: out6[q][C] = (V_C/8) sum_n (u_n(v) (x) u_n(w))_q for the 6 tensor slots
+ * (operators/inner_products.py:459-565); the forward derivative F(v) dm is dzb_tree_mass_tensor with dm as the model. */
+int dzb_tree_mass_tensor_adj(int64_t n_cells, int edges, const int32_t *ent, const double *cell_volumes,
+                             const double *v_total, const double *w_total, double *out6, void *stream);
 
 /* ---- solver-side vector kernels ------------------------------------ */
 /* One Jacobi-preconditioned CG iteration on an operator A is: Ap = A p (any apply above), dzb_dot(p, Ap -> scal[1]),
