@@ -89,7 +89,9 @@ __global__ void __launch_bounds__(256)
     k_tree_ell(i64 nrows, int K, i64 stride, const int *__restrict__ indices, const unsigned char *__restrict__ codes,
                const double *__restrict__ tab_mult, const unsigned char *__restrict__ tab_sel, int ntab,
                const double *__restrict__ g0, const double *__restrict__ g1, const double *__restrict__ g2,
-               const double *__restrict__ x, double *__restrict__ y) {
+               const int *__restrict__ perm, const double *__restrict__ x, double *__restrict__ y) {
+  // perm != NULL: the table rows (and the row geometry) are stored in an order that follows the COLUMN numbering, so that
+  // the gathers of a warp share sectors; table row r is row perm[r] of the operator
   __shared__ double s_mult[256];
   __shared__ unsigned char s_sel[256];
   for (int t = threadIdx.x; t < 256; t += blockDim.x) {
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(256)
       pc += stride;
     }
   }
-  y[row] = acc;
+  y[perm ? (i64)__ldg(perm + row) : row] = acc;
 }
 
 // CSR with warp-staged entries: a warp owns 32 consecutive rows; the contiguous span of their entries is copied
@@ -286,10 +288,23 @@ extern "C" int dzb_tree_spmv(int64_t nrows, const void *indptr, int indptr_is64,
   return check_launch("dzb_tree_spmv");
 }
 
+extern "C" int dzb_tree_ell_spmv_perm(int64_t nrows, int row_len, int64_t stride, const int32_t *indices,
+                                      const uint8_t *codes, const double *tab_mult, const uint8_t *tab_sel, int ntab,
+                                      const double *g0, const double *g1, const double *g2, int geom_by_col, int padded,
+                                      const int32_t *perm, const double *x, double *y, void *stream);
+
 extern "C" int dzb_tree_ell_spmv(int64_t nrows, int row_len, int64_t stride, const int32_t *indices, const uint8_t *codes,
                                  const double *tab_mult, const uint8_t *tab_sel, int ntab, const double *g0,
                                  const double *g1, const double *g2, int geom_by_col, int padded, const double *x,
                                  double *y, void *stream) {
+  return dzb_tree_ell_spmv_perm(nrows, row_len, stride, indices, codes, tab_mult, tab_sel, ntab, g0, g1, g2, geom_by_col,
+                                padded, nullptr, x, y, stream);
+}
+
+extern "C" int dzb_tree_ell_spmv_perm(int64_t nrows, int row_len, int64_t stride, const int32_t *indices,
+                                      const uint8_t *codes, const double *tab_mult, const uint8_t *tab_sel, int ntab,
+                                      const double *g0, const double *g1, const double *g2, int geom_by_col, int padded,
+                                      const int32_t *perm, const double *x, double *y, void *stream) {
   if (nrows <= 0) return 0;
   if (ntab < 1 || ntab > 255 || row_len < 0 || stride < nrows) {
     set_error("dzb_tree_ell_spmv: bad table size (1..255; code 255 marks padding), row length or stride");
@@ -298,7 +313,7 @@ extern "C" int dzb_tree_ell_spmv(int64_t nrows, int row_len, int64_t stride, con
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned blocks = (unsigned)((nrows + 255) / 256);
 #define DZB_ELL_LAUNCH(BC, KT, PD) \
-  k_tree_ell<BC, KT, PD><<<blocks, 256, 0, s>>>(nrows, row_len, stride, indices, codes, tab_mult, tab_sel, ntab, g0, g1, g2, x, y)
+  k_tree_ell<BC, KT, PD><<<blocks, 256, 0, s>>>(nrows, row_len, stride, indices, codes, tab_mult, tab_sel, ntab, g0, g1, g2, perm, x, y)
   if (geom_by_col) {
     DZB_ELL_LAUNCH(true, 0, true);
   } else if (padded) {

@@ -102,7 +102,7 @@ def encode_parts(geoms, parts, shape):
 class CodedCsr:
     """Device-resident coded CSR (one direction of an operator)."""
 
-    def __init__(self, geoms, parts, shape, geom_by_col, canonical=True):
+    def __init__(self, geoms, parts, shape, geom_by_col, canonical=True, sort_rows=False):
         indptr, indices, codes, tmult, tsel = (encode_parts if canonical else encode_parts_raw)(geoms, parts, shape)
         self.shape = shape
         self.nnz = int(indptr[-1])
@@ -131,6 +131,10 @@ class CodedCsr:
         avg = self.nnz / max(shape[0], 1)
         self.lpr = 1 if avg <= 7 else 2 if avg <= 16 else 4 if avg <= 40 else 16
         self.ell_indices = self.ell_codes = None
+        # rows stored in column-locality order (ELL, row geometry only): see dzb_tree_ell_spmv_perm
+        self.sort_rows = bool(sort_rows) and not self.geom_by_col
+        self.ell_perm = None
+        self.ell_geoms = self.geoms
         self.use_layout(self.layout)
 
     def use_layout(self, layout):
@@ -149,6 +153,14 @@ class CodedCsr:
                 slot = np.arange(indices.size) - np.repeat(indptr[:-1], lens)
                 ie[slot, rows] = indices
                 ce[slot, rows] = codes
+                if self.sort_rows and n > 1:
+                    first = np.where(ce[:, :n] != 255, ie[:, :n], np.iinfo(np.int32).max).min(axis=0)
+                    order = np.argsort(first, kind="stable")
+                    ie[:, :n] = ie[:, :n][:, order]
+                    ce[:, :n] = ce[:, :n][:, order]
+                    self.ell_perm = to_device(order.astype(np.int32), torch.int32)
+                    dorder = to_device(order.astype(np.int64), torch.int64)
+                    self.ell_geoms = [None if g is None else g.index_select(0, dorder) for g in self.geoms]
                 self.ell_indices = to_device(ie.reshape(-1), torch.int32)
                 self.ell_codes = to_device(ce.reshape(-1), torch.uint8)
         elif layout in ("stream", "lpr"):
@@ -164,10 +176,11 @@ class CodedCsr:
     def apply(self, x, out):
         g = self.geoms
         if self.layout == "ell":
-            check(load().dzb_tree_ell_spmv(self.shape[0], self.row_len, self.stride, ptr(self.ell_indices),
-                                           ptr(self.ell_codes), ptr(self.tab_mult), ptr(self.tab_sel), self.ntab,
-                                           ptr(g[0]), ptr(g[1]), ptr(g[2]), self.geom_by_col, self.padded, ptr(x),
-                                           ptr(out), stream_ptr()), "dzb_tree_ell_spmv")
+            g = self.ell_geoms
+            check(load().dzb_tree_ell_spmv_perm(self.shape[0], self.row_len, self.stride, ptr(self.ell_indices),
+                                                ptr(self.ell_codes), ptr(self.tab_mult), ptr(self.tab_sel), self.ntab,
+                                                ptr(g[0]), ptr(g[1]), ptr(g[2]), self.geom_by_col, self.padded,
+                                                ptr(self.ell_perm), ptr(x), ptr(out), stream_ptr()), "dzb_tree_ell_spmv")
             return
         lpr = 0 if self.layout == "stream" else self.lpr
         check(load().dzb_tree_spmv(self.shape[0], ptr(self.indptr), int(self.is64), ptr(self.indices), ptr(self.codes),
@@ -180,6 +193,11 @@ class CodedCsr:
         gsize = (self.shape[1] if self.geom_by_col else self.shape[0]) * n_geom
         ptr_bytes = 0 if self.layout == "ell" else (8 if self.is64 else 4) * (self.shape[0] + 1)
         return 8 * (self.shape[0] + self.shape[1]) + 5 * self.nnz + ptr_bytes + 8 * gsize   # padding slots not counted
+
+
+# cell-rowed operators whose ELL rows are stored in column-locality order (measured on the 10 M-cell config-3 tree,
+# tools/sweep_tree.py: cells follow the tree's Z-order, their faces / edges the Cantor key)
+SORTED_ROW_OPERATORS = {"face_divergence", "average_face_to_cell", "average_edge_to_cell", "average_node_to_cell"}
 
 
 class _StoredCsr:
@@ -219,7 +237,8 @@ class TreeOperator(Operator):
             else:
                 shape = self._fwd_shape
             try:
-                self._dev[key] = CodedCsr(geoms, parts, shape, geom_by_col=transposed)
+                self._dev[key] = CodedCsr(geoms, parts, shape, geom_by_col=transposed,
+                                          sort_rows=(not transposed) and self.name in SORTED_ROW_OPERATORS)
             except CodeTableOverflow:
                 # geometry-dependent weights (the distance weights of average_cell_to_face on non-uniform base widths):
                 # apply the reference's matrix with stored values, 12 B per entry instead of 5

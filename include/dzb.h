@@ -232,6 +232,13 @@ int dzb_tree_spmv(int64_t nrows, const void *indptr, int indptr_is64, const int3
 int dzb_tree_ell_spmv(int64_t nrows, int row_len, int64_t stride, const int32_t *indices, const uint8_t *codes,
                       const double *tab_mult, const uint8_t *tab_sel, int ntab, const double *g0, const double *g1,
                       const double *g2, int geom_by_col, int padded, const double *x, double *y, void *stream);
+/* The same with the table rows (indices, codes, row geometry g*) stored in an order that follows the COLUMN numbering
+ * (cells are numbered along the tree's Z-order, faces / edges / nodes by Cantor key: in cell order every gather of a
+ * warp touches ~25 sectors, sorted by first column ~12): table row r is row perm[r] of the operator, where y is written. */
+int dzb_tree_ell_spmv_perm(int64_t nrows, int row_len, int64_t stride, const int32_t *indices, const uint8_t *codes,
+                           const double *tab_mult, const uint8_t *tab_sel, int ntab, const double *g0, const double *g1,
+                           const double *g2, int geom_by_col, int padded, const int32_t *perm, const double *x, double *y,
+                           void *stream);
 /* y = A x for a CSR matrix with stored float64 values (int32 columns, int32 / int64 indptr): scipy
  * matrices mixed into operator algebra and the full-tensor OcTree mass matrices
  * (operators/inner_products.py:147-272 with tree_ext.pyx:5651-5763 projections). */
