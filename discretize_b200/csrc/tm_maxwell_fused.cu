@@ -140,6 +140,13 @@ static PFN_cuTensorMapEncodeTiled tmap_encoder() {
 }
 
 static int g_m3_xs = 2, g_m3_r = 8, g_m3_ns = 6;
+static int g_m3_l2hint = 1;   // L2 cache hint of the box loads: 0 none, 1 evict_last, 2 evict_first
+extern "C" void dzb_tune_maxwell_l2hint(int h) { g_m3_l2hint = h; }
+static CUtensorMapL2promotion g_m3_l2promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+extern "C" void dzb_tune_maxwell_l2promo(int bytes) {
+  g_m3_l2promo = bytes == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : bytes == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                 : bytes == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+}
 extern "C" void dzb_tune_maxwell_tmap(int xs, int r, int nslot) {
   g_m3_xs = xs;
   g_m3_r = r;
@@ -162,7 +169,7 @@ static int m3_encode(const TM &m, const double *mui, const double *sigma, const 
   static thread_local M3Key last_key = {};
   static thread_local M3Maps last_maps;
   static thread_local bool have = false;
-  const M3Key key{e, mui, sigma, m.nx, m.ny, m.nz, G::W, G::RN};
+  const M3Key key{e, mui, sigma, m.nx, m.ny, m.nz, G::W, G::RN + 1000 * (int)g_m3_l2promo};
   if (have && key == last_key) {
     maps = last_maps;
     return 0;
@@ -186,14 +193,14 @@ static int m3_encode(const TM &m, const double *mui, const double *sigma, const 
     cuuint64_t gdim[2] = {(cuuint64_t)pitch[a], (cuuint64_t)(odd ? (rows[a] + 1) / 2 : rows[a])};
     cuuint64_t gstr[1] = {(cuuint64_t)(odd ? 16 * pitch[a] : 8 * pitch[a])};
     if (enc(&maps.m[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base[a]), gdim, gstr, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, g_m3_l2promo,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return -1;
     if (odd) {
       cuuint64_t odim[2] = {(cuuint64_t)(2 * pitch[a]), (cuuint64_t)(rows[a] / 2)};
       if (odim[1] == 0) odim[1] = 1, odim[0] = (cuuint64_t)pitch[a];   // a one-row array has no odd rows: everything the box asks for is out of bounds
       if (enc(&maps.o[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base[a]), odim, gstr, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, g_m3_l2promo,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return -1;
     } else {
@@ -229,7 +236,7 @@ static int launch_m3_t(const TM &m, const double *mui, const double *sigma, cons
   const int nzb0 = (planes + kchunk - 1) / kchunk, nzb1 = (planes2 + kchunk - 1) / kchunk;
   dim3 grid((unsigned)xblocks, (unsigned)yblocks, (unsigned)(nzb0 + nzb1));
   k_maxwell_tmap<XS, R, PARX, NSLOT, MINB><<<grid, dim3(G::NT), G::SMEM, s>>>(m, maps, y, kchunk, k_begin, k_end, nzb0,
-                                                                              k_begin2, k_end2);
+                                                                              k_begin2, k_end2, g_m3_l2hint);
   return 0;
 }
 
@@ -259,7 +266,7 @@ static int launch_m3(const TM &m, const double *mui, const double *sigma, const 
     case 444: M3_LAUNCH(4, 4, 4, 1);
     default: break;
   }
-  M3_LAUNCH(2, 8, 4, 1);
+  M3_LAUNCH(2, 8, 6, 1);
 }
 
 extern "C" int dzb_tm_maxwell_range(const DzbTensorMesh *mm, const double *mui, const double *sigma, const double *e,

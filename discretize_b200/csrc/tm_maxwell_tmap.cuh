@@ -33,6 +33,24 @@ __device__ __forceinline__ void tmap_load_2d(void *dst_smem, const CUtensorMap *
       "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tmap_load_2d_hint(void *dst_smem, const CUtensorMap *map, int x, int y, uint64_t *bar,
+                                                  uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], "
+      "[%4], %5;" ::"r"(smem_u32(dst_smem)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void tmap_prefetch(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -74,7 +92,7 @@ struct M3Maps {
 template <int XS, int R, int PARX, int NSLOT, int MINB>
 __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
     k_maxwell_tmap(TM m, const __grid_constant__ M3Maps maps, double *__restrict__ y, int kchunk, int k_begin, int k_end,
-                   int nzb0, int k_begin2, int k_end2) {
+                   int nzb0, int k_begin2, int k_end2, int l2hint) {
   typedef Mx3<XS, R, PARX, NSLOT> G;
   constexpr int S = NSLOT, W = G::W;
   static_assert(S % 2 == 0, "the row-parity bookkeeping assumes an even ring depth");
@@ -135,6 +153,11 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
       }
       const int npl[5] = {nNz, nNz, nz, nz, nz};
       const int gp[5] = {nx, nNx, nNx, nx, nx};
+      const uint64_t pol = l2hint == 1 ? l2_policy_evict_last() : l2_policy_evict_first();
+      auto load = [&](void *dst, const CUtensorMap *mp, int x, int yy, uint64_t *bar) {
+        if (l2hint) tmap_load_2d_hint(dst, mp, x, yy, bar, pol);
+        else tmap_load_2d(dst, mp, x, yy, bar);
+      };
       for (int q = 0; q < nq; ++q) {
         const int slot = q % S, n = q / S;
         if (n >= 1) mbar_wait(&empty[slot], (n - 1) & 1);
@@ -157,10 +180,10 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
               // sub-tile 0 holds the staged rows rr = 0, 2, 4, .., sub-tile 1 the rows rr = 1, 3, ..: global row J0 + rr is
               // even for the rr of parity t = J0 & 1, so the even-row box goes to sub-tile t and the odd-row box to 1 - t
               const int t = J0 & 1;
-              tmap_load_2d(T + G::off(a) + t * G::sub(a), &maps.m[a], (Xb - 1) & ~1, (J0 + 1) >> 1, &full[slot]);
-              tmap_load_2d(T + G::off(a) + (t ^ 1) * G::sub(a), &maps.o[a], (gp[a] + Xb - 1) & ~1, J0 >> 1, &full[slot]);
+              load(T + G::off(a) + t * G::sub(a), &maps.m[a], (Xb - 1) & ~1, (J0 + 1) >> 1, &full[slot]);
+              load(T + G::off(a) + (t ^ 1) * G::sub(a), &maps.o[a], (gp[a] + Xb - 1) & ~1, J0 >> 1, &full[slot]);
             } else {
-              tmap_load_2d(T + G::off(a), &maps.m[a], (Xb - 1) & ~1, J0, &full[slot]);
+              load(T + G::off(a), &maps.m[a], (Xb - 1) & ~1, J0, &full[slot]);
             }
           }
         }

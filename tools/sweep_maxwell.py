@@ -44,11 +44,17 @@ if which in ("v2", "all"):
     shapes = ((2, 4, 4, 1), (2, 4, 4, 2), (2, 4, 4, 4), (2, 4, 6, 1), (2, 4, 6, 2), (4, 2, 4, 1), (4, 2, 4, 2), (4, 2, 4, 4),
               (4, 4, 4, 2), (4, 4, 4, 4), (4, 4, 6, 4), (1, 8, 4, 2))
     cases += [(2, sh, 0, 0) for sh in shapes]
+promo = int(os.environ.get("DZB_L2PROMO", "128"))
+lib.dzb_tune_maxwell_l2promo.argtypes = [ctypes.c_int]
+lib.dzb_tune_maxwell_l2promo.restype = None
+lib.dzb_tune_maxwell_l2promo(promo)
+lib.dzb_tune_maxwell_l2hint.argtypes = [ctypes.c_int]
+lib.dzb_tune_maxwell_l2hint.restype = None
+lib.dzb_tune_maxwell_l2hint(int(os.environ.get("DZB_L2HINT", "0")))
 if which in ("v3", "all"):
     lib.dzb_tune_maxwell_tmap.argtypes = [ctypes.c_int] * 3
     lib.dzb_tune_maxwell_tmap.restype = None
-    shapes3 = ((1, 4, 4), (1, 4, 6), (1, 5, 4), (1, 5, 6), (1, 6, 4), (1, 6, 6), (1, 6, 8), (1, 8, 4), (1, 8, 6), (2, 4, 4),
-               (2, 4, 6), (2, 6, 4), (2, 6, 6), (2, 8, 4), (2, 8, 6), (4, 4, 4))
+    shapes3 = ((1, 6, 6), (2, 6, 6), (2, 8, 6))
     cases += [(3, sh, 0, 0) for sh in shapes3]
 for variant, a, b, kc in cases:
     lib.dzb_tune_maxwell(variant, kc)
