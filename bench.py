@@ -297,7 +297,19 @@ def run_ours(args):
         # BASELINE configs[4]: C^T Mf(mui) C + Me(sigma) on n^3, z-slabs across the ranks (strong scaling)
         from discretize_b200.slab import SlabMaxwell
 
-        op = SlabMaxwell(n, n, n, rank, world)
+        op, halo_mode = None, "none"
+        if world > 1 and args.halo == "peer":
+            try:        # halo planes fetched by the kernel from the neighbours' memory (symmetric allocation): one launch per apply
+                op = SlabMaxwell(n, n, n, rank, world, peer_halo=True)
+                op.step_peer()
+                torch.cuda.synchronize()
+                halo_mode = "peer"
+            except Exception as exc:
+                sys.stderr.write(f"[bench] peer-read halos unavailable ({exc!r}); using NCCL send/recv\n")
+                op = None
+        if op is None:
+            op = SlabMaxwell(n, n, n, rank, world)
+            halo_mode = "nccl" if world > 1 else "none"
         ndof_total = n * (n + 1) * (n + 1) * 3
         alg_bytes = 8.0 * (2 * ndof_total + 2 * n ** 3) / world
         workload_name = f"TensorMesh {n}^3 Maxwell C^T Mf(mui) C + Me(sigma) fused matrix-free apply (BASELINE configs[4])"
@@ -306,13 +318,20 @@ def run_ours(args):
         from discretize_b200.slab import SlabDCNodal
 
         op = SlabDCNodal(n, n, n, rank, world, seed_phi=5, seed_sigma=6)
+        halo_mode = "nccl" if world > 1 else "none"
         ndof_total = (n + 1) ** 3
         alg_bytes = 8.0 * (2 * ndof_total + n ** 3) / world
         workload_name = f"TensorMesh {n}^3 DC-resistivity nodal operator G^T Me(sigma) G matrix-free apply (BASELINE configs[1])"
         kernel_name, kernel_key = "k_dc_nodal_ring<4,NWC,PARX>", "k_dc_nodal_ring"
-    step = op.step_graphed if (world > 1 and not args.eager) else op.step
-    launches_per_step = op.launches_per_step
-    parallelism = "1 GPU" if world == 1 else f"z-slabs x{world} (strong scaling), NCCL halo send/recv, no collective"
+    if args.workload == "maxwell" and halo_mode == "peer":
+        step, launches_per_step = op.step_peer, 1
+        parallelism = (f"z-slabs x{world} (strong scaling); halo planes read from the neighbours' memory over NVLink by the "
+                       "fused kernel itself (tensor maps on symmetric memory) after a device-side barrier: one launch per apply, "
+                       "no send/recv, no collective")
+    else:
+        step = op.step_graphed if (world > 1 and not args.eager) else op.step
+        launches_per_step = op.launches_per_step
+        parallelism = "1 GPU" if world == 1 else f"z-slabs x{world} (strong scaling), NCCL halo send/recv, no collective"
 
     def sync():
         if world > 1:
@@ -417,8 +436,8 @@ def run_ours(args):
                    "ms_per_step_median": ms_step, "ms_per_step_best": min(blocks) / args.steps,
                    "note": "each block = exactly `steps` applies between barrier + synchronize; median block reported"},
         "gpu_launches": launches_per_step * args.steps,
-        "launch_mode": ("cuda-graph replay" if (world > 1 and not args.eager and not getattr(op, "_graph_failed", False))
-                        else "eager"),
+        "launch_mode": ("eager" if (world == 1 or args.eager or (args.workload == "maxwell" and halo_mode == "peer")
+                                   or getattr(op, "_graph_failed", False)) else "cuda-graph replay"),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src,
@@ -464,6 +483,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the 512^3 DC object at N=1")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="N > 1, maxwell: peer = the kernel reads the halo planes from the neighbours' memory (default); "
+                         "nccl = send/recv exchange overlapped with the interior planes + one launch for the boundary planes")
     ap.add_argument("--eager", action="store_true", help="multi-GPU: launch every step from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.n is None:

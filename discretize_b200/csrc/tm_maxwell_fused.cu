@@ -163,6 +163,36 @@ struct M3Key {
   }
 };
 
+// The tensor maps of one array (pitch elements per row, `rows` rows): even pitch: the array as it is.  Odd pitch: m = its
+// EVEN rows (width = one row, row stride = two rows), o = super-rows of two rows, of which the boxes take the second
+// half: both stay inside the array whatever the parity of its row count, and a box never reads past the end of a row it
+// was not asked for.
+static int m3_encode_array(PFN_cuTensorMapEncodeTiled enc, const double *base, i64 pitch, i64 rows, int W, int hbox,
+                           CUtensorMap *m, CUtensorMap *o) {
+  if (reinterpret_cast<uintptr_t>(base) & 15) return -1;
+  if (rows >= ((i64)1 << 31) || 2 * pitch >= ((i64)1 << 31)) return -1;
+  const bool odd = (pitch & 1) != 0;
+  cuuint32_t box[2] = {(cuuint32_t)W, (cuuint32_t)hbox};
+  cuuint32_t estr[2] = {1, 1};
+  cuuint64_t gdim[2] = {(cuuint64_t)pitch, (cuuint64_t)(odd ? (rows + 1) / 2 : rows)};
+  cuuint64_t gstr[1] = {(cuuint64_t)(odd ? 16 * pitch : 8 * pitch)};
+  if (enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), gdim, gstr, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, g_m3_l2promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) !=
+      CUDA_SUCCESS)
+    return -1;
+  if (odd) {
+    cuuint64_t odim[2] = {(cuuint64_t)(2 * pitch), (cuuint64_t)(rows / 2)};
+    if (odim[1] == 0) odim[1] = 1, odim[0] = (cuuint64_t)pitch;   // a one-row array has no odd rows: everything the box asks for is out of bounds
+    if (enc(o, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), odim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, g_m3_l2promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) !=
+        CUDA_SUCCESS)
+      return -1;
+  } else {
+    *o = *m;
+  }
+  return 0;
+}
+
 // returns 0 and fills `maps`, or -1 if this mesh / these pointers cannot be described (caller falls back to bulk copies)
 template <typename G>
 static int m3_encode(const TM &m, const double *mui, const double *sigma, const double *e, M3Maps &maps) {
@@ -181,47 +211,55 @@ static int m3_encode(const TM &m, const double *mui, const double *sigma, const 
   const double *base[5] = {e, e + nEx, e + nEx + nEy, mui, sigma};
   const i64 pitch[5] = {nx, nNx, nNx, nx, nx};
   const i64 rows[5] = {nNy * nNz, ny * nNz, nNy * nz, ny * nz, ny * nz};
-  for (int a = 0; a < 5; ++a) {
-    if (reinterpret_cast<uintptr_t>(base[a]) & 15) return -1;
-    if (rows[a] >= ((i64)1 << 31) || 2 * pitch[a] >= ((i64)1 << 31)) return -1;
-    const bool odd = (pitch[a] & 1) != 0;
-    cuuint32_t box[2] = {(cuuint32_t)G::W, (cuuint32_t)G::hbox(a)};
-    cuuint32_t estr[2] = {1, 1};
-    // even pitch: the array as it is.  Odd pitch: m[a] = its EVEN rows (width = one row, row stride = two rows),
-    // o[a] = super-rows of two rows, of which the boxes take the second half: both stay inside the array whatever the
-    // parity of its row count, and a box never reads past the end of a row it was not asked for.
-    cuuint64_t gdim[2] = {(cuuint64_t)pitch[a], (cuuint64_t)(odd ? (rows[a] + 1) / 2 : rows[a])};
-    cuuint64_t gstr[1] = {(cuuint64_t)(odd ? 16 * pitch[a] : 8 * pitch[a])};
-    if (enc(&maps.m[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base[a]), gdim, gstr, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, g_m3_l2promo,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return -1;
-    if (odd) {
-      cuuint64_t odim[2] = {(cuuint64_t)(2 * pitch[a]), (cuuint64_t)(rows[a] / 2)};
-      if (odim[1] == 0) odim[1] = 1, odim[0] = (cuuint64_t)pitch[a];   // a one-row array has no odd rows: everything the box asks for is out of bounds
-      if (enc(&maps.o[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base[a]), odim, gstr, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, g_m3_l2promo,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return -1;
-    } else {
-      maps.o[a] = maps.m[a];
-    }
-  }
+  for (int a = 0; a < 5; ++a)
+    if (m3_encode_array(enc, base[a], pitch[a], rows[a], G::W, G::hbox(a), &maps.m[a], &maps.o[a]) != 0) return -1;
   last_key = key;
   last_maps = maps;
   have = true;
   return 0;
 }
 
+// peer-read halos of a z-slab: the neighbours' local edge vectors and where the halo planes sit in them
+struct M3Peers {
+  const double *e_lo, *e_hi;   // NULL: no such neighbour
+  i64 nz_lo, nz_hi;            // cell layers of the neighbours' local meshes (their edge vectors' layout)
+  M3Halo halo;
+};
+
+template <typename G>
+static int m3_encode_peers(const TM &m, const M3Peers &pr, M3Maps &maps) {
+  PFN_cuTensorMapEncodeTiled enc = tmap_encoder();
+  if (!enc) return -1;
+  const i64 nx = m.nx, ny = m.ny, nNx = nx + 1, nNy = ny + 1;
+  const double *pe[2] = {pr.e_lo, pr.e_hi};
+  const i64 pnz[2] = {pr.nz_lo, pr.nz_hi};
+  for (int side = 0; side < 2; ++side) {
+    if (!pe[side]) {
+      for (int a = 0; a < 3; ++a) maps.pm[side][a] = maps.m[a], maps.po[side][a] = maps.o[a];
+      continue;
+    }
+    const i64 nz = pnz[side], nNz = nz + 1;
+    const i64 nEx = nx * nNy * nNz, nEy = nNx * ny * nNz;
+    const double *base[3] = {pe[side], pe[side] + nEx, pe[side] + nEx + nEy};
+    const i64 pitch[3] = {nx, nNx, nNx};
+    const i64 rows[3] = {nNy * nNz, ny * nNz, nNy * nz};
+    for (int a = 0; a < 3; ++a)
+      if (m3_encode_array(enc, base[a], pitch[a], rows[a], G::W, G::hbox(a), &maps.pm[side][a], &maps.po[side][a]) != 0)
+        return -1;
+  }
+  return 0;
+}
+
 template <int XS, int R, int PARX, int NSLOT, int MINB>
 static int launch_m3_t(const TM &m, const double *mui, const double *sigma, const double *e, double *y, int k_begin,
-                       int k_end, int k_begin2, int k_end2, cudaStream_t s) {
+                       int k_end, int k_begin2, int k_end2, const M3Peers *peers, cudaStream_t s) {
   typedef Mx3<XS, R, PARX, NSLOT> G;
   M3Maps maps;
   if (m3_encode<G>(m, mui, sigma, e, maps) != 0) return -1;
-  if (cudaFuncSetAttribute(k_maxwell_tmap<XS, R, PARX, NSLOT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)G::SMEM) != cudaSuccess)
-    return -1;
+  if (peers && m3_encode_peers<G>(m, *peers, maps) != 0) return -1;
+  const void *kern = peers ? (const void *)k_maxwell_tmap<XS, R, PARX, NSLOT, MINB, true>
+                           : (const void *)k_maxwell_tmap<XS, R, PARX, NSLOT, MINB, false>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM) != cudaSuccess) return -1;
   const int nNx = (int)m.nx + 1, nNy = (int)m.ny + 1, planes = k_end - k_begin, planes2 = k_end2 - k_begin2;
   const int longest = planes > planes2 ? planes : planes2;
   const int xblocks = (nNx + XS * M3_XOUT - 1) / (XS * M3_XOUT), yblocks = (nNy + R - 1) / R;
@@ -235,17 +273,22 @@ static int launch_m3_t(const TM &m, const double *mui, const double *sigma, cons
   const int kchunk = (longest + nchunks - 1) / nchunks;
   const int nzb0 = (planes + kchunk - 1) / kchunk, nzb1 = (planes2 + kchunk - 1) / kchunk;
   dim3 grid((unsigned)xblocks, (unsigned)yblocks, (unsigned)(nzb0 + nzb1));
-  k_maxwell_tmap<XS, R, PARX, NSLOT, MINB><<<grid, dim3(G::NT), G::SMEM, s>>>(m, maps, y, kchunk, k_begin, k_end, nzb0,
-                                                                              k_begin2, k_end2, g_m3_l2hint);
+  const M3Halo none = {-1, -1, -1, -1, -1, -1};
+  if (peers)
+    k_maxwell_tmap<XS, R, PARX, NSLOT, MINB, true><<<grid, dim3(G::NT), G::SMEM, s>>>(m, maps, y, kchunk, k_begin, k_end, nzb0,
+                                                                                      k_begin2, k_end2, g_m3_l2hint, peers->halo);
+  else
+    k_maxwell_tmap<XS, R, PARX, NSLOT, MINB, false><<<grid, dim3(G::NT), G::SMEM, s>>>(m, maps, y, kchunk, k_begin, k_end, nzb0,
+                                                                                       k_begin2, k_end2, g_m3_l2hint, none);
   return 0;
 }
 
-#define M3_LAUNCH(XS, R, NS, MINB)                                                                             \
-  return parx ? launch_m3_t<XS, R, 1, NS, MINB>(m, mui, sigma, e, y, k_begin, k_end, k_begin2, k_end2, s)      \
-              : launch_m3_t<XS, R, 0, NS, MINB>(m, mui, sigma, e, y, k_begin, k_end, k_begin2, k_end2, s)
+#define M3_LAUNCH(XS, R, NS, MINB)                                                                                   \
+  return parx ? launch_m3_t<XS, R, 1, NS, MINB>(m, mui, sigma, e, y, k_begin, k_end, k_begin2, k_end2, peers, s)     \
+              : launch_m3_t<XS, R, 0, NS, MINB>(m, mui, sigma, e, y, k_begin, k_end, k_begin2, k_end2, peers, s)
 
 static int launch_m3(const TM &m, const double *mui, const double *sigma, const double *e, double *y, int k_begin,
-                     int k_end, int k_begin2, int k_end2, cudaStream_t s) {
+                     int k_end, int k_begin2, int k_end2, cudaStream_t s, const M3Peers *peers = nullptr) {
   const int parx = (int)(m.nx & 1);
   switch (g_m3_xs * 100 + g_m3_r * 10 + g_m3_ns) {
     case 144: M3_LAUNCH(1, 4, 4, 3);
@@ -271,6 +314,41 @@ static int launch_m3(const TM &m, const double *mui, const double *sigma, const 
 
 extern "C" int dzb_tm_maxwell_range(const DzbTensorMesh *mm, const double *mui, const double *sigma, const double *e,
                                     double *y, int64_t k_begin, int64_t k_end, void *stream);
+
+// A z-slab's apply with PEER-READ halos: ex, ey on the local node planes lo_plane / hi_plane and ez in the local layer
+// lo_plane are not read from `e` but from the neighbours' local edge vectors e_lo / e_hi (device pointers into peer memory
+// mapped into this process: symmetric allocation / CUDA IPC), at plane lo_peer_plane / hi_peer_plane of those arrays, whose
+// layout is that of a TensorMesh with nz_lo / nz_hi cell layers.  One launch covers all owned planes: no send / recv and no
+// separate launch for the planes next to a halo.  The caller orders the apply after the neighbours' writes to their e
+// (a barrier across the ranks).  Tensor-map path only: returns -2 where that path does not apply.
+extern "C" int dzb_tm_maxwell_range_peer(const DzbTensorMesh *mm, const double *mui, const double *sigma, const double *e,
+                                         const double *e_lo, int64_t nz_lo, int64_t lo_plane, int64_t lo_peer_plane,
+                                         const double *e_hi, int64_t nz_hi, int64_t hi_plane, int64_t hi_peer_plane,
+                                         double *y, int64_t k_begin, int64_t k_end, void *stream) {
+  if (!valid_mesh(mm)) return -1;
+  TM m(*mm);
+  if (k_begin < 0 || k_end > m.nz + 1 || k_begin > k_end) {
+    set_error("dzb_tm_maxwell_range_peer: plane range outside [0, nz+1]");
+    return -1;
+  }
+  if (k_begin == k_end) return 0;
+  const bool ring_ok = m.ny >= 1 && (m.nx + 1) * (m.ny + 1) < ((i64)1 << 31);
+  M3Peers pr;
+  pr.e_lo = e_lo;
+  pr.e_hi = e_hi;
+  pr.nz_lo = nz_lo;
+  pr.nz_hi = nz_hi;
+  pr.halo = {e_lo ? (int)lo_plane : -1, (int)lo_peer_plane, e_lo ? (int)lo_plane : -1, (int)lo_peer_plane,
+             e_hi ? (int)hi_plane : -1, (int)hi_peer_plane};
+  if (g_mx_variant == 3 && ring_ok) {
+    g_mx_last_path = 3;
+    if (launch_m3(m, mui, sigma, e, y, (int)k_begin, (int)k_end, 0, 0, (cudaStream_t)stream, &pr) == 0)
+      return check_launch("dzb_tm_maxwell_range_peer");
+    cudaGetLastError();
+  }
+  set_error("dzb_tm_maxwell_range_peer: needs the tensor-map path (16-byte aligned component offsets: nx, ny even)");
+  return -2;
+}
 
 // two disjoint plane ranges in ONE launch (the two boundary planes of a z-slab, once its halos have arrived)
 extern "C" int dzb_tm_maxwell_range2(const DzbTensorMesh *mm, const double *mui, const double *sigma, const double *e,

@@ -87,12 +87,24 @@ template <int XS, int R, int PARX, int NSLOT> struct Mx3 {
 struct M3Maps {
   CUtensorMap m[5];   // whole array (even pitch) or its even rows (odd pitch)
   CUtensorMap o[5];   // odd pitch: super-rows, used for the odd rows
+  // z-slabs with peer-read halos: the same two maps of ex, ey, ez in the memory of the lower (0) / upper (1) neighbour
+  CUtensorMap pm[2][3];
+  CUtensorMap po[2][3];
 };
 
-template <int XS, int R, int PARX, int NSLOT, int MINB>
+// Which local planes of a z-slab are halo planes and where they live in the neighbour's local edge vector.  The ring
+// fetches them straight from the neighbour's memory over NVLink (tensor maps on the peer allocation), so a distributed
+// apply is ONE launch per rank: no send / recv, no separate launch for the planes next to a halo.
+struct M3Halo {
+  int lo_plane, lo_peer_plane;   // ex, ey on local node plane lo_plane = plane lo_peer_plane of the lower neighbour (-1: none)
+  int lo_layer, lo_peer_layer;   // ez in local cell layer lo_layer = layer lo_peer_layer of the lower neighbour (-1: none)
+  int hi_plane, hi_peer_plane;   // ex, ey on local node plane hi_plane = plane hi_peer_plane of the upper neighbour (-1: none)
+};
+
+template <int XS, int R, int PARX, int NSLOT, int MINB, bool PEER>
 __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
     k_maxwell_tmap(TM m, const __grid_constant__ M3Maps maps, double *__restrict__ y, int kchunk, int k_begin, int k_end,
-                   int nzb0, int k_begin2, int k_end2, int l2hint) {
+                   int nzb0, int k_begin2, int k_end2, int l2hint, M3Halo hal) {
   typedef Mx3<XS, R, PARX, NSLOT> G;
   constexpr int S = NSLOT, W = G::W;
   static_assert(S % 2 == 0, "the row-parity bookkeeping assumes an even ring depth");
@@ -142,6 +154,18 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
 
   // rows per plane of the five staged arrays; row J = plane * rpp + (row inside the plane)
   const int rpp[5] = {nNy, ny, nNy, ny, ny};
+  // where plane / layer pl of array a is read from: 0 = this rank's array, 1 / 2 = the lower / upper neighbour's (then
+  // `pl` becomes the plane index inside the neighbour's local array)
+  auto source = [&](int a, int &pl) -> int {
+    if (!PEER || a > 2) return 0;
+    if (a < 2) {
+      if (pl == hal.lo_plane) { pl = hal.lo_peer_plane; return 1; }
+      if (pl == hal.hi_plane) { pl = hal.hi_peer_plane; return 2; }
+      return 0;
+    }
+    if (pl == hal.lo_layer) { pl = hal.lo_peer_layer; return 1; }
+    return 0;
+  };
 
   if (warp == G::NWARPS - 1) {
     // ================= producer warp: one elected lane, <= 7 box copies per stage =================
@@ -150,6 +174,13 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
       for (int a = 0; a < 5; ++a) {
         tmap_prefetch(&maps.m[a]);
         if (G::odd(a)) tmap_prefetch(&maps.o[a]);
+      }
+      if (PEER) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          if (hal.lo_plane >= 0) tmap_prefetch(&maps.pm[0][a]);
+          if (hal.hi_plane >= 0) tmap_prefetch(&maps.pm[1][a]);
+        }
       }
       const int npl[5] = {nNz, nNz, nz, nz, nz};
       const int gp[5] = {nx, nNx, nNx, nx, nx};
@@ -174,16 +205,22 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
 #pragma unroll
         for (int a = 0; a < 5; ++a) {
           if (on[a]) {
-            const int pl = jfirst + q + (a < 2 ? 1 : 0);
+            int pl = jfirst + q + (a < 2 ? 1 : 0);
+            const int src = source(a, pl);             // pl is now the plane index inside the array it is read from
+            const CUtensorMap *mE = &maps.m[a], *mO = &maps.o[a];
+            if (PEER && src) {
+              mE = &maps.pm[src - 1][a < 3 ? a : 0];
+              mO = &maps.po[src - 1][a < 3 ? a : 0];
+            }
             const int J0 = pl * rpp[a] + j0 - 1;       // first staged row (may be -1: zero-filled / previous plane)
             if (G::odd(a)) {
               // sub-tile 0 holds the staged rows rr = 0, 2, 4, .., sub-tile 1 the rows rr = 1, 3, ..: global row J0 + rr is
               // even for the rr of parity t = J0 & 1, so the even-row box goes to sub-tile t and the odd-row box to 1 - t
               const int t = J0 & 1;
-              load(T + G::off(a) + t * G::sub(a), &maps.m[a], (Xb - 1) & ~1, (J0 + 1) >> 1, &full[slot]);
-              load(T + G::off(a) + (t ^ 1) * G::sub(a), &maps.o[a], (gp[a] + Xb - 1) & ~1, J0 >> 1, &full[slot]);
+              load(T + G::off(a) + t * G::sub(a), mE, (Xb - 1) & ~1, (J0 + 1) >> 1, &full[slot]);
+              load(T + G::off(a) + (t ^ 1) * G::sub(a), mO, (gp[a] + Xb - 1) & ~1, J0 >> 1, &full[slot]);
             } else {
-              load(T + G::off(a), &maps.m[a], (Xb - 1) & ~1, J0, &full[slot]);
+              load(T + G::off(a), mE, (Xb - 1) & ~1, J0, &full[slot]);
             }
           }
         }
@@ -216,6 +253,7 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
   const int leadE = (Xb - 1) & 1;
   auto rowoff = [&](int a, int rr, int pl) -> int {
     if (G::odd(a)) {
+      if (PEER) (void)source(a, pl);      // the row parity is that of the array the plane was read from
       const int Jodd = (pl * rpp[a] + j0 - 1 + rr) & 1;
       return G::off(a) + (rr & 1) * G::sub(a) + (rr >> 1) * W + (leadE ^ Jodd);
     }
@@ -236,7 +274,7 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
       for (int u = 0; u < S; ++u) {
         const int q = qb + u;
         if (q >= nq) break;
-        const int ku = jfirst + u;   // S is even: the plane parity of slot u is the same in every ring cycle
+        const int ku = PEER ? jfirst + q : jfirst + u;   // S is even: the plane parity of slot u is the same in every ring cycle
         mbar_wait(&full[u], par);
         const double *T = tcol + u * G::STAGE;
         const double ex1 = T[rowoff(0, 0, ku + 1)], ex1u = T[rowoff(0, 1, ku + 1)];
@@ -299,7 +337,7 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
     for (int u = 0; u < S; ++u) {
       const int q = qb + u;
       if (q >= nq) break;
-      const int ku = jfirst + u;
+      const int ku = PEER ? jfirst + q : jfirst + u;   // (peer-read halos: the real plane, its source may differ)
       mbar_wait(&full[u], par);
       const double *T = tcol + u * G::STAGE;
       const double ex1 = T[rowoff(0, r + 1, ku + 1)], ex1u = T[rowoff(0, r + 2, ku + 1)];

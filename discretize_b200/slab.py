@@ -299,9 +299,12 @@ def exchange_edge_halos(local, layout: SlabLayout, es: EdgeSlab, group=None):
 class SlabMaxwell(_GraphedStep):
     """y = C^T Mf(mui) C e + Me(sigma) e on a z-slab decomposed TensorMesh (fused kernel K9 per rank)."""
 
-    def __init__(self, nx, ny, nz, rank, world, seed_e=11, seed_sigma=12, seed_mui=13, h=None, sigma=None, mui=None):
+    def __init__(self, nx, ny, nz, rank, world, seed_e=11, seed_sigma=12, seed_mui=13, h=None, sigma=None, mui=None,
+                 peer_halo=False):
         """``sigma`` / ``mui``: the global cell models (nC entries, reference order) or None for the synthetic benchmark
-        fields; ``h``: the three global width arrays (default: unit cube)."""
+        fields; ``h``: the three global width arrays (default: unit cube).  ``peer_halo``: allocate the edge vector in
+        symmetric memory (``torch.distributed._symmetric_memory``) so that the fused kernel fetches the halo planes from
+        the neighbours' memory itself (``step_peer``: one launch per apply, no send / recv)."""
         import discretize_b200 as dz
 
         self.layout = L = SlabLayout(nx, ny, nz, rank, world)
@@ -311,7 +314,13 @@ class SlabMaxwell(_GraphedStep):
         self.es = es = EdgeSlab(L)
         self.sigma = _local_cell_model(sigma, L, seed_sigma, dev)
         self.mui = _local_cell_model(mui, L, seed_mui, dev)
-        self.e = torch.zeros(es.n, dtype=torch.float64, device=dev)
+        self.peer = None
+        if peer_halo and world > 1:
+            self.peer = self._setup_peer(nx, ny, nz, rank, world, dev)
+            self.e = self.peer["buffer"][:es.n]
+            self.e.zero_()
+        else:
+            self.e = torch.zeros(es.n, dtype=torch.float64, device=dev)
         n_own_layers = L.c1 - L.c0
         for lp in range(L.p_own0, L.p_own1):      # owned node planes: Ex, Ey
             g = L.l0 + lp
@@ -326,6 +335,35 @@ class SlabMaxwell(_GraphedStep):
         self.comm_stream = torch.cuda.Stream(device=dev)
         self.launches_per_step = 2 if world > 1 else 1
         self.n_owned_edges = ((L.p_own1 - L.p_own0) * (es.px + es.py) + n_own_layers * es.pz)
+
+    def _setup_peer(self, nx, ny, nz, rank, world, dev):
+        """Edge vector in symmetric memory + the neighbours' addresses and slab layouts."""
+        import torch.distributed._symmetric_memory as symm_mem
+
+        layouts = [SlabLayout(nx, ny, nz, r, world) for r in range(world)]
+        n_max = max(EdgeSlab(l).n for l in layouts)          # symmetric allocations have one size on every rank
+        buf = symm_mem.empty(n_max, dtype=torch.float64, device=dev)
+        hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+        L = layouts[rank]
+        lower = upper = None
+        if L.has_lower:
+            Ll = layouts[rank - 1]
+            lower = (int(hdl.buffer_ptrs[rank - 1]), Ll.nz_local, L.p_own0 - 1, Ll.p_own1 - 1)
+        if L.has_upper:
+            Lu = layouts[rank + 1]
+            upper = (int(hdl.buffer_ptrs[rank + 1]), Lu.nz_local, L.p_own1, Lu.p_own0)
+        return {"buffer": buf, "handle": hdl, "lower": lower, "upper": upper}
+
+    def step_peer(self):
+        """One distributed apply as ONE launch: a barrier across the ranks (the neighbours' fields are complete), then the
+        fused kernel over all owned planes, which reads the halo planes from the neighbours' memory over NVLink.
+        (Whoever overwrites ``e`` afterwards must order that after the neighbours' kernels: another barrier.)"""
+        L, op = self.layout, self.op
+        if self.peer is None:
+            return self.step()
+        self.peer["handle"].barrier()
+        op.apply_planes_peer(self.e, self.out, L.p_own0, L.p_own1, self.peer["lower"], self.peer["upper"])
+        return self.out
 
     def step(self):
         L, op = self.layout, self.op

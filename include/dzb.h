@@ -177,6 +177,16 @@ int dzb_tm_maxwell_range(const DzbTensorMesh *m, const double *mui, const double
 /* Two disjoint plane ranges in one launch: the two boundary planes of a z-slab once its halos have arrived. */
 int dzb_tm_maxwell_range2(const DzbTensorMesh *m, const double *mui, const double *sigma, const double *e, double *y,
                           int64_t k_begin, int64_t k_end, int64_t k_begin2, int64_t k_end2, void *stream);
+/* A z-slab's apply with PEER-READ halos (one process per GPU, NVLink): ex, ey on the local node planes lo_plane /
+ * hi_plane and ez in the local layer lo_plane are fetched by the kernel itself from the neighbours' local edge vectors
+ * e_lo / e_hi (peer memory mapped into this process; NULL: no such neighbour) at plane lo_peer_plane / hi_peer_plane of
+ * those arrays, laid out like a TensorMesh with nz_lo / nz_hi cell layers.  ONE launch per apply and rank: no send / recv,
+ * no separate launch for the planes next to a halo.  The caller orders the call after the neighbours' writes to their e.
+ * Returns -2 where the tensor-map path does not apply (use dzb_tm_maxwell_range + an exchange there). */
+int dzb_tm_maxwell_range_peer(const DzbTensorMesh *m, const double *mui, const double *sigma, const double *e,
+                              const double *e_lo, int64_t nz_lo, int64_t lo_plane, int64_t lo_peer_plane,
+                              const double *e_hi, int64_t nz_hi, int64_t hi_plane, int64_t hi_peer_plane, double *y,
+                              int64_t k_begin, int64_t k_end, void *stream);
 
 /* ---- interpolation: get_interpolation_matrix --------------------------------- */
 /* base/base_tensor_mesh.py:684-790 -> utils/interpolation_utils.py:44-172 ->

@@ -59,6 +59,26 @@ for (nx, ny, nz) in ((40, 33, 29), (70, 20, 64), (300, 64, 96)):
     errs = [float((a - b).abs().max() / b.abs().max()) for a, b in zip(part.owned_parts(part.out), ref)]
     print(f"rank {rank}/{world} maxwell {nx}x{ny}x{nz} rel err Ex/Ey/Ez {errs}", flush=True)
     ok = ok and max(errs) <= 1e-14  # FMA contraction differs between the unrolled ring slots
+# peer-read halos (one launch per apply, no send / recv): even-sized meshes only (tensor-map path)
+for (nx, ny, nz) in ((40, 32, 29), (64, 20, 64), (256, 64, 96)):
+    rng = np.random.default_rng(4)
+    h = (rng.random(nx) + 0.5, rng.random(ny) + 0.5, rng.random(nz) + 0.5)
+    part = SlabMaxwell(nx, ny, nz, rank, world, h=h, peer_halo=True)
+    for _ in range(2):
+        part.step_peer()
+    torch.cuda.synchronize()
+    whole = SlabMaxwell(nx, ny, nz, 0, 1, h=h)
+    whole.step()
+    torch.cuda.synchronize()
+    L, esw = part.layout, whole.es
+    g0, g1 = L.c0, L.c1 + (0 if L.has_upper else 1)
+    ref = (whole.out[g0 * esw.px:g1 * esw.px], whole.out[esw.off_y + g0 * esw.py:esw.off_y + g1 * esw.py],
+           whole.out[esw.off_z + L.c0 * esw.pz:esw.off_z + L.c1 * esw.pz])
+    errs = [float((a - b).abs().max() / b.abs().max()) for a, b in zip(part.owned_parts(part.out), ref)]
+    print(f"rank {rank}/{world} maxwell PEER-READ halos {nx}x{ny}x{nz} rel err Ex/Ey/Ez {errs}", flush=True)
+    ok = ok and max(errs) <= 1e-14
+    dist.barrier()
+    del part
 # the same operators with USER models and a global field handed over by every rank (the mesh-level API of a
 # distributed apply): compared with the single-GPU operator of the public TensorMesh API
 import discretize_b200 as dz

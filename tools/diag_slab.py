@@ -55,7 +55,8 @@ def whole():
     op.op.apply_planes(op.e, op.out, L.p_own0, L.p_own1)
 
 
-res = {"step_eager": timeit(op.step), "step_graph": timeit(op.step_graphed), "interior": timeit(interior),
+peer = SlabMaxwell(n, n, n, rank, world, peer_halo=True) if world > 1 else None
+res = {"step_peer_read_one_launch": timeit(peer.step_peer) if peer is not None else 0.0, "step_eager": timeit(op.step), "step_graph": timeit(op.step_graphed), "interior": timeit(interior),
        "boundary_launches": timeit(boundary), "exchange": timeit(exchange), "one_launch_all_owned_planes": timeit(whole)}
 if rank == 0:
     print({k: round(v, 4) for k, v in res.items()}, "ms; planes per rank", L.p_own1 - L.p_own0, flush=True)
