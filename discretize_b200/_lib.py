@@ -60,6 +60,7 @@ SIGNATURES = {
     "dzb_tm_mass_deriv_apply": [_MP, _I, _I, _P, _D, _P, _I, _P, _P, _P],
     "dzb_tm_dc_nodal": [_MP, _P, _P, _P, _P],
     "dzb_tm_dc_nodal_range": [_MP, _P, _P, _P, _L, _L, _P],
+    "dzb_tm_dc_nodal_multi": [_MP, _P, _P, _P, _I, _L, _P],
     "dzb_tm_dc_cell": [_MP, _P, _I, _P, _P, _P],
     "dzb_tm_dc_cell_mi": [_MP, _P, _I, _P, _P, _P],
     "dzb_tm_maxwell": [_MP, _P, _P, _P, _P, _P],

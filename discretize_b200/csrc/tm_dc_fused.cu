@@ -220,9 +220,15 @@ template <int RY, int NWC, int PARX> struct DcRing {
 
 template <int RY, int NWC, int PARX>
 __global__ void __launch_bounds__((NWC + 1) * 32, 1)
-    k_dc_nodal_ring(TM m, const double *__restrict__ sigma, const double *__restrict__ phi, double *__restrict__ y,
-                    int kchunk, int nwc, int k_begin, int k_end) {
+    k_dc_nodal_ring(TM m, const double *__restrict__ sigma, const double *__restrict__ phi_all, double *__restrict__ y_all,
+                    int kchunk, int nwc, int k_begin, int k_end, int nrhs, long long ldx) {
   typedef DcRing<RY, NWC, PARX> G;
+  // multi-RHS launch: blockIdx.x = x-block * nrhs + rhs -- the right-hand side is the FASTEST index of the launch order, so
+  // that the nrhs blocks that stage the same sigma tile run side by side and all but the first find it in L2 (sigma is
+  // 1/3 of the traffic of one apply)
+  const int rhs = (int)(blockIdx.x % (unsigned)nrhs), xblock = (int)(blockIdx.x / (unsigned)nrhs), zchunk = (int)blockIdx.z;
+  const double *__restrict__ phi = phi_all + (long long)rhs * ldx;
+  double *__restrict__ y = y_all + (long long)rhs * ldx;
   constexpr int RP = G::RP, RC = G::RC, S = DC_SLOTS, PP = G::PP, CP = G::CP;
   static_assert(S == 4, "the consumer loop is unrolled over a ring of four slots");
   extern __shared__ __align__(128) unsigned char dc_smem_raw[];
@@ -239,8 +245,8 @@ __global__ void __launch_bounds__((NWC + 1) * 32, 1)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = (nwc + 1) * 32;
   const int j0 = blockIdx.y * RY;
-  const int Xb = blockIdx.x * (nwc * DC_XOUT);
-  const int kb = k_begin + blockIdx.z * kchunk;
+  const int Xb = xblock * (nwc * DC_XOUT);
+  const int kb = k_begin + zchunk * kchunk;
   const int ke = min(kb + kchunk, k_end);
   const int jfirst = kb - 2;  // first stage of this block
 
@@ -421,7 +427,7 @@ extern "C" void dzb_tune_dc_variant(int variant) { g_dc_variant = variant; }
 
 template <int RY, int NWC, int PARX>
 static int launch_dc_ring_t(const TM &m, const double *sigma, const double *phi, double *y, int kchunk, int xblocks,
-                            int nwc, int k_begin, int k_end, cudaStream_t s) {
+                            int nwc, int k_begin, int k_end, cudaStream_t s, int nrhs = 1, long long ldx = 0) {
   typedef DcRing<RY, NWC, PARX> G;
   // the attribute is per device (a process may drive several GPUs); setting it is cheap, so no process-wide flag
   if (cudaFuncSetAttribute(k_dc_nodal_ring<RY, NWC, PARX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -433,16 +439,16 @@ static int launch_dc_ring_t(const TM &m, const double *sigma, const double *phi,
   const int zb_target = (4 * 148 + nxy - 1) / nxy;
   const int fair = (k_end - k_begin + zb_target - 1) / zb_target;
   kchunk = kchunk < fair ? kchunk : (fair < 8 ? 8 : fair);
-  dim3 grid((unsigned)xblocks, (unsigned)((nNy + RY - 1) / RY), (unsigned)((k_end - k_begin + kchunk - 1) / kchunk));
+  dim3 grid((unsigned)xblocks * nrhs, (unsigned)((nNy + RY - 1) / RY), (unsigned)((k_end - k_begin + kchunk - 1) / kchunk));
   k_dc_nodal_ring<RY, NWC, PARX><<<grid, dim3((nwc + 1) * 32), G::SMEM, s>>>(m, sigma, phi, y, kchunk, nwc, k_begin,
-                                                                           k_end);
+                                                                           k_end, nrhs, ldx);
   return 0;
 }
 
 constexpr int DC_NWC_BIG = 18, DC_NWC_SMALL = 6;
 
 static int launch_dc_ring(const TM &m, const double *sigma, const double *phi, double *y, int kchunk, int k_begin,
-                          int k_end, cudaStream_t s) {
+                          int k_end, cudaStream_t s, int nrhs = 1, long long ldx = 0) {
   const int nNx = (int)m.nx + 1;
   const int strips = (nNx + DC_XOUT - 1) / DC_XOUT;
   const bool small = strips <= DC_NWC_SMALL;
@@ -452,10 +458,10 @@ static int launch_dc_ring(const TM &m, const double *sigma, const double *phi, d
   kchunk = kchunk > DC_MAXCHUNK ? DC_MAXCHUNK : kchunk;
   const int parx = (int)(m.nx & 1);
   if (small)
-    return parx ? launch_dc_ring_t<4, DC_NWC_SMALL, 1>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s)
-                : launch_dc_ring_t<4, DC_NWC_SMALL, 0>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s);
-  return parx ? launch_dc_ring_t<4, DC_NWC_BIG, 1>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s)
-              : launch_dc_ring_t<4, DC_NWC_BIG, 0>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s);
+    return parx ? launch_dc_ring_t<4, DC_NWC_SMALL, 1>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, nrhs, ldx)
+                : launch_dc_ring_t<4, DC_NWC_SMALL, 0>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, nrhs, ldx);
+  return parx ? launch_dc_ring_t<4, DC_NWC_BIG, 1>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, nrhs, ldx)
+              : launch_dc_ring_t<4, DC_NWC_BIG, 0>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, nrhs, ldx);
 }
 
 extern "C" int dzb_tm_dc_nodal_range(const DzbTensorMesh *mm, const double *sigma, const double *phi, double *y,
@@ -491,6 +497,32 @@ extern "C" int dzb_tm_dc_nodal_range(const DzbTensorMesh *mm, const double *sigm
   else if (ry == 4) k_dc_nodal<4, 4><<<grid, block, 0, s>>>(m, sigma, phi, y, kchunk, kb0, ke0);
   else k_dc_nodal<8, 2><<<grid, block, 0, s>>>(m, sigma, phi, y, kchunk, kb0, ke0);
   return check_launch("dzb_tm_dc_nodal");
+}
+
+// y[r] = A phi[r] for nrhs right-hand sides stored one after the other (right-hand side r at phi + r * ldx): ONE launch;
+// the blocks of the nrhs right-hand sides that stage the same sigma tile run side by side and share it through L2.
+extern "C" int dzb_tm_dc_nodal_multi(const DzbTensorMesh *mm, const double *sigma, const double *phi, double *y, int nrhs,
+                                     int64_t ldx, void *stream) {
+  if (!mm || mm->nx <= 0 || mm->ny <= 0 || mm->nz <= 0) {
+    set_error("dzb_tm_dc_nodal_multi: invalid mesh");
+    return -1;
+  }
+  TM m(*mm);
+  if (nrhs < 1 || ldx < m.nN()) {
+    set_error("dzb_tm_dc_nodal_multi: nrhs >= 1 and ldx >= number of nodes required");
+    return -1;
+  }
+  const i64 nNx = m.nx + 1, nNy = m.ny + 1, nNz = m.nz + 1;
+  const bool ring = g_dc_variant == 1 && m.ny >= 2 && m.nN() < ((i64)1 << 31) && nNx * nNy < ((i64)1 << 31) &&
+                    nrhs <= 4096;
+  if (ring && launch_dc_ring(m, sigma, phi, y, g_dc_kchunk, 0, (int)nNz, (cudaStream_t)stream, nrhs, ldx) == 0)
+    return check_launch("dzb_tm_dc_nodal_multi");
+  cudaGetLastError();
+  for (int r = 0; r < nrhs; ++r) {
+    const int rc = dzb_tm_dc_nodal_range(mm, sigma, phi + (i64)r * ldx, y + (i64)r * ldx, 0, nNz, stream);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 extern "C" int dzb_tm_dc_nodal(const DzbTensorMesh *mm, const double *sigma, const double *phi, double *y,

@@ -184,6 +184,19 @@ class Operator(LinearOperator):
                 y = yd.cpu().numpy()
             return y.reshape(-1, 1) if x.ndim == 2 else y
         if x.ndim == 2 and x.shape[0] == n_in:
+            multi = getattr(self, "_dev_apply_t_multi" if transpose else "_dev_apply_multi", None)
+            if multi is not None and x.shape[1] > 1:
+                # multi-RHS kernels take the right-hand sides one after the other: (k, n) row-major = the columns of a
+                # Fortran-ordered (n, k) block, which is passed through without a copy
+                dev = cuda_device()
+                if is_torch:
+                    xt = x.to(device=dev, dtype=torch.float64).T
+                else:
+                    xt = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64).T)).to(dev)
+                xt = xt if xt.is_contiguous() else xt.contiguous()
+                yt = torch.empty((xt.shape[0], self.shape[1] if transpose else self.shape[0]), dtype=torch.float64, device=dev)
+                multi(xt, yt)
+                return yt.T if is_torch else yt.cpu().numpy().T
             xd = to_device(x)
             cols = [self.apply_device(xd[:, c].contiguous(), transpose) for c in range(xd.shape[1])]
             yd = torch.stack(cols, dim=1) if cols else torch.empty(

@@ -317,6 +317,18 @@ class DCNodalOperator(Operator):
 
     _dev_apply_t = _dev_apply
 
+    def _dev_apply_multi(self, xs, outs):
+        """``outs[r] = A xs[r]`` for the rows of a (k, n) block in ONE launch (``matmat``): sigma is read from DRAM once
+        per tile instead of once per right-hand side (the k blocks of a tile run side by side and share it through L2)."""
+        # measured at 512^3 (tools/bench_multi_rhs.py): 2 right-hand sides +4.5 %, 4: +7.7 %, 8: none -- beyond 4 the tiles of a
+        # group no longer stay in L2 together, so larger blocks go in groups of 4
+        for r0 in range(0, xs.shape[0], 4):
+            k = min(4, xs.shape[0] - r0)
+            check(load().dzb_tm_dc_nodal_multi(C.byref(self.mesh.device_mesh()), ptr(self.sigma), ptr(xs[r0:r0 + k]),
+                                               ptr(outs[r0:r0 + k]), k, int(xs.shape[1]), stream_ptr()), "dzb_tm_dc_nodal_multi")
+
+    _dev_apply_t_multi = _dev_apply_multi
+
     def diagonal_device(self):
         """diag(G^T Me G) = (G o G)^T diag(Me): one apply of the entrywise-squared gradient to the edge mass
         diagonal (the Jacobi preconditioner of ``solvers.pcg``)."""

@@ -147,6 +147,11 @@ int dzb_tm_mass_deriv_apply(const DzbTensorMesh *m, int flags, int model_kind, c
  * (rows are staged with 16-byte bulk copies that stop at the aligned bounds inside the arrays; the at most
  * one element left at an odd-aligned end is staged by a plain load). */
 int dzb_tm_dc_nodal(const DzbTensorMesh *m, const double *sigma, const double *phi, double *y, void *stream);
+/* The same operator on nrhs right-hand sides in ONE launch (multi-source DC surveys: scipy's matmat): right-hand side r is
+ * phi + r * ldx, its result y + r * ldx (ldx >= nN).  sigma is read from DRAM once per tile, not once per right-hand
+ * side: the nrhs blocks that stage the same tile are scheduled side by side and share it through L2. */
+int dzb_tm_dc_nodal_multi(const DzbTensorMesh *m, const double *sigma, const double *phi, double *y, int nrhs, int64_t ldx,
+                          void *stream);
 /* Same, writing only the node planes k_begin <= k < k_end of y (0 <= k <= nz).  This is the
  * building block of the z-slab decomposition: a rank applies it to its local sub-mesh (its cell
  * layers plus one halo layer / node plane per neighbour) for the planes it owns, interior

@@ -679,3 +679,25 @@ def test_frequency_domain_maxwell_operator():
     assert_close_vec(S @ e, (1.5 - 2j) * (M @ e))
     assert_close_vec((S.H @ e), (1.5 + 2j) * (M @ e))
     assert_close_vec(((2j * Cd) @ e), 2j * (C @ e))
+
+
+def test_dc_nodal_multi_rhs():
+    """matmat on the fused DC operator: all right-hand sides in one launch, for numpy (C- and F-ordered) and CUDA blocks."""
+    mesh, grid = make_pair("wide")
+    rng = np.random.default_rng(61)
+    sigma = np.exp(rng.standard_normal(grid.nC))
+    G = T.nodal_gradient(grid)
+    ref = (G.T @ T.inner_product(grid, "E", sigma) @ G).tocsr()
+    Gd = mesh.nodal_gradient
+    A = Gd.T @ mesh.get_edge_inner_product(sigma) @ Gd
+    X = rng.standard_normal((grid.nN, 5))
+    want = ref @ X
+    assert_close_vec(A @ X, want)
+    assert_close_vec(A.matmat(np.asfortranarray(X)), want)
+    assert_close_vec(A.T @ X, want)
+    Xt = torch.as_tensor(X).cuda()
+    Y = A @ Xt
+    assert Y.shape == (grid.nN, 5) and Y.is_cuda
+    assert_close_vec(Y.cpu().numpy(), want)
+    for c in range(5):                                    # bitwise the single right-hand side kernel
+        assert np.array_equal(Y[:, c].cpu().numpy(), (A @ Xt[:, c].contiguous()).cpu().numpy())
