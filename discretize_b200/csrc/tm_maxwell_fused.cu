@@ -12,7 +12,10 @@
 #include "tm_mass_common.cuh"
 #include "tm_maxwell_rows.cuh"
 #include "tm_maxwell_tmap.cuh"
+#include "tm_maxwell_cplx.cuh"
 #include <cudaTypedefs.h>
+#include <cstdio>
+#include <cstdlib>
 #include "tm_rowkernels.cuh"
 
 namespace dzb {
@@ -289,8 +292,15 @@ static int launch_m3_t(const TM &m, const double *mui, const double *sigma, cons
 
 static int launch_m3(const TM &m, const double *mui, const double *sigma, const double *e, double *y, int k_begin,
                      int k_end, int k_begin2, int k_end2, cudaStream_t s, const M3Peers *peers = nullptr) {
+  static const bool env_read = []() {       // DZB_K9_SHAPE=xs,r,slots: experiment knob, like dzb_tune_maxwell_tmap
+    int a, b, c;
+    const char *v = getenv("DZB_K9_SHAPE");
+    if (v && sscanf(v, "%d,%d,%d", &a, &b, &c) == 3) g_m3_xs = a, g_m3_r = b, g_m3_ns = c;
+    return true;
+  }();
+  (void)env_read;
   const int parx = (int)(m.nx & 1);
-  switch (g_m3_xs * 100 + g_m3_r * 10 + g_m3_ns) {
+  switch (g_m3_r < 10 ? g_m3_xs * 100 + g_m3_r * 10 + g_m3_ns : g_m3_xs * 1000 + g_m3_r * 10 + g_m3_ns) {
     case 144: M3_LAUNCH(1, 4, 4, 3);
     case 146: M3_LAUNCH(1, 4, 6, 3);
     case 154: M3_LAUNCH(1, 5, 4, 3);
@@ -307,6 +317,10 @@ static int launch_m3(const TM &m, const double *mui, const double *sigma, const 
     case 284: M3_LAUNCH(2, 8, 4, 1);
     case 286: M3_LAUNCH(2, 8, 6, 1);
     case 444: M3_LAUNCH(4, 4, 4, 1);
+    case 1126: M3_LAUNCH(1, 12, 6, 1);
+    case 1164: M3_LAUNCH(1, 16, 4, 1);
+    case 1166: M3_LAUNCH(1, 16, 6, 1);
+    case 2104: M3_LAUNCH(2, 10, 4, 1);
     default: break;
   }
   M3_LAUNCH(2, 8, 6, 1);
@@ -314,6 +328,78 @@ static int launch_m3(const TM &m, const double *mui, const double *sigma, const 
 
 extern "C" int dzb_tm_maxwell_range(const DzbTensorMesh *mm, const double *mui, const double *sigma, const double *e,
                                     double *y, int64_t k_begin, int64_t k_end, void *stream);
+
+// ---------------------------------------------------------------------------------------------------------------
+// complex edge fields: y = C^T Mf(mui) C e + (a + ib) Me(sigma) e in one launch (tm_maxwell_cplx.cuh)
+// ---------------------------------------------------------------------------------------------------------------
+template <int XS, int R, int PARX, int NSLOT, int MINB>
+static int launch_m3c_t(const TM &m, const double *mui, const double *sigma, double ar, double ai, const double *e, double *y,
+                        cudaStream_t s) {
+  typedef Mx3c<XS, R, PARX, NSLOT> G;
+  PFN_cuTensorMapEncodeTiled enc = tmap_encoder();
+  if (!enc) return -1;
+  const i64 nx = m.nx, ny = m.ny, nz = m.nz, nNx = nx + 1, nNy = ny + 1, nNz = nz + 1;
+  const i64 nEx = nx * nNy * nNz, nEy = nNx * ny * nNz;
+  M3Maps maps;
+  // the three edge components as float64 matrices with 2 * pitch columns (interleaved re / im): every row starts on a
+  // 16-byte boundary, so one plain map each
+  const double *eb[3] = {e, e + 2 * nEx, e + 2 * (nEx + nEy)};
+  const i64 epitch[3] = {2 * nx, 2 * nNx, 2 * nNx};
+  const i64 erows[3] = {nNy * nNz, ny * nNz, nNy * nz};
+  for (int a = 0; a < 3; ++a)
+    if (m3_encode_array(enc, eb[a], epitch[a], erows[a], 2 * G::WE, G::rows(a), &maps.m[a], &maps.o[a]) != 0) return -1;
+  if (m3_encode_array(enc, mui, nx, ny * nz, G::W, G::hbox(3), &maps.m[3], &maps.o[3]) != 0) return -1;
+  if (m3_encode_array(enc, sigma, nx, ny * nz, G::W, G::hbox(4), &maps.m[4], &maps.o[4]) != 0) return -1;
+  for (int side = 0; side < 2; ++side)
+    for (int a = 0; a < 3; ++a) maps.pm[side][a] = maps.m[a], maps.po[side][a] = maps.o[a];
+  if (cudaFuncSetAttribute(k_maxwell_cplx<XS, R, PARX, NSLOT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)G::SMEM) != cudaSuccess)
+    return -1;
+  const int planes = (int)nNz;
+  const int xblocks = (int)((nNx + XS * M3_XOUT - 1) / (XS * M3_XOUT)), yblocks = (int)((nNy + R - 1) / R);
+  int nchunks = (planes + 143) / 144;
+  const long long nxy = (long long)xblocks * yblocks;
+  const long long want = (4ll * 148 * MINB + nxy - 1) / nxy;
+  if (nchunks < want) nchunks = (int)(want < (planes + 7) / 8 ? want : (planes + 7) / 8);
+  if (nchunks < 1) nchunks = 1;
+  const int kchunk = (planes + nchunks - 1) / nchunks;
+  dim3 grid((unsigned)xblocks, (unsigned)yblocks, (unsigned)((planes + kchunk - 1) / kchunk));
+  k_maxwell_cplx<XS, R, PARX, NSLOT, MINB><<<grid, dim3(G::NT), G::SMEM, s>>>(m, maps, y, ar, ai, kchunk, 0, planes);
+  return 0;
+}
+
+static int g_m3c_xs = 1, g_m3c_r = 6;
+extern "C" void dzb_tune_maxwell_cplx(int xs, int r) {
+  g_m3c_xs = xs;
+  g_m3c_r = r;
+}
+
+// e, y: interleaved complex (2 * nE doubles).  Returns -2 where the tensor-map path does not apply (the caller then applies
+// the real kernels to the two parts).
+extern "C" int dzb_tm_maxwell_cplx(const DzbTensorMesh *mm, const double *mui, const double *sigma, double alpha_re,
+                                   double alpha_im, const double *e, double *y, void *stream) {
+  if (!valid_mesh(mm)) return -1;
+  TM m(*mm);
+  const bool ring_ok = m.ny >= 1 && (m.nx + 1) * (m.ny + 1) < ((i64)1 << 31);
+  if (ring_ok) {
+    const int parx = (int)(m.nx & 1);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if (g_m3c_xs == 2 && g_m3c_r == 4)
+      rc = parx ? launch_m3c_t<2, 4, 1, 4, 1>(m, mui, sigma, alpha_re, alpha_im, e, y, s)
+                : launch_m3c_t<2, 4, 0, 4, 1>(m, mui, sigma, alpha_re, alpha_im, e, y, s);
+    else if (g_m3c_xs == 1 && g_m3c_r == 6)
+      rc = parx ? launch_m3c_t<1, 6, 1, 4, 2>(m, mui, sigma, alpha_re, alpha_im, e, y, s)
+                : launch_m3c_t<1, 6, 0, 4, 2>(m, mui, sigma, alpha_re, alpha_im, e, y, s);
+    else
+      rc = parx ? launch_m3c_t<1, 8, 1, 4, 1>(m, mui, sigma, alpha_re, alpha_im, e, y, s)
+                : launch_m3c_t<1, 8, 0, 4, 1>(m, mui, sigma, alpha_re, alpha_im, e, y, s);
+    if (rc == 0) return check_launch("dzb_tm_maxwell_cplx");
+    cudaGetLastError();
+  }
+  set_error("dzb_tm_maxwell_cplx: needs the tensor-map path (16-byte aligned e, mui, sigma)");
+  return -2;
+}
 
 // A z-slab's apply with PEER-READ halos: ex, ey on the local node planes lo_plane / hi_plane and ez in the local layer
 // lo_plane are not read from `e` but from the neighbours' local edge vectors e_lo / e_hi (device pointers into peer memory

@@ -416,11 +416,13 @@ class ScaledOperator(Operator):
 
     def _dev_apply(self, x, out):
         self.base._dev_apply(x, out)
-        out.mul_(self.alpha)
+        if self.alpha != 1.0:
+            out.mul_(self.alpha)
 
     def _dev_apply_t(self, x, out):
         self.base._dev_apply_t(x, out)
-        out.mul_(self.alpha)
+        if self.alpha != 1.0:
+            out.mul_(self.alpha)
 
     def _apply_complex(self, x, transpose):
         return self.alpha * self.base._apply_any(x, transpose)     # .T is the plain transpose: alpha is not conjugated
@@ -460,19 +462,34 @@ class SumOperator(Operator):
         fused = fuse_sum(flat)
         return fused if fused is not None else SumOperator(flat)
 
+    def _scratch(self, like):
+        """One temporary per operator and output size, kept between applies (no allocation on the apply path)."""
+        t = getattr(self, "_tmp", None)
+        if t is None or t.shape != like.shape or t.device != like.device:
+            t = self._tmp = torch.empty_like(like)
+        return t
+
     def _dev_apply(self, x, out):
         self.terms[0]._dev_apply(x, out)
-        tmp = torch.empty_like(out)
+        tmp = self._scratch(out)
         for t in self.terms[1:]:
-            t._dev_apply(x, tmp)
-            out.add_(tmp)
+            if isinstance(t, ScaledOperator):          # alpha * B: one fused multiply-add pass instead of scale + add
+                t.base._dev_apply(x, tmp)
+                out.add_(tmp, alpha=t.alpha)
+            else:
+                t._dev_apply(x, tmp)
+                out.add_(tmp)
 
     def _dev_apply_t(self, x, out):
         self.terms[0]._dev_apply_t(x, out)
-        tmp = torch.empty_like(out)
+        tmp = self._scratch(out)
         for t in self.terms[1:]:
-            t._dev_apply_t(x, tmp)
-            out.add_(tmp)
+            if isinstance(t, ScaledOperator):
+                t.base._dev_apply_t(x, tmp)
+                out.add_(tmp, alpha=t.alpha)
+            else:
+                t._dev_apply_t(x, tmp)
+                out.add_(tmp)
 
     def _transpose(self):
         return SumOperator.make([t.T for t in self.terms])

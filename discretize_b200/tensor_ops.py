@@ -595,6 +595,21 @@ class ComplexMaxwellOperator(Operator):
         self._kam = MaxwellOperator(mesh, mui_dev, sigma_dev * alpha.real)
         self._bm = MassOperator(mesh, "E", _Model(mesh, sigma_dev * alpha.imag), False, False)
 
+    #: the one-launch kernel on interleaved complex edges (K9c); False forces the two-part path below (tests compare them)
+    fused = True
+
+    def apply_device_complex(self, xc, out=None):
+        """y = A x for a complex128 CUDA tensor in ONE launch (K9c); returns None where the tensor-map path does not apply."""
+        if out is None:
+            out = torch.empty_like(xc)
+        xr_, yr_ = torch.view_as_real(xc), torch.view_as_real(out)          # interleaved (re, im) storage
+        rc = load().dzb_tm_maxwell_cplx(C.byref(self.mesh.device_mesh()), ptr(self.mui), ptr(self.sigma), self.alpha.real,
+                                        self.alpha.imag, ptr(xr_), ptr(yr_), stream_ptr())
+        if rc == -2:
+            return None
+        check(rc, "dzb_tm_maxwell_cplx")
+        return out
+
     def _apply_complex(self, x, transpose):
         is_torch = isinstance(x, torch.Tensor)
         xa = x if is_torch else np.asarray(x)
@@ -605,6 +620,16 @@ class ComplexMaxwellOperator(Operator):
         if flat.shape[0] != self.shape[1]:
             raise ValueError(f"dimension mismatch: operator {self.shape}, input {tuple(xa.shape)}")
         cplx = flat.is_complex() if is_torch else np.iscomplexobj(flat)
+        if self.fused:
+            dev = cuda_device()
+            xc = (flat if is_torch else torch.from_numpy(np.ascontiguousarray(flat))).to(device=dev, dtype=torch.complex128).contiguous()
+            yc = self.apply_device_complex(xc)
+            if yc is not None:
+                if is_torch:
+                    yc = yc if x.device.type == "cuda" else yc.cpu()
+                else:
+                    yc = yc.cpu().numpy()
+                return yc.reshape(xa.shape) if xa.ndim == 2 else yc
         xr = to_device(flat.real if cplx else flat)
         yr, yi = self._kam.apply_device(xr), self._bm.apply_device(xr)
         if cplx:

@@ -192,6 +192,12 @@ int dzb_tm_maxwell_range_peer(const DzbTensorMesh *m, const double *mui, const d
                               const double *e_lo, int64_t nz_lo, int64_t lo_plane, int64_t lo_peer_plane,
                               const double *e_hi, int64_t nz_hi, int64_t hi_plane, int64_t hi_peer_plane, double *y,
                               int64_t k_begin, int64_t k_end, void *stream);
+/* y = C^T Mf(mui) C e + (alpha_re + i alpha_im) Me(sigma) e for a COMPLEX edge field in ONE launch: e and y are
+ * interleaved (re, im) arrays of 2 nE doubles (numpy / torch complex128).  This is the frequency-domain Maxwell operator
+ * SimPEG applies (alpha = i omega).  Face weights and edge masses are computed once for both parts.
+ * Returns -2 where the tensor-map path does not apply (e, mui, sigma not 16-byte aligned). */
+int dzb_tm_maxwell_cplx(const DzbTensorMesh *m, const double *mui, const double *sigma, double alpha_re, double alpha_im,
+                        const double *e, double *y, void *stream);
 
 /* ---- interpolation: get_interpolation_matrix --------------------------------- */
 /* base/base_tensor_mesh.py:684-790 -> utils/interpolation_utils.py:44-172 ->

@@ -664,7 +664,11 @@ def test_frequency_domain_maxwell_operator():
     A = Cd.T @ mesh.get_face_inner_product(mui) @ Cd + 1j * omega * mesh.get_edge_inner_product(sigma)
     assert isinstance(A, ComplexMaxwellOperator) and A.dtype == np.complex128
     e = rng.standard_normal(grid.nE) + 1j * rng.standard_normal(grid.nE)
-    assert_close_vec(A @ e, ref @ e)
+    assert_close_vec(A @ e, ref @ e)                        # K9c: one launch on the interleaved complex field
+    assert A.apply_device_complex(torch.as_tensor(e).cuda()) is not None
+    A.fused = False
+    assert_close_vec(A @ e, ref @ e)                        # two-part path: K9 on a*sigma, K5 on b*sigma
+    A.fused = True
     assert_close_vec(A @ e.real, ref @ e.real)
     assert_close_vec(A.T @ e, ref.T @ e)
     assert_close_vec(A.H @ e, ref.conj().T @ e)
@@ -701,3 +705,34 @@ def test_dc_nodal_multi_rhs():
     assert_close_vec(Y.cpu().numpy(), want)
     for c in range(5):                                    # bitwise the single right-hand side kernel
         assert np.array_equal(Y[:, c].cpu().numpy(), (A @ Xt[:, c].contiguous()).cpu().numpy())
+
+
+@pytest.mark.parametrize("shape", [(40, 24, 36), (33, 18, 7), (64, 31, 12), (5, 4, 3), (70, 9, 37)])
+@pytest.mark.parametrize("cfg", [(1, 6), (1, 8), (2, 4)])
+def test_complex_maxwell_kernel_shapes(shape, cfg):
+    """K9c on even / odd sized meshes (odd nx: super-row maps for the two model arrays), every block shape."""
+    import ctypes
+
+    import discretize_b200 as dz
+    from discretize_b200._lib import load
+
+    lib = load()
+    lib.dzb_tune_maxwell_cplx.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.dzb_tune_maxwell_cplx.restype = None
+    rng = np.random.default_rng(71)
+    h = [rng.random(n) + 0.5 for n in shape]
+    mesh, grid = dz.TensorMesh(h), T.Grid(h)
+    sigma, mui = np.exp(rng.standard_normal(grid.nC)), np.exp(rng.standard_normal(grid.nC))
+    C = T.edge_curl(grid)
+    alpha = 0.3 - 2.5j
+    ref = (C.T @ T.inner_product(grid, "F", mui) @ C + alpha * T.inner_product(grid, "E", sigma)).tocsr()
+    Cd = mesh.edge_curl
+    A = Cd.T @ mesh.get_face_inner_product(mui) @ Cd + alpha * mesh.get_edge_inner_product(sigma)
+    e = rng.standard_normal(grid.nE) + 1j * rng.standard_normal(grid.nE)
+    lib.dzb_tune_maxwell_cplx(*cfg)
+    try:
+        y = A.apply_device_complex(torch.as_tensor(e).cuda())
+        assert y is not None
+        assert_close_vec(y.cpu().numpy(), ref @ e)
+    finally:
+        lib.dzb_tune_maxwell_cplx(1, 6)

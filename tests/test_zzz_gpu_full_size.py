@@ -123,6 +123,30 @@ def test_config5_maxwell_1024():
             assert np.abs(got - want).max() <= RTOL * np.abs(want).max(), (a, name, np.abs(got - want).max())
 
 
+def test_frequency_domain_maxwell_512_one_launch():
+    """C^T Mf C + i omega Me on a complex 512^3 field (K9c, one launch) against the real kernels applied to both parts."""
+    import discretize_b200 as dz
+
+    n, dev = 512, torch.device("cuda")
+    mesh = dz.TensorMesh([n, n, n])
+    er, ei = _randn(mesh.nE, 21, dev), _randn(mesh.nE, 22, dev)
+    sigma = torch.exp(_randn(mesh.nC, 23, dev))
+    mui = torch.exp(_randn(mesh.nC, 24, dev))
+    omega = 2 * np.pi * 7.0
+    C = mesh.edge_curl
+    Mf, Me = mesh.get_face_inner_product(mui), mesh.get_edge_inner_product(sigma)
+    A = C.T @ Mf @ C + 1j * omega * Me
+    assert type(A).__name__ == "ComplexMaxwellOperator"
+    y = A.apply_device_complex(torch.complex(er, ei))
+    assert y is not None
+    K = lambda v: C.T.apply_device(Mf.apply_device(C.apply_device(v)))
+    want_r = K(er) - omega * Me.apply_device(ei)
+    want_i = K(ei) + omega * Me.apply_device(er)
+    scale = float(torch.maximum(want_r.abs().max(), want_i.abs().max()))
+    assert float((y.real - want_r).abs().max()) <= RTOL * scale
+    assert float((y.imag - want_i).abs().max()) <= RTOL * scale
+
+
 # ------------------------------------------------------------------------------------------------------------
 # config 4: 1e8 random points on TensorMesh 512^3
 # ------------------------------------------------------------------------------------------------------------

@@ -50,11 +50,11 @@ lib.dzb_tune_maxwell_l2promo.restype = None
 lib.dzb_tune_maxwell_l2promo(promo)
 lib.dzb_tune_maxwell_l2hint.argtypes = [ctypes.c_int]
 lib.dzb_tune_maxwell_l2hint.restype = None
-lib.dzb_tune_maxwell_l2hint(int(os.environ.get("DZB_L2HINT", "0")))
+lib.dzb_tune_maxwell_l2hint(int(os.environ.get("DZB_L2HINT", "1")))
 if which in ("v3", "all"):
     lib.dzb_tune_maxwell_tmap.argtypes = [ctypes.c_int] * 3
     lib.dzb_tune_maxwell_tmap.restype = None
-    shapes3 = ((1, 6, 6), (2, 6, 6), (2, 8, 6))
+    shapes3 = ((2, 8, 6), (1, 12, 6), (1, 16, 4), (1, 16, 6), (2, 10, 4))
     cases += [(3, sh, 0, 0) for sh in shapes3]
 for variant, a, b, kc in cases:
     lib.dzb_tune_maxwell(variant, kc)
