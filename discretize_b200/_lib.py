@@ -74,6 +74,10 @@ SIGNATURES = {
     "dzb_interp_apply_perm": [_P, _I, _P, _P, _P, _L, _P, _P, _P],
     "dzb_interp_apply_t_perm": [_P, _I, _P, _P, _P, _L, _P, _P, _P],
     "dzb_gather_rows": [_L, _P, _P, _P, _P],
+    "dzb_interp_locate_compact": [_P, _L, _P, _L, _P, _L, _P, _L, _L, _P, _I, _P, _P, _P, _P],
+    "dzb_interp_apply_compact": [_P, _I, _P, _P, _P, _L, _L, _P, _L, _P, _P, _P],
+    "dzb_interp_apply_t_compact": [_P, _I, _P, _P, _P, _L, _L, _P, _P, _L, _P, _P, _P],
+    "dzb_interp_expand": [_P, _I, _P, _P, _P, _L, _L, _L, _P, _I, _P, _P],
     "dzb_interp_fused": [_P, _L, _P, _L, _P, _L, _P, _L, _L, _P, _P, _P, _P],
     "dzb_tree_spmv": [_L, _P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _I, _P],
     "dzb_tree_ell_spmv": [_L, _I, _L, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P],

@@ -176,6 +176,9 @@ __global__ void __launch_bounds__(256) k_interp_apply(const IDX *__restrict__ co
 
 // dst[i] = src[idx[i]]: brings a result computed in bucket order back to point order.  A random 8-byte READ costs one
 // 32-byte sector; the equivalent scatter (dst[perm[p]] = ..) costs a sector fill plus a sector write-back per value.
+// 1e8 values take 2.2 ms = 46 G random sectors / s, the rate of the memory system whatever the unrolling; routing the
+// values through destination blocks in two passes (scattered writes merged in L2, then reads inside an L2-resident
+// window) measures 3.8 ms or more (tools/perm_probe).
 __global__ void __launch_bounds__(256) k_gather_rows(i64 n, const double *__restrict__ src, const int *__restrict__ idx,
                                                      double *__restrict__ dst) {
   const i64 stride = (i64)gridDim.x * blockDim.x;
@@ -224,6 +227,108 @@ __global__ void __launch_bounds__(256) k_interp_fused(Axes g, const double *__re
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc += w8[e] * __ldg(v + c8[e]);
     y[p] = scale ? acc * __ldg(scale + p) : acc;
+  }
+}
+
+
+// ---- compact tables (K10c / K11c) ---------------------------------------------------------------------------------
+// The eight entries of a row are a product structure: columns base + {0,1} + {0,sy} + {0,sz}, weights
+// ((wx * wy) * wz) with w2 = 1 - w1 per axis.  A compact row keeps the flat index of the first grid sample and the three
+// w1 (28 bytes instead of 96); the kernels rebuild columns and weights with the reference's expressions, so the expanded
+// tables are bit-identical to K10's.  An unclamped w1 = (a[i2] - x) / (a[i2] - a[i1]) with a[i1] <= x < a[i2] lies in
+// (0, 1]; where the axis is clamped (i2 == i1, both weights 0.5 in the reference) the weight is stored as -0.5, the
+// sign being the "no step along this axis" flag.
+// One THREAD per point: its eight gathers are in flight together (the 8-lanes-per-point kernel above keeps only four
+// points per warp in flight and is latency-bound: ncu long_scoreboard 76 %, DRAM 38 % busy).
+__device__ __forceinline__ double compact_weight(const AxisHit &h) { return h.i1 == h.i2 ? -0.5 : h.w1; }
+
+template <typename IDX>
+__global__ void __launch_bounds__(256) k_interp_locate_c(Axes g, const double *__restrict__ pts, i64 npts, i64 col_offset,
+                                                         IDX *__restrict__ base, double *__restrict__ wx,
+                                                         double *__restrict__ wy, double *__restrict__ wz) {
+  Axes a = g;
+  axes_means(a);
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += stride) {
+    const AxisHit hx = locate_axis(a.tx, a.ntx, __ldg(pts + 3 * p), a.ix);
+    const AxisHit hy = locate_axis(a.ty, a.nty, __ldg(pts + 3 * p + 1), a.iy);
+    const AxisHit hz = locate_axis(a.tz, a.ntz, __ldg(pts + 3 * p + 2), a.iz);
+    base[p] = (IDX)(col_offset + hx.i1 + a.ntx * (hy.i1 + a.nty * hz.i1));
+    wx[p] = compact_weight(hx);
+    wy[p] = compact_weight(hy);
+    wz[p] = compact_weight(hz);
+  }
+}
+
+struct CompactRow {
+  i64 col[8];
+  double w[8];
+};
+
+// columns and weights of a compact row in the entry order of _interpmat3D (see entries())
+__device__ __forceinline__ CompactRow expand_row(i64 b, double ax, double ay, double az, i64 sy, i64 sz) {
+  const double x1 = fabs(ax), y1 = fabs(ay), z1 = fabs(az);
+  const double x2 = 1 - x1, y2 = 1 - y1, z2 = 1 - z1;
+  const i64 dx = ax < 0 ? 0 : 1, dy = ay < 0 ? 0 : sy, dz = az < 0 ? 0 : sz;
+  CompactRow r;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const bool ux = (e >> 1) & 1, uy = e & 1, uz = (e >> 2) & 1;
+    r.col[e] = b + (ux ? dx : 0) + (uy ? dy : 0) + (uz ? dz : 0);
+    r.w[e] = ((ux ? x2 : x1) * (uy ? y2 : y1)) * (uz ? z2 : z1);
+  }
+  return r;
+}
+
+template <typename IDX>
+__global__ void __launch_bounds__(256) k_interp_apply_c(const IDX *__restrict__ base, const double *__restrict__ wx,
+                                                        const double *__restrict__ wy, const double *__restrict__ wz,
+                                                        i64 sy, i64 sz, const double *__restrict__ scale, i64 npts,
+                                                        const double *__restrict__ v, double *__restrict__ y) {
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += stride) {
+    const CompactRow r = expand_row((i64)__ldg(base + p), __ldg(wx + p), __ldg(wy + p), __ldg(wz + p), sy, sz);
+    double xv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) xv[e] = __ldg(v + r.col[e]);
+    double acc = 0.0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc += r.w[e] * xv[e];
+    __stcs(y + p, scale ? acc * __ldg(scale + p) : acc);
+  }
+}
+
+// y[col[p,e]] += scale[p] w[p,e] x[perm ? perm[p] : p]
+template <typename IDX>
+__global__ void __launch_bounds__(256) k_interp_apply_t_c(const IDX *__restrict__ base, const double *__restrict__ wx,
+                                                          const double *__restrict__ wy, const double *__restrict__ wz,
+                                                          i64 sy, i64 sz, const double *__restrict__ scale,
+                                                          const int *__restrict__ perm, i64 npts,
+                                                          const double *__restrict__ x, double *__restrict__ y) {
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += stride) {
+    const CompactRow r = expand_row((i64)__ldg(base + p), __ldg(wx + p), __ldg(wy + p), __ldg(wz + p), sy, sz);
+    double xv = __ldg(x + (perm ? (i64)__ldg(perm + p) : p));
+    if (scale) xv *= __ldg(scale + p);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(y + r.col[e], r.w[e] * xv);
+  }
+}
+
+// the (npts, 8) tables of K10 from compact rows (for .tocsr() and for callers that want scipy-like arrays)
+template <typename IDX, typename CIDX>
+__global__ void __launch_bounds__(256) k_interp_expand(const IDX *__restrict__ base, const double *__restrict__ wx,
+                                                       const double *__restrict__ wy, const double *__restrict__ wz,
+                                                       i64 sy, i64 sz, i64 npts, CIDX *__restrict__ cols,
+                                                       double *__restrict__ w) {
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += stride) {
+    const CompactRow r = expand_row((i64)__ldg(base + p), __ldg(wx + p), __ldg(wy + p), __ldg(wz + p), sy, sz);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      cols[p * 8 + e] = (CIDX)r.col[e];
+      w[p * 8 + e] = r.w[e];
+    }
   }
 }
 
@@ -301,7 +406,7 @@ extern "C" int dzb_interp_apply_perm(const void *cols, int cols_is64, const doub
 
 extern "C" int dzb_gather_rows(int64_t n, const double *src, const int32_t *idx, double *dst, void *stream) {
   if (n == 0) return 0;
-  k_gather_rows<<<blocks_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(n, src, idx, dst);
+  k_gather_rows<<<blocks_for(n, 256, 32), 256, 0, (cudaStream_t)stream>>>(n, src, idx, dst);
   return check_launch("dzb_gather_rows");
 }
 
@@ -326,6 +431,66 @@ extern "C" int dzb_interp_apply_t_perm(const void *cols, int cols_is64, const do
 extern "C" int dzb_interp_apply_t(const void *cols, int cols_is64, const double *w, const double *row_scale,
                                   int64_t npts, const double *x, double *y, void *stream) {
   return dzb_interp_apply_t_perm(cols, cols_is64, w, row_scale, nullptr, npts, x, y, stream);
+}
+
+
+// ---- compact tables ----------------------------------------------------------------------------------------------
+extern "C" int dzb_interp_locate_compact(const double *tx, int64_t ntx, const double *ty, int64_t nty, const double *tz,
+                                         int64_t ntz, const double *pts, int64_t npts, int64_t col_offset, void *base,
+                                         int base_is64, double *wx, double *wy, double *wz, void *stream) {
+  if (npts == 0) return 0;
+  if (!base_is64 && col_offset + ntx * nty * ntz > 2147483647LL) {
+    set_error("dzb_interp_locate_compact: column indices do not fit int32; pass an int64 table (base_is64 = 1)");
+    return -1;
+  }
+  Axes g{tx, ty, tz, ntx, nty, ntz, 0.0, 0.0, 0.0};
+  const unsigned nb = blocks_for(npts, 256, 16);
+  if (base_is64) k_interp_locate_c<i64><<<nb, 256, 0, (cudaStream_t)stream>>>(g, pts, npts, col_offset, (i64 *)base, wx, wy, wz);
+  else k_interp_locate_c<int><<<nb, 256, 0, (cudaStream_t)stream>>>(g, pts, npts, col_offset, (int *)base, wx, wy, wz);
+  return check_launch("dzb_interp_locate_compact");
+}
+
+extern "C" int dzb_interp_apply_compact(const void *base, int base_is64, const double *wx, const double *wy,
+                                        const double *wz, int64_t ntx, int64_t nty, const double *row_scale, int64_t npts,
+                                        const double *v, double *y, void *stream) {
+  if (npts == 0) return 0;
+  const unsigned nb = blocks_for(npts, 256, 32);
+  const i64 sy = ntx, sz = ntx * nty;
+  if (base_is64) k_interp_apply_c<i64><<<nb, 256, 0, (cudaStream_t)stream>>>((const i64 *)base, wx, wy, wz, sy, sz, row_scale, npts, v, y);
+  else k_interp_apply_c<int><<<nb, 256, 0, (cudaStream_t)stream>>>((const int *)base, wx, wy, wz, sy, sz, row_scale, npts, v, y);
+  return check_launch("dzb_interp_apply_compact");
+}
+
+extern "C" int dzb_interp_apply_t_compact(const void *base, int base_is64, const double *wx, const double *wy,
+                                          const double *wz, int64_t ntx, int64_t nty, const double *row_scale,
+                                          const int32_t *perm, int64_t npts, const double *x, double *y, void *stream) {
+  if (npts == 0) return 0;
+  if (perm && npts >= ((int64_t)1 << 31)) {
+    set_error("dzb_interp_apply_t_compact: bucketed tables are limited to 2^31 - 1 points");
+    return -1;
+  }
+  const unsigned nb = blocks_for(npts, 256, 32);
+  const i64 sy = ntx, sz = ntx * nty;
+  if (base_is64) k_interp_apply_t_c<i64><<<nb, 256, 0, (cudaStream_t)stream>>>((const i64 *)base, wx, wy, wz, sy, sz, row_scale, perm, npts, x, y);
+  else k_interp_apply_t_c<int><<<nb, 256, 0, (cudaStream_t)stream>>>((const int *)base, wx, wy, wz, sy, sz, row_scale, perm, npts, x, y);
+  return check_launch("dzb_interp_apply_t_compact");
+}
+
+extern "C" int dzb_interp_expand(const void *base, int base_is64, const double *wx, const double *wy, const double *wz,
+                                 int64_t ntx, int64_t nty, int64_t npts, void *cols, int cols_is64, double *w,
+                                 void *stream) {
+  if (npts == 0) return 0;
+  if (base_is64 && !cols_is64) {
+    set_error("dzb_interp_expand: int64 compact rows need an int64 column table");
+    return -1;
+  }
+  const unsigned nb = blocks_for(npts, 256, 16);
+  const i64 sy = ntx, sz = ntx * nty;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (base_is64) k_interp_expand<i64, i64><<<nb, 256, 0, s>>>((const i64 *)base, wx, wy, wz, sy, sz, npts, (i64 *)cols, w);
+  else if (cols_is64) k_interp_expand<int, i64><<<nb, 256, 0, s>>>((const int *)base, wx, wy, wz, sy, sz, npts, (i64 *)cols, w);
+  else k_interp_expand<int, int><<<nb, 256, 0, s>>>((const int *)base, wx, wy, wz, sy, sz, npts, (int *)cols, w);
+  return check_launch("dzb_interp_expand");
 }
 
 extern "C" int dzb_interp_fused(const double *tx, int64_t ntx, const double *ty, int64_t nty, const double *tz,

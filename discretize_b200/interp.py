@@ -35,7 +35,9 @@ def _location_layout(mesh, location_type):
 
 
 class InterpolationOperator(Operator):
-    """Q (npts x ncols), <= 8 entries per row, stored as (npts, 8) column/weight tables on the GPU."""
+    """Q (npts x ncols), <= 8 entries per row, stored as COMPACT rows on the GPU: the flat index of the first grid
+    sample plus three per-axis weights (28 bytes per point; K10c / K11c in csrc/interp.cu).  `cols` / `w` expand them to
+    the (npts, 8) tables the reference's COO triplets hold (interputils_cython.pyx:145-180), bit for bit."""
 
     def __init__(self, mesh, pts_dev, location_type, zeros_outside, row_scale, store=True):
         key, off, ncols = _location_layout(mesh, location_type)
@@ -44,16 +46,16 @@ class InterpolationOperator(Operator):
         self.mesh, self.col_offset, self.row_scale = mesh, off, row_scale
         self.pts = pts_dev
         self.axes = [to_device(t) for t in mesh.get_tensor(key)]
-        self.cols = self.w = None
-        self.cols_is64 = ncols > 2**31 - 1      # int32 column tables while they fit (like scipy's indices)
-        # Bucketing (K11): before the first apply of a LARGE operator the table rows are sorted once by the flat index
-        # of their first grid sample; the gathers then stream through the grid vector instead of paying a 128-byte DRAM
+        self.base = self.wx = self.wy = self.wz = None
+        self.cols_is64 = ncols > 2**31 - 1      # int32 indices while they fit (like scipy's index arrays)
+        # Bucketing (K11): before the first apply of a LARGE operator the rows are sorted once by the flat index of
+        # their first grid sample; the gathers then stream through the grid vector instead of paying a 128-byte DRAM
         # fetch per random 8-byte value.  perm[p] = the point row p belongs to.  Done lazily so that building Q stays a
         # single locate pass (BASELINE config 4 times the build), and only where it pays (the sort costs ~10 applies).
         self.perm = None
         self._scale_rows = row_scale            # row_scale in table order
         self.bucket_min_points = 1 << 20
-        self.unpermute = "gather"             # or "scatter": y[perm[p]] written by the apply kernel itself
+        self.unpermute = "gather"             # or "scatter": the transposed kernel's order, y[perm[p]] by index_copy
         if store:
             self._locate()
 
@@ -61,22 +63,46 @@ class InterpolationOperator(Operator):
         a = self.axes
         return (ptr(a[0]), a[0].numel(), ptr(a[1]), a[1].numel(), ptr(a[2]), a[2].numel())
 
+    def _row_args(self):
+        return (ptr(self.base), int(self.cols_is64), ptr(self.wx), ptr(self.wy), ptr(self.wz),
+                self.axes[0].numel(), self.axes[1].numel())
+
     def _locate(self):
         npts = self.shape[0]
         dev = cuda_device()
-        self.cols = torch.empty((npts, 8), dtype=torch.int64 if self.cols_is64 else torch.int32, device=dev)
-        self.w = torch.empty((npts, 8), dtype=torch.float64, device=dev)
-        self.perm, self._scale_rows = None, self.row_scale          # fresh tables are in point order
-        check(load().dzb_interp_locate(*self._axes_args(), ptr(self.pts), npts, self.col_offset, ptr(self.cols),
-                                       int(self.cols_is64), ptr(self.w), stream_ptr()), "dzb_interp_locate")
+        self.base = torch.empty(npts, dtype=torch.int64 if self.cols_is64 else torch.int32, device=dev)
+        self.wx, self.wy, self.wz = (torch.empty(npts, dtype=torch.float64, device=dev) for _ in range(3))
+        self.perm, self._scale_rows = None, self.row_scale          # fresh rows are in point order
+        check(load().dzb_interp_locate_compact(*self._axes_args(), ptr(self.pts), npts, self.col_offset, ptr(self.base),
+                                               int(self.cols_is64), ptr(self.wx), ptr(self.wy), ptr(self.wz),
+                                               stream_ptr()), "dzb_interp_locate_compact")
+
+    def tables(self):
+        """(cols, w): the (npts, 8) index / weight tables in TABLE order (row p belongs to point perm[p] once bucketed)."""
+        if self.base is None:
+            self._locate()
+        npts = self.shape[0]
+        cols = torch.empty((npts, 8), dtype=self.base.dtype, device=self.base.device)
+        w = torch.empty((npts, 8), dtype=torch.float64, device=self.base.device)
+        check(load().dzb_interp_expand(*self._row_args(), npts, ptr(cols), int(self.cols_is64), ptr(w), stream_ptr()),
+              "dzb_interp_expand")
+        return cols, w
+
+    @property
+    def cols(self):
+        return self.tables()[0]
+
+    @property
+    def w(self):
+        return self.tables()[1]
 
     def bucket(self):
-        """Sort the table rows by their first column (x fastest, like the grid vector) and remember the permutation."""
-        if self.perm is not None or self.cols is None or self.shape[0] >= 2**31 - 1:
+        """Sort the rows by their first column (x fastest, like the grid vector) and remember the permutation."""
+        if self.perm is not None or self.base is None or self.shape[0] >= 2**31 - 1:
             return
-        order = torch.argsort(self.cols[:, 0])
-        self.cols = self.cols.index_select(0, order)
-        self.w = self.w.index_select(0, order)
+        order = torch.argsort(self.base)
+        self.base = self.base.index_select(0, order)
+        self.wx, self.wy, self.wz = (t.index_select(0, order) for t in (self.wx, self.wy, self.wz))
         if self.row_scale is not None:
             self._scale_rows = self.row_scale.index_select(0, order)
         self.perm = order.to(torch.int32)
@@ -90,41 +116,37 @@ class InterpolationOperator(Operator):
 
     def _dev_apply(self, x, out):
         npts = self.shape[0]
-        if self.cols is None:  # fused locate + apply, nothing stored
+        if self.base is None:  # fused locate + apply, nothing stored
             check(load().dzb_interp_fused(*self._axes_args(), ptr(self.pts), npts, self.col_offset,
                                           ptr(self.row_scale), ptr(x), ptr(out), stream_ptr()), "dzb_interp_fused")
-        else:
-            self._maybe_bucket()
-            if self.perm is None:
-                check(load().dzb_interp_apply(ptr(self.cols), int(self.cols_is64), ptr(self.w), ptr(self._scale_rows), npts,
-                                              ptr(x), ptr(out), stream_ptr()), "dzb_interp_apply")
-            elif self.unpermute == "scatter":
-                check(load().dzb_interp_apply_perm(ptr(self.cols), int(self.cols_is64), ptr(self.w), ptr(self._scale_rows),
-                                                   ptr(self.perm), npts, ptr(x), ptr(out), stream_ptr()), "dzb_interp_apply")
+            return
+        self._maybe_bucket()
+        # bucketed rows: the result comes out in bucket order (coalesced), then one pass of random READS brings it back
+        # to point order (a scatter costs a sector fill plus a write-back per value)
+        dst = out if self.perm is None else self._sorted_out
+        check(load().dzb_interp_apply_compact(*self._row_args(), ptr(self._scale_rows), npts, ptr(x), ptr(dst),
+                                              stream_ptr()), "dzb_interp_apply_compact")
+        if self.perm is not None:
+            if self.unpermute == "scatter":
+                out.index_copy_(0, self.perm.long(), dst)
             else:
-                # result in bucket order (coalesced), then one pass of random reads back to point order
-                check(load().dzb_interp_apply(ptr(self.cols), int(self.cols_is64), ptr(self.w), ptr(self._scale_rows), npts,
-                                              ptr(x), ptr(self._sorted_out), stream_ptr()), "dzb_interp_apply")
-                check(load().dzb_gather_rows(npts, ptr(self._sorted_out), ptr(self.inv_perm), ptr(out), stream_ptr()),
-                      "dzb_gather_rows")
+                check(load().dzb_gather_rows(npts, ptr(dst), ptr(self.inv_perm), ptr(out), stream_ptr()), "dzb_gather_rows")
 
     def _dev_apply_t(self, x, out):
-        if self.cols is None:
+        if self.base is None:
             self._locate()
         self._maybe_bucket()
         out.zero_()
-        check(load().dzb_interp_apply_t_perm(ptr(self.cols), int(self.cols_is64), ptr(self.w), ptr(self._scale_rows),
-                                             ptr(self.perm), self.shape[0], ptr(x), ptr(out), stream_ptr()),
-              "dzb_interp_apply_t")
+        check(load().dzb_interp_apply_t_compact(*self._row_args(), ptr(self._scale_rows), ptr(self.perm), self.shape[0],
+                                                ptr(x), ptr(out), stream_ptr()), "dzb_interp_apply_t_compact")
 
     def _tocsr(self):
         """COO -> CSR exactly like the reference: duplicate columns summed, sorted, explicit zeros kept;
         zeros_outside rows become full rows of explicit zeros (base_tensor_mesh.py:771-772)."""
-        if self.cols is None:
-            self._locate()
         npts, ncols = self.shape
-        cols = self.cols.cpu().numpy().reshape(-1).astype(np.int64)
-        w = self.w.cpu().numpy().reshape(-1)
+        cols, w = self.tables()
+        cols = cols.cpu().numpy().reshape(-1).astype(np.int64)
+        w = w.cpu().numpy().reshape(-1)
         # bucketed tables: row p of the table is row perm[p] of the matrix
         rows = np.repeat(np.arange(npts) if self.perm is None else self.perm.cpu().numpy().astype(np.int64), 8)
         Q = sp.csr_matrix((w, (rows, cols)), shape=(npts, ncols))

@@ -226,6 +226,23 @@ int dzb_interp_apply_t_perm(const void *cols, int cols_is64, const double *w, co
 /* dst[i] = src[idx[i]], i < n: returns a result computed in bucket order (dzb_interp_apply on bucketed tables with
  * perm == NULL) to point order with random READS, which cost half of what the scattered writes of *_perm cost. */
 int dzb_gather_rows(int64_t n, const double *src, const int32_t *idx, double *dst, void *stream);
+/* Compact tables (K10c / K11c): a row keeps the flat index of its first grid sample (`base`, int32 or int64) and the
+ * three per-axis weights w1 (28 bytes instead of 96); a weight stored as -0.5 marks an axis where the reference clamps
+ * (i2 == i1, both weights 0.5).  Columns base + {0,1} + {0,ntx} + {0,ntx*nty} and weights ((wx*wy)*wz), w2 = 1 - w1, are
+ * rebuilt in the kernels with the reference's expressions (interputils_cython.pyx:60-67, 145-180): dzb_interp_expand
+ * writes tables bit-identical to dzb_interp_locate's.  Rows may be in any order (the host side sorts them by `base`);
+ * `perm` as in dzb_interp_apply_t_perm. */
+int dzb_interp_locate_compact(const double *tx, int64_t ntx, const double *ty, int64_t nty, const double *tz, int64_t ntz,
+                              const double *pts, int64_t npts, int64_t col_offset, void *base, int base_is64, double *wx,
+                              double *wy, double *wz, void *stream);
+int dzb_interp_apply_compact(const void *base, int base_is64, const double *wx, const double *wy, const double *wz,
+                             int64_t ntx, int64_t nty, const double *row_scale, int64_t npts, const double *v, double *y,
+                             void *stream);
+int dzb_interp_apply_t_compact(const void *base, int base_is64, const double *wx, const double *wy, const double *wz,
+                               int64_t ntx, int64_t nty, const double *row_scale, const int32_t *perm, int64_t npts,
+                               const double *x, double *y, void *stream);
+int dzb_interp_expand(const void *base, int base_is64, const double *wx, const double *wy, const double *wz, int64_t ntx,
+                      int64_t nty, int64_t npts, void *cols, int cols_is64, double *w, void *stream);
 /* Fused locate + apply: y = Q v without storing Q. */
 int dzb_interp_fused(const double *tx, int64_t ntx, const double *ty, int64_t nty, const double *tz, int64_t ntz,
                      const double *pts, int64_t npts, int64_t col_offset, const double *row_scale, const double *v,

@@ -601,6 +601,53 @@ def test_dc_cell_fused(mesh_name):
         assert_close_vec(A2 @ x2, D2 @ (T.inner_product(g2, "F", rho2, invert_matrix=True) @ (D2.T @ x2)))
 
 
+@pytest.mark.parametrize("mesh_name", ["graded", "wide"])
+@pytest.mark.parametrize("loc", ["CC", "N", "Ez", "Fy"])
+def test_interpolation_compact_rows_expand_to_the_full_tables(mesh_name, loc):
+    """K10c keeps 28 bytes per point (first column + three weights, sign = clamped axis); expanded, they must be the very
+    tables the (npts, 8) locate kernel writes: same columns, same weights, bit for bit -- including points in the
+    half-cell clamp zones, on the boundary, and NaN / infinite coordinates."""
+    import torch
+
+    from discretize_b200._lib import check, load
+    from discretize_b200.interp import InterpolationOperator
+    from discretize_b200.operators import ptr, stream_ptr, to_device
+
+    mesh, grid = make_pair(mesh_name)
+    rng = np.random.default_rng(43)
+    lo = np.array([t[0] for t in grid.nodes])
+    hi = np.array([t[-1] for t in grid.nodes])
+    pts = lo + rng.random((4000, 3)) * (hi - lo)
+    pts[:50] = lo
+    pts[50:100] = hi
+    pts[100:140, 0] = grid.nodes[0][rng.integers(0, grid.nodes[0].size, 40)]      # exactly on grid lines
+    pts[140:150, 1] = [np.nan, np.inf, -np.inf, 1e300, -1e300] * 2
+    Q = InterpolationOperator(mesh, to_device(pts), loc, False, None)
+    cols, w = Q.tables()
+    full_c = torch.empty_like(cols)
+    full_w = torch.empty_like(w)
+    check(load().dzb_interp_locate(*Q._axes_args(), ptr(Q.pts), pts.shape[0], Q.col_offset, ptr(full_c), 0, ptr(full_w),
+                                   stream_ptr()), "dzb_interp_locate")
+    assert torch.equal(cols, full_c)
+    assert torch.equal(w.view(torch.int64), full_w.view(torch.int64))
+    assert (Q.wx < 0).any() and (Q.wy < 0).any()                # clamped axes are present in the sample
+    # apply / transpose on those rows against the stored-table kernels
+    v = to_device(rng.standard_normal(Q.shape[1]))
+    x = to_device(rng.standard_normal(Q.shape[0]))
+    good = torch.isfinite(to_device(pts)).all(dim=1)
+    y_full = torch.empty(Q.shape[0], dtype=torch.float64, device=v.device)
+    check(load().dzb_interp_apply(ptr(full_c), 0, ptr(full_w), None, pts.shape[0], ptr(v), ptr(y_full), stream_ptr()),
+          "dzb_interp_apply")
+    y = Q.apply_device(v)
+    scale = float(y_full[good].abs().max())
+    assert float((y - y_full)[good].abs().max()) <= RTOL * scale
+    z_full = torch.zeros(Q.shape[1], dtype=torch.float64, device=v.device)
+    check(load().dzb_interp_apply_t(ptr(full_c), 0, ptr(full_w), None, pts.shape[0], ptr(x), ptr(z_full), stream_ptr()),
+          "dzb_interp_apply_t")
+    z = Q.T.apply_device(x)
+    assert float((z - z_full).abs().max()) <= RTOL * float(z_full.abs().max())
+
+
 @pytest.mark.parametrize("loc", ["CC", "N", "Ey", "Fx", "CCVz"])
 @pytest.mark.parametrize("zeros_outside", [False, True])
 def test_interpolation_bucketed_tables(loc, zeros_outside):
