@@ -298,7 +298,7 @@ def run_ours(args):
         from discretize_b200.slab import SlabMaxwell
 
         op, halo_mode = None, "none"
-        if world > 1 and args.halo == "peer":
+        if world > 1 and args.halo.startswith("peer"):
             try:        # halo planes fetched by the kernel from the neighbours' memory (symmetric allocation): one launch per apply
                 op = SlabMaxwell(n, n, n, rank, world, peer_halo=True)
                 op.step_peer()
@@ -317,17 +317,30 @@ def run_ours(args):
     else:
         from discretize_b200.slab import SlabDCNodal
 
-        op = SlabDCNodal(n, n, n, rank, world, seed_phi=5, seed_sigma=6)
-        halo_mode = "nccl" if world > 1 else "none"
+        op, halo_mode = None, "none"
+        if world > 1 and args.halo.startswith("peer"):
+            try:
+                op = SlabDCNodal(n, n, n, rank, world, seed_phi=5, seed_sigma=6, peer_halo=True)
+                op.step_peer()
+                torch.cuda.synchronize()
+                halo_mode = "peer"
+            except Exception as exc:
+                sys.stderr.write(f"[bench] peer-read halos unavailable ({exc!r}); using NCCL send/recv\n")
+                op = None
+        if op is None:
+            op = SlabDCNodal(n, n, n, rank, world, seed_phi=5, seed_sigma=6)
+            halo_mode = "nccl" if world > 1 else "none"
         ndof_total = (n + 1) ** 3
         alg_bytes = 8.0 * (2 * ndof_total + n ** 3) / world
         workload_name = f"TensorMesh {n}^3 DC-resistivity nodal operator G^T Me(sigma) G matrix-free apply (BASELINE configs[1])"
         kernel_name, kernel_key = "k_dc_nodal_ring<4,NWC,PARX>", "k_dc_nodal_ring"
-    if args.workload == "maxwell" and halo_mode == "peer":
+    if halo_mode == "peer":
         step, launches_per_step = op.step_peer, 1
+        if args.halo == "peer-barrier":      # ordering by a device-side barrier in front of every launch (comparison)
+            step = lambda: op.step_peer(sync="barrier")
         parallelism = (f"z-slabs x{world} (strong scaling); halo planes read from the neighbours' memory over NVLink by the "
-                       "fused kernel itself (tensor maps on symmetric memory) after a device-side barrier: one launch per apply, "
-                       "no send/recv, no collective")
+                       "fused kernel itself (TMA copies from symmetric memory), ordered by epoch signals the launches write into each "
+                       "other's memory: one launch per apply, no send/recv, no barrier, no collective")
     else:
         step = op.step_graphed if (world > 1 and not args.eager) else op.step
         launches_per_step = op.launches_per_step
@@ -346,6 +359,20 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     blocks = timed_blocks(step, args.steps, args.repeats, sync, world, dev)
+    if halo_mode == "peer" and args.halo == "peer":
+        # a halo wait inside a kernel that gave up (2 s) invalidates the run on EVERY rank: measure again with the
+        # barrier-ordered launches, and say so
+        bad = torch.tensor([1.0 if op.peer_sync_timed_out() else 0.0], device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if float(bad.item()) > 0:
+            sys.stderr.write("[bench] a halo wait inside the kernel timed out; re-measuring with a barrier per apply\n")
+            step = lambda: op.step_peer(sync="barrier")
+            parallelism = parallelism.replace("ordered by epoch signals the launches write into each other's memory",
+                                              "ordered by a device-side barrier in front of each launch")
+            for _ in range(warmup):
+                step()
+            sync()
+            blocks = timed_blocks(step, args.steps, args.repeats, sync, world, dev)
     clocks = sampler.stop() if rank == 0 else None
     ms_step = float(np.median(blocks)) / args.steps
     value = ndof_total / (ms_step * 1e-3) / 1e9
@@ -436,7 +463,7 @@ def run_ours(args):
                    "ms_per_step_median": ms_step, "ms_per_step_best": min(blocks) / args.steps,
                    "note": "each block = exactly `steps` applies between barrier + synchronize; median block reported"},
         "gpu_launches": launches_per_step * args.steps,
-        "launch_mode": ("eager" if (world == 1 or args.eager or (args.workload == "maxwell" and halo_mode == "peer")
+        "launch_mode": ("eager" if (world == 1 or args.eager or halo_mode == "peer"
                                    or getattr(op, "_graph_failed", False)) else "cuda-graph replay"),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -483,7 +510,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the 512^3 DC object at N=1")
-    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--halo", default="peer", choices=["peer", "peer-barrier", "nccl"],
                     help="N > 1, maxwell: peer = the kernel reads the halo planes from the neighbours' memory (default); "
                          "nccl = send/recv exchange overlapped with the interior planes + one launch for the boundary planes")
     ap.add_argument("--eager", action="store_true", help="multi-GPU: launch every step from Python instead of replaying a CUDA graph")

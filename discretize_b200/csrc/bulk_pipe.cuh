@@ -54,6 +54,36 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 }
 
 
+// ---- signals between GPUs (peer memory over NVLink) ---------------------------------------------------------------
+// A 32-bit word in a peer's memory is written with system-scope release semantics and polled with system-scope
+// acquire loads; fence_proxy_async_global orders the acquire before TMA (async proxy) reads of the data it guards.
+__device__ __forceinline__ void signal_release_sys(unsigned *flag, unsigned value) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+__device__ __forceinline__ unsigned load_acquire_sys(const unsigned *flag) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// waits until *flag >= value (wrap-around safe); gives up after ~2 s and reports it through *timed_out
+__device__ __forceinline__ void wait_signal_sys(const unsigned *flag, unsigned value, unsigned *timed_out) {
+  if ((int)(load_acquire_sys(flag) - value) >= 0) return;
+  const unsigned long long t0 = global_timer_ns();
+  while ((int)(load_acquire_sys(flag) - value) < 0) {
+    __nanosleep(64);
+    if (global_timer_ns() - t0 > 2000000000ULL) {
+      atomicExch(timed_out, 1u);
+      return;
+    }
+  }
+}
+
 // non-blocking probe: issue early, test the predicate after independent work, fall back to mbar_wait
 __device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;

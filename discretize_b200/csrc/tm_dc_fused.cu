@@ -218,10 +218,28 @@ template <int RY, int NWC, int PARX> struct DcRing {
   static constexpr size_t SMEM = (size_t)DC_SLOTS * STAGE * 8 + 2 * DC_SLOTS * 8 + 2 * RC * 8 + 2 * (DC_MAXCHUNK + 2) * 8;
 };
 
-template <int RY, int NWC, int PARX>
+// Peer-read halos (z-slabs, one process per GPU): the node planes lo_plane / hi_plane of the local vector are not read
+// from it but from a neighbour's vector mapped into this process (NVLink): *_addr is the ELEMENT address (address / 8) of
+// that plane in the neighbour's array, [*_beg, *_end) the extent of that array.  plane < 0: no such neighbour.
+//
+// Ordering against the neighbours' writes, inside the kernel (sync != NULL; else the caller puts a barrier in front):
+// sync[0] / sync[1] are set by the lower / upper neighbour, sync[2] counts this rank's completed launches, sync[3] the
+// blocks of the running launch that have finished, sync[4] != 0 reports a wait that timed out.  A launch belongs to
+// epoch e = sync[2] + 1.  Its first block tells both neighbours "my vector of epoch e is complete" (true by stream
+// order: the launch follows whatever produced phi) by writing e to their sync words; a producer warp that is about to
+// copy a halo plane waits until the neighbour it comes from has announced epoch e.  Nobody waits for anything that
+// depends on another rank's progress through its own launch, so the ranks cannot block each other; every rank must apply
+// the operator the same number of times.
+struct DcHalo {
+  int lo_plane, hi_plane;
+  long long lo_addr, lo_beg, lo_end, hi_addr, hi_beg, hi_end;
+  unsigned *sync, *lo_signal, *hi_signal;
+};
+
+template <int RY, int NWC, int PARX, bool PEER>
 __global__ void __launch_bounds__((NWC + 1) * 32, 1)
     k_dc_nodal_ring(TM m, const double *__restrict__ sigma, const double *__restrict__ phi_all, double *__restrict__ y_all,
-                    int kchunk, int nwc, int k_begin, int k_end, int nrhs, long long ldx) {
+                    int kchunk, int nwc, int k_begin, int k_end, int nrhs, long long ldx, DcHalo hal) {
   typedef DcRing<RY, NWC, PARX> G;
   // multi-RHS launch: blockIdx.x = x-block * nrhs + rhs -- the right-hand side is the FASTEST index of the launch order, so
   // that the nrhs blocks that stage the same sigma tile run side by side and all but the first find it in L2 (sigma is
@@ -272,8 +290,25 @@ __global__ void __launch_bounds__((NWC + 1) * 32, 1)
     }
     fence_barrier_init();
   }
+  unsigned epoch = 0;
+  if (PEER && hal.sync) {
+    epoch = *reinterpret_cast<volatile unsigned *>(hal.sync + 2) + 1;   // changes only after ALL blocks have passed here
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+      __threadfence_system();
+      if (hal.lo_signal) signal_release_sys(hal.lo_signal, epoch);
+      if (hal.hi_signal) signal_release_sys(hal.hi_signal, epoch);
+    }
+  }
   fence_proxy_async_smem();
   __syncthreads();
+  if (PEER && hal.sync && tid == 0) {   // the last block to get here closes the epoch
+    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+    if (atomicAdd(hal.sync + 3, 1u) == total - 1) {
+      hal.sync[3] = 0;
+      __threadfence();
+      *reinterpret_cast<volatile unsigned *>(hal.sync + 2) = epoch;
+    }
+  }
 
   const long long pstride = (long long)nNx * nNy, cstride = (long long)nx * ny;
   const int cs = max(Xb - 1, 0);  // first staged column (nodes and cells)
@@ -305,14 +340,26 @@ __global__ void __launch_bounds__((NWC + 1) * 32, 1)
         if (n >= 1) mbar_wait(&empty[slot], (n - 1) & 1);
         const int pl = jst + ploff;
         const bool on = row_ok && pl >= 0 && pl < npl;
-        const long long lo = rowbase + pstr * pl;
-        RowCopy rc = plan_row_copy(lo, lo + ncol, abeg, aend);
+        long long lo = rowbase + pstr * pl, lead_a = a0 + pstr * pl, ab = abeg, ae = aend;
+        if (PEER && isp && (pl == hal.lo_plane || pl == hal.hi_plane)) {   // this plane lives in a neighbour's memory
+          const bool low = pl == hal.lo_plane;
+          const long long pb = low ? hal.lo_addr : hal.hi_addr;
+          lead_a = pb + cs + (long long)nNx * (j0 - 1);
+          lo = lead_a + (long long)r * nNx;
+          ab = low ? hal.lo_beg : hal.hi_beg;
+          ae = low ? hal.lo_end : hal.hi_end;
+          if (hal.sync && on) {   // the neighbour's vector of this epoch must be complete
+            wait_signal_sys(hal.sync + (low ? 0 : 1), epoch, hal.sync + 4);
+            fence_proxy_async_global();
+          }
+        }
+        RowCopy rc = plan_row_copy(lo, lo + ncol, ab, ae);
         if (!on) {
           rc.bytes = 0;
           rc.head = rc.tail = false;
         }
         double *T = tiles + slot * G::STAGE;
-        const int dst0 = soff + (int)((a0 + pstr * pl) & 1);   // element lo lands here: one lead bit per stage
+        const int dst0 = soff + (int)(lead_a & 1);   // element lo lands here: one lead bit per stage
         const unsigned total = __reduce_add_sync(0xffffffffu, rc.bytes);
         if (__any_sync(0xffffffffu, rc.head | rc.tail)) {   // only the rows that hold the first / last element of an odd-aligned array
           if (rc.head) T[dst0] = *reinterpret_cast<const double *>(lo << 3);
@@ -369,7 +416,15 @@ __global__ void __launch_bounds__((NWC + 1) * 32, 1)
       if (q == 1) mbar_wait(&full[0], 0);  // stage 0 only carries plane kb-1 (read below as P0)
       mbar_wait(&full[slot], par);
       // lead bits of the planes j (stage j-1), j+1 (stage j) and of layer j (stage j)
-      const int lp0 = (l0p + pbP * j) & 1, lp1 = (l0p + pbP * (j + 1)) & 1, lc = (l0c + pbC * j) & 1;
+      int lp0 = (l0p + pbP * j) & 1, lp1 = (l0p + pbP * (j + 1)) & 1;
+      const int lc = (l0c + pbC * j) & 1;
+      if (PEER) {   // a plane fetched from a neighbour carries the lead bit of its address there
+        const long long rel = cs + (long long)nNx * (j0 - 1);
+        if (j == hal.lo_plane) lp0 = (int)((hal.lo_addr + rel) & 1);
+        if (j == hal.hi_plane) lp0 = (int)((hal.hi_addr + rel) & 1);
+        if (j + 1 == hal.lo_plane) lp1 = (int)((hal.lo_addr + rel) & 1);
+        if (j + 1 == hal.hi_plane) lp1 = (int)((hal.hi_addr + rel) & 1);
+      }
       const double *tP0 = tiles + slot_prev * G::STAGE + (c2 + lp0);
       const double *tP1 = tiles + slot * G::STAGE + (c2 + lp1);
       const double *tS = tiles + slot * G::STAGE + G::REGP + (c2 + lc);
@@ -425,30 +480,50 @@ extern "C" void dzb_tune_dc(int ry, int kchunk) {
 }
 extern "C" void dzb_tune_dc_variant(int variant) { g_dc_variant = variant; }
 
-template <int RY, int NWC, int PARX>
+template <int RY, int NWC, int PARX, bool PEER = false>
 static int launch_dc_ring_t(const TM &m, const double *sigma, const double *phi, double *y, int kchunk, int xblocks,
-                            int nwc, int k_begin, int k_end, cudaStream_t s, int nrhs = 1, long long ldx = 0) {
+                            int nwc, int k_begin, int k_end, cudaStream_t s, int nrhs = 1, long long ldx = 0,
+                            const DcHalo *hal = nullptr) {
   typedef DcRing<RY, NWC, PARX> G;
   // the attribute is per device (a process may drive several GPUs); setting it is cheap, so no process-wide flag
-  if (cudaFuncSetAttribute(k_dc_nodal_ring<RY, NWC, PARX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (cudaFuncSetAttribute(k_dc_nodal_ring<RY, NWC, PARX, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)G::SMEM) != cudaSuccess)
     return -1;
+  const DcHalo none{-1, -1, 0, 0, 0, 0, 0, 0, nullptr, nullptr, nullptr};
   const int nNy = (int)m.ny + 1;
-  // short plane ranges (z-slabs on many GPUs): shrink the z-chunk until the grid has ~4 waves of blocks
-  const int nxy = xblocks * ((nNy + RY - 1) / RY);
-  const int zb_target = (4 * 148 + nxy - 1) / nxy;
-  const int fair = (k_end - k_begin + zb_target - 1) / zb_target;
-  kchunk = kchunk < fair ? kchunk : (fair < 8 ? 8 : fair);
+  // z-chunk: one block per SM is resident (192 KB of stages), so a launch runs in waves of `sms` blocks and a block
+  // costs (planes + 2 halo stages + ~3 stages of start-up) stage times; pick the split that minimises waves x cost.
+  // (A 64-plane slab of 512^3 on 8 GPUs: 129 blocks of 65 planes in ONE wave instead of 645 blocks of 13 planes in
+  // five, each of them staging 15 planes.)
+  const int nxy = xblocks * ((nNy + RY - 1) / RY) * nrhs;
+  {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int planes = k_end - k_begin, maxc = kchunk > DC_MAXCHUNK ? DC_MAXCHUNK : kchunk + kchunk / 4;
+    long long best = -1;
+    int best_kc = planes < maxc ? planes : maxc;
+    for (int zb = (planes + maxc - 1) / maxc; zb <= planes && zb <= 256; ++zb) {
+      const int kc = (planes + zb - 1) / zb;
+      const long long blocks = (long long)nxy * ((planes + kc - 1) / kc);
+      const long long cost = ((blocks + sms - 1) / sms) * (kc + 5);
+      if (best < 0 || cost < best) {
+        best = cost;
+        best_kc = kc;
+      }
+    }
+    kchunk = best_kc;
+  }
   dim3 grid((unsigned)xblocks * nrhs, (unsigned)((nNy + RY - 1) / RY), (unsigned)((k_end - k_begin + kchunk - 1) / kchunk));
-  k_dc_nodal_ring<RY, NWC, PARX><<<grid, dim3((nwc + 1) * 32), G::SMEM, s>>>(m, sigma, phi, y, kchunk, nwc, k_begin,
-                                                                           k_end, nrhs, ldx);
+  k_dc_nodal_ring<RY, NWC, PARX, PEER><<<grid, dim3((nwc + 1) * 32), G::SMEM, s>>>(m, sigma, phi, y, kchunk, nwc, k_begin,
+                                                                                 k_end, nrhs, ldx, hal ? *hal : none);
   return 0;
 }
 
 constexpr int DC_NWC_BIG = 18, DC_NWC_SMALL = 6;
 
 static int launch_dc_ring(const TM &m, const double *sigma, const double *phi, double *y, int kchunk, int k_begin,
-                          int k_end, cudaStream_t s, int nrhs = 1, long long ldx = 0) {
+                          int k_end, cudaStream_t s, int nrhs = 1, long long ldx = 0, const DcHalo *hal = nullptr) {
   const int nNx = (int)m.nx + 1;
   const int strips = (nNx + DC_XOUT - 1) / DC_XOUT;
   const bool small = strips <= DC_NWC_SMALL;
@@ -457,6 +532,13 @@ static int launch_dc_ring(const TM &m, const double *sigma, const double *phi, d
   const int nwc = (strips + xblocks - 1) / xblocks;  // balanced consumer warps per block
   kchunk = kchunk > DC_MAXCHUNK ? DC_MAXCHUNK : kchunk;
   const int parx = (int)(m.nx & 1);
+  if (hal) {
+    if (small)
+      return parx ? launch_dc_ring_t<4, DC_NWC_SMALL, 1, true>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, 1, 0, hal)
+                  : launch_dc_ring_t<4, DC_NWC_SMALL, 0, true>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, 1, 0, hal);
+    return parx ? launch_dc_ring_t<4, DC_NWC_BIG, 1, true>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, 1, 0, hal)
+                : launch_dc_ring_t<4, DC_NWC_BIG, 0, true>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, 1, 0, hal);
+  }
   if (small)
     return parx ? launch_dc_ring_t<4, DC_NWC_SMALL, 1>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, nrhs, ldx)
                 : launch_dc_ring_t<4, DC_NWC_SMALL, 0>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, nrhs, ldx);
@@ -497,6 +579,51 @@ extern "C" int dzb_tm_dc_nodal_range(const DzbTensorMesh *mm, const double *sigm
   else if (ry == 4) k_dc_nodal<4, 4><<<grid, block, 0, s>>>(m, sigma, phi, y, kchunk, kb0, ke0);
   else k_dc_nodal<8, 2><<<grid, block, 0, s>>>(m, sigma, phi, y, kchunk, kb0, ke0);
   return check_launch("dzb_tm_dc_nodal");
+}
+
+// A z-slab's apply with PEER-READ halos: the node planes lo_plane / hi_plane of the local vector are fetched by the
+// producer warp from the neighbours' vectors phi_lo / phi_hi (plane lo_peer_plane / hi_peer_plane of arrays with
+// nz_lo + 1 / nz_hi + 1 node planes of the same nx, ny): one launch per apply, no send / recv.
+extern "C" int dzb_tm_dc_nodal_range_peer(const DzbTensorMesh *mm, const double *sigma, const double *phi,
+                                          const double *phi_lo, int64_t nz_lo, int64_t lo_plane, int64_t lo_peer_plane,
+                                          const double *phi_hi, int64_t nz_hi, int64_t hi_plane, int64_t hi_peer_plane,
+                                          uint32_t *sync, uint32_t *lo_signal, uint32_t *hi_signal, double *y,
+                                          int64_t k_begin, int64_t k_end, void *stream) {
+  if (!mm || mm->nx <= 0 || mm->ny <= 0 || mm->nz <= 0) {
+    set_error("dzb_tm_dc_nodal_range_peer: invalid mesh");
+    return -1;
+  }
+  TM m(*mm);
+  const i64 nNx = m.nx + 1, nNy = m.ny + 1, nNz = m.nz + 1, pstride = nNx * nNy;
+  if (k_begin < 0 || k_end > nNz || k_begin > k_end) {
+    set_error("dzb_tm_dc_nodal_range_peer: plane range outside [0, nz+1]");
+    return -1;
+  }
+  if ((phi_lo && (lo_plane < 0 || lo_plane >= nNz || lo_peer_plane < 0 || lo_peer_plane > nz_lo)) ||
+      (phi_hi && (hi_plane < 0 || hi_plane >= nNz || hi_peer_plane < 0 || hi_peer_plane > nz_hi))) {
+    set_error("dzb_tm_dc_nodal_range_peer: halo plane outside the local / the neighbour's array");
+    return -1;
+  }
+  if (k_begin == k_end) return 0;
+  if (!(m.ny >= 2 && m.nN() < ((i64)1 << 31) && pstride < ((i64)1 << 31))) return -2;   // ring kernel only
+  DcHalo hal{-1, -1, 0, 0, 0, 0, 0, 0, sync, sync ? lo_signal : nullptr, sync ? hi_signal : nullptr};
+  if (phi_lo) {
+    hal.lo_plane = (int)lo_plane;
+    hal.lo_beg = (long long)((unsigned long long)phi_lo >> 3);
+    hal.lo_end = hal.lo_beg + pstride * (nz_lo + 1);
+    hal.lo_addr = hal.lo_beg + pstride * lo_peer_plane;
+  }
+  if (phi_hi) {
+    hal.hi_plane = (int)hi_plane;
+    hal.hi_beg = (long long)((unsigned long long)phi_hi >> 3);
+    hal.hi_end = hal.hi_beg + pstride * (nz_hi + 1);
+    hal.hi_addr = hal.hi_beg + pstride * hi_peer_plane;
+  }
+  if (launch_dc_ring(m, sigma, phi, y, g_dc_kchunk, (int)k_begin, (int)k_end, (cudaStream_t)stream, 1, 0, &hal) != 0) {
+    cudaGetLastError();
+    return -2;
+  }
+  return check_launch("dzb_tm_dc_nodal_range_peer");
 }
 
 // y[r] = A phi[r] for nrhs right-hand sides stored one after the other (right-hand side r at phi + r * ldx): ONE launch;

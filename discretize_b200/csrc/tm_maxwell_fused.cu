@@ -276,7 +276,7 @@ static int launch_m3_t(const TM &m, const double *mui, const double *sigma, cons
   const int kchunk = (longest + nchunks - 1) / nchunks;
   const int nzb0 = (planes + kchunk - 1) / kchunk, nzb1 = (planes2 + kchunk - 1) / kchunk;
   dim3 grid((unsigned)xblocks, (unsigned)yblocks, (unsigned)(nzb0 + nzb1));
-  const M3Halo none = {-1, -1, -1, -1, -1, -1};
+  const M3Halo none = {-1, -1, -1, -1, -1, -1, nullptr, nullptr, nullptr};
   if (peers)
     k_maxwell_tmap<XS, R, PARX, NSLOT, MINB, true><<<grid, dim3(G::NT), G::SMEM, s>>>(m, maps, y, kchunk, k_begin, k_end, nzb0,
                                                                                       k_begin2, k_end2, g_m3_l2hint, peers->halo);
@@ -407,10 +407,12 @@ extern "C" int dzb_tm_maxwell_cplx(const DzbTensorMesh *mm, const double *mui, c
 // layout is that of a TensorMesh with nz_lo / nz_hi cell layers.  One launch covers all owned planes: no send / recv and no
 // separate launch for the planes next to a halo.  The caller orders the apply after the neighbours' writes to their e
 // (a barrier across the ranks).  Tensor-map path only: returns -2 where that path does not apply.
-extern "C" int dzb_tm_maxwell_range_peer(const DzbTensorMesh *mm, const double *mui, const double *sigma, const double *e,
-                                         const double *e_lo, int64_t nz_lo, int64_t lo_plane, int64_t lo_peer_plane,
-                                         const double *e_hi, int64_t nz_hi, int64_t hi_plane, int64_t hi_peer_plane,
-                                         double *y, int64_t k_begin, int64_t k_end, void *stream) {
+extern "C" int dzb_tm_maxwell_range_peer_sync(const DzbTensorMesh *mm, const double *mui, const double *sigma,
+                                              const double *e, const double *e_lo, int64_t nz_lo, int64_t lo_plane,
+                                              int64_t lo_peer_plane, const double *e_hi, int64_t nz_hi, int64_t hi_plane,
+                                              int64_t hi_peer_plane, uint32_t *sync, uint32_t *lo_signal,
+                                              uint32_t *hi_signal, double *y, int64_t k_begin, int64_t k_end,
+                                              void *stream) {
   if (!valid_mesh(mm)) return -1;
   TM m(*mm);
   if (k_begin < 0 || k_end > m.nz + 1 || k_begin > k_end) {
@@ -425,7 +427,7 @@ extern "C" int dzb_tm_maxwell_range_peer(const DzbTensorMesh *mm, const double *
   pr.nz_lo = nz_lo;
   pr.nz_hi = nz_hi;
   pr.halo = {e_lo ? (int)lo_plane : -1, (int)lo_peer_plane, e_lo ? (int)lo_plane : -1, (int)lo_peer_plane,
-             e_hi ? (int)hi_plane : -1, (int)hi_peer_plane};
+             e_hi ? (int)hi_plane : -1, (int)hi_peer_plane, sync, sync ? lo_signal : nullptr, sync ? hi_signal : nullptr};
   if (g_mx_variant == 3 && ring_ok) {
     g_mx_last_path = 3;
     if (launch_m3(m, mui, sigma, e, y, (int)k_begin, (int)k_end, 0, 0, (cudaStream_t)stream, &pr) == 0)
@@ -434,6 +436,14 @@ extern "C" int dzb_tm_maxwell_range_peer(const DzbTensorMesh *mm, const double *
   }
   set_error("dzb_tm_maxwell_range_peer: needs the tensor-map path (16-byte aligned component offsets: nx, ny even)");
   return -2;
+}
+
+extern "C" int dzb_tm_maxwell_range_peer(const DzbTensorMesh *mm, const double *mui, const double *sigma, const double *e,
+                                         const double *e_lo, int64_t nz_lo, int64_t lo_plane, int64_t lo_peer_plane,
+                                         const double *e_hi, int64_t nz_hi, int64_t hi_plane, int64_t hi_peer_plane,
+                                         double *y, int64_t k_begin, int64_t k_end, void *stream) {
+  return dzb_tm_maxwell_range_peer_sync(mm, mui, sigma, e, e_lo, nz_lo, lo_plane, lo_peer_plane, e_hi, nz_hi, hi_plane,
+                                        hi_peer_plane, nullptr, nullptr, nullptr, y, k_begin, k_end, stream);
 }
 
 // two disjoint plane ranges in ONE launch (the two boundary planes of a z-slab, once its halos have arrived)

@@ -99,6 +99,12 @@ struct M3Halo {
   int lo_plane, lo_peer_plane;   // ex, ey on local node plane lo_plane = plane lo_peer_plane of the lower neighbour (-1: none)
   int lo_layer, lo_peer_layer;   // ez in local cell layer lo_layer = layer lo_peer_layer of the lower neighbour (-1: none)
   int hi_plane, hi_peer_plane;   // ex, ey on local node plane hi_plane = plane hi_peer_plane of the upper neighbour (-1: none)
+  // ordering against the neighbours' writes inside the kernel (NULL: the caller put a barrier in front of the launch):
+  // sync[0] / sync[1] are written by the lower / upper neighbour, sync[2] = launches completed, sync[3] = blocks of this
+  // launch that have started, sync[4] != 0: a wait gave up.  Same protocol as K8 (tm_dc_fused.cu, DcHalo): a launch
+  // announces "e of epoch sync[2] + 1 is complete" to both neighbours from its first block, and the producer lane waits for
+  // the neighbour's announcement of that epoch before its first copy out of that neighbour's memory.
+  unsigned *sync, *lo_signal, *hi_signal;
 };
 
 template <int XS, int R, int PARX, int NSLOT, int MINB, bool PEER>
@@ -149,8 +155,25 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
     for (int q = 0; q < S * G::XROWS * XS; ++q) mbar_init(&xready[q], 1);
     fence_barrier_init();
   }
+  unsigned epoch = 0;
+  if (PEER && hal.sync) {
+    epoch = *reinterpret_cast<volatile unsigned *>(hal.sync + 2) + 1;   // changes only after ALL blocks have passed here
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+      __threadfence_system();
+      if (hal.lo_signal) signal_release_sys(hal.lo_signal, epoch);
+      if (hal.hi_signal) signal_release_sys(hal.hi_signal, epoch);
+    }
+  }
   fence_proxy_async_smem();
   __syncthreads();
+  if (PEER && hal.sync && tid == 0) {   // the last block to get here closes the epoch
+    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+    if (atomicAdd(hal.sync + 3, 1u) == total - 1) {
+      hal.sync[3] = 0;
+      __threadfence();
+      *reinterpret_cast<volatile unsigned *>(hal.sync + 2) = epoch;
+    }
+  }
 
   // rows per plane of the five staged arrays; row J = plane * rpp + (row inside the plane)
   const int rpp[5] = {nNy, ny, nNy, ny, ny};
@@ -189,6 +212,7 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
         if (l2hint) tmap_load_2d_hint(dst, mp, x, yy, bar, pol);
         else tmap_load_2d(dst, mp, x, yy, bar);
       };
+      unsigned announced = 0;   // neighbours whose epoch announcement this lane has seen
       for (int q = 0; q < nq; ++q) {
         const int slot = q % S, n = q / S;
         if (n >= 1) mbar_wait(&empty[slot], (n - 1) & 1);
@@ -211,6 +235,11 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
             if (PEER && src) {
               mE = &maps.pm[src - 1][a < 3 ? a : 0];
               mO = &maps.po[src - 1][a < 3 ? a : 0];
+              if (hal.sync && !((announced >> src) & 1u)) {   // the neighbour's vector of this epoch must be complete
+                wait_signal_sys(hal.sync + (src - 1), epoch, hal.sync + 4);
+                fence_proxy_async_global();
+                announced |= 1u << src;
+              }
             }
             const int J0 = pl * rpp[a] + j0 - 1;       // first staged row (may be -1: zero-filled / previous plane)
             if (G::odd(a)) {

@@ -129,6 +129,38 @@ def _local_cell_model(model, layout, seed, dev):
     return part.to(device=dev, dtype=torch.float64).contiguous()
 
 
+def _symmetric_vector(local_size, nx, ny, nz, rank, world, dev):
+    """A rank's local vector in symmetric memory (``torch.distributed._symmetric_memory``: every rank learns the device
+    addresses of the others' buffers) + what the fused kernels need to read the halo planes from the neighbours:
+    ``lower`` / ``upper`` = (neighbour's buffer address, its local cell layers, local halo plane, that plane's index in the
+    neighbour's array) or None.  ``local_size(layout)`` = entries of a rank's local vector."""
+    import torch.distributed._symmetric_memory as symm_mem
+
+    layouts = [SlabLayout(nx, ny, nz, r, world) for r in range(world)]
+    n_max = max(local_size(l) for l in layouts)              # symmetric allocations have one size on every rank
+    n_max = (n_max + 1) // 2 * 2
+    buf = symm_mem.empty(n_max + 8, dtype=torch.float64, device=dev)     # + 64 bytes of sync words (dzb.h)
+    hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+    buf.zero_()
+    torch.cuda.synchronize()
+    dist.barrier()                                           # nobody signals into words that are yet to be cleared
+    L = layouts[rank]
+    lower = upper = None
+    sync_off = n_max * 8
+    lo_signal = hi_signal = 0
+    if L.has_lower:
+        Ll = layouts[rank - 1]
+        lower = (int(hdl.buffer_ptrs[rank - 1]), Ll.nz_local, L.p_own0 - 1, Ll.p_own1 - 1)
+        lo_signal = int(hdl.buffer_ptrs[rank - 1]) + sync_off + 4      # the lower neighbour's "set by my upper" word
+    if L.has_upper:
+        Lu = layouts[rank + 1]
+        upper = (int(hdl.buffer_ptrs[rank + 1]), Lu.nz_local, L.p_own1, Lu.p_own0)
+        hi_signal = int(hdl.buffer_ptrs[rank + 1]) + sync_off           # the upper neighbour's "set by my lower" word
+    return {"buffer": buf, "handle": hdl, "lower": lower, "upper": upper,
+            "sync": int(hdl.buffer_ptrs[rank]) + sync_off, "lo_signal": lo_signal, "hi_signal": hi_signal,
+            "sync_words": buf[n_max:].view(torch.int32)}
+
+
 class SlabDCNodal(_GraphedStep):
     """y = G^T Me(sigma) G phi on a z-slab decomposed TensorMesh([nx, ny, nz]) (unit cube widths).
 
@@ -136,9 +168,11 @@ class SlabDCNodal(_GraphedStep):
     the interior planes, then the two boundary planes.
     """
 
-    def __init__(self, nx, ny, nz, rank, world, seed_phi=5, seed_sigma=6, h=None, sigma=None):
+    def __init__(self, nx, ny, nz, rank, world, seed_phi=5, seed_sigma=6, h=None, sigma=None, peer_halo=False):
         """``sigma``: the global conductivity model (nC entries, reference order) or None for the synthetic benchmark
-        field; ``h``: the three global width arrays (default: unit cube)."""
+        field; ``h``: the three global width arrays (default: unit cube).  ``peer_halo``: keep phi in symmetric memory so
+        that the fused kernel reads the halo planes from the neighbours' memory itself (``step_peer``: one launch per
+        apply, no send / recv)."""
         import discretize_b200 as dz
 
         self.layout = L = SlabLayout(nx, ny, nz, rank, world)
@@ -147,7 +181,14 @@ class SlabDCNodal(_GraphedStep):
         self.mesh = dz.TensorMesh([np.asarray(hx), np.asarray(hy), np.asarray(hz)[L.l0:L.l1]])
         # static model incl. its halo layer
         self.sigma = _local_cell_model(sigma, L, seed_sigma, dev)
-        self.phi = torch.zeros((L.nz_local + 1) * L.plane, dtype=torch.float64, device=dev)
+        n_local = (L.nz_local + 1) * L.plane
+        self.peer = None
+        if peer_halo and world > 1:
+            self.peer = _symmetric_vector(lambda l: (l.nz_local + 1) * l.plane, nx, ny, nz, rank, world, dev)
+            self.phi = self.peer["buffer"][:n_local]
+            self.phi.zero_()
+        else:
+            self.phi = torch.zeros(n_local, dtype=torch.float64, device=dev)
         for lp in range(L.p_own0, L.p_own1):
             self.phi[lp * L.plane:(lp + 1) * L.plane] = plane_field(seed_phi, L.l0 + lp, L.plane, dev)
         self.out = torch.zeros_like(self.phi)
@@ -155,6 +196,28 @@ class SlabDCNodal(_GraphedStep):
         self.op = G.T @ self.mesh.get_edge_inner_product(self.sigma) @ G
         self.comm_stream = torch.cuda.Stream(device=dev)
         self.launches_per_step = 3 if world > 1 else 1
+
+    def step_peer(self, sync="kernel"):
+        """One distributed apply as ONE launch of the fused kernel over all owned planes; its producer warps copy the two
+        halo planes from the neighbours' memory over NVLink.  ``sync="kernel"``: the launches order themselves -- each
+        announces its epoch to the neighbours and waits, where it needs a halo plane, for theirs (dzb.h); nothing else
+        runs between two applies.  ``sync="barrier"``: a device-side barrier across all ranks in front of the launch.
+        (Whoever overwrites ``phi`` afterwards orders that after the neighbours' kernels, e.g. by the all-reduce of a
+        dot product.)"""
+        L, P = self.layout, self.peer
+        if P is None:
+            return self.step()
+        if sync == "barrier":
+            P["handle"].barrier()
+            self.op.apply_planes_peer(self.phi, self.out, L.p_own0, L.p_own1, P["lower"], P["upper"])
+        else:
+            self.op.apply_planes_peer(self.phi, self.out, L.p_own0, L.p_own1, P["lower"], P["upper"],
+                                      sync=(P["sync"], P["lo_signal"], P["hi_signal"]))
+        return self.out
+
+    def peer_sync_timed_out(self):
+        """True if a halo wait inside a kernel gave up (the neighbour never announced its epoch): results are invalid."""
+        return self.peer is not None and bool(int(self.peer["sync_words"][4].item()))
 
     def step(self):
         L, op = self.layout, self.op
@@ -338,32 +401,29 @@ class SlabMaxwell(_GraphedStep):
 
     def _setup_peer(self, nx, ny, nz, rank, world, dev):
         """Edge vector in symmetric memory + the neighbours' addresses and slab layouts."""
-        import torch.distributed._symmetric_memory as symm_mem
+        return _symmetric_vector(lambda l: EdgeSlab(l).n, nx, ny, nz, rank, world, dev)
 
-        layouts = [SlabLayout(nx, ny, nz, r, world) for r in range(world)]
-        n_max = max(EdgeSlab(l).n for l in layouts)          # symmetric allocations have one size on every rank
-        buf = symm_mem.empty(n_max, dtype=torch.float64, device=dev)
-        hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
-        L = layouts[rank]
-        lower = upper = None
-        if L.has_lower:
-            Ll = layouts[rank - 1]
-            lower = (int(hdl.buffer_ptrs[rank - 1]), Ll.nz_local, L.p_own0 - 1, Ll.p_own1 - 1)
-        if L.has_upper:
-            Lu = layouts[rank + 1]
-            upper = (int(hdl.buffer_ptrs[rank + 1]), Lu.nz_local, L.p_own1, Lu.p_own0)
-        return {"buffer": buf, "handle": hdl, "lower": lower, "upper": upper}
-
-    def step_peer(self):
-        """One distributed apply as ONE launch: a barrier across the ranks (the neighbours' fields are complete), then the
-        fused kernel over all owned planes, which reads the halo planes from the neighbours' memory over NVLink.
-        (Whoever overwrites ``e`` afterwards must order that after the neighbours' kernels: another barrier.)"""
-        L, op = self.layout, self.op
-        if self.peer is None:
+    def step_peer(self, sync="kernel"):
+        """One distributed apply as ONE launch of the fused kernel over all owned planes, which reads the halo planes from
+        the neighbours' memory over NVLink.  ``sync="kernel"``: the launches order themselves (each announces its epoch to
+        the neighbours and waits, before its first copy out of a neighbour's memory, for that neighbour's announcement:
+        dzb.h) -- nothing else runs between two applies; ``sync="barrier"``: a device-side barrier across all ranks in
+        front of the launch.  (Whoever overwrites ``e`` afterwards orders that after the neighbours' kernels, e.g. by the
+        all-reduce of a dot product.)"""
+        L, op, P = self.layout, self.op, self.peer
+        if P is None:
             return self.step()
-        self.peer["handle"].barrier()
-        op.apply_planes_peer(self.e, self.out, L.p_own0, L.p_own1, self.peer["lower"], self.peer["upper"])
+        if sync == "barrier":
+            P["handle"].barrier()
+            op.apply_planes_peer(self.e, self.out, L.p_own0, L.p_own1, P["lower"], P["upper"])
+        else:
+            op.apply_planes_peer(self.e, self.out, L.p_own0, L.p_own1, P["lower"], P["upper"],
+                                 sync=(P["sync"], P["lo_signal"], P["hi_signal"]))
         return self.out
+
+    def peer_sync_timed_out(self):
+        """True if a halo wait inside a kernel gave up (the neighbour never announced its epoch): results are invalid."""
+        return self.peer is not None and bool(int(self.peer["sync_words"][4].item()))
 
     def step(self):
         L, op = self.layout, self.op

@@ -345,6 +345,21 @@ class DCNodalOperator(Operator):
         check(load().dzb_tm_dc_nodal_range(C.byref(self.mesh.device_mesh()), ptr(self.sigma), ptr(x), ptr(out),
                                            int(k_begin), int(k_end), stream_ptr()), "dzb_tm_dc_nodal_range")
 
+    def apply_planes_peer(self, x, out, k_begin, k_end, lower=None, upper=None, sync=None):
+        """Node planes [k_begin, k_end) of a z-slab whose halo planes are read from the neighbours' memory by the kernel.
+        ``lower`` = (device pointer of the lower neighbour's local nodal vector, its cell layers, local halo plane, plane
+        in the neighbour's array) or None; ``upper`` likewise.  ``sync`` = (this rank's sync words, the lower neighbour's
+        signal word, the upper neighbour's) for ordering inside the kernel, or None (the caller put a barrier in front)."""
+        lo = lower if lower is not None else (0, 0, -1, -1)
+        hi = upper if upper is not None else (0, 0, -1, -1)
+        sy = sync if sync is not None else (0, 0, 0)
+        check(load().dzb_tm_dc_nodal_range_peer(C.byref(self.mesh.device_mesh()), ptr(self.sigma), ptr(x),
+                                                C.c_void_p(int(lo[0])), int(lo[1]), int(lo[2]), int(lo[3]),
+                                                C.c_void_p(int(hi[0])), int(hi[1]), int(hi[2]), int(hi[3]),
+                                                C.c_void_p(int(sy[0])), C.c_void_p(int(sy[1])), C.c_void_p(int(sy[2])),
+                                                ptr(out), int(k_begin), int(k_end), stream_ptr()),
+              "dzb_tm_dc_nodal_range_peer")
+
     def matvec(self, x, out=None):
         # Host (CPU tensor) input: stream z-chunks through the GPU so that the H2D copy of chunk c+1, the
         # kernel on chunk c and the D2H copy of chunk c-1 overlap (PCIe is full duplex); the apply then
@@ -501,16 +516,21 @@ class MaxwellOperator(Operator):
                                            ptr(out), int(a0), int(a1), int(b0), int(b1), stream_ptr()),
               "dzb_tm_maxwell_range2")
 
-    def apply_planes_peer(self, x, out, k_begin, k_end, lower=None, upper=None):
+    def apply_planes_peer(self, x, out, k_begin, k_end, lower=None, upper=None, sync=None):
         """Planes [k_begin, k_end) of a z-slab whose halo planes are read from the neighbours' memory by the kernel itself.
         ``lower`` = (device pointer of the lower neighbour's local edge vector, its cell layers, local halo plane, plane in
-        the neighbour's array) or None; ``upper`` likewise.  Raises where the tensor-map path does not apply."""
+        the neighbour's array) or None; ``upper`` likewise.  ``sync`` = (this rank's sync words, the lower neighbour's
+        signal word, the upper neighbour's) for ordering inside the kernel, or None (the caller put a barrier in front).
+        Raises where the tensor-map path does not apply."""
         lo = lower if lower is not None else (0, 0, -1, -1)
         hi = upper if upper is not None else (0, 0, -1, -1)
-        check(load().dzb_tm_maxwell_range_peer(C.byref(self.mesh.device_mesh()), ptr(self.mui), ptr(self.sigma), ptr(x),
-                                               C.c_void_p(int(lo[0])), int(lo[1]), int(lo[2]), int(lo[3]),
-                                               C.c_void_p(int(hi[0])), int(hi[1]), int(hi[2]), int(hi[3]),
-                                               ptr(out), int(k_begin), int(k_end), stream_ptr()), "dzb_tm_maxwell_range_peer")
+        sy = sync if sync is not None else (0, 0, 0)
+        check(load().dzb_tm_maxwell_range_peer_sync(C.byref(self.mesh.device_mesh()), ptr(self.mui), ptr(self.sigma), ptr(x),
+                                                    C.c_void_p(int(lo[0])), int(lo[1]), int(lo[2]), int(lo[3]),
+                                                    C.c_void_p(int(hi[0])), int(hi[1]), int(hi[2]), int(hi[3]),
+                                                    C.c_void_p(int(sy[0])), C.c_void_p(int(sy[1])), C.c_void_p(int(sy[2])),
+                                                    ptr(out), int(k_begin), int(k_end), stream_ptr()),
+              "dzb_tm_maxwell_range_peer")
 
     def matvec(self, x, out=None):
         # pinned host input: stream z-chunks (H2D of chunk c+1, kernel on chunk c, D2H of chunk c-1 overlap)

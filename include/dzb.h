@@ -147,6 +147,23 @@ int dzb_tm_mass_deriv_apply(const DzbTensorMesh *m, int flags, int model_kind, c
  * (rows are staged with 16-byte bulk copies that stop at the aligned bounds inside the arrays; the at most
  * one element left at an odd-aligned end is staged by a plain load). */
 int dzb_tm_dc_nodal(const DzbTensorMesh *m, const double *sigma, const double *phi, double *y, void *stream);
+/* A z-slab's apply with PEER-READ halos (one process per GPU, NVLink): phi on the local node planes lo_plane / hi_plane
+ * is fetched by the kernel's producer warp from the neighbours' local vectors phi_lo / phi_hi (peer memory mapped into
+ * this process; NULL: no such neighbour) at plane lo_peer_plane / hi_peer_plane of those arrays, which hold nz_lo + 1 /
+ * nz_hi + 1 node planes of the same nx, ny.  ONE launch per apply and rank: no send / recv, no separate launches for the
+ * planes next to a halo.  Returns -2 where the staged-ring kernel does not apply (use dzb_tm_dc_nodal_range + an exchange).
+ * Ordering after the neighbours' writes to their phi: sync == NULL -- the caller's job (a barrier across the ranks in
+ * front of the call); else IN the kernel: sync = 5 zero-initialised words of this rank ([0] / [1] written by the lower /
+ * upper neighbour, [2] launches completed, [3] scratch, [4] set if a wait gave up after 2 s), lo_signal / hi_signal = the
+ * addresses of the lower neighbour's sync[1] / the upper neighbour's sync[0] (peer memory; NULL: no such neighbour).  Each
+ * launch announces "phi of epoch sync[2] + 1 is complete" to both neighbours and its producer warps wait for the
+ * neighbours' announcement of the same epoch before they copy a halo plane, so every rank must call this the same number
+ * of times; nothing but the stream order of each rank is needed around the call. */
+int dzb_tm_dc_nodal_range_peer(const DzbTensorMesh *m, const double *sigma, const double *phi, const double *phi_lo,
+                               int64_t nz_lo, int64_t lo_plane, int64_t lo_peer_plane, const double *phi_hi,
+                               int64_t nz_hi, int64_t hi_plane, int64_t hi_peer_plane, uint32_t *sync,
+                               uint32_t *lo_signal, uint32_t *hi_signal, double *y, int64_t k_begin, int64_t k_end,
+                               void *stream);
 /* The same operator on nrhs right-hand sides in ONE launch (multi-source DC surveys: scipy's matmat): right-hand side r is
  * phi + r * ldx, its result y + r * ldx (ldx >= nN).  sigma is read from DRAM once per tile, not once per right-hand
  * side: the nrhs blocks that stage the same tile are scheduled side by side and share it through L2. */
@@ -192,6 +209,14 @@ int dzb_tm_maxwell_range_peer(const DzbTensorMesh *m, const double *mui, const d
                               const double *e_lo, int64_t nz_lo, int64_t lo_plane, int64_t lo_peer_plane,
                               const double *e_hi, int64_t nz_hi, int64_t hi_plane, int64_t hi_peer_plane, double *y,
                               int64_t k_begin, int64_t k_end, void *stream);
+/* The same with the ordering against the neighbours' writes done INSIDE the kernel: sync / lo_signal / hi_signal as for
+ * dzb_tm_dc_nodal_range_peer (5 zero-initialised words of this rank; the lower neighbour's sync[1], the upper neighbour's
+ * sync[0]).  No barrier, no other launch between two distributed applies; every rank calls it the same number of times. */
+int dzb_tm_maxwell_range_peer_sync(const DzbTensorMesh *m, const double *mui, const double *sigma, const double *e,
+                                   const double *e_lo, int64_t nz_lo, int64_t lo_plane, int64_t lo_peer_plane,
+                                   const double *e_hi, int64_t nz_hi, int64_t hi_plane, int64_t hi_peer_plane,
+                                   uint32_t *sync, uint32_t *lo_signal, uint32_t *hi_signal, double *y, int64_t k_begin,
+                                   int64_t k_end, void *stream);
 /* y = C^T Mf(mui) C e + (alpha_re + i alpha_im) Me(sigma) e for a COMPLEX edge field in ONE launch: e and y are
  * interleaved (re, im) arrays of 2 nE doubles (numpy / torch complex128).  This is the frequency-domain Maxwell operator
  * SimPEG applies (alpha = i omega).  Face weights and edge masses are computed once for both parts.

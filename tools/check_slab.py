@@ -42,6 +42,38 @@ for (nx, ny, nz) in ((40, 33, 29), (70, 20, 64), (512, 64, 96)):
     err_h = float((host_out - ref.cpu()).abs().max() / ref.abs().max())
     print(f"rank {rank}/{world} mesh {nx}x{ny}x{nz} step_from_host rel err {err_h:.2e}", flush=True)
     ok = ok and err_h == 0.0
+# K8 with peer-read halos: one launch per apply, the producer warp copies the halo planes from the neighbours' memory
+for (nx, ny, nz) in ((40, 33, 29), (70, 20, 64), (41, 32, 30), (512, 64, 96)):
+    rng = np.random.default_rng(1)
+    h = (rng.random(nx) + 0.5, rng.random(ny) + 0.5, rng.random(nz) + 0.5)
+    part = SlabDCNodal(nx, ny, nz, rank, world, h=h, peer_halo=True)
+    whole = SlabDCNodal(nx, ny, nz, 0, 1, h=h)
+    whole.step()
+    torch.cuda.synchronize()
+    ref = whole.out[part.layout.owned_node_slice()]
+    for mode in ("barrier", "kernel"):          # ordering by a barrier in front / by signals inside the kernel
+        part.out.zero_()
+        for _ in range(3):
+            part.step_peer(sync=mode)
+        torch.cuda.synchronize()
+        err = float((part.owned_output() - ref).abs().max() / ref.abs().max())
+        print(f"rank {rank}/{world} dc PEER-READ halos ({mode}) {nx}x{ny}x{nz} rel err {err:.2e} "
+              f"timed out {part.peer_sync_timed_out()}", flush=True)
+        ok = ok and err == 0.0 and not part.peer_sync_timed_out()
+    # a field that CHANGES between the applies: the in-kernel ordering must deliver the neighbours' new planes
+    for it in range(4):
+        dist.barrier()                          # the neighbours have finished reading the previous field
+        part.phi.mul_(1.0 + 0.25 * (it + 1))
+        whole.phi.mul_(1.0 + 0.25 * (it + 1))
+        part.step_peer(sync="kernel")
+        whole.step()
+        torch.cuda.synchronize()
+        ref2 = whole.out[part.layout.owned_node_slice()]
+        err = float((part.owned_output() - ref2).abs().max() / ref2.abs().max())
+        ok = ok and err == 0.0
+    print(f"rank {rank}/{world} dc PEER-READ halos, field rescaled between applies: last rel err {err:.2e}", flush=True)
+    dist.barrier()
+    del part
 for (nx, ny, nz) in ((40, 33, 29), (70, 20, 64), (300, 64, 96)):
     rng = np.random.default_rng(2)
     h = (rng.random(nx) + 0.5, rng.random(ny) + 0.5, rng.random(nz) + 0.5)
@@ -64,19 +96,35 @@ for (nx, ny, nz) in ((40, 32, 29), (64, 20, 64), (256, 64, 96)):
     rng = np.random.default_rng(4)
     h = (rng.random(nx) + 0.5, rng.random(ny) + 0.5, rng.random(nz) + 0.5)
     part = SlabMaxwell(nx, ny, nz, rank, world, h=h, peer_halo=True)
-    for _ in range(2):
-        part.step_peer()
-    torch.cuda.synchronize()
     whole = SlabMaxwell(nx, ny, nz, 0, 1, h=h)
-    whole.step()
-    torch.cuda.synchronize()
     L, esw = part.layout, whole.es
     g0, g1 = L.c0, L.c1 + (0 if L.has_upper else 1)
-    ref = (whole.out[g0 * esw.px:g1 * esw.px], whole.out[esw.off_y + g0 * esw.py:esw.off_y + g1 * esw.py],
-           whole.out[esw.off_z + L.c0 * esw.pz:esw.off_z + L.c1 * esw.pz])
-    errs = [float((a - b).abs().max() / b.abs().max()) for a, b in zip(part.owned_parts(part.out), ref)]
-    print(f"rank {rank}/{world} maxwell PEER-READ halos {nx}x{ny}x{nz} rel err Ex/Ey/Ez {errs}", flush=True)
-    ok = ok and max(errs) <= 1e-14
+
+    def owned_of_whole():
+        return (whole.out[g0 * esw.px:g1 * esw.px], whole.out[esw.off_y + g0 * esw.py:esw.off_y + g1 * esw.py],
+                whole.out[esw.off_z + L.c0 * esw.pz:esw.off_z + L.c1 * esw.pz])
+
+    whole.step()
+    torch.cuda.synchronize()
+    for mode in ("barrier", "kernel"):          # ordering by a barrier in front / by signals inside the kernel
+        part.out.zero_()
+        for _ in range(3):
+            part.step_peer(sync=mode)
+        torch.cuda.synchronize()
+        errs = [float((a - b).abs().max() / b.abs().max()) for a, b in zip(part.owned_parts(part.out), owned_of_whole())]
+        print(f"rank {rank}/{world} maxwell PEER-READ halos ({mode}) {nx}x{ny}x{nz} rel err Ex/Ey/Ez {errs} "
+              f"timed out {part.peer_sync_timed_out()}", flush=True)
+        ok = ok and max(errs) <= 1e-14 and not part.peer_sync_timed_out()
+    for it in range(4):                         # a field that changes between the applies
+        dist.barrier()
+        part.e.mul_(1.0 + 0.25 * (it + 1))
+        whole.e.mul_(1.0 + 0.25 * (it + 1))
+        part.step_peer(sync="kernel")
+        whole.step()
+        torch.cuda.synchronize()
+        errs = [float((a - b).abs().max() / b.abs().max()) for a, b in zip(part.owned_parts(part.out), owned_of_whole())]
+        ok = ok and max(errs) <= 1e-14
+    print(f"rank {rank}/{world} maxwell PEER-READ halos, field rescaled between applies: last rel err {errs}", flush=True)
     dist.barrier()
     del part
 # the same operators with USER models and a global field handed over by every rank (the mesh-level API of a
