@@ -136,6 +136,74 @@ __global__ void __launch_bounds__(256)
   y[perm ? (i64)__ldg(perm + row) : row] = acc;
 }
 
+// Sliced ELL (SELL-32) for rows of DIFFERENT lengths (the transposed operators, nodal_gradient: 1..24 entries): rows are
+// cut into slices of 32 (one warp); slice s stores its entries column-major with the slice's own width
+// K_s = (slice_ptr[s+1] - slice_ptr[s]) / 32, entry e of the slice's row l at slice_ptr[s] + 32 e + l, shorter rows padded
+// with ELL_PAD codes.  Index and code loads are coalesced like ELL's and there is no row-pointer load in front of them (the
+// CSR kernel's dependent chain is indptr -> index -> gather); on an OcTree most slices are uniform, so the padding is a
+// few per cent.  Entries are processed four at a time: four index loads, then four gathers in flight.
+template <bool BYCOL, typename SP>
+__global__ void __launch_bounds__(256)
+    k_tree_sell(i64 nrows, i64 nslices, const SP *__restrict__ slice_ptr, const int *__restrict__ indices,
+                const unsigned char *__restrict__ codes, const double *__restrict__ tab_mult,
+                const unsigned char *__restrict__ tab_sel, int ntab, const double *__restrict__ g0,
+                const double *__restrict__ g1, const double *__restrict__ g2, const int *__restrict__ perm,
+                const double *__restrict__ x, double *__restrict__ y) {
+  __shared__ double s_mult[256];
+  __shared__ unsigned char s_sel[256];
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) {
+    s_mult[t] = t < ntab ? tab_mult[t] : 0.0;
+    s_sel[t] = t < ntab ? tab_sel[t] : 0;
+  }
+  __syncthreads();
+  const i64 row = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const i64 slice = row >> 5;
+  if (slice >= nslices) return;
+  const i64 base = (i64)__ldg(slice_ptr + slice);
+  const int K = (int)(((i64)__ldg(slice_ptr + slice + 1) - base) >> 5);
+  const bool live = row < nrows;
+  double gr[3] = {1.0, 1.0, 1.0};
+  if (!BYCOL && live) {
+    if (g0) gr[0] = __ldg(g0 + row);
+    if (g1) gr[1] = __ldg(g1 + row);
+    if (g2) gr[2] = __ldg(g2 + row);
+  }
+  const int *pi = indices + base + (threadIdx.x & 31);
+  const unsigned char *pc = codes + base + (threadIdx.x & 31);
+  double acc = 0.0;
+  int e = 0;
+  for (; e + 4 <= K; e += 4) {
+    int col[4], c[4];
+    double xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      col[u] = __ldg(pi + (e + u) * 32);
+      c[u] = __ldg(pc + (e + u) * 32);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) xv[u] = c[u] != ELL_PAD ? __ldg(x + col[u]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (c[u] != ELL_PAD) acc += coded_value(c[u], col[u], s_mult, s_sel, BYCOL, gr, g0, g1, g2) * xv[u];
+  }
+  if (e < K) {   // 1..3 entries left: loads first, predicated
+    int col[3], c[3];
+    double xv[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const bool on = e + u < K;
+      col[u] = on ? __ldg(pi + (e + u) * 32) : 0;
+      c[u] = on ? (int)__ldg(pc + (e + u) * 32) : ELL_PAD;
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) xv[u] = c[u] != ELL_PAD ? __ldg(x + col[u]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+      if (c[u] != ELL_PAD) acc += coded_value(c[u], col[u], s_mult, s_sel, BYCOL, gr, g0, g1, g2) * xv[u];
+  }
+  if (live) y[perm ? (i64)__ldg(perm + row) : row] = acc;
+}
+
 // CSR with warp-staged entries: a warp owns 32 consecutive rows; the contiguous span of their entries is copied
 // to shared memory with coalesced loads, then every lane walks its own row out of shared memory.  (Measured SLOWER
 // than the plain kernel on OcTree operators -- the gathers, not the index loads, set the pace -- kept for comparison.)
@@ -331,6 +399,31 @@ extern "C" int dzb_tree_ell_spmv_perm(int64_t nrows, int row_len, int64_t stride
   }
 #undef DZB_ELL_LAUNCH
   return check_launch("dzb_tree_ell_spmv");
+}
+
+extern "C" int dzb_tree_sell_spmv(int64_t nrows, const void *slice_ptr, int slice_ptr_is64, const int32_t *indices,
+                                  const uint8_t *codes, const double *tab_mult, const uint8_t *tab_sel, int ntab,
+                                  const double *g0, const double *g1, const double *g2, int geom_by_col,
+                                  const int32_t *perm, const double *x, double *y, void *stream) {
+  if (nrows <= 0) return 0;
+  if (ntab < 1 || ntab > 255) {
+    set_error("dzb_tree_sell_spmv: the code table must have 1..255 entries (code 255 marks padding)");
+    return -1;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const i64 nslices = (nrows + 31) / 32;
+  const unsigned blocks = (unsigned)((nslices * 32 + 255) / 256);
+#define DZB_SELL_LAUNCH(BC, SP) \
+  k_tree_sell<BC, SP><<<blocks, 256, 0, s>>>(nrows, nslices, (const SP *)slice_ptr, indices, codes, tab_mult, tab_sel, ntab, g0, g1, g2, perm, x, y)
+  if (geom_by_col) {
+    if (slice_ptr_is64) DZB_SELL_LAUNCH(true, i64);
+    else DZB_SELL_LAUNCH(true, int);
+  } else {
+    if (slice_ptr_is64) DZB_SELL_LAUNCH(false, i64);
+    else DZB_SELL_LAUNCH(false, int);
+  }
+#undef DZB_SELL_LAUNCH
+  return check_launch("dzb_tree_sell_spmv");
 }
 
 extern "C" int dzb_csr_spmv(int64_t nrows, const void *indptr, int indptr_is64, const int32_t *indices,

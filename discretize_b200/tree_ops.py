@@ -49,6 +49,38 @@ def _group_values(data):
     return rep, group[inv]
 
 
+def fold_geometry(geoms, parts, geom_by_col):
+    """Multiply the row (or column) geometry into the entries where the result still fits a code table.
+
+    An operator is  sum_s diag(geom_s) @ M_s  (transposed: M_s^T @ diag(geom_s)).  On an OcTree over a UNIFORM base mesh
+    -- what discretize's octrees are in practice -- 1/h, 1/L take one value per level, so the products
+    multiplier * geometry are a handful of numbers: they go into the table as they are (the same IEEE product the kernel
+    would form, so nothing changes bitwise) and the kernel reads no geometry arrays at all (face_divergence: 24 of 88
+    bytes per cell).  Returns (geoms, parts) unchanged if any part would need more than MAX_CODES values in total."""
+    if not any(s_ for s_, _ in parts):
+        return geoms, parts
+    folded, total = [], 0
+    for s_, M in parts:
+        M = sp.csr_matrix(M)
+        if s_:
+            g = np.asarray(geoms[s_ - 1], dtype=np.float64)
+            if geom_by_col:
+                data = M.data * g[M.indices]
+            else:
+                data = M.data * np.repeat(g, np.diff(M.indptr))
+            M = sp.csr_matrix((data, M.indices, M.indptr), shape=M.shape)
+        # distinct values of this part, without a full sort where they are few
+        sample = np.unique(M.data[: min(M.data.size, 1 << 18)])
+        if sample.size > MAX_CODES:
+            return geoms, parts
+        vals, _ = _unique_small(M.data)
+        total += vals.size
+        if total > MAX_CODES:
+            return geoms, parts
+        folded.append((0, M))
+    return [], folded
+
+
 def encode_parts_raw(geoms, parts, shape):
     """Like ``encode_parts`` for parts that hold DUPLICATE (row, column) pairs on purpose (ghost columns redirected by
     ``tree_shard``): entries are concatenated row by row, never summed."""
@@ -102,7 +134,9 @@ def encode_parts(geoms, parts, shape):
 class CodedCsr:
     """Device-resident coded CSR (one direction of an operator)."""
 
-    def __init__(self, geoms, parts, shape, geom_by_col, canonical=True, sort_rows=False):
+    def __init__(self, geoms, parts, shape, geom_by_col, canonical=True, sort_rows=False, fold=True):
+        if fold:
+            geoms, parts = fold_geometry(geoms, parts, geom_by_col)
         indptr, indices, codes, tmult, tsel = (encode_parts if canonical else encode_parts_raw)(geoms, parts, shape)
         self.shape = shape
         self.nnz = int(indptr[-1])
@@ -127,18 +161,32 @@ class CodedCsr:
             if kmax > 0 and (lens.min() == kmax or (kmax <= 12 and kmax <= 1.5 * avg_len)):
                 self.row_len = kmax
             self.padded = int(lens.min() != kmax)
-        self.layout = "ell" if self.row_len > 0 else "lpr"   # measured: "stream" loses to "lpr" (tools/sweep_tree.py)
+        # rows of different lengths (transposed operators, nodal_gradient): sliced ELL; "lpr" / "stream" (CSR) stay
+        # selectable for comparison (tools/sweep_tree.py)
+        self.layout = "ell" if self.row_len > 0 else "lpr"
+        if self.row_len <= 0 and lens.size and self.ntab <= 255:
+            # sliced ELL only where its slices are nearly uniform: on the 10 M-cell config-3 tree every transposed
+            # operator has a long row (a parent face / edge with hanging children) in most slices of 32 -- 50..87 %
+            # padding, and the CSR kernel is 20 % faster there (tools/bench_tree.py)
+            lp = np.zeros((lens.size + 31) // 32 * 32, dtype=np.int64)
+            lp[:lens.size] = lens
+            padded_entries = int(lp.reshape(-1, 32).max(axis=1).sum()) * 32
+            if padded_entries <= 1.1 * max(self.nnz, 1):
+                self.layout = "sell"
         avg = self.nnz / max(shape[0], 1)
         self.lpr = 1 if avg <= 7 else 2 if avg <= 16 else 4 if avg <= 40 else 16
         self.ell_indices = self.ell_codes = None
-        # rows stored in column-locality order (ELL, row geometry only): see dzb_tree_ell_spmv_perm
-        self.sort_rows = bool(sort_rows) and not self.geom_by_col
+        self.sell_ptr = self.sell_indices = self.sell_codes = None
+        self.sell_padding = 0.0
+        # rows stored in column-locality order (ELL / SELL): see dzb_tree_ell_spmv_perm
+        self.sort_rows = bool(sort_rows)
         self.ell_perm = None
         self.ell_geoms = self.geoms
         self.use_layout(self.layout)
 
     def use_layout(self, layout):
-        """Select (and upload on first use) one of the device layouts: "ell" (constant row length only), "stream", "lpr"."""
+        """Select (and upload on first use) one of the device layouts: "ell" (constant row length only), "sell" (sliced
+        ELL, any rows), "stream", "lpr"."""
         indptr, indices, codes = self._host
         if layout == "ell":
             if self.row_len <= 0:
@@ -153,7 +201,7 @@ class CodedCsr:
                 slot = np.arange(indices.size) - np.repeat(indptr[:-1], lens)
                 ie[slot, rows] = indices
                 ce[slot, rows] = codes
-                if self.sort_rows and n > 1:
+                if self.sort_rows and n > 1 and not self.geom_by_col:
                     first = np.where(ce[:, :n] != 255, ie[:, :n], np.iinfo(np.int32).max).min(axis=0)
                     order = np.argsort(first, kind="stable")
                     ie[:, :n] = ie[:, :n][:, order]
@@ -163,6 +211,43 @@ class CodedCsr:
                     self.ell_geoms = [None if g is None else g.index_select(0, dorder) for g in self.geoms]
                 self.ell_indices = to_device(ie.reshape(-1), torch.int32)
                 self.ell_codes = to_device(ce.reshape(-1), torch.uint8)
+        elif layout == "sell":
+            if self.sell_indices is None:
+                n = self.shape[0]
+                lens = np.diff(indptr)
+                order = None
+                if self.sort_rows and n > 1:
+                    first = np.full(n, np.iinfo(np.int32).max, dtype=np.int64)
+                    has = lens > 0
+                    first[has] = indices[indptr[:-1][has]]          # canonical CSR: the smallest column comes first
+                    order = np.argsort(first, kind="stable")
+                l = lens if order is None else lens[order]
+                starts = indptr[:-1] if order is None else indptr[:-1][order]
+                nsl = (n + 31) // 32
+                lp = np.zeros(nsl * 32, dtype=np.int64)
+                lp[:n] = l
+                K = lp.reshape(nsl, 32).max(axis=1)
+                sptr = np.r_[0, np.cumsum(K * 32)].astype(np.int64)
+                total = int(sptr[-1])
+                ie = np.zeros(total, dtype=np.int32)
+                ce = np.full(total, 255, dtype=np.uint8)           # 255 = padding slot
+                new_row = np.repeat(np.arange(n, dtype=np.int64), l)
+                slot = np.arange(int(l.sum()), dtype=np.int64) - np.repeat(np.cumsum(l) - l, l)
+                src = np.repeat(starts, l) + slot
+                dst = sptr[new_row >> 5] + slot * 32 + (new_row & 31)
+                ie[dst] = indices[src]
+                ce[dst] = codes[src]
+                self.sell_padding = total / max(self.nnz, 1) - 1.0
+                self.sell_is64 = total >= 2**31 - 1
+                self.sell_ptr = to_device(sptr if self.sell_is64 else sptr.astype(np.int32),
+                                          torch.int64 if self.sell_is64 else torch.int32)
+                self.sell_indices = to_device(ie, torch.int32)
+                self.sell_codes = to_device(ce, torch.uint8)
+                if order is not None:
+                    self.ell_perm = to_device(order.astype(np.int32), torch.int32)
+                    if not self.geom_by_col:
+                        dorder = to_device(order.astype(np.int64), torch.int64)
+                        self.ell_geoms = [None if g is None else g.index_select(0, dorder) for g in self.geoms]
         elif layout in ("stream", "lpr"):
             if self.indices is None:
                 self.indptr = to_device(indptr if self.is64 else indptr.astype(np.int32),
@@ -182,6 +267,13 @@ class CodedCsr:
                                                 ptr(g[0]), ptr(g[1]), ptr(g[2]), self.geom_by_col, self.padded,
                                                 ptr(self.ell_perm), ptr(x), ptr(out), stream_ptr()), "dzb_tree_ell_spmv")
             return
+        if self.layout == "sell":
+            g = self.ell_geoms
+            check(load().dzb_tree_sell_spmv(self.shape[0], ptr(self.sell_ptr), int(self.sell_is64), ptr(self.sell_indices),
+                                            ptr(self.sell_codes), ptr(self.tab_mult), ptr(self.tab_sel), self.ntab,
+                                            ptr(g[0]), ptr(g[1]), ptr(g[2]), self.geom_by_col, ptr(self.ell_perm),
+                                            ptr(x), ptr(out), stream_ptr()), "dzb_tree_sell_spmv")
+            return
         lpr = 0 if self.layout == "stream" else self.lpr
         check(load().dzb_tree_spmv(self.shape[0], ptr(self.indptr), int(self.is64), ptr(self.indices), ptr(self.codes),
                                    ptr(self.tab_mult), ptr(self.tab_sel), self.ntab, ptr(g[0]), ptr(g[1]), ptr(g[2]),
@@ -191,7 +283,7 @@ class CodedCsr:
         """Algorithmic bytes: vectors + int32 columns + code bytes + indptr + row geometry."""
         n_geom = sum(g is not None for g in self.geoms)
         gsize = (self.shape[1] if self.geom_by_col else self.shape[0]) * n_geom
-        ptr_bytes = 0 if self.layout == "ell" else (8 if self.is64 else 4) * (self.shape[0] + 1)
+        ptr_bytes = 0 if self.layout in ("ell", "sell") else (8 if self.is64 else 4) * (self.shape[0] + 1)
         return 8 * (self.shape[0] + self.shape[1]) + 5 * self.nnz + ptr_bytes + 8 * gsize   # padding slots not counted
 
 
@@ -237,8 +329,9 @@ class TreeOperator(Operator):
             else:
                 shape = self._fwd_shape
             try:
+                label = self.name + (".T" if transposed else "")
                 self._dev[key] = CodedCsr(geoms, parts, shape, geom_by_col=transposed,
-                                          sort_rows=(not transposed) and self.name in SORTED_ROW_OPERATORS)
+                                          sort_rows=label in SORTED_ROW_OPERATORS)
             except CodeTableOverflow:
                 # geometry-dependent weights (the distance weights of average_cell_to_face on non-uniform base widths):
                 # apply the reference's matrix with stored values, 12 B per entry instead of 5

@@ -302,6 +302,14 @@ int dzb_tree_ell_spmv_perm(int64_t nrows, int row_len, int64_t stride, const int
                            const double *tab_mult, const uint8_t *tab_sel, int ntab, const double *g0, const double *g1,
                            const double *g2, int geom_by_col, int padded, const int32_t *perm, const double *x, double *y,
                            void *stream);
+/* Sliced ELL (SELL-32) for rows of different lengths (transposed operators, nodal_gradient): slice s = rows 32 s ..
+ * 32 s + 31 stores entry e of its row l at slice_ptr[s] + 32 e + l with the slice's own width
+ * (slice_ptr[s+1] - slice_ptr[s]) / 32; padding slots carry code 255.  slice_ptr: ceil(nrows / 32) + 1 offsets (int32 or
+ * int64); perm as in dzb_tree_ell_spmv_perm (NULL: table row r is row r). */
+int dzb_tree_sell_spmv(int64_t nrows, const void *slice_ptr, int slice_ptr_is64, const int32_t *indices,
+                       const uint8_t *codes, const double *tab_mult, const uint8_t *tab_sel, int ntab, const double *g0,
+                       const double *g1, const double *g2, int geom_by_col, const int32_t *perm, const double *x,
+                       double *y, void *stream);
 /* y = A x for a CSR matrix with stored float64 values (int32 columns, int32 / int64 indptr): scipy
  * matrices mixed into operator algebra and the full-tensor OcTree mass matrices
  * (operators/inner_products.py:147-272 with tree_ext.pyx:5651-5763 projections). */

@@ -164,7 +164,10 @@ def test_sharded_tree_operators_loopback(gold, world):
 
 @pytest.mark.parametrize("name", ["face_divergence", "average_edge_to_cell", "edge_curl", "nodal_gradient"])
 def test_tree_spmv_layouts_agree(gold, name):
-    """ELL (constant row length), warp-staged CSR and the lanes-per-row kernel are three implementations of one SpMV."""
+    """ELL (constant row length), sliced ELL (natural and column-sorted rows), warp-staged CSR and the lanes-per-row
+    kernel are implementations of one SpMV."""
+    from discretize_b200.tree_ops import CodedCsr
+
     m = _mesh_from_fixture(gold, "b", "refine")
     ref = golden_matrix(gold, f"b_{name}")
     rng = np.random.default_rng(13)
@@ -172,7 +175,7 @@ def test_tree_spmv_layouts_agree(gold, name):
     op = getattr(m, name)
     for tr, vec, r in ((False, x, ref @ x), (True, y, ref.T @ y)):
         csr = op._csr(tr)
-        layouts = ["stream", "lpr"] + (["ell"] if csr.row_len > 0 else [])
+        layouts = ["stream", "lpr", "sell"] + (["ell"] if csr.row_len > 0 else [])
         if not tr and name in ("face_divergence", "average_edge_to_cell"):
             assert "ell" in layouts       # every cell-rowed operator has rows of one length
         for layout in layouts:
@@ -182,6 +185,18 @@ def test_tree_spmv_layouts_agree(gold, name):
                 out = torch.empty(csr.shape[0], dtype=torch.float64, device="cuda")
                 csr.apply(torch.from_numpy(vec).cuda(), out)
                 assert_close_vec(out.cpu().numpy(), r)
+        # sliced ELL with its rows stored in column-locality order (result scattered through the permutation), with the
+        # geometry kept in arrays (fold=False) as on meshes whose products do not fit a code table
+        geoms, parts = m._host_parts(name)
+        if tr:
+            parts = [(s_, P.T.tocsr()) for s_, P in parts]
+        for fold in (True, False):
+            c2 = CodedCsr(geoms, parts, csr.shape, geom_by_col=tr, sort_rows=True, fold=fold)
+            c2.use_layout("sell")
+            assert c2.ell_perm is not None
+            out = torch.full((c2.shape[0],), float("nan"), dtype=torch.float64, device="cuda")
+            c2.apply(torch.from_numpy(vec).cuda(), out)
+            assert_close_vec(out.cpu().numpy(), r)
 
 
 @pytest.mark.parametrize("tag", ["a", "b"])

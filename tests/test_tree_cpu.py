@@ -224,3 +224,35 @@ def test_code_table_holds_exact_values_and_overflow_is_signalled():
     wide = sp.csr_matrix(np.diag(rng.random(300) + 0.5))
     with pytest.raises(CodeTableOverflow):
         encode_parts([], [(0, wide)], wide.shape)
+
+
+def test_geometry_folds_into_the_code_table_on_uniform_base_meshes():
+    """On an OcTree over a uniform base mesh the products multiplier * (1/h, 1/L) are a handful of values: they replace
+    the per-row geometry arrays (the SpMV kernel then reads none) and reproduce the reference's matrix entry for entry;
+    a strongly graded base mesh keeps its geometry arrays."""
+    import scipy.sparse as sp
+
+    from discretize_b200.tree_ops import encode_parts, fold_geometry
+
+    mesh = TreeMesh([16, 16, 16])
+    mesh.refine_points(np.array([[0.3, 0.3, 0.3], [0.7, 0.6, 0.2]]), -1, finalize=True)
+    for name in ("face_divergence", "edge_curl", "nodal_gradient"):
+        geoms, parts = mesh._host_parts(name)
+        M = mesh._host_matrix(name)
+        for by_col in (False, True):
+            pp = [(s_, sp.csr_matrix(P.T)) for s_, P in parts] if by_col else parts
+            want = sp.csr_matrix(M.T) if by_col else M
+            g2, p2 = fold_geometry(geoms, pp, by_col)
+            assert g2 == [] and all(s_ == 0 for s_, _ in p2)
+            total = sum(P for _, P in p2)
+            assert_same_matrix(sp.csr_matrix(total), want)
+            indptr, indices, codes, tmult, tsel = encode_parts(g2, p2, want.shape)
+            assert not tsel.any() and tmult.size < 64
+            got = sp.csr_matrix((tmult[codes], indices, indptr), shape=want.shape)
+            assert_same_matrix(got, want)
+    rng = np.random.default_rng(5)
+    graded = TreeMesh([rng.random(64) + 0.5, rng.random(64) + 0.5, rng.random(8) + 0.5])
+    graded.refine(-1, finalize=True)            # every base cell: 64 distinct widths along x and y
+    geoms, parts = graded._host_parts("face_divergence")
+    g2, p2 = fold_geometry(geoms, parts, False)
+    assert g2 is geoms and p2 is parts
