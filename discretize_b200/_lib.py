@@ -54,6 +54,7 @@ SIGNATURES = {
     "dzb_tm_csr_count_flags": [_MP, _I, _I, _I, _P, _P],
     "dzb_tm_csr_fill_flags": [_MP, _I, _I, _I, _P, _P, _P, _P],
     "dzb_tm_mass_diag": [_MP, _I, _I, _P, _D, _P, _P],
+    "dzb_tm_tensor_invert": [_L, _P, _P, _P],
     "dzb_tm_mass_apply": [_MP, _I, _I, _P, _D, _P, _P, _P],
     "dzb_tm_mass_tensor_csr_count": [_MP, _I, _P, _P],
     "dzb_tm_mass_tensor_csr_fill": [_MP, _I, _P, _P, _P, _P, _P],

@@ -14,6 +14,7 @@
 #include "tm_mass_common.cuh"
 #include "tm_rowkernels.cuh"
 #include "tm_mass_march.cuh"
+#include "tm_mass_tensor_march.cuh"
 
 namespace dzb {
 
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(BX *BY *BZ)
   mass_diag_one<EDGE, 2, MODE>(m, md, inv_mat, i, j, k, x, out);
 }
 
+int g_mass_tensor_march = 1;  // K6: 0 = generic row generator (cross-check), 1 = plane-marching kernels (> 1: sweep)
 int g_mass_march = 1;  // 0: generic kernel (kept as cross-check), 1: plane-marching kernel (> 1: sweep configurations)
 
 template <bool EDGE, int MODE>
@@ -312,6 +314,16 @@ using namespace dzb;
 
 // experiment knob (not part of the stable ABI)
 extern "C" void dzb_tune_mass(int march) { dzb::g_mass_march = march; }
+extern "C" void dzb_tune_mass_tensor(int march) { dzb::g_mass_tensor_march = march; }
+
+// out = the inverses of the nC symmetric 3x3 tensors in `model` (six columns xx, yy, zz, xy, xz, yz of nC entries, like the
+// reference's (nC, 6) property in Fortran order; utils/matrix_utils.py:734-754 closed form)
+extern "C" int dzb_tm_tensor_invert(int64_t n_cells, const double *model, double *out, void *stream) {
+  if (n_cells <= 0) return 0;
+  const i64 need = (n_cells + 255) / 256;
+  k_tensor_invert<<<(unsigned)(need < 148 * 16 ? need : 148 * 16), 256, 0, (cudaStream_t)stream>>>(n_cells, model, out);
+  return check_launch("dzb_tm_tensor_invert");
+}
 
 extern "C" int dzb_tm_mass_diag(const DzbTensorMesh *mm, int flags, int model_kind, const double *model,
                                 double model_scalar, double *diag, void *stream) {
@@ -342,6 +354,12 @@ extern "C" int dzb_tm_mass_apply(const DzbTensorMesh *mm, int flags, int model_k
     if (inv_mat) {
       set_error("Solver needed to invert A.");
       return -2;
+    }
+    if (g_mass_tensor_march && !md.inv && m.nN() < ((i64)1 << 62)) {
+      // (invert_model: the host side inverts the tensors once with dzb_tm_tensor_invert and calls this without the flag)
+      if (flags & DZB_EDGES) launch_mass_tensor_march<true>(m, md.p, x, y, s);
+      else launch_mass_tensor_march<false>(m, md.p, x, y, s);
+      return check_launch("dzb_tm_mass_apply");
     }
     Args a{x, y, nullptr, nullptr, nullptr, nullptr};
     if (flags & DZB_EDGES) launch_all(RowsMassTensor<true>{md}, MODE_APPLY, m, a, s);

@@ -138,6 +138,13 @@ class MassOperator(Operator):
             else:
                 self._apply_model = 1.0 / model.dev
             self._apply_flags &= ~_lib.FLAG_INVERT_MODEL
+        if not self.is_diagonal and invert_model:
+            # full tensors: Sigma^-1 of every cell once (the closed form the kernels use), so that the apply takes the
+            # marching kernels K6 like a plain tensor model
+            inv = torch.empty_like(model.dev)
+            check(load().dzb_tm_tensor_invert(mesh.n_cells, ptr(model.dev), ptr(inv), stream_ptr()), "dzb_tm_tensor_invert")
+            self._apply_model = inv
+            self._apply_flags &= ~_lib.FLAG_INVERT_MODEL
         self._inv_diag = None
 
     @property

@@ -126,6 +126,10 @@ int dzb_tm_mass_diag(const DzbTensorMesh *m, int flags, int model_kind, const do
 /* y = M(model) x for any model kind, generated on the fly (no stored matrix). */
 int dzb_tm_mass_apply(const DzbTensorMesh *m, int flags, int model_kind, const double *model, double model_scalar,
                       const double *x, double *y, void *stream);
+/* out = the inverses of the n_cells symmetric 3x3 tensors of a full-tensor property (six columns xx, yy, zz, xy, xz, yz;
+ * closed form of utils/matrix_utils.py:734-754): `invert_model` for MODEL_TENSOR done once, so that dzb_tm_mass_apply
+ * can take its marching kernels on the result (without DZB_INVERT_MODEL). */
+int dzb_tm_tensor_invert(int64_t n_cells, const double *model, double *out, void *stream);
 /* CSR of the full-tensor mass matrix (<= 9 entries per row). */
 int dzb_tm_mass_tensor_csr_count(const DzbTensorMesh *m, int flags, int64_t *row_nnz, void *stream);
 int dzb_tm_mass_tensor_csr_fill(const DzbTensorMesh *m, int flags, const double *model, const int64_t *indptr,
