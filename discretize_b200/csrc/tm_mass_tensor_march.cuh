@@ -223,9 +223,18 @@ static void launch_mass_tensor_march(const TM &m, const double *sg, const double
     case 4: launch_mass_tensor_march_cfg<EDGE, MarchCfg<4, 32, 4>>(m, sg, x, y, s); break;
     case 5: launch_mass_tensor_march_cfg<EDGE, MarchCfg<8, 16, 0>>(m, sg, x, y, s); break;
     case 6: launch_mass_tensor_march_cfg<EDGE, MarchCfg<4, 16, 0>>(m, sg, x, y, s); break;
-    // 512^3 sweep (tools/sweep_tensor_mass.py): 8 x 32 threads over 32 planes, uncapped registers (124 / 116): Mf 2.90 ms,
-    // Me 3.42 ms; capping at 80 registers spills in the edge kernel (3.99 ms)
-    default: launch_mass_tensor_march_cfg<EDGE, MarchCfg<8, 32, 0>>(m, sg, x, y, s); break;
+    case 7: launch_mass_tensor_march_cfg<EDGE, MarchCfg<8, 32, 3>>(m, sg, x, y, s); break;
+    case 8: launch_mass_tensor_march_cfg<EDGE, MarchCfg<8, 64, 0>>(m, sg, x, y, s); break;
+    case 9: launch_mass_tensor_march_cfg<EDGE, MarchCfg<4, 32, 0>>(m, sg, x, y, s); break;
+    case 10: launch_mass_tensor_march_cfg<EDGE, MarchCfg<16, 32, 0>>(m, sg, x, y, s); break;
+    case 11: launch_mass_tensor_march_cfg<EDGE, MarchCfg<4, 64, 5>>(m, sg, x, y, s); break;
+    // 512^3 sweep (tools/sweep_tensor_mass.py): faces 8 x 32 threads over 32 planes, uncapped registers (124): 2.90 ms;
+    // edges 4 x 32 threads over 64 planes at 96 registers (5 blocks / SM): 3.07 ms (uncapped, 116 registers: 3.42 ms;
+    // capped at 80: spills, 3.9 ms)
+    default:
+      if (EDGE) launch_mass_tensor_march_cfg<EDGE, MarchCfg<4, 64, 5>>(m, sg, x, y, s);
+      else launch_mass_tensor_march_cfg<EDGE, MarchCfg<8, 32, 0>>(m, sg, x, y, s);
+      break;
   }
 }
 
