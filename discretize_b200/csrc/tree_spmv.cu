@@ -204,6 +204,39 @@ __global__ void __launch_bounds__(256)
   if (live) y[perm ? (i64)__ldg(perm + row) : row] = acc;
 }
 
+// Overflow rows of the hybrid layout (ELL of width K0 + the entries beyond K0 of the few longer rows): one thread per
+// overflow row, y[row] += sum of its extra entries.  Launched after the ELL kernel on the same stream.
+template <bool BYCOL, typename IP>
+__global__ void __launch_bounds__(256)
+    k_tree_rows_add(i64 nrem, const int *__restrict__ rows, const IP *__restrict__ indptr, const int *__restrict__ indices,
+                    const unsigned char *__restrict__ codes, const double *__restrict__ tab_mult,
+                    const unsigned char *__restrict__ tab_sel, int ntab, const double *__restrict__ g0,
+                    const double *__restrict__ g1, const double *__restrict__ g2, const double *__restrict__ x,
+                    double *__restrict__ y) {
+  __shared__ double s_mult[256];
+  __shared__ unsigned char s_sel[256];
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) {
+    s_mult[t] = t < ntab ? tab_mult[t] : 0.0;
+    s_sel[t] = t < ntab ? tab_sel[t] : 0;
+  }
+  __syncthreads();
+  const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrem) return;
+  const i64 row = __ldg(rows + r);
+  double gr[3] = {1.0, 1.0, 1.0};
+  if (!BYCOL) {
+    if (g0) gr[0] = __ldg(g0 + row);
+    if (g1) gr[1] = __ldg(g1 + row);
+    if (g2) gr[2] = __ldg(g2 + row);
+  }
+  double acc = 0.0;
+  for (i64 p = (i64)indptr[r], p1 = (i64)indptr[r + 1]; p < p1; ++p) {
+    const int c = __ldg(codes + p), col = __ldg(indices + p);
+    acc += coded_value(c, col, s_mult, s_sel, BYCOL, gr, g0, g1, g2) * __ldg(x + col);
+  }
+  y[row] += acc;
+}
+
 // CSR with warp-staged entries: a warp owns 32 consecutive rows; the contiguous span of their entries is copied
 // to shared memory with coalesced loads, then every lane walks its own row out of shared memory.  (Measured SLOWER
 // than the plain kernel on OcTree operators -- the gathers, not the index loads, set the pace -- kept for comparison.)
@@ -383,10 +416,18 @@ extern "C" int dzb_tree_ell_spmv_perm(int64_t nrows, int row_len, int64_t stride
 #define DZB_ELL_LAUNCH(BC, KT, PD) \
   k_tree_ell<BC, KT, PD><<<blocks, 256, 0, s>>>(nrows, row_len, stride, indices, codes, tab_mult, tab_sel, ntab, g0, g1, g2, perm, x, y)
   if (geom_by_col) {
-    DZB_ELL_LAUNCH(true, 0, true);
+    switch (row_len) {
+      case 2: DZB_ELL_LAUNCH(true, 2, true); break;
+      case 4: DZB_ELL_LAUNCH(true, 4, true); break;
+      default: DZB_ELL_LAUNCH(true, 0, true); break;
+    }
   } else if (padded) {
     switch (row_len) {
+      case 2: DZB_ELL_LAUNCH(false, 2, true); break;
+      case 3: DZB_ELL_LAUNCH(false, 3, true); break;
+      case 4: DZB_ELL_LAUNCH(false, 4, true); break;
       case 6: DZB_ELL_LAUNCH(false, 6, true); break;
+      case 8: DZB_ELL_LAUNCH(false, 8, true); break;
       default: DZB_ELL_LAUNCH(false, 0, true); break;
     }
   } else {
@@ -424,6 +465,31 @@ extern "C" int dzb_tree_sell_spmv(int64_t nrows, const void *slice_ptr, int slic
   }
 #undef DZB_SELL_LAUNCH
   return check_launch("dzb_tree_sell_spmv");
+}
+
+// y[rows[r]] += the entries indptr[r] .. indptr[r+1] of overflow row r (hybrid layout: call after dzb_tree_ell_spmv)
+extern "C" int dzb_tree_rows_add(int64_t nrem, const int32_t *rows, const void *indptr, int indptr_is64,
+                                 const int32_t *indices, const uint8_t *codes, const double *tab_mult,
+                                 const uint8_t *tab_sel, int ntab, const double *g0, const double *g1, const double *g2,
+                                 int geom_by_col, const double *x, double *y, void *stream) {
+  if (nrem <= 0) return 0;
+  if (ntab < 1 || ntab > 256) {
+    set_error("dzb_tree_rows_add: the code table must have 1..256 entries");
+    return -1;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)((nrem + 255) / 256);
+#define DZB_REM_LAUNCH(BC, IP) \
+  k_tree_rows_add<BC, IP><<<blocks, 256, 0, s>>>(nrem, rows, (const IP *)indptr, indices, codes, tab_mult, tab_sel, ntab, g0, g1, g2, x, y)
+  if (geom_by_col) {
+    if (indptr_is64) DZB_REM_LAUNCH(true, i64);
+    else DZB_REM_LAUNCH(true, int);
+  } else {
+    if (indptr_is64) DZB_REM_LAUNCH(false, i64);
+    else DZB_REM_LAUNCH(false, int);
+  }
+#undef DZB_REM_LAUNCH
+  return check_launch("dzb_tree_rows_add");
 }
 
 extern "C" int dzb_csr_spmv(int64_t nrows, const void *indptr, int indptr_is64, const int32_t *indices,

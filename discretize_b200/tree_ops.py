@@ -164,7 +164,26 @@ class CodedCsr:
         # rows of different lengths (transposed operators, nodal_gradient): sliced ELL; "lpr" / "stream" (CSR) stay
         # selectable for comparison (tools/sweep_tree.py)
         self.layout = "ell" if self.row_len > 0 else "lpr"
-        if self.row_len <= 0 and lens.size and self.ntab <= 255:
+        # ragged rows (transposed operators, nodal_gradient): HYBRID = ELL of width K0 on the first K0 entries of every row
+        # + a small CSR of what the few longer rows (parent faces / edges / nodes with hanging children) have beyond K0.
+        # K0 minimises  padded ELL slots + 3 x overflow entries  (an overflow entry costs a row index, a row pointer and
+        # uncoalesced loads); used when the overflow stays below 30 % of the entries.
+        self.hyb_K = 0
+        self.hyb = None
+        if self.row_len <= 0 and lens.size and self.ntab <= 255 and lens.max() > 0:
+            hist = np.bincount(lens)
+            ks = np.arange(1, hist.size)
+            longer = np.array([(hist[k + 1:] * (np.arange(k + 1, hist.size) - k)).sum() for k in ks])
+            cost = lens.size * ks + 3 * longer
+            k0 = int(ks[np.argmin(cost)])
+            # measured on the 10 M-cell config-3 tree (tools/bench_tree.py) against the CSR kernel: D.T 320 -> 283 us,
+            # C.T 404 -> 344, G 300 -> 285, aveF2CC.T 320 -> 281, aveE2CC.T 429 -> 397 (K0 = 2 or 4); the node-rowed
+            # transposes (K0 = 6, 8: G.T 264 -> 301, aveN2CC.T 285 -> 359) lose, so wide rows stay on the CSR kernel
+            if longer[k0 - 1] <= 0.3 * max(self.nnz, 1):
+                self.hyb_K = k0
+                if k0 <= 4:
+                    self.layout = "hyb"
+        if self.layout == "lpr" and lens.size and self.ntab <= 255:
             # sliced ELL only where its slices are nearly uniform: on the 10 M-cell config-3 tree every transposed
             # operator has a long row (a parent face / edge with hanging children) in most slices of 32 -- 50..87 %
             # padding, and the CSR kernel is 20 % faster there (tools/bench_tree.py)
@@ -185,8 +204,8 @@ class CodedCsr:
         self.use_layout(self.layout)
 
     def use_layout(self, layout):
-        """Select (and upload on first use) one of the device layouts: "ell" (constant row length only), "sell" (sliced
-        ELL, any rows), "stream", "lpr"."""
+        """Select (and upload on first use) one of the device layouts: "ell" (constant row length only), "hyb" (ELL +
+        overflow rows), "sell" (sliced ELL, any rows), "stream", "lpr"."""
         indptr, indices, codes = self._host
         if layout == "ell":
             if self.row_len <= 0:
@@ -211,6 +230,29 @@ class CodedCsr:
                     self.ell_geoms = [None if g is None else g.index_select(0, dorder) for g in self.geoms]
                 self.ell_indices = to_device(ie.reshape(-1), torch.int32)
                 self.ell_codes = to_device(ce.reshape(-1), torch.uint8)
+        elif layout == "hyb":
+            if self.hyb_K <= 0:
+                raise ValueError("the hybrid layout needs a width K0 (ragged rows with a short overflow)")
+            if self.hyb is None:
+                n, K = self.shape[0], self.hyb_K
+                self.stride = (n + 31) // 32 * 32
+                lens = np.diff(indptr)
+                rows = np.repeat(np.arange(n), lens)
+                slot = np.arange(indices.size) - np.repeat(indptr[:-1], lens)
+                head = slot < K
+                ie = np.zeros((K, self.stride), dtype=np.int32)
+                ce = np.full((K, self.stride), 255, dtype=np.uint8)      # 255 = padding slot
+                ie[slot[head], rows[head]] = indices[head]
+                ce[slot[head], rows[head]] = codes[head]
+                over = np.nonzero(lens > K)[0]
+                rptr = np.r_[0, np.cumsum(lens[over] - K)].astype(np.int64)
+                self.hyb = {
+                    "indices": to_device(ie.reshape(-1), torch.int32), "codes": to_device(ce.reshape(-1), torch.uint8),
+                    "rows": to_device(over.astype(np.int32), torch.int32), "nrem": int(over.size),
+                    "ptr": to_device(rptr.astype(np.int32), torch.int32),
+                    "rem_indices": to_device(indices[~head], torch.int32), "rem_codes": to_device(codes[~head], torch.uint8),
+                    "padded": int((lens < K).any()),
+                }
         elif layout == "sell":
             if self.sell_indices is None:
                 n = self.shape[0]
@@ -267,6 +309,18 @@ class CodedCsr:
                                                 ptr(g[0]), ptr(g[1]), ptr(g[2]), self.geom_by_col, self.padded,
                                                 ptr(self.ell_perm), ptr(x), ptr(out), stream_ptr()), "dzb_tree_ell_spmv")
             return
+        if self.layout == "hyb":
+            h = self.hyb
+            check(load().dzb_tree_ell_spmv_perm(self.shape[0], self.hyb_K, self.stride, ptr(h["indices"]), ptr(h["codes"]),
+                                                ptr(self.tab_mult), ptr(self.tab_sel), self.ntab, ptr(g[0]), ptr(g[1]),
+                                                ptr(g[2]), self.geom_by_col, 1, None, ptr(x), ptr(out), stream_ptr()),
+                  "dzb_tree_ell_spmv")
+            if h["nrem"]:
+                check(load().dzb_tree_rows_add(h["nrem"], ptr(h["rows"]), ptr(h["ptr"]), 0, ptr(h["rem_indices"]),
+                                               ptr(h["rem_codes"]), ptr(self.tab_mult), ptr(self.tab_sel), self.ntab,
+                                               ptr(g[0]), ptr(g[1]), ptr(g[2]), self.geom_by_col, ptr(x), ptr(out),
+                                               stream_ptr()), "dzb_tree_rows_add")
+            return
         if self.layout == "sell":
             g = self.ell_geoms
             check(load().dzb_tree_sell_spmv(self.shape[0], ptr(self.sell_ptr), int(self.sell_is64), ptr(self.sell_indices),
@@ -283,7 +337,7 @@ class CodedCsr:
         """Algorithmic bytes: vectors + int32 columns + code bytes + indptr + row geometry."""
         n_geom = sum(g is not None for g in self.geoms)
         gsize = (self.shape[1] if self.geom_by_col else self.shape[0]) * n_geom
-        ptr_bytes = 0 if self.layout in ("ell", "sell") else (8 if self.is64 else 4) * (self.shape[0] + 1)
+        ptr_bytes = 0 if self.layout in ("ell", "sell", "hyb") else (8 if self.is64 else 4) * (self.shape[0] + 1)
         return 8 * (self.shape[0] + self.shape[1]) + 5 * self.nnz + ptr_bytes + 8 * gsize   # padding slots not counted
 
 

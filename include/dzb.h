@@ -314,6 +314,12 @@ int dzb_tree_sell_spmv(int64_t nrows, const void *slice_ptr, int slice_ptr_is64,
                        const uint8_t *codes, const double *tab_mult, const uint8_t *tab_sel, int ntab, const double *g0,
                        const double *g1, const double *g2, int geom_by_col, const int32_t *perm, const double *x,
                        double *y, void *stream);
+/* Hybrid layout for ragged rows: dzb_tree_ell_spmv(_perm) on the first K0 entries of every row (padded = 1), then this
+ * on the few rows that have more: y[rows[r]] += the entries indptr[r] .. indptr[r+1] of overflow row r.  Same code table
+ * and geometry arrays as the ELL part; same stream, after it. */
+int dzb_tree_rows_add(int64_t nrem, const int32_t *rows, const void *indptr, int indptr_is64, const int32_t *indices,
+                      const uint8_t *codes, const double *tab_mult, const uint8_t *tab_sel, int ntab, const double *g0,
+                      const double *g1, const double *g2, int geom_by_col, const double *x, double *y, void *stream);
 /* y = A x for a CSR matrix with stored float64 values (int32 columns, int32 / int64 indptr): scipy
  * matrices mixed into operator algebra and the full-tensor OcTree mass matrices
  * (operators/inner_products.py:147-272 with tree_ext.pyx:5651-5763 projections). */
