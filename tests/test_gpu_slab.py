@@ -41,8 +41,8 @@ def _sync_words(world):
     return words
 
 
-@pytest.mark.parametrize("shape", [(40, 33, 29), (41, 32, 30), (70, 20, 19)])
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("shape,world", [((40, 33, 29), 2), ((40, 33, 29), 3), ((41, 32, 30), 2), ((41, 32, 30), 3),
+                                         ((70, 20, 19), 2), ((70, 20, 19), 3), ((37, 18, 5), 4), ((600, 9, 7), 7)])
 def test_dc_slabs_with_peer_read_halos(shape, world):
     from discretize_b200.slab import SlabDCNodal
 
@@ -82,8 +82,8 @@ def test_dc_slabs_with_peer_read_halos(shape, world):
                     w[1] = 1 << 30
 
 
-@pytest.mark.parametrize("shape", [(40, 32, 29), (64, 20, 18), (62, 34, 12)])
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("shape,world", [((40, 32, 29), 2), ((40, 32, 29), 3), ((64, 20, 18), 2), ((64, 20, 18), 3),
+                                         ((62, 34, 12), 2), ((62, 34, 12), 3), ((36, 18, 5), 4), ((130, 10, 7), 7)])
 def test_maxwell_slabs_with_peer_read_halos(shape, world):
     from discretize_b200.slab import SlabMaxwell
 
