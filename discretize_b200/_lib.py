@@ -84,6 +84,7 @@ SIGNATURES = {
     "dzb_interp_fused": [_P, _L, _P, _L, _P, _L, _P, _L, _L, _P, _P, _P, _P],
     "dzb_tree_spmv": [_L, _P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _I, _P],
     "dzb_tree_ell_spmv": [_L, _I, _L, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P],
+    "dzb_tree_locate": [_P, _P, _P, _P, _I, _P, _L, _P, _L, _P, _P],
     "dzb_tree_rows_add": [_L, _P, _P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P],
     "dzb_tree_sell_spmv": [_L, _P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P],
     "dzb_tree_ell_spmv_perm": [_L, _I, _L, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P],

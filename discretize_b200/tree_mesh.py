@@ -120,6 +120,16 @@ _TREE_REMOVED.update({"cellGradStencil": "cell_gradient_stencil", "maxLevel": "m
                       "permuteCC": "permute_cells", "permuteE": "permute_edges", "permuteF": "permute_faces"})
 
 
+def _cuda_ready():
+    """True where the CUDA library can run (a device is visible); host-side tree logic works without one."""
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:  # pragma: no cover
+        return False
+
+
 class TreeMesh(_MeshPersistence):
     """3-D OcTree.  ``TreeMesh([hx, hy])`` gives the 2-D QuadTree (``quad_mesh.QuadTreeMesh``, a subclass that shares
     the constructor and every refinement method, and assembles its operators on the host)."""
@@ -1709,6 +1719,8 @@ class TreeMesh(_MeshPersistence):
         tr = self._tree
         pts = np.asarray(points, dtype=np.float64)
         n = pts.shape[0]
+        if n >= self._device_locate_min_points and self.dim == 3 and _cuda_ready():
+            return self.containing_cells_device(pts).cpu().numpy()
         c = np.zeros((n, 3), dtype=np.int64)
         for d in range(3):
             edges = self._xs[d][2 * tr.rw * np.arange(1, tr.roots[d])]          # interior root boundaries
@@ -1734,6 +1746,38 @@ class TreeMesh(_MeshPersistence):
                     c[go, d] = 2 * c[go, d] + (pts[go, d] > mid)
         leaf_lo, _ = tr.leaves()
         return np.searchsorted(tr.keys(leaf_lo), tr.keys(lo))
+
+    _device_locate_min_points = 1 << 16     # below this the host descent is faster than the transfers
+
+    def containing_cells_device(self, points):
+        """``_containing_cells`` on the GPU (``dzb_tree_locate``, csrc/tree_locate.cu): int64 CUDA tensor of cell indices
+        for an (n, 3) array or CUDA tensor of points.  The reference's level-by-level descent is replaced by two
+        bisections per axis, a Morton key and one bisection over the sorted leaf keys -- same cells, ties included."""
+        import ctypes as C
+
+        import torch
+
+        from ._lib import check, load
+        from .operators import ptr, stream_ptr, to_device
+
+        if self.dim != 3:
+            raise NotImplementedError("device point location is built for the OcTree")
+        self._t()
+        tr = self._tree
+        dev = self._dev.get("locate")
+        if dev is None:
+            leaf_lo, _ = tr.leaves()
+            dev = {"nodes": [to_device(np.ascontiguousarray(self._xs[d][::2])) for d in range(3)],
+                   "keys": to_device(np.ascontiguousarray(tr.keys(leaf_lo).astype(np.int64)), torch.int64)}
+            self._dev["locate"] = dev
+        pts = points if isinstance(points, torch.Tensor) else np.ascontiguousarray(points, dtype=np.float64)
+        pts = to_device(pts).reshape(-1, 3).contiguous()
+        out = torch.empty(pts.shape[0], dtype=torch.int64, device=pts.device)
+        roots = (C.c_int32 * 3)(*[int(r) for r in tr.roots])
+        check(load().dzb_tree_locate(ptr(dev["nodes"][0]), ptr(dev["nodes"][1]), ptr(dev["nodes"][2]), roots, int(tr.rw),
+                                     ptr(dev["keys"]), int(dev["keys"].numel()), ptr(pts), int(pts.shape[0]), ptr(out),
+                                     stream_ptr()), "dzb_tree_locate")
+        return out
 
     def point2index(self, locs):
         """reference: tree_mesh.py:984-986 (index of the cell containing each point)."""

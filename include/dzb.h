@@ -320,6 +320,15 @@ int dzb_tree_sell_spmv(int64_t nrows, const void *slice_ptr, int slice_ptr_is64,
 int dzb_tree_rows_add(int64_t nrem, const int32_t *rows, const void *indptr, int indptr_is64, const int32_t *indices,
                       const uint8_t *codes, const double *tab_mult, const uint8_t *tab_sel, int ntab, const double *g0,
                       const double *g1, const double *g2, int geom_by_col, const double *x, double *y, void *stream);
+
+/* OcTree point location (TreeMesh.point2index / get_containing_cells; _extensions/tree.cpp:758-766, 1499-1516): cells[p] =
+ * the leaf that contains point p (ties and outside points as in the reference: root boundaries go high, cell centres go
+ * low, outside points end in a boundary cell).  nodes_*: fine-grid node coordinates per axis (n + 1 entries, device);
+ * roots: root cells per axis (3 host ints); root_width: fine cells per root (power of two); leaf_keys: the sorted keys
+ * root_id * root_width^3 + Z-order code of every leaf's low corner, in cell order (device); pts: (npts, 3) row-major. */
+int dzb_tree_locate(const double *nodes_x, const double *nodes_y, const double *nodes_z, const int32_t *roots, int root_width,
+                    const int64_t *leaf_keys, int64_t n_leaves, const double *pts, int64_t npts, int64_t *cells,
+                    void *stream);
 /* y = A x for a CSR matrix with stored float64 values (int32 columns, int32 / int64 indptr): scipy
  * matrices mixed into operator algebra and the full-tensor OcTree mass matrices
  * (operators/inner_products.py:147-272 with tree_ext.pyx:5651-5763 projections). */

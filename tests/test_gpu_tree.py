@@ -314,3 +314,32 @@ def test_tree_operators_with_many_distinct_weights_fall_back_to_stored_values():
         x, y = rng.standard_normal(M.shape[1]), rng.standard_normal(M.shape[0])
         assert_close_vec(op @ x, M @ x)
         assert_close_vec(op.T @ y, M.T @ y)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_device_point_location_matches_the_host_descent(gold, tag):
+    """dzb_tree_locate (bisections + Morton key + leaf-key search) against the level-by-level descent that restates
+    tree.cpp:758-766, 1499-1516: random points, points exactly on fine nodes and cell centres (the reference's ties: root
+    boundaries go high, centres go low), points outside the mesh, NaN; also on a non-cubic mesh (several roots)."""
+    import discretize_b200 as dz
+
+    meshes = [_mesh_from_fixture(gold, tag, "refine")]
+    rng = np.random.default_rng(21)
+    m2 = dz.TreeMesh([rng.random(32) + 0.5, rng.random(16) + 0.5, rng.random(64) + 0.5], origin=[-3.0, 1.0, 0.5])
+    m2.refine_points(rng.random((40, 3)) * np.array([20.0, 10.0, 40.0]) + np.array([-3.0, 1.0, 0.5]), -1, finalize=True)
+    meshes.append(m2)
+    for m in meshes:
+        lo = np.array([x[0] for x in m._xs])
+        hi = np.array([x[-1] for x in m._xs])
+        pts = lo + rng.random((20000, 3)) * (hi - lo)
+        k = 3000
+        for d in range(3):                                   # coordinates exactly on fine nodes / fine cell centres
+            pts[:k, d] = m._xs[d][rng.integers(0, m._xs[d].size, k)]
+        pts[k:k + 500] = lo + (rng.random((500, 3)) * 3.0 - 1.0) * (hi - lo)      # inside and outside
+        pts[k + 500:k + 510, 1] = np.nan
+        m._device_locate_min_points = 1 << 62
+        host = m._containing_cells(pts)
+        dev = m.containing_cells_device(pts).cpu().numpy()
+        assert np.array_equal(host, dev)
+        m._device_locate_min_points = 1
+        assert np.array_equal(m.point2index(pts), host)      # the public call takes the device path for large inputs
