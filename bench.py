@@ -6,7 +6,8 @@ TensorMesh 1024^3 Maxwell operator  y = C^T Mf(mui) C e + Me(sigma) e  (tests/bo
 in the reference), applied matrix-free by ONE fused kernel (K9) per rank.  It fits one B200 (68.8 GB), so N=1 runs the
 same mesh and N = 2/4/8 split it into z-slabs (STRONG scaling: efficiency = v_N / (N v_1) is the north-star figure).
 A "step" is one apply over one synthetic field (e ~ N(0,1), sigma and mui log-normal); "dof" = one output row.
-At N=1 the line also carries `secondary`: BASELINE configs[1] (512^3 DC nodal operator G^T Me(sigma) G, kernel K8).
+At N=1 the line also carries `secondary`: BASELINE configs[1] (512^3 DC nodal operator G^T Me(sigma) G, kernel K8), and
+`secondary_complex`: the frequency-domain form C^T Mf C + i omega Me on a complex 512^3 field (kernel K9c, one launch).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload maxwell|dc] [--n N]
 
@@ -229,6 +230,41 @@ def timed_blocks(step, steps, repeats, sync, world, dev):
             ms = float(t.item())
         out.append(ms)
     return out
+
+
+def secondary_complex_maxwell(args, dev, peak):
+    """The frequency-domain form of the benched operator, C^T Mf C + i omega Me on a COMPLEX 512^3 field: one launch (K9c)."""
+    import torch
+
+    import discretize_b200 as dz
+
+    n = 512
+    mesh = dz.TensorMesh([n, n, n])
+    gen = torch.Generator(device=dev); gen.manual_seed(21)
+    e = torch.complex(torch.randn(mesh.nE, dtype=torch.float64, device=dev, generator=gen),
+                      torch.randn(mesh.nE, dtype=torch.float64, device=dev, generator=gen))
+    sigma = torch.exp(torch.randn(mesh.nC, dtype=torch.float64, device=dev, generator=gen))
+    mui = torch.exp(torch.randn(mesh.nC, dtype=torch.float64, device=dev, generator=gen))
+    C = mesh.edge_curl
+    A = C.T @ mesh.get_face_inner_product(mui) @ C + 1j * (2 * np.pi * 10.0) * mesh.get_edge_inner_product(sigma)
+    assert type(A).__name__ == "ComplexMaxwellOperator"
+    out = torch.empty_like(e)
+    if A.apply_device_complex(e, out=out) is None:
+        raise RuntimeError("the one-launch complex kernel does not apply to this mesh")
+    step = lambda: A.apply_device_complex(e, out=out)
+    for _ in range(3):
+        step()
+    blocks = timed_blocks(step, args.steps, 3, torch.cuda.synchronize, 1, dev)
+    ms = float(np.median(blocks)) / args.steps
+    alg = 8.0 * (4 * mesh.nE + 2 * mesh.nC)          # complex e in and out, the two models once
+    return {
+        "workload": "TensorMesh 512^3 frequency-domain Maxwell C^T Mf(mui) C + i omega Me(sigma) on a complex field, one launch",
+        "value": mesh.nE / (ms * 1e-3) / 1e9, "unit": "complex " + UNIT, "ms_per_step": ms, "steps": args.steps,
+        "block_ms": blocks, "dofs_per_step": int(mesh.nE), "gpu_launches": args.steps,
+        "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                     "kernel": "k_maxwell_cplx<1,6,PARX,4,2>", "algorithmic_bytes_per_launch": alg},
+    }
 
 
 def secondary_dc(args, dev, peak):
@@ -481,6 +517,8 @@ def run_ours(args):
         if args.workload == "maxwell" and not args.no_secondary:
             try:
                 line["secondary"] = secondary_dc(args, dev, peak)
+                torch.cuda.empty_cache()
+                line["secondary_complex"] = secondary_complex_maxwell(args, dev, peak)
             except Exception as exc:
                 line["secondary_error"] = repr(exc)[:300]
         if not args.no_cpu:
