@@ -20,6 +20,7 @@
 // falls back to the bulk-copy ring.
 // The arithmetic, the mailboxes and the halo warps are those of tm_maxwell_rows.cuh (see there for the formulas).
 #pragma once
+#include <type_traits>
 #include <cuda.h>
 #include "bulk_pipe.cuh"
 #include "tm_common.cuh"
@@ -226,33 +227,44 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
         }
         mbar_arrive_expect_tx(&full[slot], total);
         double *T = tiles + slot * G::STAGE;
+        // the stage's copies; FROM_PEER: one of its planes is a halo plane read from a neighbour (at most two stages of a
+        // block) -- everything else takes the path of the plain kernel, with compile-time map addresses (the producer
+        // lane is on the critical path: with the neighbour tests in every stage the whole kernel ran 12-20 % slower)
+        auto issue = [&](auto peer_tag) {
+          constexpr bool FROM_PEER = decltype(peer_tag)::value;
 #pragma unroll
-        for (int a = 0; a < 5; ++a) {
-          if (on[a]) {
-            int pl = jfirst + q + (a < 2 ? 1 : 0);
-            const int src = source(a, pl);             // pl is now the plane index inside the array it is read from
-            const CUtensorMap *mE = &maps.m[a], *mO = &maps.o[a];
-            if (PEER && src) {
-              mE = &maps.pm[src - 1][a < 3 ? a : 0];
-              mO = &maps.po[src - 1][a < 3 ? a : 0];
-              if (hal.sync && !((announced >> src) & 1u)) {   // the neighbour's vector of this epoch must be complete
-                wait_signal_sys(hal.sync + (src - 1), epoch, hal.sync + 4);
-                fence_proxy_async_global();
-                announced |= 1u << src;
+          for (int a = 0; a < 5; ++a) {
+            if (on[a]) {
+              int pl = jfirst + q + (a < 2 ? 1 : 0);
+              const CUtensorMap *mE = &maps.m[a], *mO = &maps.o[a];
+              if (FROM_PEER) {
+                const int src = source(a, pl);         // pl is now the plane index inside the array it is read from
+                if (src) {
+                  mE = &maps.pm[src - 1][a < 3 ? a : 0];
+                  mO = &maps.po[src - 1][a < 3 ? a : 0];
+                  if (hal.sync && !((announced >> src) & 1u)) {   // the neighbour's vector of this epoch must be complete
+                    wait_signal_sys(hal.sync + (src - 1), epoch, hal.sync + 4);
+                    fence_proxy_async_global();
+                    announced |= 1u << src;
+                  }
+                }
+              }
+              const int J0 = pl * rpp[a] + j0 - 1;     // first staged row (may be -1: zero-filled / previous plane)
+              if (G::odd(a)) {
+                // sub-tile 0 holds the staged rows rr = 0, 2, 4, .., sub-tile 1 the rows rr = 1, 3, ..: global row J0 + rr
+                // is even for the rr of parity t = J0 & 1, so the even-row box goes to sub-tile t, the odd-row box to 1 - t
+                const int t = J0 & 1;
+                load(T + G::off(a) + t * G::sub(a), mE, (Xb - 1) & ~1, (J0 + 1) >> 1, &full[slot]);
+                load(T + G::off(a) + (t ^ 1) * G::sub(a), mO, (gp[a] + Xb - 1) & ~1, J0 >> 1, &full[slot]);
+              } else {
+                load(T + G::off(a), mE, (Xb - 1) & ~1, J0, &full[slot]);
               }
             }
-            const int J0 = pl * rpp[a] + j0 - 1;       // first staged row (may be -1: zero-filled / previous plane)
-            if (G::odd(a)) {
-              // sub-tile 0 holds the staged rows rr = 0, 2, 4, .., sub-tile 1 the rows rr = 1, 3, ..: global row J0 + rr is
-              // even for the rr of parity t = J0 & 1, so the even-row box goes to sub-tile t and the odd-row box to 1 - t
-              const int t = J0 & 1;
-              load(T + G::off(a) + t * G::sub(a), mE, (Xb - 1) & ~1, (J0 + 1) >> 1, &full[slot]);
-              load(T + G::off(a) + (t ^ 1) * G::sub(a), mO, (gp[a] + Xb - 1) & ~1, J0 >> 1, &full[slot]);
-            } else {
-              load(T + G::off(a), mE, (Xb - 1) & ~1, J0, &full[slot]);
-            }
           }
-        }
+        };
+        const int plane = jfirst + q + 1, layer = jfirst + q;
+        if (PEER && (plane == hal.lo_plane || plane == hal.hi_plane || layer == hal.lo_layer)) issue(std::true_type{});
+        else issue(std::false_type{});
       }
     }
     return;
@@ -280,14 +292,25 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
   // accordingly).  Boxes start on even columns: column Xb-1 sits at box column leadE = (Xb-1)&1 in boxes of even global
   // rows and -- the pitch being odd -- at 1-leadE in boxes of odd global rows.
   const int leadE = (Xb - 1) & 1;
-  auto rowoff = [&](int a, int rr, int pl) -> int {
+  // `flip`: 1 where the plane was read from a neighbour's array and sits on a plane of the other parity there (the row
+  // parity is that of the array the plane was read from); the plane index itself only enters through its parity, which
+  // is the same in every ring cycle (S is even), so `pl` is jfirst + slot and everything but `flip` folds per slot
+  auto rowoff = [&](int a, int rr, int pl, int flip) -> int {
     if (G::odd(a)) {
-      if (PEER) (void)source(a, pl);      // the row parity is that of the array the plane was read from
-      const int Jodd = (pl * rpp[a] + j0 - 1 + rr) & 1;
+      const int Jodd = ((pl * rpp[a] + j0 - 1 + rr) & 1) ^ (flip & rpp[a] & 1);
       return G::off(a) + (rr & 1) * G::sub(a) + (rr >> 1) * W + (leadE ^ Jodd);
     }
     return G::off(a) + rr * W + leadE;
   };
+  // parity flips of the node plane `pl` (ex, ey) / the cell layer `pl` (ez) when it comes from a neighbour
+  // (kept to two compares per stage: the stages q whose plane / layer is a halo one, and their flips, are fixed per block)
+  const int q_lo = PEER && hal.lo_plane >= 0 ? hal.lo_plane - 1 - jfirst : -1000000;
+  const int q_hi = PEER && hal.hi_plane >= 0 ? hal.hi_plane - 1 - jfirst : -1000000;
+  const int q_ll = PEER && hal.lo_layer >= 0 ? hal.lo_layer - jfirst : -1000000;
+  const int f_lo = PEER ? (hal.lo_plane ^ hal.lo_peer_plane) & 1 : 0, f_hi = PEER ? (hal.hi_plane ^ hal.hi_peer_plane) & 1 : 0;
+  const int f_ll = PEER ? (hal.lo_layer ^ hal.lo_peer_layer) & 1 : 0;
+  auto flip_plane_q = [&](int q) -> int { return !PEER ? 0 : q == q_lo ? f_lo : q == q_hi ? f_hi : 0; };
+  auto flip_layer_q = [&](int q) -> int { return !PEER ? 0 : q == q_ll ? f_ll : 0; };
 
   const long long nEx = (long long)nx * nNy * nNz, nEy = (long long)nNx * ny * nNz;
   const long long pEx = (long long)nx * nNy, pEy = (long long)nNx * ny, pEz = (long long)nNx * nNy;
@@ -303,17 +326,18 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
       for (int u = 0; u < S; ++u) {
         const int q = qb + u;
         if (q >= nq) break;
-        const int ku = PEER ? jfirst + q : jfirst + u;   // S is even: the plane parity of slot u is the same in every ring cycle
+        const int ku = jfirst + u;   // S is even: the plane parity of slot u is the same in every ring cycle
+        const int fP = flip_plane_q(q), fL = flip_layer_q(q);
         mbar_wait(&full[u], par);
         const double *T = tcol + u * G::STAGE;
-        const double ex1 = T[rowoff(0, 0, ku + 1)], ex1u = T[rowoff(0, 1, ku + 1)];
-        const double *tEY = T + rowoff(1, 0, ku + 1);
+        const double ex1 = T[rowoff(0, 0, ku + 1, fP)], ex1u = T[rowoff(0, 1, ku + 1, fP)];
+        const double *tEY = T + rowoff(1, 0, ku + 1, fP);
         const double ey1 = tEY[0], ey1r = tEY[1];
         if (q >= 1) {
-          const double *tMU = T + rowoff(3, 0, ku);
+          const double *tMU = T + rowoff(3, 0, ku, 0);
           const int t = q - 1;
           const double hz = s_hz[t], rzh = s_rzh[t];
-          const double ez0 = T[rowoff(2, 0, ku)], ezu = T[rowoff(2, 1, ku)];
+          const double ez0 = T[rowoff(2, 0, ku, fL)], ezu = T[rowoff(2, 1, ku, fL)];
           const double mu0 = tMU[0], mul = tMU[-1];
           const double circx = hz * (ezu - ez0) - hy * (ey1 - ey0);
           const double circz = hy * (ey0r - ey0) - hx * (ex0u - ex0);
@@ -366,19 +390,20 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
     for (int u = 0; u < S; ++u) {
       const int q = qb + u;
       if (q >= nq) break;
-      const int ku = PEER ? jfirst + q : jfirst + u;   // (peer-read halos: the real plane, its source may differ)
+      const int ku = jfirst + u;
+      const int fP = flip_plane_q(q), fL = flip_layer_q(q);
       mbar_wait(&full[u], par);
       const double *T = tcol + u * G::STAGE;
-      const double ex1 = T[rowoff(0, r + 1, ku + 1)], ex1u = T[rowoff(0, r + 2, ku + 1)];
-      const double *tEY = T + rowoff(1, r + 1, ku + 1);
+      const double ex1 = T[rowoff(0, r + 1, ku + 1, fP)], ex1u = T[rowoff(0, r + 2, ku + 1, fP)];
+      const double *tEY = T + rowoff(1, r + 1, ku + 1, fP);
       const double ey1 = tEY[0], ey1r = tEY[1];
       if (q >= 1) {
         const int k = jfirst + q;          // this step works on plane k / layer k
-        const double *tEZ = T + rowoff(2, r + 1, ku);
-        const double *tMU = T + rowoff(3, r + 1, ku);
+        const double *tEZ = T + rowoff(2, r + 1, ku, fL);
+        const double *tMU = T + rowoff(3, r + 1, ku, 0);
         const int t = q - 1;
         const double hz = s_hz[t], rzh = s_rzh[t];
-        const double ez0 = tEZ[0], ezu = T[rowoff(2, r + 2, ku)];
+        const double ez0 = tEZ[0], ezu = T[rowoff(2, r + 2, ku, fL)];
         const double mu0 = tMU[0], mul = tMU[-1];
         const double circx = hz * (ezu - ez0) - hy * (ey1 - ey0);
         const double circz = hy * (ey0r - ey0) - hx * (ex0u - ex0);
@@ -395,8 +420,8 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
         }
         const unsigned xpar = (u == 0) ? (par ^ 1u) : par;   // slot 0 carries no fluxes in the first ring cycle
         const bool xok = mbar_test_wait(xr_bar + u * (G::XROWS * XS), xpar);   // probe now, consume after the y-face work
-        const double ezr = tEZ[1], mud = T[rowoff(3, r, ku)];
-        const double sg0 = T[rowoff(4, r + 1, ku)], sgd = T[rowoff(4, r, ku)];
+        const double ezr = tEZ[1], mud = T[rowoff(3, r, ku, 0)];
+        const double sg0 = T[rowoff(4, r + 1, ku, 0)], sgd = T[rowoff(4, r, ku, 0)];
         const double circy = hx * (ex1 - ex0) - hz * (ezr - ez0);
         const double gfy = ((hyd * mud + hy * mu0) * (rx * rzh)) * circy;
         const double gfzl = __shfl_up_sync(0xffffffffu, gfz, 1);
