@@ -61,7 +61,14 @@ constexpr int M3_MAXCHUNK = 160;  // max z-planes per block (size of the hz tabl
 
 // compile-time geometry: XS strips x R rows per block, PARX = nx & 1, NSLOT ring slots
 template <int XS, int R, int PARX, int NSLOT> struct Mx3 {
-  static constexpr int NCONS = XS * R, NHALO = XS, NWARPS = NCONS + NHALO + 1, NT = NWARPS * 32;
+  // NPW producer warps share the copies of a stage (one elected lane each).  Measured at 1024^3 under the power cap: two
+  // producers 12.16 ms, one 12.08 ms -- the ~225 instructions one lane spends per stage are not what limits the ring, so
+  // one producer warp it is (what did cost 12-20 % in the peer-read variant was selecting the tensor map at run time in
+  // EVERY stage; see the producer loop)
+  static constexpr int NPW = 1;
+  static constexpr int NCONS = XS * R, NHALO = XS, NWARPS = NCONS + NHALO + NPW, NT = NWARPS * 32;
+  // producer 0 copies the arrays of mask0, producer 1 the others (balanced in boxes: odd-pitch arrays take two)
+  static constexpr bool mine(int a, int pw) { return NPW == 1 || (PARX ? (a <= 2) : (a == 1 || a == 2)) == (pw == 0); }
   static constexpr int RN = R + 2, RC = R + 1;          // staged node rows j0-1 .. j0+R, cell rows j0-1 .. j0+R-1
   // box width: the box starts at the even column <= Xb-1 (the TMA unit wants 16-byte aligned inner coordinates: an odd
   // start raises an illegal-instruction fault, tools/tma_probe) and must reach column Xb+XS*31
@@ -109,7 +116,7 @@ struct M3Halo {
 };
 
 template <int XS, int R, int PARX, int NSLOT, int MINB, bool PEER>
-__global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
+__global__ void __launch_bounds__((XS *R + XS + Mx3<XS, R, PARX, NSLOT>::NPW) * 32, MINB)
     k_maxwell_tmap(TM m, const __grid_constant__ M3Maps maps, double *__restrict__ y, int kchunk, int k_begin, int k_end,
                    int nzb0, int k_begin2, int k_end2, int l2hint, M3Halo hal) {
   typedef Mx3<XS, R, PARX, NSLOT> G;
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
   }
   if (tid == 0) {
     for (int q = 0; q < S; ++q) {
-      mbar_init(&full[q], 1);
+      mbar_init(&full[q], G::NPW);
       mbar_init(&empty[q], G::NCONS + G::NHALO);
     }
     for (int q = 0; q < S * G::XROWS * XS; ++q) mbar_init(&xready[q], 1);
@@ -191,11 +198,13 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
     return 0;
   };
 
-  if (warp == G::NWARPS - 1) {
-    // ================= producer warp: one elected lane, <= 7 box copies per stage =================
+  if (warp >= G::NCONS + G::NHALO) {
+    // ================= producer warp(s): one elected lane each, <= 7 box copies per stage =================
+    const int pw = warp - (G::NCONS + G::NHALO);
     if (lane == 0) {
 #pragma unroll
       for (int a = 0; a < 5; ++a) {
+        if (!G::mine(a, pw)) continue;
         tmap_prefetch(&maps.m[a]);
         if (G::odd(a)) tmap_prefetch(&maps.o[a]);
       }
@@ -222,7 +231,7 @@ __global__ void __launch_bounds__((XS *R + XS + 1) * 32, MINB)
 #pragma unroll
         for (int a = 0; a < 5; ++a) {
           const int pl = jfirst + q + (a < 2 ? 1 : 0);
-          on[a] = pl >= 0 && pl < npl[a] && !(q == 0 && a >= 2);   // ez / mui / sigma of the first stage are never read
+          on[a] = G::mine(a, pw) && pl >= 0 && pl < npl[a] && !(q == 0 && a >= 2);   // ez / mui / sigma of the first stage are never read
           total += on[a] ? G::bytes(a) : 0u;
         }
         mbar_arrive_expect_tx(&full[slot], total);
