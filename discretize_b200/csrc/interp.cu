@@ -16,8 +16,8 @@ constexpr int IT = 128;  // threads (= points) per tile
 #endif
 
 struct AxisHit {
-  i64 i1, i2;
-  double w1, w2;
+  int i1, i2;        // positions on one axis: 32-bit (an axis has far fewer than 2^31 entries; 64-bit index arithmetic made
+  double w1, w2;     // the locate kernels issue-bound: 414 instructions per point)
 };
 
 // _bisect_right + _get_inds_ws (interputils_cython.pyx:42-67).
@@ -25,13 +25,14 @@ struct AxisHit {
 // is bit-identical to the reference's bisection.  `inv_mean` = (n-1)/(a[n-1]-a[0]) gives a guess that is
 // exact or off by a few entries on smooth meshes; a short walk fixes it, and a bisection over the
 // remaining bracket handles arbitrary (strongly graded) arrays.
-__device__ __forceinline__ AxisHit locate_axis(const double *__restrict__ a, i64 n, double xp, double inv_mean) {
-  i64 lo = 0, hi = n;
+__device__ __forceinline__ AxisHit locate_axis(const double *__restrict__ a, i64 n64, double xp, double inv_mean) {
+  const int n = (int)n64;
+  int lo = 0, hi = n;
   if (n >= 8 && xp == xp) {
     double g = (xp - a[0]) * inv_mean;
     g = fmin(fmax(g, -1.0), (double)n);
-    i64 r = (i64)g + 1;                       // guess for bisect_right
-    r = max(min(r, n), (i64)0);
+    int r = (int)g + 1;                       // guess for bisect_right
+    r = max(min(r, n), 0);
     // walk at most 4 entries towards the answer, then keep the tight bracket for the bisection
     int steps = 0;
     while (steps < 4) {
@@ -47,13 +48,13 @@ __device__ __forceinline__ AxisHit locate_axis(const double *__restrict__ a, i64
     }
   }
   while (lo < hi) {
-    const i64 mid = (lo + hi) / 2;
+    const int mid = (lo + hi) / 2;
     if (xp < a[mid]) hi = mid;
     else lo = mid + 1;
   }
   AxisHit h;
-  h.i2 = max(min(lo, n - 1), (i64)0);
-  h.i1 = max(min(lo - 1, n - 1), (i64)0);
+  h.i2 = max(min(lo, n - 1), 0);
+  h.i1 = max(min(lo - 1, n - 1), 0);
   if (h.i1 == h.i2) h.w1 = 0.5;
   else h.w1 = (a[h.i2] - xp) / (a[h.i2] - a[h.i1]);
   h.w2 = 1 - h.w1;
@@ -95,7 +96,7 @@ __device__ __forceinline__ void entries(const AxisHit &hx, const AxisHit &hy, co
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const bool x2 = (e >> 1) & 1, y2 = e & 1, z2 = (e >> 2) & 1;
-    const i64 ix = x2 ? hx.i2 : hx.i1, iy = y2 ? hy.i2 : hy.i1, iz = z2 ? hz.i2 : hz.i1;
+    const i64 ix = x2 ? hx.i2 : hx.i1, iy = y2 ? hy.i2 : hy.i1, iz = z2 ? hz.i2 : hz.i1;   // 64-bit from here on
     col[e] = col_offset + ix + nx * (iy + ny * iz);
     w[e] = ((x2 ? hx.w2 : hx.w1) * (y2 ? hy.w2 : hy.w1)) * (z2 ? hz.w2 : hz.w1);
   }
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(256) k_interp_locate_c(Axes g, const double *_
     const AxisHit hx = locate_axis(a.tx, a.ntx, __ldg(pts + 3 * p), a.ix);
     const AxisHit hy = locate_axis(a.ty, a.nty, __ldg(pts + 3 * p + 1), a.iy);
     const AxisHit hz = locate_axis(a.tz, a.ntz, __ldg(pts + 3 * p + 2), a.iz);
-    base[p] = (IDX)(col_offset + hx.i1 + a.ntx * (hy.i1 + a.nty * hz.i1));
+    base[p] = (IDX)(col_offset + hx.i1 + a.ntx * (hy.i1 + a.nty * (i64)hz.i1));
     wx[p] = compact_weight(hx);
     wy[p] = compact_weight(hy);
     wz[p] = compact_weight(hz);
