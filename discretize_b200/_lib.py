@@ -68,6 +68,7 @@ SIGNATURES = {
     "dzb_tm_maxwell_range": [_MP, _P, _P, _P, _P, _L, _L, _P],
     "dzb_tm_maxwell_range2": [_MP, _P, _P, _P, _P, _L, _L, _L, _L, _P],
     "dzb_tm_maxwell_cplx": [_MP, _P, _P, _D, _D, _P, _P, _P],
+    "dzb_tm_dc_nodal_dot": [_MP, _P, _P, _P, _P, _L, _P, _P],
     "dzb_tm_dc_nodal_range_peer": [_MP, _P, _P, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _P, _P, _L, _L, _P],
     "dzb_tm_maxwell_range_peer_sync": [_MP, _P, _P, _P, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _P, _P, _L, _L, _P],
     "dzb_tm_maxwell_range_peer": [_MP, _P, _P, _P, _P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _P],

@@ -236,10 +236,11 @@ struct DcHalo {
   unsigned *sync, *lo_signal, *hi_signal;
 };
 
-template <int RY, int NWC, int PARX, bool PEER>
+template <int RY, int NWC, int PARX, bool PEER, bool DOT>
 __global__ void __launch_bounds__((NWC + 1) * 32, 1)
     k_dc_nodal_ring(TM m, const double *__restrict__ sigma, const double *__restrict__ phi_all, double *__restrict__ y_all,
-                    int kchunk, int nwc, int k_begin, int k_end, int nrhs, long long ldx, DcHalo hal) {
+                    int kchunk, int nwc, int k_begin, int k_end, int nrhs, long long ldx, DcHalo hal,
+                    double *__restrict__ dotp) {
   typedef DcRing<RY, NWC, PARX> G;
   // multi-RHS launch: blockIdx.x = x-block * nrhs + rhs -- the right-hand side is the FASTEST index of the launch order, so
   // that the nrhs blocks that stage the same sigma tile run side by side and all but the first find it in L2 (sigma is
@@ -394,6 +395,7 @@ __global__ void __launch_bounds__((NWC + 1) * 32, 1)
     if (writer && (j0 + r) < nNy) wmask |= 1u << r;
 
   double Ap[RY], Bp[RY + 1], fzp[RY];
+  double dacc = 0.0;   // dotp: this warp's part of phi . (A phi), the p.Ap of a conjugate-gradient iteration
 #pragma unroll
   for (int r = 0; r < RY; ++r) Ap[r] = fzp[r] = 0.0;
 #pragma unroll
@@ -455,7 +457,10 @@ __global__ void __launch_bounds__((NWC + 1) * 32, 1)
         const double fz = (qz * (a + al)) * (ph1 - P0[r + 1]);
         const double out = (fxl - fx) + (fy[r] - fy[r + 1]) + (fzp[r] - fz);
         fzp[r] = fz;
-        if ((wm >> r) & 1u) py[r * nNx] = out;
+        if ((wm >> r) & 1u) {
+          py[r * nNx] = out;
+          if (DOT) dacc += out * P0[r + 1];
+        }
       }
       py += pstride;
       // the plane of stage j-1 is dead now: hand its slot back to the producer
@@ -463,6 +468,28 @@ __global__ void __launch_bounds__((NWC + 1) * 32, 1)
       if (lane == 0) mbar_arrive(&empty[slot_prev]);
     }
   }
+  if (DOT) {   // one partial per (block, consumer warp), summed in index order by k_sum_partials: deterministic
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
+    if (lane == 0) {
+      const long long b = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      dotp[b * nwc + warp] = dacc;
+    }
+  }
+}
+
+// out[0] = sum of partials[0 .. n) in index order (one block)
+__global__ void __launch_bounds__(256) k_sum_partials(long long n, const double *__restrict__ partials, double *out) {
+  __shared__ double sm[256];
+  double v = 0.0;
+  for (long long t = threadIdx.x; t < n; t += 256) v += partials[t];
+  sm[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sm[0];
 }
 
 static int g_dc_ry = 4;
@@ -483,11 +510,15 @@ extern "C" void dzb_tune_dc_variant(int variant) { g_dc_variant = variant; }
 template <int RY, int NWC, int PARX, bool PEER = false>
 static int launch_dc_ring_t(const TM &m, const double *sigma, const double *phi, double *y, int kchunk, int xblocks,
                             int nwc, int k_begin, int k_end, cudaStream_t s, int nrhs = 1, long long ldx = 0,
-                            const DcHalo *hal = nullptr) {
+                            const DcHalo *hal = nullptr, double *dotp = nullptr, long long dot_cap = 0,
+                            long long *n_partials = nullptr) {
   typedef DcRing<RY, NWC, PARX> G;
   // the attribute is per device (a process may drive several GPUs); setting it is cheap, so no process-wide flag
-  if (cudaFuncSetAttribute(k_dc_nodal_ring<RY, NWC, PARX, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (cudaFuncSetAttribute(k_dc_nodal_ring<RY, NWC, PARX, PEER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)G::SMEM) != cudaSuccess)
+    return -1;
+  if (!PEER && cudaFuncSetAttribute(k_dc_nodal_ring<RY, NWC, PARX, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)G::SMEM) != cudaSuccess)
     return -1;
   const DcHalo none{-1, -1, 0, 0, 0, 0, 0, 0, nullptr, nullptr, nullptr};
   const int nNy = (int)m.ny + 1;
@@ -515,15 +546,26 @@ static int launch_dc_ring_t(const TM &m, const double *sigma, const double *phi,
     kchunk = best_kc;
   }
   dim3 grid((unsigned)xblocks * nrhs, (unsigned)((nNy + RY - 1) / RY), (unsigned)((k_end - k_begin + kchunk - 1) / kchunk));
-  k_dc_nodal_ring<RY, NWC, PARX, PEER><<<grid, dim3((nwc + 1) * 32), G::SMEM, s>>>(m, sigma, phi, y, kchunk, nwc, k_begin,
-                                                                                 k_end, nrhs, ldx, hal ? *hal : none);
+  if (dotp) {
+    const long long need = (long long)grid.x * grid.y * grid.z * nwc;
+    if (need > dot_cap) return -3;          // workspace too small: the caller takes a separate dot kernel
+    if (n_partials) *n_partials = need;
+  }
+  if (dotp && !PEER)   // the variant that also accumulates phi . y (kept apart: it costs the plain kernel 64 bytes of spills)
+    k_dc_nodal_ring<RY, NWC, PARX, false, true><<<grid, dim3((nwc + 1) * 32), G::SMEM, s>>>(m, sigma, phi, y, kchunk, nwc,
+                                                                                          k_begin, k_end, nrhs, ldx, none, dotp);
+  else
+    k_dc_nodal_ring<RY, NWC, PARX, PEER, false><<<grid, dim3((nwc + 1) * 32), G::SMEM, s>>>(m, sigma, phi, y, kchunk, nwc,
+                                                                                          k_begin, k_end, nrhs, ldx,
+                                                                                          hal ? *hal : none, nullptr);
   return 0;
 }
 
 constexpr int DC_NWC_BIG = 18, DC_NWC_SMALL = 6;
 
 static int launch_dc_ring(const TM &m, const double *sigma, const double *phi, double *y, int kchunk, int k_begin,
-                          int k_end, cudaStream_t s, int nrhs = 1, long long ldx = 0, const DcHalo *hal = nullptr) {
+                          int k_end, cudaStream_t s, int nrhs = 1, long long ldx = 0, const DcHalo *hal = nullptr,
+                          double *dotp = nullptr, long long dot_cap = 0, long long *n_partials = nullptr) {
   const int nNx = (int)m.nx + 1;
   const int strips = (nNx + DC_XOUT - 1) / DC_XOUT;
   const bool small = strips <= DC_NWC_SMALL;
@@ -540,10 +582,10 @@ static int launch_dc_ring(const TM &m, const double *sigma, const double *phi, d
                 : launch_dc_ring_t<4, DC_NWC_BIG, 0, true>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, 1, 0, hal);
   }
   if (small)
-    return parx ? launch_dc_ring_t<4, DC_NWC_SMALL, 1>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, nrhs, ldx)
-                : launch_dc_ring_t<4, DC_NWC_SMALL, 0>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, nrhs, ldx);
-  return parx ? launch_dc_ring_t<4, DC_NWC_BIG, 1>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, nrhs, ldx)
-              : launch_dc_ring_t<4, DC_NWC_BIG, 0>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, nrhs, ldx);
+    return parx ? launch_dc_ring_t<4, DC_NWC_SMALL, 1>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, nrhs, ldx, nullptr, dotp, dot_cap, n_partials)
+                : launch_dc_ring_t<4, DC_NWC_SMALL, 0>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, nrhs, ldx, nullptr, dotp, dot_cap, n_partials);
+  return parx ? launch_dc_ring_t<4, DC_NWC_BIG, 1>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, nrhs, ldx, nullptr, dotp, dot_cap, n_partials)
+              : launch_dc_ring_t<4, DC_NWC_BIG, 0>(m, sigma, phi, y, kchunk, xblocks, nwc, k_begin, k_end, s, nrhs, ldx, nullptr, dotp, dot_cap, n_partials);
 }
 
 extern "C" int dzb_tm_dc_nodal_range(const DzbTensorMesh *mm, const double *sigma, const double *phi, double *y,
@@ -650,6 +692,29 @@ extern "C" int dzb_tm_dc_nodal_multi(const DzbTensorMesh *mm, const double *sigm
     if (rc) return rc;
   }
   return 0;
+}
+
+// y = A phi and, in the same launch, dot[0] = phi . y (the p.Ap of a conjugate-gradient iteration: the consumers hold both
+// values of every node they write, so the separate 16 B / node dot kernel goes away).  Partials per (block, consumer warp)
+// go to `workspace` (capacity in doubles) and are summed in index order by a one-block kernel: deterministic.  Returns -2
+// where the ring kernel does not apply or the workspace is too small (use dzb_tm_dc_nodal + a dot kernel there).
+extern "C" int dzb_tm_dc_nodal_dot(const DzbTensorMesh *mm, const double *sigma, const double *phi, double *y,
+                                   double *workspace, int64_t workspace_doubles, double *dot, void *stream) {
+  if (!mm || mm->nx <= 0 || mm->ny <= 0 || mm->nz <= 0) {
+    set_error("dzb_tm_dc_nodal_dot: invalid mesh");
+    return -1;
+  }
+  TM m(*mm);
+  const i64 nNx = m.nx + 1, nNy = m.ny + 1, nNz = m.nz + 1;
+  if (!(g_dc_variant == 1 && m.ny >= 2 && m.nN() < ((i64)1 << 31) && nNx * nNy < ((i64)1 << 31)) || !workspace) return -2;
+  long long np = 0;
+  if (launch_dc_ring(m, sigma, phi, y, g_dc_kchunk, 0, (int)nNz, (cudaStream_t)stream, 1, 0, nullptr, workspace,
+                     (long long)workspace_doubles, &np) != 0) {
+    cudaGetLastError();
+    return -2;
+  }
+  k_sum_partials<<<1, 256, 0, (cudaStream_t)stream>>>(np, workspace, dot);
+  return check_launch("dzb_tm_dc_nodal_dot");
 }
 
 extern "C" int dzb_tm_dc_nodal(const DzbTensorMesh *mm, const double *sigma, const double *phi, double *y,

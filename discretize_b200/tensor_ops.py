@@ -396,6 +396,22 @@ class DCNodalOperator(Operator):
         check(load().dzb_tm_dc_nodal_range(C.byref(self.mesh.device_mesh()), ptr(self.sigma), ptr(x), ptr(out),
                                            int(k_begin), int(k_end), stream_ptr()), "dzb_tm_dc_nodal_range")
 
+    def apply_with_dot(self, x, out, dot):
+        """``out = A x`` and ``dot[0] = x . out`` in one pass (``dzb_tm_dc_nodal_dot``): the p.Ap of a CG iteration without
+        a second sweep over p and Ap.  ``dot``: a one-element CUDA tensor (or a view of one).  Returns False where the
+        fused form does not apply (the caller then uses ``apply_device`` + a dot kernel)."""
+        ws = getattr(self, "_dot_ws", None)
+        if ws is None:
+            nx, ny, nz = self.mesh.shape_cells
+            blocks = ((nx + 1 + 539) // 540) * ((ny + 1 + 3) // 4) * 256       # z-chunks are at most 256
+            ws = self._dot_ws = torch.empty(min(blocks * 18, 1 << 24), dtype=torch.float64, device=cuda_device())
+        rc = load().dzb_tm_dc_nodal_dot(C.byref(self.mesh.device_mesh()), ptr(self.sigma), ptr(x), ptr(out), ptr(ws),
+                                        int(ws.numel()), ptr(dot), stream_ptr())
+        if rc == -2:
+            return False
+        check(rc, "dzb_tm_dc_nodal_dot")
+        return True
+
     def apply_planes_peer(self, x, out, k_begin, k_end, lower=None, upper=None, sync=None):
         """Node planes [k_begin, k_end) of a z-slab whose halo planes are read from the neighbours' memory by the kernel.
         ``lower`` = (device pointer of the lower neighbour's local nodal vector, its cell layers, local halo plane, plane

@@ -173,6 +173,13 @@ int dzb_tm_dc_nodal_range_peer(const DzbTensorMesh *m, const double *sigma, cons
  * side: the nrhs blocks that stage the same tile are scheduled side by side and share it through L2. */
 int dzb_tm_dc_nodal_multi(const DzbTensorMesh *m, const double *sigma, const double *phi, double *y, int nrhs, int64_t ldx,
                           void *stream);
+/* y = A phi and dot[0] = phi . y in ONE pass over the data (the p.Ap of a conjugate-gradient iteration): the
+ * kernel's consumers hold phi and y of every node they write.  workspace: scratch for the per-(block, warp) partials,
+ * workspace_doubles >= blocks x consumer warps of the launch (2^20 doubles cover 512^3); the partials are summed in index
+ * order (deterministic).  dot: one device double.  Returns -2 where the staged-ring kernel does not apply or the
+ * workspace is too small (then: dzb_tm_dc_nodal + dzb_dot). */
+int dzb_tm_dc_nodal_dot(const DzbTensorMesh *m, const double *sigma, const double *phi, double *y, double *workspace,
+                        int64_t workspace_doubles, double *dot, void *stream);
 /* Same, writing only the node planes k_begin <= k < k_end of y (0 <= k <= nz).  This is the
  * building block of the z-slab decomposition: a rank applies it to its local sub-mesh (its cell
  * layers plus one halo layer / node plane per neighbour) for the planes it owns, interior

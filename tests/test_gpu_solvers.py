@@ -140,3 +140,28 @@ def test_pcg_survives_convergence_inside_a_blind_window():
         xs = x.cpu().numpy()
         assert np.isfinite(xs).all() and info.converged
         assert_close_vec(xs, b / d)
+
+
+@pytest.mark.parametrize("shape", [(33, 20, 17), (70, 41, 64), (600, 9, 130)])
+def test_dc_apply_with_fused_dot(shape):
+    """K8 with the p.Ap of a CG iteration accumulated by its consumers: same y as the plain kernel (bitwise) and the same
+    dot product as a separate reduction (to rounding), deterministic from run to run."""
+    import discretize_b200 as dz
+
+    rng = np.random.default_rng(8)
+    mesh = dz.TensorMesh([rng.random(n) + 0.5 for n in shape])
+    sigma = np.exp(rng.standard_normal(mesh.nC))
+    G = mesh.nodal_gradient
+    A = G.T @ mesh.get_edge_inner_product(sigma) @ G
+    x = torch.as_tensor(rng.standard_normal(mesh.nN), device="cuda")
+    y0 = A.apply_device(x)
+    y1 = torch.full_like(y0, float("nan"))
+    dots = torch.zeros(3, dtype=torch.float64, device="cuda")
+    assert A.apply_with_dot(x, y1, dots[1:2])
+    assert torch.equal(y0, y1)
+    want = float(torch.dot(x, y0))
+    assert abs(float(dots[1]) - want) <= 1e-12 * float(torch.linalg.vector_norm(x) * torch.linalg.vector_norm(y0))
+    assert float(dots[0]) == 0.0 and float(dots[2]) == 0.0
+    again = torch.zeros(1, dtype=torch.float64, device="cuda")
+    assert A.apply_with_dot(x, y1, again)
+    assert float(again[0]) == float(dots[1])

@@ -199,6 +199,13 @@ def test_tree_spmv_layouts_agree(gold, name):
             out = torch.full((c2.shape[0],), float("nan"), dtype=torch.float64, device="cuda")
             c2.apply(torch.from_numpy(vec).cuda(), out)
             assert_close_vec(out.cpu().numpy(), r)
+            # hybrid layout (ELL of the common width + overflow rows), geometry by row / by column kept in arrays too
+            c3 = CodedCsr(geoms, parts, csr.shape, geom_by_col=tr, fold=fold)
+            if c3.hyb_K > 0:
+                c3.use_layout("hyb")
+                out = torch.full((c3.shape[0],), float("nan"), dtype=torch.float64, device="cuda")
+                c3.apply(torch.from_numpy(vec).cuda(), out)
+                assert_close_vec(out.cpu().numpy(), r)
 
 
 @pytest.mark.parametrize("tag", ["a", "b"])
