@@ -256,3 +256,46 @@ def test_geometry_folds_into_the_code_table_on_uniform_base_meshes():
     geoms, parts = graded._host_parts("face_divergence")
     g2, p2 = fold_geometry(geoms, parts, False)
     assert g2 is geoms and p2 is parts
+
+
+def test_point_location_by_keys_equals_the_descent():
+    """The device kernel dzb_tree_locate replaces the reference's level-by-level descent (tree.cpp:758-766, 1499-1516) by two
+    bisections per axis, a Morton key and a search in the sorted leaf keys.  The same algorithm in numpy against the
+    descent (`TreeMesh._containing_cells`, itself checked against the reference fixture): random points, points exactly on
+    nodes and cell centres, points outside, on cubic and non-cubic (several roots) trees."""
+    from discretize_b200.octree import _spread
+
+    rng = np.random.default_rng(33)
+    meshes = []
+    m = TreeMesh([16, 16, 16])
+    m.refine_points(rng.random((12, 3)), -1, finalize=True)
+    meshes.append(m)
+    m = TreeMesh([rng.random(32) + 0.5, rng.random(8) + 0.5, rng.random(16) + 0.5], origin=[-2.0, 0.5, 3.0])
+    m.refine_points(rng.random((30, 3)) * np.array([20.0, 5.0, 10.0]) + np.array([-2.0, 0.5, 3.0]), -1, finalize=True)
+    meshes.append(m)
+    for m in meshes:
+        tr = m._tree
+        lo = np.array([x[0] for x in m._xs])
+        hi = np.array([x[-1] for x in m._xs])
+        pts = lo + (rng.random((6000, 3)) * 1.4 - 0.2) * (hi - lo)
+        for d in range(3):
+            pts[:2000, d] = m._xs[d][rng.integers(0, m._xs[d].size, 2000)]
+        want = m._containing_cells(pts)
+        leaf_lo, _ = tr.leaves()
+        leaf_keys = tr.keys(leaf_lo)
+        assert (np.diff(leaf_keys) > 0).all()
+        root_id = np.zeros(pts.shape[0], dtype=np.int64)
+        code = np.zeros(pts.shape[0], dtype=np.int64)
+        stride = 1
+        for d in range(3):
+            nodes = m._xs[d][::2]
+            root = np.searchsorted(nodes[tr.rw * np.arange(1, tr.roots[d])], pts[:, d], side="right")
+            fine = np.empty(pts.shape[0], dtype=np.int64)
+            for r in range(tr.roots[d]):
+                sel = root == r
+                fine[sel] = np.searchsorted(nodes[tr.rw * r + 1:tr.rw * (r + 1)], pts[sel, d], side="left")
+            root_id += stride * root
+            stride *= tr.roots[d]
+            code |= _spread(fine, tr.nbits, 3) << d
+        got = np.searchsorted(leaf_keys, root_id * np.int64(tr.rw) ** 3 + code, side="right") - 1
+        assert np.array_equal(got, want)
